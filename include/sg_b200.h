@@ -1,0 +1,259 @@
+/*
+ * sg_b200.h -- C ABI of the B200-native batched rollout engine for Scenario Gym.
+ *
+ * The reference (driskai/scenario_gym v0.3.1) is pure Python and has no FFI; the
+ * "plugin API" is Python subclassing.  This header is the boundary a maintainer
+ * would bind (ctypes stub in INTEGRATION.md) to replace the reference's per-tick
+ * path.  Each entry point cites the reference code it replaces (paths relative
+ * to the reference root).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types.
+ *   - every array pointer inside SgScene / SgState / SgInputs given to the sg_*
+ *     entry points is CALLER-OWNED DEVICE memory (e.g. torch allocations); the
+ *     library never frees it.  The *_host entry points take HOST pointers.
+ *   - layout is structure-of-arrays: a "plane" is [N*M] (N scenarios x M entity
+ *     slots, scenario-major), multi-component fields are [C][N*M].
+ *   - all floating point is IEEE fp64 and follows the reference's operation order
+ *     (no FMA contraction where the reference has none).
+ *   - return code: 0 ok, negative = error; text via sg_last_error().
+ *   - stream-ordered and non-blocking unless stated; `stream` is a cudaStream_t
+ *     passed as void* (NULL = legacy default stream).
+ *   - no global mutable state except the last-error string (thread-local).
+ *
+ * The CPU oracle (oracle/sg_oracle.c, test infrastructure) exports the same
+ * signatures with the prefix sgo_ and host pointers, so tests drive both through
+ * identical code.
+ */
+#ifndef SG_B200_H
+#define SG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_ABI_VERSION 3
+
+/* entity slot kinds (who produces the slot's next pose each tick) */
+enum SgKind {
+  SG_KIND_EMPTY = 0,        /* padding slot                                               */
+  SG_KIND_REPLAY = 1,       /* no agent: BatchReplayEntity, entity/batch.py:34-53,55-128   */
+  SG_KIND_AGENT_REPLAY = 2, /* ReplayTrajectoryAgent (default ego), agent.py:118-128       */
+  SG_KIND_VEHICLE = 3,      /* agent with VehicleController, controller.py:57-140          */
+  SG_KIND_PEDESTRIAN = 4,   /* PedestrianAgent + SocialForce, pedestrian/                  */
+  SG_KIND_HOST = 5          /* pose supplied by a host-side (Python) agent every tick      */
+};
+
+/* catalog type of the entity (collision.py:85, pedestrian/sensor.py:61) */
+enum SgEntityType { SG_ETYPE_VEHICLE = 0, SG_ETYPE_PEDESTRIAN = 1, SG_ETYPE_MISC = 2 };
+
+/* terminal conditions, state/state.py:397-408 (bit flags) */
+enum SgTerminal {
+  SG_TERM_MAX_LENGTH = 1,
+  SG_TERM_COLLISION = 2,
+  SG_TERM_EGO_COLLISION = 4
+};
+
+/* feature switches (bit flags in SgParams.features) */
+enum SgFeature {
+  SG_FEAT_COLLISIONS = 1,   /* state.collisions() + CollisionMetric, a8-a10 */
+  SG_FEAT_EGO_METRICS = 2,  /* EgoAvgSpeed/EgoMaxSpeed/EgoDistanceTravelled, a11 */
+  SG_FEAT_RSS = 4,          /* RSSDistances callback + RSS metric, a13-a14 */
+  SG_FEAT_COLL_MATRIX = 8   /* also write the per-tick pair matrix SgState.coll_mask */
+};
+
+/* record codes appended to RSSDistances.intersect[e] (rss/callback.py:168-228,304-338) */
+enum SgRssRecord {
+  SG_RSS_SAFE = 0,
+  SG_RSS_LATERAL = 1,
+  SG_RSS_LONGITUDINAL = 2,
+  SG_RSS_BOTH = 3,
+  SG_RSS_UNSAFE_LATERAL = 4,
+  SG_RSS_UNSAFE_LONGITUDINAL = 5,
+  SG_RSS_FOUND = 6,
+  SG_RSS_NONE = 255 /* entity absent this tick: nothing appended */
+};
+
+/* scalar parameters (gym / controller / behaviour constructor arguments) */
+typedef struct SgParams {
+  double timestep;         /* ScenarioGym(timestep), scenario_gym.py:31                   */
+  int32_t persist;         /* ScenarioGym(persist), scenario_gym.py:32                    */
+  int32_t terminal;        /* SgTerminal bits, scenario_gym.py:34-36                      */
+  int32_t features;        /* SgFeature bits                                              */
+  int32_t max_ticks;       /* safety bound for sg_rollout loops                           */
+  /* VehicleController(max_steer, max_accel, max_speed, allow_reverse) controller.py:64-98 */
+  double veh_max_steer;
+  double veh_max_accel;
+  double veh_max_speed;    /* NaN = None                                                  */
+  int32_t veh_allow_reverse;
+  int32_t _pad0;
+  /* PedestrianAgent / SocialForceParameters, pedestrian/agent.py:18-44, social_force.py:16-30 */
+  double ped_max_speed;          /* PedestrianController(max_speed=5.0)                   */
+  double ped_head_rot_angle;     /* PedestrianSensor(head_rot_angle=0.0)                  */
+  double ped_distance_threshold; /* PedestrianSensor(distance_threshold=1.0)              */
+  double sf_max_speed_factor;    /* BehaviourParameters.max_speed_factor = 1.3            */
+  double sf_bias_lon, sf_bias_lat; /* noise means (std must be 0 for parity)              */
+  double sf_sight_weight;        /* 0.5                                                   */
+  int32_t sf_sight_weight_use;   /* True                                                  */
+  int32_t _pad1;
+  double sf_sight_angle;         /* 200 (degrees)                                         */
+  double sf_relaxation_time;     /* 1.5                                                   */
+  double sf_ped_repulse_V;       /* 1.0                                                   */
+  double sf_ped_repulse_sigma;   /* 1.0                                                   */
+  double sf_ped_attract_C;       /* 0.0                                                   */
+  /* RSSParameters, metrics/rss/callback.py:21-31 */
+  double rss_response_time;      /* 0.6                                                   */
+  double rss_min_long_accel;     /* 1.2*9.81                                              */
+  double rss_max_long_accel;     /* 1.2*9.81                                              */
+  double rss_min_safe_clearance; /* 0.1                                                   */
+} SgParams;
+
+/* immutable description of N scenarios x M slots */
+typedef struct SgScene {
+  int32_t n_scenarios; /* N */
+  int32_t n_slots;     /* M, 1..1024 */
+  int64_t n_traj_rows; /* total control points in traj_rows */
+  int64_t n_union_rows;/* total rows in union_t            */
+  int64_t n_route_pts; /* total points in route_xy         */
+  const uint8_t* kind;   /* [N*M] SgKind */
+  const uint8_t* etype;  /* [N*M] SgEntityType */
+  const double* box;     /* [4][N*M]: width, length, center_x, center_y (catalog_entry.py:83-90) */
+  /* every slot's own trajectory (trajectory.py:34-96), CSR over slots; rows are
+     [t,x,y,z,h,p,r]; a slot with 1 row is "static" (entity/base.py:154-156) */
+  const int64_t* traj_off; /* [N*M+1] */
+  const double* traj_rows; /* [n_traj_rows][7] */
+  /* BatchReplayEntity union-knot table of scenario n (entity/batch.py:80-128):
+     knots union_t[union_off[n] .. union_off[n+1]) ; values union_x[row][6][M] */
+  const int64_t* union_off; /* [N+1] */
+  const double* union_t;    /* [n_union_rows] */
+  const double* union_x;    /* [n_union_rows][6][M] */
+  const double* t0;         /* [N] start time, scenario_gym.py:213-215 */
+  const double* length;     /* [N] scenario.length, scenario/scenario.py:88-91 */
+  const int32_t* ego_slot;  /* [N] slot of scenario.ego */
+  const int32_t* first_slot;/* [N] slot of scenario.entities[0] (ego_collision) */
+  /* pedestrians (pedestrian/agent.py:18-47) */
+  const double* ped_speed_desired; /* [N*M] */
+  const int64_t* route_off;        /* [N*M+1] */
+  const double* route_xy;          /* [n_route_pts][2] */
+} SgScene;
+
+/* one recorded ego-collision rising edge (metrics/collision.py:70-75) */
+typedef struct SgEvent {
+  int32_t scenario;
+  int32_t tick;   /* 1-based tick index at which it was recorded */
+  int32_t slot;   /* hazard slot */
+  int32_t _pad;
+  double t;       /* state.t */
+} SgEvent;
+
+/* mutable state + outputs; all arrays caller-owned */
+typedef struct SgState {
+  /* State buffers, state/state.py:90-96 */
+  double* pose;      /* [6][N*M] x,y,z,h,p,r */
+  double* vel;       /* [6][N*M] */
+  double* dist;      /* [N*M] */
+  uint8_t* present;  /* [N*M] entity in state.poses */
+  double* t;         /* [N] */
+  double* prev_t;    /* [N] */
+  int32_t* tick;     /* [N] ticks taken since reset */
+  uint8_t* done;     /* [N] state.is_done */
+  /* controller state */
+  double* speed;     /* [N*M] VehicleController.speed / PedestrianController.speed */
+  int32_t* goal_idx; /* [N*M] PedestrianAgent.goal_idx */
+  double* force;     /* [2][N*M] PedestrianAgent.force */
+  /* search cursors (implementation state; reset by sg_reset) */
+  int32_t* cur_own;   /* [N*M] */
+  int32_t* cur_union; /* [N] */
+  /* ego metrics, metrics/trajectory.py */
+  double* ego_avg_speed; /* [N] */
+  double* ego_avg_t;     /* [N] EgoAvgSpeed.t */
+  double* ego_max_speed; /* [N] */
+  double* ego_dist;      /* [N] */
+  /* collisions */
+  uint32_t* ego_hits;       /* [N][W] CollisionMetric.last_timestep as a bit set, W=ceil(M/32) */
+  uint32_t* coll_mask;      /* [N][M][W] pair matrix of the current tick (SG_FEAT_COLL_MATRIX) */
+  uint8_t* collided;        /* [N*M] slot was in any collision so far */
+  int32_t* first_coll_tick; /* [N] first tick with any collision, -1 = none */
+  int32_t* first_coll_pair; /* [N][2] smallest (i,j), i<j, colliding at that tick */
+  int64_t* n_pair_ticks;    /* [N] sum over ticks of #colliding unordered pairs */
+  SgEvent* events;          /* [event_cap] ego rising-edge events (unordered) */
+  int32_t* event_count;     /* [1] total events produced (may exceed event_cap) */
+  int32_t event_cap;
+  int32_t trace_cap;        /* ticks of trace storage, 0 = no trace */
+  /* RSS, metrics/rss/callback.py */
+  uint8_t* rss_state;   /* [N*M] bits0-1 last marker (0 none,1 lateral,2 longitudinal); bits2-3 found (0,1 unsafe_lateral,2 unsafe_longitudinal) */
+  uint8_t* rss_last;    /* [N*M] SgRssRecord appended this tick */
+  double* safe_dist;    /* [2][N*M] RSSDistances.safe_distances[e] = [lat, long] */
+  double* safe_ratio;   /* [2][N*M] RSSDistances.entity_safe_ratios[e] */
+  uint8_t* rss_flags;   /* [N] bit0: safe_longitudinal violated, bit1: safe_lateral violated */
+  /* optional trace (State._recorded_poses, state/state.py:227-228); index 0 = reset */
+  double* trace_pose;      /* [trace_cap][6][N*M] */
+  uint8_t* trace_present;  /* [trace_cap][N*M] */
+  double* trace_t;         /* [trace_cap][N] */
+} SgState;
+
+/* per-call inputs */
+typedef struct SgInputs {
+  /* VehicleAction(accel, steer) tables, action.py:66-83: actions[k][c][N*M] is consumed
+     by the k-th tick executed in this call (k = 0 .. n_action_ticks-1) */
+  const double* actions;
+  int32_t n_action_ticks;
+  int32_t _pad;
+  /* SG_KIND_HOST slots: pose returned by the host agent for the next tick */
+  const double* host_pose;      /* [6][N*M] or NULL */
+  const uint8_t* host_present;  /* [N*M] 0 = agent returned None */
+} SgInputs;
+
+int sg_abi_version(void);
+/* sizeof() of the ABI structs so bindings can verify their mirror: which = 0 SgParams,
+   1 SgScene, 2 SgState, 3 SgInputs, 4 SgEvent */
+int64_t sg_sizeof(int which);
+const char* sg_last_error(void);
+void sg_default_params(SgParams* p);
+
+/* State.reset(t0) + Metric.reset + Agent.reset: state/state.py:106-143,
+   scenario_gym.py:217-225, controller.py:100-103, metrics/trajectory.py:13-18 */
+int sg_reset(const SgScene* scene, const SgParams* params, SgState* state, int device, void* stream);
+
+/* n_ticks x ScenarioGym.step() fused on device (scenario_gym.py:227-254): agents /
+   batch replay -> State.step -> RSSDistances -> terminal check -> metrics.  Scenarios
+   that are done are skipped.  n_ticks < 0: run every scenario to is_done
+   (ScenarioGym.rollout, scenario_gym.py:256-267), bounded by params->max_ticks. */
+int sg_rollout(const SgScene* scene, const SgParams* params, SgState* state,
+               const SgInputs* inputs, int n_ticks, int device, void* stream);
+
+/* exact closed-set intersection test of oriented boxes (entity/base.py:100-138 +
+   utils.py:28-62), for unit tests: poses [n][3] = x,y,h ; boxes [n][4] ; out[n] */
+int sg_test_box_pairs(const double* pose_a, const double* box_a, const double* pose_b,
+                      const double* box_b, uint8_t* out, int64_t n, int device, void* stream);
+
+/* Host-buffer convenience used for the end-to-end number: copy the scene/initial
+   inputs H2D (pinned host memory recommended), reset, rollout to completion and copy
+   the per-scenario results back.  `dev_*` are device mirrors with the same shapes. */
+typedef struct SgHostResults {
+  double* ego_avg_speed;    /* [N] */
+  double* ego_max_speed;    /* [N] */
+  double* ego_dist;         /* [N] */
+  int32_t* first_coll_tick; /* [N] */
+  int32_t* first_coll_pair; /* [N][2] */
+  int64_t* n_pair_ticks;    /* [N] */
+  uint8_t* rss_flags;       /* [N] */
+  int32_t* tick;            /* [N] */
+  double* t;                /* [N] */
+  int32_t* event_count;     /* [1] */
+} SgHostResults;
+
+int sg_rollout_host(const SgScene* host_scene, const SgScene* dev_scene, const SgParams* params,
+                    SgState* dev_state, const SgInputs* host_inputs, const SgInputs* dev_inputs,
+                    SgHostResults* host_results, int copy_static, int device, void* stream);
+
+/* bytes moved by sg_rollout_host per call (for the e2e report) */
+int64_t sg_host_h2d_bytes(const SgScene* host_scene, const SgInputs* host_inputs, int copy_static);
+int64_t sg_host_d2h_bytes(const SgScene* host_scene);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SG_B200_H */

@@ -1,0 +1,248 @@
+"""
+Scene packing: lower scenarios + agent assignment to the flat structure-of-arrays
+description consumed by the engine (``SgScene`` in include/sg_b200.h).
+
+Host-side logic only (numpy).  The one piece of reference arithmetic that lives
+here is the construction of the ``BatchReplayEntity`` union-knot table
+(reference entity/batch.py:55-128), which the device then interpolates per tick.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import abi
+
+
+def call_linear(x: np.ndarray, y: np.ndarray, x_new: np.ndarray) -> np.ndarray:
+    """
+    Linear interpolation with the operation order of scipy 1.18 ``interp1d._call_linear``
+    (scipy/interpolate/_interpolate.py:491-518), as used by the reference at
+    trajectory.py:178-184 and entity/batch.py:99-127.
+
+    x: (K,), y: (K, m), x_new: (n,) -> (n, m).  Extrapolates linearly outside [x0, xK-1].
+    """
+    idx = np.searchsorted(x, x_new).clip(1, len(x) - 1).astype(int)
+    lo, hi = idx - 1, idx
+    x_lo, x_hi = x[lo], x[hi]
+    return ((x_new - x_lo) / (x_hi - x_lo))[:, None] * y[hi] + (
+        (x_hi - x_new) / (x_hi - x_lo)
+    )[:, None] * y[lo]
+
+
+def call_linear_clamped(x: np.ndarray, y: np.ndarray, x_new: np.ndarray) -> np.ndarray:
+    """interp1d(..., bounds_error=False, fill_value=(y[0], y[-1])) (_interpolate.py:561-574)."""
+    out = call_linear(x, y, x_new)
+    out[x_new < x[0]] = y[0]
+    out[x_new > x[-1]] = y[-1]
+    return out
+
+
+def build_union_table(trajs: Sequence[np.ndarray]):
+    """
+    Restates ``BatchReplayEntity.add_entities`` (entity/batch.py:80-112): every
+    trajectory is resampled (clamped) at the sorted union of all control-point
+    times.  Returns ``ts (Nk,)`` and ``X (Nk, n_ents, 6)``.
+    """
+    datas = []
+    for data in trajs:
+        d = np.nan_to_num(data)
+        if d.shape[0] == 1:
+            d = np.repeat(d, 2, axis=0)
+            d[-1, 0] += 1e-1
+        datas.append(d)
+    ts = np.array(sorted(set(t for d in datas for t in d[:, 0])))
+    X = np.stack([call_linear_clamped(d[:, 0], d[:, 1:], ts) for d in datas], axis=1)
+    return ts, X
+
+
+@dataclass
+class SlotSpec:
+    """One entity slot of a scenario."""
+
+    kind: int
+    traj: np.ndarray  # (K, 7) [t, x, y, z, h, p, r] as held by Trajectory.data
+    box: Sequence[float] = (2.0, 4.0, 0.0, 0.0)  # width, length, center_x, center_y
+    etype: int = abi.ETYPE_VEHICLE
+    speed_desired: float = 0.0
+    route: Optional[np.ndarray] = None  # (R, 2)
+    ref: str = ""
+
+
+@dataclass
+class ScenarioSpec:
+    """
+    One scenario: ``slots`` must be ordered like ``state.poses`` of the reference,
+    i.e. agents (scenario order) first, then replayed entities
+    (scenario_gym.py:232-245).
+    """
+
+    slots: List[SlotSpec]
+    ego_slot: int = 0
+    first_slot: int = 0
+    t0: Optional[float] = None
+    length: Optional[float] = None
+    name: str = ""
+
+    def finalize(self):
+        if self.length is None:  # Scenario.length, scenario/scenario.py:88-91
+            self.length = max(float(s.traj[:, 0].max()) for s in self.slots)
+        if self.t0 is None:  # ScenarioGym.get_start_time, scenario_gym.py:213-215
+            self.t0 = max(0.0, float(self.slots[self.ego_slot].traj[:, 0].min()))
+
+
+@dataclass
+class PackedScene:
+    """numpy arrays behind ``SgScene`` (host side)."""
+
+    N: int
+    M: int
+    kind: np.ndarray
+    etype: np.ndarray
+    box: np.ndarray
+    traj_off: np.ndarray
+    traj_rows: np.ndarray
+    union_off: np.ndarray
+    union_t: np.ndarray
+    union_x: np.ndarray
+    t0: np.ndarray
+    length: np.ndarray
+    ego_slot: np.ndarray
+    first_slot: np.ndarray
+    ped_speed_desired: np.ndarray
+    route_off: np.ndarray
+    route_xy: np.ndarray
+    n_entities: np.ndarray = field(default=None)
+
+    @property
+    def W(self) -> int:
+        return (self.M + 31) // 32
+
+    def arrays(self):
+        return {k: getattr(self, k) for k in abi.SCENE_FIELDS}
+
+    def nbytes(self) -> int:
+        return int(sum(a.nbytes for a in self.arrays().values()))
+
+
+def pack_scenarios(specs: Sequence[ScenarioSpec], n_slots: Optional[int] = None) -> PackedScene:
+    """Pack scenario specs into one PackedScene (slots padded with EMPTY)."""
+    N = len(specs)
+    for s in specs:
+        s.finalize()
+    M = n_slots or max(len(s.slots) for s in specs)
+    if M > 1024 or M < 1:
+        raise ValueError("1 <= n_slots <= 1024")
+    if any(len(s.slots) > M for s in specs):
+        raise ValueError("scenario has more entities than n_slots")
+    NM = N * M
+    kind = np.zeros(NM, np.uint8)
+    etype = np.zeros(NM, np.uint8)
+    box = np.zeros((4, NM), np.float64)
+    box[0:2] = 1.0
+    speed_desired = np.zeros(NM, np.float64)
+    traj_off = np.zeros(NM + 1, np.int64)
+    route_off = np.zeros(NM + 1, np.int64)
+    rows, routes = [], []
+    union_off = np.zeros(N + 1, np.int64)
+    union_t, union_x = [], []
+    nrow = nroute = 0
+    for n, sp in enumerate(specs):
+        replay_idx = []
+        for s in range(M):
+            i = n * M + s
+            if s < len(sp.slots):
+                sl = sp.slots[s]
+                tr = np.ascontiguousarray(sl.traj, dtype=np.float64)
+                if tr.ndim != 2 or tr.shape[1] != 7 or tr.shape[0] < 1:
+                    raise ValueError("trajectory must be (K>=1, 7)")
+                kind[i] = sl.kind
+                etype[i] = sl.etype
+                box[:, i] = sl.box
+                speed_desired[i] = sl.speed_desired
+                rows.append(tr)
+                nrow += tr.shape[0]
+                if sl.route is not None:
+                    r = np.ascontiguousarray(sl.route, dtype=np.float64).reshape(-1, 2)
+                    routes.append(r)
+                    nroute += r.shape[0]
+                if sl.kind == abi.KIND_REPLAY:
+                    replay_idx.append(s)
+            traj_off[i + 1] = nrow
+            route_off[i + 1] = nroute
+        if replay_idx:
+            ts, X = build_union_table([sp.slots[s].traj for s in replay_idx])
+            full = np.zeros((len(ts), 6, M), np.float64)
+            full[:, :, replay_idx] = np.transpose(X, (0, 2, 1))
+            union_t.append(ts)
+            union_x.append(full)
+            union_off[n + 1] = union_off[n] + len(ts)
+        else:
+            union_off[n + 1] = union_off[n]
+    return PackedScene(
+        N=N,
+        M=M,
+        kind=kind,
+        etype=etype,
+        box=box,
+        traj_off=traj_off,
+        traj_rows=np.concatenate(rows, axis=0) if rows else np.zeros((0, 7)),
+        union_off=union_off,
+        union_t=np.concatenate(union_t) if union_t else np.zeros(0),
+        union_x=np.concatenate(union_x, axis=0) if union_x else np.zeros((0, 6, M)),
+        t0=np.array([s.t0 for s in specs], np.float64),
+        length=np.array([s.length for s in specs], np.float64),
+        ego_slot=np.array([s.ego_slot for s in specs], np.int32),
+        first_slot=np.array([s.first_slot for s in specs], np.int32),
+        ped_speed_desired=speed_desired,
+        route_off=route_off,
+        route_xy=np.concatenate(routes, axis=0) if routes else np.zeros((0, 2)),
+        n_entities=np.array([len(s.slots) for s in specs], np.int32),
+    )
+
+
+def tile_scene(scene: PackedScene, reps: int) -> PackedScene:
+    """Replicate every scenario ``reps`` times round-robin (config C2: bit-identical copies)."""
+    N, M = scene.N, scene.M
+    order = np.tile(np.arange(N), reps)
+
+    def plane(a):  # (..., N*M)
+        lead = a.shape[:-1]
+        return a.reshape(lead + (N, M))[..., order, :].reshape(lead + (len(order) * M,)).copy()
+
+    def csr(off, data, per):
+        cnt = np.diff(off).reshape(N, per)
+        new_cnt = cnt[order].reshape(-1)
+        new_off = np.concatenate([[0], np.cumsum(new_cnt)]).astype(np.int64)
+        starts = off[:-1].reshape(N, per)[order].reshape(-1)
+        idx = np.concatenate(
+            [np.arange(s, s + c) for s, c in zip(starts, new_cnt)] or [np.zeros(0, np.int64)]
+        ).astype(np.int64)
+        return new_off, data[idx]
+
+    traj_off, traj_rows = csr(scene.traj_off, scene.traj_rows, M)
+    route_off, route_xy = csr(scene.route_off, scene.route_xy, M)
+    union_off, union_t = csr(scene.union_off, scene.union_t, 1)
+    _, union_x = csr(scene.union_off, scene.union_x, 1)
+    return PackedScene(
+        N=len(order),
+        M=M,
+        kind=plane(scene.kind),
+        etype=plane(scene.etype),
+        box=plane(scene.box),
+        traj_off=traj_off,
+        traj_rows=traj_rows,
+        union_off=union_off,
+        union_t=union_t,
+        union_x=union_x,
+        t0=scene.t0[order].copy(),
+        length=scene.length[order].copy(),
+        ego_slot=scene.ego_slot[order].copy(),
+        first_slot=scene.first_slot[order].copy(),
+        ped_speed_desired=plane(scene.ped_speed_desired),
+        route_off=route_off,
+        route_xy=route_xy,
+        n_entities=scene.n_entities[order].copy(),
+    )
