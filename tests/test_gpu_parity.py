@@ -1,0 +1,305 @@
+"""
+GPU parity tests (run on the B200 box): the CUDA engine, called through the C ABI, against
+(a) the reference's golden vectors and (b) the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): collision flags, first-collision tick, pairs and events
+bit-exact; poses and continuous metrics within 1e-9 absolute-or-relative in fp64.
+"""
+import numpy as np
+import pytest
+
+from oracle import golden_cases
+from oracle.runner import OracleEngine
+from scenario_gym_b200 import abi, synthetic
+from scenario_gym_b200.packing import pack_scenarios, tile_scene
+from scenario_gym_b200.synthetic import pack_synthetic
+
+from helpers import all_xosc_specs, check_against_golden, golden, manifest, sub
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def make_gpu(scene, params, trace_cap=0):
+    from scenario_gym_b200.engine import Engine
+
+    return Engine(scene, params, device=0, event_cap=1 << 16, trace_cap=trace_cap)
+
+
+def _params(**kw):
+    p = abi.default_params()
+    p.features = abi.FEAT_COLLISIONS | abi.FEAT_EGO_METRICS | abi.FEAT_COLL_MATRIX
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def close(a, b, what, tol=TOL):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    err = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    err[np.isnan(a) & np.isnan(b)] = 0.0
+    err[(a == b)] = 0.0
+    assert np.all(err <= tol), f"{what}: max err {np.nanmax(err):.3e}"
+
+
+def compare_engines(gpu, cpu, scene, what, check_rss=False, check_ped=False):
+    """Final state of a GPU engine vs the CPU oracle after identical calls."""
+    for k in ("tick", "done", "present", "collided", "first_coll_tick", "first_coll_pair",
+              "n_pair_ticks", "ego_hits"):
+        assert np.array_equal(gpu.get(k), cpu.get(k)), f"{what}: {k} differs"
+    assert np.array_equal(gpu.get("t"), cpu.get("t")), f"{what}: tick times differ"
+    ge, ce = gpu.events(), cpu.events()
+    assert len(ge) == len(ce), f"{what}: {len(ge)} vs {len(ce)} events"
+    for f in ("scenario", "tick", "slot", "t"):
+        assert np.array_equal(ge[f], ce[f]), f"{what}: event {f} differs"
+    pres = cpu.get("present").astype(bool)
+    for k in ("pose", "vel"):
+        close(gpu.get(k)[:, pres], cpu.get(k)[:, pres], f"{what}: {k}")
+    for k in ("dist", "speed", "ego_avg_speed", "ego_max_speed", "ego_dist"):
+        close(gpu.get(k), cpu.get(k), f"{what}: {k}")
+    if check_rss:
+        assert np.array_equal(gpu.get("rss_flags"), cpu.get("rss_flags")), f"{what}: rss flags"
+        assert np.array_equal(gpu.get("rss_state"), cpu.get("rss_state")), f"{what}: rss state"
+        assert np.array_equal(gpu.get("rss_last"), cpu.get("rss_last")), f"{what}: rss record"
+        fin = np.isfinite(cpu.get("safe_ratio"))
+        close(gpu.get("safe_dist"), cpu.get("safe_dist"), f"{what}: safe_dist")
+        close(gpu.get("safe_ratio")[fin], cpu.get("safe_ratio")[fin], f"{what}: safe_ratio")
+    if check_ped:
+        assert np.array_equal(gpu.get("goal_idx"), cpu.get("goal_idx")), f"{what}: goal_idx"
+        close(gpu.get("force"), cpu.get("force"), f"{what}: force")
+
+
+# ----------------------------------------------------------------------------- golden vectors
+XOSC = all_xosc_specs("xosc")
+
+
+@pytest.mark.parametrize("case", XOSC, ids=[c[0][:8] for c in XOSC])
+def test_xosc_replay_golden(case):
+    name, spec, order, out = case
+    check_against_golden(make_gpu, pack_scenarios([spec]), _params(), out, 0, order)
+
+
+@pytest.mark.parametrize("variant", ["xosc_norelabel", "xosc_persist"])
+def test_xosc_variants_golden(variant):
+    for name, spec, order, out in all_xosc_specs(variant):
+        p = _params(persist=1 if variant == "xosc_persist" else 0)
+        check_against_golden(make_gpu, pack_scenarios([spec]), p, out, 0, order)
+
+
+@pytest.mark.parametrize("tag,terminal", [
+    ("veh", abi.TERM_MAX_LENGTH),
+    ("veh_term", abi.TERM_MAX_LENGTH | abi.TERM_COLLISION),
+    ("veh_egoterm", abi.TERM_MAX_LENGTH | abi.TERM_EGO_COLLISION),
+])
+def test_vehicle_golden(tag, terminal):
+    cfg = golden_cases.veh_cfg()
+    scene = pack_synthetic(cfg)
+    g = golden("veh_rss")
+    p = _params(timestep=cfg.dt, terminal=terminal)
+    for n in range(cfg.N):
+        check_against_golden(make_gpu, scene, p, sub(g, f"{tag}/{n}/out"), n, list(range(cfg.M)),
+                             actions=cfg.actions)
+
+
+def test_rss_golden():
+    cfg = golden_cases.rss_cfg()
+    scene = pack_synthetic(cfg)
+    g = golden("veh_rss")
+    p = _params(timestep=cfg.dt)
+    p.features |= abi.FEAT_RSS
+    M = cfg.M
+    eng = make_gpu(scene, p)
+    eng.reset()
+    T = cfg.T
+    for k in range(1, T + 1):
+        eng.rollout(1, actions=cfg.actions[k - 1: k])
+        rec = eng.get("rss_last").reshape(cfg.N, M)
+        sd = eng.get("safe_dist").reshape(2, cfg.N, M)
+        ratio = eng.get("safe_ratio").reshape(2, cfg.N, M)
+        for n in range(cfg.N):
+            out = sub(g, f"rss/{n}/out")
+            assert np.array_equal(rec[n], out["rss_rec"][k]), f"RSS records differ, scenario {n} tick {k}"
+            live = rec[n] != abi.RSS_NONE
+            close(sd[:, n].T[live], out["rss_sd"][k][live], "safe distances")
+            close(ratio[:, n].T[live], out["rss_ratio"][k][live], "safe ratios")
+    flags = eng.get("rss_flags")
+    for n in range(cfg.N):
+        out = sub(g, f"rss/{n}/out")
+        assert (not (flags[n] & 1)) == bool(out["rss_safe_longitudinal"])
+        assert (not (flags[n] & 2)) == bool(out["rss_safe_lateral"])
+        check_against_golden(make_gpu, scene, p, out, n, list(range(M)), actions=cfg.actions)
+
+
+def test_social_force_golden():
+    cfg = golden_cases.ped_cfg()
+    scene = pack_synthetic(cfg)
+    g = golden("ped")
+    p = _params(timestep=cfg.dt)
+    M = cfg.M
+    eng = make_gpu(scene, p)
+    eng.reset()
+    for k in range(1, cfg.T + 1):
+        eng.rollout(1)
+        goal = eng.get("goal_idx").reshape(cfg.N, M)
+        force = eng.get("force").reshape(2, cfg.N, M)
+        for n in range(cfg.N):
+            out = sub(g, f"ped/{n}/out")
+            assert np.array_equal(goal[n], out["goal"][k]), f"goal_idx scenario {n} tick {k}"
+            close(force[:, n].T, out["force"][k], "social force")
+    for n in range(cfg.N):
+        check_against_golden(make_gpu, scene, p, sub(g, f"ped/{n}/out"), n, list(range(M)))
+
+
+def test_box_pairs_golden():
+    """Exact closed-set box intersection incl. touching and identical boxes (unit vectors)."""
+    import torch
+
+    from scenario_gym_b200.abi import load_product
+
+    lib = load_product()
+    g = sub(golden("unit"), "unit")
+    W, L, cx, cy = manifest()["unit"]["box"]
+    n = len(g["pair_hit"])
+    dev = torch.device("cuda:0")
+    pa = torch.from_numpy(np.ascontiguousarray(g["pair_pose_a"][:, [0, 1, 3]])).to(dev)
+    pb = torch.from_numpy(np.ascontiguousarray(g["pair_pose_b"][:, [0, 1, 3]])).to(dev)
+    box = torch.tensor([[W, L, cx, cy]] * n, dtype=torch.float64, device=dev)
+    out = torch.zeros(n, dtype=torch.uint8, device=dev)
+    rc = lib["test_box_pairs"](pa.data_ptr(), box.data_ptr(), pb.data_ptr(), box.data_ptr(),
+                               out.data_ptr(), n, 0, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), g["pair_hit"])
+
+
+# ----------------------------------------------------------------------------- vs CPU oracle
+def _run_both(scene, p, actions=None, n_calls=1, ticks=-1):
+    gpu = make_gpu(scene, p)
+    cpu = OracleEngine(scene, p, event_cap=1 << 16)
+    for eng in (gpu, cpu):
+        eng.reset()
+        k0 = 0
+        for _ in range(n_calls):
+            if ticks < 0:
+                eng.rollout(-1, actions=actions)
+            else:
+                eng.rollout(ticks, actions=None if actions is None else actions[k0: k0 + ticks])
+                k0 += ticks
+    return gpu, cpu
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_vehicles_vs_oracle(seed):
+    """C3 shape (M = 64) at a size the oracle finishes in seconds; dense enough to collide."""
+    cfg = synthetic.vehicles_config(seed=seed, N=96, M=64, T=48, half_extent=60.0)
+    scene = pack_synthetic(cfg)
+    p = _params(timestep=cfg.dt)
+    gpu, cpu = _run_both(scene, p, actions=cfg.actions)
+    assert cpu.get("n_pair_ticks").sum() > 100, "config must produce collisions"
+    compare_engines(gpu, cpu, scene, f"vehicles seed {seed}")
+    assert np.array_equal(gpu.get("coll_mask"), cpu.get("coll_mask"))
+    # the same rollout split into several calls must give bit-identical results on the GPU
+    gpu2, _ = _run_both(scene, p, actions=cfg.actions, n_calls=3, ticks=16)
+    for k in ("pose", "vel", "dist", "speed", "t", "ego_avg_speed", "n_pair_ticks", "collided"):
+        assert np.array_equal(gpu.get(k), gpu2.get(k)), f"split rollout differs in {k}"
+
+
+@pytest.mark.parametrize("M", [1, 3, 20, 33, 100])
+def test_ragged_slot_counts_vs_oracle(M):
+    """Group sizes: sub-warp (several scenarios per warp), one warp, several warps with padding."""
+    cfg = synthetic.vehicles_config(seed=7, N=37, M=M, T=24, half_extent=5.0 + 2.0 * M ** 0.5)
+    scene = pack_synthetic(cfg)
+    p = _params(timestep=cfg.dt)
+    gpu, cpu = _run_both(scene, p, actions=cfg.actions)
+    compare_engines(gpu, cpu, scene, f"M={M}")
+    assert np.array_equal(gpu.get("coll_mask"), cpu.get("coll_mask"))
+
+
+def test_highway_rss_vs_oracle():
+    """C5 shape at reduced size: RSS + SafeDistance next to collisions."""
+    cfg = synthetic.highway_config(seed=3, N=24, M=64, T=40, lanes=4)
+    cfg.x0[:] = cfg.x0 * 0.5  # tighten headways so buffers are entered
+    scene = pack_synthetic(cfg)
+    p = _params(timestep=cfg.dt)
+    p.features |= abi.FEAT_RSS
+    gpu, cpu = _run_both(scene, p, actions=cfg.actions)
+    assert cpu.get("rss_flags").any(), "config must violate RSS somewhere"
+    compare_engines(gpu, cpu, scene, "highway", check_rss=True)
+
+
+def test_crowd_vs_oracle():
+    """C4 shape at reduced size: social force with many neighbours per pedestrian."""
+    cfg = synthetic.crowd_config(seed=5, N=6, M=96, T=30, side=9.0)
+    scene = pack_synthetic(cfg)
+    p = _params(timestep=cfg.dt)
+    gpu, cpu = _run_both(scene, p)
+    compare_engines(gpu, cpu, scene, "crowd", check_ped=True)
+
+
+def test_big_group_vs_oracle():
+    """M > 256: one scenario per CTA (M = 320)."""
+    cfg = synthetic.crowd_config(seed=6, N=3, M=320, T=12, side=16.0)
+    scene = pack_synthetic(cfg)
+    p = _params(timestep=cfg.dt)
+    gpu, cpu = _run_both(scene, p)
+    compare_engines(gpu, cpu, scene, "crowd M=320", check_ped=True)
+
+
+def test_c2_replicas_identical():
+    """C2: replicas of the test scenarios are bit-identical copies => identical results per file."""
+    specs = [s for _, s, _, _ in XOSC]
+    scene = pack_scenarios(specs)
+    tiled = tile_scene(scene, 5)
+    p = _params()
+    p.features &= ~abi.FEAT_COLL_MATRIX
+    gpu = make_gpu(tiled, p)
+    gpu.reset()
+    gpu.rollout(-1)
+    cpu = OracleEngine(scene, p, event_cap=1 << 16)
+    cpu.reset()
+    cpu.rollout(-1)
+    N = scene.N
+    for k in ("tick", "first_coll_tick", "n_pair_ticks", "t"):
+        a = gpu.get(k).reshape(5, N)
+        assert all(np.array_equal(a[0], a[r]) for r in range(5)), k
+        assert np.array_equal(a[0], cpu.get(k)), k
+    for k in ("ego_avg_speed", "ego_max_speed", "ego_dist"):
+        a = gpu.get(k).reshape(5, N)
+        assert all(np.array_equal(a[0], a[r]) for r in range(5)), k
+        close(a[0], cpu.get(k), k)
+    assert len(gpu.events()) == 5 * len(cpu.events())
+    # golden tick counts / end times of SURVEY.md section 8c
+    for n, (name, _, _, out) in enumerate(XOSC):
+        assert gpu.get("tick")[n] == int(out["n_ticks"])
+        assert gpu.get("t")[n] == float(out["t_end"])
+
+
+def test_properties_full_size_sample():
+    """
+    Size-independent properties on a larger batch (no oracle): permuting the scenarios of a
+    batch permutes the results bit-identically; n_pair_ticks is consistent with collided flags.
+    """
+    cfg = synthetic.vehicles_config(seed=11, N=2048, M=64, T=32, half_extent=80.0)
+    scene = pack_synthetic(cfg)
+    p = _params(timestep=cfg.dt)
+    p.features &= ~abi.FEAT_COLL_MATRIX
+    gpu = make_gpu(scene, p)
+    gpu.reset()
+    gpu.rollout(-1, actions=cfg.actions)
+    perm = np.random.default_rng(0).permutation(cfg.N)
+    cfg2 = synthetic.vehicles_config(seed=11, N=2048, M=64, T=32, half_extent=80.0)
+    for name in ("x0", "y0", "h0", "v0"):
+        setattr(cfg2, name, getattr(cfg, name)[perm])
+    cfg2.actions = cfg.actions.reshape(cfg.T, 2, cfg.N, cfg.M)[:, :, perm].reshape(cfg.T, 2, -1).copy()
+    gpu2 = make_gpu(pack_synthetic(cfg2), p)
+    gpu2.reset()
+    gpu2.rollout(-1, actions=cfg2.actions)
+    for k in ("ego_avg_speed", "ego_dist", "first_coll_tick", "n_pair_ticks", "tick"):
+        assert np.array_equal(gpu.get(k)[perm], gpu2.get(k)), k
+    pose = gpu.get("pose").reshape(6, cfg.N, cfg.M)
+    assert np.array_equal(pose[:, perm], gpu2.get("pose").reshape(6, cfg.N, cfg.M))
+    col = gpu.get("collided").reshape(cfg.N, cfg.M)
+    npt = gpu.get("n_pair_ticks")
+    assert np.array_equal(col.any(axis=1), npt > 0)
+    assert np.array_equal(gpu.get("first_coll_tick") >= 0, npt > 0)
