@@ -460,12 +460,19 @@ static void collisions_update(const SgScene* sc, const SgParams* p, SgState* st,
                               int record_metric, int* out_any, int* out_first_hit) {
   int64_t nm = NM;
   int M = sc->n_slots, W = (M + 31) / 32;
-  double* pts = (double*)malloc(sizeof(double) * 8 * M);
+  double* pts = (double*)malloc(sizeof(double) * 12 * M);
+  double* env = pts + 8 * M;
   for (int s = 0; s < M; ++s) {
     int64_t i = IDX(n, s);
     if (!st->present[i]) continue;
     box_points(st->pose[i], st->pose[nm + i], st->pose[3 * nm + i], sc->box[i], sc->box[nm + i],
                sc->box[2 * nm + i], sc->box[3 * nm + i], pts + 8 * s);
+    const double* q = pts + 8 * s;
+    double* e = env + 4 * s;
+    e[0] = fmin(fmin(q[0], q[2]), fmin(q[4], q[6]));
+    e[1] = fmin(fmin(q[1], q[3]), fmin(q[5], q[7]));
+    e[2] = fmax(fmax(q[0], q[2]), fmax(q[4], q[6]));
+    e[3] = fmax(fmax(q[1], q[3]), fmax(q[5], q[7]));
   }
   uint32_t* ego_now = (uint32_t*)calloc(W, sizeof(uint32_t));
   int es = sc->ego_slot[n], fs = sc->first_slot[n];
@@ -478,6 +485,9 @@ static void collisions_update(const SgScene* sc, const SgParams* p, SgState* st,
     for (int b = a + 1; b < M; ++b) {
       if (!st->present[IDX(n, b)]) continue;
       const double *qa = pts + 8 * a, *qb = pts + 8 * b;
+      /* STRtree.query first filters by envelope intersection (closed, exact on fp64) */
+      const double *ea = env + 4 * a, *eb = env + 4 * b;
+      if (ea[0] > eb[2] || eb[0] > ea[2] || ea[1] > eb[3] || eb[1] > ea[3]) continue;
       if (memcmp(qa, qb, 64) == 0) continue; /* `g != g_prime`, utils.py:58 */
       if (!quads_intersect(qa, qb)) continue;
       ++npairs;

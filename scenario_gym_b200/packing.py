@@ -246,3 +246,31 @@ def tile_scene(scene: PackedScene, reps: int) -> PackedScene:
         route_xy=route_xy,
         n_entities=scene.n_entities[order].copy(),
     )
+
+
+def slice_scene(scene: PackedScene, lo: int, hi: int) -> PackedScene:
+    """Scenarios [lo, hi) of a packed scene (used to shard a batch across ranks / workers)."""
+    N, M = scene.N, scene.M
+    hi = min(hi, N)
+    n = hi - lo
+
+    def plane(a):
+        lead = a.shape[:-1]
+        return np.ascontiguousarray(a.reshape(lead + (N, M))[..., lo:hi, :].reshape(lead + (n * M,)))
+
+    def csr(off, data, per):
+        a, b = off[lo * per], off[hi * per]
+        return (off[lo * per: hi * per + 1] - a).astype(np.int64), np.ascontiguousarray(data[a:b])
+
+    traj_off, traj_rows = csr(scene.traj_off, scene.traj_rows, M)
+    route_off, route_xy = csr(scene.route_off, scene.route_xy, M)
+    union_off, union_t = csr(scene.union_off, scene.union_t, 1)
+    _, union_x = csr(scene.union_off, scene.union_x, 1)
+    return PackedScene(
+        N=n, M=M, kind=plane(scene.kind), etype=plane(scene.etype), box=plane(scene.box),
+        traj_off=traj_off, traj_rows=traj_rows, union_off=union_off, union_t=union_t,
+        union_x=union_x, t0=scene.t0[lo:hi].copy(), length=scene.length[lo:hi].copy(),
+        ego_slot=scene.ego_slot[lo:hi].copy(), first_slot=scene.first_slot[lo:hi].copy(),
+        ped_speed_desired=plane(scene.ped_speed_desired), route_off=route_off, route_xy=route_xy,
+        n_entities=scene.n_entities[lo:hi].copy(),
+    )

@@ -112,8 +112,16 @@ def pack_synthetic(cfg: SyntheticConfig) -> PackedScene:
     )
 
 
+def _uniform_into(rng, out: np.ndarray, low: float, high: float) -> None:
+    """Same stream and bits as rng.uniform(low, high, out.shape), written into `out`."""
+    rng.random(out=out)
+    out *= high - low
+    out += low
+
+
 def vehicles_config(seed: int, N: int, M: int = 64, T: int = 256, dt: float = 0.1,
-                    half_extent: float = 200.0, name: str = "C3") -> SyntheticConfig:
+                    half_extent: float = 200.0, name: str = "C3",
+                    actions_out: Optional[np.ndarray] = None) -> SyntheticConfig:
     """
     C3: M VehicleController agents per scenario with random accel/steer actions.
     x,y ~ U(-half_extent, half_extent), h ~ U(-pi, pi), v0 ~ U(0, 15),
@@ -124,9 +132,15 @@ def vehicles_config(seed: int, N: int, M: int = 64, T: int = 256, dt: float = 0.
     y0 = rng.uniform(-half_extent, half_extent, (N, M))
     h0 = rng.uniform(-np.pi, np.pi, (N, M))
     v0 = rng.uniform(0.0, 15.0, (N, M))
-    actions = np.empty((T, 2, N * M))
-    actions[:, 0] = rng.uniform(-6.0, 6.0, (T, N * M))
-    actions[:, 1] = rng.uniform(-1.0, 1.0, (T, N * M))
+    actions = np.empty((T, 2, N * M)) if actions_out is None else actions_out
+    assert actions.shape == (T, 2, N * M) and actions.dtype == np.float64
+    # drawn plane by plane (all accel rows, then all steer rows), in place: the table can be
+    # a view of pinned host memory
+    tmp = np.empty(N * M)
+    for c, (lo, hi) in enumerate(((-6.0, 6.0), (-1.0, 1.0))):
+        for k in range(T):
+            _uniform_into(rng, tmp, lo, hi)
+            actions[k, c] = tmp
     return SyntheticConfig(
         name=name, N=N, M=M, T=T, dt=dt, x0=x0, y0=y0, h0=h0, v0=v0,
         box=np.array(CAR1_BOX), kind=np.full((N, M), abi.KIND_VEHICLE, np.uint8),
