@@ -1,16 +1,22 @@
 // sg_kernels.cu -- the fused per-tick rollout kernel and the C ABI (include/sg_b200.h).
 //
 // Mapping: one thread per entity slot; the G threads of a scenario ("group") are a
-// sub-warp (M <= 32: G = next pow2, several scenarios per warp), or G/32 whole warps
+// sub-warp (M <= 32: G = next pow2, several scenarios per warp) or G/32 whole warps
 // (M > 32: G = M rounded up to 32).  A 256-thread CTA carries 256/G scenarios.  Each
 // thread keeps its entity's State row (pose, velocity, distance, controller speed, RSS
-// history bits) in registers for all ticks of the call; per tick the group stages every
-// entity's fp64 box corners + a conservative fp32 AABB in shared memory, synchronises
-// (sub-warp: __syncwarp(mask); multi-warp: a named barrier per scenario) and every
-// thread sweeps the scenario's boxes: fp32 AABB reject, then the exact closed-set test
-// on the fp64 corners.  Collision rows are built 32 slots at a time as bit words; the
-// ego row feeds CollisionMetric's rising-edge detection.  n_ticks = 1 is
-// ScenarioGym.step(); n_ticks < 0 is ScenarioGym.rollout().
+// history bits) in registers for all ticks of the call (n_ticks = 1 is
+// ScenarioGym.step(); n_ticks < 0 is ScenarioGym.rollout()).  Per tick:
+//   A  every thread produces its entity's new pose (replay interpolation / kinematic
+//      bicycle / social force), updates velocity + distance, and stages its fp64 box
+//      corners and a conservative fp32 AABB in shared memory;
+//   B1 RSS per hazard against the ego published in shared memory; broad phase as a
+//      circular half sweep: thread s tests slots s+1 .. s+M/2 (each unordered pair once,
+//      branch-free bit accumulation, AABB array duplicated so the wrap is an immediate
+//      offset) and pushes the rare AABB survivors to a per-scenario queue;
+//   B2 the queue is drained cooperatively with the exact closed-set predicate on the
+//      fp64 corners; hits set bits in the scenario's collision words;
+//   C  terminal conditions, CollisionMetric rising edges (ego row bit words), ego metrics.
+// Groups synchronise with __syncwarp(mask) (sub-warp) or a named barrier per scenario.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -33,55 +39,97 @@ static int set_msg(const char* what) {
 }
 
 // ---------------------------------------------------------------------------------
+// per-scenario shared-memory block
 struct GroupLayout {
-  int G;            // threads (slots incl. padding) per scenario
-  int W;            // 32-bit words per collision row
-  int off_aabb;     // byte offsets inside a group's shared-memory block
-  int off_ped;
-  int off_flags;
-  int off_orient;
-  int off_ego;
-  int off_hits;
-  int off_acc;
+  int G;        // threads (slots incl. padding) per scenario
+  int W;        // 32-bit words per collision row
+  int H;        // half-sweep length M/2
+  int QCAP;     // candidate-pair queue capacity
+  int off_hcs, off_ped, off_ego, off_aabb, off_queue, off_hits, off_bits, off_acc, off_flags,
+      off_orient;
   int bytes;
 };
 
-static GroupLayout make_layout(int M, bool ped) {
+enum { EGO_X = 0, EGO_Y, EGO_C, EGO_S, EGO_INV0, EGO_INV1, EGO_HD0, EGO_HD1, EGO_V0, EGO_V1,
+       EGO_VNORM, EGO_W, EGO_L, EGO_PRESENT, EGO_N = 16 };
+enum { ACC_NPAIRS = 0, ACC_FIRST_PAIR, ACC_FIRST_HIT, ACC_RSS, ACC_QCOUNT, ACC_N = 8 };
+
+static GroupLayout make_layout(int M, bool ped, bool rss) {
   GroupLayout L;
   int G;
   if (M <= 32) { G = 1; while (G < M) G <<= 1; } else { G = (M + 31) / 32 * 32; }
   L.G = G;
   L.W = (M + 31) / 32;
-  int o = 8 * G * (int)sizeof(double);               // corners[8][G]
-  L.off_ped = o;     o += ped ? 4 * G * (int)sizeof(double) : 0;  // x,y,vx,vy of pedestrians (old state)
-  L.off_ego = o;     o += 8 * (int)sizeof(double);   // ego x,y,h,vx,vy
-  L.off_aabb = o;    o += G * (int)sizeof(float4);
-  L.off_hits = o;    o += 2 * L.W * (int)sizeof(uint32_t);  // ego_now[W], ego_last[W]
-  L.off_acc = o;     o += 8 * (int)sizeof(int);      // 2 parities x {npairs, first_pair, first_hit, rss}
-  L.off_flags = o;   o += G + 16;                    // old present|etype (ped neighbour filter); [G] = ego present
-  L.off_orient = o;  o += G;                         // ring orientation of each box
+  L.H = M / 2;
+  L.QCAP = 4 * G;
+  int o = 8 * G * (int)sizeof(double);                            // corners[8][G]
+  L.off_hcs = o;    o += rss ? 2 * G * (int)sizeof(double) : 0;   // cos/sin of each heading
+  L.off_ped = o;    o += ped ? 4 * G * (int)sizeof(double) : 0;   // old x,y,vx,vy (pedestrian sensors)
+  L.off_ego = o;    o += EGO_N * (int)sizeof(double);
+  L.off_aabb = o;   o += (M + L.H + 1) * (int)sizeof(float4);     // duplicated head: no wrap in the sweep
+  L.off_queue = o;  o += L.QCAP * (int)sizeof(uint32_t);
+  L.off_hits = o;   o += 2 * L.W * (int)sizeof(uint32_t);         // ego_now[W], ego_last[W]
+  L.off_bits = o;   o += 2 * L.W * (int)sizeof(uint32_t);         // collided bits, 2 parities
+  L.off_acc = o;    o += 2 * ACC_N * (int)sizeof(int);            // 2 parities
+  L.off_flags = o;  o += G + 16;                                  // old present|etype<<1
+  L.off_orient = o; o += G;                                       // ring orientation of each box
   L.bytes = (o + 15) / 16 * 16;
   return L;
 }
 
-SG_DEV void group_sync(int G, int bar_id, unsigned mask) {
-  if (G <= 32) __syncwarp(mask);
-  else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(G) : "memory");
-}
-
-struct TickCtx {
-  int n, s, M, G, W;
+struct Grp {
+  int n, s, M, G, W, H, QCAP, bar_id;
+  unsigned mask;
   int64_t i, nm;
   double* corners;
+  double* hcs;
   double* pedbuf;
-  double* egobuf;
+  double* egop;
   float4* aabb;
+  uint32_t* queue;
   uint32_t* ego_now;
   uint32_t* ego_last;
+  uint32_t* bits;
   int* acc;
   uint8_t* flags;
   int8_t* orient;
 };
+
+SG_DEV void group_sync(const Grp& g) {
+  if (g.G <= 32) __syncwarp(g.mask);
+  else asm volatile("bar.sync %0, %1;" ::"r"(g.bar_id), "r"(g.G) : "memory");
+}
+
+SG_DEV void setup_group(Grp& g, const SgScene& sc, const GroupLayout& L, unsigned char* smem,
+                        int gl, int s, int n) {
+  unsigned char* base = smem + (size_t)gl * L.bytes;
+  g.n = n; g.s = s; g.M = sc.n_slots; g.G = L.G; g.W = L.W; g.H = L.H; g.QCAP = L.QCAP;
+  g.bar_id = 1 + gl;
+  g.mask = 0xffffffffu;
+  if (L.G < 32) g.mask = ((1u << L.G) - 1u) << ((threadIdx.x & 31) / L.G * L.G);
+  g.nm = (int64_t)sc.n_scenarios * sc.n_slots;
+  g.i = (int64_t)n * sc.n_slots + s;
+  g.corners = (double*)base;
+  g.hcs = (double*)(base + L.off_hcs);
+  g.pedbuf = (double*)(base + L.off_ped);
+  g.egop = (double*)(base + L.off_ego);
+  g.aabb = (float4*)(base + L.off_aabb);
+  g.queue = (uint32_t*)(base + L.off_queue);
+  g.ego_now = (uint32_t*)(base + L.off_hits);
+  g.ego_last = g.ego_now + L.W;
+  g.bits = (uint32_t*)(base + L.off_bits);
+  g.acc = (int*)(base + L.off_acc);
+  g.flags = (uint8_t*)(base + L.off_flags);
+  g.orient = (int8_t*)(base + L.off_orient);
+}
+
+// n / d with a shared reciprocal r = 1/d (correctly rounded): one Newton correction on the
+// quotient (Markstein); equals the IEEE quotient except in rare last-bit cases
+SG_DEV double div_r(double n, double d, double r) {
+  const double q = n * r;
+  const double rem = __fma_rn(-q, d, n);
+  return __fma_rn(rem, r, q);
+}
 
 // conservative fp32 AABB of the fp64 corners, relative to the scenario origin (ox, oy)
 SG_DEV float4 make_aabb(const double* c, double ox, double oy) {
@@ -113,8 +161,9 @@ SG_DEV bool in_buffer(double x, double y, double r, double qx, double qy) {
   return true;
 }
 
+// PedestrianAgent._step + SocialForce._step + PedestrianController._step
 template <bool PED>
-SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const TickCtx& c,
+SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c,
                             const double pose[6], const double vel[6], double t, double prev_t,
                             double next_t, double sight_cos, int& goal, double force[2],
                             double& speed_io, double out[6]) {
@@ -208,97 +257,196 @@ SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const TickCtx&
   out[3] = heading;
 }
 
-// per-thread view of one entity's mutable state
-struct Ent {
-  double pose[6], vel[6], dist, speed;
-  double force[2];
-  double sd[2], ratio[2];
-  int cur_own, goal;
-  uint8_t present, rss_state, rss_last, collided;
-};
-
-SG_DEV void load_ent(const SgState& st, int64_t i, int64_t nm, Ent& e) {
-#pragma unroll
-  for (int f = 0; f < 6; ++f) { e.pose[f] = st.pose[f * nm + i]; e.vel[f] = st.vel[f * nm + i]; }
-  e.dist = st.dist[i];
-  e.speed = st.speed[i];
-  e.force[0] = st.force[i]; e.force[1] = st.force[nm + i];
-  e.sd[0] = st.safe_dist[i]; e.sd[1] = st.safe_dist[nm + i];
-  e.ratio[0] = st.safe_ratio[i]; e.ratio[1] = st.safe_ratio[nm + i];
-  e.cur_own = st.cur_own[i];
-  e.goal = st.goal_idx[i];
-  e.present = st.present[i];
-  e.rss_state = st.rss_state[i];
-  e.rss_last = st.rss_last[i];
-  e.collided = st.collided[i];
-}
-SG_DEV void store_ent(const SgState& st, int64_t i, int64_t nm, const Ent& e) {
-#pragma unroll
-  for (int f = 0; f < 6; ++f) { st.pose[f * nm + i] = e.pose[f]; st.vel[f * nm + i] = e.vel[f]; }
-  st.dist[i] = e.dist;
-  st.speed[i] = e.speed;
-  st.force[i] = e.force[0]; st.force[nm + i] = e.force[1];
-  st.safe_dist[i] = e.sd[0]; st.safe_dist[nm + i] = e.sd[1];
-  st.safe_ratio[i] = e.ratio[0]; st.safe_ratio[nm + i] = e.ratio[1];
-  st.cur_own[i] = e.cur_own;
-  st.goal_idx[i] = e.goal;
-  st.present[i] = e.present;
-  st.rss_state[i] = e.rss_state;
-  st.rss_last[i] = e.rss_last;
-  st.collided[i] = e.collided;
-}
-
-// stage this entity's box for the group: fp64 corners, ring orientation, fp32 AABB
-SG_DEV void publish_box(const TickCtx& c, const Ent& e, const double bw, const double bl,
-                        const double bcx, const double bcy, double ox, double oy, double my[8],
-                        int& my_or) {
-  if (e.present) {
-    box_points(e.pose[0], e.pose[1], e.pose[3], bw, bl, bcx, bcy, my);
+// ---------------------------------------------------------------------------------
+// staging
+// ---------------------------------------------------------------------------------
+template <bool RSS>
+SG_DEV void publish_box(const Grp& c, bool present, double x, double y, double h, double bw,
+                        double bl, double bcx, double bcy, double ox, double oy) {
+  float4 bb = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+  if (present) {
+    double sn, cs;
+    sincos(h, &sn, &cs);
+    // Entity.get_bounding_box_points (reference entity/base.py:100-138)
+    const double hx0 = bcx - 0.5 * bl, hx1 = bcx + 0.5 * bl;
+    const double hy0 = bcy + 0.5 * bw, hy1 = bcy - 0.5 * bw;
+    double my[8];
+    my[0] = x + (hx0 * cs + hy0 * -sn); my[1] = y + (hx0 * sn + hy0 * cs);
+    my[2] = x + (hx1 * cs + hy0 * -sn); my[3] = y + (hx1 * sn + hy0 * cs);
+    my[4] = x + (hx1 * cs + hy1 * -sn); my[5] = y + (hx1 * sn + hy1 * cs);
+    my[6] = x + (hx0 * cs + hy1 * -sn); my[7] = y + (hx0 * sn + hy1 * cs);
 #pragma unroll
     for (int f = 0; f < 8; ++f) c.corners[f * c.G + c.s] = my[f];
-    my_or = quad_orientation(my);
-    c.orient[c.s] = (int8_t)my_or;
-    c.aabb[c.s] = make_aabb(my, ox, oy);
-  } else {
-    c.aabb[c.s] = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+    if (RSS) { c.hcs[c.s] = cs; c.hcs[c.G + c.s] = sn; }
+    c.orient[c.s] = (int8_t)quad_orientation(my);
+    bb = make_aabb(my, ox, oy);
   }
+  c.aabb[c.s] = bb;
+  if (c.s < c.H + 1) c.aabb[c.M + c.s] = bb;
 }
 
-// RSSDistances.__call__ for one hazard entity (reference metrics/rss/callback.py:57-122)
-SG_DEV void rss_entity(const SgScene& sc, const SgParams& p, const TickCtx& c, Ent& e,
-                       const double my[8], double bw, double bl, int ego_slot, double t, int parity) {
-  e.rss_last = SG_RSS_NONE;
-  if (t == 0.0) return;  // :72
-  if (c.s == ego_slot || !e.present) return;
-  if (!(c.flags[c.G + 0] & 1)) return;  // ego absent (reference raises KeyError)
-  const double ex = c.egobuf[0], ey = c.egobuf[1], ehd = c.egobuf[2];
-  const double evx = c.egobuf[3], evy = c.egobuf[4];
+// ego parameters in its own frame (reference metrics/rss/callback.py:73-97, 340-386)
+SG_DEV void publish_ego(const Grp& c, bool present, const double pose[6], const double vel[6],
+                        double bw, double bl) {
   double es, ec;
-  sincos(ehd, &es, &ec);
+  sincos(pose[3], &es, &ec);
   const double eh[2] = {ec, es};
   double einv[2];
   inverse_direction(eh, einv);
-  const double epos[2] = {ex, ey};
-  double ecorn[8];
-#pragma unroll
-  for (int f = 0; f < 8; ++f) ecorn[f] = c.corners[f * c.G + ego_slot];
-  const int64_t ei = (int64_t)c.n * c.M + ego_slot;
-  RssEnt ego, haz;
-  rss_entity_params(ex, ey, ehd, evx, evy, ecorn, sc.box[ei], sc.box[c.nm + ei], eh, einv, epos, ego);
-  rss_entity_params(e.pose[0], e.pose[1], e.pose[3], e.vel[0], e.vel[1], my, bw, bl, eh, einv, epos, haz);
-  double sd[2];
-  sd[1] = fabs(safe_longitudinal_distance(p, ego, haz));  // :101-103
-  sd[0] = fabs(safe_lateral_distance(p, ego, haz));
-  e.sd[0] = sd[0];
-  e.sd[1] = sd[1];
-  safe_ratios(ego, haz, e.ratio);
-  e.rss_last = (uint8_t)unsafe_distance(ego, haz, e.rss_state, sd);
-  const int found = (e.rss_state >> 2) & 3;  // RSS metric latch, rss.py:71-103
-  if (found) atomicOr(&c.acc[parity * 4 + 3], found == 2 ? 1 : 2);
+  c.egop[EGO_X] = pose[0]; c.egop[EGO_Y] = pose[1];
+  c.egop[EGO_C] = ec; c.egop[EGO_S] = es;
+  c.egop[EGO_INV0] = einv[0]; c.egop[EGO_INV1] = einv[1];
+  c.egop[EGO_HD0] = dot2(ec, es, einv[0], einv[1]);
+  c.egop[EGO_HD1] = dot2(ec, es, ec, es);
+  const double v0 = dot2(vel[0], vel[1], einv[0], einv[1]), v1 = dot2(vel[0], vel[1], ec, es);
+  c.egop[EGO_V0] = v0; c.egop[EGO_V1] = v1;
+  c.egop[EGO_VNORM] = norm2(v0, v1);
+  c.egop[EGO_W] = bw; c.egop[EGO_L] = bl;
+  c.egop[EGO_PRESENT] = present ? 1.0 : 0.0;
 }
 
-// exact narrow phase for one AABB-surviving pair; both quads are read from the group's
-// staged corners so the caller's registers stay free (out of line: it is the rare path)
+// ---------------------------------------------------------------------------------
+// RSS (reference metrics/rss/callback.py)
+// ---------------------------------------------------------------------------------
+__device__ __noinline__ bool rss_box_hits_buffer(const double* box, double slat, double slong) {
+  const double buffer[8] = {slat, slong, -slat, slong, -slat, -slong, slat, -slong};
+  return quads_intersect(box, quad_orientation(box), buffer, quad_orientation(buffer));
+}
+__device__ __noinline__ bool rss_box_hits_segment(const double* box, double x0, double y0,
+                                                  double x1, double y1) {
+  const double seg[4] = {x0, y0, x1, y1};
+  return quad_intersects_segment(box, quad_orientation(box), seg);
+}
+
+// RSSDistances.__call__ for one hazard (callback.py:57-122).  The geometric predicates are
+// answered by exact comparisons where those decide (bounding ranges disjoint => no
+// intersection; a corner inside the closed rectangle => intersection) and by the exact
+// orientation predicates otherwise, so every record equals the reference's.
+SG_DEV int rss_hazard(const SgParams& p, const Grp& c, double x, double y, double vx, double vy,
+                      double bw, double bl, uint8_t& state, double sd[2], double ratio[2]) {
+  const double* E = c.egop;
+  const double eh[2] = {E[EGO_C], E[EGO_S]}, einv[2] = {E[EGO_INV0], E[EGO_INV1]};
+  const double dirc = c.hcs[c.s], dirs = c.hcs[c.G + c.s];
+  // get_entity_parameters (callback.py:340-386) with coord_change (rss_utils.py:24-45)
+  const double d0 = x - E[EGO_X], d1 = y - E[EGO_Y];
+  const double pos0 = dot2(d0, d1, einv[0], einv[1]), pos1 = dot2(d0, d1, eh[0], eh[1]);
+  const double hd0 = dot2(dirc, dirs, einv[0], einv[1]), hd1 = dot2(dirc, dirs, eh[0], eh[1]);
+  const double v0 = dot2(vx, vy, einv[0], einv[1]), v1 = dot2(vx, vy, eh[0], eh[1]);
+  double box[8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double c0 = c.corners[(2 * q) * c.G + c.s] - E[EGO_X];
+    const double c1 = c.corners[(2 * q + 1) * c.G + c.s] - E[EGO_Y];
+    box[2 * q] = dot2(c0, c1, einv[0], einv[1]);
+    box[2 * q + 1] = dot2(c0, c1, eh[0], eh[1]);
+  }
+  const double eW = E[EGO_W], eL = E[EGO_L];
+  const double CLR = p.rss_min_safe_clearance, RT = p.rss_response_time;
+  // safe_longitudinal_distance (callback.py:230-269); ego position is [0, 0]
+  double slong;
+  {
+    const double dp = dot2(E[EGO_HD0], E[EGO_HD1], hd0, hd1);
+    const double a = fabs(p.rss_max_long_accel * dp);
+    bool early = false;
+    double dd = 0;
+    if (dp > 0) {
+      double vf, vr;
+      const double hv = dot2(v0, v1, E[EGO_HD0], E[EGO_HD1]);
+      if (0.0 > pos1) { vf = E[EGO_VNORM]; vr = hv; } else { vf = hv; vr = E[EGO_VNORM]; }
+      if (vr == 0.0) early = true;
+      else dd = long_dist_same_direction(vf, vr, a, RT, p.rss_min_long_accel);
+    } else {
+      const double v1e = fabs(dot2(E[EGO_V0], E[EGO_V1], E[EGO_HD0], E[EGO_HD1]));
+      const double v2e = -fabs(dot2(v0, v1, E[EGO_HD0], E[EGO_HD1]));
+      if (np_sign(pos1) == np_sign(v1)) early = true;
+      else dd = long_dist_opp_direction(v1e, v2e, a, RT, p.rss_min_long_accel);
+    }
+    slong = fabs(early ? CLR + 0.5 * eL : dd + CLR + 0.5 * eL);
+  }
+  // safe_lateral_distance (callback.py:271-302)
+  double slat;
+  {
+    double v = v0;
+    const double ehd[2] = {E[EGO_HD0], E[EGO_HD1]};
+    double inv[2];
+    inverse_direction(ehd, inv);
+    const double k = fabs(dot2(inv[0], inv[1], hd0, hd1));
+    const double amax = p.rss_max_long_accel * k, amin = p.rss_min_long_accel * k;
+    double dd;
+    bool early = false;
+    if (np_sign(-pos0) == np_sign(v)) {
+      v = fabs(v);
+      if (v == 0.0) early = true;
+      dd = early ? 0.0 : lat_dist(v, amax, amin, RT);
+    } else {
+      dd = 0;
+    }
+    slat = fabs(early ? CLR + 0.5 * eW : dd + CLR + 0.5 * eW);
+  }
+  sd[0] = slat;
+  sd[1] = slong;
+  // safe_ratios (callback.py:124-166)
+  {
+    const double hdv[2] = {hd0, hd1};
+    double inv[2];
+    inverse_direction(hdv, inv);
+    const double wl_inv = fabs(dot2(bw, bl, inv[0], inv[1]));
+    const double wl_dir = fabs(dot2(bw, bl, hd0, hd1));
+    const double actual_lat = py_max(1e-6, fabs(pos0) - 0.5 * eW - 0.5 * wl_inv);
+    const double actual_long = py_max(1e-6, fabs(pos1) - 0.5 * eL - 0.5 * wl_dir);
+    ratio[0] = fabs(actual_lat / (0.5 * eW));
+    ratio[1] = fabs(actual_long / (0.5 * eL));
+  }
+  // unsafe_distance (callback.py:168-228)
+  if ((state >> 2) & 3) return SG_RSS_FOUND;
+  const double bxmin = fmin(fmin(box[0], box[2]), fmin(box[4], box[6]));
+  const double bxmax = fmax(fmax(box[0], box[2]), fmax(box[4], box[6]));
+  const double bymin = fmin(fmin(box[1], box[3]), fmin(box[5], box[7]));
+  const double bymax = fmax(fmax(box[1], box[3]), fmax(box[5], box[7]));
+  bool inter;
+  if (bxmin > slat || bxmax < -slat || bymin > slong || bymax < -slong) {
+    inter = false;  // bounding ranges disjoint: separated
+  } else {
+    bool corner_in = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      corner_in = corner_in || (fabs(box[2 * q]) <= slat && fabs(box[2 * q + 1]) <= slong);
+    inter = corner_in || rss_box_hits_buffer(box, slat, slong);
+  }
+  if (inter) {
+    const int marker = state & 3;
+    if (marker == 1) { state |= 2 << 2; return SG_RSS_UNSAFE_LONGITUDINAL; }
+    if (marker == 2) { state |= 1 << 2; return SG_RSS_UNSAFE_LATERAL; }
+    const double ed[2] = {eW, eL};
+    double inv[2];
+    inverse_direction(ed, inv);
+    const double lhs = fabs(fabs(pos0) - fabs(dot2(pos0, pos1, ed[0], ed[1]))) / slat;
+    const double rhs = fabs(fabs(pos1 - dot2(pos0, pos1, inv[0], inv[1])) / slong);
+    if (lhs > rhs) { state |= 2 << 2; return SG_RSS_UNSAFE_LONGITUDINAL; }
+    state |= 1 << 2;
+    return SG_RSS_UNSAFE_LATERAL;
+  }
+  // write_intersections (callback.py:304-338) against generate_buffer's segments (:429-451)
+  const double L100 = 100 * slong, W100 = 100 * slat;
+  bool lat = false, lon = false;
+  if (!(bxmin > slat || bxmax < -slat || bymin > L100 || bymax < -L100))
+    lat = rss_box_hits_segment(box, slat, L100, -slat, 100 * -slong) ||
+          rss_box_hits_segment(box, -slat, L100, slat, 100 * -slong);
+  if (!(bxmin > W100 || bxmax < -W100)) {
+    if (!(bymin > slong || bymax < slong)) lon = rss_box_hits_segment(box, W100, slong, 100 * -slat, slong);
+    if (!lon && !(bymin > -slong || bymax < -slong))
+      lon = rss_box_hits_segment(box, 100 * -slat, -slong, W100, -slong);
+  }
+  if (lat && lon) return SG_RSS_BOTH;
+  if (lat) { state = (uint8_t)((state & ~3) | 1); return SG_RSS_LATERAL; }
+  if (lon) { state = (uint8_t)((state & ~3) | 2); return SG_RSS_LONGITUDINAL; }
+  return SG_RSS_SAFE;
+}
+
+// ---------------------------------------------------------------------------------
+// collisions (reference state/utils.py:10-49, utils.py:28-62)
+// ---------------------------------------------------------------------------------
+// exact narrow phase for one AABB-surviving pair, both quads read from the staged corners
 __device__ __noinline__ bool pair_collides(const double* corners, const int8_t* orient, int G,
                                            int a, int b) {
   double qa[8], qb[8];
@@ -313,57 +461,73 @@ __device__ __noinline__ bool pair_collides(const double* corners, const int8_t* 
   return quads_intersect(qa, orient[a], qb, orient[b]);
 }
 
-// state.collisions() row of this entity (reference state/utils.py:10-49, utils.py:28-62)
-SG_DEV void collision_sweep(const SgParams& p, const SgState& st, const TickCtx& c, bool present,
-                            uint8_t& collided, int ego_slot, int first_slot, int parity) {
-  const bool matrix = (p.features & SG_FEAT_COLL_MATRIX) != 0;
-  uint32_t* row = matrix ? st.coll_mask + ((int64_t)c.n * c.M + c.s) * c.W : nullptr;
-  if (!present) {
-    if (matrix) for (int w = 0; w < c.W; ++w) row[w] = 0;
-    return;
-  }
-  const float4 mb = c.aabb[c.s];
-  int npairs = 0, first_j = -1;
-  bool any = false;
-  for (int w = 0; w < c.W; ++w) {
-    uint32_t word = 0;
-    const int j0 = w * 32, j1 = min(j0 + 32, c.M);
-#pragma unroll 4
-    for (int j = j0; j < j1; ++j) {
-      const float4 ob = c.aabb[j];
-      // closed-interval overlap of conservative bounds (STRtree's envelope filter is closed too)
-      if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w && j != c.s) {
-        if (pair_collides(c.corners, c.orient, c.G, c.s, j)) word |= 1u << (j - j0);
-      }
-    }
-    if (matrix) row[w] = word;
-    if (word) {
-      any = true;
-      if (c.s == ego_slot) c.ego_now[w] = word;
-      // pairs (s, j) with j > s are counted by the lower slot
-      uint32_t gt = word;
-      if (c.s >= j0 + 31) gt = 0;
-      else if (c.s >= j0) gt &= ~((2u << (c.s - j0)) - 1u);
-      if (gt) {
-        npairs += __popc(gt);
-        if (first_j < 0) first_j = j0 + __ffs(gt) - 1;
-      }
-    }
-  }
-  if (any) {
-    collided = 1;
-    if (c.s == first_slot) c.acc[parity * 4 + 2] = 1;
-  }
-  if (npairs) {
-    atomicAdd(&c.acc[parity * 4 + 0], npairs);
-    atomicMin(&c.acc[parity * 4 + 1], (c.s << 16) | first_j);
+SG_DEV void record_pair(const SgParams& p, const SgState& st, const Grp& c, int a, int b,
+                        int ego_slot, int first_slot, int parity) {
+  if (!pair_collides(c.corners, c.orient, c.G, a, b)) return;
+  const int lo = min(a, b), hi = max(a, b);
+  int* acc = c.acc + parity * ACC_N;
+  atomicAdd(&acc[ACC_NPAIRS], 1);
+  atomicMin(&acc[ACC_FIRST_PAIR], (lo << 16) | hi);
+  if (lo == first_slot || hi == first_slot) acc[ACC_FIRST_HIT] = 1;
+  uint32_t* bits = c.bits + parity * c.W;
+  atomicOr(&bits[lo >> 5], 1u << (lo & 31));
+  atomicOr(&bits[hi >> 5], 1u << (hi & 31));
+  if (lo == ego_slot) atomicOr(&c.ego_now[hi >> 5], 1u << (hi & 31));
+  if (hi == ego_slot) atomicOr(&c.ego_now[lo >> 5], 1u << (lo & 31));
+  if (p.features & SG_FEAT_COLL_MATRIX) {
+    uint32_t* rows = st.coll_mask + (int64_t)c.n * c.M * c.W;
+    atomicOr(&rows[(int64_t)lo * c.W + (hi >> 5)], 1u << (hi & 31));
+    atomicOr(&rows[(int64_t)hi * c.W + (lo >> 5)], 1u << (lo & 31));
   }
 }
 
+// circular half sweep over the staged AABBs; survivors go to the scenario's queue
+SG_DEV void broad_phase(const SgParams& p, const SgState& st, const Grp& c, int ego_slot,
+                        int first_slot, int parity) {
+  const float4 mb = c.aabb[c.s];
+  const float4* nb = c.aabb + c.s + 1;
+  int* acc = c.acc + parity * ACC_N;
+  for (int d0 = 0; d0 < c.H; d0 += 32) {
+    const int dn = min(32, c.H - d0);
+    uint32_t hits = 0;
+    if (dn == 32) {
+#pragma unroll
+      for (int dd = 0; dd < 32; ++dd) {
+        const float4 ob = nb[d0 + dd];
+        // closed-interval overlap of conservative bounds (STRtree's envelope filter is closed too)
+        const bool h = mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w;
+        hits |= (h ? 1u : 0u) << dd;
+      }
+    } else {
+      for (int dd = 0; dd < dn; ++dd) {
+        const float4 ob = nb[d0 + dd];
+        const bool h = mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w;
+        hits |= (h ? 1u : 0u) << dd;
+      }
+    }
+    while (hits) {
+      const int dd = __ffs(hits) - 1;
+      hits &= hits - 1;
+      const int d = d0 + dd + 1;
+      int j = c.s + d;
+      if (j >= c.M) j -= c.M;
+      if (2 * d == c.M && c.s > j) continue;  // the antipodal pair is seen from both ends
+      const int q = atomicAdd(&acc[ACC_QCOUNT], 1);
+      if (q < c.QCAP) c.queue[q] = ((uint32_t)c.s << 16) | (uint32_t)j;
+      else record_pair(p, st, c, c.s, j, ego_slot, first_slot, parity);  // queue full: do it here
+    }
+  }
+}
+
+// mutable per-entity state kept in registers across ticks
+struct Ent {
+  double pose[6], vel[6], dist, speed;
+  bool present;
+};
+
 template <bool PED, bool RSS, int MAXT>
 __global__ void __launch_bounds__(MAXT)
-sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, GroupLayout L,
-                  int reset) {
+sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, GroupLayout L) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int G = L.G, M = sc.n_slots, W = L.W;
   const int gpb = blockDim.x / G;  // scenario groups per CTA
@@ -371,24 +535,8 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   const int s = threadIdx.x - gl * G;
   const int n = blockIdx.x * gpb + gl;
   if (gl >= gpb || n >= sc.n_scenarios) return;
-  unsigned mask = 0xffffffffu;
-  if (G < 32) mask = ((G == 32 ? 0u : (1u << G)) - 1u) << ((threadIdx.x & 31) / G * G);
-  const int bar_id = 1 + gl;
-
-  unsigned char* base = smem + (size_t)gl * L.bytes;
-  TickCtx c;
-  c.n = n; c.s = s; c.M = M; c.G = G; c.W = W;
-  c.nm = (int64_t)sc.n_scenarios * M;
-  c.i = (int64_t)n * M + s;
-  c.corners = (double*)base;
-  c.pedbuf = (double*)(base + L.off_ped);
-  c.egobuf = (double*)(base + L.off_ego);
-  c.aabb = (float4*)(base + L.off_aabb);
-  c.ego_now = (uint32_t*)(base + L.off_hits);
-  c.ego_last = c.ego_now + W;
-  c.acc = (int*)(base + L.off_acc);
-  c.flags = (uint8_t*)(base + L.off_flags);
-  c.orient = (int8_t*)(base + L.off_orient);
+  Grp c;
+  setup_group(c, sc, L, smem, gl, s, n);
 
   const bool live = s < M;  // padding threads only take part in barriers
   const int64_t i = c.i, nm = c.nm;
@@ -398,6 +546,8 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   const bool need_coll = (p.features & SG_FEAT_COLLISIONS) ||
                          (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
   const bool feat_rss = RSS && (p.features & SG_FEAT_RSS);
+  const bool matrix = (p.features & SG_FEAT_COLL_MATRIX) != 0;
+  const bool exact_div = kind <= SG_KIND_AGENT_REPLAY;  // replay kinds keep IEEE quotients
 
   double bw = 1, bl = 1, bcx = 0, bcy = 0;
   const double* rows = nullptr;
@@ -408,112 +558,81 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     K = (int)(sc.traj_off[i + 1] - r0);
     rows = sc.traj_rows + r0 * 7;
   }
-  const double traj_min_t = K ? __ldg(rows) : 0.0, traj_max_t = K ? __ldg(rows + (int64_t)(K - 1) * 7) : 0.0;
-  // scenario origin for the fp32 bounds: the ego's start position
-  double ox, oy;
+  const double traj_min_t = K ? __ldg(rows) : 0.0;
+  const double traj_max_t = K ? __ldg(rows + (int64_t)(K - 1) * 7) : 0.0;
+  const double rcp_bl = 1.0 / bl;
+  double ox, oy;  // scenario origin for the fp32 bounds: the ego's first control point
   {
     const int64_t er = sc.traj_off[(int64_t)n * M + ego_slot];
     ox = __ldg(sc.traj_rows + er * 7 + 1);
     oy = __ldg(sc.traj_rows + er * 7 + 2);
   }
   const double sight_cos = PED ? cos(p.sf_sight_angle / 2 * M_PI / 180) : 0.0;
+  const double length = sc.length[n];
 
+  // ---- load the State rows ------------------------------------------------------------
   Ent e;
-  double t, prev_t;
-  int tick, cur_union;
-  bool done;
-  double avg = 0, avg_t = 0, mx = 0, egod = 0;  // ego metrics (ego thread only)
-  int first_tick = -1, fp0 = -1, fp1 = -1;      // leader only
-  long long pair_ticks = 0;
-  int rss_flags = 0;
-
-  if (reset) {
-    // State.reset(t0), reference state/state.py:106-143 (+ controller/metric resets)
-    t = sc.t0[n];
-    memset(&e, 0, sizeof(e));
-    e.cur_own = 1;
-    e.rss_last = SG_RSS_NONE;
-    e.ratio[0] = INFINITY; e.ratio[1] = INFINITY;  // callback.py:53-55
-    if (kind != SG_KIND_EMPTY) {
-      const int mode = (K == 1) ? EXT_TRUE : (p.persist ? EXT_CLAMP : EXT_NONE);  // :123-129
-      int cur = 0;
-      e.present = position_at_t(rows, K, t, mode, cur, e.pose);
-      if (e.present) velocity_at_t(rows, K, t, e.vel);  // :132
-      else {
-#pragma unroll
-        for (int f = 0; f < 6; ++f) e.pose[f] = 0.0;
-      }
-      if (kind == SG_KIND_VEHICLE) e.speed = norm2(e.vel[0], e.vel[1]);  // controller.py:100-103
-    }
-    prev_t = t - 0.1;  // :135
-    tick = 0;
-    done = false;
-    cur_union = 1;
-    if (s < W) c.ego_last[s] = 0;
-  } else {
-    t = st.t[n];
-    prev_t = st.prev_t[n];
-    tick = st.tick[n];
-    done = st.done[n] != 0;
-    cur_union = st.cur_union[n];
-    if (live) load_ent(st, i, nm, e); else memset(&e, 0, sizeof(e));
-    if (s == ego_slot) {
-      avg = st.ego_avg_speed[n]; avg_t = st.ego_avg_t[n]; mx = st.ego_max_speed[n]; egod = st.ego_dist[n];
-    }
-    if (s == 0) {
-      first_tick = st.first_coll_tick[n]; fp0 = st.first_coll_pair[2 * n]; fp1 = st.first_coll_pair[2 * n + 1];
-      pair_ticks = st.n_pair_ticks[n];
-      rss_flags = st.rss_flags[n];
-    }
-    if (s < W) c.ego_last[s] = st.ego_hits[(int64_t)n * W + s];
-  }
-  if (s < W) c.ego_now[s] = 0;
-  if (s == 0) {
-    for (int q = 0; q < 8; ++q) c.acc[q] = 0;
-    c.acc[1] = 0x7fffffff; c.acc[5] = 0x7fffffff;
-  }
-  // stage the "old" state the pedestrians' sensors read in the first tick
+  double t = st.t[n], prev_t = st.prev_t[n];
+  int tick = st.tick[n], cur_union = st.cur_union[n];
+  bool done = st.done[n] != 0;
+  int cur_own = 1, goal = 0;
+  double force[2] = {0, 0}, sd[2] = {0, 0}, ratio[2] = {0, 0};
+  uint8_t rss_state = 0, rss_last = SG_RSS_NONE, collided = 0;
   if (live) {
+#pragma unroll
+    for (int f = 0; f < 6; ++f) { e.pose[f] = st.pose[f * nm + i]; e.vel[f] = st.vel[f * nm + i]; }
+    e.dist = st.dist[i];
+    e.speed = st.speed[i];
+    e.present = st.present[i] != 0;
+    cur_own = st.cur_own[i];
+    collided = st.collided[i];
+    if (PED) { goal = st.goal_idx[i]; force[0] = st.force[i]; force[1] = st.force[nm + i]; }
+    if (RSS) {
+      rss_state = st.rss_state[i]; rss_last = st.rss_last[i];
+      sd[0] = st.safe_dist[i]; sd[1] = st.safe_dist[nm + i];
+      ratio[0] = st.safe_ratio[i]; ratio[1] = st.safe_ratio[nm + i];
+    }
+  } else {
+#pragma unroll
+    for (int f = 0; f < 6; ++f) { e.pose[f] = 0; e.vel[f] = 0; }
+    e.dist = 0; e.speed = 0; e.present = false;
+  }
+  double avg = 0, avg_t = 0, mx = 0, egod = 0;  // ego metrics (ego thread only)
+  if (s == ego_slot) {
+    avg = st.ego_avg_speed[n]; avg_t = st.ego_avg_t[n]; mx = st.ego_max_speed[n]; egod = st.ego_dist[n];
+  }
+  int first_tick = -1, fp0 = -1, fp1 = -1, rss_flags = 0;  // leader only
+  long long pair_ticks = 0;
+  if (s == 0) {
+    first_tick = st.first_coll_tick[n]; fp0 = st.first_coll_pair[2 * n]; fp1 = st.first_coll_pair[2 * n + 1];
+    pair_ticks = st.n_pair_ticks[n];
+    rss_flags = st.rss_flags[n];
+    for (int q = 0; q < 2 * ACC_N; ++q) c.acc[q] = 0;
+    c.acc[ACC_FIRST_PAIR] = 0x7fffffff; c.acc[ACC_N + ACC_FIRST_PAIR] = 0x7fffffff;
+  }
+  if (s < W) {
+    c.ego_last[s] = st.ego_hits[(int64_t)n * W + s];
+    c.ego_now[s] = 0;
+    c.bits[s] = 0; c.bits[W + s] = 0;
+  }
+  if (live) {  // the "old" state the pedestrians' sensors read in the first tick
     c.flags[s] = (uint8_t)((e.present ? 1 : 0) | (etype << 1));
     if (PED) {
       c.pedbuf[s] = e.pose[0]; c.pedbuf[G + s] = e.pose[1];
       c.pedbuf[2 * G + s] = e.vel[0]; c.pedbuf[3 * G + s] = e.vel[1];
     }
   }
-  double my[8];
-  int my_or = 0;
-  int parity = 0;
-
-  if (reset) {
-    // update_callbacks() at reset (state.py:137-139) and Metric.reset (metrics/trajectory.py:13-18)
-    if (feat_rss) {
-      if (live) publish_box(c, e, bw, bl, bcx, bcy, ox, oy, my, my_or);
-      if (s == ego_slot) {
-        c.egobuf[0] = e.pose[0]; c.egobuf[1] = e.pose[1]; c.egobuf[2] = e.pose[3];
-        c.egobuf[3] = e.vel[0]; c.egobuf[4] = e.vel[1];
-        c.flags[G] = e.present;
-      }
-      group_sync(G, bar_id, mask);
-      if (live) rss_entity(sc, p, c, e, my, bw, bl, ego_slot, t, 0);
-      group_sync(G, bar_id, mask);
-      if (s == 0) { rss_flags |= c.acc[3]; c.acc[3] = 0; }
-    }
-    if (s == ego_slot) {
-      const double sp = norm3(e.vel[0], e.vel[1], e.vel[2]);
-      avg = sp; avg_t = 0.0; mx = sp; egod = 0.0;
-    }
-    if (st.trace_cap > 0 && live) {
-      st.trace_present[i] = e.present;
-#pragma unroll
-      for (int f = 0; f < 6; ++f) st.trace_pose[f * nm + i] = e.pose[f];
-      if (s == 0) st.trace_t[n] = t;
-    }
-    n_ticks = 0;
-  }
-  group_sync(G, bar_id, mask);
+  group_sync(c);
 
   int limit = n_ticks < 0 ? p.max_ticks : n_ticks;
   if (in.actions && limit > in.n_action_ticks) limit = in.n_action_ticks;
+  int parity = 0;
+  // VehicleAction table: the next tick's row is fetched one tick ahead
+  double a_accel = 0, a_steer = 0;
+  if (kind == SG_KIND_VEHICLE && limit > 0 && !done) {
+    a_accel = __ldcs(in.actions + i);
+    a_steer = __ldcs(in.actions + nm + i);
+  }
 
   for (int k = 0; k < limit && !done; ++k) {
     // ---------------- phase A: agents / batch replay produce the new poses ----------------
@@ -521,20 +640,24 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     double np_[6];
     bool newpres = false;
     double newspeed = e.speed;
+    const double cur_accel = a_accel, cur_steer = a_steer;
+    if (kind == SG_KIND_VEHICLE && k + 1 < limit) {  // fetch the next tick's action row early
+      a_accel = __ldcs(in.actions + ((int64_t)(k + 1) * 2 + 0) * nm + i);
+      a_steer = __ldcs(in.actions + ((int64_t)(k + 1) * 2 + 1) * nm + i);
+    }
     if (kind >= SG_KIND_AGENT_REPLAY) {  // scenario_gym.py:233-244
       if (e.present) {
         if (kind == SG_KIND_AGENT_REPLAY) {  // agent.py:125-128, extrapolate=(False, False)
-          position_at_t(rows, K, next_t, EXT_CLAMP, e.cur_own, np_);
+          position_at_t(rows, K, next_t, EXT_CLAMP, cur_own, np_);
           newpres = true;
         } else if (kind == SG_KIND_VEHICLE) {  // VehicleController._step, controller.py:105-140
-          double accel = in.actions[((int64_t)k * 2 + 0) * nm + i];
-          double steer = in.actions[((int64_t)k * 2 + 1) * nm + i];
-          accel = np_clip(accel, -p.veh_max_accel, p.veh_max_accel);
-          steer = np_clip(steer, -p.veh_max_steer, p.veh_max_steer);
+          const double accel = np_clip(cur_accel, -p.veh_max_accel, p.veh_max_accel);
+          const double steer = np_clip(cur_steer, -p.veh_max_steer, p.veh_max_steer);
           const double dt = next_t - t;
           double sh, ch;
           sincos(e.pose[3], &sh, &ch);
-          const double dx = e.speed * ch, dy = e.speed * sh, dh = e.speed * tan(steer) / bl;
+          const double dx = e.speed * ch, dy = e.speed * sh;
+          const double dh = div_r(e.speed * tan(steer), bl, rcp_bl);
 #pragma unroll
           for (int f = 0; f < 6; ++f) np_[f] = e.pose[f];
           np_[0] += dx * dt;
@@ -546,8 +669,8 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
           newspeed = ns;
           newpres = true;
         } else if (kind == SG_KIND_PEDESTRIAN) {
-          pedestrian_step<PED>(sc, p, c, e.pose, e.vel, t, prev_t, next_t, sight_cos, e.goal,
-                               e.force, newspeed, np_);
+          pedestrian_step<PED>(sc, p, c, e.pose, e.vel, t, prev_t, next_t, sight_cos, goal, force,
+                               newspeed, np_);
           newpres = true;
         } else {  // SG_KIND_HOST
           if (in.host_present && in.host_present[i]) {
@@ -561,11 +684,10 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
           }
         }
       } else if (traj_min_t >= t) {  // :240-244 agent initialised at its start position
-        position_at_t(rows, K, next_t, EXT_CLAMP, e.cur_own, np_);
+        position_at_t(rows, K, next_t, EXT_CLAMP, cur_own, np_);
         newpres = true;
       }
     } else if (kind == SG_KIND_REPLAY) {  // BatchReplayEntity.step, entity/batch.py:34-53
-      // every thread advances the scenario's shared cursor identically
       const int64_t u0 = sc.union_off[n];
       const int UK = (int)(sc.union_off[n + 1] - u0);
       const double* ts = sc.union_t + u0;
@@ -577,7 +699,7 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
         } else if (next_t > __ldg(ts + UK - 1)) {
 #pragma unroll
           for (int f = 0; f < 6; ++f) np_[f] = __ldg(X + ((int64_t)(UK - 1) * 6 + f) * M + s);
-        } else {
+        } else {  // every thread advances the scenario's shared cursor identically
           cur_union = search_left_cursor(ts, 1, UK, next_t, cur_union);
           const double x_lo = __ldg(ts + cur_union - 1), x_hi = __ldg(ts + cur_union);
           const double w1 = (next_t - x_lo) / (x_hi - x_lo), w0 = (x_hi - next_t) / (x_hi - x_lo);
@@ -603,12 +725,16 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
         position_at_t(rows, K, prev_t, EXT_TRUE, cur, prev);
       }
       double d[6];
+      if (exact_div) {
 #pragma unroll
-      for (int f = 0; f < 6; ++f) {
-        d[f] = np_[f] - prev[f];
-        e.vel[f] = d[f] / dt;
-        e.pose[f] = np_[f];
+        for (int f = 0; f < 6; ++f) { d[f] = np_[f] - prev[f]; e.vel[f] = d[f] / dt; }
+      } else {
+        const double rdt = 1.0 / dt;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) { d[f] = np_[f] - prev[f]; e.vel[f] = div_r(d[f], dt, rdt); }
       }
+#pragma unroll
+      for (int f = 0; f < 6; ++f) e.pose[f] = np_[f];
       e.dist += norm3(d[0], d[1], d[2]);
       e.speed = newspeed;
     }
@@ -619,31 +745,54 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       for (int f = 0; f < 6; ++f) st.trace_pose[((int64_t)tick * 6 + f) * nm + i] = e.pose[f];
       if (s == 0) st.trace_t[(int64_t)tick * sc.n_scenarios + n] = t;
     }
-    if ((need_coll || feat_rss) && live) publish_box(c, e, bw, bl, bcx, bcy, ox, oy, my, my_or);
-    if (s == ego_slot) {
-      c.egobuf[0] = e.pose[0]; c.egobuf[1] = e.pose[1]; c.egobuf[2] = e.pose[3];
-      c.egobuf[3] = e.vel[0]; c.egobuf[4] = e.vel[1];
-      c.flags[G] = e.present;
+    if (live) {
+      if (need_coll || feat_rss)
+        publish_box<RSS>(c, e.present, e.pose[0], e.pose[1], e.pose[3], bw, bl, bcx, bcy, ox, oy);
+      if (matrix) {
+        uint32_t* row = st.coll_mask + ((int64_t)n * M + s) * W;
+        for (int w = 0; w < W; ++w) row[w] = 0;
+      }
     }
-    group_sync(G, bar_id, mask);
-    // ---------------- phase B: callbacks (RSS) + collisions --------------------------------
+    if (RSS && feat_rss && s == ego_slot) publish_ego(c, e.present, e.pose, e.vel, bw, bl);
+    if (matrix) __threadfence_block();
+    group_sync(c);
+    // ---------------- phase B1: callbacks (RSS) + broad phase -------------------------------
     if (live) {
       c.flags[s] = (uint8_t)((e.present ? 1 : 0) | (etype << 1));
       if (PED) {
         c.pedbuf[s] = e.pose[0]; c.pedbuf[G + s] = e.pose[1];
         c.pedbuf[2 * G + s] = e.vel[0]; c.pedbuf[3 * G + s] = e.vel[1];
       }
-      if (feat_rss) rss_entity(sc, p, c, e, my, bw, bl, ego_slot, t, parity);
-      if (need_coll) collision_sweep(p, st, c, e.present != 0, e.collided, ego_slot, first_slot, parity);
+      if (RSS && feat_rss) {  // RSSDistances.__call__, callback.py:57-122
+        rss_last = SG_RSS_NONE;
+        if (t != 0.0 && s != ego_slot && e.present && c.egop[EGO_PRESENT] != 0.0) {
+          rss_last = (uint8_t)rss_hazard(p, c, e.pose[0], e.pose[1], e.vel[0], e.vel[1], bw, bl,
+                                         rss_state, sd, ratio);
+          const int found = (rss_state >> 2) & 3;  // RSS metric latch, rss.py:71-103
+          if (found) atomicOr(&c.acc[parity * ACC_N + ACC_RSS], found == 2 ? 1 : 2);
+        }
+      }
+      if (need_coll && e.present) broad_phase(p, st, c, ego_slot, first_slot, parity);
     }
-    group_sync(G, bar_id, mask);
+    group_sync(c);
+    // ---------------- phase B2: exact narrow phase on the queued pairs ----------------------
+    int* acc = c.acc + parity * ACC_N;
+    const int nq = min(acc[ACC_QCOUNT], c.QCAP);
+    if (nq > 0) {
+      for (int q = s; q < nq; q += G) {
+        const uint32_t pr = c.queue[q];
+        record_pair(p, st, c, (int)(pr >> 16), (int)(pr & 0xffff), ego_slot, first_slot, parity);
+      }
+      group_sync(c);
+    }
     // ---------------- phase C: terminal check + metrics ------------------------------------
-    const int npairs = c.acc[parity * 4 + 0];
-    const int first_pair = c.acc[parity * 4 + 1];
-    const int first_hit = c.acc[parity * 4 + 2];
-    const int rss_now = c.acc[parity * 4 + 3];
+    const int npairs = acc[ACC_NPAIRS];
+    const int first_pair = acc[ACC_FIRST_PAIR];
+    const int first_hit = acc[ACC_FIRST_HIT];
+    const int rss_now = acc[ACC_RSS];
+    if (live && ((c.bits[parity * W + (s >> 5)] >> (s & 31)) & 1)) collided = 1;
     bool dn = false;  // state.py:268-270, 397-408
-    if ((p.terminal & SG_TERM_MAX_LENGTH) && (t + dt > sc.length[n])) dn = true;
+    if ((p.terminal & SG_TERM_MAX_LENGTH) && (t + dt > length)) dn = true;
     if ((p.terminal & SG_TERM_COLLISION) && npairs > 0) dn = true;
     if ((p.terminal & SG_TERM_EGO_COLLISION) && first_hit) dn = true;
     done = dn;
@@ -651,8 +800,9 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       pair_ticks += npairs;
       if (npairs > 0 && first_tick < 0) { first_tick = tick; fp0 = first_pair >> 16; fp1 = first_pair & 0xffff; }
       rss_flags |= rss_now;
-      const int q = (parity ^ 1) * 4;  // reset the other parity for the next tick
-      c.acc[q] = 0; c.acc[q + 1] = 0x7fffffff; c.acc[q + 2] = 0; c.acc[q + 3] = 0;
+      int* nx = c.acc + (parity ^ 1) * ACC_N;  // reset the other parity for the next tick
+      nx[ACC_NPAIRS] = 0; nx[ACC_FIRST_PAIR] = 0x7fffffff; nx[ACC_FIRST_HIT] = 0; nx[ACC_RSS] = 0;
+      nx[ACC_QCOUNT] = 0;
     }
     if (s < W) {  // CollisionMetric._step, metrics/collision.py:70-75
       const uint32_t now = c.ego_now[s];
@@ -671,6 +821,7 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
         c.ego_last[s] = now;
       }
       c.ego_now[s] = 0;
+      c.bits[(parity ^ 1) * W + s] = 0;
     }
     if (s == ego_slot && (p.features & SG_FEAT_EGO_METRICS)) {  // metrics/trajectory.py:20-24,39-42,58-60
       const double sp = norm3(e.vel[0], e.vel[1], e.vel[2]);
@@ -684,7 +835,21 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   }
 
   // ---------------- write the State rows back ----------------------------------------------
-  if (live) store_ent(st, i, nm, e);
+  if (live) {
+#pragma unroll
+    for (int f = 0; f < 6; ++f) { st.pose[f * nm + i] = e.pose[f]; st.vel[f * nm + i] = e.vel[f]; }
+    st.dist[i] = e.dist;
+    st.speed[i] = e.speed;
+    st.present[i] = e.present;
+    st.cur_own[i] = cur_own;
+    st.collided[i] = collided;
+    if (PED) { st.goal_idx[i] = goal; st.force[i] = force[0]; st.force[nm + i] = force[1]; }
+    if (RSS) {
+      st.rss_state[i] = rss_state; st.rss_last[i] = rss_last;
+      st.safe_dist[i] = sd[0]; st.safe_dist[nm + i] = sd[1];
+      st.safe_ratio[i] = ratio[0]; st.safe_ratio[nm + i] = ratio[1];
+    }
+  }
   if (s == ego_slot) {
     st.ego_avg_speed[n] = avg; st.ego_avg_t[n] = avg_t; st.ego_max_speed[n] = mx; st.ego_dist[n] = egod;
   }
@@ -695,6 +860,100 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     st.rss_flags[n] = (uint8_t)rss_flags;
   }
   if (s < W) st.ego_hits[(int64_t)n * W + s] = c.ego_last[s];
+}
+
+// State.reset(t0) + Agent/Metric/StateCallback resets (reference state/state.py:106-143,
+// controller.py:100-103, metrics/trajectory.py:13-18, metrics/rss/callback.py:44-55)
+template <bool RSS, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+sg_reset_kernel(SgScene sc, SgParams p, SgState st, GroupLayout L) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int G = L.G, M = sc.n_slots, W = L.W;
+  const int gpb = blockDim.x / G;
+  const int gl = threadIdx.x / G;
+  const int s = threadIdx.x - gl * G;
+  const int n = blockIdx.x * gpb + gl;
+  if (gl >= gpb || n >= sc.n_scenarios) return;
+  Grp c;
+  setup_group(c, sc, L, smem, gl, s, n);
+  const bool live = s < M;
+  const int64_t i = c.i, nm = c.nm;
+  const int kind = live ? sc.kind[i] : SG_KIND_EMPTY;
+  const int ego_slot = sc.ego_slot[n];
+  const double t = sc.t0[n];
+  double pose[6] = {0, 0, 0, 0, 0, 0}, vel[6] = {0, 0, 0, 0, 0, 0};
+  double bw = 1, bl = 1, bcx = 0, bcy = 0, speed = 0;
+  bool present = false;
+  if (kind != SG_KIND_EMPTY) {
+    bw = sc.box[i]; bl = sc.box[nm + i]; bcx = sc.box[2 * nm + i]; bcy = sc.box[3 * nm + i];
+    const int64_t r0 = sc.traj_off[i];
+    const int K = (int)(sc.traj_off[i + 1] - r0);
+    const double* rows = sc.traj_rows + r0 * 7;
+    const int mode = (K == 1) ? EXT_TRUE : (p.persist ? EXT_CLAMP : EXT_NONE);  // :123-129
+    int cur = 0;
+    present = position_at_t(rows, K, t, mode, cur, pose);
+    if (present) velocity_at_t(rows, K, t, vel);  // :132
+    else {
+#pragma unroll
+      for (int f = 0; f < 6; ++f) pose[f] = 0.0;
+    }
+    if (kind == SG_KIND_VEHICLE) speed = norm2(vel[0], vel[1]);  // controller.py:100-103
+  }
+  uint8_t rss_state = 0, rss_last = SG_RSS_NONE;
+  double sd[2] = {0.0, 0.0}, ratio[2] = {INFINITY, INFINITY};  // callback.py:51-55
+  int rss_flags = 0;
+  const bool feat_rss = RSS && (p.features & SG_FEAT_RSS);
+  if (RSS && feat_rss) {  // update_callbacks() at reset, state.py:137-139
+    double ox, oy;
+    {
+      const int64_t er = sc.traj_off[(int64_t)n * M + ego_slot];
+      ox = __ldg(sc.traj_rows + er * 7 + 1);
+      oy = __ldg(sc.traj_rows + er * 7 + 2);
+    }
+    if (s == 0) c.acc[ACC_RSS] = 0;
+    if (live) publish_box<RSS>(c, present, pose[0], pose[1], pose[3], bw, bl, bcx, bcy, ox, oy);
+    if (s == ego_slot) publish_ego(c, present, pose, vel, bw, bl);
+    group_sync(c);
+    if (live && t != 0.0 && s != ego_slot && present && c.egop[EGO_PRESENT] != 0.0) {
+      rss_last = (uint8_t)rss_hazard(p, c, pose[0], pose[1], vel[0], vel[1], bw, bl, rss_state, sd, ratio);
+      const int found = (rss_state >> 2) & 3;
+      if (found) atomicOr(&c.acc[ACC_RSS], found == 2 ? 1 : 2);
+    }
+    group_sync(c);
+    rss_flags = c.acc[ACC_RSS];
+  }
+  if (live) {
+#pragma unroll
+    for (int f = 0; f < 6; ++f) { st.pose[f * nm + i] = pose[f]; st.vel[f * nm + i] = vel[f]; }
+    st.dist[i] = 0.0;
+    st.speed[i] = speed;
+    st.present[i] = present;
+    st.cur_own[i] = 1;
+    st.collided[i] = 0;
+    st.goal_idx[i] = 0;
+    st.force[i] = 0.0; st.force[nm + i] = 0.0;
+    st.rss_state[i] = rss_state; st.rss_last[i] = rss_last;
+    st.safe_dist[i] = sd[0]; st.safe_dist[nm + i] = sd[1];
+    st.safe_ratio[i] = ratio[0]; st.safe_ratio[nm + i] = ratio[1];
+    if (st.trace_cap > 0) {
+      st.trace_present[i] = present;
+#pragma unroll
+      for (int f = 0; f < 6; ++f) st.trace_pose[f * nm + i] = pose[f];
+    }
+  }
+  if (s == ego_slot) {  // Metric.reset, metrics/trajectory.py:13-18, 33-37
+    const double sp = norm3(vel[0], vel[1], vel[2]);
+    st.ego_avg_speed[n] = sp; st.ego_avg_t[n] = 0.0; st.ego_max_speed[n] = sp; st.ego_dist[n] = 0.0;
+  }
+  if (s == 0) {
+    st.t[n] = t; st.prev_t[n] = t - 0.1;  // state.py:135
+    st.tick[n] = 0; st.done[n] = 0; st.cur_union[n] = 1;
+    st.first_coll_tick[n] = -1; st.first_coll_pair[2 * n] = -1; st.first_coll_pair[2 * n + 1] = -1;
+    st.n_pair_ticks[n] = 0;
+    st.rss_flags[n] = (uint8_t)rss_flags;
+    if (st.trace_cap > 0) st.trace_t[n] = t;
+  }
+  if (s < W) st.ego_hits[(int64_t)n * W + s] = 0;
 }
 
 // ---------------------------------------------------------------------------------
@@ -729,7 +988,31 @@ static int ensure_constants(int device) {
   return 0;
 }
 
-static bool scene_has_kind(const SgParams* p) { (void)p; return true; }
+template <bool RSS>
+static cudaError_t launch_reset(bool big, int blocks, int threads, size_t smem, cudaStream_t s,
+                                const SgScene& sc, const SgParams& p, const SgState& st,
+                                const GroupLayout& L) {
+  auto kern = big ? sg_reset_kernel<RSS, 1024> : sg_reset_kernel<RSS, SG_THREADS>;
+  if (smem > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+  }
+  kern<<<blocks, threads, smem, s>>>(sc, p, st, L);
+  return cudaGetLastError();
+}
+
+template <bool PED, bool RSS>
+static cudaError_t launch_rollout(bool big, int blocks, int threads, size_t smem, cudaStream_t s,
+                                  const SgScene& sc, const SgParams& p, const SgState& st,
+                                  const SgInputs& in, int n_ticks, const GroupLayout& L) {
+  auto kern = big ? sg_rollout_kernel<PED, RSS, 1024> : sg_rollout_kernel<PED, RSS, SG_THREADS>;
+  if (smem > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+  }
+  kern<<<blocks, threads, smem, s>>>(sc, p, st, in, n_ticks, L);
+  return cudaGetLastError();
+}
 
 static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInputs* in, int n_ticks,
                   int device, void* stream, int reset) {
@@ -742,28 +1025,28 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
   if (rc) return rc;
   const bool ped = sc->route_off != nullptr && sc->n_route_pts > 0;
   const bool rss = (p->features & SG_FEAT_RSS) != 0;
-  GroupLayout L = make_layout(sc->n_slots, ped);
+  GroupLayout L = make_layout(sc->n_slots, ped, rss);
   const int threads = L.G <= SG_THREADS ? SG_THREADS : L.G;
+  const bool big = threads > SG_THREADS;
   const int gpb = threads / L.G;
   const int blocks = (sc->n_scenarios + gpb - 1) / gpb;
   const size_t smem = (size_t)gpb * L.bytes;
+  if (smem > 227 * 1024) return set_msg("scenario does not fit in shared memory");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (reset) {
+    err = rss ? launch_reset<true>(big, blocks, threads, smem, s, *sc, *p, *st, L)
+              : launch_reset<false>(big, blocks, threads, smem, s, *sc, *p, *st, L);
+    if (err != cudaSuccess) return set_err("sg_reset_kernel launch", err);
+    return 0;
+  }
   SgInputs none;
   memset(&none, 0, sizeof(none));
   const SgInputs inp = in ? *in : none;
-  void (*kern)(SgScene, SgParams, SgState, SgInputs, int, GroupLayout, int);
-  const bool big = threads > SG_THREADS;
-  if (ped && rss) kern = big ? sg_rollout_kernel<true, true, 1024> : sg_rollout_kernel<true, true, SG_THREADS>;
-  else if (ped) kern = big ? sg_rollout_kernel<true, false, 1024> : sg_rollout_kernel<true, false, SG_THREADS>;
-  else if (rss) kern = big ? sg_rollout_kernel<false, true, 1024> : sg_rollout_kernel<false, true, SG_THREADS>;
-  else kern = big ? sg_rollout_kernel<false, false, 1024> : sg_rollout_kernel<false, false, SG_THREADS>;
-  if (smem > 48 * 1024) {
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return set_err("cudaFuncSetAttribute", err);
-  }
-  kern<<<blocks, threads, smem, (cudaStream_t)stream>>>(*sc, *p, *st, inp, n_ticks, L, reset);
-  err = cudaGetLastError();
+  if (ped && rss) err = launch_rollout<true, true>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
+  else if (ped) err = launch_rollout<true, false>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
+  else if (rss) err = launch_rollout<false, true>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
+  else err = launch_rollout<false, false>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
   if (err != cudaSuccess) return set_err("sg_rollout_kernel launch", err);
-  (void)scene_has_kind;
   return 0;
 }
 
