@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 3
+#define SG_ABI_VERSION 4
 
 /* entity slot kinds (who produces the slot's next pose each tick) */
 enum SgKind {
@@ -117,6 +117,11 @@ typedef struct SgScene {
   int64_t n_traj_rows; /* total control points in traj_rows */
   int64_t n_union_rows;/* total rows in union_t            */
   int64_t n_route_pts; /* total points in route_xy         */
+  /* OR of (1u << SgKind) over all slots, or 0 = unspecified (always valid).  A non-zero mask
+     lets the library pick a specialised kernel; {VEHICLE[,EMPTY]} additionally promises that
+     every vehicle slot is present at reset (its trajectory covers t0). */
+  uint32_t kind_mask;
+  uint32_t _pad0;
   const uint8_t* kind;   /* [N*M] SgKind */
   const uint8_t* etype;  /* [N*M] SgEntityType */
   const double* box;     /* [4][N*M]: width, length, center_x, center_y (catalog_entry.py:83-90) */

@@ -11,7 +11,7 @@ import math
 import os
 from typing import Dict, Optional
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # SgKind
 KIND_EMPTY, KIND_REPLAY, KIND_AGENT_REPLAY, KIND_VEHICLE, KIND_PEDESTRIAN, KIND_HOST = range(6)
@@ -76,6 +76,8 @@ class SgScene(C.Structure):
         ("n_traj_rows", C.c_int64),
         ("n_union_rows", C.c_int64),
         ("n_route_pts", C.c_int64),
+        ("kind_mask", C.c_uint32),
+        ("_pad0", C.c_uint32),
         ("kind", _p),
         ("etype", _p),
         ("box", _p),
@@ -293,7 +295,8 @@ def bind(lib: C.CDLL, prefix: str) -> Dict[str, object]:
 
 
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PRODUCT_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libsg_b200.so")
+PRODUCT_LIB = os.environ.get(
+    "SG_B200_LIB", os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libsg_b200.so"))
 
 _product: Optional[Dict[str, object]] = None
 

@@ -25,6 +25,9 @@
 #include "sg_device.cuh"
 
 #define SG_THREADS 256
+#ifndef SG_VEH_MINB
+#define SG_VEH_MINB 2  // resident CTAs per SM the vehicle kernel is compiled for
+#endif
 
 __constant__ double c_ngon[64][2];  // (cos, sin)(-k * 2pi/64): GEOS Point.buffer vertices
 
@@ -45,13 +48,15 @@ struct GroupLayout {
   int W;        // 32-bit words per collision row
   int H;        // half-sweep length M/2
   int QCAP;     // candidate-pair queue capacity
-  int off_hcs, off_ped, off_ego, off_aabb, off_queue, off_hits, off_bits, off_acc, off_flags,
-      off_orient;
+  int off_hcs, off_ped, off_box, off_ego, off_cold, off_aabb, off_queue, off_hits, off_bits,
+      off_acc, off_flags, off_orient;
   int bytes;
 };
 
-enum { EGO_X = 0, EGO_Y, EGO_C, EGO_S, EGO_INV0, EGO_INV1, EGO_HD0, EGO_HD1, EGO_V0, EGO_V1,
-       EGO_VNORM, EGO_W, EGO_L, EGO_PRESENT, EGO_N = 16 };
+enum { EGO_X = 0, EGO_Y, EGO_C, EGO_S, EGO_INV0, EGO_INV1, EGO_HD0, EGO_HD1, EGO_HINV0, EGO_HINV1,
+       EGO_V0, EGO_V1, EGO_VNORM, EGO_VLONG, EGO_W, EGO_L, EGO_RHW, EGO_RHL, EGO_PRESENT, EGO_N = 20 };
+enum { COLD_AVG = 0, COLD_AVG_T, COLD_MAX, COLD_EGOD, COLD_ND = 4 };                 // doubles
+enum { COLD_FIRST_TICK = 0, COLD_FP0, COLD_FP1, COLD_RSS, COLD_PAIR_TICKS = 4, COLD_NI = 8 };  // ints
 enum { ACC_NPAIRS = 0, ACC_FIRST_PAIR, ACC_FIRST_HIT, ACC_RSS, ACC_QCOUNT, ACC_N = 8 };
 
 static GroupLayout make_layout(int M, bool ped, bool rss) {
@@ -65,7 +70,9 @@ static GroupLayout make_layout(int M, bool ped, bool rss) {
   int o = 8 * G * (int)sizeof(double);                            // corners[8][G]
   L.off_hcs = o;    o += rss ? 2 * G * (int)sizeof(double) : 0;   // cos/sin of each heading
   L.off_ped = o;    o += ped ? 4 * G * (int)sizeof(double) : 0;   // old x,y,vx,vy (pedestrian sensors)
+  L.off_box = o;    o += 4 * G * (int)sizeof(double);             // width, length, center_x, center_y
   L.off_ego = o;    o += EGO_N * (int)sizeof(double);
+  L.off_cold = o;   o += COLD_ND * (int)sizeof(double) + COLD_NI * (int)sizeof(int);
   L.off_aabb = o;   o += (M + L.H + 1) * (int)sizeof(float4);     // duplicated head: no wrap in the sweep
   L.off_queue = o;  o += L.QCAP * (int)sizeof(uint32_t);
   L.off_hits = o;   o += 2 * L.W * (int)sizeof(uint32_t);         // ego_now[W], ego_last[W]
@@ -84,7 +91,10 @@ struct Grp {
   double* corners;
   double* hcs;
   double* pedbuf;
+  double* boxp;
   double* egop;
+  double* cold_d;
+  int* cold_i;
   float4* aabb;
   uint32_t* queue;
   uint32_t* ego_now;
@@ -112,7 +122,10 @@ SG_DEV void setup_group(Grp& g, const SgScene& sc, const GroupLayout& L, unsigne
   g.corners = (double*)base;
   g.hcs = (double*)(base + L.off_hcs);
   g.pedbuf = (double*)(base + L.off_ped);
+  g.boxp = (double*)(base + L.off_box);
   g.egop = (double*)(base + L.off_ego);
+  g.cold_d = (double*)(base + L.off_cold);
+  g.cold_i = (int*)(base + L.off_cold + COLD_ND * sizeof(double));
   g.aabb = (float4*)(base + L.off_aabb);
   g.queue = (uint32_t*)(base + L.off_queue);
   g.ego_now = (uint32_t*)(base + L.off_hits);
@@ -260,14 +273,22 @@ SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c,
 // ---------------------------------------------------------------------------------
 // staging
 // ---------------------------------------------------------------------------------
+// box ring orientation is invariant under the rigid motion of entity/base.py:100-138:
+// the local ring (-,+),(+,+),(+,-),(-,-) is clockwise for W*L > 0.  Zero-area boxes are
+// decided exactly per tick.
+SG_DEV int box_orientation_hint(double bw, double bl) {
+  const double a = bw * bl;
+  return a > 0 ? -1 : (a < 0 ? 1 : 0);
+}
+
+// Entity.get_bounding_box_points (reference entity/base.py:100-138) from cos/sin of the heading
 template <bool RSS>
-SG_DEV void publish_box(const Grp& c, bool present, double x, double y, double h, double bw,
-                        double bl, double bcx, double bcy, double ox, double oy) {
+SG_DEV void publish_box(const Grp& c, bool present, double x, double y, double cs, double sn,
+                        int orient_hint, double ox, double oy) {
   float4 bb = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
   if (present) {
-    double sn, cs;
-    sincos(h, &sn, &cs);
-    // Entity.get_bounding_box_points (reference entity/base.py:100-138)
+    const double bw = c.boxp[c.s], bl = c.boxp[c.G + c.s];
+    const double bcx = c.boxp[2 * c.G + c.s], bcy = c.boxp[3 * c.G + c.s];
     const double hx0 = bcx - 0.5 * bl, hx1 = bcx + 0.5 * bl;
     const double hy0 = bcy + 0.5 * bw, hy1 = bcy - 0.5 * bw;
     double my[8];
@@ -278,7 +299,7 @@ SG_DEV void publish_box(const Grp& c, bool present, double x, double y, double h
 #pragma unroll
     for (int f = 0; f < 8; ++f) c.corners[f * c.G + c.s] = my[f];
     if (RSS) { c.hcs[c.s] = cs; c.hcs[c.G + c.s] = sn; }
-    c.orient[c.s] = (int8_t)quad_orientation(my);
+    c.orient[c.s] = (int8_t)(orient_hint ? orient_hint : quad_orientation(my));
     bb = make_aabb(my, ox, oy);
   }
   c.aabb[c.s] = bb;
@@ -286,132 +307,173 @@ SG_DEV void publish_box(const Grp& c, bool present, double x, double y, double h
 }
 
 // ego parameters in its own frame (reference metrics/rss/callback.py:73-97, 340-386)
-SG_DEV void publish_ego(const Grp& c, bool present, const double pose[6], const double vel[6],
-                        double bw, double bl) {
-  double es, ec;
-  sincos(pose[3], &es, &ec);
+SG_DEV void publish_ego(const Grp& c, bool present, double x, double y, double ec, double es,
+                        double vx, double vy) {
   const double eh[2] = {ec, es};
   double einv[2];
   inverse_direction(eh, einv);
-  c.egop[EGO_X] = pose[0]; c.egop[EGO_Y] = pose[1];
-  c.egop[EGO_C] = ec; c.egop[EGO_S] = es;
-  c.egop[EGO_INV0] = einv[0]; c.egop[EGO_INV1] = einv[1];
-  c.egop[EGO_HD0] = dot2(ec, es, einv[0], einv[1]);
-  c.egop[EGO_HD1] = dot2(ec, es, ec, es);
-  const double v0 = dot2(vel[0], vel[1], einv[0], einv[1]), v1 = dot2(vel[0], vel[1], ec, es);
-  c.egop[EGO_V0] = v0; c.egop[EGO_V1] = v1;
-  c.egop[EGO_VNORM] = norm2(v0, v1);
-  c.egop[EGO_W] = bw; c.egop[EGO_L] = bl;
-  c.egop[EGO_PRESENT] = present ? 1.0 : 0.0;
+  double* E = c.egop;
+  E[EGO_X] = x; E[EGO_Y] = y;
+  E[EGO_C] = ec; E[EGO_S] = es;
+  E[EGO_INV0] = einv[0]; E[EGO_INV1] = einv[1];
+  const double hd[2] = {dot2(ec, es, einv[0], einv[1]), dot2(ec, es, ec, es)};
+  E[EGO_HD0] = hd[0]; E[EGO_HD1] = hd[1];
+  double hinv[2];
+  inverse_direction(hd, hinv);  // used by safe_lateral_distance for every hazard
+  E[EGO_HINV0] = hinv[0]; E[EGO_HINV1] = hinv[1];
+  const double v0 = dot2(vx, vy, einv[0], einv[1]), v1 = dot2(vx, vy, ec, es);
+  E[EGO_V0] = v0; E[EGO_V1] = v1;
+  E[EGO_VNORM] = norm2(v0, v1);
+  E[EGO_VLONG] = fabs(dot2(v0, v1, hd[0], hd[1]));
+  const double eW = c.boxp[c.s], eL = c.boxp[c.G + c.s];
+  E[EGO_W] = eW; E[EGO_L] = eL;
+  E[EGO_RHW] = 1.0 / (0.5 * eW); E[EGO_RHL] = 1.0 / (0.5 * eL);
+  E[EGO_PRESENT] = present ? 1.0 : 0.0;
 }
 
 // ---------------------------------------------------------------------------------
 // RSS (reference metrics/rss/callback.py)
 // ---------------------------------------------------------------------------------
-__device__ __noinline__ bool rss_box_hits_buffer(const double* box, double slat, double slong) {
-  const double buffer[8] = {slat, slong, -slat, slong, -slat, -slong, slat, -slong};
-  return quads_intersect(box, quad_orientation(box), buffer, quad_orientation(buffer));
-}
 __device__ __noinline__ bool rss_box_hits_segment(const double* box, double x0, double y0,
                                                   double x1, double y1) {
   const double seg[4] = {x0, y0, x1, y1};
   return quad_intersects_segment(box, quad_orientation(box), seg);
 }
 
-// RSSDistances.__call__ for one hazard (callback.py:57-122).  The geometric predicates are
-// answered by exact comparisons where those decide (bounding ranges disjoint => no
-// intersection; a corner inside the closed rectangle => intersection) and by the exact
-// orientation predicates otherwise, so every record equals the reference's.
-SG_DEV int rss_hazard(const SgParams& p, const Grp& c, double x, double y, double vx, double vy,
-                      double bw, double bl, uint8_t& state, double sd[2], double ratio[2]) {
+// Does the infinite line through (ax, ay), (bx, by) meet the closed convex quad?  (Exact.)
+SG_DEV bool line_hits_quad(const double* q, double ax, double ay, double bx, double by) {
+  int pos = 0, neg = 0;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int sg = orient_sign(ax, ay, bx, by, q[2 * m], q[2 * m + 1]);
+    pos += sg > 0;
+    neg += sg < 0;
+  }
+  return !(pos == 4 || neg == 4);
+}
+
+// Closed intersection of a convex quad with the rectangle [-a, a] x [-b, b] whose bounding
+// ranges already overlap: separating axes are the quad's edges; per edge only the rectangle
+// corner that is extreme towards the quad's inside has to be tested.  (Exact.)
+SG_DEV bool quad_hits_centered_rect(const double* q, double a, double b) {
+  const int o = quad_orientation(q);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double ax = q[2 * k], ay = q[2 * k + 1];
+    const double bx = q[2 * ((k + 1) & 3)], by = q[2 * ((k + 1) & 3) + 1];
+    // orient(a, b, p) = dx*(py-ay) - dy*(px-ax): o*orient is largest for
+    // py = b*sign(o*dx), px = -a*sign(o*dy)
+    const double dx = bx - ax, dy = by - ay;
+    const double py = ((o > 0) == (dx > 0) || dx == 0) ? b : -b;
+    const double px = ((o > 0) == (dy > 0) && dy != 0) ? -a : a;
+    if (orient_sign(ax, ay, bx, by, px, py) * o < 0) return false;  // every corner strictly outside
+  }
+  return true;
+}
+
+struct RssConst {  // uniform per launch
+  double CLR, RT, MAXA, MINA, r2mina;
+};
+
+// RSSDistances.__call__ for one hazard (callback.py:57-122).  Geometric predicates are
+// answered by exact comparisons where those decide and by exact orientation signs otherwise,
+// so every record equals the reference's; scalar quotients with a launch-uniform or shared
+// denominator use div_r.
+SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, double vx, double vy,
+                      uint8_t& state, double sd[2], double ratio[2]) {
   const double* E = c.egop;
-  const double eh[2] = {E[EGO_C], E[EGO_S]}, einv[2] = {E[EGO_INV0], E[EGO_INV1]};
+  const double eh0 = E[EGO_C], eh1 = E[EGO_S], ei0 = E[EGO_INV0], ei1 = E[EGO_INV1];
   const double dirc = c.hcs[c.s], dirs = c.hcs[c.G + c.s];
+  const double bw = c.boxp[c.s], bl = c.boxp[c.G + c.s];
   // get_entity_parameters (callback.py:340-386) with coord_change (rss_utils.py:24-45)
   const double d0 = x - E[EGO_X], d1 = y - E[EGO_Y];
-  const double pos0 = dot2(d0, d1, einv[0], einv[1]), pos1 = dot2(d0, d1, eh[0], eh[1]);
-  const double hd0 = dot2(dirc, dirs, einv[0], einv[1]), hd1 = dot2(dirc, dirs, eh[0], eh[1]);
-  const double v0 = dot2(vx, vy, einv[0], einv[1]), v1 = dot2(vx, vy, eh[0], eh[1]);
-  double box[8];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const double c0 = c.corners[(2 * q) * c.G + c.s] - E[EGO_X];
-    const double c1 = c.corners[(2 * q + 1) * c.G + c.s] - E[EGO_Y];
-    box[2 * q] = dot2(c0, c1, einv[0], einv[1]);
-    box[2 * q + 1] = dot2(c0, c1, eh[0], eh[1]);
-  }
+  const double pos0 = dot2(d0, d1, ei0, ei1), pos1 = dot2(d0, d1, eh0, eh1);
+  const double hd0 = dot2(dirc, dirs, ei0, ei1), hd1 = dot2(dirc, dirs, eh0, eh1);
+  const double v0 = dot2(vx, vy, ei0, ei1), v1 = dot2(vx, vy, eh0, eh1);
   const double eW = E[EGO_W], eL = E[EGO_L];
-  const double CLR = p.rss_min_safe_clearance, RT = p.rss_response_time;
-  // safe_longitudinal_distance (callback.py:230-269); ego position is [0, 0]
+  const double eHD0 = E[EGO_HD0], eHD1 = E[EGO_HD1];
+  // safe_longitudinal_distance (callback.py:230-269); the ego's position is [0, 0]
   double slong;
   {
-    const double dp = dot2(E[EGO_HD0], E[EGO_HD1], hd0, hd1);
-    const double a = fabs(p.rss_max_long_accel * dp);
-    bool early = false;
+    const double dp = dot2(eHD0, eHD1, hd0, hd1);
+    const double a = fabs(K.MAXA * dp);
+    const double hv = dot2(v0, v1, eHD0, eHD1);
+    bool early;
     double dd = 0;
     if (dp > 0) {
       double vf, vr;
-      const double hv = dot2(v0, v1, E[EGO_HD0], E[EGO_HD1]);
       if (0.0 > pos1) { vf = E[EGO_VNORM]; vr = hv; } else { vf = hv; vr = E[EGO_VNORM]; }
-      if (vr == 0.0) early = true;
-      else dd = long_dist_same_direction(vf, vr, a, RT, p.rss_min_long_accel);
+      early = vr == 0.0;
+      if (!early) {  // long_dist_same_direction, callback.py:454-472
+        const double vf2a = vf * vf / (2 * a);
+        const double u = vr + K.RT * a;
+        dd = py_max(0, vr * K.RT + py_min(vf2a, 0.5 * a * (K.RT * K.RT)) +
+                           div_r(u * u, 2 * K.MINA, K.r2mina) - vf2a);
+      }
     } else {
-      const double v1e = fabs(dot2(E[EGO_V0], E[EGO_V1], E[EGO_HD0], E[EGO_HD1]));
-      const double v2e = -fabs(dot2(v0, v1, E[EGO_HD0], E[EGO_HD1]));
-      if (np_sign(pos1) == np_sign(v1)) early = true;
-      else dd = long_dist_opp_direction(v1e, v2e, a, RT, p.rss_min_long_accel);
+      early = np_sign(pos1) == np_sign(v1);
+      if (!early) {  // long_dist_opp_direction, callback.py:474-492
+        const double v1e = E[EGO_VLONG], av2 = fabs(hv);
+        const double u1 = v1e + K.RT * a, u2 = av2 + K.RT * a;
+        dd = py_max(0, (2 * v1e + K.RT * a) * K.RT / 2 + div_r(u1 * u1, 2 * K.MINA, K.r2mina) +
+                           (2 * av2 + K.RT * a) * K.RT / 2 + div_r(u2 * u2, 2 * K.MINA, K.r2mina));
+      }
     }
-    slong = fabs(early ? CLR + 0.5 * eL : dd + CLR + 0.5 * eL);
+    slong = fabs(early ? K.CLR + 0.5 * eL : dd + K.CLR + 0.5 * eL);
   }
   // safe_lateral_distance (callback.py:271-302)
   double slat;
   {
-    double v = v0;
-    const double ehd[2] = {E[EGO_HD0], E[EGO_HD1]};
-    double inv[2];
-    inverse_direction(ehd, inv);
-    const double k = fabs(dot2(inv[0], inv[1], hd0, hd1));
-    const double amax = p.rss_max_long_accel * k, amin = p.rss_min_long_accel * k;
-    double dd;
+    const double k = fabs(dot2(E[EGO_HINV0], E[EGO_HINV1], hd0, hd1));
+    const double amax = K.MAXA * k, amin = K.MINA * k;
+    double dd = 0;
     bool early = false;
-    if (np_sign(-pos0) == np_sign(v)) {
-      v = fabs(v);
-      if (v == 0.0) early = true;
-      dd = early ? 0.0 : lat_dist(v, amax, amin, RT);
-    } else {
-      dd = 0;
+    if (np_sign(-pos0) == np_sign(v0)) {
+      const double v = fabs(v0);
+      early = v == 0.0;
+      if (!early) {  // lat_dist, callback.py:494-505
+        const double den = 2 * amin, rden = 1.0 / den;
+        const double u = v + K.RT * amax, w = K.RT * amax;
+        dd = py_max(0, 0.5 * K.RT * (2 * v + K.RT * amax) + div_r(u * u, den, rden) -
+                           0.5 * (K.RT * K.RT) * amax - div_r(w * w, den, rden));
+      }
     }
-    slat = fabs(early ? CLR + 0.5 * eW : dd + CLR + 0.5 * eW);
+    slat = fabs(early ? K.CLR + 0.5 * eW : dd + K.CLR + 0.5 * eW);
   }
   sd[0] = slat;
   sd[1] = slong;
   // safe_ratios (callback.py:124-166)
   {
-    const double hdv[2] = {hd0, hd1};
-    double inv[2];
-    inverse_direction(hdv, inv);
-    const double wl_inv = fabs(dot2(bw, bl, inv[0], inv[1]));
+    const double hn = norm2(hd1, hd0), rhn = 1.0 / hn;  // inverse_direction(haz heading)
+    const double inv0 = div_r(hd1, hn, rhn), inv1 = div_r(-hd0, hn, rhn);
+    const double wl_inv = fabs(dot2(bw, bl, inv0, inv1));
     const double wl_dir = fabs(dot2(bw, bl, hd0, hd1));
     const double actual_lat = py_max(1e-6, fabs(pos0) - 0.5 * eW - 0.5 * wl_inv);
     const double actual_long = py_max(1e-6, fabs(pos1) - 0.5 * eL - 0.5 * wl_dir);
-    ratio[0] = fabs(actual_lat / (0.5 * eW));
-    ratio[1] = fabs(actual_long / (0.5 * eL));
+    ratio[0] = fabs(div_r(actual_lat, 0.5 * eW, E[EGO_RHW]));
+    ratio[1] = fabs(div_r(actual_long, 0.5 * eL, E[EGO_RHL]));
   }
   // unsafe_distance (callback.py:168-228)
   if ((state >> 2) & 3) return SG_RSS_FOUND;
+  double box[8];  // hazard corners in the ego frame
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const double c0 = c.corners[(2 * q) * c.G + c.s] - E[EGO_X];
+    const double c1 = c.corners[(2 * q + 1) * c.G + c.s] - E[EGO_Y];
+    box[2 * q] = dot2(c0, c1, ei0, ei1);
+    box[2 * q + 1] = dot2(c0, c1, eh0, eh1);
+  }
   const double bxmin = fmin(fmin(box[0], box[2]), fmin(box[4], box[6]));
   const double bxmax = fmax(fmax(box[0], box[2]), fmax(box[4], box[6]));
   const double bymin = fmin(fmin(box[1], box[3]), fmin(box[5], box[7]));
   const double bymax = fmax(fmax(box[1], box[3]), fmax(box[5], box[7]));
-  bool inter;
-  if (bxmin > slat || bxmax < -slat || bymin > slong || bymax < -slong) {
-    inter = false;  // bounding ranges disjoint: separated
-  } else {
-    bool corner_in = false;
+  bool inter = false;
+  if (!(bxmin > slat || bxmax < -slat || bymin > slong || bymax < -slong)) {
+    bool corner_in = false;  // a hazard corner inside the closed buffer decides at once
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       corner_in = corner_in || (fabs(box[2 * q]) <= slat && fabs(box[2 * q + 1]) <= slong);
-    inter = corner_in || rss_box_hits_buffer(box, slat, slong);
+    inter = corner_in || quad_hits_centered_rect(box, slat, slong);
   }
   if (inter) {
     const int marker = state & 3;
@@ -426,16 +488,28 @@ SG_DEV int rss_hazard(const SgParams& p, const Grp& c, double x, double y, doubl
     state |= 1 << 2;
     return SG_RSS_UNSAFE_LATERAL;
   }
-  // write_intersections (callback.py:304-338) against generate_buffer's segments (:429-451)
+  // write_intersections (callback.py:304-338) against generate_buffer's segments (:429-451):
+  // "lengths" are the diagonals (+-slat, 100 slong) -> (-+slat, -100 slong), "widths" the
+  // horizontal segments y = +-slong, |x| <= 100 slat.
   const double L100 = 100 * slong, W100 = 100 * slat;
   bool lat = false, lon = false;
-  if (!(bxmin > slat || bxmax < -slat || bymin > L100 || bymax < -L100))
-    lat = rss_box_hits_segment(box, slat, L100, -slat, 100 * -slong) ||
-          rss_box_hits_segment(box, -slat, L100, slat, 100 * -slong);
+  if (!(bxmin > slat || bxmax < -slat || bymin > L100 || bymax < -L100)) {
+    if (bymax < L100 && bymin > -L100)  // segment spans the box's y-range: segment <=> line
+      lat = line_hits_quad(box, slat, L100, -slat, 100 * -slong) ||
+            line_hits_quad(box, -slat, L100, slat, 100 * -slong);
+    else
+      lat = rss_box_hits_segment(box, slat, L100, -slat, 100 * -slong) ||
+            rss_box_hits_segment(box, -slat, L100, slat, 100 * -slong);
+  }
   if (!(bxmin > W100 || bxmax < -W100)) {
-    if (!(bymin > slong || bymax < slong)) lon = rss_box_hits_segment(box, W100, slong, 100 * -slat, slong);
-    if (!lon && !(bymin > -slong || bymax < -slong))
-      lon = rss_box_hits_segment(box, 100 * -slat, -slong, W100, -slong);
+    if (bxmin > -W100 && bxmax < W100) {  // box inside the segments' x-range: segment <=> line y = c
+      lon = (bymin <= slong && slong <= bymax) || (bymin <= -slong && -slong <= bymax);
+    } else {
+      if (!(bymin > slong || bymax < slong))
+        lon = rss_box_hits_segment(box, W100, slong, 100 * -slat, slong);
+      if (!lon && !(bymin > -slong || bymax < -slong))
+        lon = rss_box_hits_segment(box, 100 * -slat, -slong, W100, -slong);
+    }
   }
   if (lat && lon) return SG_RSS_BOTH;
   if (lat) { state = (uint8_t)((state & ~3) | 1); return SG_RSS_LATERAL; }
@@ -461,8 +535,8 @@ __device__ __noinline__ bool pair_collides(const double* corners, const int8_t* 
   return quads_intersect(qa, orient[a], qb, orient[b]);
 }
 
-SG_DEV void record_pair(const SgParams& p, const SgState& st, const Grp& c, int a, int b,
-                        int ego_slot, int first_slot, int parity) {
+__device__ __noinline__ void record_pair(int features, uint32_t* coll_mask, const Grp& c, int a,
+                                         int b, int ego_slot, int first_slot, int parity) {
   if (!pair_collides(c.corners, c.orient, c.G, a, b)) return;
   const int lo = min(a, b), hi = max(a, b);
   int* acc = c.acc + parity * ACC_N;
@@ -474,15 +548,15 @@ SG_DEV void record_pair(const SgParams& p, const SgState& st, const Grp& c, int 
   atomicOr(&bits[hi >> 5], 1u << (hi & 31));
   if (lo == ego_slot) atomicOr(&c.ego_now[hi >> 5], 1u << (hi & 31));
   if (hi == ego_slot) atomicOr(&c.ego_now[lo >> 5], 1u << (lo & 31));
-  if (p.features & SG_FEAT_COLL_MATRIX) {
-    uint32_t* rows = st.coll_mask + (int64_t)c.n * c.M * c.W;
+  if (features & SG_FEAT_COLL_MATRIX) {
+    uint32_t* rows = coll_mask + (int64_t)c.n * c.M * c.W;
     atomicOr(&rows[(int64_t)lo * c.W + (hi >> 5)], 1u << (hi & 31));
     atomicOr(&rows[(int64_t)hi * c.W + (lo >> 5)], 1u << (lo & 31));
   }
 }
 
 // circular half sweep over the staged AABBs; survivors go to the scenario's queue
-SG_DEV void broad_phase(const SgParams& p, const SgState& st, const Grp& c, int ego_slot,
+SG_DEV void broad_phase(int features, uint32_t* coll_mask, const Grp& c, int ego_slot,
                         int first_slot, int parity) {
   const float4 mb = c.aabb[c.s];
   const float4* nb = c.aabb + c.s + 1;
@@ -514,12 +588,276 @@ SG_DEV void broad_phase(const SgParams& p, const SgState& st, const Grp& c, int 
       if (2 * d == c.M && c.s > j) continue;  // the antipodal pair is seen from both ends
       const int q = atomicAdd(&acc[ACC_QCOUNT], 1);
       if (q < c.QCAP) c.queue[q] = ((uint32_t)c.s << 16) | (uint32_t)j;
-      else record_pair(p, st, c, c.s, j, ego_slot, first_slot, parity);  // queue full: do it here
+      else record_pair(features, coll_mask, c, c.s, j, ego_slot, first_slot, parity);  // queue full
     }
   }
 }
 
-// mutable per-entity state kept in registers across ticks
+// phases B2 + C, shared by both kernel flavours.  Returns state.is_done.
+SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int n, int s, int W,
+                        int G, int ego_slot, int first_slot, int parity, int tick, double t,
+                        double dt, double length, bool live, uint8_t& collided, double vx,
+                        double vy, double vz, double dist) {
+  int* acc = c.acc + parity * ACC_N;
+  const int nq = min(acc[ACC_QCOUNT], c.QCAP);
+  if (nq > 0) {  // phase B2: exact narrow phase on the queued pairs
+    for (int q = s; q < nq; q += G) {
+      const uint32_t pr = c.queue[q];
+      record_pair(p.features, st.coll_mask, c, (int)(pr >> 16), (int)(pr & 0xffff), ego_slot,
+                  first_slot, parity);
+    }
+    group_sync(c);
+  }
+  // phase C: terminal check + metrics
+  const int npairs = acc[ACC_NPAIRS];
+  if (live && ((c.bits[parity * W + (s >> 5)] >> (s & 31)) & 1)) collided = 1;
+  bool dn = false;  // state.py:268-270, 397-408
+  if ((p.terminal & SG_TERM_MAX_LENGTH) && (t + dt > length)) dn = true;
+  if ((p.terminal & SG_TERM_COLLISION) && npairs > 0) dn = true;
+  if ((p.terminal & SG_TERM_EGO_COLLISION) && acc[ACC_FIRST_HIT]) dn = true;
+  if (s == 0) {
+    int* cold = c.cold_i;
+    if (npairs > 0) {
+      *(long long*)(cold + COLD_PAIR_TICKS) += npairs;
+      if (cold[COLD_FIRST_TICK] < 0) {
+        const int fp = acc[ACC_FIRST_PAIR];
+        cold[COLD_FIRST_TICK] = tick; cold[COLD_FP0] = fp >> 16; cold[COLD_FP1] = fp & 0xffff;
+      }
+    }
+    cold[COLD_RSS] |= acc[ACC_RSS];
+    int* nx = c.acc + (parity ^ 1) * ACC_N;  // reset the other parity for the next tick
+    nx[ACC_NPAIRS] = 0; nx[ACC_FIRST_PAIR] = 0x7fffffff; nx[ACC_FIRST_HIT] = 0; nx[ACC_RSS] = 0;
+    nx[ACC_QCOUNT] = 0;
+  }
+  if (s < W) {  // CollisionMetric._step, metrics/collision.py:70-75
+    const uint32_t now = c.ego_now[s];
+    if (p.features & SG_FEAT_COLLISIONS) {
+      uint32_t fresh = now & ~c.ego_last[s];
+      while (fresh) {
+        const int b = __ffs(fresh) - 1;
+        fresh &= fresh - 1;
+        const int slot = atomicAdd(st.event_count, 1);
+        if (slot < st.event_cap) {
+          SgEvent ev;
+          ev.scenario = n; ev.tick = tick; ev.slot = s * 32 + b; ev._pad = 0; ev.t = t;
+          st.events[slot] = ev;
+        }
+      }
+      c.ego_last[s] = now;
+    }
+    c.ego_now[s] = 0;
+    c.bits[(parity ^ 1) * W + s] = 0;
+  }
+  if (s == ego_slot && (p.features & SG_FEAT_EGO_METRICS)) {  // metrics/trajectory.py:20-24,39-42,58-60
+    double* m = c.cold_d;
+    const double sp = norm3(vx, vy, vz);
+    const double w = m[COLD_AVG_T] / t;
+    m[COLD_AVG] += (1.0 - w) * (sp - m[COLD_AVG]);
+    m[COLD_AVG_T] = t;
+    m[COLD_MAX] = fmax(sp, m[COLD_MAX]);
+    m[COLD_EGOD] = dist;
+  }
+  return dn;
+}
+
+// per-scenario accumulators live in shared memory between ticks
+SG_DEV void load_cold(const SgState& st, const Grp& c, int n, int s, int W, int ego_slot) {
+  if (s == ego_slot) {
+    c.cold_d[COLD_AVG] = st.ego_avg_speed[n]; c.cold_d[COLD_AVG_T] = st.ego_avg_t[n];
+    c.cold_d[COLD_MAX] = st.ego_max_speed[n]; c.cold_d[COLD_EGOD] = st.ego_dist[n];
+  }
+  if (s == 0) {
+    c.cold_i[COLD_FIRST_TICK] = st.first_coll_tick[n];
+    c.cold_i[COLD_FP0] = st.first_coll_pair[2 * n]; c.cold_i[COLD_FP1] = st.first_coll_pair[2 * n + 1];
+    *(long long*)(c.cold_i + COLD_PAIR_TICKS) = st.n_pair_ticks[n];
+    c.cold_i[COLD_RSS] = st.rss_flags[n];
+    for (int q = 0; q < 2 * ACC_N; ++q) c.acc[q] = 0;
+    c.acc[ACC_FIRST_PAIR] = 0x7fffffff; c.acc[ACC_N + ACC_FIRST_PAIR] = 0x7fffffff;
+  }
+  if (s < W) {
+    c.ego_last[s] = st.ego_hits[(int64_t)n * W + s];
+    c.ego_now[s] = 0;
+    c.bits[s] = 0; c.bits[W + s] = 0;
+  }
+}
+SG_DEV void store_cold(const SgState& st, const Grp& c, int n, int s, int W, int ego_slot) {
+  if (s == ego_slot) {
+    st.ego_avg_speed[n] = c.cold_d[COLD_AVG]; st.ego_avg_t[n] = c.cold_d[COLD_AVG_T];
+    st.ego_max_speed[n] = c.cold_d[COLD_MAX]; st.ego_dist[n] = c.cold_d[COLD_EGOD];
+  }
+  if (s == 0) {
+    st.first_coll_tick[n] = c.cold_i[COLD_FIRST_TICK];
+    st.first_coll_pair[2 * n] = c.cold_i[COLD_FP0]; st.first_coll_pair[2 * n + 1] = c.cold_i[COLD_FP1];
+    st.n_pair_ticks[n] = *(long long*)(c.cold_i + COLD_PAIR_TICKS);
+    st.rss_flags[n] = (uint8_t)c.cold_i[COLD_RSS];
+  }
+  if (s < W) st.ego_hits[(int64_t)n * W + s] = c.ego_last[s];
+}
+
+SG_DEV RssConst make_rss_const(const SgParams& p) {
+  RssConst K;
+  K.CLR = p.rss_min_safe_clearance; K.RT = p.rss_response_time;
+  K.MAXA = p.rss_max_long_accel; K.MINA = p.rss_min_long_accel;
+  K.r2mina = 1.0 / (2 * p.rss_min_long_accel);
+  return K;
+}
+
+// ---------------------------------------------------------------------------------
+// Vehicle-only scenes (every live slot has a VehicleController; C3 / C5): a lean tick that
+// keeps x, y, h, their velocities, cos/sin of the heading, distance and speed in registers.
+// z, p, r never change under VehicleController._step (controller.py:122-131), so their
+// velocities are 0 after the first tick and they stay in global memory.
+// ---------------------------------------------------------------------------------
+template <bool RSS, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, GroupLayout L) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int G = L.G, M = sc.n_slots, W = L.W;
+  const int gpb = blockDim.x / G;
+  const int gl = threadIdx.x / G;
+  const int s = threadIdx.x - gl * G;
+  const int n = blockIdx.x * gpb + gl;
+  if (gl >= gpb || n >= sc.n_scenarios) return;
+  Grp c;
+  setup_group(c, sc, L, smem, gl, s, n);
+  const int64_t i = c.i, nm = c.nm;
+  const bool live = s < M && sc.kind[i] == SG_KIND_VEHICLE;
+  const int ego_slot = sc.ego_slot[n], first_slot = sc.first_slot[n];
+  const bool need_coll = (p.features & SG_FEAT_COLLISIONS) ||
+                         (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
+  const bool feat_rss = RSS && (p.features & SG_FEAT_RSS);
+  const bool matrix = (p.features & SG_FEAT_COLL_MATRIX) != 0;
+  const RssConst KR = make_rss_const(p);
+
+  double x = 0, y = 0, h = 0, vx = 0, vy = 0, vh = 0, vz = 0, dist = 0, speed = 0, cs = 1, sn = 0;
+  double bl = 1, rcp_bl = 1;
+  int orient_hint = 0;
+  bool present = false;
+  uint8_t collided = 0, rss_state = 0, rss_last = SG_RSS_NONE;
+  double sd[2] = {0, 0}, ratio[2] = {0, 0};
+  if (live) {
+    x = st.pose[i]; y = st.pose[nm + i]; h = st.pose[3 * nm + i];
+    vx = st.vel[i]; vy = st.vel[nm + i]; vz = st.vel[2 * nm + i]; vh = st.vel[3 * nm + i];
+    dist = st.dist[i]; speed = st.speed[i];
+    present = st.present[i] != 0;
+    collided = st.collided[i];
+    sincos(h, &sn, &cs);
+    const double bw = sc.box[i];
+    bl = sc.box[nm + i];
+    c.boxp[s] = bw; c.boxp[G + s] = bl;
+    c.boxp[2 * G + s] = sc.box[2 * nm + i]; c.boxp[3 * G + s] = sc.box[3 * nm + i];
+    rcp_bl = 1.0 / bl;
+    orient_hint = box_orientation_hint(bw, bl);
+    if (RSS) {
+      rss_state = st.rss_state[i]; rss_last = st.rss_last[i];
+      sd[0] = st.safe_dist[i]; sd[1] = st.safe_dist[nm + i];
+      ratio[0] = st.safe_ratio[i]; ratio[1] = st.safe_ratio[nm + i];
+    }
+  }
+  double t = st.t[n], prev_t = st.prev_t[n];
+  int tick = st.tick[n];
+  bool done = st.done[n] != 0;
+  const double length = sc.length[n];
+  double ox, oy;  // scenario origin for the fp32 bounds: the ego's first control point
+  {
+    const int64_t er = sc.traj_off[(int64_t)n * M + ego_slot];
+    ox = __ldg(sc.traj_rows + er * 7 + 1);
+    oy = __ldg(sc.traj_rows + er * 7 + 2);
+  }
+  load_cold(st, c, n, s, W, ego_slot);
+  group_sync(c);
+
+  int limit = n_ticks < 0 ? p.max_ticks : n_ticks;
+  if (limit > in.n_action_ticks) limit = in.n_action_ticks;
+  int parity = 0, ticks_run = 0;
+  const double* act = in.actions + i;
+  double a_accel = 0, a_steer = 0;  // the next tick's VehicleAction row is fetched a tick ahead
+  if (live && limit > 0 && !done) { a_accel = __ldcs(act); a_steer = __ldcs(act + nm); }
+
+  for (int k = 0; k < limit && !done; ++k) {
+    const double next_t = t + p.timestep;  // scenario_gym.py:229
+    const double dt = next_t - t;          // controller.py:123 and State.dt after the step
+    if (live && present) {  // VehicleController._step, controller.py:105-140
+      const double accel = np_clip(a_accel, -p.veh_max_accel, p.veh_max_accel);
+      const double steer = np_clip(a_steer, -p.veh_max_steer, p.veh_max_steer);
+      if (k + 1 < limit) {
+        a_accel = __ldcs(act + (int64_t)(k + 1) * 2 * nm);
+        a_steer = __ldcs(act + ((int64_t)(k + 1) * 2 + 1) * nm);
+      }
+      const double dx = speed * cs, dy = speed * sn;
+      const double dh = div_r(speed * tan(steer), bl, rcp_bl);
+      const double nx = x + dx * dt, ny = y + dy * dt, nh = h + dh * dt;
+      double ns = speed + accel * dt;
+      if (!p.veh_allow_reverse) ns = fmax(0.0, ns);
+      if (!isnan(p.veh_max_speed)) ns = fmin(p.veh_max_speed, ns);
+      speed = ns;
+      // State.update_statistics (state.py:230-239)
+      const double rdt = 1.0 / dt;
+      const double ex = nx - x, ey = ny - y, ehh = nh - h;
+      vx = div_r(ex, dt, rdt); vy = div_r(ey, dt, rdt); vh = div_r(ehh, dt, rdt);
+      vz = 0.0;
+      dist += norm3(ex, ey, 0.0);
+      x = nx; y = ny; h = nh;
+      sincos(h, &sn, &cs);
+    }
+    prev_t = t;
+    t = next_t;
+    tick += 1;
+    ticks_run += 1;
+    if (st.trace_cap > 0 && tick < st.trace_cap && s < M) {
+      st.trace_present[(int64_t)tick * nm + i] = present;
+      double* tp = st.trace_pose + (int64_t)tick * 6 * nm + i;
+      tp[0] = x; tp[nm] = y; tp[2 * nm] = st.pose[2 * nm + i]; tp[3 * nm] = h;
+      tp[4 * nm] = st.pose[4 * nm + i]; tp[5 * nm] = st.pose[5 * nm + i];
+      if (s == 0) st.trace_t[(int64_t)tick * sc.n_scenarios + n] = t;
+    }
+    if (s < M) {
+      if (need_coll || feat_rss) publish_box<RSS>(c, present, x, y, cs, sn, orient_hint, ox, oy);
+      if (matrix) {
+        uint32_t* row = st.coll_mask + ((int64_t)n * M + s) * W;
+        for (int w = 0; w < W; ++w) row[w] = 0;
+      }
+    }
+    if (RSS && feat_rss && s == ego_slot) publish_ego(c, present, x, y, cs, sn, vx, vy);
+    group_sync(c);
+    // ---- phase B1: callbacks (RSS) + broad phase
+    if (live && present) {
+      if (RSS && feat_rss) {  // RSSDistances.__call__, callback.py:57-122
+        rss_last = SG_RSS_NONE;
+        if (t != 0.0 && s != ego_slot && c.egop[EGO_PRESENT] != 0.0) {
+          rss_last = (uint8_t)rss_hazard(KR, c, x, y, vx, vy, rss_state, sd, ratio);
+          const int found = (rss_state >> 2) & 3;  // RSS metric latch, rss.py:71-103
+          if (found) atomicOr(&c.acc[parity * ACC_N + ACC_RSS], found == 2 ? 1 : 2);
+        }
+      }
+      if (need_coll) broad_phase(p.features, st.coll_mask, c, ego_slot, first_slot, parity);
+    }
+    group_sync(c);
+    done = finish_tick(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick, t, dt, length,
+                       live, collided, vx, vy, vz, dist);
+    parity ^= 1;
+  }
+
+  if (live) {
+    st.pose[i] = x; st.pose[nm + i] = y; st.pose[3 * nm + i] = h;
+    st.vel[i] = vx; st.vel[nm + i] = vy; st.vel[3 * nm + i] = vh;
+    if (ticks_run > 0 && present) { st.vel[2 * nm + i] = 0.0; st.vel[4 * nm + i] = 0.0; st.vel[5 * nm + i] = 0.0; }
+    st.dist[i] = dist;
+    st.speed[i] = speed;
+    st.collided[i] = collided;
+    if (RSS) {
+      st.rss_state[i] = rss_state; st.rss_last[i] = rss_last;
+      st.safe_dist[i] = sd[0]; st.safe_dist[nm + i] = sd[1];
+      st.safe_ratio[i] = ratio[0]; st.safe_ratio[nm + i] = ratio[1];
+    }
+  }
+  if (s == 0) { st.t[n] = t; st.prev_t[n] = prev_t; st.tick[n] = tick; st.done[n] = done; }
+  store_cold(st, c, n, s, W, ego_slot);
+}
+
+// ---------------------------------------------------------------------------------
+// General scenes: replay / batch replay / vehicles / pedestrians / host-driven slots.
+// ---------------------------------------------------------------------------------
 struct Ent {
   double pose[6], vel[6], dist, speed;
   bool present;
@@ -548,12 +886,18 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   const bool feat_rss = RSS && (p.features & SG_FEAT_RSS);
   const bool matrix = (p.features & SG_FEAT_COLL_MATRIX) != 0;
   const bool exact_div = kind <= SG_KIND_AGENT_REPLAY;  // replay kinds keep IEEE quotients
+  const RssConst KR = make_rss_const(p);
 
-  double bw = 1, bl = 1, bcx = 0, bcy = 0;
+  double bl = 1;
+  int orient_hint = 0;
   const double* rows = nullptr;
   int K = 0;
   if (kind != SG_KIND_EMPTY) {
-    bw = sc.box[i]; bl = sc.box[nm + i]; bcx = sc.box[2 * nm + i]; bcy = sc.box[3 * nm + i];
+    const double bw = sc.box[i];
+    bl = sc.box[nm + i];
+    c.boxp[s] = bw; c.boxp[G + s] = bl;
+    c.boxp[2 * G + s] = sc.box[2 * nm + i]; c.boxp[3 * G + s] = sc.box[3 * nm + i];
+    orient_hint = box_orientation_hint(bw, bl);
     const int64_t r0 = sc.traj_off[i];
     K = (int)(sc.traj_off[i + 1] - r0);
     rows = sc.traj_rows + r0 * 7;
@@ -597,24 +941,7 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     for (int f = 0; f < 6; ++f) { e.pose[f] = 0; e.vel[f] = 0; }
     e.dist = 0; e.speed = 0; e.present = false;
   }
-  double avg = 0, avg_t = 0, mx = 0, egod = 0;  // ego metrics (ego thread only)
-  if (s == ego_slot) {
-    avg = st.ego_avg_speed[n]; avg_t = st.ego_avg_t[n]; mx = st.ego_max_speed[n]; egod = st.ego_dist[n];
-  }
-  int first_tick = -1, fp0 = -1, fp1 = -1, rss_flags = 0;  // leader only
-  long long pair_ticks = 0;
-  if (s == 0) {
-    first_tick = st.first_coll_tick[n]; fp0 = st.first_coll_pair[2 * n]; fp1 = st.first_coll_pair[2 * n + 1];
-    pair_ticks = st.n_pair_ticks[n];
-    rss_flags = st.rss_flags[n];
-    for (int q = 0; q < 2 * ACC_N; ++q) c.acc[q] = 0;
-    c.acc[ACC_FIRST_PAIR] = 0x7fffffff; c.acc[ACC_N + ACC_FIRST_PAIR] = 0x7fffffff;
-  }
-  if (s < W) {
-    c.ego_last[s] = st.ego_hits[(int64_t)n * W + s];
-    c.ego_now[s] = 0;
-    c.bits[s] = 0; c.bits[W + s] = 0;
-  }
+  load_cold(st, c, n, s, W, ego_slot);
   if (live) {  // the "old" state the pedestrians' sensors read in the first tick
     c.flags[s] = (uint8_t)((e.present ? 1 : 0) | (etype << 1));
     if (PED) {
@@ -627,12 +954,6 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   int limit = n_ticks < 0 ? p.max_ticks : n_ticks;
   if (in.actions && limit > in.n_action_ticks) limit = in.n_action_ticks;
   int parity = 0;
-  // VehicleAction table: the next tick's row is fetched one tick ahead
-  double a_accel = 0, a_steer = 0;
-  if (kind == SG_KIND_VEHICLE && limit > 0 && !done) {
-    a_accel = __ldcs(in.actions + i);
-    a_steer = __ldcs(in.actions + nm + i);
-  }
 
   for (int k = 0; k < limit && !done; ++k) {
     // ---------------- phase A: agents / batch replay produce the new poses ----------------
@@ -640,19 +961,16 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     double np_[6];
     bool newpres = false;
     double newspeed = e.speed;
-    const double cur_accel = a_accel, cur_steer = a_steer;
-    if (kind == SG_KIND_VEHICLE && k + 1 < limit) {  // fetch the next tick's action row early
-      a_accel = __ldcs(in.actions + ((int64_t)(k + 1) * 2 + 0) * nm + i);
-      a_steer = __ldcs(in.actions + ((int64_t)(k + 1) * 2 + 1) * nm + i);
-    }
     if (kind >= SG_KIND_AGENT_REPLAY) {  // scenario_gym.py:233-244
       if (e.present) {
         if (kind == SG_KIND_AGENT_REPLAY) {  // agent.py:125-128, extrapolate=(False, False)
           position_at_t(rows, K, next_t, EXT_CLAMP, cur_own, np_);
           newpres = true;
         } else if (kind == SG_KIND_VEHICLE) {  // VehicleController._step, controller.py:105-140
-          const double accel = np_clip(cur_accel, -p.veh_max_accel, p.veh_max_accel);
-          const double steer = np_clip(cur_steer, -p.veh_max_steer, p.veh_max_steer);
+          const double accel = np_clip(__ldcs(in.actions + ((int64_t)k * 2 + 0) * nm + i),
+                                       -p.veh_max_accel, p.veh_max_accel);
+          const double steer = np_clip(__ldcs(in.actions + ((int64_t)k * 2 + 1) * nm + i),
+                                       -p.veh_max_steer, p.veh_max_steer);
           const double dt = next_t - t;
           double sh, ch;
           sincos(e.pose[3], &sh, &ch);
@@ -745,16 +1063,19 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       for (int f = 0; f < 6; ++f) st.trace_pose[((int64_t)tick * 6 + f) * nm + i] = e.pose[f];
       if (s == 0) st.trace_t[(int64_t)tick * sc.n_scenarios + n] = t;
     }
+    double hs = 0, hc = 1;
     if (live) {
-      if (need_coll || feat_rss)
-        publish_box<RSS>(c, e.present, e.pose[0], e.pose[1], e.pose[3], bw, bl, bcx, bcy, ox, oy);
+      if (need_coll || feat_rss) {
+        if (e.present) sincos(e.pose[3], &hs, &hc);
+        publish_box<RSS>(c, e.present, e.pose[0], e.pose[1], hc, hs, orient_hint, ox, oy);
+      }
       if (matrix) {
         uint32_t* row = st.coll_mask + ((int64_t)n * M + s) * W;
         for (int w = 0; w < W; ++w) row[w] = 0;
       }
     }
-    if (RSS && feat_rss && s == ego_slot) publish_ego(c, e.present, e.pose, e.vel, bw, bl);
-    if (matrix) __threadfence_block();
+    if (RSS && feat_rss && s == ego_slot)
+      publish_ego(c, e.present, e.pose[0], e.pose[1], hc, hs, e.vel[0], e.vel[1]);
     group_sync(c);
     // ---------------- phase B1: callbacks (RSS) + broad phase -------------------------------
     if (live) {
@@ -766,71 +1087,18 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       if (RSS && feat_rss) {  // RSSDistances.__call__, callback.py:57-122
         rss_last = SG_RSS_NONE;
         if (t != 0.0 && s != ego_slot && e.present && c.egop[EGO_PRESENT] != 0.0) {
-          rss_last = (uint8_t)rss_hazard(p, c, e.pose[0], e.pose[1], e.vel[0], e.vel[1], bw, bl,
-                                         rss_state, sd, ratio);
+          rss_last = (uint8_t)rss_hazard(KR, c, e.pose[0], e.pose[1], e.vel[0], e.vel[1], rss_state,
+                                         sd, ratio);
           const int found = (rss_state >> 2) & 3;  // RSS metric latch, rss.py:71-103
           if (found) atomicOr(&c.acc[parity * ACC_N + ACC_RSS], found == 2 ? 1 : 2);
         }
       }
-      if (need_coll && e.present) broad_phase(p, st, c, ego_slot, first_slot, parity);
+      if (need_coll && e.present)
+        broad_phase(p.features, st.coll_mask, c, ego_slot, first_slot, parity);
     }
     group_sync(c);
-    // ---------------- phase B2: exact narrow phase on the queued pairs ----------------------
-    int* acc = c.acc + parity * ACC_N;
-    const int nq = min(acc[ACC_QCOUNT], c.QCAP);
-    if (nq > 0) {
-      for (int q = s; q < nq; q += G) {
-        const uint32_t pr = c.queue[q];
-        record_pair(p, st, c, (int)(pr >> 16), (int)(pr & 0xffff), ego_slot, first_slot, parity);
-      }
-      group_sync(c);
-    }
-    // ---------------- phase C: terminal check + metrics ------------------------------------
-    const int npairs = acc[ACC_NPAIRS];
-    const int first_pair = acc[ACC_FIRST_PAIR];
-    const int first_hit = acc[ACC_FIRST_HIT];
-    const int rss_now = acc[ACC_RSS];
-    if (live && ((c.bits[parity * W + (s >> 5)] >> (s & 31)) & 1)) collided = 1;
-    bool dn = false;  // state.py:268-270, 397-408
-    if ((p.terminal & SG_TERM_MAX_LENGTH) && (t + dt > length)) dn = true;
-    if ((p.terminal & SG_TERM_COLLISION) && npairs > 0) dn = true;
-    if ((p.terminal & SG_TERM_EGO_COLLISION) && first_hit) dn = true;
-    done = dn;
-    if (s == 0) {
-      pair_ticks += npairs;
-      if (npairs > 0 && first_tick < 0) { first_tick = tick; fp0 = first_pair >> 16; fp1 = first_pair & 0xffff; }
-      rss_flags |= rss_now;
-      int* nx = c.acc + (parity ^ 1) * ACC_N;  // reset the other parity for the next tick
-      nx[ACC_NPAIRS] = 0; nx[ACC_FIRST_PAIR] = 0x7fffffff; nx[ACC_FIRST_HIT] = 0; nx[ACC_RSS] = 0;
-      nx[ACC_QCOUNT] = 0;
-    }
-    if (s < W) {  // CollisionMetric._step, metrics/collision.py:70-75
-      const uint32_t now = c.ego_now[s];
-      if (p.features & SG_FEAT_COLLISIONS) {
-        uint32_t fresh = now & ~c.ego_last[s];
-        while (fresh) {
-          const int b = __ffs(fresh) - 1;
-          fresh &= fresh - 1;
-          const int slot = atomicAdd(st.event_count, 1);
-          if (slot < st.event_cap) {
-            SgEvent ev;
-            ev.scenario = n; ev.tick = tick; ev.slot = s * 32 + b; ev._pad = 0; ev.t = t;
-            st.events[slot] = ev;
-          }
-        }
-        c.ego_last[s] = now;
-      }
-      c.ego_now[s] = 0;
-      c.bits[(parity ^ 1) * W + s] = 0;
-    }
-    if (s == ego_slot && (p.features & SG_FEAT_EGO_METRICS)) {  // metrics/trajectory.py:20-24,39-42,58-60
-      const double sp = norm3(e.vel[0], e.vel[1], e.vel[2]);
-      const double w = avg_t / t;
-      avg += (1.0 - w) * (sp - avg);
-      avg_t = t;
-      mx = fmax(sp, mx);
-      egod = e.dist;
-    }
+    done = finish_tick(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick, t, dt, length, live,
+                       collided, e.vel[0], e.vel[1], e.vel[2], e.dist);
     parity ^= 1;
   }
 
@@ -850,16 +1118,10 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       st.safe_ratio[i] = ratio[0]; st.safe_ratio[nm + i] = ratio[1];
     }
   }
-  if (s == ego_slot) {
-    st.ego_avg_speed[n] = avg; st.ego_avg_t[n] = avg_t; st.ego_max_speed[n] = mx; st.ego_dist[n] = egod;
-  }
   if (s == 0) {
     st.t[n] = t; st.prev_t[n] = prev_t; st.tick[n] = tick; st.done[n] = done; st.cur_union[n] = cur_union;
-    st.first_coll_tick[n] = first_tick; st.first_coll_pair[2 * n] = fp0; st.first_coll_pair[2 * n + 1] = fp1;
-    st.n_pair_ticks[n] = pair_ticks;
-    st.rss_flags[n] = (uint8_t)rss_flags;
   }
-  if (s < W) st.ego_hits[(int64_t)n * W + s] = c.ego_last[s];
+  store_cold(st, c, n, s, W, ego_slot);
 }
 
 // State.reset(t0) + Agent/Metric/StateCallback resets (reference state/state.py:106-143,
@@ -882,10 +1144,14 @@ sg_reset_kernel(SgScene sc, SgParams p, SgState st, GroupLayout L) {
   const int ego_slot = sc.ego_slot[n];
   const double t = sc.t0[n];
   double pose[6] = {0, 0, 0, 0, 0, 0}, vel[6] = {0, 0, 0, 0, 0, 0};
-  double bw = 1, bl = 1, bcx = 0, bcy = 0, speed = 0;
+  double speed = 0;
+  int orient_hint = 0;
   bool present = false;
   if (kind != SG_KIND_EMPTY) {
-    bw = sc.box[i]; bl = sc.box[nm + i]; bcx = sc.box[2 * nm + i]; bcy = sc.box[3 * nm + i];
+    const double bw = sc.box[i], bl = sc.box[nm + i];
+    c.boxp[s] = bw; c.boxp[G + s] = bl;
+    c.boxp[2 * G + s] = sc.box[2 * nm + i]; c.boxp[3 * G + s] = sc.box[3 * nm + i];
+    orient_hint = box_orientation_hint(bw, bl);
     const int64_t r0 = sc.traj_off[i];
     const int K = (int)(sc.traj_off[i + 1] - r0);
     const double* rows = sc.traj_rows + r0 * 7;
@@ -904,6 +1170,7 @@ sg_reset_kernel(SgScene sc, SgParams p, SgState st, GroupLayout L) {
   int rss_flags = 0;
   const bool feat_rss = RSS && (p.features & SG_FEAT_RSS);
   if (RSS && feat_rss) {  // update_callbacks() at reset, state.py:137-139
+    const RssConst KR = make_rss_const(p);
     double ox, oy;
     {
       const int64_t er = sc.traj_off[(int64_t)n * M + ego_slot];
@@ -911,11 +1178,13 @@ sg_reset_kernel(SgScene sc, SgParams p, SgState st, GroupLayout L) {
       oy = __ldg(sc.traj_rows + er * 7 + 2);
     }
     if (s == 0) c.acc[ACC_RSS] = 0;
-    if (live) publish_box<RSS>(c, present, pose[0], pose[1], pose[3], bw, bl, bcx, bcy, ox, oy);
-    if (s == ego_slot) publish_ego(c, present, pose, vel, bw, bl);
+    double hs = 0, hc = 1;
+    if (live && present) sincos(pose[3], &hs, &hc);
+    if (live) publish_box<RSS>(c, present, pose[0], pose[1], hc, hs, orient_hint, ox, oy);
+    if (s == ego_slot) publish_ego(c, present, pose[0], pose[1], hc, hs, vel[0], vel[1]);
     group_sync(c);
     if (live && t != 0.0 && s != ego_slot && present && c.egop[EGO_PRESENT] != 0.0) {
-      rss_last = (uint8_t)rss_hazard(p, c, pose[0], pose[1], vel[0], vel[1], bw, bl, rss_state, sd, ratio);
+      rss_last = (uint8_t)rss_hazard(KR, c, pose[0], pose[1], vel[0], vel[1], rss_state, sd, ratio);
       const int found = (rss_state >> 2) & 3;
       if (found) atomicOr(&c.acc[ACC_RSS], found == 2 ? 1 : 2);
     }
@@ -1014,6 +1283,19 @@ static cudaError_t launch_rollout(bool big, int blocks, int threads, size_t smem
   return cudaGetLastError();
 }
 
+template <bool RSS>
+static cudaError_t launch_vehicle(bool big, int blocks, int threads, size_t smem, cudaStream_t s,
+                                  const SgScene& sc, const SgParams& p, const SgState& st,
+                                  const SgInputs& in, int n_ticks, const GroupLayout& L) {
+  auto kern = big ? sg_vehicle_kernel<RSS, 1024, 1> : sg_vehicle_kernel<RSS, SG_THREADS, SG_VEH_MINB>;
+  if (smem > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+  }
+  kern<<<blocks, threads, smem, s>>>(sc, p, st, in, n_ticks, L);
+  return cudaGetLastError();
+}
+
 static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInputs* in, int n_ticks,
                   int device, void* stream, int reset) {
   if (!sc || !p || !st) return set_msg("null argument");
@@ -1042,7 +1324,13 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
   SgInputs none;
   memset(&none, 0, sizeof(none));
   const SgInputs inp = in ? *in : none;
-  if (ped && rss) err = launch_rollout<true, true>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
+  const uint32_t veh_bits = (1u << SG_KIND_VEHICLE), ok_bits = veh_bits | (1u << SG_KIND_EMPTY);
+  const bool veh_only = (sc->kind_mask & veh_bits) && !(sc->kind_mask & ~ok_bits);
+  if (veh_only) {
+    if (!inp.actions) return set_msg("vehicle scene needs an action table");
+    err = rss ? launch_vehicle<true>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L)
+              : launch_vehicle<false>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
+  } else if (ped && rss) err = launch_rollout<true, true>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
   else if (ped) err = launch_rollout<true, false>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
   else if (rss) err = launch_rollout<false, true>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
   else err = launch_rollout<false, false>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);

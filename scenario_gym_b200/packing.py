@@ -123,6 +123,23 @@ class PackedScene:
     def arrays(self):
         return {k: getattr(self, k) for k in abi.SCENE_FIELDS}
 
+    def kind_mask(self) -> int:
+        """SgScene.kind_mask: OR of (1 << kind), or 0 when the vehicle fast path's promise
+        (every vehicle slot present at reset) does not hold."""
+        kinds = np.unique(self.kind)
+        mask = 0
+        for k in kinds:
+            mask |= 1 << int(k)
+        if mask & ~((1 << abi.KIND_EMPTY) | (1 << abi.KIND_VEHICLE)) == 0 and mask & (1 << abi.KIND_VEHICLE):
+            veh = np.nonzero(self.kind == abi.KIND_VEHICLE)[0]
+            first = self.traj_rows[self.traj_off[veh], 0]
+            last = self.traj_rows[self.traj_off[veh + 1] - 1, 0]
+            t0 = np.repeat(self.t0, self.M)[veh]
+            single = (self.traj_off[veh + 1] - self.traj_off[veh]) == 1
+            if not np.all(single | ((first <= t0) & (t0 <= last))):
+                return 0
+        return mask
+
     def nbytes(self) -> int:
         return int(sum(a.nbytes for a in self.arrays().values()))
 
