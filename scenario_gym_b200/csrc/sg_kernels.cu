@@ -48,7 +48,7 @@ struct GroupLayout {
   int W;        // 32-bit words per collision row
   int H;        // half-sweep length M/2
   int QCAP;     // candidate-pair queue capacity
-  int off_hcs, off_ped, off_box, off_ego, off_cold, off_aabb, off_queue, off_hits, off_bits,
+  int off_act, off_hcs, off_ped, off_box, off_ego, off_cold, off_aabb, off_queue, off_hits, off_bits,
       off_acc, off_flags, off_orient;
   int bytes;
 };
@@ -68,6 +68,7 @@ static GroupLayout make_layout(int M, bool ped, bool rss) {
   L.H = M / 2;
   L.QCAP = 4 * G;
   int o = 8 * G * (int)sizeof(double);                            // corners[8][G]
+  L.off_act = o;    o += 4 * G * (int)sizeof(double);             // VehicleAction rows, 2 stages x (accel, steer)
   L.off_hcs = o;    o += rss ? 2 * G * (int)sizeof(double) : 0;   // cos/sin of each heading
   L.off_ped = o;    o += ped ? 4 * G * (int)sizeof(double) : 0;   // old x,y,vx,vy (pedestrian sensors)
   L.off_box = o;    o += 4 * G * (int)sizeof(double);             // width, length, center_x, center_y
@@ -89,6 +90,7 @@ struct Grp {
   unsigned mask;
   int64_t i, nm;
   double* corners;
+  double* actbuf;
   double* hcs;
   double* pedbuf;
   double* boxp;
@@ -105,6 +107,13 @@ struct Grp {
   int8_t* orient;
 };
 
+SG_DEV void cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a), "l"(gsrc) : "memory");
+}
+SG_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+SG_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 SG_DEV void group_sync(const Grp& g) {
   if (g.G <= 32) __syncwarp(g.mask);
   else asm volatile("bar.sync %0, %1;" ::"r"(g.bar_id), "r"(g.G) : "memory");
@@ -120,6 +129,7 @@ SG_DEV void setup_group(Grp& g, const SgScene& sc, const GroupLayout& L, unsigne
   g.nm = (int64_t)sc.n_scenarios * sc.n_slots;
   g.i = (int64_t)n * sc.n_slots + s;
   g.corners = (double*)base;
+  g.actbuf = (double*)(base + L.off_act);
   g.hcs = (double*)(base + L.off_hcs);
   g.pedbuf = (double*)(base + L.off_ped);
   g.boxp = (double*)(base + L.off_box);
@@ -144,18 +154,71 @@ SG_DEV double div_r(double n, double d, double r) {
   return __fma_rn(rem, r, q);
 }
 
-// conservative fp32 AABB of the fp64 corners, relative to the scenario origin (ox, oy)
-SG_DEV float4 make_aabb(const double* c, double ox, double oy) {
-  const double lox = fmin(fmin(c[0], c[2]), fmin(c[4], c[6]));
-  const double hix = fmax(fmax(c[0], c[2]), fmax(c[4], c[6]));
-  const double loy = fmin(fmin(c[1], c[3]), fmin(c[5], c[7]));
-  const double hiy = fmax(fmax(c[1], c[3]), fmax(c[5], c[7]));
+// Conservative fp32 AABB (relative to the scenario origin) of the box whose fp64 corners
+// publish_box stages: centre +- (|L/2 c| + |W/2 s|, |L/2 s| + |W/2 c|), widened by 32 ulp of the
+// coordinate magnitudes (covers the rounding of the reference's corner formula, ~6 ulp) and
+// rounded outwards at every step.  Costs ~20 flops instead of 12 fp64 min/max sequences.
+SG_DEV float4 make_aabb_box(double x, double y, double cs, double sn, double bw, double bl,
+                            double bcx, double bcy, double ox, double oy) {
+  const double xc = x + (bcx * cs - bcy * sn), yc = y + (bcx * sn + bcy * cs);
+  const double hl = 0.5 * bl, hw = 0.5 * bw;
+  const double m = 3.552713678800501e-15 *
+                   (fabs(x) + fabs(y) + fabs(bl) + fabs(bw) + fabs(bcx) + fabs(bcy));
+  const double ex = fabs(hl * cs) + fabs(hw * sn) + m, ey = fabs(hl * sn) + fabs(hw * cs) + m;
   float4 b;
-  b.x = __double2float_rd(__dsub_rd(lox, ox));
-  b.y = __double2float_rd(__dsub_rd(loy, oy));
-  b.z = __double2float_ru(__dsub_ru(hix, ox));
-  b.w = __double2float_ru(__dsub_ru(hiy, oy));
+  b.x = __double2float_rd(__dsub_rd(__dsub_rd(xc, ex), ox));
+  b.y = __double2float_rd(__dsub_rd(__dsub_rd(yc, ey), oy));
+  b.z = __double2float_ru(__dsub_ru(__dadd_ru(xc, ex), ox));
+  b.w = __double2float_ru(__dsub_ru(__dadd_ru(yc, ey), oy));
   return b;
+}
+
+SG_DEV double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// sin / cos kernels on |x| <= pi/4 (fdlibm k_sin.c / k_cos.c minimax polynomials, < 1 ulp),
+// coefficients read from the constant bank instead of 64-bit immediates
+__constant__ double c_trig[12] = {
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03,  -1.98412698298579493134e-04,
+    2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11};
+SG_DEV void sincos_kernel(double x, double& sn, double& cs) {
+  const double z = x * x;
+  const double* S = c_trig;
+  const double* C = c_trig + 6;
+  double r = __fma_rn(z, S[5], S[4]);
+  r = __fma_rn(z, r, S[3]);
+  r = __fma_rn(z, r, S[2]);
+  r = __fma_rn(z, r, S[1]);
+  r = __fma_rn(z, r, S[0]);
+  sn = __fma_rn(x * z, r, x);
+  double q = __fma_rn(z, C[5], C[4]);
+  q = __fma_rn(z, q, C[3]);
+  q = __fma_rn(z, q, C[2]);
+  q = __fma_rn(z, q, C[1]);
+  q = __fma_rn(z, q, C[0]);
+  const double hz = 0.5 * z, w = 1.0 - hz;
+  cs = w + (((1.0 - w) - hz) + z * (z * q));
+}
+// tan on |x| <= pi/4 (steering angles are clipped to +-max_steer)
+SG_DEV double tan_small(double x) {
+  double sn, cs;
+  sincos_kernel(x, sn, cs);
+  return sn / cs;
+}
+// sincos with a 3-term Cody-Waite reduction (exact under FMA for |x| < 1e9)
+SG_DEV void sincos_fast(double x, double& sn, double& cs) {
+  if (!(fabs(x) < 1.0e9)) { sincos(x, &sn, &cs); return; }
+  const double kd = rint(x * 0.63661977236758138);
+  double r = __fma_rn(-kd, 1.5707963267948966, x);
+  r = __fma_rn(-kd, 6.123233995736766e-17, r);
+  r = __fma_rn(-kd, -1.4973849048591698e-33, r);
+  double a, b;
+  sincos_kernel(r, a, b);
+  const int k = (int)kd;
+  const double s0 = (k & 1) ? b : a, c0 = (k & 1) ? a : b;
+  sn = (k & 2) ? -s0 : s0;
+  cs = ((k + 1) & 2) ? -c0 : c0;
 }
 
 // strict interior of Point(x, y).buffer(r): GEOS 64-gon (reference state/state.py:352-372)
@@ -300,7 +363,7 @@ SG_DEV void publish_box(const Grp& c, bool present, double x, double y, double c
     for (int f = 0; f < 8; ++f) c.corners[f * c.G + c.s] = my[f];
     if (RSS) { c.hcs[c.s] = cs; c.hcs[c.G + c.s] = sn; }
     c.orient[c.s] = (int8_t)(orient_hint ? orient_hint : quad_orientation(my));
-    bb = make_aabb(my, ox, oy);
+    bb = make_aabb_box(x, y, cs, sn, bw, bl, bcx, bcy, ox, oy);
   }
   c.aabb[c.s] = bb;
   if (c.s < c.H + 1) c.aabb[c.M + c.s] = bb;
@@ -555,9 +618,21 @@ __device__ __noinline__ void record_pair(int features, uint32_t* coll_mask, cons
   }
 }
 
-// circular half sweep over the staged AABBs; survivors go to the scenario's queue
-SG_DEV void broad_phase(int features, uint32_t* coll_mask, const Grp& c, int ego_slot,
-                        int first_slot, int parity) {
+// closed-interval overlap of two conservative AABBs as one predicate chain; sets bit `bit`
+#define SG_AABB_TEST(hits, mb, ob, bit)                                                         \
+  asm("{ .reg .pred p;\n\t"                                                                     \
+      "setp.le.f32 p, %1, %2;\n\t"                                                              \
+      "setp.le.and.f32 p, %3, %4, p;\n\t"                                                       \
+      "setp.le.and.f32 p, %5, %6, p;\n\t"                                                       \
+      "setp.le.and.f32 p, %7, %8, p;\n\t"                                                       \
+      "@p or.b32 %0, %0, %9; }"                                                                  \
+      : "+r"(hits)                                                                              \
+      : "f"(mb.x), "f"(ob.z), "f"(ob.x), "f"(mb.z), "f"(mb.y), "f"(ob.w), "f"(ob.y), "f"(mb.w), \
+        "r"(bit))
+
+// circular half sweep over the staged AABBs (STRtree's envelope filter is closed too);
+// survivors go to the scenario's queue
+SG_DEV void broad_phase(const Grp& c, int parity) {
   const float4 mb = c.aabb[c.s];
   const float4* nb = c.aabb + c.s + 1;
   int* acc = c.acc + parity * ACC_N;
@@ -568,15 +643,12 @@ SG_DEV void broad_phase(int features, uint32_t* coll_mask, const Grp& c, int ego
 #pragma unroll
       for (int dd = 0; dd < 32; ++dd) {
         const float4 ob = nb[d0 + dd];
-        // closed-interval overlap of conservative bounds (STRtree's envelope filter is closed too)
-        const bool h = mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w;
-        hits |= (h ? 1u : 0u) << dd;
+        SG_AABB_TEST(hits, mb, ob, 1u << dd);
       }
     } else {
       for (int dd = 0; dd < dn; ++dd) {
         const float4 ob = nb[d0 + dd];
-        const bool h = mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w;
-        hits |= (h ? 1u : 0u) << dd;
+        SG_AABB_TEST(hits, mb, ob, 1u << dd);
       }
     }
     while (hits) {
@@ -588,23 +660,40 @@ SG_DEV void broad_phase(int features, uint32_t* coll_mask, const Grp& c, int ego
       if (2 * d == c.M && c.s > j) continue;  // the antipodal pair is seen from both ends
       const int q = atomicAdd(&acc[ACC_QCOUNT], 1);
       if (q < c.QCAP) c.queue[q] = ((uint32_t)c.s << 16) | (uint32_t)j;
-      else record_pair(features, coll_mask, c, c.s, j, ego_slot, first_slot, parity);  // queue full
     }
+  }
+}
+
+// queue overflow (very dense scenes): redo the sweep and test every survivor in place
+__device__ __noinline__ void broad_phase_direct(int features, uint32_t* coll_mask, const Grp& c,
+                                                int ego_slot, int first_slot, int parity) {
+  const float4 mb = c.aabb[c.s];
+  for (int d = 1; d <= c.H; ++d) {
+    const float4 ob = c.aabb[c.s + d];
+    if (!(mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w)) continue;
+    int j = c.s + d;
+    if (j >= c.M) j -= c.M;
+    if (2 * d == c.M && c.s > j) continue;
+    record_pair(features, coll_mask, c, c.s, j, ego_slot, first_slot, parity);
   }
 }
 
 // phases B2 + C, shared by both kernel flavours.  Returns state.is_done.
 SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int n, int s, int W,
                         int G, int ego_slot, int first_slot, int parity, int tick, double t,
-                        double dt, double length, bool live, uint8_t& collided, double vx,
-                        double vy, double vz, double dist) {
+                        double dt, double length, bool live, bool present, uint8_t& collided,
+                        double vx, double vy, double vz, double dist) {
   int* acc = c.acc + parity * ACC_N;
-  const int nq = min(acc[ACC_QCOUNT], c.QCAP);
+  const int nq = acc[ACC_QCOUNT];
   if (nq > 0) {  // phase B2: exact narrow phase on the queued pairs
-    for (int q = s; q < nq; q += G) {
-      const uint32_t pr = c.queue[q];
-      record_pair(p.features, st.coll_mask, c, (int)(pr >> 16), (int)(pr & 0xffff), ego_slot,
-                  first_slot, parity);
+    if (nq <= c.QCAP) {
+      for (int q = s; q < nq; q += G) {
+        const uint32_t pr = c.queue[q];
+        record_pair(p.features, st.coll_mask, c, (int)(pr >> 16), (int)(pr & 0xffff), ego_slot,
+                    first_slot, parity);
+      }
+    } else if (present) {
+      broad_phase_direct(p.features, st.coll_mask, c, ego_slot, first_slot, parity);
     }
     group_sync(c);
   }
@@ -741,7 +830,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     dist = st.dist[i]; speed = st.speed[i];
     present = st.present[i] != 0;
     collided = st.collided[i];
-    sincos(h, &sn, &cs);
+    sincos_fast(h, sn, cs);
     const double bw = sc.box[i];
     bl = sc.box[nm + i];
     c.boxp[s] = bw; c.boxp[G + s] = bl;
@@ -770,26 +859,33 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   int limit = n_ticks < 0 ? p.max_ticks : n_ticks;
   if (limit > in.n_action_ticks) limit = in.n_action_ticks;
   int parity = 0, ticks_run = 0;
+  // VehicleAction rows are staged one tick ahead with cp.async (no registers held)
   const double* act = in.actions + i;
-  double a_accel = 0, a_steer = 0;  // the next tick's VehicleAction row is fetched a tick ahead
-  if (live && limit > 0 && !done) { a_accel = __ldcs(act); a_steer = __ldcs(act + nm); }
+  double* ab = c.actbuf + s;
+  if (live && limit > 0 && !done) { cp_async8(ab, act); cp_async8(ab + G, act + nm); }
+  cp_async_commit();
 
   for (int k = 0; k < limit && !done; ++k) {
     const double next_t = t + p.timestep;  // scenario_gym.py:229
     const double dt = next_t - t;          // controller.py:123 and State.dt after the step
+    cp_async_wait_all();
+    const double a_accel = ab[(k & 1) * 2 * G], a_steer = ab[(k & 1) * 2 * G + G];
+    if (live && k + 1 < limit) {
+      const double* nxt = act + (int64_t)(k + 1) * 2 * nm;
+      cp_async8(ab + ((k + 1) & 1) * 2 * G, nxt);
+      cp_async8(ab + ((k + 1) & 1) * 2 * G + G, nxt + nm);
+    }
+    cp_async_commit();
     if (live && present) {  // VehicleController._step, controller.py:105-140
-      const double accel = np_clip(a_accel, -p.veh_max_accel, p.veh_max_accel);
-      const double steer = np_clip(a_steer, -p.veh_max_steer, p.veh_max_steer);
-      if (k + 1 < limit) {
-        a_accel = __ldcs(act + (int64_t)(k + 1) * 2 * nm);
-        a_steer = __ldcs(act + ((int64_t)(k + 1) * 2 + 1) * nm);
-      }
+      const double accel = clipd(a_accel, -p.veh_max_accel, p.veh_max_accel);
+      const double steer = clipd(a_steer, -p.veh_max_steer, p.veh_max_steer);
       const double dx = speed * cs, dy = speed * sn;
-      const double dh = div_r(speed * tan(steer), bl, rcp_bl);
+      const double tn = fabs(steer) <= 0.78 ? tan_small(steer) : tan(steer);
+      const double dh = div_r(speed * tn, bl, rcp_bl);
       const double nx = x + dx * dt, ny = y + dy * dt, nh = h + dh * dt;
       double ns = speed + accel * dt;
-      if (!p.veh_allow_reverse) ns = fmax(0.0, ns);
-      if (!isnan(p.veh_max_speed)) ns = fmin(p.veh_max_speed, ns);
+      if (!p.veh_allow_reverse) ns = ns < 0.0 ? 0.0 : ns;
+      if (p.veh_max_speed == p.veh_max_speed) ns = ns > p.veh_max_speed ? p.veh_max_speed : ns;
       speed = ns;
       // State.update_statistics (state.py:230-239)
       const double rdt = 1.0 / dt;
@@ -798,7 +894,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       vz = 0.0;
       dist += norm3(ex, ey, 0.0);
       x = nx; y = ny; h = nh;
-      sincos(h, &sn, &cs);
+      sincos_fast(h, sn, cs);
     }
     prev_t = t;
     t = next_t;
@@ -830,11 +926,11 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
           if (found) atomicOr(&c.acc[parity * ACC_N + ACC_RSS], found == 2 ? 1 : 2);
         }
       }
-      if (need_coll) broad_phase(p.features, st.coll_mask, c, ego_slot, first_slot, parity);
+      if (need_coll) broad_phase(c, parity);
     }
     group_sync(c);
     done = finish_tick(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick, t, dt, length,
-                       live, collided, vx, vy, vz, dist);
+                       live, live && present, collided, vx, vy, vz, dist);
     parity ^= 1;
   }
 
@@ -1093,12 +1189,11 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
           if (found) atomicOr(&c.acc[parity * ACC_N + ACC_RSS], found == 2 ? 1 : 2);
         }
       }
-      if (need_coll && e.present)
-        broad_phase(p.features, st.coll_mask, c, ego_slot, first_slot, parity);
+      if (need_coll && e.present) broad_phase(c, parity);
     }
     group_sync(c);
     done = finish_tick(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick, t, dt, length, live,
-                       collided, e.vel[0], e.vel[1], e.vel[2], e.dist);
+                       live && e.present, collided, e.vel[0], e.vel[1], e.vel[2], e.dist);
     parity ^= 1;
   }
 
