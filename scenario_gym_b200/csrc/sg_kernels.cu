@@ -173,6 +173,8 @@ SG_DEV float4 make_aabb_box(double x, double y, double cs, double sn, double bw,
   return b;
 }
 
+SG_DEV double min2(double a, double b) { return a < b ? a : b; }
+SG_DEV double max2(double a, double b) { return a > b ? a : b; }
 SG_DEV double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // sin / cos kernels on |x| <= pi/4 (fdlibm k_sin.c / k_cos.c minimax polynomials, < 1 ulp),
@@ -369,28 +371,39 @@ SG_DEV void publish_box(const Grp& c, bool present, double x, double y, double c
   if (c.s < c.H + 1) c.aabb[c.M + c.s] = bb;
 }
 
+// the ego's box dimensions and the reciprocals safe_ratios divides by (once per launch)
+SG_DEV void publish_ego_box(const Grp& c) {
+  const double eW = c.boxp[c.s], eL = c.boxp[c.G + c.s];
+  c.egop[EGO_W] = eW; c.egop[EGO_L] = eL;
+  c.egop[EGO_RHW] = 1.0 / (0.5 * eW); c.egop[EGO_RHL] = 1.0 / (0.5 * eL);
+}
+
 // ego parameters in its own frame (reference metrics/rss/callback.py:73-97, 340-386)
 SG_DEV void publish_ego(const Grp& c, bool present, double x, double y, double ec, double es,
                         double vx, double vy) {
-  const double eh[2] = {ec, es};
   double einv[2];
-  inverse_direction(eh, einv);
+  {  // inverse_direction((cos h, sin h)), rss_utils.py:7-21
+    const double nn = norm2(es, ec), rn = 1.0 / nn;
+    einv[0] = div_r(es, nn, rn);
+    einv[1] = div_r(-ec, nn, rn);
+  }
   double* E = c.egop;
   E[EGO_X] = x; E[EGO_Y] = y;
   E[EGO_C] = ec; E[EGO_S] = es;
   E[EGO_INV0] = einv[0]; E[EGO_INV1] = einv[1];
   const double hd[2] = {dot2(ec, es, einv[0], einv[1]), dot2(ec, es, ec, es)};
   E[EGO_HD0] = hd[0]; E[EGO_HD1] = hd[1];
-  double hinv[2];
-  inverse_direction(hd, hinv);  // used by safe_lateral_distance for every hazard
+  double hinv[2];  // inverse_direction(ego-frame heading): used by safe_lateral_distance
+  {
+    const double nn = norm2(hd[1], hd[0]), rn = 1.0 / nn;
+    hinv[0] = div_r(hd[1], nn, rn);
+    hinv[1] = div_r(-hd[0], nn, rn);
+  }
   E[EGO_HINV0] = hinv[0]; E[EGO_HINV1] = hinv[1];
   const double v0 = dot2(vx, vy, einv[0], einv[1]), v1 = dot2(vx, vy, ec, es);
   E[EGO_V0] = v0; E[EGO_V1] = v1;
   E[EGO_VNORM] = norm2(v0, v1);
   E[EGO_VLONG] = fabs(dot2(v0, v1, hd[0], hd[1]));
-  const double eW = c.boxp[c.s], eL = c.boxp[c.G + c.s];
-  E[EGO_W] = eW; E[EGO_L] = eL;
-  E[EGO_RHW] = 1.0 / (0.5 * eW); E[EGO_RHL] = 1.0 / (0.5 * eL);
   E[EGO_PRESENT] = present ? 1.0 : 0.0;
 }
 
@@ -430,6 +443,22 @@ SG_DEV bool quad_hits_centered_rect(const double* q, double a, double b) {
     const double py = ((o > 0) == (dx > 0) || dx == 0) ? b : -b;
     const double px = ((o > 0) == (dy > 0) && dy != 0) ? -a : a;
     if (orient_sign(ax, ay, bx, by, px, py) * o < 0) return false;  // every corner strictly outside
+  }
+  return true;
+}
+
+// Closed intersection of a convex quad with the horizontal segment y = c, |x| <= w, when the
+// quad's y-range already contains c: the quad's corners are then not strictly on one side of
+// the segment's line, so the segment misses the quad iff some quad edge has both segment
+// endpoints strictly outside.  (Exact: 8 orientation signs.)
+SG_DEV bool quad_hits_hsegment(const double* q, double w, double c) {
+  const int o = quad_orientation(q);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double ax = q[2 * k], ay = q[2 * k + 1];
+    const double bx = q[2 * ((k + 1) & 3)], by = q[2 * ((k + 1) & 3) + 1];
+    if (orient_sign(ax, ay, bx, by, -w, c) * o < 0 && orient_sign(ax, ay, bx, by, w, c) * o < 0)
+      return false;
   }
   return true;
 }
@@ -526,10 +555,10 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
     box[2 * q] = dot2(c0, c1, ei0, ei1);
     box[2 * q + 1] = dot2(c0, c1, eh0, eh1);
   }
-  const double bxmin = fmin(fmin(box[0], box[2]), fmin(box[4], box[6]));
-  const double bxmax = fmax(fmax(box[0], box[2]), fmax(box[4], box[6]));
-  const double bymin = fmin(fmin(box[1], box[3]), fmin(box[5], box[7]));
-  const double bymax = fmax(fmax(box[1], box[3]), fmax(box[5], box[7]));
+  const double bxmin = min2(min2(box[0], box[2]), min2(box[4], box[6]));
+  const double bxmax = max2(max2(box[0], box[2]), max2(box[4], box[6]));
+  const double bymin = min2(min2(box[1], box[3]), min2(box[5], box[7]));
+  const double bymax = max2(max2(box[1], box[3]), max2(box[5], box[7]));
   bool inter = false;
   if (!(bxmin > slat || bxmax < -slat || bymin > slong || bymax < -slong)) {
     bool corner_in = false;  // a hazard corner inside the closed buffer decides at once
@@ -568,10 +597,8 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
     if (bxmin > -W100 && bxmax < W100) {  // box inside the segments' x-range: segment <=> line y = c
       lon = (bymin <= slong && slong <= bymax) || (bymin <= -slong && -slong <= bymax);
     } else {
-      if (!(bymin > slong || bymax < slong))
-        lon = rss_box_hits_segment(box, W100, slong, 100 * -slat, slong);
-      if (!lon && !(bymin > -slong || bymax < -slong))
-        lon = rss_box_hits_segment(box, 100 * -slat, -slong, W100, -slong);
+      if (!(bymin > slong || bymax < slong)) lon = quad_hits_hsegment(box, W100, slong);
+      if (!lon && !(bymin > -slong || bymax < -slong)) lon = quad_hits_hsegment(box, W100, -slong);
     }
   }
   if (lat && lon) return SG_RSS_BOTH;
@@ -854,6 +881,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     oy = __ldg(sc.traj_rows + er * 7 + 2);
   }
   load_cold(st, c, n, s, W, ego_slot);
+  if (RSS && s == ego_slot) publish_ego_box(c);
   group_sync(c);
 
   int limit = n_ticks < 0 ? p.max_ticks : n_ticks;
@@ -1038,6 +1066,7 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     e.dist = 0; e.speed = 0; e.present = false;
   }
   load_cold(st, c, n, s, W, ego_slot);
+  if (RSS && s == ego_slot) publish_ego_box(c);
   if (live) {  // the "old" state the pedestrians' sensors read in the first tick
     c.flags[s] = (uint8_t)((e.present ? 1 : 0) | (etype << 1));
     if (PED) {
@@ -1273,6 +1302,7 @@ sg_reset_kernel(SgScene sc, SgParams p, SgState st, GroupLayout L) {
       oy = __ldg(sc.traj_rows + er * 7 + 2);
     }
     if (s == 0) c.acc[ACC_RSS] = 0;
+    if (s == ego_slot) publish_ego_box(c);
     double hs = 0, hc = 1;
     if (live && present) sincos(pose[3], &hs, &hc);
     if (live) publish_box<RSS>(c, present, pose[0], pose[1], hc, hs, orient_hint, ox, oy);
