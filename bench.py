@@ -42,7 +42,7 @@ UNIT = "entity-steps/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c5"])
@@ -122,7 +122,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -423,12 +423,13 @@ def run_b200(args):
         traffic = tj.get(key)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "kernel": "sg_rollout_kernel", "kernel_ms": kern_ms, "reset_kernel_ms": reset_ms,
+        "traffic": traffic, "kernel": "sg_vehicle_kernel<RSS=%d>" % (0 if args.no_rss else 1), "kernel_ms": kern_ms, "reset_kernel_ms": reset_ms,
         "algorithmic_bytes_per_entity_step": bpe, "entity_steps_per_launch": steps_per_rollout,
         "peak_source": peak_src,
-        "note": "achieved = SURVEY 8d per-tick-streaming bytes x entity-steps / kernel time; the fused "
-                "kernel keeps State rows in registers across ticks, so its real DRAM traffic is far lower "
-                "(see traffic) and the bounding resource is the FP64 pipe (profiles/)",
+        "note": "achieved = SURVEY 8d per-tick-streaming bytes (B_tick) x entity-steps / kernel time, "
+                "of measured HBM copy bandwidth; the fused kernel keeps State rows in registers across "
+                "ticks, so its real DRAM traffic (traffic, from ncu) is ~14x lower than B_tick and the "
+                "kernel is issue/FP64-latency bound, not HBM bound (profiles/)",
     }
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -150,42 +150,59 @@ SG_DEV int orient_sign(double ax, double ay, double bx, double by, double cx, do
   return orient_exact(ax, ay, bx, by, cx, cy);
 }
 
-// ring orientation of a convex quad q[8] = x0,y0,..,x3,y3 : +1 ccw, -1 cw, 0 degenerate
-SG_DEV int quad_orientation(const double* q) {
-  int s = orient_sign(q[0], q[1], q[2], q[3], q[4], q[5]);
-  if (s == 0) s = orient_sign(q[2], q[3], q[4], q[5], q[6], q[7]);
+// The quad routines read corner k of a quad at q[2k*st] (x) and q[(2k+1)*st] (y): st = 1 for a
+// local array, st = G for the group's staged corners in shared memory.  They are out of line
+// with rolled loops on purpose: they run on the rare path (AABB survivors, RSS boundary cases)
+// with few active lanes, and keeping a single copy of the orientation predicate keeps the tick
+// loop's instruction footprint small.
+
+// ring orientation of a convex quad: +1 ccw, -1 cw, 0 degenerate
+__device__ __noinline__ int quad_orientation(const double* q, int st) {
+  int s = orient_sign(q[0], q[st], q[2 * st], q[3 * st], q[4 * st], q[5 * st]);
+  if (s == 0) s = orient_sign(q[2 * st], q[3 * st], q[4 * st], q[5 * st], q[6 * st], q[7 * st]);
   return s;
 }
 
-// true if all `npts` points are strictly outside edge k of the convex quad q (orientation o)
-SG_DEV bool edge_separates(const double* q, int o, int k, const double* pts, int npts) {
-  const double ax = q[2 * k], ay = q[2 * k + 1];
-  const double bx = q[2 * ((k + 1) & 3)], by = q[2 * ((k + 1) & 3) + 1];
-  for (int m = 0; m < npts; ++m)
-    if (orient_sign(ax, ay, bx, by, pts[2 * m], pts[2 * m + 1]) * o >= 0) return false;
+// closed-set intersection of two convex quads (touching counts, as GEOS `intersects`):
+// disjoint iff some edge of either has all four corners of the other strictly outside
+__device__ __noinline__ bool quads_intersect(const double* a, int sa, int oa, const double* b,
+                                             int sb, int ob) {
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const double* P = pass ? b : a;
+    const double* Q = pass ? a : b;
+    const int sp = pass ? sb : sa, sq = pass ? sa : sb, o = pass ? ob : oa;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      const int k1 = (k + 1) & 3;
+      const double ax = P[2 * k * sp], ay = P[(2 * k + 1) * sp];
+      const double bx = P[2 * k1 * sp], by = P[(2 * k1 + 1) * sp];
+      bool sep = true;
+#pragma unroll 1
+      for (int m = 0; m < 4 && sep; ++m)
+        sep = orient_sign(ax, ay, bx, by, Q[2 * m * sq], Q[(2 * m + 1) * sq]) * o < 0;
+      if (sep) return false;
+    }
+  }
   return true;
 }
 
-// closed-set intersection of two convex quads (touching counts, as GEOS `intersects`)
-SG_DEV bool quads_intersect(const double* a, int oa, const double* b, int ob) {
-  for (int k = 0; k < 4; ++k)
-    if (edge_separates(a, oa, k, b, 4)) return false;
-  for (int k = 0; k < 4; ++k)
-    if (edge_separates(b, ob, k, a, 4)) return false;
-  return true;
-}
-
-// closed-set intersection of a convex quad and a segment s = x0,y0,x1,y1
-SG_DEV bool quad_intersects_segment(const double* q, int o, const double* s) {
-  for (int k = 0; k < 4; ++k)
-    if (edge_separates(q, o, k, s, 2)) return false;
+// closed-set intersection of a convex quad and the segment (x0, y0)-(x1, y1)
+__device__ __noinline__ bool quad_intersects_segment(const double* q, int st, int o, double x0,
+                                                     double y0, double x1, double y1) {
   int pos = 0, neg = 0;
-  for (int m = 0; m < 4; ++m) {
-    const int sg = orient_sign(s[0], s[1], s[2], s[3], q[2 * m], q[2 * m + 1]);
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) {
+    const int k1 = (k + 1) & 3;
+    const double ax = q[2 * k * st], ay = q[(2 * k + 1) * st];
+    const double bx = q[2 * k1 * st], by = q[(2 * k1 + 1) * st];
+    if (orient_sign(ax, ay, bx, by, x0, y0) * o < 0 && orient_sign(ax, ay, bx, by, x1, y1) * o < 0)
+      return false;  // both end points strictly outside this edge
+    const int sg = orient_sign(x0, y0, x1, y1, ax, ay);
     pos += sg > 0;
     neg += sg < 0;
   }
-  return !(pos == 4 || neg == 4);
+  return !(pos == 4 || neg == 4);  // corners strictly on one side of the segment's line
 }
 
 // Entity.get_bounding_box_points (reference entity/base.py:100-138)
@@ -215,141 +232,10 @@ SG_DEV double np_clip(double v, double lo, double hi) { return fmin(fmax(v, lo),
 // ----------------------------------------------------------------------------------
 // RSS (reference metrics/rss/callback.py, rss_utils.py)
 // ----------------------------------------------------------------------------------
-struct RssEnt {
-  double position[2], heading[2], velocity[2], box[8], length, width;
-};
-
 SG_DEV void inverse_direction(const double v[2], double out[2]) {  // rss_utils.py:7-21
   const double n = norm2(v[1], v[0]);
   out[0] = v[1] / n;
   out[1] = -v[0] / n;
-}
-SG_DEV void coord_change(const double v[2], const double dir[2], const double c[2],
-                         double out[2]) {  // rss_utils.py:24-45
-  double inv[2];
-  inverse_direction(dir, inv);
-  const double d0 = v[0] - c[0], d1 = v[1] - c[1];
-  out[0] = dot2(d0, d1, inv[0], inv[1]);
-  out[1] = dot2(d0, d1, dir[0], dir[1]);
-}
-// callback.py:340-386; `pts` are the entity's world-frame corners
-SG_DEV void rss_entity_params(double x, double y, double h, double vx, double vy,
-                              const double* pts, double W, double L, const double eh[2],
-                              const double einv[2], const double epos[2], RssEnt& o) {
-  double s, c;
-  sincos(h, &s, &c);
-  const double dir[2] = {c, s};
-  const double xy[2] = {x, y};
-  coord_change(xy, eh, epos, o.position);
-  o.heading[0] = dot2(dir[0], dir[1], einv[0], einv[1]);
-  o.heading[1] = dot2(dir[0], dir[1], eh[0], eh[1]);
-  o.velocity[0] = dot2(vx, vy, einv[0], einv[1]);
-  o.velocity[1] = dot2(vx, vy, eh[0], eh[1]);
-  for (int i = 0; i < 4; ++i) coord_change(pts + 2 * i, eh, epos, o.box + 2 * i);
-  o.length = L;
-  o.width = W;
-}
-SG_DEV double long_dist_same_direction(double vf, double vr, double a, double RT, double MINA) {
-  const double v = vr * RT + py_min(vf * vf / (2 * a), 0.5 * a * (RT * RT)) +
-                   ((vr + RT * a) * (vr + RT * a)) / (2 * MINA) - vf * vf / (2 * a);
-  return py_max(0, v);  // callback.py:454-472
-}
-SG_DEV double long_dist_opp_direction(double v1, double v2, double a, double RT, double MINA) {
-  const double av2 = fabs(v2);
-  const double v = (2 * v1 + RT * a) * RT / 2 + ((v1 + RT * a) * (v1 + RT * a)) / (2 * MINA) +
-                   (2 * av2 + RT * a) * RT / 2 + ((av2 + RT * a) * (av2 + RT * a)) / (2 * MINA);
-  return py_max(0, v);  // callback.py:474-492
-}
-SG_DEV double lat_dist(double v, double amax, double amin, double RT) {  // callback.py:494-505
-  const double x = 0.5 * RT * (2 * v + RT * amax) +
-                   ((v + RT * amax) * (v + RT * amax)) / (2 * amin) - 0.5 * (RT * RT) * amax -
-                   ((RT * amax) * (RT * amax)) / (2 * amin);
-  return py_max(0, x);
-}
-SG_DEV double safe_longitudinal_distance(const SgParams& p, const RssEnt& ego, const RssEnt& haz) {
-  const double CLR = p.rss_min_safe_clearance, RT = p.rss_response_time;  // callback.py:230-269
-  const double dp = dot2(ego.heading[0], ego.heading[1], haz.heading[0], haz.heading[1]);
-  const double a = fabs(p.rss_max_long_accel * dp);
-  double d0;
-  if (dp > 0) {
-    double vf, vr;
-    if (ego.position[1] > haz.position[1]) {
-      vf = norm2(ego.velocity[0], ego.velocity[1]);
-      vr = dot2(haz.velocity[0], haz.velocity[1], ego.heading[0], ego.heading[1]);
-    } else {
-      vf = dot2(haz.velocity[0], haz.velocity[1], ego.heading[0], ego.heading[1]);
-      vr = norm2(ego.velocity[0], ego.velocity[1]);
-    }
-    if (vr == 0.0) return CLR + 0.5 * ego.length;
-    d0 = long_dist_same_direction(vf, vr, a, RT, p.rss_min_long_accel);
-  } else {
-    const double v1 = fabs(dot2(ego.velocity[0], ego.velocity[1], ego.heading[0], ego.heading[1]));
-    const double v2 = -fabs(dot2(haz.velocity[0], haz.velocity[1], ego.heading[0], ego.heading[1]));
-    if (np_sign(haz.position[1]) == np_sign(haz.velocity[1])) return CLR + 0.5 * ego.length;
-    d0 = long_dist_opp_direction(v1, v2, a, RT, p.rss_min_long_accel);
-  }
-  return d0 + CLR + 0.5 * ego.length;
-}
-SG_DEV double safe_lateral_distance(const SgParams& p, const RssEnt& ego, const RssEnt& haz) {
-  const double CLR = p.rss_min_safe_clearance, RT = p.rss_response_time;  // callback.py:271-302
-  double v = haz.velocity[0];
-  double inv[2];
-  inverse_direction(ego.heading, inv);
-  const double k = fabs(dot2(inv[0], inv[1], haz.heading[0], haz.heading[1]));
-  const double amax = p.rss_max_long_accel * k, amin = p.rss_min_long_accel * k;
-  double d0;
-  if (np_sign(-haz.position[0]) == np_sign(v)) {
-    v = fabs(v);
-    if (v == 0.0) return CLR + 0.5 * ego.width;
-    d0 = lat_dist(v, amax, amin, RT);
-  } else {
-    d0 = 0;
-  }
-  return d0 + CLR + 0.5 * ego.width;
-}
-SG_DEV void safe_ratios(const RssEnt& ego, const RssEnt& haz, double out[2]) {  // callback.py:124-166
-  const double safe_lat = 0.5 * ego.width, safe_long = 0.5 * ego.length;
-  double inv[2];
-  inverse_direction(haz.heading, inv);
-  const double wl_inv = fabs(dot2(haz.width, haz.length, inv[0], inv[1]));
-  const double wl_dir = fabs(dot2(haz.width, haz.length, haz.heading[0], haz.heading[1]));
-  const double actual_lat = py_max(1e-6, fabs(haz.position[0]) - 0.5 * ego.width - 0.5 * wl_inv);
-  const double actual_long = py_max(1e-6, fabs(haz.position[1]) - 0.5 * ego.length - 0.5 * wl_dir);
-  out[0] = fabs(actual_lat / safe_lat);
-  out[1] = fabs(actual_long / safe_long);
-}
-// callback.py:168-228 (+ :304-338 write_intersections, :388-452 generate_buffer)
-__device__ __noinline__ int unsafe_distance(const RssEnt& ego, const RssEnt& haz, uint8_t& st,
-                                            const double sd[2]) {
-  if ((st >> 2) & 3) return SG_RSS_FOUND;
-  const double slat = sd[0], slong = sd[1];
-  const double buffer[8] = {slat, slong, -slat, slong, -slat, -slong, slat, -slong};
-  const int oh = quad_orientation(haz.box), ob = quad_orientation(buffer);
-  if (quads_intersect(haz.box, oh, buffer, ob)) {
-    const int marker = st & 3;
-    if (marker == 1) { st |= 2 << 2; return SG_RSS_UNSAFE_LONGITUDINAL; }
-    if (marker == 2) { st |= 1 << 2; return SG_RSS_UNSAFE_LATERAL; }
-    const double ed[2] = {ego.width, ego.length};
-    double inv[2];
-    inverse_direction(ed, inv);
-    const double lhs =
-        fabs(fabs(haz.position[0]) - fabs(dot2(haz.position[0], haz.position[1], ed[0], ed[1]))) / slat;
-    const double rhs =
-        fabs(fabs(haz.position[1] - dot2(haz.position[0], haz.position[1], inv[0], inv[1])) / slong);
-    if (lhs > rhs) { st |= 2 << 2; return SG_RSS_UNSAFE_LONGITUDINAL; }
-    st |= 1 << 2;
-    return SG_RSS_UNSAFE_LATERAL;
-  }
-  const double len0[4] = {slat, 100 * slong, -slat, 100 * -slong};
-  const double len1[4] = {-slat, 100 * slong, slat, 100 * -slong};
-  const double wid0[4] = {100 * slat, slong, 100 * -slat, slong};
-  const double wid1[4] = {100 * -slat, -slong, 100 * slat, -slong};
-  const bool lat = quad_intersects_segment(haz.box, oh, len0) || quad_intersects_segment(haz.box, oh, len1);
-  const bool lon = quad_intersects_segment(haz.box, oh, wid0) || quad_intersects_segment(haz.box, oh, wid1);
-  if (lat && lon) return SG_RSS_BOTH;
-  if (lat) { st = (uint8_t)((st & ~3) | 1); return SG_RSS_LATERAL; }
-  if (lon) { st = (uint8_t)((st & ~3) | 2); return SG_RSS_LONGITUDINAL; }
-  return SG_RSS_SAFE;
 }
 
 // ----------------------------------------------------------------------------------

@@ -48,7 +48,7 @@ struct GroupLayout {
   int W;        // 32-bit words per collision row
   int H;        // half-sweep length M/2
   int QCAP;     // candidate-pair queue capacity
-  int off_act, off_hcs, off_ped, off_box, off_ego, off_cold, off_aabb, off_queue, off_hits, off_bits,
+  int off_act, off_rbox, off_hcs, off_ped, off_box, off_ego, off_cold, off_aabb, off_queue, off_hits, off_bits,
       off_acc, off_flags, off_orient;
   int bytes;
 };
@@ -69,6 +69,7 @@ static GroupLayout make_layout(int M, bool ped, bool rss) {
   L.QCAP = 4 * G;
   int o = 8 * G * (int)sizeof(double);                            // corners[8][G]
   L.off_act = o;    o += 4 * G * (int)sizeof(double);             // VehicleAction rows, 2 stages x (accel, steer)
+  L.off_rbox = o;   o += rss ? 8 * G * (int)sizeof(double) : 0;   // hazard corners in the ego frame
   L.off_hcs = o;    o += rss ? 2 * G * (int)sizeof(double) : 0;   // cos/sin of each heading
   L.off_ped = o;    o += ped ? 4 * G * (int)sizeof(double) : 0;   // old x,y,vx,vy (pedestrian sensors)
   L.off_box = o;    o += 4 * G * (int)sizeof(double);             // width, length, center_x, center_y
@@ -91,6 +92,7 @@ struct Grp {
   int64_t i, nm;
   double* corners;
   double* actbuf;
+  double* rbox;
   double* hcs;
   double* pedbuf;
   double* boxp;
@@ -130,6 +132,7 @@ SG_DEV void setup_group(Grp& g, const SgScene& sc, const GroupLayout& L, unsigne
   g.i = (int64_t)n * sc.n_slots + s;
   g.corners = (double*)base;
   g.actbuf = (double*)(base + L.off_act);
+  g.rbox = (double*)(base + L.off_rbox);
   g.hcs = (double*)(base + L.off_hcs);
   g.pedbuf = (double*)(base + L.off_ped);
   g.boxp = (double*)(base + L.off_box);
@@ -364,7 +367,7 @@ SG_DEV void publish_box(const Grp& c, bool present, double x, double y, double c
 #pragma unroll
     for (int f = 0; f < 8; ++f) c.corners[f * c.G + c.s] = my[f];
     if (RSS) { c.hcs[c.s] = cs; c.hcs[c.G + c.s] = sn; }
-    c.orient[c.s] = (int8_t)(orient_hint ? orient_hint : quad_orientation(my));
+    c.orient[c.s] = (int8_t)(orient_hint ? orient_hint : quad_orientation(c.corners + c.s, c.G));
     bb = make_aabb_box(x, y, cs, sn, bw, bl, bcx, bcy, ox, oy);
   }
   c.aabb[c.s] = bb;
@@ -410,18 +413,15 @@ SG_DEV void publish_ego(const Grp& c, bool present, double x, double y, double e
 // ---------------------------------------------------------------------------------
 // RSS (reference metrics/rss/callback.py)
 // ---------------------------------------------------------------------------------
-__device__ __noinline__ bool rss_box_hits_segment(const double* box, double x0, double y0,
-                                                  double x1, double y1) {
-  const double seg[4] = {x0, y0, x1, y1};
-  return quad_intersects_segment(box, quad_orientation(box), seg);
-}
+// The hazard's ego-frame corners are staged at q[k*st] in shared memory for these.
 
 // Does the infinite line through (ax, ay), (bx, by) meet the closed convex quad?  (Exact.)
-SG_DEV bool line_hits_quad(const double* q, double ax, double ay, double bx, double by) {
+__device__ __noinline__ bool line_hits_quad(const double* q, int st, double ax, double ay,
+                                            double bx, double by) {
   int pos = 0, neg = 0;
-#pragma unroll
+#pragma unroll 1
   for (int m = 0; m < 4; ++m) {
-    const int sg = orient_sign(ax, ay, bx, by, q[2 * m], q[2 * m + 1]);
+    const int sg = orient_sign(ax, ay, bx, by, q[2 * m * st], q[(2 * m + 1) * st]);
     pos += sg > 0;
     neg += sg < 0;
   }
@@ -431,12 +431,13 @@ SG_DEV bool line_hits_quad(const double* q, double ax, double ay, double bx, dou
 // Closed intersection of a convex quad with the rectangle [-a, a] x [-b, b] whose bounding
 // ranges already overlap: separating axes are the quad's edges; per edge only the rectangle
 // corner that is extreme towards the quad's inside has to be tested.  (Exact.)
-SG_DEV bool quad_hits_centered_rect(const double* q, double a, double b) {
-  const int o = quad_orientation(q);
-#pragma unroll
+__device__ __noinline__ bool quad_hits_centered_rect(const double* q, int st, double a, double b) {
+  const int o = quad_orientation(q, st);
+#pragma unroll 1
   for (int k = 0; k < 4; ++k) {
-    const double ax = q[2 * k], ay = q[2 * k + 1];
-    const double bx = q[2 * ((k + 1) & 3)], by = q[2 * ((k + 1) & 3) + 1];
+    const int k1 = (k + 1) & 3;
+    const double ax = q[2 * k * st], ay = q[(2 * k + 1) * st];
+    const double bx = q[2 * k1 * st], by = q[(2 * k1 + 1) * st];
     // orient(a, b, p) = dx*(py-ay) - dy*(px-ax): o*orient is largest for
     // py = b*sign(o*dx), px = -a*sign(o*dy)
     const double dx = bx - ax, dy = by - ay;
@@ -450,17 +451,23 @@ SG_DEV bool quad_hits_centered_rect(const double* q, double a, double b) {
 // Closed intersection of a convex quad with the horizontal segment y = c, |x| <= w, when the
 // quad's y-range already contains c: the quad's corners are then not strictly on one side of
 // the segment's line, so the segment misses the quad iff some quad edge has both segment
-// endpoints strictly outside.  (Exact: 8 orientation signs.)
-SG_DEV bool quad_hits_hsegment(const double* q, double w, double c) {
-  const int o = quad_orientation(q);
-#pragma unroll
+// endpoints strictly outside.  (Exact.)
+__device__ __noinline__ bool quad_hits_hsegment(const double* q, int st, double w, double c) {
+  const int o = quad_orientation(q, st);
+#pragma unroll 1
   for (int k = 0; k < 4; ++k) {
-    const double ax = q[2 * k], ay = q[2 * k + 1];
-    const double bx = q[2 * ((k + 1) & 3)], by = q[2 * ((k + 1) & 3) + 1];
+    const int k1 = (k + 1) & 3;
+    const double ax = q[2 * k * st], ay = q[(2 * k + 1) * st];
+    const double bx = q[2 * k1 * st], by = q[(2 * k1 + 1) * st];
     if (orient_sign(ax, ay, bx, by, -w, c) * o < 0 && orient_sign(ax, ay, bx, by, w, c) * o < 0)
       return false;
   }
   return true;
+}
+
+__device__ __noinline__ bool rss_box_hits_segment(const double* q, int st, double x0, double y0,
+                                                  double x1, double y1) {
+  return quad_intersects_segment(q, st, quad_orientation(q, st), x0, y0, x1, y1);
 }
 
 struct RssConst {  // uniform per launch
@@ -555,6 +562,10 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
     box[2 * q] = dot2(c0, c1, ei0, ei1);
     box[2 * q + 1] = dot2(c0, c1, eh0, eh1);
   }
+  double* rb = c.rbox + c.s;  // the same corners, staged for the out-of-line exact predicates
+  const int st = c.G;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) rb[q * st] = box[q];
   const double bxmin = min2(min2(box[0], box[2]), min2(box[4], box[6]));
   const double bxmax = max2(max2(box[0], box[2]), max2(box[4], box[6]));
   const double bymin = min2(min2(box[1], box[3]), min2(box[5], box[7]));
@@ -565,7 +576,7 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       corner_in = corner_in || (fabs(box[2 * q]) <= slat && fabs(box[2 * q + 1]) <= slong);
-    inter = corner_in || quad_hits_centered_rect(box, slat, slong);
+    inter = corner_in || quad_hits_centered_rect(rb, st, slat, slong);
   }
   if (inter) {
     const int marker = state & 3;
@@ -587,18 +598,18 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
   bool lat = false, lon = false;
   if (!(bxmin > slat || bxmax < -slat || bymin > L100 || bymax < -L100)) {
     if (bymax < L100 && bymin > -L100)  // segment spans the box's y-range: segment <=> line
-      lat = line_hits_quad(box, slat, L100, -slat, 100 * -slong) ||
-            line_hits_quad(box, -slat, L100, slat, 100 * -slong);
+      lat = line_hits_quad(rb, st, slat, L100, -slat, 100 * -slong) ||
+            line_hits_quad(rb, st, -slat, L100, slat, 100 * -slong);
     else
-      lat = rss_box_hits_segment(box, slat, L100, -slat, 100 * -slong) ||
-            rss_box_hits_segment(box, -slat, L100, slat, 100 * -slong);
+      lat = rss_box_hits_segment(rb, st, slat, L100, -slat, 100 * -slong) ||
+            rss_box_hits_segment(rb, st, -slat, L100, slat, 100 * -slong);
   }
   if (!(bxmin > W100 || bxmax < -W100)) {
     if (bxmin > -W100 && bxmax < W100) {  // box inside the segments' x-range: segment <=> line y = c
       lon = (bymin <= slong && slong <= bymax) || (bymin <= -slong && -slong <= bymax);
     } else {
-      if (!(bymin > slong || bymax < slong)) lon = quad_hits_hsegment(box, W100, slong);
-      if (!lon && !(bymin > -slong || bymax < -slong)) lon = quad_hits_hsegment(box, W100, -slong);
+      if (!(bymin > slong || bymax < slong)) lon = quad_hits_hsegment(rb, st, W100, slong);
+      if (!lon && !(bymin > -slong || bymax < -slong)) lon = quad_hits_hsegment(rb, st, W100, -slong);
     }
   }
   if (lat && lon) return SG_RSS_BOTH;
@@ -613,16 +624,11 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
 // exact narrow phase for one AABB-surviving pair, both quads read from the staged corners
 __device__ __noinline__ bool pair_collides(const double* corners, const int8_t* orient, int G,
                                            int a, int b) {
-  double qa[8], qb[8];
   bool same = true;
-#pragma unroll
-  for (int f = 0; f < 8; ++f) {
-    qa[f] = corners[f * G + a];
-    qb[f] = corners[f * G + b];
-    same = same && (qa[f] == qb[f]);
-  }
+#pragma unroll 1
+  for (int f = 0; f < 8; ++f) same = same && (corners[f * G + a] == corners[f * G + b]);
   if (same) return false;  // `g != g_prime`, reference utils.py:58
-  return quads_intersect(qa, orient[a], qb, orient[b]);
+  return quads_intersect(corners + a, G, orient[a], corners + b, G, orient[b]);
 }
 
 __device__ __noinline__ void record_pair(int features, uint32_t* coll_mask, const Grp& c, int a,
@@ -1360,7 +1366,7 @@ __global__ void sg_box_pairs_kernel(const double* pa, const double* ba, const do
   box_points(pb[3 * i], pb[3 * i + 1], pb[3 * i + 2], bb[4 * i], bb[4 * i + 1], bb[4 * i + 2], bb[4 * i + 3], qb);
   bool same = true;
   for (int f = 0; f < 8; ++f) same = same && (qa[f] == qb[f]);
-  out[i] = !same && quads_intersect(qa, quad_orientation(qa), qb, quad_orientation(qb));
+  out[i] = !same && quads_intersect(qa, 1, quad_orientation(qa, 1), qb, 1, quad_orientation(qb, 1));
 }
 
 // ---------------------------------------------------------------------------------
