@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 4
+#define SG_ABI_VERSION 5
 
 /* entity slot kinds (who produces the slot's next pose each tick) */
 enum SgKind {
@@ -205,7 +205,9 @@ typedef struct SgInputs {
      by the k-th tick executed in this call (k = 0 .. n_action_ticks-1) */
   const double* actions;
   int32_t n_action_ticks;
-  int32_t _pad;
+  /* non-zero: tick scenarios whose is_done flag is already set too -- ScenarioGym.step() has no
+     is_done guard (scenario_gym.py:227-254); rollout() loops `while not is_done` (:262) */
+  int32_t step_done;
   /* SG_KIND_HOST slots: pose returned by the host agent for the next tick */
   const double* host_pose;      /* [6][N*M] or NULL */
   const uint8_t* host_present;  /* [N*M] 0 = agent returned None */

@@ -115,8 +115,10 @@ class OracleEngine:
             raise RuntimeError(self.lib["last_error"]().decode())
 
     def rollout(self, n_ticks: int = -1, actions: Optional[np.ndarray] = None,
-                host_pose: Optional[np.ndarray] = None, host_present: Optional[np.ndarray] = None):
+                host_pose: Optional[np.ndarray] = None, host_present: Optional[np.ndarray] = None,
+                step_done: bool = False):
         inp = abi.SgInputs()
+        inp.step_done = int(step_done)
         if actions is not None:
             actions = np.ascontiguousarray(actions, np.float64)
             assert actions.shape[1:] == (2, self.scene.N * self.scene.M), actions.shape

@@ -877,7 +877,7 @@ int sgo_rollout(const SgScene* sc, const SgParams* p, SgState* st, const SgInput
   if (in && in->actions && limit > in->n_action_ticks) limit = in->n_action_ticks;
   for (int n = 0; n < sc->n_scenarios; ++n) {
     for (int k = 0; k < limit; ++k) {
-      if (st->done[n]) break;
+      if (st->done[n] && !(in && in->step_done)) break;
       tick_scenario(sc, p, st, in, n, k, newpose, newpres, newspeed);
     }
   }

@@ -11,7 +11,7 @@ import math
 import os
 from typing import Dict, Optional
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # SgKind
 KIND_EMPTY, KIND_REPLAY, KIND_AGENT_REPLAY, KIND_VEHICLE, KIND_PEDESTRIAN, KIND_HOST = range(6)
@@ -150,7 +150,7 @@ class SgInputs(C.Structure):
     _fields_ = [
         ("actions", _p),
         ("n_action_ticks", C.c_int32),
-        ("_pad", C.c_int32),
+        ("step_done", C.c_int32),
         ("host_pose", _p),
         ("host_present", _p),
     ]

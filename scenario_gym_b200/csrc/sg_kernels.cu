@@ -896,10 +896,10 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   // VehicleAction rows are staged one tick ahead with cp.async (no registers held)
   const double* act = in.actions + i;
   double* ab = c.actbuf + s;
-  if (live && limit > 0 && !done) { cp_async8(ab, act); cp_async8(ab + G, act + nm); }
+  if (live && limit > 0 && (!done || in.step_done)) { cp_async8(ab, act); cp_async8(ab + G, act + nm); }
   cp_async_commit();
 
-  for (int k = 0; k < limit && !done; ++k) {
+  for (int k = 0; k < limit && (!done || in.step_done); ++k) {
     const double next_t = t + p.timestep;  // scenario_gym.py:229
     const double dt = next_t - t;          // controller.py:123 and State.dt after the step
     cp_async_wait_all();
@@ -1086,7 +1086,7 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   if (in.actions && limit > in.n_action_ticks) limit = in.n_action_ticks;
   int parity = 0;
 
-  for (int k = 0; k < limit && !done; ++k) {
+  for (int k = 0; k < limit && (!done || in.step_done); ++k) {
     // ---------------- phase A: agents / batch replay produce the new poses ----------------
     const double next_t = t + p.timestep;  // scenario_gym.py:229
     double np_[6];

@@ -115,13 +115,14 @@ class Engine:
         return actions
 
     def rollout(self, n_ticks: int = -1, actions=None, tick0: int = 0, host_pose=None,
-                host_present=None) -> None:
+                host_present=None, step_done: bool = False) -> None:
         """
         ``n_ticks`` x ScenarioGym.step() fused on the device; ``n_ticks < 0`` runs every
         scenario to ``is_done`` (ScenarioGym.rollout).  ``actions`` (T, 2, N*M) is consumed
         from row ``tick0``.
         """
         inp = abi.SgInputs()
+        inp.step_done = int(step_done)
         keep = []
         if actions is not None:
             a = self.set_actions(actions) if not (

@@ -1,0 +1,457 @@
+"""
+``ScenarioGym`` -- the reference's engine class (reference scenario_gym/scenario_gym.py:13-319)
+on top of the B200 rollout engine.  Same constructor arguments and methods
+(``load_scenario``, ``set_scenario``, ``reset_scenario``, ``step``, ``rollout``, ``get_metrics``,
+``add_metrics``, ``run_scenarios``); in addition ``load_scenarios`` / ``set_scenarios`` take a
+list and roll all of them out as one batch on the device.
+
+Lowering: what ``create_agent`` returns decides each entity's device slot kind
+  None                          -> batch replay            (entity/batch.py)
+  ReplayTrajectoryAgent         -> clamped replay agent    (agent.py:118-128)
+  ActionTableAgent              -> VehicleController, whole action table on device
+  Agent + VehicleController     -> VehicleController on device, policy ``_step`` on the host per tick
+  PedestrianAgent + SocialForce -> social force on device
+  any other Agent               -> pose from ``agent.step(state)`` on the host per tick
+Built-in metrics / ``RSSDistances`` are accumulated on the device; custom ``Metric`` /
+``StateCallback`` subclasses and callable terminal conditions run on the host after every tick
+on a materialised ``State``.  A rollout without host-side plugins is a single fused launch.
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+from typing import Any, Callable, Dict, List, Optional, Union
+
+import numpy as np
+
+from . import abi
+from .entity import Entity
+from .packing import ScenarioSpec, SlotSpec, pack_scenarios
+from .plugins import (ActionTableAgent, Agent, CollisionMetric, EgoLocalizationSensor, Metric,
+                      PedestrianAgent, ReplayTrajectoryAgent, ReplayTrajectoryController, RSSDistances,
+                      SocialForce, StateCallback, VehicleAction, VehicleController, _create_agent,
+                      _DeviceMetric)
+from .scenario import Scenario
+from .state import State
+from .xosc import import_scenario
+
+_TERMINAL_BITS = {"max_length": abi.TERM_MAX_LENGTH, "collision": abi.TERM_COLLISION,
+                  "ego_collision": abi.TERM_EGO_COLLISION}
+
+
+class ScenarioGym:
+    """Loads and runs scenarios."""
+
+    @classmethod
+    def run_scenarios(cls, paths: List[str], render: bool = False, **kwargs) -> None:
+        gym = cls(**kwargs)
+        for path in paths:
+            gym.load_scenario(path)
+            gym.rollout(render=render)
+
+    def __init__(self, timestep: float = 1.0 / 30.0, persist: bool = False, viewer_class=None,
+                 terminal_conditions: Optional[List[Union[str, Callable]]] = None,
+                 state_callbacks: Optional[List[StateCallback]] = None,
+                 metrics: Optional[List[Metric]] = None, device: int = 0, **viewer_parameters):
+        self.timestep = timestep
+        self.persist = persist
+        self.device = device
+        self.viewer_parameters = viewer_parameters.copy()
+        self.terminal_conditions = ["max_length"] if terminal_conditions is None else terminal_conditions
+        self.state_callbacks = [] if state_callbacks is None else state_callbacks
+        self.viewer = None
+        self.states: List[State] = []
+        self.metrics: List[Metric] = []
+        self._engine = None
+        if metrics is not None:
+            self.add_metrics(metrics)
+
+    # ------------------------------------------------------------------ reference API
+    @property
+    def state(self) -> Optional[State]:
+        return self.states[0] if self.states else None
+
+    def reset_gym(self) -> None:
+        self.states = []
+        self.metrics = []
+        self._engine = None
+
+    def add_metrics(self, metrics: List[Metric]) -> None:
+        self.metrics.extend(metrics)
+
+    def load_scenario(self, scenario_path: str, create_agent=_create_agent, relabel: bool = False,
+                      **kwargs) -> None:
+        scenario = import_scenario(scenario_path, relabel=relabel, **kwargs)
+        self.set_scenario(scenario, scenario_path=scenario_path, create_agent=create_agent)
+
+    def load_scenarios(self, scenario_paths: List[str], create_agent=_create_agent,
+                       relabel: bool = False) -> None:
+        self.set_scenarios([import_scenario(p, relabel=relabel) for p in scenario_paths],
+                           scenario_paths=scenario_paths, create_agent=create_agent)
+
+    def set_scenario(self, scenario: Scenario, scenario_path: Optional[str] = None,
+                     create_agent=_create_agent) -> None:
+        self.set_scenarios([scenario], scenario_paths=[scenario_path], create_agent=create_agent)
+
+    def set_scenarios(self, scenarios: List[Scenario], scenario_paths=None,
+                      create_agent=_create_agent) -> None:
+        paths = scenario_paths or [None] * len(scenarios)
+        self.states = [State(self, n, sc, scenario_path=p) for n, (sc, p) in enumerate(zip(scenarios, paths))]
+        self.create_agents(create_agent=create_agent)
+        self._build()
+        self.reset_scenario(force=True)
+
+    def create_agents(self, create_agent=_create_agent) -> None:
+        """Call ``create_agent(scenario, entity)`` once per entity (reference :188-211)."""
+        for st in self.states:
+            st.agents = {}
+            for entity in st.scenario.entities:
+                agent = create_agent(st.scenario, entity)
+                if agent is not None:
+                    st.agents[entity] = agent
+
+    def get_start_time(self, scenario: Scenario) -> float:
+        return max((0.0, scenario.ego.trajectory.min_t))
+
+    def reset_scenario(self, force: bool = False) -> None:
+        """Reset the state to the beginning of the scenario(s) (reference :217-225)."""
+        if not self.states:
+            return
+        if not force and self._ticks_since_reset == 0:
+            return
+        self._sync_params()
+        self._engine.reset()
+        self._ticks_since_reset = 0
+        self._host_done = [False] * len(self.states)
+        self._last_tick = np.zeros(len(self.states), np.int32)
+        for n, st in enumerate(self.states):
+            st._invalidate()
+            st._recorded = {e: [] for e in st.scenario.entities}
+            st.next_t = None
+        if self._host_mode:
+            for n, st in enumerate(self.states):
+                st._record()
+                for cb in self._host_callbacks[n]:
+                    cb.reset(st)
+                for agent in st.agents.values():
+                    if self._agent_kind[agent] in ("host", "host_policy"):
+                        agent.reset(st)
+                for m in self._host_metrics[n]:
+                    m.reset(st)
+        for m in self.metrics:
+            if isinstance(m, _DeviceMetric):
+                m._value = None
+
+    def step(self) -> None:
+        """One tick for every scenario that is not done (reference :227-254)."""
+        self._sync_params()
+        eng = self._engine
+        N, M = eng.N, eng.M
+        actions = None
+        host_pose = host_present = None
+        if self._host_mode:
+            if self._any_host_policy:
+                actions = np.zeros((1, 2, N * M))
+            if self._any_host_agent:
+                host_pose = np.zeros((6, N * M))
+                host_present = np.zeros(N * M, np.uint8)
+            for n, st in enumerate(self.states):
+                if st.is_done and not (len(self.states) == 1):
+                    continue
+                st.next_t = st.t + self.timestep
+                for entity, agent in st.agents.items():
+                    kind = self._agent_kind[agent]
+                    i = n * M + self._slot_of[n][entity]
+                    if entity not in st.poses:
+                        continue
+                    if kind == "host_policy":
+                        act = agent._step(agent.sensor.step(st))
+                        agent.last_action = act
+                        a = (act.acceleration, act.steering) if isinstance(act, VehicleAction) else act
+                        actions[0, 0, i], actions[0, 1, i] = a
+                    elif kind == "host":
+                        pose = agent.step(st)
+                        if pose is not None:
+                            host_pose[:, i] = pose
+                            host_present[i] = 1
+        force = len(self.states) == 1  # the reference's step() has no is_done guard
+        if self._action_table is not None:
+            if actions is not None:  # merge the host policies' row into the resident table's row
+                row = self._action_table_host[self._ticks_since_reset].copy()
+                mask = self._host_policy_mask
+                row[:, mask] = actions[0][:, mask]
+                eng.rollout(1, actions=row[None], host_pose=host_pose, host_present=host_present, step_done=force)
+            else:
+                eng.rollout(1, actions=self._action_table, tick0=self._ticks_since_reset,
+                            host_pose=host_pose, host_present=host_present, step_done=force)
+        else:
+            eng.rollout(1, actions=actions, host_pose=host_pose, host_present=host_present, step_done=force)
+        self._ticks_since_reset += 1
+        for st in self.states:
+            st._invalidate()
+        if self._host_mode:
+            self._after_tick_host()
+
+    def rollout(self, render: bool = False, video_path: Optional[str] = None) -> None:
+        """Roll every scenario out to ``is_done`` (reference :256-267)."""
+        if render:
+            raise ValueError("rendering is out of scope of the device engine (no viewer)")
+        self.reset_scenario()
+        if self._host_mode:
+            while not all(st.is_done for st in self.states):
+                self.step()
+        else:
+            self._sync_params()
+            self._engine.rollout(-1, actions=self._action_table, tick0=self._ticks_since_reset)
+            self._ticks_since_reset = -1  # unknown per scenario; forces the next reset
+            for st in self.states:
+                st._invalidate()
+        for st in self.states:
+            for agent in st.agents.values():
+                agent.finish(st)
+
+    def get_metrics(self):
+        """Metric states; a dict for one scenario, a list of dicts for a batch (reference :308-319)."""
+        out = []
+        self._cache = {}
+        for n in range(len(self.states)):
+            values = {}
+            for metric in self._metrics_for(n):
+                if isinstance(metric, _DeviceMetric):
+                    metric._pull(self, n)
+                value = metric.get_state()
+                if isinstance(value, dict):
+                    for k, v in value.items():
+                        if isinstance(k, str):
+                            values[f"{metric.name}_{k}"] = v
+                elif value is not None:
+                    values[metric.name] = value
+            out.append(values)
+        return out[0] if len(out) == 1 else out
+
+    def close(self) -> None:
+        pass
+
+    # ------------------------------------------------------------------ lowering
+    def _metrics_for(self, n: int) -> List[Metric]:
+        host = {id(m0): m for m0, m in zip(self._host_metric_protos, self._host_metrics[n])} \
+            if self._host_metrics[n] else {}
+        return [host.get(id(m), m) for m in self.metrics]
+
+    def _build(self) -> None:
+        from .engine import Engine
+
+        specs, self._slot_of, self._entity_of = [], [], []
+        self._agent_kind: Dict[Agent, str] = {}
+        veh_params, ped_params = set(), set()
+        tables = {}
+        for n, st in enumerate(self.states):
+            sc = st.scenario
+            ents = [e for e in sc.entities if e in st.agents] + [e for e in sc.entities if e not in st.agents]
+            slots = []
+            for s, e in enumerate(ents):
+                agent = st.agents.get(e)
+                kw = dict(traj=np.asarray(e.trajectory.data), etype=e.etype(), ref=e.ref or "",
+                          box=(e.bounding_box.width, e.bounding_box.length, e.bounding_box.center_x,
+                               e.bounding_box.center_y))
+                if agent is None:
+                    kind = abi.KIND_REPLAY
+                elif type(agent) is ReplayTrajectoryAgent and type(agent.controller) is ReplayTrajectoryController \
+                        and agent._trajectory is None:
+                    kind, self._agent_kind[agent] = abi.KIND_AGENT_REPLAY, "device"
+                elif isinstance(agent, PedestrianAgent) and type(agent.behaviour) is SocialForce:
+                    kind, self._agent_kind[agent] = abi.KIND_PEDESTRIAN, "device"
+                    kw.update(speed_desired=agent.speed_desired, route=np.array(agent.route))
+                    pr = agent.behaviour.params
+                    ped_params.add((agent.max_speed, agent.head_rot_angle, agent.distance_threshold,
+                                    pr.max_speed_factor, pr.bias_lon, pr.bias_lat, pr.sight_weight,
+                                    bool(pr.sight_weight_use), pr.sight_angle, pr.relaxation_time,
+                                    pr.ped_repulse_V, pr.ped_repulse_sigma, pr.ped_attract_C))
+                elif type(agent.controller) is VehicleController:
+                    kind = abi.KIND_VEHICLE
+                    c = agent.controller
+                    veh_params.add((c.max_steer, c.max_accel, c.max_speed, bool(c.allow_reverse)))
+                    if type(agent) is ActionTableAgent:
+                        self._agent_kind[agent] = "device"
+                        tables[(n, s)] = agent.table
+                    else:
+                        self._agent_kind[agent] = "host_policy"
+                else:
+                    kind, self._agent_kind[agent] = abi.KIND_HOST, "host"
+                slots.append(SlotSpec(kind=kind, **kw))
+            specs.append(ScenarioSpec(slots=slots, ego_slot=ents.index(sc.ego),
+                                      first_slot=ents.index(sc.entities[0]),
+                                      t0=self.get_start_time(sc), length=sc.length, name=sc.name or ""))
+            self._slot_of.append({e: s for s, e in enumerate(ents)})
+            self._entity_of.append(ents)
+        if len(veh_params) > 1 or len(ped_params) > 1:
+            raise NotImplementedError("controller / behaviour parameters must be equal across agents")
+        self._veh_params = next(iter(veh_params)) if veh_params else None
+        self._ped_params = next(iter(ped_params)) if ped_params else None
+        scene = pack_scenarios(specs)
+        N, M = scene.N, scene.M
+
+        # host-side plugins
+        self._host_metric_protos = [m for m in self.metrics if not isinstance(m, _DeviceMetric)]
+        self._host_metrics = [[deepcopy(m) for m in self._host_metric_protos] if N > 1 else
+                              list(self._host_metric_protos) for _ in range(N)]
+        host_cbs = [cb for cb in self.state_callbacks if not getattr(cb, "_device", False)]
+        self._host_callbacks = [[deepcopy(cb) for cb in host_cbs] if N > 1 else list(host_cbs)
+                                for _ in range(N)]
+        self._host_terminal = [c for c in self.terminal_conditions if callable(c)]
+        kinds = set(self._agent_kind.values())
+        self._any_host_policy = "host_policy" in kinds
+        self._any_host_agent = "host" in kinds
+        self._host_mode = bool(self._host_metric_protos or host_cbs or self._host_terminal
+                               or self._any_host_policy or self._any_host_agent)
+
+        # parameters
+        p = abi.default_params()
+        p.terminal = 0
+        for c in self.terminal_conditions:
+            if callable(c):
+                continue
+            if c not in _TERMINAL_BITS:
+                raise NotImplementedError(f"terminal condition {c!r} is out of scope of the device engine")
+            p.terminal |= _TERMINAL_BITS[c]
+        p.features = 0
+        if any(isinstance(m, CollisionMetric) for m in self.metrics) or self._host_mode:
+            p.features |= abi.FEAT_COLLISIONS
+        if any(isinstance(m, _DeviceMetric) and not isinstance(m, CollisionMetric) for m in self.metrics) \
+                or self._host_mode:
+            p.features |= abi.FEAT_EGO_METRICS
+        self._rss_cb = next((cb for cb in self.state_callbacks if isinstance(cb, RSSDistances)), None)
+        if self._rss_cb is not None:
+            p.features |= abi.FEAT_RSS
+        if self._host_mode:
+            p.features |= abi.FEAT_COLL_MATRIX
+        for m in self.metrics:  # required callbacks must be present (reference metrics/base.py:44-53)
+            for CB in m.required_callbacks:
+                if not any(isinstance(cb, CB) for cb in self.state_callbacks):
+                    raise ValueError("Cannot run metric {} without callback {}.".format(
+                        m.__class__.__name__, CB.__name__))
+        if self._veh_params:
+            p.veh_max_steer, p.veh_max_accel = self._veh_params[0], self._veh_params[1]
+            p.veh_max_speed = float("nan") if self._veh_params[2] is None else self._veh_params[2]
+            p.veh_allow_reverse = int(self._veh_params[3])
+        if self._ped_params:
+            (p.ped_max_speed, p.ped_head_rot_angle, p.ped_distance_threshold, p.sf_max_speed_factor,
+             p.sf_bias_lon, p.sf_bias_lat, p.sf_sight_weight, suse, p.sf_sight_angle,
+             p.sf_relaxation_time, p.sf_ped_repulse_V, p.sf_ped_repulse_sigma, p.sf_ped_attract_C) = self._ped_params
+            p.sf_sight_weight_use = int(suse)
+        self._params = p
+        self._engine = Engine(scene, p, device=self.device)
+
+        # resident action table of ActionTableAgents
+        self._action_table = self._action_table_host = None
+        if tables or self._any_host_policy:
+            T = max((len(t) for t in tables.values()), default=0)
+            if self._any_host_policy:
+                T = max(T, 1)
+            tab = np.zeros((max(T, 1), 2, N * M))
+            for (n, s), t in tables.items():
+                tab[: len(t), :, n * M + s] = t
+            self._action_table_host = tab
+            if tables:
+                self._action_table = self._engine.set_actions(tab)
+            mask = np.zeros(N * M, bool)
+            for n, st in enumerate(self.states):
+                for e, a in st.agents.items():
+                    if self._agent_kind[a] == "host_policy":
+                        mask[n * M + self._slot_of[n][e]] = True
+            self._host_policy_mask = mask
+            if self._any_host_policy and tables:
+                need = 1 << 16
+                if tab.shape[0] < need:  # host policies may run longer than the tables
+                    pass
+        self._ticks_since_reset = 1
+        self._host_done = [False] * N
+        self._cache: Dict[str, np.ndarray] = {}
+
+    def _sync_params(self) -> None:
+        self._params.timestep = self.timestep
+        self._params.persist = int(self.persist)
+
+    # ------------------------------------------------------------------ device -> host views
+    def _fetch(self, name: str) -> np.ndarray:
+        if name not in self._cache:
+            self._cache[name] = self._engine.get(name)
+        return self._cache[name]
+
+    def _materialise(self, n: int) -> dict:
+        eng = self._engine
+        M = eng.M
+        sl = slice(n * M, (n + 1) * M)
+        pose = eng.tensor("pose")[:, sl].cpu().numpy()
+        vel = eng.tensor("vel")[:, sl].cpu().numpy()
+        dist = eng.tensor("dist")[sl].cpu().numpy()
+        present = eng.tensor("present")[sl].cpu().numpy()
+        ents = self._entity_of[n]
+        poses, vels = {}, {}
+        for s, e in enumerate(ents):
+            if present[s]:
+                poses[e] = pose[:, s].copy()
+                vels[e] = vel[:, s].copy()
+        if self._rss_cb is not None:
+            self._sync_rss(n, ents, sl)
+        return {
+            "t": float(eng.tensor("t")[n].item()), "prev_t": float(eng.tensor("prev_t")[n].item()),
+            "done": bool(eng.tensor("done")[n].item()), "poses": poses, "velocities": vels,
+            "distances": {e: float(dist[s]) for s, e in enumerate(ents)},
+        }
+
+    def _sync_rss(self, n: int, ents, sl) -> None:
+        eng, cb = self._engine, self._rss_cb
+        sd = eng.tensor("safe_dist")[:, sl].cpu().numpy()
+        ratio = eng.tensor("safe_ratio")[:, sl].cpu().numpy()
+        rec = eng.tensor("rss_last")[sl].cpu().numpy()
+        cb.safe_distances = {e: [float(sd[0, s]), float(sd[1, s])] for s, e in enumerate(ents)
+                             if rec[s] != abi.RSS_NONE}
+        cb.entity_safe_ratios = {e: [float(ratio[0, s]), float(ratio[1, s])] for s, e in enumerate(ents)}
+        cb.intersect = {e: [abi.RSS_RECORD_NAMES[int(rec[s])]] for s, e in enumerate(ents)
+                        if rec[s] != abi.RSS_NONE}
+
+    def _collisions(self, n: int) -> Dict[Entity, List[Entity]]:
+        eng = self._engine
+        if not (self._params.features & abi.FEAT_COLL_MATRIX):
+            raise RuntimeError("state.collisions() needs the pair matrix; it is enabled whenever a "
+                               "host-side plugin is present")
+        mask = eng.tensor("coll_mask")[n].cpu().numpy().view(np.uint32)
+        ents = self._entity_of[n]
+        present = eng.tensor("present")[n * eng.M:(n + 1) * eng.M].cpu().numpy()
+        out = {}
+        for a, e in enumerate(ents):
+            if not present[a]:
+                continue
+            out[e] = [ents[b] for b in range(len(ents))
+                      if (int(mask[a, b >> 5]) >> (b & 31)) & 1]
+        return out
+
+    def _collision_events(self, n: int) -> list:
+        if "events" not in self._cache:
+            self._cache["events"] = self._engine.events()
+        ev = self._cache["events"]
+        ev = ev[ev["scenario"] == n]
+        ents = self._entity_of[n]
+        out = []
+        for e in ev:
+            hazard = ents[int(e["slot"])]
+            ctype = "non_vehicle" if hazard.catalog_entry.catalog_type != "Vehicle" else "vehicle"
+            out.append((float(e["t"]), hazard.ref, ctype))
+        return out
+
+    def _after_tick_host(self) -> None:
+        """Host-side callbacks, terminal conditions and metrics for the scenarios that ticked."""
+        eng = self._engine
+        ticks = eng.get("tick")
+        for n, st in enumerate(self.states):
+            if ticks[n] == self._last_tick[n]:
+                continue  # done scenario of a batch: the device skipped it
+            st._record()
+            for cb in self._host_callbacks[n]:
+                cb(st)
+            if any(cond(st) for cond in self._host_terminal):
+                self._host_done[n] = True
+                eng.tensor("done")[n] = 1
+            for m in self._host_metrics[n]:
+                m.step(st)
+        self._last_tick = ticks.copy()

@@ -1,0 +1,491 @@
+"""
+Plugin API -- the reference's subclassing surface for this path, with the same names,
+constructor arguments and hook methods (reference scenario_gym/action.py, agent.py,
+controller.py, sensor/base.py, sensor/common.py, observation.py, callback.py, metrics/*.py,
+pedestrian/*.py).  ``ScenarioGym`` (gym.py) inspects what ``create_agent`` returned and lowers
+the recognised classes to device slot kinds; anything else keeps working through a per-tick
+host call on a materialised ``State`` (drop-in, just slower).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Tuple, Type
+
+import numpy as np
+
+from .entity import Entity
+from .trajectory import Trajectory
+
+
+# ------------------------------------------------------------------------------ actions
+class Action:
+    """Base class for actions that agents communicate to controllers."""
+
+
+class TeleportAction(Action):
+    """Desired coordinates for the next pose (reference action.py:12-63)."""
+
+    def __init__(self, x=0.0, y=0.0, z=0.0, h=0.0, r=0.0, p=0.0, pose: Optional[np.ndarray] = None):
+        self.x = pose[0] if pose is not None else x
+        self.y = pose[1] if pose is not None else y
+        self.z = pose[2] if pose is not None else z
+        self.h = pose[3] if pose is not None else h
+        self.r = pose[4] if pose is not None else r
+        self.p = pose[5] if pose is not None else p
+
+    @property
+    def pose(self) -> np.ndarray:
+        return np.array([self.x, self.y, self.z, self.h, self.r, self.p])
+
+
+class VehicleAction(Action):
+    """An acceleration and a steering update (reference action.py:66-83)."""
+
+    def __init__(self, accel: float, steer: float):
+        self.acceleration = accel
+        self.steering = steer
+
+
+@dataclass
+class PedestrianAction(Action):
+    speed: float
+    heading: float
+
+
+# ------------------------------------------------------------------------------ observations
+@dataclass
+class Observation:
+    pass
+
+
+@dataclass
+class SingleEntityObservation(Observation):
+    entity: Entity
+    t: float
+    next_t: float
+    pose: np.ndarray
+    velocity: np.ndarray
+    distance_travelled: float
+    recorded_poses: np.ndarray
+    entity_state: Any
+
+
+# ------------------------------------------------------------------------------ sensors
+class Sensor:
+    """Produce an observation for an entity from the global state (reference sensor/base.py)."""
+
+    def __init__(self, entity: Entity):
+        self.entity = entity
+        self.initial_observation = None
+        self.last_observation = None
+
+    def reset(self, state):
+        self.last_observation = None
+        self.initial_observation = self._reset(state)
+        return self.initial_observation
+
+    def step(self, state):
+        self.last_observation = self._step(state)
+        return self.last_observation
+
+    def _reset(self, state):
+        raise NotImplementedError
+
+    def _step(self, state):
+        raise NotImplementedError
+
+
+class EgoLocalizationSensor(Sensor):
+    """Observation with the base entity information (reference sensor/common.py:39-50)."""
+
+    def _reset(self, state):
+        return self._step(state)
+
+    def _step(self, state):
+        return SingleEntityObservation(self.entity, *state.get_entity_data(self.entity))
+
+
+# ------------------------------------------------------------------------------ controllers
+class Controller:
+    """Takes the agent's action and returns the pose (reference controller.py:12-42)."""
+
+    def __init__(self, entity: Entity):
+        self.entity = entity
+
+    def reset(self, state) -> None:
+        self._reset(state)
+
+    def step(self, state, action):
+        return self._step(state, action)
+
+    def _reset(self, state) -> None:
+        raise NotImplementedError
+
+    def _step(self, state, action):
+        raise NotImplementedError
+
+
+class ReplayTrajectoryController(Controller):
+    def _reset(self, state) -> None:
+        pass
+
+    def _step(self, state, action: TeleportAction):
+        return action.pose
+
+
+class VehicleController(Controller):
+    """
+    Kinematic bicycle with clipped acceleration / steering (reference controller.py:57-140).
+    Agents that use this exact class are integrated on the device; ``_step`` is the host
+    implementation used only when a subclass overrides behaviour.
+    """
+
+    def __init__(self, entity: Entity, max_steer: float = 0.7, max_accel: float = 5.0,
+                 max_speed: Optional[float] = None, allow_reverse: bool = False):
+        super().__init__(entity)
+        self.max_steer = max_steer
+        self.max_accel = max_accel
+        self.allow_reverse = allow_reverse
+        self.max_speed = max_speed
+
+    def _reset(self, state) -> None:
+        self.speed = np.linalg.norm(state.velocities[self.entity][:2])
+        self.l = self.entity.catalog_entry.bounding_box.length
+
+    def _step(self, state, action):
+        if isinstance(action, VehicleAction):
+            accel, steer = action.acceleration, action.steering
+        else:
+            accel, steer = action
+        accel = np.clip(accel, -self.max_accel, self.max_accel)
+        steer = np.clip(steer, -self.max_steer, self.max_steer)
+        pose = state.poses[self.entity].copy()
+        dt = state.next_t - state.t
+        h = pose[3]
+        dx, dy = self.speed * np.cos(h), self.speed * np.sin(h)
+        dh = self.speed * np.tan(steer) / self.l
+        pose[[0, 1]] += np.array([dx, dy]) * dt
+        pose[3] += dh * dt
+        speed = self.speed + accel * dt
+        if not self.allow_reverse:
+            speed = np.maximum(0.0, speed)
+        if self.max_speed is not None:
+            speed = np.minimum(self.max_speed, speed)
+        self.speed = speed
+        return pose
+
+
+# ------------------------------------------------------------------------------ agents
+class Agent:
+    """Processes observations to select an action (reference agent.py:18-115)."""
+
+    def __init__(self, entity: Entity, controller: Controller, sensor: Sensor):
+        self.entity = entity
+        self.controller = controller
+        self.sensor = sensor
+        self.last_action = None
+        self.last_reward = None
+        self._trajectory: Optional[Trajectory] = None
+
+    def reset(self, state) -> None:
+        self.last_action = None
+        self.last_reward = None
+        self.sensor.reset(state)
+        self.controller.reset(state)
+        self._reset()
+
+    def step(self, state):
+        obs = self.sensor.step(state)
+        action = self._step(obs)
+        self.last_action = action
+        return self.controller.step(state, action)
+
+    def _reset(self) -> None:
+        pass
+
+    def _step(self, observation) -> Action:
+        pass
+
+    def finish(self, state) -> None:
+        pass
+
+    @property
+    def trajectory(self) -> Trajectory:
+        return self._trajectory if self._trajectory is not None else self.entity.trajectory
+
+    @trajectory.setter
+    def trajectory(self, trajectory: Trajectory):
+        self._trajectory = trajectory
+
+    def reward(self, state):
+        r = self._reward(state)
+        if r is not None:
+            self.last_reward = r
+        return r
+
+    def _reward(self, state):
+        pass
+
+
+class ReplayTrajectoryAgent(Agent):
+    """Follows the predefined trajectory (reference agent.py:118-128)."""
+
+    def _step(self, observation) -> Action:
+        return TeleportAction(pose=self.trajectory.position_at_t(observation.next_t))
+
+
+class ActionTableAgent(Agent):
+    """
+    Vehicle agent that plays back a pre-drawn ``(T, 2)`` table of (accel, steer) through a
+    ``VehicleController``: row k is the action of the k-th step after reset.  The whole table is
+    uploaded once, so rollouts of such agents run fused on the device.
+    """
+
+    def __init__(self, entity: Entity, table: np.ndarray, **controller_kwargs):
+        super().__init__(entity, VehicleController(entity, **controller_kwargs),
+                         EgoLocalizationSensor(entity))
+        self.table = np.ascontiguousarray(table, dtype=np.float64).reshape(-1, 2)
+        self.k = 0
+
+    def _reset(self) -> None:
+        self.k = 0
+
+    def _step(self, observation) -> VehicleAction:
+        a = self.table[self.k]
+        self.k += 1
+        return VehicleAction(a[0], a[1])
+
+
+def _create_agent(scenario, entity) -> Optional[Agent]:
+    """Default: a replay agent for the entity named "ego" (reference agent.py:151-169)."""
+    if entity.ref == "ego":
+        return ReplayTrajectoryAgent(entity, ReplayTrajectoryController(entity),
+                                     EgoLocalizationSensor(entity))
+    return None
+
+
+# ------------------------------------------------------------------------------ callbacks / metrics
+class StateCallback:
+    """Per-tick callback on the state (reference callback.py:9-41)."""
+
+    required_callbacks: List[Type["StateCallback"]] = []
+
+    def __init__(self):
+        self.callbacks: List[StateCallback] = []
+
+    def reset(self, state) -> None:
+        self.callbacks.clear()
+        for req in self.required_callbacks:
+            cb = state.get_callback(req)
+            if cb is None:
+                raise ValueError(f"Callback {req.__name__} is required for {self.__class__}.")
+            self.callbacks.append(cb)
+        self._reset(state)
+
+    def _reset(self, state) -> None:
+        pass
+
+    def __call__(self, state) -> None:
+        raise NotImplementedError
+
+
+class Metric:
+    """Base class for metrics (reference metrics/base.py:8-73)."""
+
+    name: Optional[str] = None
+    required_callbacks: List[Type[StateCallback]] = []
+
+    def __init__(self, name: Optional[str] = None):
+        if name is not None:
+            self.name = name
+        elif self.name is None:
+            self.name = self.__class__.__name__
+        self.callbacks: List[StateCallback] = []
+
+    def reset(self, state) -> None:
+        self.callbacks.clear()
+        for CB in self.required_callbacks:
+            cb = state.get_callback(CB)
+            if cb is None:
+                raise ValueError("Cannot run metric {} without callback {}.".format(
+                    self.__class__.__name__, CB.__name__))
+            self.callbacks.append(cb)
+        self._reset(state)
+
+    def step(self, state) -> None:
+        self._step(state)
+
+    def _reset(self, state) -> None:
+        raise NotImplementedError
+
+    def _step(self, state) -> None:
+        raise NotImplementedError
+
+    def get_state(self) -> Any:
+        raise NotImplementedError
+
+
+class _DeviceMetric(Metric):
+    """Built-in metric whose value is accumulated on the device; ``_pull`` reads it back."""
+
+    _device = True
+
+    def _reset(self, state) -> None:
+        self._value = None
+
+    def _step(self, state) -> None:
+        pass
+
+    def _pull(self, gym, n: int) -> None:
+        raise NotImplementedError
+
+    def get_state(self):
+        return self._value
+
+
+class EgoAvgSpeed(_DeviceMetric):
+    """Time-weighted average ego speed (reference metrics/trajectory.py:8-28)."""
+
+    name = "ego_avg_speed"
+
+    def _pull(self, gym, n):
+        self._value = float(gym._fetch("ego_avg_speed")[n])
+
+
+class EgoMaxSpeed(_DeviceMetric):
+    name = "ego_max_speed"
+
+    def _pull(self, gym, n):
+        self._value = float(gym._fetch("ego_max_speed")[n])
+
+
+class EgoDistanceTravelled(_DeviceMetric):
+    name = "ego_distance_travelled"
+
+    def _pull(self, gym, n):
+        self._value = float(gym._fetch("ego_dist")[n])
+
+
+class CollisionMetric(_DeviceMetric):
+    """
+    Records ``(t, ref, type)`` for every entity that starts colliding with the ego
+    (reference metrics/collision.py:46-86).  Non-vehicle hazards are ``"non_vehicle"`` as in the
+    reference; vehicle hazards -- whose classification raises AttributeError in the reference
+    (collision.py:94) -- are reported as ``"vehicle"``.
+    """
+
+    name = "collisions"
+
+    def __init__(self, c_tol: float = 0.4, name: Optional[str] = None):
+        self.c_tol = c_tol
+        super().__init__(name=name)
+
+    def _pull(self, gym, n):
+        self._value = gym._collision_events(n)
+
+    def get_state(self):
+        return list(self._value or [])
+
+
+class RSSParameters:
+    """RSS parameters (reference metrics/rss/callback.py:21-31)."""
+
+    RESPONSE_TIME = 0.6
+    MIN_LONG_ACCEL = 1.2 * 9.81
+    MAX_LONG_ACCEL = 1.2 * 9.81
+    MIN_SAFE_CLEARANCE = 0.1
+
+
+class RSSDistances(StateCallback):
+    """
+    Per-tick safe longitudinal / lateral distances and buffer-intersection records per entity
+    (reference metrics/rss/callback.py:34-505), computed on the device.  After a step
+    ``safe_distances[entity] = [lat, long]``, ``entity_safe_ratios[entity]`` and ``intersect[entity]``
+    (the record appended this tick) are available.
+    """
+
+    _device = True
+
+    def _reset(self, state) -> None:
+        self.safe_distances: Dict[Entity, List[float]] = {}
+        self.entity_safe_ratios: Dict[Entity, List[float]] = {}
+        self.intersect: Dict[Entity, List[str]] = {}
+
+    def __call__(self, state) -> None:
+        pass
+
+
+class RSS(_DeviceMetric):
+    """``safe_longitudinal`` / ``safe_lateral`` booleans (reference metrics/rss/rss.py:106-163)."""
+
+    required_callbacks = [RSSDistances]
+
+    def _pull(self, gym, n):
+        flags = int(gym._fetch("rss_flags")[n])
+        self._value = {"safe_longitudinal": not (flags & 1), "safe_lateral": not (flags & 2)}
+
+
+# ------------------------------------------------------------------------------ pedestrians
+class BehaviourParameters:
+    max_speed_factor = 1.3
+
+    def __init__(self, **kwargs):
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+
+class RandomWalkParameters(BehaviourParameters):
+    bias_lon = 0.0
+    bias_lat = 0.0
+    std_lon = 0.000002
+    std_lat = 0.0000001
+
+
+class SocialForceParameters(RandomWalkParameters):
+    """Parameters of the social force model (reference pedestrian/social_force.py:16-30)."""
+
+    distance_threshold = 3
+    sight_weight = 0.5
+    sight_weight_use = True
+    sight_angle = 200
+    relaxation_time = 1.5
+    ped_repulse_V = 1.0
+    ped_repulse_sigma = 1.0
+    ped_attract_C = 0.0
+    boundary_repulse_U = 10.0
+    boundary_repulse_R = 0.2
+    imp_boundary_repulse_U = 2.0
+    imp_boundary_repulse_R = 0.1
+
+
+class SocialForce:
+    """Social force behaviour (reference pedestrian/social_force.py:33-222), run on the device."""
+
+    def __init__(self, params: SocialForceParameters):
+        self.params = params
+        self.max_speed_factor = params.max_speed_factor
+        if params.std_lon != 0 or params.std_lat != 0:
+            raise ValueError(
+                "SocialForce noise draws from the global np.random in the reference; the device "
+                "engine supports std_lon = std_lat = 0 only")
+
+
+class PedestrianAgent(Agent):
+    """Pedestrian following a route with a behaviour model (reference pedestrian/agent.py:15-69)."""
+
+    def __init__(self, entity: Entity, route: List[np.ndarray], speed_desired: float,
+                 behaviour: SocialForce, max_speed: float = 5.0, head_rot_angle: float = 0.0,
+                 distance_threshold: float = 1.0):
+        super().__init__(entity, None, None)
+        self.route = [np.asarray(r, dtype=np.float64) for r in route]
+        self.speed_desired = speed_desired
+        self.behaviour = behaviour
+        self.max_speed = max_speed
+        self.head_rot_angle = head_rot_angle
+        self.distance_threshold = distance_threshold
+        self.goal_idx = 0
+        self.force = np.array([0.0, 0.0])
+
+    def reset(self, state) -> None:
+        self.goal_idx = 0
+        self.force = np.array([0.0, 0.0])

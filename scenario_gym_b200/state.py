@@ -1,0 +1,112 @@
+"""
+``State`` -- the read surface plugins rely on (reference scenario_gym/state/state.py), backed
+by the device buffers of one scenario.  It is materialised lazily (one small device->host copy
+per tick) and only when a host-side plugin, metric or terminal condition needs it.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .entity import Entity
+
+
+class State:
+    """Global state of one scenario: time, terminal flag, poses and velocities of the entities."""
+
+    def __init__(self, gym, n: int, scenario, scenario_path: Optional[str] = None):
+        self._gym = gym
+        self._n = n
+        self._scenario = scenario
+        self.scenario_path = scenario_path
+        self.persist = gym.persist
+        self.agents: Dict[Entity, Any] = {}
+        self.state_callbacks = gym.state_callbacks
+        self.entity_state: Dict[Entity, Any] = dict.fromkeys(scenario.entities)
+        self.next_t: Optional[float] = None
+        self.last_keystroke = None
+        self._recorded: Dict[Entity, List[Tuple[float, np.ndarray]]] = {e: [] for e in scenario.entities}
+        self._snap: Optional[dict] = None
+        self._collisions = None
+
+    # ------------------------------------------------------------------ device sync
+    def _invalidate(self) -> None:
+        self._snap = None
+        self._collisions = None
+
+    def _data(self) -> dict:
+        if self._snap is None:
+            self._snap = self._gym._materialise(self._n)
+        return self._snap
+
+    def _record(self) -> None:
+        """Append the current poses to the host-side trace (State._recorded_poses)."""
+        d = self._data()
+        for e, pose in d["poses"].items():
+            self._recorded[e].append((d["t"], pose))
+
+    # ------------------------------------------------------------------ reference surface
+    @property
+    def scenario(self):
+        return self._scenario
+
+    @property
+    def t(self) -> float:
+        return self._data()["t"]
+
+    @property
+    def prev_t(self) -> float:
+        return self._data()["prev_t"]
+
+    @property
+    def dt(self) -> float:
+        d = self._data()
+        return d["t"] - d["prev_t"]
+
+    @property
+    def is_done(self) -> bool:
+        return self._data()["done"] or self._gym._host_done[self._n]
+
+    @property
+    def poses(self) -> Dict[Entity, np.ndarray]:
+        return self._data()["poses"]
+
+    @property
+    def velocities(self) -> Dict[Entity, np.ndarray]:
+        return self._data()["velocities"]
+
+    @property
+    def distances(self) -> Dict[Entity, float]:
+        return self._data()["distances"]
+
+    def collisions(self) -> Dict[Entity, List[Entity]]:
+        """Entities whose boxes intersect at the current time (reference state.py:306-310)."""
+        if self._collisions is None:
+            self._collisions = self._gym._collisions(self._n)
+        return self._collisions
+
+    def get_callback(self, Callback):
+        for cb in self.state_callbacks:
+            if isinstance(cb, Callback):
+                return cb
+        return None
+
+    def recorded_poses(self, entity: Optional[Entity] = None):
+        def table(rows):
+            if not rows:
+                return np.empty((0, 7))
+            ts, poses = map(np.array, zip(*rows))
+            return np.concatenate([ts[:, None], poses], axis=1)
+
+        if entity is not None:
+            return table(self._recorded.get(entity))
+        return {e: table(r) for e, r in self._recorded.items()}
+
+    def get_entity_data(self, entity: Entity):
+        return (self.t, self.next_t, self.poses.get(entity), self.velocities.get(entity),
+                self.distances.get(entity), self.recorded_poses(entity=entity),
+                self.entity_state.get(entity))
+
+    def get_entity_box_points(self, e: Entity) -> np.ndarray:
+        return e.get_bounding_box_points(self.poses[e])
