@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--scenarios-per-gpu", type=int, default=0)
     ap.add_argument("--ticks", type=int, default=256)
     ap.add_argument("--no-rss", action="store_true")
@@ -58,24 +58,47 @@ def workload_spec(args):
     if args.workload == "c3":
         n = args.scenarios_per_gpu or 12500
         return dict(name="C3", N=n, M=64, T=args.ticks, dt=0.1)
+    if args.workload == "c2":
+        return dict(name="C2", N=args.scenarios_per_gpu or 4096, M=9, T=0, dt=1.0 / 30.0)
+    if args.workload == "c4":
+        return dict(name="C4", N=args.scenarios_per_gpu or 1000, M=1024, T=min(args.ticks, 128), dt=1.0 / 15.0)
     n = args.scenarios_per_gpu or 1250
     return dict(name="C5", N=n, M=256, T=args.ticks, dt=0.1)
 
 
 def features(args) -> int:
     f = abi.FEAT_COLLISIONS | abi.FEAT_EGO_METRICS
-    if not args.no_rss:
+    if not args.no_rss and args.workload in ("c3", "c5"):
         f |= abi.FEAT_RSS
     return f
 
 
 def algorithmic_bytes_per_entity_step(args) -> int:
     """SURVEY.md section 8d B_tick (per-tick streaming design, fp64 SoA)."""
+    if args.workload == "c2":
+        return 290
+    if args.workload == "c4":
+        return 305
     return 225 if args.no_rss else 259
+
+
+def c2_scene(n_scen: int):
+    """C2: replicas of the reference's 23 test scenarios (inputs committed under tests/golden)."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from helpers import all_xosc_specs
+
+    from scenario_gym_b200.packing import pack_scenarios, tile_scene
+
+    specs = [s for _, s, _, _ in all_xosc_specs("xosc")]
+    base = pack_scenarios(specs)
+    reps = -(-n_scen // base.N)
+    return slice_scene(tile_scene(base, reps), 0, n_scen)
 
 
 def make_config(args, seed: int, n_scen: int, actions_out=None):
     w = workload_spec(args)
+    if args.workload == "c4":
+        return synthetic.crowd_config(seed=seed, N=n_scen, M=w["M"], T=w["T"], dt=w["dt"])
     if args.workload == "c3":
         return synthetic.vehicles_config(seed=seed, N=n_scen, M=w["M"], T=w["T"], dt=w["dt"],
                                          actions_out=actions_out)
@@ -89,18 +112,23 @@ def make_config(args, seed: int, n_scen: int, actions_out=None):
 def config_json(args, extra=None):
     w = workload_spec(args)
     mets = ["CollisionMetric", "EgoAvgSpeed", "EgoMaxSpeed", "EgoDistanceTravelled"]
-    if not args.no_rss:
+    if features(args) & abi.FEAT_RSS:
         mets += ["RSSDistances", "RSS"]
-    c = {
-        "workload": f"{w['name']}: {w['N']} scenarios/GPU x {w['M']} VehicleController entities x "
-                    f"{w['T']} ticks, random accel/steer actions (BASELINE.json configs[2] per-GPU shard)"
-        if args.workload == "c3" else
-        f"{w['name']}: {w['N']} scenarios/GPU x {w['M']} highway vehicles x {w['T']} ticks",
-        "scenarios_per_gpu": w["N"], "entities": w["M"], "ticks": w["T"], "timestep": w["dt"],
-        "metrics": mets,
-        "l2_policy": "inputs larger than L2: the action table read by every step is "
-                     f"{w['N'] * w['M'] * w['T'] * 16 / 1e9:.2f} GB",
-    }
+    desc = {
+        "c2": f"C2: {w['N']} replicas of the reference's 23 test scenarios (1-9 entities, 324-722 ticks at "
+              "30 Hz), trajectory replay + CollisionMetric/ego metrics (BASELINE.json configs[1])",
+        "c3": f"C3: {w['N']} scenarios/GPU x {w['M']} VehicleController entities x {w['T']} ticks, random "
+              "accel/steer actions (BASELINE.json configs[2] per-GPU shard)",
+        "c4": f"C4: {w['N']} scenarios x {w['M']} social-force pedestrians x {w['T']} ticks "
+              "(BASELINE.json configs[3])",
+        "c5": f"C5: {w['N']} scenarios/GPU x {w['M']} highway vehicles x {w['T']} ticks, RSS + SafeDistance "
+              "(BASELINE.json configs[4] per-GPU shard)",
+    }[args.workload]
+    l2 = ("inputs larger than L2: the action table read by every step is "
+          f"{w['N'] * w['M'] * w['T'] * 16 / 1e9:.2f} GB") if args.workload in ("c3", "c5") else \
+        "L2 flushed between steps: the reset kernel rewrites every state plane before each rollout"
+    c = {"workload": desc, "scenarios_per_gpu": w["N"], "entities": w["M"], "ticks": w["T"],
+         "timestep": w["dt"], "metrics": mets, "l2_policy": l2}
     if extra:
         c.update(extra)
     return c
@@ -279,14 +307,37 @@ def run_b200(args):
     NM = N * M
 
     # inputs: generated straight into pinned host memory (the e2e path copies from there)
-    act_host = torch.empty((T, 2, NM), dtype=torch.float64, pin_memory=True)
-    cfg = make_config(args, seed=rank, n_scen=N, actions_out=act_host.numpy())
-    scene = synthetic.pack_synthetic(cfg)
+    act_host = act_dev = None
+    expected_ticks = None
+    if args.workload == "c2":
+        scene = c2_scene(N)
+        M = scene.M
+        NM = N * M
+        sys.path.insert(0, os.path.join(REPO, "tests"))
+        from helpers import all_xosc_specs
+
+        outs = [o for _, _, _, o in all_xosc_specs("xosc")]
+        per = np.array([int(o["present"][1:].sum()) for o in outs], np.int64)
+        tk = np.array([int(o["n_ticks"]) for o in outs], np.int64)
+        idx = np.arange(N) % len(outs)
+        steps_expected = int(per[idx].sum())
+        expected_ticks = tk[idx]
+        dt = w["dt"]
+    else:
+        if args.workload in ("c3", "c5"):
+            act_host = torch.empty((T, 2, NM), dtype=torch.float64, pin_memory=True)
+        cfg = make_config(args, seed=rank, n_scen=N,
+                          actions_out=None if act_host is None else act_host.numpy())
+        scene = synthetic.pack_synthetic(cfg)
+        steps_expected = N * M * T
+        expected_ticks = np.full(N, T)
+        dt = cfg.dt
     p = abi.default_params()
-    p.timestep = cfg.dt
+    p.timestep = dt
     p.features = features(args)
     eng = Engine(scene, p, device=dev, event_cap=1 << 22)
-    act_dev = eng.set_actions(act_host)
+    if act_host is not None:
+        act_dev = eng.set_actions(act_host)
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
@@ -322,8 +373,8 @@ def run_b200(args):
     reset_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     clocks = sampler.stop() if rank == 0 else None
     ticks = eng.get("tick")
-    steps_per_rollout = int(ticks.sum()) * M  # every entity is present at every tick in this workload
-    assert int(ticks.min()) == T and int(ticks.max()) == T, "every scenario must run exactly T ticks"
+    steps_per_rollout = steps_expected  # entity-steps = sum over ticks of entities present
+    assert np.array_equal(ticks, expected_ticks), "every scenario must run its full number of ticks"
 
     tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     total_steps = torch.tensor([float(steps_per_rollout)], dtype=torch.float64, device=dev)
@@ -355,8 +406,9 @@ def run_b200(args):
         for k, t in host_keep.items():
             setattr(hs, k, t.data_ptr() if t.numel() else None)
         hin, din = abi.SgInputs(), abi.SgInputs()
-        hin.actions, hin.n_action_ticks = act_host.data_ptr(), T
-        din.actions, din.n_action_ticks = act_dev.data_ptr(), T
+        if act_host is not None:
+            hin.actions, hin.n_action_ticks = act_host.data_ptr(), T
+            din.actions, din.n_action_ticks = act_dev.data_ptr(), T
         res_keep = {
             "ego_avg_speed": torch.empty(N, dtype=torch.float64, pin_memory=True),
             "ego_max_speed": torch.empty(N, dtype=torch.float64, pin_memory=True),
@@ -393,7 +445,7 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
         wall = time.perf_counter() - t0
         assert np.array_equal(res_keep["ego_avg_speed"].numpy(), ref_avg), "e2e path result mismatch"
-        assert int(res_keep["tick"].numpy().min()) == T
+        assert np.array_equal(res_keep["tick"].numpy(), expected_ticks)
         tw = torch.tensor([wall], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
@@ -423,7 +475,8 @@ def run_b200(args):
         traffic = tj.get(key)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "kernel": "sg_vehicle_kernel<RSS=%d>" % (0 if args.no_rss else 1), "kernel_ms": kern_ms, "reset_kernel_ms": reset_ms,
+        "traffic": traffic, "kernel": ("sg_vehicle_kernel<RSS=%d>" % (0 if args.no_rss else 1)) if args.workload in ("c3", "c5")
+        else "sg_rollout_kernel", "kernel_ms": kern_ms, "reset_kernel_ms": reset_ms,
         "algorithmic_bytes_per_entity_step": bpe, "entity_steps_per_launch": steps_per_rollout,
         "peak_source": peak_src,
         "note": "achieved = SURVEY 8d per-tick-streaming bytes (B_tick) x entity-steps / kernel time, "
