@@ -48,7 +48,7 @@ struct GroupLayout {
   int W;        // 32-bit words per collision row
   int H;        // half-sweep length M/2
   int QCAP;     // candidate-pair queue capacity
-  int off_act, off_rbox, off_hcs, off_ped, off_box, off_ego, off_cold, off_aabb, off_queue, off_hits, off_bits,
+  int off_act, off_rbox, off_hcs, off_ped, off_pednb, off_box, off_ego, off_cold, off_aabb, off_queue, off_hits, off_bits,
       off_acc, off_flags, off_orient;
   int bytes;
 };
@@ -72,6 +72,7 @@ static GroupLayout make_layout(int M, bool ped, bool rss) {
   L.off_rbox = o;   o += rss ? 8 * G * (int)sizeof(double) : 0;   // hazard corners in the ego frame
   L.off_hcs = o;    o += rss ? 2 * G * (int)sizeof(double) : 0;   // cos/sin of each heading
   L.off_ped = o;    o += ped ? 4 * G * (int)sizeof(double) : 0;   // old x,y,vx,vy (pedestrian sensors)
+  L.off_pednb = o;  o += ped ? (G + 32) * (int)sizeof(float4) : 0; // fp32 sensor boxes of the pedestrians (old state)
   L.off_box = o;    o += 4 * G * (int)sizeof(double);             // width, length, center_x, center_y
   L.off_ego = o;    o += EGO_N * (int)sizeof(double);
   L.off_cold = o;   o += COLD_ND * (int)sizeof(double) + COLD_NI * (int)sizeof(int);
@@ -95,6 +96,7 @@ struct Grp {
   double* rbox;
   double* hcs;
   double* pedbuf;
+  float4* pednb;
   double* boxp;
   double* egop;
   double* cold_d;
@@ -135,6 +137,7 @@ SG_DEV void setup_group(Grp& g, const SgScene& sc, const GroupLayout& L, unsigne
   g.rbox = (double*)(base + L.off_rbox);
   g.hcs = (double*)(base + L.off_hcs);
   g.pedbuf = (double*)(base + L.off_ped);
+  g.pednb = (float4*)(base + L.off_pednb);
   g.boxp = (double*)(base + L.off_box);
   g.egop = (double*)(base + L.off_ego);
   g.cold_d = (double*)(base + L.off_cold);
@@ -242,6 +245,37 @@ SG_DEV bool in_buffer(double x, double y, double r, double qx, double qy) {
   return true;
 }
 
+// closed-interval overlap of two conservative AABBs as one predicate chain; sets bit `bit`
+#define SG_AABB_TEST(hits, mb, ob, bit)                                                         \
+  asm("{ .reg .pred p;\n\t"                                                                     \
+      "setp.le.f32 p, %1, %2;\n\t"                                                              \
+      "setp.le.and.f32 p, %3, %4, p;\n\t"                                                       \
+      "setp.le.and.f32 p, %5, %6, p;\n\t"                                                       \
+      "setp.le.and.f32 p, %7, %8, p;\n\t"                                                       \
+      "@p or.b32 %0, %0, %9; }"                                                                  \
+      : "+r"(hits)                                                                              \
+      : "f"(mb.x), "f"(ob.z), "f"(ob.x), "f"(mb.z), "f"(mb.y), "f"(ob.w), "f"(ob.y), "f"(mb.w), \
+        "r"(bit))
+
+// old pose / velocity of every slot as seen by the pedestrians' sensors in the next tick, plus a
+// conservative fp32 box of half-size r/2 around pedestrians: two pedestrians can only be within
+// the sensor's 64-gon (circumradius r) if those boxes overlap
+SG_DEV void stage_ped_state(const Grp& c, bool present, int etype, double x, double y, double vx,
+                            double vy, double r, double ox, double oy) {
+  c.flags[c.s] = (uint8_t)((present ? 1 : 0) | (etype << 1));
+  c.pedbuf[c.s] = x; c.pedbuf[c.G + c.s] = y;
+  c.pedbuf[2 * c.G + c.s] = vx; c.pedbuf[3 * c.G + c.s] = vy;
+  float4 b = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+  if (present && etype == SG_ETYPE_PEDESTRIAN) {
+    const double h = 0.5 * r * (1.0 + 1e-9);
+    b.x = __double2float_rd(__dsub_rd(__dsub_rd(x, h), ox));
+    b.y = __double2float_rd(__dsub_rd(__dsub_rd(y, h), oy));
+    b.z = __double2float_ru(__dsub_ru(__dadd_ru(x, h), ox));
+    b.w = __double2float_ru(__dsub_ru(__dadd_ru(y, h), oy));
+  }
+  c.pednb[c.s] = b;
+}
+
 // PedestrianAgent._step + SocialForce._step + PedestrianController._step
 template <bool PED>
 SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c,
@@ -281,9 +315,18 @@ SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c,
     const double* by = c.pedbuf + c.G;
     const double* bvx = c.pedbuf + 2 * c.G;
     const double* bvy = c.pedbuf + 3 * c.G;
-    for (int o = 0; o < c.M; ++o) {  // state.poses order == slot order
-      const uint8_t fl = c.flags[o];
-      if (o == c.s || !(fl & 1) || (fl >> 1) != SG_ETYPE_PEDESTRIAN) continue;
+    const float4 mb = c.pednb[c.s];
+    for (int o0 = 0; o0 < c.M; o0 += 32) {  // state.poses order == slot order
+      uint32_t cand = 0;
+#pragma unroll
+      for (int oo = 0; oo < 32; ++oo) {  // pednb is padded with empty boxes beyond M
+        const float4 ob = c.pednb[o0 + oo];
+        SG_AABB_TEST(cand, mb, ob, 1u << oo);
+      }
+      if (c.s >= o0 && c.s < o0 + 32) cand &= ~(1u << (c.s - o0));
+      while (cand) {
+      const int o = o0 + __ffs(cand) - 1;
+      cand &= cand - 1;
       const double ox = bx[o], oy = by[o];
       if (!in_buffer(pose[0], pose[1], thr, ox, oy)) continue;
       const double ovx = bvx[o], ovy = bvy[o];
@@ -313,6 +356,7 @@ SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c,
       } else {
         F0 += Fa0; F1 += Fa1;
         F0 += Fr0; F1 += Fr1;
+      }
       }
     }
     speed = py_min(norm2(F0, F1) + p.sf_bias_lon, speed_desired * p.sf_max_speed_factor);
@@ -650,18 +694,6 @@ __device__ __noinline__ void record_pair(int features, uint32_t* coll_mask, cons
     atomicOr(&rows[(int64_t)hi * c.W + (lo >> 5)], 1u << (lo & 31));
   }
 }
-
-// closed-interval overlap of two conservative AABBs as one predicate chain; sets bit `bit`
-#define SG_AABB_TEST(hits, mb, ob, bit)                                                         \
-  asm("{ .reg .pred p;\n\t"                                                                     \
-      "setp.le.f32 p, %1, %2;\n\t"                                                              \
-      "setp.le.and.f32 p, %3, %4, p;\n\t"                                                       \
-      "setp.le.and.f32 p, %5, %6, p;\n\t"                                                       \
-      "setp.le.and.f32 p, %7, %8, p;\n\t"                                                       \
-      "@p or.b32 %0, %0, %9; }"                                                                  \
-      : "+r"(hits)                                                                              \
-      : "f"(mb.x), "f"(ob.z), "f"(ob.x), "f"(mb.z), "f"(mb.y), "f"(ob.w), "f"(ob.y), "f"(mb.w), \
-        "r"(bit))
 
 // circular half sweep over the staged AABBs (STRtree's envelope filter is closed too);
 // survivors go to the scenario's queue
@@ -1073,12 +1105,10 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   }
   load_cold(st, c, n, s, W, ego_slot);
   if (RSS && s == ego_slot) publish_ego_box(c);
-  if (live) {  // the "old" state the pedestrians' sensors read in the first tick
-    c.flags[s] = (uint8_t)((e.present ? 1 : 0) | (etype << 1));
-    if (PED) {
-      c.pedbuf[s] = e.pose[0]; c.pedbuf[G + s] = e.pose[1];
-      c.pedbuf[2 * G + s] = e.vel[0]; c.pedbuf[3 * G + s] = e.vel[1];
-    }
+  if (PED) {  // the "old" state the pedestrians' sensors read in the first tick
+    if (live) stage_ped_state(c, e.present, etype, e.pose[0], e.pose[1], e.vel[0], e.vel[1],
+                              p.ped_distance_threshold, ox, oy);
+    for (int q = s; q < 32; q += G) c.pednb[M + q] = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
   }
   group_sync(c);
 
@@ -1210,11 +1240,8 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     group_sync(c);
     // ---------------- phase B1: callbacks (RSS) + broad phase -------------------------------
     if (live) {
-      c.flags[s] = (uint8_t)((e.present ? 1 : 0) | (etype << 1));
-      if (PED) {
-        c.pedbuf[s] = e.pose[0]; c.pedbuf[G + s] = e.pose[1];
-        c.pedbuf[2 * G + s] = e.vel[0]; c.pedbuf[3 * G + s] = e.vel[1];
-      }
+      if (PED) stage_ped_state(c, e.present, etype, e.pose[0], e.pose[1], e.vel[0], e.vel[1],
+                               p.ped_distance_threshold, ox, oy);
       if (RSS && feat_rss) {  // RSSDistances.__call__, callback.py:57-122
         rss_last = SG_RSS_NONE;
         if (t != 0.0 && s != ego_slot && e.present && c.egop[EGO_PRESENT] != 0.0) {
