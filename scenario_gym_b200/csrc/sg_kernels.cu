@@ -25,6 +25,7 @@
 #include "sg_device.cuh"
 
 #define SG_THREADS 256
+#define SG_NBCAP 12  // per-pedestrian neighbour candidate list kept in shared memory
 #ifndef SG_VEH_MINB
 #define SG_VEH_MINB 2  // resident CTAs per SM the vehicle kernel is compiled for
 #endif
@@ -48,7 +49,7 @@ struct GroupLayout {
   int W;        // 32-bit words per collision row
   int H;        // half-sweep length M/2
   int QCAP;     // candidate-pair queue capacity
-  int off_act, off_rbox, off_hcs, off_ped, off_pednb, off_box, off_ego, off_cold, off_aabb, off_queue, off_hits, off_bits,
+  int off_act, off_rbox, off_hcs, off_ped, off_pednb, off_nbl, off_box, off_ego, off_cold, off_aabb, off_queue, off_hits, off_bits,
       off_acc, off_flags, off_orient;
   int bytes;
 };
@@ -59,7 +60,7 @@ enum { COLD_AVG = 0, COLD_AVG_T, COLD_MAX, COLD_EGOD, COLD_ND = 4 };            
 enum { COLD_FIRST_TICK = 0, COLD_FP0, COLD_FP1, COLD_RSS, COLD_PAIR_TICKS = 4, COLD_NI = 8 };  // ints
 enum { ACC_NPAIRS = 0, ACC_FIRST_PAIR, ACC_FIRST_HIT, ACC_RSS, ACC_QCOUNT, ACC_N = 8 };
 
-static GroupLayout make_layout(int M, bool ped, bool rss) {
+static GroupLayout make_layout(int M, bool ped, bool rss, bool veh) {
   GroupLayout L;
   int G;
   if (M <= 32) { G = 1; while (G < M) G <<= 1; } else { G = (M + 31) / 32 * 32; }
@@ -68,11 +69,13 @@ static GroupLayout make_layout(int M, bool ped, bool rss) {
   L.H = M / 2;
   L.QCAP = 4 * G;
   int o = 8 * G * (int)sizeof(double);                            // corners[8][G]
-  L.off_act = o;    o += 4 * G * (int)sizeof(double);             // VehicleAction rows, 2 stages x (accel, steer)
+  L.off_act = o;    o += veh ? 4 * G * (int)sizeof(double) : 0;             // VehicleAction rows, 2 stages x (accel, steer)
   L.off_rbox = o;   o += rss ? 8 * G * (int)sizeof(double) : 0;   // hazard corners in the ego frame
   L.off_hcs = o;    o += rss ? 2 * G * (int)sizeof(double) : 0;   // cos/sin of each heading
   L.off_ped = o;    o += ped ? 4 * G * (int)sizeof(double) : 0;   // old x,y,vx,vy (pedestrian sensors)
   L.off_pednb = o;  o += ped ? (G + 32) * (int)sizeof(float4) : 0; // fp32 sensor boxes of the pedestrians (old state)
+  L.off_nbl = o;    o += ped ? SG_NBCAP * G * (int)sizeof(uint16_t) : 0;
+  o = (o + 15) / 16 * 16;
   L.off_box = o;    o += 4 * G * (int)sizeof(double);             // width, length, center_x, center_y
   L.off_ego = o;    o += EGO_N * (int)sizeof(double);
   L.off_cold = o;   o += COLD_ND * (int)sizeof(double) + COLD_NI * (int)sizeof(int);
@@ -97,6 +100,7 @@ struct Grp {
   double* hcs;
   double* pedbuf;
   float4* pednb;
+  uint16_t* nblist;
   double* boxp;
   double* egop;
   double* cold_d;
@@ -138,6 +142,7 @@ SG_DEV void setup_group(Grp& g, const SgScene& sc, const GroupLayout& L, unsigne
   g.hcs = (double*)(base + L.off_hcs);
   g.pedbuf = (double*)(base + L.off_ped);
   g.pednb = (float4*)(base + L.off_pednb);
+  g.nblist = (uint16_t*)(base + L.off_nbl);
   g.boxp = (double*)(base + L.off_box);
   g.egop = (double*)(base + L.off_ego);
   g.cold_d = (double*)(base + L.off_cold);
@@ -315,20 +320,10 @@ SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c,
     const double* by = c.pedbuf + c.G;
     const double* bvx = c.pedbuf + 2 * c.G;
     const double* bvy = c.pedbuf + 3 * c.G;
-    const float4 mb = c.pednb[c.s];
-    for (int o0 = 0; o0 < c.M; o0 += 32) {  // state.poses order == slot order
-      uint32_t cand = 0;
-#pragma unroll
-      for (int oo = 0; oo < 32; ++oo) {  // pednb is padded with empty boxes beyond M
-        const float4 ob = c.pednb[o0 + oo];
-        SG_AABB_TEST(cand, mb, ob, 1u << oo);
-      }
-      if (c.s >= o0 && c.s < o0 + 32) cand &= ~(1u << (c.s - o0));
-      while (cand) {
-      const int o = o0 + __ffs(cand) - 1;
-      cand &= cand - 1;
+    // neighbour force of slot o (reference social_force.py:51-80, 140-188, 213-222)
+    auto add_neighbour = [&](int o) {
       const double ox = bx[o], oy = by[o];
-      if (!in_buffer(pose[0], pose[1], thr, ox, oy)) continue;
+      if (!in_buffer(pose[0], pose[1], thr, ox, oy)) return;
       const double ovx = bvx[o], ovy = bvy[o];
       const double vdx = ovx * ch + ovy * -sh, vdy = ovx * sh + ovy * ch;
       const double vn = norm2(vdx, vdy) + 0.0000000001;
@@ -357,6 +352,34 @@ SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c,
         F0 += Fa0; F1 += Fa1;
         F0 += Fr0; F1 += Fr1;
       }
+    };
+    // sensor sweep: fp32 box prefilter over all slots in state.poses (= slot) order; candidates are
+    // first collected per thread, then the k-th candidates of all lanes are evaluated together
+    const float4 mb = c.pednb[c.s];
+    uint16_t* nbl = c.nblist + c.s;
+    int ncand = 0;
+    for (int o0 = 0; o0 < c.M; o0 += 32) {
+      uint32_t cand = 0;
+#pragma unroll
+      for (int oo = 0; oo < 32; ++oo) {  // pednb is padded with empty boxes beyond M
+        const float4 ob = c.pednb[o0 + oo];
+        SG_AABB_TEST(cand, mb, ob, 1u << oo);
+      }
+      if (c.s >= o0 && c.s < o0 + 32) cand &= ~(1u << (c.s - o0));
+      while (cand) {
+        const int o = o0 + __ffs(cand) - 1;
+        cand &= cand - 1;
+        if (ncand < SG_NBCAP) nbl[ncand * c.G] = (uint16_t)o;
+        ++ncand;
+      }
+    }
+    for (int k = 0; k < min(ncand, SG_NBCAP); ++k) add_neighbour(nbl[k * c.G]);
+    if (ncand > SG_NBCAP) {  // very dense crowd: re-sweep for the candidates beyond the list
+      int seen = 0;
+      for (int o = 0; o < c.M; ++o) {
+        const float4 ob = c.pednb[o];
+        if (o == c.s || !(mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w)) continue;
+        if (seen++ >= SG_NBCAP) add_neighbour(o);
       }
     }
     speed = py_min(norm2(F0, F1) + p.sf_bias_lon, speed_desired * p.sf_max_speed_factor);
@@ -1465,7 +1488,9 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
   if (rc) return rc;
   const bool ped = sc->route_off != nullptr && sc->n_route_pts > 0;
   const bool rss = (p->features & SG_FEAT_RSS) != 0;
-  GroupLayout L = make_layout(sc->n_slots, ped, rss);
+  const uint32_t veh_bits = (1u << SG_KIND_VEHICLE), ok_bits = veh_bits | (1u << SG_KIND_EMPTY);
+  const bool veh_only = (sc->kind_mask & veh_bits) && !(sc->kind_mask & ~ok_bits);
+  GroupLayout L = make_layout(sc->n_slots, ped, rss, veh_only);
   const int threads = L.G <= SG_THREADS ? SG_THREADS : L.G;
   const bool big = threads > SG_THREADS;
   const int gpb = threads / L.G;
@@ -1482,8 +1507,6 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
   SgInputs none;
   memset(&none, 0, sizeof(none));
   const SgInputs inp = in ? *in : none;
-  const uint32_t veh_bits = (1u << SG_KIND_VEHICLE), ok_bits = veh_bits | (1u << SG_KIND_EMPTY);
-  const bool veh_only = (sc->kind_mask & veh_bits) && !(sc->kind_mask & ~ok_bits);
   if (veh_only) {
     if (!inp.actions) return set_msg("vehicle scene needs an action table");
     err = rss ? launch_vehicle<true>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L)
