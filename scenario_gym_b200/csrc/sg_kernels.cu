@@ -26,8 +26,11 @@
 
 #define SG_THREADS 256
 #define SG_NBCAP 12  // per-pedestrian neighbour candidate list kept in shared memory
+#ifndef SG_VEH_THREADS
+#define SG_VEH_THREADS 128  // CTA size of the vehicle kernel for scenarios of up to that many slots
+#endif
 #ifndef SG_VEH_MINB
-#define SG_VEH_MINB 2  // resident CTAs per SM the vehicle kernel is compiled for
+#define SG_VEH_MINB 4  // resident CTAs per SM the vehicle kernel is compiled for
 #endif
 
 __constant__ double c_ngon[64][2];  // (cos, sin)(-k * 2pi/64): GEOS Point.buffer vertices
@@ -1465,10 +1468,17 @@ static cudaError_t launch_rollout(bool big, int blocks, int threads, size_t smem
 }
 
 template <bool RSS>
-static cudaError_t launch_vehicle(bool big, int blocks, int threads, size_t smem, cudaStream_t s,
-                                  const SgScene& sc, const SgParams& p, const SgState& st,
-                                  const SgInputs& in, int n_ticks, const GroupLayout& L) {
-  auto kern = big ? sg_vehicle_kernel<RSS, 1024, 1> : sg_vehicle_kernel<RSS, SG_THREADS, SG_VEH_MINB>;
+static cudaError_t launch_vehicle(int n_scen, cudaStream_t s, const SgScene& sc, const SgParams& p,
+                                  const SgState& st, const SgInputs& in, int n_ticks,
+                                  const GroupLayout& L) {
+  void (*kern)(SgScene, SgParams, SgState, SgInputs, int, GroupLayout);
+  int threads;
+  if (L.G <= SG_VEH_THREADS) { kern = sg_vehicle_kernel<RSS, SG_VEH_THREADS, SG_VEH_MINB>; threads = SG_VEH_THREADS; }
+  else if (L.G <= SG_THREADS) { kern = sg_vehicle_kernel<RSS, SG_THREADS, 2>; threads = SG_THREADS; }
+  else { kern = sg_vehicle_kernel<RSS, 1024, 1>; threads = L.G; }
+  const int gpb = threads / L.G;
+  const int blocks = (n_scen + gpb - 1) / gpb;
+  const size_t smem = (size_t)gpb * L.bytes;
   if (smem > 48 * 1024) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
@@ -1509,8 +1519,8 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
   const SgInputs inp = in ? *in : none;
   if (veh_only) {
     if (!inp.actions) return set_msg("vehicle scene needs an action table");
-    err = rss ? launch_vehicle<true>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L)
-              : launch_vehicle<false>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
+    err = rss ? launch_vehicle<true>(sc->n_scenarios, s, *sc, *p, *st, inp, n_ticks, L)
+              : launch_vehicle<false>(sc->n_scenarios, s, *sc, *p, *st, inp, n_ticks, L);
   } else if (ped && rss) err = launch_rollout<true, true>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
   else if (ped) err = launch_rollout<true, false>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
   else if (rss) err = launch_rollout<false, true>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
