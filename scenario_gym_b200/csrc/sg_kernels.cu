@@ -52,14 +52,15 @@ struct GroupLayout {
   int W;        // 32-bit words per collision row
   int H;        // half-sweep length M/2
   int QCAP;     // candidate-pair queue capacity
-  int off_act, off_rbox, off_hcs, off_ped, off_pednb, off_nbl, off_box, off_ego, off_cold, off_aabb, off_queue, off_hits, off_bits,
+  int off_act, off_rbox, off_tcold, off_hcs, off_ped, off_pednb, off_nbl, off_box, off_ego, off_cold, off_aabb, off_queue, off_hits, off_bits,
       off_acc, off_flags, off_orient;
   int bytes;
 };
 
 enum { EGO_X = 0, EGO_Y, EGO_C, EGO_S, EGO_INV0, EGO_INV1, EGO_HD0, EGO_HD1, EGO_HINV0, EGO_HINV1,
        EGO_V0, EGO_V1, EGO_VNORM, EGO_VLONG, EGO_W, EGO_L, EGO_RHW, EGO_RHL, EGO_PRESENT, EGO_N = 20 };
-enum { COLD_AVG = 0, COLD_AVG_T, COLD_MAX, COLD_EGOD, COLD_ND = 4 };                 // doubles
+enum { COLD_AVG = 0, COLD_AVG_T, COLD_MAX, COLD_EGOD, COLD_T0, COLD_T1, COLD_PT0, COLD_PT1, COLD_LEN,
+       COLD_OX, COLD_OY, COLD_R2MINA, COLD_ND = 12 };  // doubles (T/PT: tick time, 2 parities)
 enum { COLD_FIRST_TICK = 0, COLD_FP0, COLD_FP1, COLD_RSS, COLD_PAIR_TICKS = 4, COLD_NI = 8 };  // ints
 enum { ACC_NPAIRS = 0, ACC_FIRST_PAIR, ACC_FIRST_HIT, ACC_RSS, ACC_QCOUNT, ACC_N = 8 };
 
@@ -74,6 +75,7 @@ static GroupLayout make_layout(int M, bool ped, bool rss, bool veh) {
   int o = 8 * G * (int)sizeof(double);                            // corners[8][G]
   L.off_act = o;    o += veh ? 4 * G * (int)sizeof(double) : 0;             // VehicleAction rows, 2 stages x (accel, steer)
   L.off_rbox = o;   o += rss ? 8 * G * (int)sizeof(double) : 0;   // hazard corners in the ego frame
+  L.off_tcold = o;  o += veh ? 6 * G * (int)sizeof(double) : 0;   // per-thread cold values: sd[2], ratio[2], vh, 1/length
   L.off_hcs = o;    o += rss ? 2 * G * (int)sizeof(double) : 0;   // cos/sin of each heading
   L.off_ped = o;    o += ped ? 4 * G * (int)sizeof(double) : 0;   // old x,y,vx,vy (pedestrian sensors)
   L.off_pednb = o;  o += ped ? (G + 32) * (int)sizeof(float4) : 0; // fp32 sensor boxes of the pedestrians (old state)
@@ -100,6 +102,7 @@ struct Grp {
   double* corners;
   double* actbuf;
   double* rbox;
+  double* tcold;
   double* hcs;
   double* pedbuf;
   float4* pednb;
@@ -142,6 +145,7 @@ SG_DEV void setup_group(Grp& g, const SgScene& sc, const GroupLayout& L, unsigne
   g.corners = (double*)base;
   g.actbuf = (double*)(base + L.off_act);
   g.rbox = (double*)(base + L.off_rbox);
+  g.tcold = (double*)(base + L.off_tcold);
   g.hcs = (double*)(base + L.off_hcs);
   g.pedbuf = (double*)(base + L.off_ped);
   g.pednb = (float4*)(base + L.off_pednb);
@@ -549,7 +553,7 @@ struct RssConst {  // uniform per launch
 // so every record equals the reference's; scalar quotients with a launch-uniform or shared
 // denominator use div_r.
 SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, double vx, double vy,
-                      uint8_t& state, double sd[2], double ratio[2]) {
+                      uint8_t& state, double* out, int ost) {  // out: lat, long, ratio lat, ratio long
   const double* E = c.egop;
   const double eh0 = E[EGO_C], eh1 = E[EGO_S], ei0 = E[EGO_INV0], ei1 = E[EGO_INV1];
   const double dirc = c.hcs[c.s], dirs = c.hcs[c.G + c.s];
@@ -609,8 +613,8 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
     }
     slat = fabs(early ? K.CLR + 0.5 * eW : dd + K.CLR + 0.5 * eW);
   }
-  sd[0] = slat;
-  sd[1] = slong;
+  out[0] = slat;
+  out[ost] = slong;
   // safe_ratios (callback.py:124-166)
   {
     const double hn = norm2(hd1, hd0), rhn = 1.0 / hn;  // inverse_direction(haz heading)
@@ -619,8 +623,8 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
     const double wl_dir = fabs(dot2(bw, bl, hd0, hd1));
     const double actual_lat = py_max(1e-6, fabs(pos0) - 0.5 * eW - 0.5 * wl_inv);
     const double actual_long = py_max(1e-6, fabs(pos1) - 0.5 * eL - 0.5 * wl_dir);
-    ratio[0] = fabs(div_r(actual_lat, 0.5 * eW, E[EGO_RHW]));
-    ratio[1] = fabs(div_r(actual_long, 0.5 * eL, E[EGO_RHL]));
+    out[2 * ost] = fabs(div_r(actual_lat, 0.5 * eW, E[EGO_RHW]));
+    out[3 * ost] = fabs(div_r(actual_long, 0.5 * eL, E[EGO_RHL]));
   }
   // unsafe_distance (callback.py:168-228)
   if ((state >> 2) & 3) return SG_RSS_FOUND;
@@ -900,80 +904,80 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   if (gl >= gpb || n >= sc.n_scenarios) return;
   Grp c;
   setup_group(c, sc, L, smem, gl, s, n);
-  const int64_t i = c.i, nm = c.nm;
-  const bool live = s < M && sc.kind[i] == SG_KIND_VEHICLE;
+  const bool live = s < M && sc.kind[c.i] == SG_KIND_VEHICLE;
   const int ego_slot = sc.ego_slot[n], first_slot = sc.first_slot[n];
   const bool need_coll = (p.features & SG_FEAT_COLLISIONS) ||
                          (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
   const bool feat_rss = RSS && (p.features & SG_FEAT_RSS);
   const bool matrix = (p.features & SG_FEAT_COLL_MATRIX) != 0;
-  const RssConst KR = make_rss_const(p);
 
-  double x = 0, y = 0, h = 0, vx = 0, vy = 0, vh = 0, vz = 0, dist = 0, speed = 0, cs = 1, sn = 0;
-  double bl = 1, rcp_bl = 1;
+  // hot per-entity state in registers; everything that is only read back at the end (safe
+  // distances, ratios, heading rate) or is uniform per scenario (tick times, length, origin)
+  // lives in shared memory to keep the register footprint of the tick loop small
+  double x = 0, y = 0, h = 0, vx = 0, vy = 0, dist = 0, speed = 0, cs = 1, sn = 0;
   int orient_hint = 0;
   bool present = false;
   uint8_t collided = 0, rss_state = 0, rss_last = SG_RSS_NONE;
-  double sd[2] = {0, 0}, ratio[2] = {0, 0};
-  if (live) {
-    x = st.pose[i]; y = st.pose[nm + i]; h = st.pose[3 * nm + i];
-    vx = st.vel[i]; vy = st.vel[nm + i]; vz = st.vel[2 * nm + i]; vh = st.vel[3 * nm + i];
-    dist = st.dist[i]; speed = st.speed[i];
-    present = st.present[i] != 0;
-    collided = st.collided[i];
-    sincos_fast(h, sn, cs);
-    const double bw = sc.box[i];
-    bl = sc.box[nm + i];
-    c.boxp[s] = bw; c.boxp[G + s] = bl;
-    c.boxp[2 * G + s] = sc.box[2 * nm + i]; c.boxp[3 * G + s] = sc.box[3 * nm + i];
-    rcp_bl = 1.0 / bl;
-    orient_hint = box_orientation_hint(bw, bl);
-    if (RSS) {
-      rss_state = st.rss_state[i]; rss_last = st.rss_last[i];
-      sd[0] = st.safe_dist[i]; sd[1] = st.safe_dist[nm + i];
-      ratio[0] = st.safe_ratio[i]; ratio[1] = st.safe_ratio[nm + i];
+  double* tc = c.tcold + s;  // [0..3] safe dist / ratios, [4] heading rate, [5] 1 / wheelbase
+  {
+    const int64_t i = c.i, nm = c.nm;
+    if (live) {
+      x = st.pose[i]; y = st.pose[nm + i]; h = st.pose[3 * nm + i];
+      vx = st.vel[i]; vy = st.vel[nm + i];
+      dist = st.dist[i]; speed = st.speed[i];
+      present = st.present[i] != 0;
+      collided = st.collided[i];
+      sincos_fast(h, sn, cs);
+      const double bw = sc.box[i], bl = sc.box[nm + i];
+      c.boxp[s] = bw; c.boxp[G + s] = bl;
+      c.boxp[2 * G + s] = sc.box[2 * nm + i]; c.boxp[3 * G + s] = sc.box[3 * nm + i];
+      tc[4 * G] = st.vel[3 * nm + i];
+      tc[5 * G] = 1.0 / bl;
+      orient_hint = box_orientation_hint(bw, bl);
+      if (RSS) {
+        rss_state = st.rss_state[i]; rss_last = st.rss_last[i];
+        tc[0] = st.safe_dist[i]; tc[G] = st.safe_dist[nm + i];
+        tc[2 * G] = st.safe_ratio[i]; tc[3 * G] = st.safe_ratio[nm + i];
+      }
+    }
+    if (s == 0) {
+      double* U = c.cold_d;
+      U[COLD_T0] = st.t[n]; U[COLD_PT0] = st.prev_t[n];
+      U[COLD_LEN] = sc.length[n];
+      const int64_t er = sc.traj_off[(int64_t)n * M + ego_slot];  // origin of the fp32 bounds
+      U[COLD_OX] = __ldg(sc.traj_rows + er * 7 + 1);
+      U[COLD_OY] = __ldg(sc.traj_rows + er * 7 + 2);
+      U[COLD_R2MINA] = 1.0 / (2 * p.rss_min_long_accel);
     }
   }
-  double t = st.t[n], prev_t = st.prev_t[n];
   int tick = st.tick[n];
   bool done = st.done[n] != 0;
-  const double length = sc.length[n];
-  double ox, oy;  // scenario origin for the fp32 bounds: the ego's first control point
-  {
-    const int64_t er = sc.traj_off[(int64_t)n * M + ego_slot];
-    ox = __ldg(sc.traj_rows + er * 7 + 1);
-    oy = __ldg(sc.traj_rows + er * 7 + 2);
-  }
   load_cold(st, c, n, s, W, ego_slot);
   if (RSS && s == ego_slot) publish_ego_box(c);
   group_sync(c);
 
   int limit = n_ticks < 0 ? p.max_ticks : n_ticks;
   if (limit > in.n_action_ticks) limit = in.n_action_ticks;
-  int parity = 0, ticks_run = 0;
+  int parity = 0;
+  const int tick0 = tick;
   // VehicleAction rows are staged one tick ahead with cp.async (no registers held)
-  const double* act = in.actions + i;
+  const double* act = in.actions + c.i;
   double* ab = c.actbuf + s;
-  if (live && limit > 0 && (!done || in.step_done)) { cp_async8(ab, act); cp_async8(ab + G, act + nm); }
+  if (live && limit > 0 && (!done || in.step_done)) { cp_async8(ab, act); cp_async8(ab + G, act + c.nm); }
   cp_async_commit();
 
   for (int k = 0; k < limit && (!done || in.step_done); ++k) {
+    const double* U = c.cold_d;
+    const double t = U[COLD_T0 + parity];
     const double next_t = t + p.timestep;  // scenario_gym.py:229
     const double dt = next_t - t;          // controller.py:123 and State.dt after the step
     cp_async_wait_all();
-    const double a_accel = ab[(k & 1) * 2 * G], a_steer = ab[(k & 1) * 2 * G + G];
-    if (live && k + 1 < limit) {
-      const double* nxt = act + (int64_t)(k + 1) * 2 * nm;
-      cp_async8(ab + ((k + 1) & 1) * 2 * G, nxt);
-      cp_async8(ab + ((k + 1) & 1) * 2 * G + G, nxt + nm);
-    }
-    cp_async_commit();
     if (live && present) {  // VehicleController._step, controller.py:105-140
-      const double accel = clipd(a_accel, -p.veh_max_accel, p.veh_max_accel);
-      const double steer = clipd(a_steer, -p.veh_max_steer, p.veh_max_steer);
+      const double accel = clipd(ab[parity * 2 * G], -p.veh_max_accel, p.veh_max_accel);
+      const double steer = clipd(ab[parity * 2 * G + G], -p.veh_max_steer, p.veh_max_steer);
       const double dx = speed * cs, dy = speed * sn;
       const double tn = fabs(steer) <= 0.78 ? tan_small(steer) : tan(steer);
-      const double dh = div_r(speed * tn, bl, rcp_bl);
+      const double dh = div_r(speed * tn, c.boxp[G + s], tc[5 * G]);
       const double nx = x + dx * dt, ny = y + dy * dt, nh = h + dh * dt;
       double ns = speed + accel * dt;
       if (!p.veh_allow_reverse) ns = ns < 0.0 ? 0.0 : ns;
@@ -981,39 +985,52 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       speed = ns;
       // State.update_statistics (state.py:230-239)
       const double rdt = 1.0 / dt;
-      const double ex = nx - x, ey = ny - y, ehh = nh - h;
-      vx = div_r(ex, dt, rdt); vy = div_r(ey, dt, rdt); vh = div_r(ehh, dt, rdt);
-      vz = 0.0;
+      const double ex = nx - x, ey = ny - y;
+      vx = div_r(ex, dt, rdt); vy = div_r(ey, dt, rdt);
+      tc[4 * G] = div_r(nh - h, dt, rdt);
       dist += norm3(ex, ey, 0.0);
       x = nx; y = ny; h = nh;
       sincos_fast(h, sn, cs);
     }
-    prev_t = t;
-    t = next_t;
+    if (live && k + 1 < limit) {
+      act += 2 * c.nm;
+      cp_async8(ab + (parity ^ 1) * 2 * G, act);
+      cp_async8(ab + (parity ^ 1) * 2 * G + G, act + c.nm);
+    }
+    cp_async_commit();
     tick += 1;
-    ticks_run += 1;
     if (st.trace_cap > 0 && tick < st.trace_cap && s < M) {
+      const int64_t i = c.i, nm = c.nm;
       st.trace_present[(int64_t)tick * nm + i] = present;
       double* tp = st.trace_pose + (int64_t)tick * 6 * nm + i;
       tp[0] = x; tp[nm] = y; tp[2 * nm] = st.pose[2 * nm + i]; tp[3 * nm] = h;
       tp[4 * nm] = st.pose[4 * nm + i]; tp[5 * nm] = st.pose[5 * nm + i];
-      if (s == 0) st.trace_t[(int64_t)tick * sc.n_scenarios + n] = t;
+      if (s == 0) st.trace_t[(int64_t)tick * sc.n_scenarios + n] = next_t;
     }
     if (s < M) {
-      if (need_coll || feat_rss) publish_box<RSS>(c, present, x, y, cs, sn, orient_hint, ox, oy);
+      if (need_coll || feat_rss)
+        publish_box<RSS>(c, present, x, y, cs, sn, orient_hint, U[COLD_OX], U[COLD_OY]);
       if (matrix) {
         uint32_t* row = st.coll_mask + ((int64_t)n * M + s) * W;
         for (int w = 0; w < W; ++w) row[w] = 0;
       }
     }
     if (RSS && feat_rss && s == ego_slot) publish_ego(c, present, x, y, cs, sn, vx, vy);
+    if (s == 0) {  // the next tick reads its times from the other parity
+      c.cold_d[COLD_T0 + (parity ^ 1)] = next_t;
+      c.cold_d[COLD_PT0 + (parity ^ 1)] = t;
+    }
     group_sync(c);
     // ---- phase B1: callbacks (RSS) + broad phase
     if (live && present) {
       if (RSS && feat_rss) {  // RSSDistances.__call__, callback.py:57-122
         rss_last = SG_RSS_NONE;
-        if (t != 0.0 && s != ego_slot && c.egop[EGO_PRESENT] != 0.0) {
-          rss_last = (uint8_t)rss_hazard(KR, c, x, y, vx, vy, rss_state, sd, ratio);
+        if (next_t != 0.0 && s != ego_slot && c.egop[EGO_PRESENT] != 0.0) {
+          RssConst KR;
+          KR.CLR = p.rss_min_safe_clearance; KR.RT = p.rss_response_time;
+          KR.MAXA = p.rss_max_long_accel; KR.MINA = p.rss_min_long_accel;
+          KR.r2mina = c.cold_d[COLD_R2MINA];
+          rss_last = (uint8_t)rss_hazard(KR, c, x, y, vx, vy, rss_state, tc, G);
           const int found = (rss_state >> 2) & 3;  // RSS metric latch, rss.py:71-103
           if (found) atomicOr(&c.acc[parity * ACC_N + ACC_RSS], found == 2 ? 1 : 2);
         }
@@ -1021,25 +1038,30 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       if (need_coll) broad_phase(c, parity);
     }
     group_sync(c);
-    done = finish_tick(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick, t, dt, length,
-                       live, live && present, collided, vx, vy, vz, dist);
+    done = finish_tick(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick,
+                       c.cold_d[COLD_T0 + (parity ^ 1)], c.cold_d[COLD_T0 + (parity ^ 1)] - c.cold_d[COLD_PT0 + (parity ^ 1)],
+                       c.cold_d[COLD_LEN], live, live && present, collided, vx, vy, 0.0, dist);
     parity ^= 1;
   }
 
   if (live) {
+    const int64_t i = c.i, nm = c.nm;
     st.pose[i] = x; st.pose[nm + i] = y; st.pose[3 * nm + i] = h;
-    st.vel[i] = vx; st.vel[nm + i] = vy; st.vel[3 * nm + i] = vh;
-    if (ticks_run > 0 && present) { st.vel[2 * nm + i] = 0.0; st.vel[4 * nm + i] = 0.0; st.vel[5 * nm + i] = 0.0; }
+    st.vel[i] = vx; st.vel[nm + i] = vy; st.vel[3 * nm + i] = tc[4 * G];
+    if (tick > tick0 && present) { st.vel[2 * nm + i] = 0.0; st.vel[4 * nm + i] = 0.0; st.vel[5 * nm + i] = 0.0; }
     st.dist[i] = dist;
     st.speed[i] = speed;
     st.collided[i] = collided;
     if (RSS) {
       st.rss_state[i] = rss_state; st.rss_last[i] = rss_last;
-      st.safe_dist[i] = sd[0]; st.safe_dist[nm + i] = sd[1];
-      st.safe_ratio[i] = ratio[0]; st.safe_ratio[nm + i] = ratio[1];
+      st.safe_dist[i] = tc[0]; st.safe_dist[nm + i] = tc[G];
+      st.safe_ratio[i] = tc[2 * G]; st.safe_ratio[nm + i] = tc[3 * G];
     }
   }
-  if (s == 0) { st.t[n] = t; st.prev_t[n] = prev_t; st.tick[n] = tick; st.done[n] = done; }
+  if (s == 0) {
+    st.t[n] = c.cold_d[COLD_T0 + parity]; st.prev_t[n] = c.cold_d[COLD_PT0 + parity];
+    st.tick[n] = tick; st.done[n] = done;
+  }
   store_cold(st, c, n, s, W, ego_slot);
 }
 
@@ -1271,8 +1293,9 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       if (RSS && feat_rss) {  // RSSDistances.__call__, callback.py:57-122
         rss_last = SG_RSS_NONE;
         if (t != 0.0 && s != ego_slot && e.present && c.egop[EGO_PRESENT] != 0.0) {
-          rss_last = (uint8_t)rss_hazard(KR, c, e.pose[0], e.pose[1], e.vel[0], e.vel[1], rss_state,
-                                         sd, ratio);
+          double ro[4];
+          rss_last = (uint8_t)rss_hazard(KR, c, e.pose[0], e.pose[1], e.vel[0], e.vel[1], rss_state, ro, 1);
+          sd[0] = ro[0]; sd[1] = ro[1]; ratio[0] = ro[2]; ratio[1] = ro[3];
           const int found = (rss_state >> 2) & 3;  // RSS metric latch, rss.py:71-103
           if (found) atomicOr(&c.acc[parity * ACC_N + ACC_RSS], found == 2 ? 1 : 2);
         }
@@ -1368,7 +1391,9 @@ sg_reset_kernel(SgScene sc, SgParams p, SgState st, GroupLayout L) {
     if (s == ego_slot) publish_ego(c, present, pose[0], pose[1], hc, hs, vel[0], vel[1]);
     group_sync(c);
     if (live && t != 0.0 && s != ego_slot && present && c.egop[EGO_PRESENT] != 0.0) {
-      rss_last = (uint8_t)rss_hazard(KR, c, pose[0], pose[1], vel[0], vel[1], rss_state, sd, ratio);
+      double ro[4];
+      rss_last = (uint8_t)rss_hazard(KR, c, pose[0], pose[1], vel[0], vel[1], rss_state, ro, 1);
+      sd[0] = ro[0]; sd[1] = ro[1]; ratio[0] = ro[2]; ratio[1] = ro[3];
       const int found = (rss_state >> 2) & 3;
       if (found) atomicOr(&c.acc[ACC_RSS], found == 2 ? 1 : 2);
     }
