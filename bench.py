@@ -159,7 +159,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def window(self, t0: float, t1: float) -> None:
+        """Only samples that arrived inside [t0, t1] (the timed region) are reported."""
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.proc is None:
@@ -171,7 +175,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        inside = [ln for ts, ln in self.lines if t0 <= ts <= t1 + 0.05]
+        for line in (inside or [ln for _, ln in self.lines[-3:]]):
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 7:
                 continue
@@ -350,12 +356,13 @@ def run_b200(args):
         eng.rollout(-1, actions=act_dev)
 
     # ---- device-resident timing -----------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs a few 100 ms to deliver its first sample
     for _ in range(args.warmup):
         one_step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    t_wall0 = time.time()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -368,6 +375,7 @@ def run_b200(args):
         ev[k][2].record(stream)
     stop.record(stream)
     barrier()
+    sampler.window(t_wall0, time.time())
     elapsed_ms = start.elapsed_time(stop)
     kern_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     reset_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
