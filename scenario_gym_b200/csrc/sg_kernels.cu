@@ -220,6 +220,10 @@ SG_DEV void sincos_kernel(double x, double& sn, double& cs) {
   const double hz = 0.5 * z, w = 1.0 - hz;
   cs = w + (((1.0 - w) - hz) + z * (z * q));
 }
+// library fall-backs kept out of line so the tick loop does not carry their code
+__device__ __noinline__ void sincos_lib(double x, double* sn, double* cs) { sincos(x, sn, cs); }
+__device__ __noinline__ double tan_lib(double x) { return tan(x); }
+
 // tan on |x| <= pi/4 (steering angles are clipped to +-max_steer)
 SG_DEV double tan_small(double x) {
   double sn, cs;
@@ -228,7 +232,7 @@ SG_DEV double tan_small(double x) {
 }
 // sincos with a 3-term Cody-Waite reduction (exact under FMA for |x| < 1e9)
 SG_DEV void sincos_fast(double x, double& sn, double& cs) {
-  if (!(fabs(x) < 1.0e9)) { sincos(x, &sn, &cs); return; }
+  if (!(fabs(x) < 1.0e9)) { sincos_lib(x, &sn, &cs); return; }
   const double kd = rint(x * 0.63661977236758138);
   double r = __fma_rn(-kd, 1.5707963267948966, x);
   r = __fma_rn(-kd, 6.123233995736766e-17, r);
@@ -976,7 +980,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       const double accel = clipd(ab[parity * 2 * G], -p.veh_max_accel, p.veh_max_accel);
       const double steer = clipd(ab[parity * 2 * G + G], -p.veh_max_steer, p.veh_max_steer);
       const double dx = speed * cs, dy = speed * sn;
-      const double tn = fabs(steer) <= 0.78 ? tan_small(steer) : tan(steer);
+      const double tn = fabs(steer) <= 0.78 ? tan_small(steer) : tan_lib(steer);
       const double dh = div_r(speed * tn, c.boxp[G + s], tc[5 * G]);
       const double nx = x + dx * dt, ny = y + dy * dt, nh = h + dh * dt;
       double ns = speed + accel * dt;
