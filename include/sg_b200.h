@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 5
+#define SG_ABI_VERSION 6
 
 /* entity slot kinds (who produces the slot's next pose each tick) */
 enum SgKind {
@@ -43,7 +43,8 @@ enum SgKind {
   SG_KIND_AGENT_REPLAY = 2, /* ReplayTrajectoryAgent (default ego), agent.py:118-128       */
   SG_KIND_VEHICLE = 3,      /* agent with VehicleController, controller.py:57-140          */
   SG_KIND_PEDESTRIAN = 4,   /* PedestrianAgent + SocialForce, pedestrian/                  */
-  SG_KIND_HOST = 5          /* pose supplied by a host-side (Python) agent every tick      */
+  SG_KIND_HOST = 5,         /* pose supplied by a host-side (Python) agent every tick      */
+  SG_KIND_PID = 6           /* PIDAgent + PIDController, agent.py:131-148, controller.py:143-258 */
 };
 
 /* catalog type of the entity (collision.py:85, pedestrian/sensor.py:61) */
@@ -108,6 +109,8 @@ typedef struct SgParams {
   double rss_min_long_accel;     /* 1.2*9.81                                              */
   double rss_max_long_accel;     /* 1.2*9.81                                              */
   double rss_min_safe_clearance; /* 0.1                                                   */
+  /* PIDController gains, controller.py:154-161 (vehicle limits above apply to it too) */
+  double pid_steer_Kp, pid_steer_Kd, pid_accel_Kp, pid_accel_Kd, pid_accel_Ki;
 } SgParams;
 
 /* immutable description of N scenarios x M slots */
@@ -197,6 +200,8 @@ typedef struct SgState {
   double* trace_pose;      /* [trace_cap][6][N*M] */
   uint8_t* trace_present;  /* [trace_cap][N*M] */
   double* trace_t;         /* [trace_cap][N] */
+  /* PIDController state: e_lon_prev, e_lon_int, e_lat_prev (controller.py:198-203) */
+  double* pid_err;         /* [3][N*M] */
 } SgState;
 
 /* per-call inputs */

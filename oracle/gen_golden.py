@@ -361,6 +361,37 @@ def gen_ped(store, manifest):
     manifest["ped"] = {"N": cfg.N, "M": cfg.M, "T": cfg.T, "dt": cfg.dt}
 
 
+# --------------------------------------------------------------------------- PID
+def gen_pid(store, manifest):
+    """PIDAgent / PIDController (agent.py:131-148, controller.py:143-258) on two test scenarios."""
+    from scenario_gym.agent import PIDAgent
+
+    cases = {
+        # the reference's own test, tests/test_controller.py:7-25
+        "a98d5c7d": dict(timestep=0.1, kwargs=dict(accel_Kp=2.0, max_accel=5.0, max_steer=float(np.pi / 90))),
+        "3fee6507": dict(timestep=1.0 / 30.0, kwargs={}),
+    }
+    files = sorted(glob.glob(os.path.join(SCEN_DIR, "*.xosc")))
+    for short, cfg in cases.items():
+        f = [x for x in files if short in x][0]
+        name = os.path.splitext(os.path.basename(f))[0]
+        rec = Recorder()
+        gym = ScenarioGym(timestep=cfg["timestep"],
+                          metrics=[EgoAvgSpeed(), EgoMaxSpeed(), EgoDistanceTravelled(), rec])
+
+        def create_agent(s, e, kw=cfg["kwargs"]):
+            if e.ref == "ego":
+                return PIDAgent(e, **kw)
+
+        gym.load_scenario(f, create_agent=create_agent, relabel=True)
+        out, m = run_gym(gym, rec, dec=8)
+        out["t_end"] = np.float64(gym.state.t)
+        flat(f"pid/{name}/out", out, store)
+        manifest.setdefault("pid", {})[name] = {"timestep": cfg["timestep"], "kwargs": cfg["kwargs"],
+                                                "n_ticks": int(rec.tick)}
+        print("pid", name, rec.tick, repr(float(gym.state.t)), m)
+
+
 # --------------------------------------------------------------------------- unit vectors
 def gen_unit(store, manifest):
     rng = np.random.default_rng(123)
@@ -428,34 +459,45 @@ def gen_unit(store, manifest):
 
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
-    manifest = {"reference": "driskai/scenario_gym v0.3.1", "numpy": np.__version__}
+    only = set(sys.argv[1:])  # e.g. `python -m oracle.gen_golden pid` regenerates one file only
+    mpath = os.path.join(GOLDEN, "manifest.json")
+    manifest = json.load(open(mpath)) if (only and os.path.exists(mpath)) else {}
+    manifest.update({"reference": "driskai/scenario_gym v0.3.1", "numpy": np.__version__})
     import scipy
 
     manifest["scipy"] = scipy.__version__
 
-    store = {}
-    gen_unit(store, manifest)
-    np.savez_compressed(os.path.join(GOLDEN, "unit.npz"), **store)
+    def want(name):
+        return not only or name in only
 
-    store = {}
-    gen_xosc(store, manifest)
-    np.savez_compressed(os.path.join(GOLDEN, "xosc.npz"), **store)
+    if want("unit"):
+        store = {}
+        gen_unit(store, manifest)
+        np.savez_compressed(os.path.join(GOLDEN, "unit.npz"), **store)
+    if want("xosc"):
+        store = {}
+        gen_xosc(store, manifest)
+        np.savez_compressed(os.path.join(GOLDEN, "xosc.npz"), **store)
+    if want("veh_rss"):
+        store = {}
+        cfg = golden_cases.veh_cfg()
+        gen_vehicle_like("veh", cfg, store, manifest)
+        # terminal conditions "collision" / "ego_collision" (state/state.py:399-400)
+        gen_vehicle_like("veh_term", cfg, store, manifest, terminal=["max_length", "collision"])
+        gen_vehicle_like("veh_egoterm", cfg, store, manifest, terminal=["max_length", "ego_collision"])
+        cfg = golden_cases.rss_cfg()
+        gen_vehicle_like("rss", cfg, store, manifest, rss=True)
+        np.savez_compressed(os.path.join(GOLDEN, "veh_rss.npz"), **store)
+    if want("ped"):
+        store = {}
+        gen_ped(store, manifest)
+        np.savez_compressed(os.path.join(GOLDEN, "ped.npz"), **store)
+    if want("pid"):
+        store = {}
+        gen_pid(store, manifest)
+        np.savez_compressed(os.path.join(GOLDEN, "pid.npz"), **store)
 
-    store = {}
-    cfg = golden_cases.veh_cfg()
-    gen_vehicle_like("veh", cfg, store, manifest)
-    # terminal conditions "collision" / "ego_collision" (state/state.py:399-400)
-    gen_vehicle_like("veh_term", cfg, store, manifest, terminal=["max_length", "collision"])
-    gen_vehicle_like("veh_egoterm", cfg, store, manifest, terminal=["max_length", "ego_collision"])
-    cfg = golden_cases.rss_cfg()
-    gen_vehicle_like("rss", cfg, store, manifest, rss=True)
-    np.savez_compressed(os.path.join(GOLDEN, "veh_rss.npz"), **store)
-
-    store = {}
-    gen_ped(store, manifest)
-    np.savez_compressed(os.path.join(GOLDEN, "ped.npz"), **store)
-
-    with open(os.path.join(GOLDEN, "manifest.json"), "w") as f:
+    with open(mpath, "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     for fn in sorted(os.listdir(GOLDEN)):
         print(fn, os.path.getsize(os.path.join(GOLDEN, fn)))

@@ -74,6 +74,11 @@ void sgo_default_params(SgParams* p) {
   p->rss_min_long_accel = 1.2 * 9.81;
   p->rss_max_long_accel = 1.2 * 9.81;
   p->rss_min_safe_clearance = 0.1;
+  p->pid_steer_Kp = 0.03054; /* controller.py:154-161 */
+  p->pid_steer_Kd = 1.5709;
+  p->pid_accel_Kp = 0.3753;
+  p->pid_accel_Kd = 1.8970;
+  p->pid_accel_Ki = 0.0204;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -574,7 +579,8 @@ int sgo_reset(const SgScene* sc, const SgParams* p, SgState* st, int device, voi
       }
       st->dist[i] = 0.0;
       /* VehicleController._reset controller.py:100-103 ; PedestrianController._reset :23 */
-      st->speed[i] = (kind == SG_KIND_VEHICLE) ? norm2(vel[0], vel[1]) : 0.0;
+      st->speed[i] = (kind == SG_KIND_VEHICLE || kind == SG_KIND_PID) ? norm2(vel[0], vel[1]) : 0.0;
+      for (int f = 0; f < 3; ++f) st->pid_err[f * nm + i] = 0.0; /* controller.py:198-203 */
       st->goal_idx[i] = 0;
       st->force[i] = 0.0;
       st->force[nm + i] = 0.0;
@@ -765,15 +771,42 @@ static void tick_scenario(const SgScene* sc, const SgParams* p, SgState* st, con
         if (kind == SG_KIND_AGENT_REPLAY) { /* agent.py:125-128, default extrapolate=(False, False) */
           position_at_t(rows, K, next_t, EXT_CLAMP, np_);
           newpres[s] = 1;
-        } else if (kind == SG_KIND_VEHICLE) { /* controller.py:105-140 */
-          double accel = in->actions[((int64_t)k_action * 2 + 0) * nm + i];
-          double steer = in->actions[((int64_t)k_action * 2 + 1) * nm + i];
-          accel = np_clip(accel, -p->veh_max_accel, p->veh_max_accel);
-          steer = np_clip(steer, -p->veh_max_steer, p->veh_max_steer);
+        } else if (kind == SG_KIND_VEHICLE || kind == SG_KIND_PID) {
+          double accel, steer;
           double pose[6];
           for (int f = 0; f < 6; ++f) pose[f] = st->pose[f * nm + i];
-          double dt = next_t - t;
           double h = pose[3], spd = st->speed[i], l = sc->box[nm + i];
+          if (kind == SG_KIND_PID) {
+            /* PIDAgent._step agent.py:144-148 + PIDController._step controller.py:205-258 */
+            double tgt[6];
+            position_at_t(rows, K, next_t, EXT_CLAMP, tgt);
+            double e0 = tgt[0] - pose[0], e1 = tgt[1] - pose[1];
+            double ch = cos(h), sh = sin(h);
+            double e_lon = ch * e0 + sh * e1, e_lat = -sh * e0 + ch * e1;
+            double gain_adj;
+            if (spd > 5.0 && spd <= 15) gain_adj = 1.0 - 0.9 * ((spd - 5.0)) / 10.0;
+            else if (spd > 15) gain_adj = 0.1;
+            else gain_adj = 1.0;
+            double sdt = st->t[n] - st->prev_t[n]; /* state.dt */
+            double e_lat_D = (e_lat - st->pid_err[2 * nm + i]) / sdt;
+            steer = (p->pid_steer_Kp * gain_adj) * e_lat + (p->pid_steer_Kd * gain_adj) * e_lat_D;
+            double e_lon_D = (e_lon - st->pid_err[i]) / sdt;
+            double e_lon_I = st->pid_err[nm + i] + e_lon * sdt;
+            if (fabs(e_lon) > 0.1)
+              accel = p->pid_accel_Kp * e_lon + p->pid_accel_Kd * e_lon_D + p->pid_accel_Ki * e_lon_I;
+            else
+              accel = 0.0;
+            st->pid_err[2 * nm + i] = e_lat;
+            st->pid_err[i] = e_lon;
+            st->pid_err[nm + i] = e_lon_I;
+          } else {
+            accel = in->actions[((int64_t)k_action * 2 + 0) * nm + i];
+            steer = in->actions[((int64_t)k_action * 2 + 1) * nm + i];
+          }
+          /* VehicleController._step controller.py:105-140 */
+          accel = np_clip(accel, -p->veh_max_accel, p->veh_max_accel);
+          steer = np_clip(steer, -p->veh_max_steer, p->veh_max_steer);
+          double dt = next_t - t;
           double dx = spd * cos(h), dy = spd * sin(h), dh = spd * tan(steer) / l;
           pose[0] += dx * dt;
           pose[1] += dy * dt;

@@ -10,7 +10,7 @@ from .entity import BoundingBox, CatalogEntry, Entity, MiscObject, Pedestrian, V
 from .gym import ScenarioGym
 from .plugins import (RSS, Action, ActionTableAgent, Agent, CollisionMetric, Controller,
                       EgoAvgSpeed, EgoDistanceTravelled, EgoLocalizationSensor, EgoMaxSpeed, Metric,
-                      Observation, PedestrianAction, PedestrianAgent, ReplayTrajectoryAgent,
+                      Observation, PedestrianAction, PedestrianAgent, PIDAgent, PIDController, ReplayTrajectoryAgent,
                       ReplayTrajectoryController, RSSDistances, RSSParameters, Sensor,
                       SingleEntityObservation, SocialForce, SocialForceParameters, StateCallback,
                       TeleportAction, VehicleAction, VehicleController)

@@ -11,10 +11,10 @@ import math
 import os
 from typing import Dict, Optional
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # SgKind
-KIND_EMPTY, KIND_REPLAY, KIND_AGENT_REPLAY, KIND_VEHICLE, KIND_PEDESTRIAN, KIND_HOST = range(6)
+KIND_EMPTY, KIND_REPLAY, KIND_AGENT_REPLAY, KIND_VEHICLE, KIND_PEDESTRIAN, KIND_HOST, KIND_PID = range(7)
 # SgEntityType
 ETYPE_VEHICLE, ETYPE_PEDESTRIAN, ETYPE_MISC = range(3)
 # SgTerminal
@@ -66,6 +66,11 @@ class SgParams(C.Structure):
         ("rss_min_long_accel", C.c_double),
         ("rss_max_long_accel", C.c_double),
         ("rss_min_safe_clearance", C.c_double),
+        ("pid_steer_Kp", C.c_double),
+        ("pid_steer_Kd", C.c_double),
+        ("pid_accel_Kp", C.c_double),
+        ("pid_accel_Kd", C.c_double),
+        ("pid_accel_Ki", C.c_double),
     ]
 
 
@@ -143,6 +148,7 @@ class SgState(C.Structure):
         ("trace_pose", _p),
         ("trace_present", _p),
         ("trace_t", _p),
+        ("pid_err", _p),
     ]
 
 
@@ -206,6 +212,7 @@ STATE_FIELDS = [
     ("trace_pose", "float64", ("T", "6", "NM")),
     ("trace_present", "uint8", ("T", "NM")),
     ("trace_t", "float64", ("T", "N")),
+    ("pid_err", "float64", ("3", "NM")),
 ]
 
 SCENE_FIELDS = [
@@ -243,6 +250,8 @@ def default_params() -> SgParams:
     p.rss_min_long_accel = 1.2 * 9.81
     p.rss_max_long_accel = 1.2 * 9.81
     p.rss_min_safe_clearance = 0.1
+    p.pid_steer_Kp, p.pid_steer_Kd = 0.03054, 1.5709
+    p.pid_accel_Kp, p.pid_accel_Kd, p.pid_accel_Ki = 0.3753, 1.8970, 0.0204
     return p
 
 

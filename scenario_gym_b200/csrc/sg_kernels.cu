@@ -1099,7 +1099,7 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
                          (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
   const bool feat_rss = RSS && (p.features & SG_FEAT_RSS);
   const bool matrix = (p.features & SG_FEAT_COLL_MATRIX) != 0;
-  const bool exact_div = kind <= SG_KIND_AGENT_REPLAY;  // replay kinds keep IEEE quotients
+  const bool exact_div = kind <= SG_KIND_AGENT_REPLAY || kind == SG_KIND_PID;  // IEEE quotients
   const RssConst KR = make_rss_const(p);
 
   double bl = 1;
@@ -1179,14 +1179,40 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
         if (kind == SG_KIND_AGENT_REPLAY) {  // agent.py:125-128, extrapolate=(False, False)
           position_at_t(rows, K, next_t, EXT_CLAMP, cur_own, np_);
           newpres = true;
-        } else if (kind == SG_KIND_VEHICLE) {  // VehicleController._step, controller.py:105-140
-          const double accel = np_clip(__ldcs(in.actions + ((int64_t)k * 2 + 0) * nm + i),
-                                       -p.veh_max_accel, p.veh_max_accel);
-          const double steer = np_clip(__ldcs(in.actions + ((int64_t)k * 2 + 1) * nm + i),
-                                       -p.veh_max_steer, p.veh_max_steer);
-          const double dt = next_t - t;
+        } else if (kind == SG_KIND_VEHICLE || kind == SG_KIND_PID) {
+          double accel, steer;
           double sh, ch;
           sincos(e.pose[3], &sh, &ch);
+          if (kind == SG_KIND_PID) {
+            // PIDAgent._step (agent.py:144-148) + PIDController._step (controller.py:205-258);
+            // the three error terms stay in global memory (rare kind)
+            double tgt[6];
+            position_at_t(rows, K, next_t, EXT_CLAMP, cur_own, tgt);
+            const double e0 = tgt[0] - e.pose[0], e1 = tgt[1] - e.pose[1];
+            const double e_lon = ch * e0 + sh * e1, e_lat = -sh * e0 + ch * e1;
+            double gain_adj;
+            if (e.speed > 5.0 && e.speed <= 15) gain_adj = 1.0 - 0.9 * ((e.speed - 5.0)) / 10.0;
+            else if (e.speed > 15) gain_adj = 0.1;
+            else gain_adj = 1.0;
+            const double sdt = t - prev_t;  // state.dt
+            const double e_lat_D = (e_lat - st.pid_err[2 * nm + i]) / sdt;
+            steer = (p.pid_steer_Kp * gain_adj) * e_lat + (p.pid_steer_Kd * gain_adj) * e_lat_D;
+            const double e_lon_D = (e_lon - st.pid_err[i]) / sdt;
+            const double e_lon_I = st.pid_err[nm + i] + e_lon * sdt;
+            accel = fabs(e_lon) > 0.1
+                        ? p.pid_accel_Kp * e_lon + p.pid_accel_Kd * e_lon_D + p.pid_accel_Ki * e_lon_I
+                        : 0.0;
+            st.pid_err[2 * nm + i] = e_lat;
+            st.pid_err[i] = e_lon;
+            st.pid_err[nm + i] = e_lon_I;
+          } else {
+            accel = __ldcs(in.actions + ((int64_t)k * 2 + 0) * nm + i);
+            steer = __ldcs(in.actions + ((int64_t)k * 2 + 1) * nm + i);
+          }
+          // VehicleController._step, controller.py:105-140
+          accel = np_clip(accel, -p.veh_max_accel, p.veh_max_accel);
+          steer = np_clip(steer, -p.veh_max_steer, p.veh_max_steer);
+          const double dt = next_t - t;
           const double dx = e.speed * ch, dy = e.speed * sh;
           const double dh = div_r(e.speed * tan(steer), bl, rcp_bl);
 #pragma unroll
@@ -1373,7 +1399,7 @@ sg_reset_kernel(SgScene sc, SgParams p, SgState st, GroupLayout L) {
 #pragma unroll
       for (int f = 0; f < 6; ++f) pose[f] = 0.0;
     }
-    if (kind == SG_KIND_VEHICLE) speed = norm2(vel[0], vel[1]);  // controller.py:100-103
+    if (kind == SG_KIND_VEHICLE || kind == SG_KIND_PID) speed = norm2(vel[0], vel[1]);  // controller.py:100-103
   }
   uint8_t rss_state = 0, rss_last = SG_RSS_NONE;
   double sd[2] = {0.0, 0.0}, ratio[2] = {INFINITY, INFINITY};  // callback.py:51-55
@@ -1414,6 +1440,7 @@ sg_reset_kernel(SgScene sc, SgParams p, SgState st, GroupLayout L) {
     st.collided[i] = 0;
     st.goal_idx[i] = 0;
     st.force[i] = 0.0; st.force[nm + i] = 0.0;
+    st.pid_err[i] = 0.0; st.pid_err[nm + i] = 0.0; st.pid_err[2 * nm + i] = 0.0;  // controller.py:198-203
     st.rss_state[i] = rss_state; st.rss_last[i] = rss_last;
     st.safe_dist[i] = sd[0]; st.safe_dist[nm + i] = sd[1];
     st.safe_ratio[i] = ratio[0]; st.safe_ratio[nm + i] = ratio[1];
@@ -1597,6 +1624,11 @@ void sg_default_params(SgParams* p) {
   p->rss_min_long_accel = 1.2 * 9.81;
   p->rss_max_long_accel = 1.2 * 9.81;
   p->rss_min_safe_clearance = 0.1;
+  p->pid_steer_Kp = 0.03054;
+  p->pid_steer_Kd = 1.5709;
+  p->pid_accel_Kp = 0.3753;
+  p->pid_accel_Kd = 1.8970;
+  p->pid_accel_Ki = 0.0204;
 }
 
 int sg_reset(const SgScene* scene, const SgParams* params, SgState* state, int device, void* stream) {

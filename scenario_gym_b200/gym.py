@@ -27,7 +27,7 @@ from . import abi
 from .entity import Entity
 from .packing import ScenarioSpec, SlotSpec, pack_scenarios
 from .plugins import (ActionTableAgent, Agent, CollisionMetric, EgoLocalizationSensor, Metric,
-                      PedestrianAgent, ReplayTrajectoryAgent, ReplayTrajectoryController, RSSDistances,
+                      PedestrianAgent, PIDAgent, PIDController, ReplayTrajectoryAgent, ReplayTrajectoryController, RSSDistances,
                       SocialForce, StateCallback, VehicleAction, VehicleController, _create_agent,
                       _DeviceMetric)
 from .scenario import Scenario
@@ -242,7 +242,7 @@ class ScenarioGym:
 
         specs, self._slot_of, self._entity_of = [], [], []
         self._agent_kind: Dict[Agent, str] = {}
-        veh_params, ped_params = set(), set()
+        veh_params, ped_params, pid_params = set(), set(), set()
         tables = {}
         for n, st in enumerate(self.states):
             sc = st.scenario
@@ -266,6 +266,12 @@ class ScenarioGym:
                                     pr.max_speed_factor, pr.bias_lon, pr.bias_lat, pr.sight_weight,
                                     bool(pr.sight_weight_use), pr.sight_angle, pr.relaxation_time,
                                     pr.ped_repulse_V, pr.ped_repulse_sigma, pr.ped_attract_C))
+                elif type(agent) is PIDAgent and type(agent.controller) is PIDController \
+                        and agent._trajectory is None:
+                    kind, self._agent_kind[agent] = abi.KIND_PID, "device"
+                    c = agent.controller
+                    veh_params.add((c.max_steer, c.max_accel, c.max_speed, bool(c.allow_reverse)))
+                    pid_params.add((c.steer_Kp, c.steer_Kd, c.accel_Kp, c.accel_Kd, c.accel_Ki))
                 elif type(agent.controller) is VehicleController:
                     kind = abi.KIND_VEHICLE
                     c = agent.controller
@@ -283,7 +289,7 @@ class ScenarioGym:
                                       t0=self.get_start_time(sc), length=sc.length, name=sc.name or ""))
             self._slot_of.append({e: s for s, e in enumerate(ents)})
             self._entity_of.append(ents)
-        if len(veh_params) > 1 or len(ped_params) > 1:
+        if len(veh_params) > 1 or len(ped_params) > 1 or len(pid_params) > 1:
             raise NotImplementedError("controller / behaviour parameters must be equal across agents")
         self._veh_params = next(iter(veh_params)) if veh_params else None
         self._ped_params = next(iter(ped_params)) if ped_params else None
@@ -333,6 +339,8 @@ class ScenarioGym:
             p.veh_max_steer, p.veh_max_accel = self._veh_params[0], self._veh_params[1]
             p.veh_max_speed = float("nan") if self._veh_params[2] is None else self._veh_params[2]
             p.veh_allow_reverse = int(self._veh_params[3])
+        if pid_params:
+            (p.pid_steer_Kp, p.pid_steer_Kd, p.pid_accel_Kp, p.pid_accel_Kd, p.pid_accel_Ki) = next(iter(pid_params))
         if self._ped_params:
             (p.ped_max_speed, p.ped_head_rot_angle, p.ped_distance_threshold, p.sf_max_speed_factor,
              p.sf_bias_lon, p.sf_bias_lat, p.sf_sight_weight, suse, p.sf_sight_angle,

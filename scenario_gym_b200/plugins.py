@@ -175,6 +175,20 @@ class VehicleController(Controller):
         return pose
 
 
+class PIDController(VehicleController):
+    """
+    PID steering / acceleration towards a target point (reference controller.py:143-258); runs
+    on the device for ``PIDAgent``.  Keyword arguments go to the underlying vehicle model.
+    """
+
+    def __init__(self, entity: Entity, steer_Kp: float = 0.03054, steer_Kd: float = 1.5709,
+                 accel_Kp: float = 0.3753, accel_Kd: float = 1.8970, accel_Ki: float = 0.0204,
+                 **kwargs):
+        super().__init__(entity, **kwargs)
+        self.steer_Kp, self.steer_Kd = steer_Kp, steer_Kd
+        self.accel_Kp, self.accel_Ki, self.accel_Kd = accel_Kp, accel_Ki, accel_Kd
+
+
 # ------------------------------------------------------------------------------ agents
 class Agent:
     """Processes observations to select an action (reference agent.py:18-115)."""
@@ -232,6 +246,17 @@ class ReplayTrajectoryAgent(Agent):
 
     def _step(self, observation) -> Action:
         return TeleportAction(pose=self.trajectory.position_at_t(observation.next_t))
+
+
+class PIDAgent(Agent):
+    """Follows its trajectory with a PID controller (reference agent.py:131-148)."""
+
+    def __init__(self, entity: Entity, **controller_kwargs):
+        super().__init__(entity, PIDController(entity, **controller_kwargs), EgoLocalizationSensor(entity))
+
+    def _step(self, observation) -> TeleportAction:
+        pos = self.trajectory.position_at_t(observation.next_t)
+        return TeleportAction(x=pos[0], y=pos[1], z=pos[2])
 
 
 class ActionTableAgent(Agent):

@@ -32,7 +32,8 @@ def sub(d: Dict[str, np.ndarray], prefix: str) -> Dict[str, np.ndarray]:
     return {k[len(prefix):]: v for k, v in d.items() if k.startswith(prefix)}
 
 
-def xosc_spec(inp: Dict[str, np.ndarray]) -> Tuple[ScenarioSpec, List[int]]:
+def xosc_spec(inp: Dict[str, np.ndarray], agent_kind: int = abi.KIND_AGENT_REPLAY
+              ) -> Tuple[ScenarioSpec, List[int]]:
     """ScenarioSpec from golden scenario inputs; returns slot -> entity index map."""
     n = int(inp["n_entities"])
     is_agent = inp["is_agent"].astype(bool)
@@ -41,7 +42,7 @@ def xosc_spec(inp: Dict[str, np.ndarray]) -> Tuple[ScenarioSpec, List[int]]:
     for i in order:
         slots.append(
             SlotSpec(
-                kind=abi.KIND_AGENT_REPLAY if is_agent[i] else abi.KIND_REPLAY,
+                kind=agent_kind if is_agent[i] else abi.KIND_REPLAY,
                 traj=inp[f"traj{i}"],
                 box=tuple(inp["box"][i]),
                 etype=int(inp["etype"][i]),

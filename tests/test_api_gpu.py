@@ -316,3 +316,26 @@ def test_social_force_pedestrians():
     assert close(final, out["pose"][-1])
     with pytest.raises(ValueError):
         SocialForce(SocialForceParameters())  # default noise std > 0 is stochastic in the reference
+
+
+def test_pid_agent():
+    """reference tests/test_controller.py:7-25 (same scenario and gains), against its golden record."""
+    from scenario_gym_b200 import PIDAgent
+
+    gp, man = golden("pid"), manifest()["pid"]
+    scs = {name: sc for name, sc, _ in golden_scenarios()}
+    for name, info in sorted(man.items()):
+        out = sub(gp, f"pid/{name}/out")
+        gym = ScenarioGym(timestep=info["timestep"], metrics=std_metrics())
+
+        def create_agent(s, e, kw=info["kwargs"]):
+            if e.ref == "ego":
+                return PIDAgent(e, **kw)
+
+        gym.set_scenario(scs[name], create_agent=create_agent)
+        gym.rollout()
+        m = gym.get_metrics()
+        assert gym.state.t == float(out["t_end"])
+        assert close(m["ego_avg_speed"], out["ego_avg_speed"])
+        assert close(m["ego_max_speed"], out["ego_max_speed"])
+        assert close(m["ego_distance_travelled"], out["ego_distance_travelled"])

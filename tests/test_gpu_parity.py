@@ -151,6 +151,13 @@ def test_social_force_golden():
         check_against_golden(make_gpu, scene, p, sub(g, f"ped/{n}/out"), n, list(range(M)))
 
 
+def test_pid_golden():
+    from test_oracle_golden import pid_cases
+
+    for name, spec, order, p, out in pid_cases():
+        check_against_golden(make_gpu, pack_scenarios([spec]), p, out, 0, order)
+
+
 def test_box_pairs_golden():
     """Exact closed-set box intersection incl. touching and identical boxes (unit vectors)."""
     import torch

@@ -108,6 +108,26 @@ def test_social_force():
             np.testing.assert_allclose(eng.get("force")[:, sl].T, out["force"][k], rtol=1e-9, atol=1e-9)
 
 
+def pid_cases():
+    from helpers import xosc_spec
+
+    g, gp, man = golden("xosc"), golden("pid"), manifest()["pid"]
+    for name, info in sorted(man.items()):
+        spec, order = xosc_spec(sub(g, f"xosc/{name}/in"), agent_kind=abi.KIND_PID)
+        p = _params(timestep=info["timestep"])
+        kw = info["kwargs"]
+        p.pid_accel_Kp = kw.get("accel_Kp", p.pid_accel_Kp)
+        p.veh_max_accel = kw.get("max_accel", p.veh_max_accel)
+        p.veh_max_steer = kw.get("max_steer", p.veh_max_steer)
+        yield name, spec, order, p, sub(gp, f"pid/{name}/out")
+
+
+def test_pid_controller():
+    """Section 8f item 1: PIDAgent + PIDController (reference tests/test_controller.py:7-25)."""
+    for name, spec, order, p, out in pid_cases():
+        check_against_golden(make_oracle, pack_scenarios([spec]), p, out, 0, order)
+
+
 def test_unit_vectors(oracle_lib):
     """Trajectory.position_at_t / velocity_at_t, box corners, box-pair intersects."""
     import ctypes as C
