@@ -51,10 +51,14 @@ class ScenarioGym:
     def __init__(self, timestep: float = 1.0 / 30.0, persist: bool = False, viewer_class=None,
                  terminal_conditions: Optional[List[Union[str, Callable]]] = None,
                  state_callbacks: Optional[List[StateCallback]] = None,
-                 metrics: Optional[List[Metric]] = None, device: int = 0, **viewer_parameters):
+                 metrics: Optional[List[Metric]] = None, device: int = 0, record: bool = False,
+                 **viewer_parameters):
         self.timestep = timestep
         self.persist = persist
         self.device = device
+        # record=True keeps a device-side trace of every tick's poses so that
+        # state.recorded_poses() / state.to_scenario() also work after a fused rollout
+        self.record = record
         self.viewer_parameters = viewer_parameters.copy()
         self.terminal_conditions = ["max_length"] if terminal_conditions is None else terminal_conditions
         self.state_callbacks = [] if state_callbacks is None else state_callbacks
@@ -347,7 +351,11 @@ class ScenarioGym:
              p.sf_relaxation_time, p.sf_ped_repulse_V, p.sf_ped_repulse_sigma, p.sf_ped_attract_C) = self._ped_params
             p.sf_sight_weight_use = int(suse)
         self._params = p
-        self._engine = Engine(scene, p, device=self.device)
+        trace_cap = 0
+        if self.record and not self._host_mode:
+            ts = float(self.timestep)
+            trace_cap = int(max((sp.length - sp.t0) / ts for sp in specs)) + 8
+        self._engine = Engine(scene, p, device=self.device, trace_cap=trace_cap)
 
         # resident action table of ActionTableAgents
         self._action_table = self._action_table_host = None
@@ -417,6 +425,25 @@ class ScenarioGym:
         cb.entity_safe_ratios = {e: [float(ratio[0, s]), float(ratio[1, s])] for s, e in enumerate(ents)}
         cb.intersect = {e: [abi.RSS_RECORD_NAMES[int(rec[s])]] for s, e in enumerate(ents)
                         if rec[s] != abi.RSS_NONE}
+
+    def _device_trace(self, n: int):
+        """Recorded (t, pose) rows per entity from the device trace of a fused rollout."""
+        eng = self._engine
+        if eng.trace_cap <= 0:
+            return None
+        M = eng.M
+        T = int(eng.tensor("tick")[n].item()) + 1
+        if T > eng.trace_cap:
+            raise RuntimeError("trace buffer too short (timestep changed after set_scenario?)")
+        sl = slice(n * M, (n + 1) * M)
+        pose = eng.tensor("trace_pose")[:T, :, sl].cpu().numpy()
+        present = eng.tensor("trace_present")[:T, sl].cpu().numpy().astype(bool)
+        ts = eng.tensor("trace_t")[:T, n].cpu().numpy()
+        out = {}
+        for s, e in enumerate(self._entity_of[n]):
+            k = np.nonzero(present[:, s])[0]
+            out[e] = np.concatenate([ts[k, None], pose[k, :, s]], axis=1) if len(k) else np.empty((0, 7))
+        return out
 
     def _collisions(self, n: int) -> Dict[Entity, List[Entity]]:
         eng = self._engine

@@ -99,9 +99,31 @@ class State:
             ts, poses = map(np.array, zip(*rows))
             return np.concatenate([ts[:, None], poses], axis=1)
 
+        dev = self._gym._device_trace(self._n)
+        if dev is not None:  # fused rollout with ScenarioGym(record=True)
+            return dev[entity] if entity is not None else dev
         if entity is not None:
             return table(self._recorded.get(entity))
         return {e: table(r) for e, r in self._recorded.items()}
+
+    def to_scenario(self, name: Optional[str] = None):
+        """Scenario built from the recorded poses (reference state/state.py:374-394)."""
+        from copy import deepcopy
+
+        from .scenario import Scenario
+        from .trajectory import Trajectory, is_stationary
+
+        if name is None:
+            name = f"Simulation of {self.scenario.name}" if self.scenario.name is None else None
+        entities = []
+        for entity, poses in self.recorded_poses().items():
+            new_entity = deepcopy(entity)
+            if is_stationary(poses):
+                poses = poses[None, 0]
+            new_entity.trajectory = Trajectory(poses)
+            entities.append(new_entity)
+        return Scenario(entities, name=name, road_network=self.scenario.road_network,
+                        actions=self.scenario.actions)
 
     def get_entity_data(self, entity: Entity):
         return (self.t, self.next_t, self.poses.get(entity), self.velocities.get(entity),

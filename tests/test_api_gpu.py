@@ -339,3 +339,44 @@ def test_pid_agent():
         assert close(m["ego_avg_speed"], out["ego_avg_speed"])
         assert close(m["ego_max_speed"], out["ego_max_speed"])
         assert close(m["ego_distance_travelled"], out["ego_distance_travelled"])
+
+
+def test_recorded_poses_and_to_scenario():
+    """reference tests/test_state.py:210-258: to_scenario round trip of a rollout, here from the
+    device trace of a fused rollout, and identical to the host-side record of a stepped rollout."""
+    sc = import_scenario(os.path.join(DATA, "Scenarios", "demo.xosc"))
+    gym = ScenarioGym(timestep=0.1, record=True, metrics=[EgoAvgSpeed()])
+    gym.set_scenario(sc)
+    gym.rollout()
+    rec = gym.state.recorded_poses()
+    assert set(rec) == set(sc.entities)
+    ego = rec[sc.ego]
+    assert ego.shape[1] == 7 and ego[0, 0] == 0.0 and np.isclose(ego[-1, 0], gym.state.t)
+    assert np.array_equal(ego[-1, 1:], gym.state.poses[sc.ego])
+
+    class Count(Metric):  # any host-side metric forces the stepped path
+        def _reset(self, state):
+            self.n = 0
+
+        def _step(self, state):
+            self.n += 1
+
+        def get_state(self):
+            return self.n
+
+    gym2 = ScenarioGym(timestep=0.1, metrics=[Count()])
+    gym2.set_scenario(sc)
+    gym2.rollout()
+    rec2 = gym2.state.recorded_poses()
+    for e in sc.entities:
+        assert np.array_equal(rec[e], rec2[e]), e.ref
+    assert gym2.get_metrics()["Count"] == len(ego) - 1
+
+    new = gym.state.to_scenario()
+    assert len(new.entities) == len(sc.entities)
+    parked = [e for e in new.entities if e.ref == "vehicle_1"][0]
+    # (a replayed static entity carries the interpolation's rounding noise, as in the reference)
+    assert np.ptp(parked.trajectory.data[:, 1:], axis=0).max() < 1e-12
+    # replaying the recorded scenario reproduces the ego's path at the recorded times
+    t_mid = ego[len(ego) // 2, 0]
+    assert np.allclose(new.ego.trajectory.position_at_t(t_mid), ego[len(ego) // 2, 1:])
