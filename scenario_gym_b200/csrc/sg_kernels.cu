@@ -121,9 +121,8 @@ struct Grp {
   int8_t* orient;
 };
 
-SG_DEV void cp_async8(void* smem_dst, const void* gsrc) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a), "l"(gsrc) : "memory");
+SG_DEV void cp_async8(unsigned smem_addr, const void* gsrc) {  // smem_addr: shared-window address
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gsrc) : "memory");
 }
 SG_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 SG_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -162,6 +161,17 @@ SG_DEV void setup_group(Grp& g, const SgScene& sc, const GroupLayout& L, unsigne
   g.acc = (int*)(base + L.off_acc);
   g.flags = (uint8_t*)(base + L.off_flags);
   g.orient = (int8_t*)(base + L.off_orient);
+}
+
+// 1/d for a finite, normal, non-zero d: hardware seed (rcp.approx.ftz.f64, ~2^-23) refined by
+// two Newton steps to within an ulp; no special-case paths, ~6 instructions instead of ~25
+SG_DEV double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = __fma_rn(-d, r, 1.0);
+  r = __fma_rn(r, e, r);
+  e = __fma_rn(-d, r, 1.0);
+  return __fma_rn(r, e, r);
 }
 
 // n / d with a shared reciprocal r = 1/d (correctly rounded): one Newton correction on the
@@ -228,7 +238,7 @@ __device__ __noinline__ double tan_lib(double x) { return tan(x); }
 SG_DEV double tan_small(double x) {
   double sn, cs;
   sincos_kernel(x, sn, cs);
-  return sn / cs;
+  return div_r(sn, cs, fast_rcp(cs));
 }
 // sincos with a 3-term Cody-Waite reduction (exact under FMA for |x| < 1e9)
 SG_DEV void sincos_fast(double x, double& sn, double& cs) {
@@ -464,7 +474,7 @@ SG_DEV void publish_ego(const Grp& c, bool present, double x, double y, double e
                         double vx, double vy) {
   double einv[2];
   {  // inverse_direction((cos h, sin h)), rss_utils.py:7-21
-    const double nn = norm2(es, ec), rn = 1.0 / nn;
+    const double nn = norm2(es, ec), rn = fast_rcp(nn);
     einv[0] = div_r(es, nn, rn);
     einv[1] = div_r(-ec, nn, rn);
   }
@@ -476,7 +486,7 @@ SG_DEV void publish_ego(const Grp& c, bool present, double x, double y, double e
   E[EGO_HD0] = hd[0]; E[EGO_HD1] = hd[1];
   double hinv[2];  // inverse_direction(ego-frame heading): used by safe_lateral_distance
   {
-    const double nn = norm2(hd[1], hd[0]), rn = 1.0 / nn;
+    const double nn = norm2(hd[1], hd[0]), rn = fast_rcp(nn);
     hinv[0] = div_r(hd[1], nn, rn);
     hinv[1] = div_r(-hd[0], nn, rn);
   }
@@ -582,7 +592,7 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
       if (0.0 > pos1) { vf = E[EGO_VNORM]; vr = hv; } else { vf = hv; vr = E[EGO_VNORM]; }
       early = vr == 0.0;
       if (!early) {  // long_dist_same_direction, callback.py:454-472
-        const double vf2a = vf * vf / (2 * a);
+        const double vf2a = div_r(vf * vf, 2 * a, fast_rcp(2 * a));
         const double u = vr + K.RT * a;
         dd = py_max(0, vr * K.RT + py_min(vf2a, 0.5 * a * (K.RT * K.RT)) +
                            div_r(u * u, 2 * K.MINA, K.r2mina) - vf2a);
@@ -609,7 +619,7 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
       const double v = fabs(v0);
       early = v == 0.0;
       if (!early) {  // lat_dist, callback.py:494-505
-        const double den = 2 * amin, rden = 1.0 / den;
+        const double den = 2 * amin, rden = fast_rcp(den);
         const double u = v + K.RT * amax, w = K.RT * amax;
         dd = py_max(0, 0.5 * K.RT * (2 * v + K.RT * amax) + div_r(u * u, den, rden) -
                            0.5 * (K.RT * K.RT) * amax - div_r(w * w, den, rden));
@@ -621,7 +631,7 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
   out[ost] = slong;
   // safe_ratios (callback.py:124-166)
   {
-    const double hn = norm2(hd1, hd0), rhn = 1.0 / hn;  // inverse_direction(haz heading)
+    const double hn = norm2(hd1, hd0), rhn = fast_rcp(hn);  // inverse_direction(haz heading)
     const double inv0 = div_r(hd1, hn, rhn), inv1 = div_r(-hd0, hn, rhn);
     const double wl_inv = fabs(dot2(bw, bl, inv0, inv1));
     const double wl_dir = fabs(dot2(bw, bl, hd0, hd1));
@@ -967,7 +977,8 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   // VehicleAction rows are staged one tick ahead with cp.async (no registers held)
   const double* act = in.actions + c.i;
   double* ab = c.actbuf + s;
-  if (live && limit > 0 && (!done || in.step_done)) { cp_async8(ab, act); cp_async8(ab + G, act + c.nm); }
+  const unsigned ab_sh = (unsigned)__cvta_generic_to_shared(ab);  // converted once, not per tick
+  if (live && limit > 0 && (!done || in.step_done)) { cp_async8(ab_sh, act); cp_async8(ab_sh + G * 8, act + c.nm); }
   cp_async_commit();
 
   for (int k = 0; k < limit && (!done || in.step_done); ++k) {
@@ -988,7 +999,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       if (p.veh_max_speed == p.veh_max_speed) ns = ns > p.veh_max_speed ? p.veh_max_speed : ns;
       speed = ns;
       // State.update_statistics (state.py:230-239)
-      const double rdt = 1.0 / dt;
+      const double rdt = fast_rcp(dt);
       const double ex = nx - x, ey = ny - y;
       vx = div_r(ex, dt, rdt); vy = div_r(ey, dt, rdt);
       tc[4 * G] = div_r(nh - h, dt, rdt);
@@ -998,8 +1009,8 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     }
     if (live && k + 1 < limit) {
       act += 2 * c.nm;
-      cp_async8(ab + (parity ^ 1) * 2 * G, act);
-      cp_async8(ab + (parity ^ 1) * 2 * G + G, act + c.nm);
+      cp_async8(ab_sh + (parity ^ 1) * 2 * G * 8, act);
+      cp_async8(ab_sh + ((parity ^ 1) * 2 * G + G) * 8, act + c.nm);
     }
     cp_async_commit();
     tick += 1;
