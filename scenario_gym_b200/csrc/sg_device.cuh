@@ -150,57 +150,82 @@ SG_DEV int orient_sign(double ax, double ay, double bx, double by, double cx, do
   return orient_exact(ax, ay, bx, by, cx, cy);
 }
 
-// The quad routines read corner k of a quad at q[2k*st] (x) and q[(2k+1)*st] (y): st = 1 for a
-// local array, st = G for the group's staged corners in shared memory.  They are out of line
-// with rolled loops on purpose: they run on the rare path (AABB survivors, RSS boundary cases)
-// with few active lanes, and keeping a single copy of the orientation predicate keeps the tick
-// loop's instruction footprint small.
+// The exact quad predicates run on the rare path (AABB survivors, RSS boundary cases) with few
+// active lanes.  They are out of line, keep the quad in registers (loaded once with ld.shared
+// from the group's staged corners) and walk the edges by rotating the corner registers, so the
+// orientation predicate is instantiated only four times per routine.
+struct Quad {
+  double x0, y0, x1, y1, x2, y2, x3, y3;
+};
+SG_DEV void rotate(Quad& q) {  // corner k <- corner k+1
+  const double tx = q.x0, ty = q.y0;
+  q.x0 = q.x1; q.y0 = q.y1; q.x1 = q.x2; q.y1 = q.y2; q.x2 = q.x3; q.y2 = q.y3; q.x3 = tx; q.y3 = ty;
+}
+// Only used inside out-of-line helpers that do not store to shared memory themselves (the call is
+// the ordering point), so the loads may be scheduled freely: not volatile.
+SG_DEV double lds_f64(unsigned addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+// corner k of a staged quad sits at shared address base + (2k)*stride (x) and base + (2k+1)*stride (y)
+SG_DEV Quad load_quad_shared(unsigned base, unsigned stride) {
+  Quad q;
+  q.x0 = lds_f64(base); q.y0 = lds_f64(base + stride);
+  q.x1 = lds_f64(base + 2 * stride); q.y1 = lds_f64(base + 3 * stride);
+  q.x2 = lds_f64(base + 4 * stride); q.y2 = lds_f64(base + 5 * stride);
+  q.x3 = lds_f64(base + 6 * stride); q.y3 = lds_f64(base + 7 * stride);
+  return q;
+}
+SG_DEV Quad quad_from_array(const double* p) {
+  Quad q = {p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7]};
+  return q;
+}
 
 // ring orientation of a convex quad: +1 ccw, -1 cw, 0 degenerate
-__device__ __noinline__ int quad_orientation(const double* q, int st) {
-  int s = orient_sign(q[0], q[st], q[2 * st], q[3 * st], q[4 * st], q[5 * st]);
-  if (s == 0) s = orient_sign(q[2 * st], q[3 * st], q[4 * st], q[5 * st], q[6 * st], q[7 * st]);
+SG_DEV int quad_orientation(const Quad& q) {
+  int s = orient_sign(q.x0, q.y0, q.x1, q.y1, q.x2, q.y2);
+  if (s == 0) s = orient_sign(q.x1, q.y1, q.x2, q.y2, q.x3, q.y3);
   return s;
+}
+
+// are all four corners of b strictly outside edge (corner 0 -> corner 1) of a (orientation o)?
+SG_DEV bool edge01_separates(const Quad& a, int o, const Quad& b) {
+  return orient_sign(a.x0, a.y0, a.x1, a.y1, b.x0, b.y0) * o < 0 &&
+         orient_sign(a.x0, a.y0, a.x1, a.y1, b.x1, b.y1) * o < 0 &&
+         orient_sign(a.x0, a.y0, a.x1, a.y1, b.x2, b.y2) * o < 0 &&
+         orient_sign(a.x0, a.y0, a.x1, a.y1, b.x3, b.y3) * o < 0;
 }
 
 // closed-set intersection of two convex quads (touching counts, as GEOS `intersects`):
 // disjoint iff some edge of either has all four corners of the other strictly outside
-__device__ __noinline__ bool quads_intersect(const double* a, int sa, int oa, const double* b,
-                                             int sb, int ob) {
+__device__ __noinline__ bool quads_intersect(Quad a, int oa, Quad b, int ob) {
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
-    const double* P = pass ? b : a;
-    const double* Q = pass ? a : b;
-    const int sp = pass ? sb : sa, sq = pass ? sa : sb, o = pass ? ob : oa;
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
-      const int k1 = (k + 1) & 3;
-      const double ax = P[2 * k * sp], ay = P[(2 * k + 1) * sp];
-      const double bx = P[2 * k1 * sp], by = P[(2 * k1 + 1) * sp];
-      bool sep = true;
-#pragma unroll 1
-      for (int m = 0; m < 4 && sep; ++m)
-        sep = orient_sign(ax, ay, bx, by, Q[2 * m * sq], Q[(2 * m + 1) * sq]) * o < 0;
-      if (sep) return false;
+      if (edge01_separates(a, oa, b)) return false;
+      rotate(a);
     }
+    const Quad t = a; a = b; b = t;
+    const int to = oa; oa = ob; ob = to;
   }
   return true;
 }
 
 // closed-set intersection of a convex quad and the segment (x0, y0)-(x1, y1)
-__device__ __noinline__ bool quad_intersects_segment(const double* q, int st, int o, double x0,
-                                                     double y0, double x1, double y1) {
+__device__ __noinline__ bool quad_intersects_segment(Quad q, int o, double x0, double y0, double x1,
+                                                     double y1) {
   int pos = 0, neg = 0;
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) {
-    const int k1 = (k + 1) & 3;
-    const double ax = q[2 * k * st], ay = q[(2 * k + 1) * st];
-    const double bx = q[2 * k1 * st], by = q[(2 * k1 + 1) * st];
-    if (orient_sign(ax, ay, bx, by, x0, y0) * o < 0 && orient_sign(ax, ay, bx, by, x1, y1) * o < 0)
+    if (orient_sign(q.x0, q.y0, q.x1, q.y1, x0, y0) * o < 0 &&
+        orient_sign(q.x0, q.y0, q.x1, q.y1, x1, y1) * o < 0)
       return false;  // both end points strictly outside this edge
-    const int sg = orient_sign(x0, y0, x1, y1, ax, ay);
+    const int sg = orient_sign(x0, y0, x1, y1, q.x0, q.y0);
     pos += sg > 0;
     neg += sg < 0;
+    rotate(q);
   }
   return !(pos == 4 || neg == 4);  // corners strictly on one side of the segment's line
 }

@@ -102,6 +102,7 @@ struct Grp {
   double* corners;
   double* actbuf;
   double* rbox;
+  unsigned corners_sh, rbox_sh;  // shared-window addresses for the ld.shared predicates
   double* tcold;
   double* hcs;
   double* pedbuf;
@@ -144,6 +145,8 @@ SG_DEV void setup_group(Grp& g, const SgScene& sc, const GroupLayout& L, unsigne
   g.corners = (double*)base;
   g.actbuf = (double*)(base + L.off_act);
   g.rbox = (double*)(base + L.off_rbox);
+  g.corners_sh = (unsigned)__cvta_generic_to_shared(base);
+  g.rbox_sh = g.corners_sh + (unsigned)L.off_rbox;
   g.tcold = (double*)(base + L.off_tcold);
   g.hcs = (double*)(base + L.off_hcs);
   g.pedbuf = (double*)(base + L.off_ped);
@@ -455,7 +458,7 @@ SG_DEV void publish_box(const Grp& c, bool present, double x, double y, double c
 #pragma unroll
     for (int f = 0; f < 8; ++f) c.corners[f * c.G + c.s] = my[f];
     if (RSS) { c.hcs[c.s] = cs; c.hcs[c.G + c.s] = sn; }
-    c.orient[c.s] = (int8_t)(orient_hint ? orient_hint : quad_orientation(c.corners + c.s, c.G));
+    c.orient[c.s] = (int8_t)(orient_hint ? orient_hint : quad_orientation(quad_from_array(my)));
     bb = make_aabb_box(x, y, cs, sn, bw, bl, bcx, bcy, ox, oy);
   }
   c.aabb[c.s] = bb;
@@ -501,15 +504,27 @@ SG_DEV void publish_ego(const Grp& c, bool present, double x, double y, double e
 // ---------------------------------------------------------------------------------
 // RSS (reference metrics/rss/callback.py)
 // ---------------------------------------------------------------------------------
-// The hazard's ego-frame corners are staged at q[k*st] in shared memory for these.
+// The hazard's ego-frame corners are staged in shared memory (rbox) for these; `qa` is the shared
+// address of the thread's first coordinate, `qs` the byte stride between coordinates.
+
+// (These read the corners on the fly with ld.shared inside rolled loops: few registers, so the
+// caller saves little around the call.)
+SG_DEV double qx(unsigned qa, unsigned qs, int k) { return lds_f64(qa + 2u * (unsigned)(k & 3) * qs); }
+SG_DEV double qy(unsigned qa, unsigned qs, int k) { return lds_f64(qa + (2u * (unsigned)(k & 3) + 1u) * qs); }
+SG_DEV int quad_orientation_sh(unsigned qa, unsigned qs) {
+  int s = orient_sign(qx(qa, qs, 0), qy(qa, qs, 0), qx(qa, qs, 1), qy(qa, qs, 1), qx(qa, qs, 2), qy(qa, qs, 2));
+  if (s == 0)
+    s = orient_sign(qx(qa, qs, 1), qy(qa, qs, 1), qx(qa, qs, 2), qy(qa, qs, 2), qx(qa, qs, 3), qy(qa, qs, 3));
+  return s;
+}
 
 // Does the infinite line through (ax, ay), (bx, by) meet the closed convex quad?  (Exact.)
-__device__ __noinline__ bool line_hits_quad(const double* q, int st, double ax, double ay,
-                                            double bx, double by) {
+__device__ __noinline__ bool line_hits_quad(unsigned qa, unsigned qs, double ax, double ay, double bx,
+                                            double by) {
   int pos = 0, neg = 0;
 #pragma unroll 1
   for (int m = 0; m < 4; ++m) {
-    const int sg = orient_sign(ax, ay, bx, by, q[2 * m * st], q[(2 * m + 1) * st]);
+    const int sg = orient_sign(ax, ay, bx, by, qx(qa, qs, m), qy(qa, qs, m));
     pos += sg > 0;
     neg += sg < 0;
   }
@@ -519,19 +534,17 @@ __device__ __noinline__ bool line_hits_quad(const double* q, int st, double ax, 
 // Closed intersection of a convex quad with the rectangle [-a, a] x [-b, b] whose bounding
 // ranges already overlap: separating axes are the quad's edges; per edge only the rectangle
 // corner that is extreme towards the quad's inside has to be tested.  (Exact.)
-__device__ __noinline__ bool quad_hits_centered_rect(const double* q, int st, double a, double b) {
-  const int o = quad_orientation(q, st);
+__device__ __noinline__ bool quad_hits_centered_rect(unsigned qa, unsigned qs, double a, double b) {
+  const int o = quad_orientation_sh(qa, qs);
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) {
-    const int k1 = (k + 1) & 3;
-    const double ax = q[2 * k * st], ay = q[(2 * k + 1) * st];
-    const double bx = q[2 * k1 * st], by = q[(2 * k1 + 1) * st];
-    // orient(a, b, p) = dx*(py-ay) - dy*(px-ax): o*orient is largest for
+    const double x0 = qx(qa, qs, k), y0 = qy(qa, qs, k), x1 = qx(qa, qs, k + 1), y1 = qy(qa, qs, k + 1);
+    // orient(p0, p1, p) = dx*(py-y0) - dy*(px-x0): o*orient is largest for
     // py = b*sign(o*dx), px = -a*sign(o*dy)
-    const double dx = bx - ax, dy = by - ay;
+    const double dx = x1 - x0, dy = y1 - y0;
     const double py = ((o > 0) == (dx > 0) || dx == 0) ? b : -b;
     const double px = ((o > 0) == (dy > 0) && dy != 0) ? -a : a;
-    if (orient_sign(ax, ay, bx, by, px, py) * o < 0) return false;  // every corner strictly outside
+    if (orient_sign(x0, y0, x1, y1, px, py) * o < 0) return false;  // every corner strictly outside
   }
   return true;
 }
@@ -540,22 +553,21 @@ __device__ __noinline__ bool quad_hits_centered_rect(const double* q, int st, do
 // quad's y-range already contains c: the quad's corners are then not strictly on one side of
 // the segment's line, so the segment misses the quad iff some quad edge has both segment
 // endpoints strictly outside.  (Exact.)
-__device__ __noinline__ bool quad_hits_hsegment(const double* q, int st, double w, double c) {
-  const int o = quad_orientation(q, st);
+__device__ __noinline__ bool quad_hits_hsegment(unsigned qa, unsigned qs, double w, double c) {
+  const int o = quad_orientation_sh(qa, qs);
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) {
-    const int k1 = (k + 1) & 3;
-    const double ax = q[2 * k * st], ay = q[(2 * k + 1) * st];
-    const double bx = q[2 * k1 * st], by = q[(2 * k1 + 1) * st];
-    if (orient_sign(ax, ay, bx, by, -w, c) * o < 0 && orient_sign(ax, ay, bx, by, w, c) * o < 0)
+    const double x0 = qx(qa, qs, k), y0 = qy(qa, qs, k), x1 = qx(qa, qs, k + 1), y1 = qy(qa, qs, k + 1);
+    if (orient_sign(x0, y0, x1, y1, -w, c) * o < 0 && orient_sign(x0, y0, x1, y1, w, c) * o < 0)
       return false;
   }
   return true;
 }
 
-__device__ __noinline__ bool rss_box_hits_segment(const double* q, int st, double x0, double y0,
+__device__ __noinline__ bool rss_box_hits_segment(unsigned qa, unsigned qs, double x0, double y0,
                                                   double x1, double y1) {
-  return quad_intersects_segment(q, st, quad_orientation(q, st), x0, y0, x1, y1);
+  const Quad q = load_quad_shared(qa, qs);
+  return quad_intersects_segment(q, quad_orientation(q), x0, y0, x1, y1);
 }
 
 struct RssConst {  // uniform per launch
@@ -650,10 +662,10 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
     box[2 * q] = dot2(c0, c1, ei0, ei1);
     box[2 * q + 1] = dot2(c0, c1, eh0, eh1);
   }
-  double* rb = c.rbox + c.s;  // the same corners, staged for the out-of-line exact predicates
-  const int st = c.G;
+  double* rbp = c.rbox + c.s;  // the same corners, staged for the out-of-line exact predicates
 #pragma unroll
-  for (int q = 0; q < 8; ++q) rb[q * st] = box[q];
+  for (int q = 0; q < 8; ++q) rbp[q * c.G] = box[q];
+  const unsigned rb = c.rbox_sh + (unsigned)c.s * 8u, st = (unsigned)c.G * 8u;
   const double bxmin = min2(min2(box[0], box[2]), min2(box[4], box[6]));
   const double bxmax = max2(max2(box[0], box[2]), max2(box[4], box[6]));
   const double bymin = min2(min2(box[1], box[3]), min2(box[5], box[7]));
@@ -709,19 +721,39 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
 // ---------------------------------------------------------------------------------
 // collisions (reference state/utils.py:10-49, utils.py:28-62)
 // ---------------------------------------------------------------------------------
-// exact narrow phase for one AABB-surviving pair, both quads read from the staged corners
-__device__ __noinline__ bool pair_collides(const double* corners, const int8_t* orient, int G,
-                                           int a, int b) {
+// exact narrow phase for one AABB-surviving pair; both quads are read on the fly from the staged
+// corners with ld.shared inside rolled loops (`csh`: shared address of corners[0][0]), so the
+// routine needs few registers and its callers save little around the call
+__device__ __noinline__ bool pair_collides(unsigned csh, const int8_t* orient, int G, int a, int b) {
+  const unsigned qs = (unsigned)G * 8u;
+  unsigned pa = csh + (unsigned)a * 8u, pb = csh + (unsigned)b * 8u;
   bool same = true;
 #pragma unroll 1
-  for (int f = 0; f < 8; ++f) same = same && (corners[f * G + a] == corners[f * G + b]);
+  for (unsigned f = 0; f < 8; ++f) same = same && (lds_f64(pa + f * qs) == lds_f64(pb + f * qs));
   if (same) return false;  // `g != g_prime`, reference utils.py:58
-  return quads_intersect(corners + a, G, orient[a], corners + b, G, orient[b]);
+  int oa = orient[a], ob = orient[b];
+  // closed-set intersection of two convex quads (touching counts, as GEOS `intersects`):
+  // disjoint iff some edge of either has all four corners of the other strictly outside
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      const double ax = qx(pa, qs, k), ay = qy(pa, qs, k), bx = qx(pa, qs, k + 1), by = qy(pa, qs, k + 1);
+      bool sep = true;
+#pragma unroll 1
+      for (int m = 0; m < 4 && sep; ++m)
+        sep = orient_sign(ax, ay, bx, by, qx(pb, qs, m), qy(pb, qs, m)) * oa < 0;
+      if (sep) return false;
+    }
+    const unsigned tp = pa; pa = pb; pb = tp;
+    const int to = oa; oa = ob; ob = to;
+  }
+  return true;
 }
 
 __device__ __noinline__ void record_pair(int features, uint32_t* coll_mask, const Grp& c, int a,
                                          int b, int ego_slot, int first_slot, int parity) {
-  if (!pair_collides(c.corners, c.orient, c.G, a, b)) return;
+  if (!pair_collides(c.corners_sh, c.orient, c.G, a, b)) return;
   const int lo = min(a, b), hi = max(a, b);
   int* acc = c.acc + parity * ACC_N;
   atomicAdd(&acc[ACC_NPAIRS], 1);
@@ -1486,7 +1518,8 @@ __global__ void sg_box_pairs_kernel(const double* pa, const double* ba, const do
   box_points(pb[3 * i], pb[3 * i + 1], pb[3 * i + 2], bb[4 * i], bb[4 * i + 1], bb[4 * i + 2], bb[4 * i + 3], qb);
   bool same = true;
   for (int f = 0; f < 8; ++f) same = same && (qa[f] == qb[f]);
-  out[i] = !same && quads_intersect(qa, 1, quad_orientation(qa, 1), qb, 1, quad_orientation(qb, 1));
+  const Quad A = quad_from_array(qa), B = quad_from_array(qb);
+  out[i] = !same && quads_intersect(A, quad_orientation(A), B, quad_orientation(B));
 }
 
 // ---------------------------------------------------------------------------------
