@@ -310,3 +310,47 @@ def test_properties_full_size_sample():
     npt = gpu.get("n_pair_ticks")
     assert np.array_equal(col.any(axis=1), npt > 0)
     assert np.array_equal(gpu.get("first_coll_tick") >= 0, npt > 0)
+
+
+@pytest.mark.parametrize("M,N,rss", [(256, 5, True), (300, 3, True), (300, 2, False)])
+def test_large_vehicle_groups_vs_oracle(M, N, rss):
+    """Vehicle kernel variants: one 256-thread CTA per scenario, and the 1024-thread variant."""
+    cfg = synthetic.highway_config(seed=9, N=N, M=M, T=16, lanes=4 if M % 4 == 0 else 3)
+    cfg.x0[:] = cfg.x0 * 0.5
+    scene = pack_synthetic(cfg)
+    p = _params(timestep=cfg.dt)
+    if rss:
+        p.features |= abi.FEAT_RSS
+    gpu, cpu = _run_both(scene, p, actions=cfg.actions)
+    compare_engines(gpu, cpu, scene, f"highway M={M}", check_rss=rss)
+
+
+def test_candidate_queue_overflow_vs_oracle():
+    """So dense that the AABB survivors exceed the per-scenario queue (4 G entries): the kernel
+    falls back to testing every survivor in place; results must not change."""
+    cfg = synthetic.vehicles_config(seed=12, N=5, M=64, T=6, half_extent=3.0)
+    scene = pack_synthetic(cfg)
+    p = _params(timestep=cfg.dt)
+    gpu, cpu = _run_both(scene, p, actions=cfg.actions)
+    assert cpu.get("n_pair_ticks").min() > 4 * 64, "config must overflow the queue"
+    compare_engines(gpu, cpu, scene, "queue overflow")
+    assert np.array_equal(gpu.get("coll_mask"), cpu.get("coll_mask"))
+
+
+def test_step_done_and_zero_ticks():
+    """ScenarioGym.step() has no is_done guard (step_done=1); rollout() stops at is_done."""
+    cfg = synthetic.vehicles_config(seed=2, N=3, M=8, T=10, half_extent=30.0)
+    scene = pack_synthetic(cfg)
+    p = _params(timestep=cfg.dt)
+    table = np.concatenate([cfg.actions, cfg.actions], axis=0)
+    for make in (make_gpu, lambda s, q, trace_cap=0: OracleEngine(s, q)):
+        eng = make(scene, p)
+        eng.reset()
+        eng.rollout(0, actions=table)
+        assert (eng.get("tick") == 0).all()
+        eng.rollout(-1, actions=table)
+        assert (eng.get("tick") == cfg.T).all() and eng.get("done").all()
+        eng.rollout(2, actions=table[cfg.T:])  # done: skipped
+        assert (eng.get("tick") == cfg.T).all()
+        eng.rollout(2, actions=table[cfg.T:], step_done=True)  # stepped anyway
+        assert (eng.get("tick") == cfg.T + 2).all()
