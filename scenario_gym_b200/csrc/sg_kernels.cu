@@ -591,52 +591,46 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
   const double v0 = dot2(vx, vy, ei0, ei1), v1 = dot2(vx, vy, eh0, eh1);
   const double eW = E[EGO_W], eL = E[EGO_L];
   const double eHD0 = E[EGO_HD0], eHD1 = E[EGO_HD1];
-  // safe_longitudinal_distance (callback.py:230-269); the ego's position is [0, 0]
+  // safe_longitudinal_distance (callback.py:230-269); the ego's position is [0, 0].  Both
+  // branches of the reference (same / opposite direction) are evaluated and selected: lanes of
+  // a warp take both anyway, and straight-line code lets the two chains overlap.
   double slong;
   {
     const double dp = dot2(eHD0, eHD1, hd0, hd1);
     const double a = fabs(K.MAXA * dp);
     const double hv = dot2(v0, v1, eHD0, eHD1);
-    bool early;
-    double dd = 0;
-    if (dp > 0) {
-      double vf, vr;
-      if (0.0 > pos1) { vf = E[EGO_VNORM]; vr = hv; } else { vf = hv; vr = E[EGO_VNORM]; }
-      early = vr == 0.0;
-      if (!early) {  // long_dist_same_direction, callback.py:454-472
-        const double vf2a = div_r(vf * vf, 2 * a, fast_rcp(2 * a));
-        const double u = vr + K.RT * a;
-        dd = py_max(0, vr * K.RT + py_min(vf2a, 0.5 * a * (K.RT * K.RT)) +
-                           div_r(u * u, 2 * K.MINA, K.r2mina) - vf2a);
-      }
-    } else {
-      early = np_sign(pos1) == np_sign(v1);
-      if (!early) {  // long_dist_opp_direction, callback.py:474-492
-        const double v1e = E[EGO_VLONG], av2 = fabs(hv);
-        const double u1 = v1e + K.RT * a, u2 = av2 + K.RT * a;
-        dd = py_max(0, (2 * v1e + K.RT * a) * K.RT / 2 + div_r(u1 * u1, 2 * K.MINA, K.r2mina) +
-                           (2 * av2 + K.RT * a) * K.RT / 2 + div_r(u2 * u2, 2 * K.MINA, K.r2mina));
-      }
-    }
+    const double rta = K.RT * a;
+    // same direction: long_dist_same_direction, callback.py:243-256, 454-472
+    const bool ahead = 0.0 > pos1;
+    const double vf = ahead ? E[EGO_VNORM] : hv, vr = ahead ? hv : E[EGO_VNORM];
+    const double a2 = 2 * a;
+    const double vf2a = div_r(vf * vf, a2, fast_rcp(a2));
+    const double u = vr + rta;
+    const double dd_s = py_max(0, vr * K.RT + py_min(vf2a, 0.5 * a * (K.RT * K.RT)) +
+                                      div_r(u * u, 2 * K.MINA, K.r2mina) - vf2a);
+    // opposite direction: long_dist_opp_direction, callback.py:257-268, 474-492
+    const double v1e = E[EGO_VLONG], av2 = fabs(hv);
+    const double u1 = v1e + rta, u2 = av2 + rta;
+    const double dd_o = py_max(0, (2 * v1e + rta) * K.RT / 2 + div_r(u1 * u1, 2 * K.MINA, K.r2mina) +
+                                      (2 * av2 + rta) * K.RT / 2 + div_r(u2 * u2, 2 * K.MINA, K.r2mina));
+    const bool same = dp > 0;
+    const bool early = same ? (vr == 0.0) : (np_sign(pos1) == np_sign(v1));
+    const double dd = same ? dd_s : dd_o;
     slong = fabs(early ? K.CLR + 0.5 * eL : dd + K.CLR + 0.5 * eL);
   }
-  // safe_lateral_distance (callback.py:271-302)
+  // safe_lateral_distance (callback.py:271-302), lat_dist :494-505
   double slat;
   {
     const double k = fabs(dot2(E[EGO_HINV0], E[EGO_HINV1], hd0, hd1));
     const double amax = K.MAXA * k, amin = K.MINA * k;
-    double dd = 0;
-    bool early = false;
-    if (np_sign(-pos0) == np_sign(v0)) {
-      const double v = fabs(v0);
-      early = v == 0.0;
-      if (!early) {  // lat_dist, callback.py:494-505
-        const double den = 2 * amin, rden = fast_rcp(den);
-        const double u = v + K.RT * amax, w = K.RT * amax;
-        dd = py_max(0, 0.5 * K.RT * (2 * v + K.RT * amax) + div_r(u * u, den, rden) -
-                           0.5 * (K.RT * K.RT) * amax - div_r(w * w, den, rden));
-      }
-    }
+    const double v = fabs(v0);
+    const double den = 2 * amin, rden = fast_rcp(den);
+    const double w = K.RT * amax, u = v + w;
+    const double dl = py_max(0, 0.5 * K.RT * (2 * v + w) + div_r(u * u, den, rden) -
+                                    0.5 * (K.RT * K.RT) * amax - div_r(w * w, den, rden));
+    const bool conv = np_sign(-pos0) == np_sign(v0);  // lateral convergence
+    const bool early = conv && v == 0.0;
+    const double dd = (conv && !early) ? dl : 0.0;
     slat = fabs(early ? K.CLR + 0.5 * eW : dd + K.CLR + 0.5 * eW);
   }
   out[0] = slat;
