@@ -1115,7 +1115,7 @@ struct Ent {
 };
 
 template <bool PED, bool RSS, int MAXT>
-__global__ void __launch_bounds__(MAXT)
+__global__ void __launch_bounds__(MAXT, MAXT >= 1024 ? 1 : 2)
 sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, GroupLayout L) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int G = L.G, M = sc.n_slots, W = L.W;
@@ -1400,7 +1400,7 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
 // State.reset(t0) + Agent/Metric/StateCallback resets (reference state/state.py:106-143,
 // controller.py:100-103, metrics/trajectory.py:13-18, metrics/rss/callback.py:44-55)
 template <bool RSS, int MAXT>
-__global__ void __launch_bounds__(MAXT)
+__global__ void __launch_bounds__(MAXT, MAXT >= 1024 ? 1 : 2)
 sg_reset_kernel(SgScene sc, SgParams p, SgState st, GroupLayout L) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int G = L.G, M = sc.n_slots, W = L.W;
