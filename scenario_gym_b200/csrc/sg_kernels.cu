@@ -177,6 +177,22 @@ SG_DEV double fast_rcp(double d) {
   return __fma_rn(r, e, r);
 }
 
+// sqrt(x) for finite x >= 0: hardware rsqrt seed, two Newton steps on 1/sqrt and one residual
+// correction on the root (within an ulp); ~12 instructions, no special-case paths
+SG_DEV double fast_sqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = __fma_rn(-hx * y, y, 0.5);
+  y = __fma_rn(y, e, y);
+  e = __fma_rn(-hx * y, y, 0.5);
+  y = __fma_rn(y, e, y);
+  double r = x * y;
+  r = __fma_rn(__fma_rn(-r, r, x), 0.5 * y, r);
+  return x > 0.0 ? r : 0.0;
+}
+SG_DEV double fnorm2(double a, double b) { return fast_sqrt(a * a + b * b); }
+
 // n / d with a shared reciprocal r = 1/d (correctly rounded): one Newton correction on the
 // quotient (Markstein); equals the IEEE quotient except in rare last-bit cases
 SG_DEV double div_r(double n, double d, double r) {
@@ -477,7 +493,7 @@ SG_DEV void publish_ego(const Grp& c, bool present, double x, double y, double e
                         double vx, double vy) {
   double einv[2];
   {  // inverse_direction((cos h, sin h)), rss_utils.py:7-21
-    const double nn = norm2(es, ec), rn = fast_rcp(nn);
+    const double nn = fnorm2(es, ec), rn = fast_rcp(nn);
     einv[0] = div_r(es, nn, rn);
     einv[1] = div_r(-ec, nn, rn);
   }
@@ -489,14 +505,14 @@ SG_DEV void publish_ego(const Grp& c, bool present, double x, double y, double e
   E[EGO_HD0] = hd[0]; E[EGO_HD1] = hd[1];
   double hinv[2];  // inverse_direction(ego-frame heading): used by safe_lateral_distance
   {
-    const double nn = norm2(hd[1], hd[0]), rn = fast_rcp(nn);
+    const double nn = fnorm2(hd[1], hd[0]), rn = fast_rcp(nn);
     hinv[0] = div_r(hd[1], nn, rn);
     hinv[1] = div_r(-hd[0], nn, rn);
   }
   E[EGO_HINV0] = hinv[0]; E[EGO_HINV1] = hinv[1];
   const double v0 = dot2(vx, vy, einv[0], einv[1]), v1 = dot2(vx, vy, ec, es);
   E[EGO_V0] = v0; E[EGO_V1] = v1;
-  E[EGO_VNORM] = norm2(v0, v1);
+  E[EGO_VNORM] = fnorm2(v0, v1);
   E[EGO_VLONG] = fabs(dot2(v0, v1, hd[0], hd[1]));
   E[EGO_PRESENT] = present ? 1.0 : 0.0;
 }
@@ -637,7 +653,7 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
   out[ost] = slong;
   // safe_ratios (callback.py:124-166)
   {
-    const double hn = norm2(hd1, hd0), rhn = fast_rcp(hn);  // inverse_direction(haz heading)
+    const double hn = fnorm2(hd1, hd0), rhn = fast_rcp(hn);  // inverse_direction(haz heading)
     const double inv0 = div_r(hd1, hn, rhn), inv1 = div_r(-hd0, hn, rhn);
     const double wl_inv = fabs(dot2(bw, bl, inv0, inv1));
     const double wl_dir = fabs(dot2(bw, bl, hd0, hd1));
@@ -1029,7 +1045,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       const double ex = nx - x, ey = ny - y;
       vx = div_r(ex, dt, rdt); vy = div_r(ey, dt, rdt);
       tc[4 * G] = div_r(nh - h, dt, rdt);
-      dist += norm3(ex, ey, 0.0);
+      dist += fnorm2(ex, ey);
       x = nx; y = ny; h = nh;
       sincos_fast(h, sn, cs);
     }
