@@ -707,10 +707,27 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
   const double L100 = 100 * slong, W100 = 100 * slat;
   bool lat = false, lon = false;
   if (!(bxmin > slat || bxmax < -slat || bymin > L100 || bymax < -L100)) {
-    if (bymax < L100 && bymin > -L100)  // segment spans the box's y-range: segment <=> line
-      lat = line_hits_quad(rb, st, slat, L100, -slat, 100 * -slong) ||
-            line_hits_quad(rb, st, -slat, L100, slat, 100 * -slong);
-    else
+    if (bymax < L100 && bymin > -L100) {  // segment spans the box's y-range: segment <=> line
+      // Both diagonals pass through the origin (their end points are exact negatives), so
+      // orient(a, -a, c) = 2 (a_y c_x - a_x c_y): the side of corner c is the sign of
+      // L100 c_x -+ slat c_y, decided here whenever it clears the rounding bound of that
+      // expression (3 roundings) and by the exact predicate otherwise.
+      int pos1 = 0, neg1 = 0, pos2 = 0, neg2 = 0;
+      bool unsure = false;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double pp = L100 * box[2 * q], rr = slat * box[2 * q + 1];
+        const double d1 = pp - rr, d2 = pp + rr, tol = 4e-16 * (fabs(pp) + fabs(rr));
+        unsure = unsure || !(fabs(d1) > tol) || !(fabs(d2) > tol);
+        pos1 += d1 > 0; neg1 += d1 < 0;
+        pos2 += d2 > 0; neg2 += d2 < 0;
+      }
+      if (unsure)
+        lat = line_hits_quad(rb, st, slat, L100, -slat, 100 * -slong) ||
+              line_hits_quad(rb, st, -slat, L100, slat, 100 * -slong);
+      else
+        lat = !(pos1 == 4 || neg1 == 4) || !(pos2 == 4 || neg2 == 4);
+    } else
       lat = rss_box_hits_segment(rb, st, slat, L100, -slat, 100 * -slong) ||
             rss_box_hits_segment(rb, st, -slat, L100, slat, 100 * -slong);
   }
