@@ -136,65 +136,121 @@ def config_json(args, extra=None):
 
 # ------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples taken DURING the timed region."""
+    """SM clock / throttle-reason samples taken DURING the timed region.
+
+    NVML is polled from a thread every few ms (the timed region of a short run is < 100 ms, too
+    short for `nvidia-smi -lms`); `nvidia-smi` is the fall-back when NVML cannot be loaded.
+    """
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
-        self.index = index
+    def __init__(self, index: int, uuid: str = None, period_s: float = 0.004):
+        self.index, self.uuid, self.period = index, uuid, period_s
         self.proc = None
-        self.lines = []
+        self.nvml = None
+        self.samples = []  # (wall time, sm MHz, max MHz, watts, set of reasons)
+        self._stop = threading.Event()
+        self.thread = None
+
+    # -- NVML ---------------------------------------------------------------------------
+    def _nvml_open(self):
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = None
+        if self.uuid:
+            for u in (self.uuid, "GPU-" + self.uuid):
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(u.encode() if isinstance(u, str) else u)
+                    break
+                except Exception:
+                    h = None
+        if h is None:
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        self.nvml, self.handle = nv, h
+
+    def _nvml_loop(self):
+        nv, h = self.nvml, self.handle
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                try:
+                    watts = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+                except Exception:
+                    watts = float("nan")
+                self.samples.append((time.time(), mhz, self.max_mhz, watts,
+                                     {nm for b, nm in bits if r & b}))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    # -- nvidia-smi fall-back -------------------------------------------------------------
+    def _smi_loop(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.strip().split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                self.samples.append((time.time(), float(parts[0]), float(parts[1]), float(parts[2]),
+                                     {nm for nm, v in zip(self.NAMES, parts[3:7])
+                                      if v.lower().startswith("active")}))
+            except ValueError:
+                continue
 
     def start(self):
         try:
+            self._nvml_open()
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
-
     def window(self, t0: float, t1: float) -> None:
-        """Only samples that arrived inside [t0, t1] (the timed region) are reported."""
+        """Only samples taken inside [t0, t1] (the timed region) are reported."""
         self.t0, self.t1 = t0, t1
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
-        inside = [ln for ts, ln in self.lines if t0 <= ts <= t1 + 0.05]
-        for line in (inside or [ln for _, ln in self.lines[-3:]]):
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
-                continue
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no NVML / nvidia-smi"]}
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-                power.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        reasons = set()
+        for s in inside:
+            reasons |= s[4]
+        power = [s[3] for s in inside if s[3] == s[3]]
         return {
-            "sm_mhz": float(np.median(sm)) if sm else None,
-            "sm_max_mhz": float(max(mx)) if mx else None,
+            "sm_mhz": float(np.median([s[1] for s in inside])) if inside else None,
+            "sm_max_mhz": float(max(s[2] for s in inside)) if inside else None,
             "power_w_max": float(max(power)) if power else None,
-            "samples": len(sm),
+            "samples": len(inside),
+            "source": "nvml" if self.nvml is not None else "nvidia-smi",
             "reasons": sorted(reasons),
         }
 
@@ -356,9 +412,13 @@ def run_b200(args):
         eng.rollout(-1, actions=act_dev)
 
     # ---- device-resident timing -----------------------------------------------------
-    sampler = ClockSampler(local)
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid)
     if rank == 0:
-        sampler.start()  # nvidia-smi needs a few 100 ms to deliver its first sample
+        sampler.start()
     for _ in range(args.warmup):
         one_step()
     barrier()

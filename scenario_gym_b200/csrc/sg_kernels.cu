@@ -250,7 +250,11 @@ SG_DEV void sincos_kernel(double x, double& sn, double& cs) {
   cs = w + (((1.0 - w) - hz) + z * (z * q));
 }
 // library fall-backs kept out of line so the tick loop does not carry their code
-__device__ __noinline__ void sincos_lib(double x, double* sn, double* cs) { sincos(x, sn, cs); }
+__device__ __noinline__ double2 sincos_lib(double x) {  // by value: no address-taken locals in the callers
+  double2 r;
+  sincos(x, &r.x, &r.y);
+  return r;
+}
 __device__ __noinline__ double tan_lib(double x) { return tan(x); }
 
 // tan on |x| <= pi/4 (steering angles are clipped to +-max_steer)
@@ -261,7 +265,7 @@ SG_DEV double tan_small(double x) {
 }
 // sincos with a 3-term Cody-Waite reduction (exact under FMA for |x| < 1e9)
 SG_DEV void sincos_fast(double x, double& sn, double& cs) {
-  if (!(fabs(x) < 1.0e9)) { sincos_lib(x, &sn, &cs); return; }
+  if (!(fabs(x) < 1.0e9)) { const double2 r = sincos_lib(x); sn = r.x; cs = r.y; return; }
   const double kd = rint(x * 0.63661977236758138);
   double r = __fma_rn(-kd, 1.5707963267948966, x);
   r = __fma_rn(-kd, 6.123233995736766e-17, r);
@@ -778,30 +782,45 @@ __device__ __noinline__ bool pair_collides(unsigned csh, const int8_t* orient, i
   return true;
 }
 
+// Where a colliding pair is booked: passed BY VALUE to the out-of-line routines so that the
+// group descriptor itself never has its address taken (it then lives in registers / is
+// rematerialised from the constant bank instead of being re-read from local memory).
+struct PairSink {
+  int* acc;            // this tick's accumulators
+  uint32_t* bits;      // this tick's collided bits
+  uint32_t* ego_now;   // ego row of this tick
+  uint32_t* rows;      // optional pair matrix of this scenario (SG_FEAT_COLL_MATRIX)
+  int W, ego_slot, first_slot;
+};
+SG_DEV PairSink make_sink(int features, uint32_t* coll_mask, const Grp& c, int ego_slot, int first_slot,
+                          int parity) {
+  PairSink k;
+  k.acc = c.acc + parity * ACC_N;
+  k.bits = c.bits + parity * c.W;
+  k.ego_now = c.ego_now;
+  k.rows = (features & SG_FEAT_COLL_MATRIX) ? coll_mask + (int64_t)c.n * c.M * c.W : nullptr;
+  k.W = c.W; k.ego_slot = ego_slot; k.first_slot = first_slot;
+  return k;
+}
+
 // book-keeping for one colliding pair (scenario-level shared atomics)
-__device__ __noinline__ void commit_pair(int features, uint32_t* coll_mask, const Grp& c, int a,
-                                         int b, int ego_slot, int first_slot, int parity) {
+__device__ __noinline__ void commit_pair(PairSink k, int a, int b) {
   const int lo = min(a, b), hi = max(a, b);
-  int* acc = c.acc + parity * ACC_N;
-  atomicAdd(&acc[ACC_NPAIRS], 1);
-  atomicMin(&acc[ACC_FIRST_PAIR], (lo << 16) | hi);
-  if (lo == first_slot || hi == first_slot) acc[ACC_FIRST_HIT] = 1;
-  uint32_t* bits = c.bits + parity * c.W;
-  atomicOr(&bits[lo >> 5], 1u << (lo & 31));
-  atomicOr(&bits[hi >> 5], 1u << (hi & 31));
-  if (lo == ego_slot) atomicOr(&c.ego_now[hi >> 5], 1u << (hi & 31));
-  if (hi == ego_slot) atomicOr(&c.ego_now[lo >> 5], 1u << (lo & 31));
-  if (features & SG_FEAT_COLL_MATRIX) {
-    uint32_t* rows = coll_mask + (int64_t)c.n * c.M * c.W;
-    atomicOr(&rows[(int64_t)lo * c.W + (hi >> 5)], 1u << (hi & 31));
-    atomicOr(&rows[(int64_t)hi * c.W + (lo >> 5)], 1u << (lo & 31));
+  atomicAdd(&k.acc[ACC_NPAIRS], 1);
+  atomicMin(&k.acc[ACC_FIRST_PAIR], (lo << 16) | hi);
+  if (lo == k.first_slot || hi == k.first_slot) k.acc[ACC_FIRST_HIT] = 1;
+  atomicOr(&k.bits[lo >> 5], 1u << (lo & 31));
+  atomicOr(&k.bits[hi >> 5], 1u << (hi & 31));
+  if (lo == k.ego_slot) atomicOr(&k.ego_now[hi >> 5], 1u << (hi & 31));
+  if (hi == k.ego_slot) atomicOr(&k.ego_now[lo >> 5], 1u << (lo & 31));
+  if (k.rows) {
+    atomicOr(&k.rows[(int64_t)lo * k.W + (hi >> 5)], 1u << (hi & 31));
+    atomicOr(&k.rows[(int64_t)hi * k.W + (lo >> 5)], 1u << (lo & 31));
   }
 }
 
-SG_DEV void record_pair(int features, uint32_t* coll_mask, const Grp& c, int a, int b, int ego_slot,
-                        int first_slot, int parity) {
-  if (pair_collides(c.corners_sh, c.orient, c.G, a, b))
-    commit_pair(features, coll_mask, c, a, b, ego_slot, first_slot, parity);
+SG_DEV void record_pair(const PairSink& k, unsigned corners_sh, const int8_t* orient, int G, int a, int b) {
+  if (pair_collides(corners_sh, orient, G, a, b)) commit_pair(k, a, b);
 }
 
 // Warp-cooperative exact narrow phase for one pair: the 32 lanes evaluate the 8 edges x 4 corners
@@ -865,16 +884,16 @@ SG_DEV void broad_phase(const Grp& c, int parity) {
 }
 
 // queue overflow (very dense scenes): redo the sweep and test every survivor in place
-__device__ __noinline__ void broad_phase_direct(int features, uint32_t* coll_mask, const Grp& c,
-                                                int ego_slot, int first_slot, int parity) {
-  const float4 mb = c.aabb[c.s];
-  for (int d = 1; d <= c.H; ++d) {
-    const float4 ob = c.aabb[c.s + d];
+__device__ __noinline__ void broad_phase_direct(PairSink k, const float4* aabb, unsigned corners_sh,
+                                                const int8_t* orient, int G, int M, int H, int s) {
+  const float4 mb = aabb[s];
+  for (int d = 1; d <= H; ++d) {
+    const float4 ob = aabb[s + d];
     if (!(mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w)) continue;
-    int j = c.s + d;
-    if (j >= c.M) j -= c.M;
-    if (2 * d == c.M && c.s > j) continue;
-    record_pair(features, coll_mask, c, c.s, j, ego_slot, first_slot, parity);
+    int j = s + d;
+    if (j >= M) j -= M;
+    if (2 * d == M && s > j) continue;
+    record_pair(k, corners_sh, orient, G, s, j);
   }
 }
 
@@ -886,22 +905,21 @@ SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int 
   int* acc = c.acc + parity * ACC_N;
   const int nq = acc[ACC_QCOUNT];
   if (nq > 0) {  // phase B2: exact narrow phase on the queued pairs
+    const PairSink sink = make_sink(p.features, st.coll_mask, c, ego_slot, first_slot, parity);
     if (G >= 32 && nq <= 2 * (G >> 5)) {
       // few pairs (the usual case): one warp per pair, all lanes share the orientation tests
       for (int q = s >> 5; q < nq; q += G >> 5) {
         const uint32_t pr = c.queue[q];
         const int a = (int)(pr >> 16), b = (int)(pr & 0xffff);
-        if (pair_collides_warp(c.corners_sh, c.orient, G, a, b) && (s & 31) == 0)
-          commit_pair(p.features, st.coll_mask, c, a, b, ego_slot, first_slot, parity);
+        if (pair_collides_warp(c.corners_sh, c.orient, G, a, b) && (s & 31) == 0) commit_pair(sink, a, b);
       }
     } else if (nq <= c.QCAP) {
       for (int q = s; q < nq; q += G) {
         const uint32_t pr = c.queue[q];
-        record_pair(p.features, st.coll_mask, c, (int)(pr >> 16), (int)(pr & 0xffff), ego_slot,
-                    first_slot, parity);
+        record_pair(sink, c.corners_sh, c.orient, G, (int)(pr >> 16), (int)(pr & 0xffff));
       }
     } else if (present) {
-      broad_phase_direct(p.features, st.coll_mask, c, ego_slot, first_slot, parity);
+      broad_phase_direct(sink, c.aabb, c.corners_sh, c.orient, G, c.M, c.H, s);
     }
     group_sync(c);
   }
