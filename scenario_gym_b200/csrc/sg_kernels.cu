@@ -26,6 +26,12 @@
 
 #define SG_THREADS 256
 #define SG_NBCAP 12  // per-pedestrian neighbour candidate list kept in shared memory
+// uniform cell grid of a crowd scenario (one CTA per scenario): 64 x 64 cells, toroidal
+#define SG_GRID_BITS 6
+#define SG_GRID_DIM (1 << SG_GRID_BITS)
+#define SG_GRID_CELLS (SG_GRID_DIM * SG_GRID_DIM)
+#define SG_GRID_LCAP 64        // entities too large for the grid are kept in a list
+#define SG_GRID_LARGE 0x8000u  // flag on a sorted slot id
 #ifndef SG_VEH_THREADS
 #define SG_VEH_THREADS 128  // CTA size of the vehicle kernel for scenarios of up to that many slots
 #endif
@@ -54,6 +60,8 @@ struct GroupLayout {
   int QCAP;     // candidate-pair queue capacity
   int off_act, off_rbox, off_tcold, off_hcs, off_ped, off_pednb, off_nbl, off_box, off_ego, off_cold, off_aabb, off_queue, off_hits, off_bits,
       off_acc, off_flags, off_orient;
+  int grid;     // crowd scenario with a shared-memory cell grid (sensor + broad phase)
+  int off_gstart, off_gsorted, off_glarge, off_gmisc;
   int bytes;
 };
 
@@ -64,7 +72,7 @@ enum { COLD_AVG = 0, COLD_AVG_T, COLD_MAX, COLD_EGOD, COLD_T0, COLD_T1, COLD_PT0
 enum { COLD_FIRST_TICK = 0, COLD_FP0, COLD_FP1, COLD_RSS, COLD_PAIR_TICKS = 4, COLD_NI = 8 };  // ints
 enum { ACC_NPAIRS = 0, ACC_FIRST_PAIR, ACC_FIRST_HIT, ACC_RSS, ACC_QCOUNT, ACC_N = 8 };
 
-static GroupLayout make_layout(int M, bool ped, bool rss, bool veh) {
+static GroupLayout make_layout(int M, bool ped, bool rss, bool veh, bool grid = false) {
   GroupLayout L;
   int G;
   if (M <= 32) { G = 1; while (G < M) G <<= 1; } else { G = (M + 31) / 32 * 32; }
@@ -91,6 +99,12 @@ static GroupLayout make_layout(int M, bool ped, bool rss, bool veh) {
   L.off_acc = o;    o += 2 * ACC_N * (int)sizeof(int);            // 2 parities
   L.off_flags = o;  o += G + 16;                                  // old present|etype<<1
   L.off_orient = o; o += G;                                       // ring orientation of each box
+  o = (o + 15) / 16 * 16;
+  L.grid = (grid && ped && G > SG_THREADS) ? 1 : 0;
+  L.off_gstart = o;  o += L.grid ? (SG_GRID_CELLS / 2 + 4) * (int)sizeof(uint32_t) : 0;  // packed 16-bit cell starts (+ end)
+  L.off_gsorted = o; o += L.grid ? G * (int)sizeof(uint16_t) : 0;                         // slot ids sorted by cell
+  L.off_glarge = o;  o += L.grid ? SG_GRID_LCAP * (int)sizeof(uint16_t) : 0;
+  L.off_gmisc = o;   o += L.grid ? 40 * (int)sizeof(int) : 0;                             // counters + 32 warp totals
   L.bytes = (o + 15) / 16 * 16;
   return L;
 }
@@ -120,6 +134,10 @@ struct Grp {
   int* acc;
   uint8_t* flags;
   int8_t* orient;
+  uint32_t* gstart;
+  uint16_t* gsorted;
+  uint16_t* glarge;
+  int* gmisc;
 };
 
 SG_DEV void cp_async8(unsigned smem_addr, const void* gsrc) {  // smem_addr: shared-window address
@@ -164,6 +182,10 @@ SG_DEV void setup_group(Grp& g, const SgScene& sc, const GroupLayout& L, unsigne
   g.acc = (int*)(base + L.off_acc);
   g.flags = (uint8_t*)(base + L.off_flags);
   g.orient = (int8_t*)(base + L.off_orient);
+  g.gstart = (uint32_t*)(base + L.off_gstart);
+  g.gsorted = (uint16_t*)(base + L.off_gsorted);
+  g.glarge = (uint16_t*)(base + L.off_glarge);
+  g.gmisc = (int*)(base + L.off_gmisc);
 }
 
 // 1/d for a finite, normal, non-zero d: hardware seed (rcp.approx.ftz.f64, ~2^-23) refined by
@@ -325,12 +347,152 @@ SG_DEV void stage_ped_state(const Grp& c, bool present, int etype, double x, dou
   c.pednb[c.s] = b;
 }
 
+
+// ---------------------------------------------------------------------------------
+// Cell grid of a crowd scenario (one CTA per scenario, G > 256).  Every present entity is binned
+// by its pose position into a 64 x 64 toroidal grid of cell size cs = r (1 + 1e-6):
+//   * pedestrian sensors: a neighbour strictly inside the 64-gon of circumradius r lies in the
+//     3 x 3 cells around the pedestrian;
+//   * broad phase: entities whose AABB reaches at most cs/2 from their position ("small") can
+//     only overlap small entities in the 3 x 3 cells around them; the few large ones are kept
+//     in a list that every entity tests against.
+// Aliasing through the wrap only adds candidates, and the fp32 box tests applied to the
+// candidates are the ones the exhaustive sweeps use, so the outcomes are identical.  O(M) per
+// tick instead of O(M^2).
+// ---------------------------------------------------------------------------------
+struct GridPos {
+  int ix, iy;
+  bool large;
+};
+
+SG_DEV uint32_t grid_start(const uint32_t* gs, int cell) {  // cell in [0, SG_GRID_CELLS]
+  const uint32_t w = gs[cell >> 1];
+  return (cell & 1) ? (w >> 16) : (w & 0xffffu);
+}
+
+// up to two index ranges of gsorted that hold the cells (ix-1 .. ix+1, row iy + dy)
+SG_DEV int grid_row_ranges(const uint32_t* gs, int ix, int iy, int dy, int beg[2], int end[2]) {
+  const int row = ((iy + dy) & (SG_GRID_DIM - 1)) << SG_GRID_BITS;
+  const int a = (ix - 1) & (SG_GRID_DIM - 1), b = (ix + 1) & (SG_GRID_DIM - 1);
+  if (a < b) {
+    beg[0] = (int)grid_start(gs, row | a); end[0] = (int)grid_start(gs, (row | b) + 1);
+    return 1;
+  }
+  beg[0] = (int)grid_start(gs, row | a); end[0] = (int)grid_start(gs, row + SG_GRID_DIM);
+  beg[1] = (int)grid_start(gs, row);     end[1] = (int)grid_start(gs, (row | b) + 1);
+  return 2;
+}
+
+// All G threads of the scenario's CTA call this (it synchronises the group).
+SG_DEV GridPos grid_build(const Grp& c, bool present, bool have_box, double x, double y, double ox,
+                          double oy, double cs, double inv_cs) {
+  uint32_t* gs = c.gstart;
+  const int nwords = SG_GRID_CELLS / 2;  // two 16-bit cells per word; word nwords holds the end
+  for (int q = c.s; q <= nwords; q += c.G) gs[q] = 0;
+  if (c.s == 0) c.gmisc[0] = 0;
+  group_sync(c);
+  GridPos g;
+  g.ix = 0; g.iy = 0; g.large = false;
+  int cell = 0;
+  uint32_t rank = 0;
+  if (present) {
+    const double px = x - ox, py = y - oy;
+    g.ix = __double2int_rd(px * inv_cs);
+    g.iy = __double2int_rd(py * inv_cs);
+    cell = ((g.iy & (SG_GRID_DIM - 1)) << SG_GRID_BITS) | (g.ix & (SG_GRID_DIM - 1));
+    if (have_box) {
+      const float4 bb = c.aabb[c.s];
+      const double reach = fmax(fmax(px - (double)bb.x, (double)bb.z - px),
+                                fmax(py - (double)bb.y, (double)bb.w - py));
+      g.large = !(reach <= 0.5 * cs * (1.0 - 1e-6));
+      if (g.large) {
+        const int k = atomicAdd(&c.gmisc[0], 1);
+        if (k < SG_GRID_LCAP) c.glarge[k] = (uint16_t)c.s;
+      }
+    }
+    const uint32_t old = atomicAdd(&gs[cell >> 1], (cell & 1) ? 0x10000u : 1u);
+    rank = (cell & 1) ? (old >> 16) : (old & 0xffffu);
+  }
+  group_sync(c);
+  // exclusive scan of the packed counts: thread s owns wpt consecutive words
+  const int wpt = (nwords + c.G - 1) / c.G;
+  const int w0 = c.s * wpt;
+  uint32_t local = 0;
+  for (int q = 0; q < wpt; ++q)
+    if (w0 + q < nwords) { const uint32_t v = gs[w0 + q]; local += (v & 0xffffu) + (v >> 16); }
+  const int lane = threadIdx.x & 31, wid = c.s >> 5;
+  uint32_t incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) c.gmisc[8 + wid] = (int)incl;
+  group_sync(c);
+  uint32_t wt = lane < (c.G >> 5) ? (uint32_t)c.gmisc[8 + lane] : 0u, wi = wt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+    if (lane >= d) wi += o;
+  }
+  const uint32_t wbase = __shfl_sync(0xffffffffu, wi - wt, wid);
+  const uint32_t total = __shfl_sync(0xffffffffu, wi, 31);
+  uint32_t run = wbase + incl - local;
+  for (int q = 0; q < wpt; ++q)
+    if (w0 + q < nwords) {
+      const uint32_t v = gs[w0 + q], lo = v & 0xffffu, hi = v >> 16;
+      gs[w0 + q] = run | ((run + lo) << 16);
+      run += lo + hi;
+    }
+  if (c.s == 0) gs[nwords] = total;
+  group_sync(c);
+  if (present)
+    c.gsorted[grid_start(gs, cell) + rank] = (uint16_t)((uint32_t)c.s | (g.large ? SG_GRID_LARGE : 0u));
+  group_sync(c);
+  return g;
+}
+
+// broad phase through the grid: every unordered pair whose conservative AABBs overlap is queued
+// exactly once (small-small by the lower slot, small-large by the small one, large-large by the
+// lower slot).  Falls back to the exhaustive half sweep when the large list overflowed.
+SG_DEV void broad_phase(const Grp& c, int parity);
+SG_DEV void broad_phase_grid(const Grp& c, int parity, const GridPos& g) {
+  const int nl = c.gmisc[0];
+  if (nl > SG_GRID_LCAP) { broad_phase(c, parity); return; }
+  const float4 mb = c.aabb[c.s];
+  int* acc = c.acc + parity * ACC_N;
+  auto test = [&](int o) {
+    const float4 ob = c.aabb[o];
+    if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) {
+      const int q = atomicAdd(&acc[ACC_QCOUNT], 1);
+      if (q < c.QCAP) c.queue[q] = ((uint32_t)c.s << 16) | (uint32_t)o;
+    }
+  };
+  if (!g.large) {
+    for (int dy = -1; dy <= 1; ++dy) {
+      int beg[2], end[2];
+      const int nr = grid_row_ranges(c.gstart, g.ix, g.iy, dy, beg, end);
+      for (int r = 0; r < nr; ++r)
+        for (int idx = beg[r]; idx < end[r]; ++idx) {
+          const uint32_t o = c.gsorted[idx];
+          if (o > (uint32_t)c.s && o < SG_GRID_LARGE) test((int)o);
+        }
+    }
+  }
+  for (int k = 0; k < nl; ++k) {
+    const int o = c.glarge[k];
+    if (o == c.s || (g.large && o < c.s)) continue;
+    test(o);
+  }
+}
+
 // PedestrianAgent._step + SocialForce._step + PedestrianController._step
 template <bool PED>
 SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c,
                             const double pose[6], const double vel[6], double t, double prev_t,
                             double next_t, double sight_cos, int& goal, double force[2],
-                            double& speed_io, double out[6]) {
+                            double& speed_io, double out[6], bool use_grid, double ox, double oy,
+                            double inv_cs) {
   if (!PED) return;
   const int64_t r0 = sc.route_off[c.i];
   const int R = (int)(sc.route_off[c.i + 1] - r0);
@@ -397,33 +559,64 @@ SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c,
         F0 += Fr0; F1 += Fr1;
       }
     };
-    // sensor sweep: fp32 box prefilter over all slots in state.poses (= slot) order; candidates are
-    // first collected per thread, then the k-th candidates of all lanes are evaluated together
+    // sensor: fp32 box prefilter over the slots in state.poses (= slot) order; candidates are first
+    // collected per thread, then the k-th candidates of all lanes are evaluated together
     const float4 mb = c.pednb[c.s];
     uint16_t* nbl = c.nblist + c.s;
     int ncand = 0;
-    for (int o0 = 0; o0 < c.M; o0 += 32) {
-      uint32_t cand = 0;
+    if (use_grid) {  // candidates from the 3 x 3 cells around the pedestrian, then put in slot order
+      const int ix = __double2int_rd((pose[0] - ox) * inv_cs), iy = __double2int_rd((pose[1] - oy) * inv_cs);
+      for (int dy = -1; dy <= 1; ++dy) {
+        int beg[2], end[2];
+        const int nr = grid_row_ranges(c.gstart, ix, iy, dy, beg, end);
+        for (int r = 0; r < nr; ++r)
+          for (int idx = beg[r]; idx < end[r]; ++idx) {
+            const int o = (int)(c.gsorted[idx] & (SG_GRID_LARGE - 1u));
+            const float4 ob = c.pednb[o];
+            if (o == c.s || !(mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w)) continue;
+            if (ncand < SG_NBCAP) nbl[ncand * c.G] = (uint16_t)o;
+            ++ncand;
+          }
+      }
+      for (int a = 1; a < min(ncand, SG_NBCAP); ++a) {  // insertion sort (a handful of entries)
+        const uint16_t v = nbl[a * c.G];
+        int b = a - 1;
+        while (b >= 0 && nbl[b * c.G] > v) { nbl[(b + 1) * c.G] = nbl[b * c.G]; --b; }
+        nbl[(b + 1) * c.G] = v;
+      }
+      if (ncand <= SG_NBCAP) {
+        for (int k = 0; k < ncand; ++k) add_neighbour(nbl[k * c.G]);
+      } else {  // very dense crowd: exhaustive sweep in slot order
+        for (int o = 0; o < c.M; ++o) {
+          const float4 ob = c.pednb[o];
+          if (o == c.s || !(mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w)) continue;
+          add_neighbour(o);
+        }
+      }
+    } else {
+      for (int o0 = 0; o0 < c.M; o0 += 32) {
+        uint32_t cand = 0;
 #pragma unroll
-      for (int oo = 0; oo < 32; ++oo) {  // pednb is padded with empty boxes beyond M
-        const float4 ob = c.pednb[o0 + oo];
-        SG_AABB_TEST(cand, mb, ob, 1u << oo);
+        for (int oo = 0; oo < 32; ++oo) {  // pednb is padded with empty boxes beyond M
+          const float4 ob = c.pednb[o0 + oo];
+          SG_AABB_TEST(cand, mb, ob, 1u << oo);
+        }
+        if (c.s >= o0 && c.s < o0 + 32) cand &= ~(1u << (c.s - o0));
+        while (cand) {
+          const int o = o0 + __ffs(cand) - 1;
+          cand &= cand - 1;
+          if (ncand < SG_NBCAP) nbl[ncand * c.G] = (uint16_t)o;
+          ++ncand;
+        }
       }
-      if (c.s >= o0 && c.s < o0 + 32) cand &= ~(1u << (c.s - o0));
-      while (cand) {
-        const int o = o0 + __ffs(cand) - 1;
-        cand &= cand - 1;
-        if (ncand < SG_NBCAP) nbl[ncand * c.G] = (uint16_t)o;
-        ++ncand;
-      }
-    }
-    for (int k = 0; k < min(ncand, SG_NBCAP); ++k) add_neighbour(nbl[k * c.G]);
-    if (ncand > SG_NBCAP) {  // very dense crowd: re-sweep for the candidates beyond the list
-      int seen = 0;
-      for (int o = 0; o < c.M; ++o) {
-        const float4 ob = c.pednb[o];
-        if (o == c.s || !(mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w)) continue;
-        if (seen++ >= SG_NBCAP) add_neighbour(o);
+      for (int k = 0; k < min(ncand, SG_NBCAP); ++k) add_neighbour(nbl[k * c.G]);
+      if (ncand > SG_NBCAP) {  // very dense crowd: re-sweep for the candidates beyond the list
+        int seen = 0;
+        for (int o = 0; o < c.M; ++o) {
+          const float4 ob = c.pednb[o];
+          if (o == c.s || !(mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w)) continue;
+          if (seen++ >= SG_NBCAP) add_neighbour(o);
+        }
       }
     }
     speed = py_min(norm2(F0, F1) + p.sf_bias_lon, speed_desired * p.sf_max_speed_factor);
@@ -1285,10 +1478,16 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   }
   load_cold(st, c, n, s, W, ego_slot);
   if (RSS && s == ego_slot) publish_ego_box(c);
+  // crowd scenarios (one CTA per scenario) bin their entities into a cell grid of the sensor radius
+  const bool use_grid = PED && L.grid != 0;
+  const double grid_cs = p.ped_distance_threshold * (1.0 + 1e-6), grid_inv_cs = 1.0 / grid_cs;
+  GridPos gpos;
+  gpos.ix = 0; gpos.iy = 0; gpos.large = false;
   if (PED) {  // the "old" state the pedestrians' sensors read in the first tick
     if (live) stage_ped_state(c, e.present, etype, e.pose[0], e.pose[1], e.vel[0], e.vel[1],
                               p.ped_distance_threshold, ox, oy);
     for (int q = s; q < 32; q += G) c.pednb[M + q] = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+    if (use_grid) gpos = grid_build(c, live && e.present, false, e.pose[0], e.pose[1], ox, oy, grid_cs, grid_inv_cs);
   }
   group_sync(c);
 
@@ -1355,7 +1554,7 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
           newpres = true;
         } else if (kind == SG_KIND_PEDESTRIAN) {
           pedestrian_step<PED>(sc, p, c, e.pose, e.vel, t, prev_t, next_t, sight_cos, goal, force,
-                               newspeed, np_);
+                               newspeed, np_, use_grid, ox, oy, grid_inv_cs);
           newpres = true;
         } else {  // SG_KIND_HOST
           if (in.host_present && in.host_present[i]) {
@@ -1458,7 +1657,11 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
           if (found) atomicOr(&c.acc[parity * ACC_N + ACC_RSS], found == 2 ? 1 : 2);
         }
       }
-      if (need_coll && e.present) broad_phase(c, parity);
+      if (need_coll && e.present && !use_grid) broad_phase(c, parity);
+    }
+    if (PED && use_grid) {  // bin the new positions: this tick's broad phase and the next tick's sensors
+      gpos = grid_build(c, live && e.present, need_coll, e.pose[0], e.pose[1], ox, oy, grid_cs, grid_inv_cs);
+      if (need_coll && live && e.present) broad_phase_grid(c, parity, gpos);
     }
     group_sync(c);
     done = finish_tick(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick, t, dt, length, live,
@@ -1685,7 +1888,10 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
   const bool rss = (p->features & SG_FEAT_RSS) != 0;
   const uint32_t veh_bits = (1u << SG_KIND_VEHICLE), ok_bits = veh_bits | (1u << SG_KIND_EMPTY);
   const bool veh_only = (sc->kind_mask & veh_bits) && !(sc->kind_mask & ~ok_bits);
-  GroupLayout L = make_layout(sc->n_slots, ped, rss, veh_only);
+  const bool grid_ok = ped && p->ped_distance_threshold > 0.0 && p->ped_distance_threshold < 1.0e6 &&
+                       !(p->features & SG_FEAT_NO_GRID);
+  GroupLayout L = make_layout(sc->n_slots, ped, rss, veh_only, grid_ok);
+  if (L.grid && (size_t)L.bytes > 227 * 1024) L = make_layout(sc->n_slots, ped, rss, veh_only, false);
   const int threads = L.G <= SG_THREADS ? SG_THREADS : L.G;
   const bool big = threads > SG_THREADS;
   const int gpb = threads / L.G;

@@ -253,6 +253,51 @@ def test_big_group_vs_oracle():
     compare_engines(gpu, cpu, scene, "crowd M=320", check_ped=True)
 
 
+def _final_arrays(eng):
+    keys = ("tick", "done", "present", "collided", "first_coll_tick", "first_coll_pair", "n_pair_ticks",
+            "ego_hits", "t", "pose", "vel", "dist", "speed", "goal_idx", "force", "ego_avg_speed")
+    return {k: eng.get(k).copy() for k in keys}
+
+
+@pytest.mark.parametrize("case", ["sparse", "dense", "wrap", "large"])
+def test_crowd_cell_grid(case):
+    """
+    Crowd scenarios with one CTA per scenario bin their entities into a shared-memory cell grid
+    (sensor neighbours + collision broad phase).  The grid must change nothing: bit-identical to the
+    exhaustive sweeps (FEAT_NO_GRID) and within tolerance of the CPU oracle.
+      dense: more candidates than the per-pedestrian list holds; wrap: scene wider than the 64-cell
+      torus; large: several vehicles too big for a cell walk through the crowd.
+    """
+    if case == "sparse":
+        cfg = synthetic.crowd_config(seed=11, N=3, M=1024, T=10, side=40.0)
+    elif case == "dense":
+        cfg = synthetic.crowd_config(seed=12, N=2, M=288, T=8, side=5.0)
+    elif case == "wrap":
+        cfg = synthetic.crowd_config(seed=13, N=2, M=512, T=10, side=150.0)
+        # clusters one torus period (64 cells of 1 m) apart alias into the same cells
+        cfg.x0[:, 1::2] = cfg.x0[:, 1::2] % 8.0
+        cfg.x0[:, 2::2] = cfg.x0[:, 2::2] % 8.0 + 64.0
+        cfg.y0[:, 1:] = cfg.y0[:, 1:] % 12.0
+    else:
+        cfg = synthetic.crowd_config(seed=14, N=2, M=400, T=12, side=14.0)
+        for k in range(1, 9):  # pedestrians with car-sized boxes standing in the crowd
+            cfg.box[:, k] = synthetic.CAR1_BOX
+    scene = pack_synthetic(cfg)
+    p = _params(timestep=cfg.dt)
+    gpu, cpu = _run_both(scene, p)
+    compare_engines(gpu, cpu, scene, f"crowd grid/{case}", check_ped=True)
+    assert int(cpu.get("n_pair_ticks").sum()) > 0, "case must exercise the broad phase"
+    q = _params(timestep=cfg.dt)
+    q.features |= abi.FEAT_NO_GRID
+    ref = make_gpu(scene, q)
+    ref.reset()
+    ref.rollout(-1)
+    a, b = _final_arrays(gpu), _final_arrays(ref)
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True) if a[k].dtype.kind == "f" else np.array_equal(a[k], b[k]), \
+            f"grid vs exhaustive sweep: {k} differs"
+
+
 def test_c2_replicas_identical():
     """C2: replicas of the test scenarios are bit-identical copies => identical results per file."""
     specs = [s for _, s, _, _ in XOSC]
