@@ -63,8 +63,11 @@ enum SgFeature {
   SG_FEAT_EGO_METRICS = 2,  /* EgoAvgSpeed/EgoMaxSpeed/EgoDistanceTravelled, a11 */
   SG_FEAT_RSS = 4,          /* RSSDistances callback + RSS metric, a13-a14 */
   SG_FEAT_COLL_MATRIX = 8,  /* also write the per-tick pair matrix SgState.coll_mask */
-  SG_FEAT_NO_GRID = 16      /* crowd scenarios: exhaustive O(M^2) sensor / broad-phase sweeps instead of
+  SG_FEAT_NO_GRID = 16,     /* crowd scenarios: exhaustive O(M^2) sensor / broad-phase sweeps instead of
                                the shared-memory cell grid (same results; kept for cross-checks) */
+  SG_FEAT_SEQUENTIAL = 32   /* replay-only scenes: walk the ticks one after another instead of the
+                               tick-parallel kernel (same results up to the summation order of the
+                               distances; kept for cross-checks) */
 };
 
 /* record codes appended to RSSDistances.intersect[e] (rss/callback.py:168-228,304-338) */

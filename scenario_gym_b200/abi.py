@@ -20,7 +20,7 @@ ETYPE_VEHICLE, ETYPE_PEDESTRIAN, ETYPE_MISC = range(3)
 # SgTerminal
 TERM_MAX_LENGTH, TERM_COLLISION, TERM_EGO_COLLISION = 1, 2, 4
 # SgFeature
-FEAT_COLLISIONS, FEAT_EGO_METRICS, FEAT_RSS, FEAT_COLL_MATRIX, FEAT_NO_GRID = 1, 2, 4, 8, 16
+FEAT_COLLISIONS, FEAT_EGO_METRICS, FEAT_RSS, FEAT_COLL_MATRIX, FEAT_NO_GRID, FEAT_SEQUENTIAL = 1, 2, 4, 8, 16, 32
 # SgRssRecord
 RSS_RECORD_NAMES = {
     0: "safe",

@@ -1810,6 +1810,8 @@ __global__ void sg_box_pairs_kernel(const double* pa, const double* ba, const do
   out[i] = !same && quads_intersect(A, quad_orientation(A), B, quad_orientation(B));
 }
 
+#include "sg_replay.cuh"
+
 // ---------------------------------------------------------------------------------
 static bool g_ngon_ready[64] = {false};
 
@@ -1908,6 +1910,24 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
   SgInputs none;
   memset(&none, 0, sizeof(none));
   const SgInputs inp = in ? *in : none;
+  // replay-only scenes (every slot a BatchReplayEntity or ReplayTrajectoryAgent) rolled out for
+  // several ticks: the tick-parallel kernel (sg_replay.cuh)
+  const uint32_t replay_bits = (1u << SG_KIND_EMPTY) | (1u << SG_KIND_REPLAY) | (1u << SG_KIND_AGENT_REPLAY);
+  const bool replay_only = sc->kind_mask != 0 && !(sc->kind_mask & ~replay_bits) &&
+                           (sc->kind_mask & ~(1u << SG_KIND_EMPTY));
+  if (replay_only && !rss && !ped && sc->n_slots <= 32 && st->trace_cap == 0 && !inp.step_done &&
+      !inp.actions && !inp.host_present && p->timestep > 0.0 && (n_ticks < 0 || n_ticks >= 8) &&
+      !(p->features & SG_FEAT_SEQUENTIAL)) {
+    const size_t rsm = replay_smem_bytes(sc->n_slots);
+    if (rsm > 48 * 1024) {
+      err = cudaFuncSetAttribute(sg_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+      if (err != cudaSuccess) return set_err("cudaFuncSetAttribute", err);
+    }
+    sg_replay_kernel<<<sc->n_scenarios, SG_RP_THREADS, rsm, s>>>(*sc, *p, *st, n_ticks);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return set_err("sg_replay_kernel launch", err);
+    return 0;
+  }
   if (veh_only) {
     if (!inp.actions) return set_msg("vehicle scene needs an action table");
     err = rss ? launch_vehicle<true>(sc->n_scenarios, s, *sc, *p, *st, inp, n_ticks, L)

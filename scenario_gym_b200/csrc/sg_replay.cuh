@@ -1,0 +1,482 @@
+// sg_replay.cuh -- tick-parallel rollout of replay-only scenes (C1 / C2).
+//
+// When every slot of a scene is a BatchReplayEntity (entity/batch.py:34-128) or a
+// ReplayTrajectoryAgent (agent.py:118-128), nothing a tick computes depends on the previous tick's
+// *poses*: poses and presence are pure functions of the tick times, and the only cross-tick
+// state is a handful of running reductions (tick times, distance, EgoAvgSpeed, the previous
+// tick's ego collision row).  So instead of walking the ticks of a scenario one after another
+// (latency bound: ~700 dependent ticks, a third of the lanes active), one CTA takes a scenario and
+// its threads take 128 consecutive TICKS at a time:
+//   1  thread 0 extends the tick times by repeated addition (scenario_gym.py:229 - the running
+//      fp64 sum is part of the reference's results) and applies `max_length`;
+//   2  every thread evaluates its tick: poses at t_k and t_{k-1} of all slots (uniform loops over
+//      the slots: no divergence between entity kinds), distance increments, ego speed, staged
+//      conservative fp32 AABBs, the pair sweep and (rarely) the exact narrow phase;
+//   3  the chunk is committed: ordered reductions over the ticks (distance, EgoAvgSpeed recurrence
+//      with the same operation order as metrics/trajectory.py:20-24, collision rising edges,
+//      first collision, terminal conditions) and the State rows of the entities that left / the
+//      final tick.
+// Results equal the sequential kernel's bit for bit except the accumulated distances, which are
+// summed as a fixed tree over the ticks (<= 1e-15 relative, deterministic).
+#pragma once
+
+#define SG_RP_THREADS 128
+#define SG_RP_WARPS (SG_RP_THREADS / 32)
+
+struct RpUnion {  // position of a time in the scenario's union-knot table
+  int mode;       // 0: before the first knot, 1: after the last, 2: interpolate rows cur-1, cur
+  int cur;
+  double w1, w0;
+};
+
+SG_DEV RpUnion rp_union_weights(const double* __restrict__ ts, int UK, double t) {
+  RpUnion u;
+  u.mode = 0; u.cur = 1; u.w1 = 0.0; u.w0 = 0.0;
+  if (UK <= 0 || t < __ldg(ts)) return u;  // fill_value = (X[0], X[-1]), entity/batch.py:120-127
+  if (t > __ldg(ts + UK - 1)) { u.mode = 1; return u; }
+  u.mode = 2;
+  u.cur = min(max(search_left(ts, 1, UK, t), 1), UK - 1);
+  const double x_lo = __ldg(ts + u.cur - 1), x_hi = __ldg(ts + u.cur);
+  u.w1 = (t - x_lo) / (x_hi - x_lo);
+  u.w0 = (x_hi - t) / (x_hi - x_lo);
+  return u;
+}
+SG_DEV double rp_union_value(const RpUnion& u, const double* __restrict__ X, int UK, int M, int s, int f) {
+  if (u.mode == 0) return __ldg(X + f * M + s);
+  if (u.mode == 1) return __ldg(X + ((int64_t)(UK - 1) * 6 + f) * M + s);
+  const double* lo = X + (int64_t)(u.cur - 1) * 6 * M + s;
+  return u.w1 * __ldg(lo + (6 + f) * M) + u.w0 * __ldg(lo + f * M);
+}
+
+struct RpSlot {
+  int kind, K;
+  const double* rows;
+  double tmin, tmax;
+};
+SG_DEV RpSlot rp_slot(const SgScene& sc, int64_t i) {
+  RpSlot e;
+  e.kind = sc.kind[i];
+  const int64_t r0 = sc.traj_off[i];
+  e.K = (int)(sc.traj_off[i + 1] - r0);
+  e.rows = sc.traj_rows + r0 * 7;
+  e.tmin = e.K ? __ldg(e.rows) : 0.0;
+  e.tmax = e.K ? __ldg(e.rows + (int64_t)(e.K - 1) * 7) : 0.0;
+  return e;
+}
+// presence after a tick to time tau (scenario_gym.py:233-245, entity/batch.py:47-52); for an
+// agent slot `agent_pres` = present at launch or inserted by the first tick (its trajectory
+// starts at or after the launch time), which then holds for every later tick
+SG_DEV bool rp_present(const RpSlot& e, int persist, double tau, bool agent_pres) {
+  if (e.kind == SG_KIND_AGENT_REPLAY) return agent_pres;
+  return persist || e.K == 1 || (tau >= e.tmin && tau <= e.tmax);
+}
+template <int NF>
+SG_DEV void rp_pose(const RpSlot& e, const RpUnion& u, const double* __restrict__ X, int UK, int M, int s,
+                    double tau, double out[6]) {
+  if (e.kind == SG_KIND_AGENT_REPLAY) {  // agent.py:125-128, extrapolate=(False, False)
+    int cur = 0;
+    double full[6];
+    position_at_t(e.rows, e.K, tau, EXT_CLAMP, cur, full);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) out[f] = full[f];
+  } else {
+#pragma unroll
+    for (int f = 0; f < NF; ++f) out[f] = rp_union_value(u, X, UK, M, s, f);
+  }
+}
+
+struct RpCtx {  // per-scenario constants
+  int n, M, ego_slot, first_slot, UK;
+  const double* ts;
+  const double* X;
+  double t_launch, ox, oy;
+};
+
+// full pose of slot s after the tick (tkm -> tk) and the pose State.update_poses differences it
+// against (state.py:203-239): last tick's pose, or for a newcomer its trajectory extrapolated
+// to the previous time.  `first`: the previous tick is the launch state (read from State).
+SG_DEV void rp_pose_and_prev(const SgScene& sc, const SgParams& p, const SgState& st, const RpCtx& c,
+                             const RpSlot& e, int s, bool agent_pres, double tk, double tkm, bool first,
+                             double pk[6], double prev[6]) {
+  const int64_t i = (int64_t)c.n * c.M + s, nm = (int64_t)sc.n_scenarios * c.M;
+  const RpUnion uk = rp_union_weights(c.ts, c.UK, tk);
+  rp_pose<6>(e, uk, c.X, c.UK, c.M, s, tk, pk);
+  bool ppres;
+  if (first) {
+    ppres = st.present[i] != 0;
+    if (ppres) {
+#pragma unroll
+      for (int f = 0; f < 6; ++f) prev[f] = st.pose[f * nm + i];
+    }
+  } else {
+    ppres = rp_present(e, p.persist, tkm, agent_pres);
+    if (ppres) {
+      const RpUnion um = rp_union_weights(c.ts, c.UK, tkm);
+      rp_pose<6>(e, um, c.X, c.UK, c.M, s, tkm, prev);
+    }
+  }
+  if (!ppres) {  // state.py:219-222
+    int cur = 0;
+    position_at_t(e.rows, e.K, tkm, EXT_TRUE, cur, prev);
+  }
+}
+
+// State rows of slot s as they stand after the tick (tkm -> tk); rare (once per slot per launch)
+__device__ __noinline__ void rp_write_rows(const SgScene* sc, const SgParams* p, const SgState* st,
+                                           RpCtx c, int s, bool agent_pres, double tk, double tkm,
+                                           bool first) {
+  const int64_t i = (int64_t)c.n * c.M + s, nm = (int64_t)sc->n_scenarios * c.M;
+  const RpSlot e = rp_slot(*sc, i);
+  double pk[6], prev[6];
+  rp_pose_and_prev(*sc, *p, *st, c, e, s, agent_pres, tk, tkm, first, pk, prev);
+  const double dt = tk - tkm;
+#pragma unroll
+  for (int f = 0; f < 6; ++f) {
+    st->pose[f * nm + i] = pk[f];
+    st->vel[f * nm + i] = (pk[f] - prev[f]) / dt;  // state.py:234-236
+  }
+}
+
+// fp64 corners of slot s at time tk (Entity.get_bounding_box_points, entity/base.py:100-138;
+// the same expression and libm call as publish_box) and the ring orientation
+__device__ __noinline__ Quad rp_corners(const SgScene* sc, RpCtx c, int s, double tk, int* orient) {
+  const int64_t i = (int64_t)c.n * c.M + s, nm = (int64_t)sc->n_scenarios * c.M;
+  const RpSlot e = rp_slot(*sc, i);
+  const RpUnion uk = rp_union_weights(c.ts, c.UK, tk);
+  double pk[6];
+  rp_pose<4>(e, uk, c.X, c.UK, c.M, s, tk, pk);
+  double sn, cs;
+  sincos(pk[3], &sn, &cs);
+  const double bw = sc->box[i], bl = sc->box[nm + i], bcx = sc->box[2 * nm + i], bcy = sc->box[3 * nm + i];
+  const double hx0 = bcx - 0.5 * bl, hx1 = bcx + 0.5 * bl;
+  const double hy0 = bcy + 0.5 * bw, hy1 = bcy - 0.5 * bw;
+  const double x = pk[0], y = pk[1];
+  Quad q;
+  q.x0 = x + (hx0 * cs + hy0 * -sn); q.y0 = y + (hx0 * sn + hy0 * cs);
+  q.x1 = x + (hx1 * cs + hy0 * -sn); q.y1 = y + (hx1 * sn + hy0 * cs);
+  q.x2 = x + (hx1 * cs + hy1 * -sn); q.y2 = y + (hx1 * sn + hy1 * cs);
+  q.x3 = x + (hx0 * cs + hy1 * -sn); q.y3 = y + (hx0 * sn + hy1 * cs);
+  const int hint = box_orientation_hint(bw, bl);
+  *orient = hint ? hint : quad_orientation(q);
+  return q;
+}
+
+// exact narrow phase of one AABB-surviving pair at time tk (state/utils.py:10-49, utils.py:28-62)
+__device__ __noinline__ bool rp_pair_exact(const SgScene* sc, RpCtx c, int a, int b, double tk) {
+  int oa, ob;
+  const Quad A = rp_corners(sc, c, a, tk, &oa), B = rp_corners(sc, c, b, tk, &ob);
+  const bool same = A.x0 == B.x0 && A.y0 == B.y0 && A.x1 == B.x1 && A.y1 == B.y1 && A.x2 == B.x2 &&
+                    A.y2 == B.y2 && A.x3 == B.x3 && A.y3 == B.y3;
+  if (same) return false;  // `g != g_prime`, reference utils.py:58
+  return quads_intersect(A, oa, B, ob);
+}
+
+struct RpCarry {  // cross-chunk state of the scenario (shared memory, owned by thread 0)
+  double t, prev_t, avg, avg_t, mx, last_sp;
+  long long pair_ticks;
+  int tick, executed, done, nv, first_tick, fp0, fp1, end_here;
+  uint32_t ego_last, collided, chunk_first;
+};
+
+__global__ void __launch_bounds__(SG_RP_THREADS)
+sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgParams p,
+                 const __grid_constant__ SgState st, int n_ticks) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int CH = SG_RP_THREADS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  RpCtx c;
+  c.n = blockIdx.x; c.M = sc.n_slots;
+  const int M = c.M, n = c.n;
+  const int64_t nm = (int64_t)sc.n_scenarios * M, i0 = (int64_t)n * M;
+  c.ego_slot = sc.ego_slot[n]; c.first_slot = sc.first_slot[n];
+  {
+    const int64_t u0 = sc.union_off[n];
+    c.UK = (int)(sc.union_off[n + 1] - u0);
+    c.ts = sc.union_t + u0;
+    c.X = sc.union_x + u0 * 6 * M;
+    const int64_t er = sc.traj_off[i0 + c.ego_slot];  // origin of the fp32 bounds
+    c.ox = __ldg(sc.traj_rows + er * 7 + 1);
+    c.oy = __ldg(sc.traj_rows + er * 7 + 2);
+  }
+  c.t_launch = st.t[n];
+  const bool need_coll = (p.features & SG_FEAT_COLLISIONS) ||
+                         (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
+  const bool coll_terminal = (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION)) != 0;
+  const int limit = n_ticks < 0 ? p.max_ticks : n_ticks;
+
+  // shared layout
+  double* T = (double*)smem;                         // [CH + 2] tick times of the chunk, T[0] = time before it
+  double* spv = T + CH + 2;                          // [CH] ego speed after each tick (NaN: ego absent)
+  double* cwv = spv + CH;                            // [CH] 1 - t_prev / t of EgoAvgSpeed
+  double* part = cwv + CH;                           // [SG_RP_WARPS][M] distance partial sums
+  double* cdist = part + SG_RP_WARPS * M;            // [M] accumulated distance
+  float4* aabb = (float4*)(cdist + M + (M & 1));     // [M][CH]
+  uint32_t* egonow = (uint32_t*)(aabb + (size_t)M * CH);  // [CH]
+  uint32_t* cbits = egonow + CH;                     // [CH]
+  uint32_t* fpair = cbits + CH;                      // [CH]
+  int* npairs = (int*)(fpair + CH);                  // [CH]
+  uint32_t* tflag = (uint32_t*)(npairs + CH);        // [CH] bit0: terminal condition met at this tick
+  uint8_t* apres = (uint8_t*)(tflag + CH);           // [M] agent slots: present from the first tick on
+  RpCarry* car = (RpCarry*)(apres + ((M + 15) / 16) * 16);
+
+  if (tid < M) {
+    const int64_t i = i0 + tid;
+    cdist[tid] = st.dist[i];
+    const RpSlot e = rp_slot(sc, i);
+    apres[tid] = (st.present[i] != 0) || (e.K > 0 && e.tmin >= c.t_launch);  // scenario_gym.py:240-244
+  }
+  if (tid == 0) {
+    car->t = c.t_launch; car->prev_t = st.prev_t[n];
+    car->avg = st.ego_avg_speed[n]; car->avg_t = st.ego_avg_t[n]; car->mx = st.ego_max_speed[n];
+    {
+      const int64_t ie = i0 + c.ego_slot;
+      car->last_sp = norm3(st.vel[ie], st.vel[nm + ie], st.vel[2 * nm + ie]);
+    }
+    car->pair_ticks = st.n_pair_ticks[n];
+    car->tick = st.tick[n]; car->executed = 0; car->done = st.done[n] != 0;
+    car->first_tick = st.first_coll_tick[n];
+    car->fp0 = st.first_coll_pair[2 * n]; car->fp1 = st.first_coll_pair[2 * n + 1];
+    car->ego_last = st.ego_hits[n];
+    car->collided = 0;
+  }
+  __syncthreads();
+
+  for (;;) {
+    // ---- 1: tick times of this chunk (scenario_gym.py:229; max_length, state.py:397-398) ----
+    if (tid == 0) {
+      double t = car->t, pt = car->prev_t;
+      int nv = 0, done = car->done;
+      T[0] = t;
+      while (nv < CH && car->executed + nv < limit && !done) {
+        const double nt = t + p.timestep;
+        pt = t; t = nt;
+        T[++nv] = t;
+        if ((p.terminal & SG_TERM_MAX_LENGTH) && (t + (t - pt) > sc.length[n])) done = 1;
+      }
+      T[nv + 1] = t + p.timestep;  // look-ahead for "does the entity leave at the next tick"
+      car->nv = nv;
+      car->end_here = done || car->executed + nv >= limit;
+      car->chunk_first = 0xffffffffu;
+      if (nv > 0) { car->done = done; }
+    }
+    __syncthreads();
+    int nv = car->nv;
+    if (nv == 0) break;
+    const bool first_chunk = car->executed == 0;
+
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      // ---- 2: every thread evaluates its tick ---------------------------------------------
+      const bool valid = tid < nv;
+      const double tk = valid ? T[tid + 1] : T[1], tkm = valid ? T[tid] : T[0];
+      const double dt = tk - tkm;
+      const bool first = first_chunk && tid == 0;
+      const RpUnion uk = rp_union_weights(c.ts, c.UK, tk);
+      const RpUnion um = rp_union_weights(c.ts, c.UK, tkm);
+      uint32_t pm = 0;  // present slots after this tick
+      double sp = NAN;
+      for (int s = 0; s < M; ++s) {
+        const int64_t i = i0 + s;
+        const RpSlot e = rp_slot(sc, i);
+        float4 bb = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+        double inc = 0.0;
+        if (e.kind != SG_KIND_EMPTY && valid && rp_present(e, p.persist, tk, apres[s] != 0)) {
+          pm |= 1u << s;
+          double pk[6], prev[6];
+          rp_pose<4>(e, uk, c.X, c.UK, M, s, tk, pk);
+          bool ppres;
+          if (first) {
+            ppres = st.present[i] != 0;
+            if (ppres) { prev[0] = st.pose[i]; prev[1] = st.pose[nm + i]; prev[2] = st.pose[2 * nm + i]; }
+          } else {
+            ppres = rp_present(e, p.persist, tkm, apres[s] != 0);
+            if (ppres) rp_pose<3>(e, um, c.X, c.UK, M, s, tkm, prev);
+          }
+          if (!ppres) {  // newcomer: state.py:219-222
+            int cur = 0;
+            double full[6];
+            position_at_t(e.rows, e.K, tkm, EXT_TRUE, cur, full);
+            prev[0] = full[0]; prev[1] = full[1]; prev[2] = full[2];
+          }
+          const double d0 = pk[0] - prev[0], d1 = pk[1] - prev[1], d2 = pk[2] - prev[2];
+          inc = norm3(d0, d1, d2);  // state.py:237-239
+          if (s == c.ego_slot) sp = norm3(d0 / dt, d1 / dt, d2 / dt);  // metrics/trajectory.py:21
+          if (need_coll) {
+            double sn, cs;
+            sincos(pk[3], &sn, &cs);
+            bb = make_aabb_box(pk[0], pk[1], cs, sn, sc.box[i], sc.box[nm + i], sc.box[2 * nm + i],
+                               sc.box[3 * nm + i], c.ox, c.oy);
+          }
+        }
+        if (need_coll) aabb[(size_t)s * CH + tid] = bb;
+        // distance: fixed tree over the ticks of the warp, then over the warps in order
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) inc += __shfl_xor_sync(0xffffffffu, inc, off);
+        if (lane == 0) part[warp * M + s] = inc;
+      }
+      spv[tid] = sp;
+      cwv[tid] = 1.0 - (first_chunk && tid == 0 ? car->avg_t : tkm) / tk;  // metrics/trajectory.py:20-24
+      // pair sweep on the conservative AABBs, exact narrow phase on the survivors
+      uint32_t cb = 0, en = 0, fp = 0x7fffffffu, term = 0;
+      int np = 0;
+      if (need_coll && valid) {
+        for (int a = 0; a < M; ++a) {
+          if (!((pm >> a) & 1)) continue;
+          const float4 A = aabb[(size_t)a * CH + tid];
+          for (int b = a + 1; b < M; ++b) {
+            if (!((pm >> b) & 1)) continue;
+            const float4 B = aabb[(size_t)b * CH + tid];
+            if (!(A.x <= B.z && B.x <= A.z && A.y <= B.w && B.y <= A.w)) continue;
+            if (!rp_pair_exact(&sc, c, a, b, tk)) continue;
+            ++np;
+            fp = min(fp, ((uint32_t)a << 16) | (uint32_t)b);
+            cb |= (1u << a) | (1u << b);
+            if (a == c.ego_slot) en |= 1u << b;
+            if (b == c.ego_slot) en |= 1u << a;
+            if (a == c.first_slot || b == c.first_slot) term |= 2u;
+          }
+        }
+        if ((p.terminal & SG_TERM_COLLISION) && np > 0) term |= 1u;
+        if ((p.terminal & SG_TERM_EGO_COLLISION) && (term & 2u)) term |= 1u;
+      }
+      egonow[tid] = en; cbits[tid] = cb; fpair[tid] = fp; npairs[tid] = np; tflag[tid] = term;
+      if (coll_terminal && (term & 1u)) atomicMin(&car->chunk_first, (uint32_t)tid);
+      __syncthreads();
+      if (!coll_terminal || car->chunk_first >= (uint32_t)(nv - 1)) {
+        if (coll_terminal && car->chunk_first == (uint32_t)(nv - 1) && tid == 0) { car->done = 1; car->end_here = 1; }
+        break;
+      }
+      // a collision ends the rollout inside the chunk: redo the reductions over the shorter range
+      nv = (int)car->chunk_first + 1;
+      __syncthreads();
+      if (tid == 0) { car->nv = nv; car->done = 1; car->end_here = 1; car->chunk_first = 0xffffffffu; T[nv + 1] = T[nv] + p.timestep; }
+      __syncthreads();
+    }
+    __syncthreads();
+
+    // ---- 3: commit the chunk ------------------------------------------------------------------
+    const bool valid = tid < nv;
+    const bool end_here = car->end_here != 0;
+    if (tid < M) {
+      double d = cdist[tid];
+#pragma unroll
+      for (int w = 0; w < SG_RP_WARPS; ++w) d += part[w * M + tid];
+      cdist[tid] = d;
+    }
+    if (need_coll) {
+      uint32_t cb = valid ? cbits[tid] : 0u;
+      cb = __reduce_or_sync(0xffffffffu, cb);
+      int np = valid ? npairs[tid] : 0;
+      np = __reduce_add_sync(0xffffffffu, np);
+      const uint32_t hit = __ballot_sync(0xffffffffu, valid && npairs[tid] > 0);
+      if (lane == 0) {
+        if (cb) atomicOr(&car->collided, cb);
+        if (np) atomicAdd((unsigned long long*)&car->pair_ticks, (unsigned long long)np);
+        if (hit) atomicMin(&car->chunk_first, (uint32_t)(warp * 32 + __ffs(hit) - 1));
+      }
+      if ((p.features & SG_FEAT_COLLISIONS) && valid) {  // CollisionMetric._step, metrics/collision.py:70-75
+        uint32_t fresh = egonow[tid] & ~(tid ? egonow[tid - 1] : car->ego_last);
+        while (fresh) {
+          const int b = __ffs(fresh) - 1;
+          fresh &= fresh - 1;
+          const int slot = atomicAdd(st.event_count, 1);
+          if (slot < st.event_cap) {
+            SgEvent ev;
+            ev.scenario = n; ev.tick = car->tick + tid + 1; ev.slot = b; ev._pad = 0; ev.t = T[tid + 1];
+            st.events[slot] = ev;
+          }
+        }
+      }
+    }
+    // State rows of the slots that are present now and not after the next tick (or at the end)
+    if (valid) {
+      const double tk = T[tid + 1], tkm = T[tid], tkn = T[tid + 2];
+      const bool first = first_chunk && tid == 0;
+      const bool is_end = end_here && tid == nv - 1;
+      for (int s = 0; s < M; ++s) {
+        const int64_t i = i0 + s;
+        const RpSlot e = rp_slot(sc, i);
+        const bool ap = apres[s] != 0;
+        const bool pres = e.kind != SG_KIND_EMPTY && rp_present(e, p.persist, tk, ap);
+        if (pres && (is_end || !rp_present(e, p.persist, tkn, ap)))
+          rp_write_rows(&sc, &p, &st, c, s, ap, tk, tkm, first);
+        if (is_end) { st.present[i] = pres; st.cur_own[i] = 1; }
+      }
+      if (is_end && (p.features & SG_FEAT_COLL_MATRIX)) {  // pair matrix of the final tick
+        uint32_t* rows = st.coll_mask + i0;  // W = 1
+        for (int s = 0; s < M; ++s) rows[s] = 0;
+        uint32_t pm = 0;
+        for (int s = 0; s < M; ++s) {
+          const RpSlot e = rp_slot(sc, i0 + s);
+          if (e.kind != SG_KIND_EMPTY && rp_present(e, p.persist, tk, apres[s] != 0)) pm |= 1u << s;
+        }
+        if (need_coll)
+          for (int a = 0; a < M; ++a) {
+            if (!((pm >> a) & 1)) continue;
+            const float4 A = aabb[(size_t)a * CH + tid];
+            for (int b = a + 1; b < M; ++b) {
+              if (!((pm >> b) & 1)) continue;
+              const float4 B = aabb[(size_t)b * CH + tid];
+              if (!(A.x <= B.z && B.x <= A.z && A.y <= B.w && B.y <= A.w)) continue;
+              if (!rp_pair_exact(&sc, c, a, b, tk)) continue;
+              rows[a] |= 1u << b;
+              rows[b] |= 1u << a;
+            }
+          }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (p.features & SG_FEAT_EGO_METRICS) {  // metrics/trajectory.py:20-24, 39-42: in tick order
+        double avg = car->avg, mx = car->mx, last = car->last_sp;
+        for (int j = 0; j < nv; ++j) {
+          double sp = spv[j];
+          if (sp != sp) sp = last; else last = sp;  // ego absent: its velocity is unchanged
+          avg += cwv[j] * (sp - avg);
+          mx = fmax(sp, mx);
+        }
+        car->avg = avg; car->mx = mx; car->last_sp = last; car->avg_t = T[nv];
+      }
+      if (need_coll && car->first_tick < 0 && car->chunk_first != 0xffffffffu) {
+        const int j = (int)car->chunk_first;
+        car->first_tick = car->tick + j + 1;
+        car->fp0 = (int)(fpair[j] >> 16); car->fp1 = (int)(fpair[j] & 0xffffu);
+      }
+      if (p.features & SG_FEAT_COLLISIONS) car->ego_last = egonow[nv - 1];
+      car->t = T[nv]; car->prev_t = T[nv - 1];
+      car->tick += nv; car->executed += nv;
+    }
+    __syncthreads();
+    if (car->end_here) break;
+  }
+
+  // ---- per-scenario results ---------------------------------------------------------------------
+  if (car->executed > 0) {
+    if (tid < M) {
+      const int64_t i = i0 + tid;
+      st.dist[i] = cdist[tid];
+      if ((car->collided >> tid) & 1) st.collided[i] = 1;
+    }
+    if (tid == 0) {
+      st.t[n] = car->t; st.prev_t[n] = car->prev_t; st.tick[n] = car->tick; st.done[n] = car->done;
+      st.cur_union[n] = 1;
+      if (p.features & SG_FEAT_EGO_METRICS) {
+        st.ego_avg_speed[n] = car->avg; st.ego_avg_t[n] = car->avg_t; st.ego_max_speed[n] = car->mx;
+        st.ego_dist[n] = cdist[c.ego_slot];
+      }
+      st.first_coll_tick[n] = car->first_tick;
+      st.first_coll_pair[2 * n] = car->fp0; st.first_coll_pair[2 * n + 1] = car->fp1;
+      st.n_pair_ticks[n] = car->pair_ticks;
+      st.ego_hits[n] = car->ego_last;
+    }
+  }
+}
+
+static size_t replay_smem_bytes(int M) {
+  const int CH = SG_RP_THREADS;
+  size_t o = (size_t)(CH + 2 + CH + CH + SG_RP_WARPS * M + M + (M & 1)) * sizeof(double);
+  o += (size_t)M * CH * sizeof(float4);
+  o += (size_t)CH * 5 * sizeof(uint32_t);
+  o += (size_t)((M + 15) / 16) * 16;
+  o += sizeof(RpCarry) + 16;
+  return o;
+}

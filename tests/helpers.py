@@ -147,6 +147,24 @@ def check_against_golden(make_engine, scene: PackedScene, params, out: Dict[str,
             assert ev_t[(int(t), int(inv[j]))] == float(tt)
     final_fused = {k: eng.get(k).copy() for k in ("pose", "vel", "dist", "t", "tick", "ego_avg_speed")}
 
+    # (a') fused rollout without a trace: replay-only scenes take the tick-parallel kernel, whose
+    # results must equal the sequential kernel's bit for bit, except the accumulated distances
+    # (fixed summation tree over the ticks: tolerance)
+    disc = ("tick", "done", "present", "collided", "first_coll_tick", "first_coll_pair", "n_pair_ticks",
+            "ego_hits", "t", "prev_t", "pose", "vel", "ego_avg_speed", "ego_max_speed", "speed")
+    seq = {k: eng.get(k).copy() for k in disc + ("dist", "ego_dist")}
+    seq_ev = eng.events()
+    par = make_engine(scene, params, trace_cap=0)
+    par.reset()
+    par.rollout(-1, actions=actions)
+    for k in disc:
+        assert np.array_equal(par.get(k), seq[k], equal_nan=True), f"trace-free fused rollout: {k} differs"
+    close(par.get("dist"), seq["dist"], "trace-free fused rollout: dist")
+    close(par.get("ego_dist"), seq["ego_dist"], "trace-free fused rollout: ego_dist")
+    pe = par.events()
+    key = lambda e: sorted(zip(e["scenario"].tolist(), e["tick"].tolist(), e["slot"].tolist(), e["t"].tolist()))
+    assert key(pe) == key(seq_ev), "trace-free fused rollout: events differ"
+
     # (b) tick by tick with the pair matrix
     eng = make_engine(scene, params, trace_cap=0)
     eng.reset()

@@ -298,6 +298,48 @@ def test_crowd_cell_grid(case):
             f"grid vs exhaustive sweep: {k} differs"
 
 
+_RP_DISC = ("tick", "done", "present", "collided", "first_coll_tick", "first_coll_pair", "n_pair_ticks",
+            "ego_hits", "t", "prev_t", "pose", "vel", "ego_avg_speed", "ego_max_speed", "coll_mask")
+
+
+@pytest.mark.parametrize("terminal", ["max_length", "collision", "ego_collision"])
+@pytest.mark.parametrize("calls", [(-1,), (50, 37, -1), (130, 8, 300, -1)])
+@pytest.mark.parametrize("persist", [0, 1])
+def test_replay_tick_parallel_equals_sequential(terminal, calls, persist):
+    """
+    Replay-only scenes are rolled out by the tick-parallel kernel (one thread per tick); it must give
+    the sequential kernel's (FEAT_SEQUENTIAL) results bit for bit -- poses, velocities, tick times,
+    collisions, events, ego metrics -- for whole and partial rollouts and for every terminal
+    condition; only the accumulated distances are summed in a different (fixed) order.
+    """
+    specs = [s for _, s, _, _ in XOSC] + [s for _, s, _, _ in all_xosc_specs("xosc_norelabel")]
+    scene = pack_scenarios(specs)
+    term = {"max_length": abi.TERM_MAX_LENGTH, "collision": abi.TERM_MAX_LENGTH | abi.TERM_COLLISION,
+            "ego_collision": abi.TERM_MAX_LENGTH | abi.TERM_EGO_COLLISION}[terminal]
+    engines = []
+    for seq in (False, True):
+        p = _params(terminal=term, persist=persist)
+        if seq:
+            p.features |= abi.FEAT_SEQUENTIAL
+        eng = make_gpu(scene, p)
+        eng.reset()
+        for k in calls:
+            eng.rollout(k)
+        engines.append(eng)
+    par, seq = engines
+    assert bool(seq.get("done").all())
+    if terminal != "max_length":
+        assert int((seq.get("first_coll_tick") >= 0).sum()) > 0, "case must end some rollouts early"
+    for k in _RP_DISC:
+        assert np.array_equal(par.get(k), seq.get(k), equal_nan=True), f"{k} differs"
+    close(par.get("dist"), seq.get("dist"), "dist")
+    close(par.get("ego_dist"), seq.get("ego_dist"), "ego_dist")
+    a, b = par.events(), seq.events()
+    assert len(a) == len(b)
+    for f in ("scenario", "tick", "slot", "t"):
+        assert np.array_equal(a[f], b[f]), f"event {f} differs"
+
+
 def test_c2_replicas_identical():
     """C2: replicas of the test scenarios are bit-identical copies => identical results per file."""
     specs = [s for _, s, _, _ in XOSC]
