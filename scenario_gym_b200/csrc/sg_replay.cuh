@@ -6,12 +6,14 @@
 // state is a handful of running reductions (tick times, distance, EgoAvgSpeed, the previous
 // tick's ego collision row).  So instead of walking the ticks of a scenario one after another
 // (latency bound: ~700 dependent ticks, a third of the lanes active), one CTA takes a scenario and
-// its threads take 128 consecutive TICKS at a time:
-//   1  thread 0 extends the tick times by repeated addition (scenario_gym.py:229 - the running
-//      fp64 sum is part of the reference's results) and applies `max_length`;
-//   2  every thread evaluates its tick: poses at t_k and t_{k-1} of all slots (uniform loops over
-//      the slots: no divergence between entity kinds), distance increments, ego speed, staged
-//      conservative fp32 AABBs, the pair sweep and (rarely) the exact narrow phase;
+// its threads take 124 consecutive TICKS at a time:
+//   1  one thread extends the tick times by repeated addition (scenario_gym.py:229 - the running
+//      fp64 sum is part of the reference's results) while the previous chunk is committed;
+//      `max_length` is then decided for all ticks of the chunk at once;
+//   2  every thread evaluates its time: presence and poses of all slots (uniform loops over the
+//      slots: no divergence between entity kinds; the previous pose comes from the neighbouring
+//      lane), distance increments, ego speed, staged conservative fp32 AABBs, the pair sweep and
+//      (rarely) the exact narrow phase;
 //   3  the chunk is committed: ordered reductions over the ticks (distance, EgoAvgSpeed recurrence
 //      with the same operation order as metrics/trajectory.py:20-24, collision rising edges,
 //      first collision, terminal conditions) and the State rows of the entities that left / the
@@ -22,6 +24,9 @@
 
 #define SG_RP_THREADS 128
 #define SG_RP_WARPS (SG_RP_THREADS / 32)
+// Lane 0 of every warp only supplies the pose "before" the warp's first tick (what lane l - 1
+// computed is the previous pose of lane l), so a warp advances 31 ticks and a chunk 124.
+#define SG_RP_TPC (SG_RP_WARPS * 31)
 
 struct RpUnion {  // position of a time in the scenario's union-knot table
   int mode;       // 0: before the first knot, 1: after the last, 2: interpolate rows cur-1, cur
@@ -171,19 +176,41 @@ __device__ __noinline__ bool rp_pair_exact(const SgScene* sc, RpCtx c, int a, in
   return quads_intersect(A, oa, B, ob);
 }
 
-struct RpCarry {  // cross-chunk state of the scenario (shared memory, owned by thread 0)
-  double t, prev_t, avg, avg_t, mx, last_sp;
+// out-of-line so that the tick loop carries one copy of the control-point search
+__device__ __noinline__ double4 rp_agent_pose4(const double* rows, int K, double t, int mode) {
+  int cur = 0;
+  double full[6];
+  position_at_t(rows, K, t, mode, cur, full);
+  return make_double4(full[0], full[1], full[2], full[3]);
+}
+__device__ __noinline__ RpUnion rp_union_weights_ool(const double* ts, int UK, double t) {
+  return rp_union_weights(ts, UK, t);
+}
+
+struct RpDesc {  // per-slot constants staged in shared memory
+  const double* rows;
+  double tmin, tmax, bw, bl, bcx, bcy;
+  int K, kind;
+};
+SG_DEV bool rp_present_d(const RpDesc& e, int persist, double tau, bool agent_pres) {
+  if (e.kind == SG_KIND_AGENT_REPLAY) return agent_pres;
+  return persist || e.K == 1 || (tau >= e.tmin && tau <= e.tmax);
+}
+
+struct RpCarry {  // cross-chunk state of the scenario (shared memory)
+  double avg, avg_t, mx, last_sp;
   long long pair_ticks;
-  int tick, executed, done, nv, first_tick, fp0, fp1, end_here;
-  uint32_t ego_last, collided, chunk_first;
+  int tick, executed, done, cnt, nv, first_tick, fp0, fp1, end_here, buf;
+  uint32_t collided, chunk_first, term_first;
 };
 
 __global__ void __launch_bounds__(SG_RP_THREADS)
 sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgParams p,
                  const __grid_constant__ SgState st, int n_ticks) {
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int CH = SG_RP_THREADS;
+  constexpr int CH = SG_RP_THREADS, TPC = SG_RP_TPC, TS = TPC + 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = 31 * warp + lane;  // time index inside the chunk: T[j]; lanes >= 1 own tick j
   RpCtx c;
   c.n = blockIdx.x; c.M = sc.n_slots;
   const int M = c.M, n = c.n;
@@ -203,20 +230,21 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
                          (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
   const bool coll_terminal = (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION)) != 0;
   const int limit = n_ticks < 0 ? p.max_ticks : n_ticks;
+  const double length = sc.length[n];
 
   // shared layout
-  double* T = (double*)smem;                         // [CH + 2] tick times of the chunk, T[0] = time before it
-  double* spv = T + CH + 2;                          // [CH] ego speed after each tick (NaN: ego absent)
-  double* cwv = spv + CH;                            // [CH] 1 - t_prev / t of EgoAvgSpeed
-  double* part = cwv + CH;                           // [SG_RP_WARPS][M] distance partial sums
+  double* Tb = (double*)smem;                        // [2][TS] tick times (double buffered); T[0] = time before the chunk
+  double* spv = Tb + 2 * TS;                         // [TS] ego speed after tick j (NaN: ego absent)
+  double* cwv = spv + TS;                            // [TS] 1 - t_prev / t of EgoAvgSpeed
+  double* part = cwv + TS;                           // [SG_RP_WARPS][M] distance partial sums
   double* cdist = part + SG_RP_WARPS * M;            // [M] accumulated distance
-  float4* aabb = (float4*)(cdist + M + (M & 1));     // [M][CH]
-  uint32_t* egonow = (uint32_t*)(aabb + (size_t)M * CH);  // [CH]
-  uint32_t* cbits = egonow + CH;                     // [CH]
-  uint32_t* fpair = cbits + CH;                      // [CH]
-  int* npairs = (int*)(fpair + CH);                  // [CH]
-  uint32_t* tflag = (uint32_t*)(npairs + CH);        // [CH] bit0: terminal condition met at this tick
-  uint8_t* apres = (uint8_t*)(tflag + CH);           // [M] agent slots: present from the first tick on
+  RpDesc* desc = (RpDesc*)(cdist + M + (M & 1));     // [M]
+  float4* aabb = (float4*)(desc + M);                // [M][CH]
+  uint32_t* egonow = (uint32_t*)(aabb + (size_t)M * CH);  // [TS]; [0] = ego row before the chunk
+  uint32_t* cbits = egonow + TS;                     // [TS]
+  uint32_t* fpair = cbits + TS;                      // [TS]
+  int* npairs = (int*)(fpair + TS);                  // [TS]
+  uint8_t* apres = (uint8_t*)(npairs + TS);          // [M] agent slots: present from the first tick on
   RpCarry* car = (RpCarry*)(apres + ((M + 15) / 16) * 16);
 
   if (tid < M) {
@@ -224,9 +252,12 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
     cdist[tid] = st.dist[i];
     const RpSlot e = rp_slot(sc, i);
     apres[tid] = (st.present[i] != 0) || (e.K > 0 && e.tmin >= c.t_launch);  // scenario_gym.py:240-244
+    RpDesc d;
+    d.rows = e.rows; d.tmin = e.tmin; d.tmax = e.tmax; d.K = e.K; d.kind = e.kind;
+    d.bw = sc.box[i]; d.bl = sc.box[nm + i]; d.bcx = sc.box[2 * nm + i]; d.bcy = sc.box[3 * nm + i];
+    desc[tid] = d;
   }
   if (tid == 0) {
-    car->t = c.t_launch; car->prev_t = st.prev_t[n];
     car->avg = st.ego_avg_speed[n]; car->avg_t = st.ego_avg_t[n]; car->mx = st.ego_max_speed[n];
     {
       const int64_t ie = i0 + c.ego_slot;
@@ -236,75 +267,88 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
     car->tick = st.tick[n]; car->executed = 0; car->done = st.done[n] != 0;
     car->first_tick = st.first_coll_tick[n];
     car->fp0 = st.first_coll_pair[2 * n]; car->fp1 = st.first_coll_pair[2 * n + 1];
-    car->ego_last = st.ego_hits[n];
+    egonow[0] = st.ego_hits[n];
     car->collided = 0;
+    car->buf = 0;
+    // tick times of the first chunk by repeated addition (scenario_gym.py:229)
+    int cnt = 0;
+    double t = c.t_launch;
+    Tb[0] = t;
+    if (!car->done)
+      while (cnt < TPC && cnt < limit) { t = t + p.timestep; Tb[++cnt] = t; }
+    Tb[cnt + 1] = t + p.timestep;
+    car->cnt = cnt;
   }
   __syncthreads();
 
   for (;;) {
-    // ---- 1: tick times of this chunk (scenario_gym.py:229; max_length, state.py:397-398) ----
-    if (tid == 0) {
-      double t = car->t, pt = car->prev_t;
-      int nv = 0, done = car->done;
-      T[0] = t;
-      while (nv < CH && car->executed + nv < limit && !done) {
-        const double nt = t + p.timestep;
-        pt = t; t = nt;
-        T[++nv] = t;
-        if ((p.terminal & SG_TERM_MAX_LENGTH) && (t + (t - pt) > sc.length[n])) done = 1;
-      }
-      T[nv + 1] = t + p.timestep;  // look-ahead for "does the entity leave at the next tick"
-      car->nv = nv;
-      car->end_here = done || car->executed + nv >= limit;
-      car->chunk_first = 0xffffffffu;
-      if (nv > 0) { car->done = done; }
+    const double* T = Tb + car->buf * TS;
+    const int cnt = car->cnt;
+    if (cnt == 0) break;
+    const bool first_chunk = car->executed == 0;
+    // ---- 1: `max_length` (state.py:397-398) decided per tick in parallel ------------------------
+    if (tid == 0) { car->nv = cnt; car->term_first = 0xffffffffu; car->chunk_first = 0xffffffffu; }
+    __syncthreads();
+    if (p.terminal & SG_TERM_MAX_LENGTH) {
+      const bool over = lane >= 1 && j <= cnt && (T[j] + (T[j] - T[j - 1]) > length);
+      const uint32_t b = __ballot_sync(0xffffffffu, over);
+      if (b && lane == 0) atomicMin(&car->nv, 31 * warp + __ffs(b) - 1);
     }
     __syncthreads();
     int nv = car->nv;
-    if (nv == 0) break;
-    const bool first_chunk = car->executed == 0;
+    bool done = nv < cnt || ((p.terminal & SG_TERM_MAX_LENGTH) && (T[nv] + (T[nv] - T[nv - 1]) > length));
 
     for (int attempt = 0; attempt < 2; ++attempt) {
-      // ---- 2: every thread evaluates its tick ---------------------------------------------
-      const bool valid = tid < nv;
-      const double tk = valid ? T[tid + 1] : T[1], tkm = valid ? T[tid] : T[0];
-      const double dt = tk - tkm;
-      const bool first = first_chunk && tid == 0;
-      const RpUnion uk = rp_union_weights(c.ts, c.UK, tk);
-      const RpUnion um = rp_union_weights(c.ts, c.UK, tkm);
+      // ---- 2: every thread evaluates its time ----------------------------------------------------
+      const bool live_t = j <= nv;             // T[j] is a time of this chunk
+      const bool valid = lane >= 1 && live_t;  // this thread owns tick j
+      const double tj = live_t ? T[j] : T[0], tkm = valid ? T[j - 1] : T[0];
+      const double dt = tj - tkm;
+      const bool first = first_chunk && j == 1;
+      const RpUnion uk = rp_union_weights_ool(c.ts, c.UK, tj);
       uint32_t pm = 0;  // present slots after this tick
       double sp = NAN;
       for (int s = 0; s < M; ++s) {
-        const int64_t i = i0 + s;
-        const RpSlot e = rp_slot(sc, i);
+        const RpDesc e = desc[s];
+        if (e.kind == SG_KIND_EMPTY) {
+          if (need_coll) aabb[(size_t)s * CH + tid] = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+          if (lane == 0) part[warp * M + s] = 0.0;
+          continue;  // uniform over the CTA
+        }
+        const bool ap = apres[s] != 0;
+        const bool pres = live_t && rp_present_d(e, p.persist, tj, ap);
+        double4 pk = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (pres) {
+          if (e.kind == SG_KIND_AGENT_REPLAY) pk = rp_agent_pose4(e.rows, e.K, tj, EXT_CLAMP);  // agent.py:125-128
+          else {
+            pk.x = rp_union_value(uk, c.X, c.UK, M, s, 0); pk.y = rp_union_value(uk, c.X, c.UK, M, s, 1);
+            pk.z = rp_union_value(uk, c.X, c.UK, M, s, 2); pk.w = rp_union_value(uk, c.X, c.UK, M, s, 3);
+          }
+        }
+        // what lane l - 1 computed is the pose before this lane's tick
+        bool ppres = __shfl_up_sync(0xffffffffu, (int)pres, 1) != 0;
+        double px = __shfl_up_sync(0xffffffffu, pk.x, 1), py = __shfl_up_sync(0xffffffffu, pk.y, 1),
+               pz = __shfl_up_sync(0xffffffffu, pk.z, 1);
         float4 bb = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
         double inc = 0.0;
-        if (e.kind != SG_KIND_EMPTY && valid && rp_present(e, p.persist, tk, apres[s] != 0)) {
+        if (valid && pres) {
           pm |= 1u << s;
-          double pk[6], prev[6];
-          rp_pose<4>(e, uk, c.X, c.UK, M, s, tk, pk);
-          bool ppres;
-          if (first) {
+          if (first) {  // the previous tick is the launch state
+            const int64_t i = i0 + s;
             ppres = st.present[i] != 0;
-            if (ppres) { prev[0] = st.pose[i]; prev[1] = st.pose[nm + i]; prev[2] = st.pose[2 * nm + i]; }
-          } else {
-            ppres = rp_present(e, p.persist, tkm, apres[s] != 0);
-            if (ppres) rp_pose<3>(e, um, c.X, c.UK, M, s, tkm, prev);
+            if (ppres) { px = st.pose[i]; py = st.pose[nm + i]; pz = st.pose[2 * nm + i]; }
           }
           if (!ppres) {  // newcomer: state.py:219-222
-            int cur = 0;
-            double full[6];
-            position_at_t(e.rows, e.K, tkm, EXT_TRUE, cur, full);
-            prev[0] = full[0]; prev[1] = full[1]; prev[2] = full[2];
+            const double4 q = rp_agent_pose4(e.rows, e.K, tkm, EXT_TRUE);
+            px = q.x; py = q.y; pz = q.z;
           }
-          const double d0 = pk[0] - prev[0], d1 = pk[1] - prev[1], d2 = pk[2] - prev[2];
+          const double d0 = pk.x - px, d1 = pk.y - py, d2 = pk.z - pz;
           inc = norm3(d0, d1, d2);  // state.py:237-239
           if (s == c.ego_slot) sp = norm3(d0 / dt, d1 / dt, d2 / dt);  // metrics/trajectory.py:21
           if (need_coll) {
             double sn, cs;
-            sincos(pk[3], &sn, &cs);
-            bb = make_aabb_box(pk[0], pk[1], cs, sn, sc.box[i], sc.box[nm + i], sc.box[2 * nm + i],
-                               sc.box[3 * nm + i], c.ox, c.oy);
+            sincos(pk.w, &sn, &cs);
+            bb = make_aabb_box(pk.x, pk.y, cs, sn, e.bw, e.bl, e.bcx, e.bcy, c.ox, c.oy);
           }
         }
         if (need_coll) aabb[(size_t)s * CH + tid] = bb;
@@ -313,8 +357,6 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
         for (int off = 16; off > 0; off >>= 1) inc += __shfl_xor_sync(0xffffffffu, inc, off);
         if (lane == 0) part[warp * M + s] = inc;
       }
-      spv[tid] = sp;
-      cwv[tid] = 1.0 - (first_chunk && tid == 0 ? car->avg_t : tkm) / tk;  // metrics/trajectory.py:20-24
       // pair sweep on the conservative AABBs, exact narrow phase on the survivors
       uint32_t cb = 0, en = 0, fp = 0x7fffffffu, term = 0;
       int np = 0;
@@ -326,7 +368,7 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
             if (!((pm >> b) & 1)) continue;
             const float4 B = aabb[(size_t)b * CH + tid];
             if (!(A.x <= B.z && B.x <= A.z && A.y <= B.w && B.y <= A.w)) continue;
-            if (!rp_pair_exact(&sc, c, a, b, tk)) continue;
+            if (!rp_pair_exact(&sc, c, a, b, tj)) continue;
             ++np;
             fp = min(fp, ((uint32_t)a << 16) | (uint32_t)b);
             cb |= (1u << a) | (1u << b);
@@ -338,76 +380,113 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
         if ((p.terminal & SG_TERM_COLLISION) && np > 0) term |= 1u;
         if ((p.terminal & SG_TERM_EGO_COLLISION) && (term & 2u)) term |= 1u;
       }
-      egonow[tid] = en; cbits[tid] = cb; fpair[tid] = fp; npairs[tid] = np; tflag[tid] = term;
-      if (coll_terminal && (term & 1u)) atomicMin(&car->chunk_first, (uint32_t)tid);
+      if (valid) {
+        spv[j] = sp;
+        cwv[j] = 1.0 - (first ? car->avg_t : tkm) / tj;  // metrics/trajectory.py:20-24
+        egonow[j] = en; cbits[j] = cb; fpair[j] = fp; npairs[j] = np;
+        if (coll_terminal && (term & 1u)) atomicMin(&car->term_first, (uint32_t)j);
+      }
       __syncthreads();
-      if (!coll_terminal || car->chunk_first >= (uint32_t)(nv - 1)) {
-        if (coll_terminal && car->chunk_first == (uint32_t)(nv - 1) && tid == 0) { car->done = 1; car->end_here = 1; }
+      if (!coll_terminal || car->term_first >= (uint32_t)nv) {
+        if (coll_terminal && car->term_first == (uint32_t)nv) done = true;
         break;
       }
       // a collision ends the rollout inside the chunk: redo the reductions over the shorter range
-      nv = (int)car->chunk_first + 1;
+      nv = (int)car->term_first;
+      done = true;
       __syncthreads();
-      if (tid == 0) { car->nv = nv; car->done = 1; car->end_here = 1; car->chunk_first = 0xffffffffu; T[nv + 1] = T[nv] + p.timestep; }
+      if (tid == 0) car->term_first = 0xffffffffu;
       __syncthreads();
     }
-    __syncthreads();
+    const bool end_here = done || car->executed + nv >= limit;
+    const bool valid = lane >= 1 && j <= nv;
 
-    // ---- 3: commit the chunk ------------------------------------------------------------------
-    const bool valid = tid < nv;
-    const bool end_here = car->end_here != 0;
-    if (tid < M) {
-      double d = cdist[tid];
+    // ---- 3: commit the chunk; the two serial recurrences run on different warps -------------------
+    if (tid == 0 && (p.features & SG_FEAT_EGO_METRICS)) {
+      // EgoAvgSpeed / EgoMaxSpeed in tick order (metrics/trajectory.py:20-24, 39-42)
+      double avg = car->avg, mx = car->mx, last = car->last_sp;
+      for (int q = 1; q <= nv; ++q) {
+        double sp = spv[q];
+        if (sp != sp) sp = last; else last = sp;  // ego absent: its velocity is unchanged
+        avg += cwv[q] * (sp - avg);
+        mx = fmax(sp, mx);
+      }
+      car->avg = avg; car->mx = mx; car->last_sp = last; car->avg_t = T[nv];
+    }
+    if (tid == 32) {  // tick times of the next chunk by repeated addition (scenario_gym.py:229)
+      double* Tn = Tb + (car->buf ^ 1) * TS;
+      int cn = 0;
+      double t = T[nv];
+      Tn[0] = t;
+      if (!end_here) {
+        const int left = limit - (car->executed + nv);
+        while (cn < TPC && cn < left) { t = t + p.timestep; Tn[++cn] = t; }
+      }
+      Tn[cn + 1] = t + p.timestep;
+      car->cnt = cn;
+    }
+    if (tid >= 64 && tid < 64 + M) {
+      const int s = tid - 64;
+      double d = cdist[s];
 #pragma unroll
-      for (int w = 0; w < SG_RP_WARPS; ++w) d += part[w * M + tid];
-      cdist[tid] = d;
+      for (int w = 0; w < SG_RP_WARPS; ++w) d += part[w * M + s];
+      cdist[s] = d;
     }
     if (need_coll) {
-      uint32_t cb = valid ? cbits[tid] : 0u;
+      uint32_t cb = valid ? cbits[j] : 0u;
       cb = __reduce_or_sync(0xffffffffu, cb);
-      int np = valid ? npairs[tid] : 0;
+      int np = valid ? npairs[j] : 0;
+      const uint32_t hit = __ballot_sync(0xffffffffu, np > 0);
       np = __reduce_add_sync(0xffffffffu, np);
-      const uint32_t hit = __ballot_sync(0xffffffffu, valid && npairs[tid] > 0);
       if (lane == 0) {
         if (cb) atomicOr(&car->collided, cb);
         if (np) atomicAdd((unsigned long long*)&car->pair_ticks, (unsigned long long)np);
-        if (hit) atomicMin(&car->chunk_first, (uint32_t)(warp * 32 + __ffs(hit) - 1));
+        if (hit) atomicMin(&car->chunk_first, (uint32_t)(31 * warp + __ffs(hit) - 1));
       }
       if ((p.features & SG_FEAT_COLLISIONS) && valid) {  // CollisionMetric._step, metrics/collision.py:70-75
-        uint32_t fresh = egonow[tid] & ~(tid ? egonow[tid - 1] : car->ego_last);
+        uint32_t fresh = egonow[j] & ~egonow[j - 1];
         while (fresh) {
           const int b = __ffs(fresh) - 1;
           fresh &= fresh - 1;
           const int slot = atomicAdd(st.event_count, 1);
           if (slot < st.event_cap) {
             SgEvent ev;
-            ev.scenario = n; ev.tick = car->tick + tid + 1; ev.slot = b; ev._pad = 0; ev.t = T[tid + 1];
+            ev.scenario = n; ev.tick = car->tick + j; ev.slot = b; ev._pad = 0; ev.t = T[j];
             st.events[slot] = ev;
           }
         }
       }
     }
-    // State rows of the slots that are present now and not after the next tick (or at the end)
-    if (valid) {
-      const double tk = T[tid + 1], tkm = T[tid], tkn = T[tid + 2];
-      const bool first = first_chunk && tid == 0;
-      const bool is_end = end_here && tid == nv - 1;
+    // State rows of a slot that is present after tick j but not after the next one
+    if (valid && !(end_here && j == nv)) {
+      const double tj = T[j], tkm = T[j - 1], tkn = T[j + 1];
       for (int s = 0; s < M; ++s) {
-        const int64_t i = i0 + s;
-        const RpSlot e = rp_slot(sc, i);
+        const RpDesc e = desc[s];
         const bool ap = apres[s] != 0;
-        const bool pres = e.kind != SG_KIND_EMPTY && rp_present(e, p.persist, tk, ap);
-        if (pres && (is_end || !rp_present(e, p.persist, tkn, ap)))
-          rp_write_rows(&sc, &p, &st, c, s, ap, tk, tkm, first);
-        if (is_end) { st.present[i] = pres; st.cur_own[i] = 1; }
+        if (e.kind != SG_KIND_EMPTY && e.kind != SG_KIND_AGENT_REPLAY && rp_present_d(e, p.persist, tj, ap) &&
+            !rp_present_d(e, p.persist, tkn, ap))
+          rp_write_rows(&sc, &p, &st, c, s, ap, tj, tkm, first_chunk && j == 1);
       }
-      if (is_end && (p.features & SG_FEAT_COLL_MATRIX)) {  // pair matrix of the final tick
+    }
+    if (end_here) {
+      const double tj = T[nv], tkm = T[nv - 1];
+      if (tid >= 96 && tid < 96 + M) {  // final tick: one thread per slot
+        const int s = tid - 96;
+        const int64_t i = i0 + s;
+        const RpDesc e = desc[s];
+        const bool ap = apres[s] != 0;
+        const bool pres = e.kind != SG_KIND_EMPTY && rp_present_d(e, p.persist, tj, ap);
+        if (pres) rp_write_rows(&sc, &p, &st, c, s, ap, tj, tkm, first_chunk && nv == 1);
+        st.present[i] = pres;
+        st.cur_own[i] = 1;
+      }
+      if (valid && j == nv && (p.features & SG_FEAT_COLL_MATRIX)) {  // pair matrix of the final tick
         uint32_t* rows = st.coll_mask + i0;  // W = 1
         for (int s = 0; s < M; ++s) rows[s] = 0;
         uint32_t pm = 0;
         for (int s = 0; s < M; ++s) {
-          const RpSlot e = rp_slot(sc, i0 + s);
-          if (e.kind != SG_KIND_EMPTY && rp_present(e, p.persist, tk, apres[s] != 0)) pm |= 1u << s;
+          const RpDesc e = desc[s];
+          if (e.kind != SG_KIND_EMPTY && rp_present_d(e, p.persist, tj, apres[s] != 0)) pm |= 1u << s;
         }
         if (need_coll)
           for (int a = 0; a < M; ++a) {
@@ -417,7 +496,7 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
               if (!((pm >> b) & 1)) continue;
               const float4 B = aabb[(size_t)b * CH + tid];
               if (!(A.x <= B.z && B.x <= A.z && A.y <= B.w && B.y <= A.w)) continue;
-              if (!rp_pair_exact(&sc, c, a, b, tk)) continue;
+              if (!rp_pair_exact(&sc, c, a, b, tj)) continue;
               rows[a] |= 1u << b;
               rows[b] |= 1u << a;
             }
@@ -426,27 +505,24 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
     }
     __syncthreads();
     if (tid == 0) {
-      if (p.features & SG_FEAT_EGO_METRICS) {  // metrics/trajectory.py:20-24, 39-42: in tick order
-        double avg = car->avg, mx = car->mx, last = car->last_sp;
-        for (int j = 0; j < nv; ++j) {
-          double sp = spv[j];
-          if (sp != sp) sp = last; else last = sp;  // ego absent: its velocity is unchanged
-          avg += cwv[j] * (sp - avg);
-          mx = fmax(sp, mx);
-        }
-        car->avg = avg; car->mx = mx; car->last_sp = last; car->avg_t = T[nv];
-      }
       if (need_coll && car->first_tick < 0 && car->chunk_first != 0xffffffffu) {
-        const int j = (int)car->chunk_first;
-        car->first_tick = car->tick + j + 1;
-        car->fp0 = (int)(fpair[j] >> 16); car->fp1 = (int)(fpair[j] & 0xffffu);
+        const int q = (int)car->chunk_first;
+        car->first_tick = car->tick + q;
+        car->fp0 = (int)(fpair[q] >> 16); car->fp1 = (int)(fpair[q] & 0xffffu);
       }
-      if (p.features & SG_FEAT_COLLISIONS) car->ego_last = egonow[nv - 1];
-      car->t = T[nv]; car->prev_t = T[nv - 1];
+      if (p.features & SG_FEAT_COLLISIONS) egonow[0] = egonow[nv];
       car->tick += nv; car->executed += nv;
+      car->done = done; car->end_here = end_here;
+      car->buf ^= 1;
+      if (end_here) car->cnt = 0;
     }
     __syncthreads();
-    if (car->end_here) break;
+    if (end_here) {
+      if (tid == 0) {  // times after the last executed tick
+        st.t[n] = T[nv]; st.prev_t[n] = T[nv - 1];
+      }
+      break;
+    }
   }
 
   // ---- per-scenario results ---------------------------------------------------------------------
@@ -457,7 +533,7 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
       if ((car->collided >> tid) & 1) st.collided[i] = 1;
     }
     if (tid == 0) {
-      st.t[n] = car->t; st.prev_t[n] = car->prev_t; st.tick[n] = car->tick; st.done[n] = car->done;
+      st.tick[n] = car->tick; st.done[n] = car->done;
       st.cur_union[n] = 1;
       if (p.features & SG_FEAT_EGO_METRICS) {
         st.ego_avg_speed[n] = car->avg; st.ego_avg_t[n] = car->avg_t; st.ego_max_speed[n] = car->mx;
@@ -466,16 +542,17 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
       st.first_coll_tick[n] = car->first_tick;
       st.first_coll_pair[2 * n] = car->fp0; st.first_coll_pair[2 * n + 1] = car->fp1;
       st.n_pair_ticks[n] = car->pair_ticks;
-      st.ego_hits[n] = car->ego_last;
+      if (p.features & SG_FEAT_COLLISIONS) st.ego_hits[n] = egonow[0];
     }
   }
 }
 
 static size_t replay_smem_bytes(int M) {
-  const int CH = SG_RP_THREADS;
-  size_t o = (size_t)(CH + 2 + CH + CH + SG_RP_WARPS * M + M + (M & 1)) * sizeof(double);
+  const int CH = SG_RP_THREADS, TS = SG_RP_TPC + 2;
+  size_t o = (size_t)(4 * TS + SG_RP_WARPS * M + M + (M & 1)) * sizeof(double);
+  o += (size_t)M * sizeof(RpDesc);
   o += (size_t)M * CH * sizeof(float4);
-  o += (size_t)CH * 5 * sizeof(uint32_t);
+  o += (size_t)TS * 4 * sizeof(uint32_t);
   o += (size_t)((M + 15) / 16) * 16;
   o += sizeof(RpCarry) + 16;
   return o;
