@@ -1923,7 +1923,7 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
       err = cudaFuncSetAttribute(sg_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
       if (err != cudaSuccess) return set_err("cudaFuncSetAttribute", err);
     }
-    sg_replay_kernel<<<sc->n_scenarios, SG_RP_THREADS, rsm, s>>>(*sc, *p, *st, n_ticks);
+    sg_replay_kernel<<<sc->n_scenarios, SG_RP_BLOCK, rsm, s>>>(*sc, *p, *st, n_ticks);
     err = cudaGetLastError();
     if (err != cudaSuccess) return set_err("sg_replay_kernel launch", err);
     return 0;

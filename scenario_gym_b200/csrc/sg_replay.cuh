@@ -27,6 +27,9 @@
 // Lane 0 of every warp only supplies the pose "before" the warp's first tick (what lane l - 1
 // computed is the previous pose of lane l), so a warp advances 31 ticks and a chunk 124.
 #define SG_RP_TPC (SG_RP_WARPS * 31)
+// A fifth warp runs the two serial recurrences off the critical path: while the workers evaluate
+// chunk c, it extends the tick times for chunk c + 1 and folds chunk c - 1 into EgoAvgSpeed.
+#define SG_RP_BLOCK (SG_RP_THREADS + 32)
 
 struct RpUnion {  // position of a time in the scenario's union-knot table
   int mode;       // 0: before the first knot, 1: after the last, 2: interpolate rows cur-1, cur
@@ -200,11 +203,24 @@ SG_DEV bool rp_present_d(const RpDesc& e, int persist, double tau, bool agent_pr
 struct RpCarry {  // cross-chunk state of the scenario (shared memory)
   double avg, avg_t, mx, last_sp;
   long long pair_ticks;
-  int tick, executed, done, cnt, nv, first_tick, fp0, fp1, end_here, buf;
+  int tick, executed, done, cnt, cnt_next, nv, nv_prev, first_tick, fp0, fp1, end_here, buf;
   uint32_t collided, chunk_first, term_first;
 };
 
-__global__ void __launch_bounds__(SG_RP_THREADS)
+// EgoAvgSpeed / EgoMaxSpeed over one chunk in tick order (metrics/trajectory.py:20-24, 39-42);
+// t_last = time after the chunk's last tick
+SG_DEV void rp_ego_metrics(RpCarry* car, const double* spv, const double* cwv, int nv, double t_last) {
+  double avg = car->avg, mx = car->mx, last = car->last_sp;
+  for (int q = 1; q <= nv; ++q) {
+    double sp = spv[q];
+    if (sp != sp) sp = last; else last = sp;  // ego absent: its velocity is unchanged
+    avg += cwv[q] * (sp - avg);
+    mx = fmax(sp, mx);
+  }
+  car->avg = avg; car->mx = mx; car->last_sp = last; car->avg_t = t_last;
+}
+
+__global__ void __launch_bounds__(SG_RP_BLOCK)
 sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgParams p,
                  const __grid_constant__ SgState st, int n_ticks) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -234,9 +250,9 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
 
   // shared layout
   double* Tb = (double*)smem;                        // [2][TS] tick times (double buffered); T[0] = time before the chunk
-  double* spv = Tb + 2 * TS;                         // [TS] ego speed after tick j (NaN: ego absent)
-  double* cwv = spv + TS;                            // [TS] 1 - t_prev / t of EgoAvgSpeed
-  double* part = cwv + TS;                           // [SG_RP_WARPS][M] distance partial sums
+  double* spb = Tb + 2 * TS;                         // [2][TS] ego speed after tick j (NaN: ego absent)
+  double* cwb = spb + 2 * TS;                        // [2][TS] 1 - t_prev / t of EgoAvgSpeed
+  double* part = cwb + 2 * TS;                       // [SG_RP_WARPS][M] distance partial sums
   double* cdist = part + SG_RP_WARPS * M;            // [M] accumulated distance
   RpDesc* desc = (RpDesc*)(cdist + M + (M & 1));     // [M]
   float4* aabb = (float4*)(desc + M);                // [M][CH]
@@ -270,6 +286,7 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
     egonow[0] = st.ego_hits[n];
     car->collided = 0;
     car->buf = 0;
+    car->nv_prev = 0;
     // tick times of the first chunk by repeated addition (scenario_gym.py:229)
     int cnt = 0;
     double t = c.t_launch;
@@ -282,7 +299,10 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
   __syncthreads();
 
   for (;;) {
-    const double* T = Tb + car->buf * TS;
+    const int buf = car->buf;
+    const double* T = Tb + buf * TS;
+    double* spv = spb + buf * TS;
+    double* cwv = cwb + buf * TS;
     const int cnt = car->cnt;
     if (cnt == 0) break;
     const bool first_chunk = car->executed == 0;
@@ -298,93 +318,110 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
     int nv = car->nv;
     bool done = nv < cnt || ((p.terminal & SG_TERM_MAX_LENGTH) && (T[nv] + (T[nv] - T[nv - 1]) > length));
 
+    // ---- helper warp: serial recurrences, overlapped with the workers' pass ----------------------
+    if (tid == SG_RP_THREADS && (p.features & SG_FEAT_EGO_METRICS) && car->nv_prev > 0)
+      rp_ego_metrics(car, spb + (buf ^ 1) * TS, cwb + (buf ^ 1) * TS, car->nv_prev, T[0]);
+    if (tid == SG_RP_THREADS + 1) {  // tick times of the next chunk by repeated addition (scenario_gym.py:229)
+      double* Tn = Tb + (buf ^ 1) * TS;
+      int cn = 0;
+      double t = T[cnt];
+      Tn[0] = t;
+      const int left = limit - (car->executed + cnt);
+      if (cnt == TPC)
+        while (cn < TPC && cn < left) { t = t + p.timestep; Tn[++cn] = t; }
+      Tn[cn + 1] = t + p.timestep;
+      car->cnt_next = cn;
+    }
+
     for (int attempt = 0; attempt < 2; ++attempt) {
       // ---- 2: every thread evaluates its time ----------------------------------------------------
-      const bool live_t = j <= nv;             // T[j] is a time of this chunk
-      const bool valid = lane >= 1 && live_t;  // this thread owns tick j
-      const double tj = live_t ? T[j] : T[0], tkm = valid ? T[j - 1] : T[0];
-      const double dt = tj - tkm;
-      const bool first = first_chunk && j == 1;
-      const RpUnion uk = rp_union_weights_ool(c.ts, c.UK, tj);
-      uint32_t pm = 0;  // present slots after this tick
-      double sp = NAN;
-      for (int s = 0; s < M; ++s) {
-        const RpDesc e = desc[s];
-        if (e.kind == SG_KIND_EMPTY) {
-          if (need_coll) aabb[(size_t)s * CH + tid] = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
-          if (lane == 0) part[warp * M + s] = 0.0;
-          continue;  // uniform over the CTA
+      if (warp < SG_RP_WARPS) {
+        const bool live_t = j <= nv;             // T[j] is a time of this chunk
+        const bool valid = lane >= 1 && live_t;  // this thread owns tick j
+        const double tj = live_t ? T[j] : T[0], tkm = valid ? T[j - 1] : T[0];
+        const double dt = tj - tkm;
+        const bool first = first_chunk && j == 1;
+        const RpUnion uk = rp_union_weights_ool(c.ts, c.UK, tj);
+        uint32_t pm = 0;  // present slots after this tick
+        double sp = NAN;
+        for (int s = 0; s < M; ++s) {
+          const RpDesc e = desc[s];
+          if (e.kind == SG_KIND_EMPTY) {
+            if (need_coll) aabb[(size_t)s * CH + tid] = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+            if (lane == 0) part[warp * M + s] = 0.0;
+            continue;  // uniform over the CTA
+          }
+          const bool ap = apres[s] != 0;
+          const bool pres = live_t && rp_present_d(e, p.persist, tj, ap);
+          double4 pk = make_double4(0.0, 0.0, 0.0, 0.0);
+          if (pres) {
+            if (e.kind == SG_KIND_AGENT_REPLAY) pk = rp_agent_pose4(e.rows, e.K, tj, EXT_CLAMP);  // agent.py:125-128
+            else {
+              pk.x = rp_union_value(uk, c.X, c.UK, M, s, 0); pk.y = rp_union_value(uk, c.X, c.UK, M, s, 1);
+              pk.z = rp_union_value(uk, c.X, c.UK, M, s, 2); pk.w = rp_union_value(uk, c.X, c.UK, M, s, 3);
+            }
+          }
+          // what lane l - 1 computed is the pose before this lane's tick
+          bool ppres = __shfl_up_sync(0xffffffffu, (int)pres, 1) != 0;
+          double px = __shfl_up_sync(0xffffffffu, pk.x, 1), py = __shfl_up_sync(0xffffffffu, pk.y, 1),
+                 pz = __shfl_up_sync(0xffffffffu, pk.z, 1);
+          float4 bb = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+          double inc = 0.0;
+          if (valid && pres) {
+            pm |= 1u << s;
+            if (first) {  // the previous tick is the launch state
+              const int64_t i = i0 + s;
+              ppres = st.present[i] != 0;
+              if (ppres) { px = st.pose[i]; py = st.pose[nm + i]; pz = st.pose[2 * nm + i]; }
+            }
+            if (!ppres) {  // newcomer: state.py:219-222
+              const double4 q = rp_agent_pose4(e.rows, e.K, tkm, EXT_TRUE);
+              px = q.x; py = q.y; pz = q.z;
+            }
+            const double d0 = pk.x - px, d1 = pk.y - py, d2 = pk.z - pz;
+            inc = norm3(d0, d1, d2);  // state.py:237-239
+            if (s == c.ego_slot) sp = norm3(d0 / dt, d1 / dt, d2 / dt);  // metrics/trajectory.py:21
+            if (need_coll) {
+              double sn, cs;
+              sincos(pk.w, &sn, &cs);
+              bb = make_aabb_box(pk.x, pk.y, cs, sn, e.bw, e.bl, e.bcx, e.bcy, c.ox, c.oy);
+            }
+          }
+          if (need_coll) aabb[(size_t)s * CH + tid] = bb;
+          // distance: fixed tree over the ticks of the warp, then over the warps in order
+  #pragma unroll
+          for (int off = 16; off > 0; off >>= 1) inc += __shfl_xor_sync(0xffffffffu, inc, off);
+          if (lane == 0) part[warp * M + s] = inc;
         }
-        const bool ap = apres[s] != 0;
-        const bool pres = live_t && rp_present_d(e, p.persist, tj, ap);
-        double4 pk = make_double4(0.0, 0.0, 0.0, 0.0);
-        if (pres) {
-          if (e.kind == SG_KIND_AGENT_REPLAY) pk = rp_agent_pose4(e.rows, e.K, tj, EXT_CLAMP);  // agent.py:125-128
-          else {
-            pk.x = rp_union_value(uk, c.X, c.UK, M, s, 0); pk.y = rp_union_value(uk, c.X, c.UK, M, s, 1);
-            pk.z = rp_union_value(uk, c.X, c.UK, M, s, 2); pk.w = rp_union_value(uk, c.X, c.UK, M, s, 3);
+        // pair sweep on the conservative AABBs, exact narrow phase on the survivors
+        uint32_t cb = 0, en = 0, fp = 0x7fffffffu, term = 0;
+        int np = 0;
+        if (need_coll && valid) {
+          for (int a = 0; a < M; ++a) {
+            if (!((pm >> a) & 1)) continue;
+            const float4 A = aabb[(size_t)a * CH + tid];
+            for (int b = a + 1; b < M; ++b) {
+              if (!((pm >> b) & 1)) continue;
+              const float4 B = aabb[(size_t)b * CH + tid];
+              if (!(A.x <= B.z && B.x <= A.z && A.y <= B.w && B.y <= A.w)) continue;
+              if (!rp_pair_exact(&sc, c, a, b, tj)) continue;
+              ++np;
+              fp = min(fp, ((uint32_t)a << 16) | (uint32_t)b);
+              cb |= (1u << a) | (1u << b);
+              if (a == c.ego_slot) en |= 1u << b;
+              if (b == c.ego_slot) en |= 1u << a;
+              if (a == c.first_slot || b == c.first_slot) term |= 2u;
+            }
           }
+          if ((p.terminal & SG_TERM_COLLISION) && np > 0) term |= 1u;
+          if ((p.terminal & SG_TERM_EGO_COLLISION) && (term & 2u)) term |= 1u;
         }
-        // what lane l - 1 computed is the pose before this lane's tick
-        bool ppres = __shfl_up_sync(0xffffffffu, (int)pres, 1) != 0;
-        double px = __shfl_up_sync(0xffffffffu, pk.x, 1), py = __shfl_up_sync(0xffffffffu, pk.y, 1),
-               pz = __shfl_up_sync(0xffffffffu, pk.z, 1);
-        float4 bb = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
-        double inc = 0.0;
-        if (valid && pres) {
-          pm |= 1u << s;
-          if (first) {  // the previous tick is the launch state
-            const int64_t i = i0 + s;
-            ppres = st.present[i] != 0;
-            if (ppres) { px = st.pose[i]; py = st.pose[nm + i]; pz = st.pose[2 * nm + i]; }
-          }
-          if (!ppres) {  // newcomer: state.py:219-222
-            const double4 q = rp_agent_pose4(e.rows, e.K, tkm, EXT_TRUE);
-            px = q.x; py = q.y; pz = q.z;
-          }
-          const double d0 = pk.x - px, d1 = pk.y - py, d2 = pk.z - pz;
-          inc = norm3(d0, d1, d2);  // state.py:237-239
-          if (s == c.ego_slot) sp = norm3(d0 / dt, d1 / dt, d2 / dt);  // metrics/trajectory.py:21
-          if (need_coll) {
-            double sn, cs;
-            sincos(pk.w, &sn, &cs);
-            bb = make_aabb_box(pk.x, pk.y, cs, sn, e.bw, e.bl, e.bcx, e.bcy, c.ox, c.oy);
-          }
+        if (valid) {
+          spv[j] = sp;
+          cwv[j] = 1.0 - (first ? car->avg_t : tkm) / tj;  // metrics/trajectory.py:20-24
+          egonow[j] = en; cbits[j] = cb; fpair[j] = fp; npairs[j] = np;
+          if (coll_terminal && (term & 1u)) atomicMin(&car->term_first, (uint32_t)j);
         }
-        if (need_coll) aabb[(size_t)s * CH + tid] = bb;
-        // distance: fixed tree over the ticks of the warp, then over the warps in order
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) inc += __shfl_xor_sync(0xffffffffu, inc, off);
-        if (lane == 0) part[warp * M + s] = inc;
-      }
-      // pair sweep on the conservative AABBs, exact narrow phase on the survivors
-      uint32_t cb = 0, en = 0, fp = 0x7fffffffu, term = 0;
-      int np = 0;
-      if (need_coll && valid) {
-        for (int a = 0; a < M; ++a) {
-          if (!((pm >> a) & 1)) continue;
-          const float4 A = aabb[(size_t)a * CH + tid];
-          for (int b = a + 1; b < M; ++b) {
-            if (!((pm >> b) & 1)) continue;
-            const float4 B = aabb[(size_t)b * CH + tid];
-            if (!(A.x <= B.z && B.x <= A.z && A.y <= B.w && B.y <= A.w)) continue;
-            if (!rp_pair_exact(&sc, c, a, b, tj)) continue;
-            ++np;
-            fp = min(fp, ((uint32_t)a << 16) | (uint32_t)b);
-            cb |= (1u << a) | (1u << b);
-            if (a == c.ego_slot) en |= 1u << b;
-            if (b == c.ego_slot) en |= 1u << a;
-            if (a == c.first_slot || b == c.first_slot) term |= 2u;
-          }
-        }
-        if ((p.terminal & SG_TERM_COLLISION) && np > 0) term |= 1u;
-        if ((p.terminal & SG_TERM_EGO_COLLISION) && (term & 2u)) term |= 1u;
-      }
-      if (valid) {
-        spv[j] = sp;
-        cwv[j] = 1.0 - (first ? car->avg_t : tkm) / tj;  // metrics/trajectory.py:20-24
-        egonow[j] = en; cbits[j] = cb; fpair[j] = fp; npairs[j] = np;
-        if (coll_terminal && (term & 1u)) atomicMin(&car->term_first, (uint32_t)j);
       }
       __syncthreads();
       if (!coll_terminal || car->term_first >= (uint32_t)nv) {
@@ -399,32 +436,9 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
       __syncthreads();
     }
     const bool end_here = done || car->executed + nv >= limit;
-    const bool valid = lane >= 1 && j <= nv;
+    const bool valid = warp < SG_RP_WARPS && lane >= 1 && j <= nv;
 
-    // ---- 3: commit the chunk; the two serial recurrences run on different warps -------------------
-    if (tid == 0 && (p.features & SG_FEAT_EGO_METRICS)) {
-      // EgoAvgSpeed / EgoMaxSpeed in tick order (metrics/trajectory.py:20-24, 39-42)
-      double avg = car->avg, mx = car->mx, last = car->last_sp;
-      for (int q = 1; q <= nv; ++q) {
-        double sp = spv[q];
-        if (sp != sp) sp = last; else last = sp;  // ego absent: its velocity is unchanged
-        avg += cwv[q] * (sp - avg);
-        mx = fmax(sp, mx);
-      }
-      car->avg = avg; car->mx = mx; car->last_sp = last; car->avg_t = T[nv];
-    }
-    if (tid == 32) {  // tick times of the next chunk by repeated addition (scenario_gym.py:229)
-      double* Tn = Tb + (car->buf ^ 1) * TS;
-      int cn = 0;
-      double t = T[nv];
-      Tn[0] = t;
-      if (!end_here) {
-        const int left = limit - (car->executed + nv);
-        while (cn < TPC && cn < left) { t = t + p.timestep; Tn[++cn] = t; }
-      }
-      Tn[cn + 1] = t + p.timestep;
-      car->cnt = cn;
-    }
+    // ---- 3: commit the chunk ----------------------------------------------------------------------
     if (tid >= 64 && tid < 64 + M) {
       const int s = tid - 64;
       double d = cdist[s];
@@ -514,18 +528,21 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
       car->tick += nv; car->executed += nv;
       car->done = done; car->end_here = end_here;
       car->buf ^= 1;
-      if (end_here) car->cnt = 0;
+      car->nv_prev = nv;
+      car->cnt = end_here ? 0 : car->cnt_next;
     }
     __syncthreads();
     if (end_here) {
       if (tid == 0) {  // times after the last executed tick
         st.t[n] = T[nv]; st.prev_t[n] = T[nv - 1];
+        if (p.features & SG_FEAT_EGO_METRICS) rp_ego_metrics(car, spv, cwv, nv, T[nv]);
       }
       break;
     }
   }
 
   // ---- per-scenario results ---------------------------------------------------------------------
+  __syncthreads();
   if (car->executed > 0) {
     if (tid < M) {
       const int64_t i = i0 + tid;
@@ -549,7 +566,7 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
 
 static size_t replay_smem_bytes(int M) {
   const int CH = SG_RP_THREADS, TS = SG_RP_TPC + 2;
-  size_t o = (size_t)(4 * TS + SG_RP_WARPS * M + M + (M & 1)) * sizeof(double);
+  size_t o = (size_t)(6 * TS + SG_RP_WARPS * M + M + (M & 1)) * sizeof(double);
   o += (size_t)M * sizeof(RpDesc);
   o += (size_t)M * CH * sizeof(float4);
   o += (size_t)TS * 4 * sizeof(uint32_t);
