@@ -531,27 +531,30 @@ SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c,
       const double ox = bx[o], oy = by[o];
       if (!in_buffer(pose[0], pose[1], thr, ox, oy)) return;
       const double ovx = bvx[o], ovy = bvy[o];
+      // (tolerance path: square roots and quotients through the rsqrt / rcp seeded helpers, < 1 ulp)
       const double vdx = ovx * ch + ovy * -sh, vdy = ovx * sh + ovy * ch;
-      const double vn = norm2(vdx, vdy) + 0.0000000001;
-      const double view0 = vdx / vn, view1 = vdy / vn;
+      const double vn = fnorm2(vdx, vdy) + 0.0000000001, rvn = fast_rcp(vn);
+      const double view0 = div_r(vdx, vn, rvn), view1 = div_r(vdy, vn, rvn);
       // _force_pedestrian_repulsion :140-176
-      const double rx = pose[0] - ox, ry = pose[1] - oy, rn = norm2(rx, ry);
-      const double vmag = norm2(ovx, ovy) + 0.0000000001;
-      const double uox = ovx / vmag, uoy = ovy / vmag;
+      const double rx = pose[0] - ox, ry = pose[1] - oy, rn = fnorm2(rx, ry), rrn = fast_rcp(rn);
+      const double vmag = fnorm2(ovx, ovy) + 0.0000000001, rvm = fast_rcp(vmag);
+      const double uox = div_r(ovx, vmag, rvm), uoy = div_r(ovy, vmag, rvm);
       const double other_step = vmag * (next_t - t);
       const double r2x = rx - other_step * uox, r2y = ry - other_step * uoy;
-      const double r2n = norm2(r2x, r2y) + 0.0000000001;
-      const double b = (1.0 / 2) * sqrt((rn + r2n) * (rn + r2n) - other_step * other_step);
-      const double c0 = (1.0 / 4) * (1 / b) * (rn + r2n);
-      const double dbx = c0 * (rx / rn + r2x / r2n), dby = c0 * (ry / rn + r2y / r2n);
+      const double r2n = fnorm2(r2x, r2y) + 0.0000000001, rr2 = fast_rcp(r2n);
+      const double b = (1.0 / 2) * fast_sqrt((rn + r2n) * (rn + r2n) - other_step * other_step);
+      const double c0 = (1.0 / 4) * fast_rcp(b) * (rn + r2n);
+      const double dbx = c0 * (div_r(rx, rn, rrn) + div_r(r2x, r2n, rr2)),
+                   dby = c0 * (div_r(ry, rn, rrn) + div_r(r2y, r2n, rr2));
       const double g = p.sf_ped_repulse_V / p.sf_ped_repulse_sigma * exp(-b / p.sf_ped_repulse_sigma);
       const double Fr0 = g * dbx, Fr1 = g * dby;
       const double Fa0 = 2 * p.sf_ped_attract_C * rx, Fa1 = 2 * p.sf_ped_attract_C * ry;
       if (p.sf_sight_weight_use) {  // _sight_weight :213-222
-        double dd = dot2(view0, view1, Fr0, Fr1) / (norm2(Fr0, Fr1) + 0.0000000001);
+        const double nr = fnorm2(Fr0, Fr1) + 0.0000000001, na = fnorm2(Fa0, Fa1) + 0.0000000001;
+        double dd = div_r(dot2(view0, view1, Fr0, Fr1), nr, fast_rcp(nr));
         double w = dd >= sight_cos ? 1.0 : p.sf_sight_weight;
         F0 += w * Fr0; F1 += w * Fr1;
-        dd = dot2(view0, view1, Fa0, Fa1) / (norm2(Fa0, Fa1) + 0.0000000001);
+        dd = div_r(dot2(view0, view1, Fa0, Fa1), na, fast_rcp(na));
         w = dd >= sight_cos ? 1.0 : p.sf_sight_weight;
         F0 += w * Fa0; F1 += w * Fa1;
       } else {
