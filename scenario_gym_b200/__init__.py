@@ -17,6 +17,6 @@ from .plugins import (RSS, Action, ActionTableAgent, Agent, CollisionMetric, Con
 from .scenario import Scenario
 from .state import State
 from .trajectory import Trajectory
-from .xosc import import_scenario, read_catalog, relabel_scenario
+from .xosc import import_scenario, import_scenarios, read_catalog, relabel_scenario
 
 __all__ = [n for n in dir() if not n.startswith("_")]

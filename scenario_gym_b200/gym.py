@@ -32,7 +32,7 @@ from .plugins import (ActionTableAgent, Agent, CollisionMetric, EgoLocalizationS
                       _DeviceMetric)
 from .scenario import Scenario
 from .state import State
-from .xosc import import_scenario
+from .xosc import import_scenario, import_scenarios
 
 _TERMINAL_BITS = {"max_length": abi.TERM_MAX_LENGTH, "collision": abi.TERM_COLLISION,
                   "ego_collision": abi.TERM_EGO_COLLISION}
@@ -42,11 +42,15 @@ class ScenarioGym:
     """Loads and runs scenarios."""
 
     @classmethod
-    def run_scenarios(cls, paths: List[str], render: bool = False, **kwargs) -> None:
+    def run_scenarios(cls, paths: List[str], render: bool = False, **kwargs) -> "ScenarioGym":
+        """
+        Reference scenario_gym.py:16-27 loads and rolls the paths out one by one; here they are
+        ingested together and rolled out as ONE device batch (scenarios are independent).
+        """
         gym = cls(**kwargs)
-        for path in paths:
-            gym.load_scenario(path)
-            gym.rollout(render=render)
+        gym.load_scenarios(list(paths))
+        gym.rollout(render=render)
+        return gym
 
     def __init__(self, timestep: float = 1.0 / 30.0, persist: bool = False, viewer_class=None,
                  terminal_conditions: Optional[List[Union[str, Callable]]] = None,
@@ -88,8 +92,9 @@ class ScenarioGym:
         self.set_scenario(scenario, scenario_path=scenario_path, create_agent=create_agent)
 
     def load_scenarios(self, scenario_paths: List[str], create_agent=_create_agent,
-                       relabel: bool = False) -> None:
-        self.set_scenarios([import_scenario(p, relabel=relabel) for p in scenario_paths],
+                       relabel: bool = False, workers: Optional[int] = None) -> None:
+        """N scenario files as one device batch (batched ingest: xosc.import_scenarios)."""
+        self.set_scenarios(import_scenarios(scenario_paths, relabel=relabel, workers=workers),
                            scenario_paths=scenario_paths, create_agent=create_agent)
 
     def set_scenario(self, scenario: Scenario, scenario_path: Optional[str] = None,

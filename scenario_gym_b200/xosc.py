@@ -50,7 +50,23 @@ def _load_object(element, catalog_name: Optional[str]) -> Optional[Entity]:
     return ENTITY_CLASS_BY_TAG.get(element.tag, Entity)(entry)
 
 
-@lru_cache(maxsize=None)
+_CATALOG_CACHE: Dict[Tuple[str, float, int], Tuple[str, Dict[str, Entity]]] = {}
+
+
+def read_catalog_cached(catalog_file: str) -> Tuple[str, Dict[str, Entity]]:
+    """
+    ``read_catalog`` memoised on (path, mtime, size).  The reference re-parses every catalog
+    file for every scenario (read.py:97-118), which is most of its ~17 ms per file; entries
+    are copied before use (``ent.copy()`` in import_scenario), so sharing them is safe.
+    """
+    st = os.stat(catalog_file)
+    key = (os.path.abspath(catalog_file), st.st_mtime, st.st_size)
+    hit = _CATALOG_CACHE.get(key)
+    if hit is None:
+        hit = _CATALOG_CACHE[key] = read_catalog(catalog_file)
+    return hit
+
+
 def read_catalog(catalog_file: str) -> Tuple[str, Dict[str, Entity]]:
     """Catalog name and a dict entry name -> entity (reference catalogs.py:30-84)."""
     root = ET.parse(catalog_file).getroot()
@@ -103,7 +119,7 @@ def import_scenario(osc_file: str, relabel: bool = True, entity_types=None) -> S
             continue
         for fn in os.listdir(path):
             if fn.endswith(".xosc"):
-                name, entries = read_catalog(os.path.join(path, fn))
+                name, entries = read_catalog_cached(os.path.join(path, fn))
                 catalogs[name] = entries
     entities: Dict[str, Entity] = {}
     for obj in root.iterfind("Entities/ScenarioObject"):
@@ -158,3 +174,33 @@ def import_scenario(osc_file: str, relabel: bool = True, entity_types=None) -> S
     scenario = Scenario(list(entities.values()),
                         name=os.path.splitext(os.path.basename(osc_file))[0], properties=props)
     return relabel_scenario(scenario) if relabel else scenario
+
+
+def _import_one(args) -> Scenario:
+    path, relabel, entity_types = args
+    return import_scenario(path, relabel=relabel, entity_types=entity_types)
+
+
+def import_scenarios(osc_files, relabel: bool = True, entity_types=None, workers: Optional[int] = None):
+    """
+    Batched ingest: import many OpenSCENARIO files, catalogs parsed
+    once per process, files spread over ``workers`` processes (default: serial for few or small
+    files, else one per core; ``Scenario`` objects are picklable, as in the reference's ``mp.Pool``
+    fan-out, tests/test_scenario_gym.py:152-160).  Order is preserved; a missing file raises
+    ``FileNotFoundError`` like ``import_scenario``.
+    """
+    files = list(osc_files)
+    for f in files:
+        if not os.path.exists(f):
+            raise FileNotFoundError(f)
+    if workers is None:  # a pool only pays for many sizeable files (fork + pickling ~1 ms per scenario)
+        big = len(files) >= 64 and sum(os.path.getsize(f) for f in files) >= 32768 * len(files)
+        workers = min(os.cpu_count() or 1, 16) if big else 1
+    if workers <= 1 or len(files) <= 1:
+        return [import_scenario(f, relabel=relabel, entity_types=entity_types) for f in files]
+    import multiprocessing as mp
+
+    ctx = mp.get_context("fork")
+    chunk = max(1, len(files) // (4 * workers))
+    with ctx.Pool(workers) as pool:
+        return pool.map(_import_one, [(f, relabel, entity_types) for f in files], chunksize=chunk)

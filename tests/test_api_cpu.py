@@ -145,3 +145,23 @@ def test_missing_required_callback_raises():
     else:
         with pytest.raises((ValueError, RuntimeError)):
             gym.set_scenario(sc)
+
+
+def test_batched_ingest_matches_single_imports():
+    """import_scenarios (catalog cache, optional process pool) == a loop of import_scenario."""
+    import os
+
+    from scenario_gym_b200.xosc import import_scenario, import_scenarios
+
+    f = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "Scenarios", "demo.xosc")
+    one = import_scenario(f)
+    for workers in (1, 2):
+        many = import_scenarios([f] * 5, workers=workers)
+        assert len(many) == 5
+        for sc in many:
+            assert [e.ref for e in sc.entities] == [e.ref for e in one.entities]
+            for a, b in zip(sc.entities, one.entities):
+                assert np.array_equal(a.trajectory.data, b.trajectory.data)
+                assert a.bounding_box == b.bounding_box
+    with pytest.raises(FileNotFoundError):
+        import_scenarios([f, f + ".missing"])

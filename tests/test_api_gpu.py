@@ -180,6 +180,20 @@ def test_load_scenario_from_xosc():
     assert refs <= {"oncoming", "crossing", "parked"}
 
 
+def test_run_scenarios_is_one_batched_rollout():
+    """ScenarioGym.run_scenarios(paths): batched ingest + ONE device rollout; per-file results as single runs."""
+    path = os.path.join(DATA, "Scenarios", "demo.xosc")
+    single = ScenarioGym(metrics=std_metrics())
+    single.load_scenario(path)
+    single.rollout()
+    want = single.get_metrics()
+    gym = ScenarioGym.run_scenarios([path] * 7, metrics=std_metrics())
+    got = gym.get_metrics()
+    assert isinstance(got, list) and len(got) == 7
+    for m in got:
+        assert m == want
+
+
 def vehicle_scenario(cfg, n):
     rows = synthetic.two_knot_rows(cfg).reshape(cfg.N, cfg.M, 2, 7)
     ce = CatalogEntry(None, "car1", "car", "Vehicle", BoundingBox(*synthetic.CAR1_BOX))
