@@ -394,6 +394,11 @@ def run_b200(args):
         steps_expected = N * M * T
         expected_ticks = np.full(N, T)
         dt = cfg.dt
+    l2_note = None
+    if args.workload == "c2":
+        in_bytes = sum(a.nbytes for a in scene.arrays().values())
+        l2_note = (f"inputs larger than L2: the trajectory / union-knot tables read by every step are "
+                   f"{in_bytes / 1e6:.0f} MB")
     p = abi.default_params()
     p.timestep = dt
     p.features = features(args)
@@ -543,14 +548,17 @@ def run_b200(args):
         traffic = tj.get(key)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "kernel": ("sg_vehicle_kernel<RSS=%d>" % (0 if args.no_rss else 1)) if args.workload in ("c3", "c5")
-        else "sg_rollout_kernel", "kernel_ms": kern_ms, "reset_kernel_ms": reset_ms,
+        "traffic": traffic, "kernel": {"c3": "sg_vehicle_kernel<RSS=%d>" % (0 if args.no_rss else 1),
+                                       "c5": "sg_vehicle_kernel<RSS=%d>" % (0 if args.no_rss else 1),
+                                       "c2": "sg_replay_kernel (tick-parallel)",
+                                       "c4": "sg_rollout_kernel<PED=1> (cell grid)"}[args.workload],
+        "kernel_ms": kern_ms, "reset_kernel_ms": reset_ms,
         "algorithmic_bytes_per_entity_step": bpe, "entity_steps_per_launch": steps_per_rollout,
         "peak_source": peak_src,
         "note": "achieved = SURVEY 8d per-tick-streaming bytes (B_tick) x entity-steps / kernel time, "
-                "of measured HBM copy bandwidth; the fused kernel keeps State rows in registers across "
-                "ticks, so its real DRAM traffic (traffic, from ncu) is ~14x lower than B_tick and the "
-                "kernel is issue/FP64-latency bound, not HBM bound (profiles/)",
+                "of measured HBM copy bandwidth; the fused kernels keep State rows on chip across "
+                "ticks, so their real DRAM traffic (traffic, from ncu) is far below B_tick and they "
+                "are issue/latency bound, not HBM bound (profiles/)",
     }
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -563,7 +571,8 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_json(args, {"parallelism": f"scenario-sharded x{world}, no per-tick communication"}),
+        "config": config_json(args, dict({"parallelism": f"scenario-sharded x{world}, no per-tick communication"},
+                                         **({"l2_policy": l2_note} if l2_note else {}))),
         "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline,
         "cpu_baseline": cpu, "gather_ms": gather_ms,
         "collisions": {"pair_ticks": int(eng.get("n_pair_ticks").sum()),

@@ -43,27 +43,29 @@ if os.path.exists(lpath):
             f.write(f"| `{name}` | {n} | {ns / 1e6:.3f} | {100 * ns / total:.2f} % |\n")
     print(open(os.path.join(out_dir, f"{tag}_launches.md")).read())
 
-# ---- full capture of the top kernel -------------------------------------------------------
-ppath = os.path.join(go, f"prof_{tag}.ncu-rep")
-if os.path.exists(ppath):
-    raw = subprocess.run(["ncu", "-i", ppath, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# ---- full captures of the dominant kernel of each workload ----------------------------------
+WANT = [
+    "Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__warps_eligible.avg.per_cycle_active",
+    "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct", "lts__t_sector_op_read_hit_rate.pct",
+    "sm__icc_request_hit_rate.pct",
+]
+
+
+def summarise(rep, out_md, title):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
     m = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
-    want = [
-        "Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "launch__registers_per_thread",
-        "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers",
-        "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
-        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
-        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__warps_eligible.avg.per_cycle_active",
-        "l1tex__t_bytes_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_bytes_pipe_lsu_mem_local_op_st.sum",
-    ]
-    with open(os.path.join(out_dir, f"{tag}_top_kernel.md"), "w") as f:
-        f.write(f"# ncu --set full: top kernel ({tag})\n\n| metric | unit | value |\n|---|---|---|\n")
-        for k in want:
+    with open(out_md, "w") as f:
+        f.write(f"# ncu --set full: {title}\n\n| metric | unit | value |\n|---|---|---|\n")
+        for k in WANT:
             if k in m:
                 f.write(f"| {k} | {m[k][0]} | {m[k][1]} |\n")
         f.write("\n## warp stall reasons (warps stalled per issue-active cycle)\n\n| reason | value |\n|---|---:|\n")
@@ -71,20 +73,31 @@ if os.path.exists(ppath):
             if "issue_stalled" in h and h.endswith("per_issue_active.ratio"):
                 f.write(f"| {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')} "
                         f"| {float(m[h][1]):.3f} |\n")
-    print(open(os.path.join(out_dir, f"{tag}_top_kernel.md")).read())
 
     def num(k):
         u, v = m[k]
         x = float(v.replace(",", ""))
         return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
 
-    traffic = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
-    tpath = os.path.join(out_dir, "traffic.json")
-    tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
-    key = sys.argv[2] if len(sys.argv) > 2 else "c3_12500x64x256"
-    tj[key] = traffic
-    json.dump(tj, open(tpath, "w"), indent=1, sort_keys=True)
-    print("traffic bytes/launch", traffic, "->", key)
+    return num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+
+
+tpath = os.path.join(out_dir, "traffic.json")
+tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
+for w in ("c3", "c5", "c2", "c4"):
+    rep = os.path.join(go, f"prof_{tag}_{w}.ncu-rep")
+    if not os.path.exists(rep):
+        continue
+    traffic = summarise(rep, os.path.join(out_dir, f"{tag}_top_kernel_{w}.md"), f"dominant kernel of workload {w} ({tag})")
+    # the bench looks the measurement up under "<workload>[_norss]_<N>x<M>x<T>" of its own config
+    bj = os.path.join(go, f"bench_{tag}.json" if w == "c3" else f"bench_{tag}_{w}.json")
+    if os.path.exists(bj) and w != "c4":  # (the c4 capture runs a reduced scenario count)
+        cfg = json.loads(open(bj).read().strip().splitlines()[-1])["config"]
+        key = f"{w}_{cfg['scenarios_per_gpu']}x{cfg['entities']}x{cfg['ticks']}"
+        tj[key] = traffic
+        print("traffic bytes/launch", traffic, "->", key)
+    print(open(os.path.join(out_dir, f"{tag}_top_kernel_{w}.md")).read()[:1800])
+json.dump(tj, open(tpath, "w"), indent=1, sort_keys=True)
 
 bpath = os.path.join(go, f"bench_{tag}.json")
 if os.path.exists(bpath):
@@ -94,3 +107,8 @@ if os.path.exists(bpath):
     if os.path.exists(rp):
         with open(os.path.join(out_dir, f"{tag}_bench_reference_arm.json"), "w") as f:
             f.write(open(rp).read())
+    for w in ("c2", "c4", "c5", "c3_norss"):
+        bp = os.path.join(go, f"bench_{tag}_{w}.json")
+        if os.path.exists(bp):
+            with open(os.path.join(out_dir, f"{tag}_bench_{w}.json"), "w") as f:
+                f.write(open(bp).read())
