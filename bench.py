@@ -266,21 +266,38 @@ def _worker_init(args_dict, per_worker):
 
     args = _ap.Namespace(**args_dict)
     ident = os.getpid()
-    cfg = make_config(args, seed=1000 + ident % 1000, n_scen=per_worker)
-    scene = synthetic.pack_synthetic(cfg)
-    p = abi.default_params()
-    p.timestep = cfg.dt
-    p.features = features(args)
+    scene, p, actions, steps = cpu_sample(args, seed=1000 + ident % 1000, n_scen=per_worker)
     _W["eng"] = OracleEngine(scene, p, event_cap=1 << 16)
-    _W["cfg"] = cfg
+    _W["actions"], _W["steps"], _W["M"] = actions, steps, scene.M
 
 
 def _worker_step(_):
-    eng, cfg = _W["eng"], _W["cfg"]
+    eng = _W["eng"]
     t0 = time.perf_counter()
     eng.reset()
-    eng.rollout(-1, actions=cfg.actions)
-    return int(eng.get("present").sum() * 0 + eng.get("tick").sum()) * cfg.M, time.perf_counter() - t0
+    eng.rollout(-1, actions=_W["actions"])
+    steps = _W["steps"] if _W["steps"] is not None else int(eng.get("tick").sum()) * _W["M"]
+    return steps, time.perf_counter() - t0
+
+
+def cpu_sample(args, seed: int, n_scen: int):
+    """(scene, params, actions, entity-steps per rollout or None) of a bounded sample of the workload."""
+    if args.workload == "c2":
+        scene = c2_scene(n_scen)
+        sys.path.insert(0, os.path.join(REPO, "tests"))
+        from helpers import all_xosc_specs
+
+        per = np.array([int(o["present"][1:].sum()) for _, _, _, o in all_xosc_specs("xosc")], np.int64)
+        steps = int(per[np.arange(n_scen) % len(per)].sum())
+        dt, actions = workload_spec(args)["dt"], None
+    else:
+        cfg = make_config(args, seed=seed, n_scen=n_scen)
+        scene = synthetic.pack_synthetic(cfg)
+        steps, dt, actions = None, cfg.dt, cfg.actions
+    p = abi.default_params()
+    p.timestep = dt
+    p.features = features(args)
+    return scene, p, actions, steps
 
 
 def cpu_oracle_single(args, budget_s: float = 12.0):
@@ -290,23 +307,20 @@ def cpu_oracle_single(args, budget_s: float = 12.0):
     w = workload_spec(args)
     n = 8
     while True:
-        cfg = make_config(args, seed=0, n_scen=n)
-        scene = synthetic.pack_synthetic(cfg)
-        p = abi.default_params()
-        p.timestep = cfg.dt
-        p.features = features(args)
+        scene, p, actions, steps = cpu_sample(args, seed=0, n_scen=n)
         eng = OracleEngine(scene, p, event_cap=1 << 16)
         t0 = time.perf_counter()
         eng.reset()
-        eng.rollout(-1, actions=cfg.actions)
+        eng.rollout(-1, actions=actions)
         dt = time.perf_counter() - t0
-        steps = int(eng.get("tick").sum()) * cfg.M
+        if steps is None:
+            steps = int(eng.get("tick").sum()) * scene.M
         if dt >= budget_s / 4 or n >= 2048:
             break
         n = min(2048, max(n * 2, int(n * budget_s / max(dt, 1e-3) / 2)))
     return {
         "value": steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
-        "sample": f"{n} scenarios x {w['M']} entities x {w['T']} ticks of the same workload "
+        "sample": f"{n} scenarios x {w['M']} entities x {w['T'] or 'all'} ticks of the same workload "
                   f"({steps} entity-steps in {dt:.2f} s), oracle/sg_oracle.c single thread",
     }
 
@@ -322,7 +336,7 @@ def run_reference(args):
     build_oracle()
     cores = os.cpu_count() or 1
     w = workload_spec(args)
-    per_worker = max(1, int(round(4e5 / (w["M"] * w["T"]))))  # ~0.2-0.4 s of work per step per core
+    per_worker = max(1, int(round(4e5 / (w["M"] * max(w["T"], 200)))))  # ~0.2-0.4 s of work per step per core
     args_dict = vars(args)
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_worker_init, initargs=(args_dict, per_worker)) as pool:

@@ -91,7 +91,7 @@ for w in ("c3", "c5", "c2", "c4"):
     traffic = summarise(rep, os.path.join(out_dir, f"{tag}_top_kernel_{w}.md"), f"dominant kernel of workload {w} ({tag})")
     # the bench looks the measurement up under "<workload>[_norss]_<N>x<M>x<T>" of its own config
     bj = os.path.join(go, f"bench_{tag}.json" if w == "c3" else f"bench_{tag}_{w}.json")
-    if os.path.exists(bj) and w != "c4":  # (the c4 capture runs a reduced scenario count)
+    if os.path.exists(bj) and os.path.getsize(bj) > 2 and w != "c4":  # (the c4 capture runs a reduced scenario count)
         cfg = json.loads(open(bj).read().strip().splitlines()[-1])["config"]
         key = f"{w}_{cfg['scenarios_per_gpu']}x{cfg['entities']}x{cfg['ticks']}"
         tj[key] = traffic
