@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 6
+#define SG_ABI_VERSION 7
 
 /* entity slot kinds (who produces the slot's next pose each tick) */
 enum SgKind {
@@ -240,6 +240,14 @@ int sg_reset(const SgScene* scene, const SgParams* params, SgState* state, int d
    (ScenarioGym.rollout, scenario_gym.py:256-267), bounded by params->max_ticks. */
 int sg_rollout(const SgScene* scene, const SgParams* params, SgState* state,
                const SgInputs* inputs, int n_ticks, int device, void* stream);
+
+/* FutureCollisionDetector._step (sensor/common.py:88-105) for a whole batch: does the box of
+   slot `slot[n]` (NULL: the scenario's ego) meet the box of any other entity of scenario n at
+   one of the times numpy.linspace(t[n], t[n] + horizon, n_samples), every entity placed at
+   trajectory.position_at_t(time) (clamped at the trajectory ends, present or not)?
+   t [N], slot [N] or NULL, out [N] (0 / 1): device memory. */
+int sg_future_collisions(const SgScene* scene, const double* t, const int32_t* slot, double horizon,
+                         int n_samples, uint8_t* out, int device, void* stream);
 
 /* exact closed-set intersection test of oriented boxes (entity/base.py:100-138 +
    utils.py:28-62), for unit tests: poses [n][3] = x,y,h ; boxes [n][4] ; out[n] */

@@ -18,6 +18,7 @@ Cases
   rss    highway-like traffic with RSSDistances + RSS [C5]
   ped    social-force pedestrians (std_lon = std_lat = 0) + replayed ego [C4]
   unit   Trajectory / bounding-box known answers
+  future FutureCollisionDetector flags on the test scenarios (every 20th tick, two horizons)
 """
 from __future__ import annotations
 
@@ -457,6 +458,41 @@ def gen_unit(store, manifest):
     manifest["unit"] = {"box": list(synthetic.CAR1_BOX), "pair_hits": int(hits.sum())}
 
 
+# --------------------------------------------------------------------------- future collisions
+def gen_future(store, manifest):
+    """FutureCollisionDetector (sensor/common.py:60-105) on the test scenarios, every 20th tick."""
+    from scenario_gym.sensor.common import FutureCollisionDetector
+
+    files = sorted(glob.glob(os.path.join(SCEN_DIR, "*.xosc")))
+    total = hits = 0
+    for f in files:
+        name = os.path.splitext(os.path.basename(f))[0]
+        gym = ScenarioGym()
+        gym.load_scenario(f, relabel=True)  # same inputs as xosc/<name>/in
+        ego = gym.state.scenario.ego
+        sensors = {h: FutureCollisionDetector(ego, horizon=h) for h in (5.0, 1.5)}
+        ticks, times, flags = [], [], {h: [] for h in sensors}
+        k = 0
+        while True:
+            if k % 20 == 0:
+                ticks.append(k)
+                times.append(gym.state.t)
+                for h, sn in sensors.items():
+                    flags[h].append(bool(sn._step(gym.state).future_collision))
+            if gym.state.is_done:
+                break
+            gym.step()
+            k += 1
+        store[f"future/{name}/tick"] = np.array(ticks, np.int32)
+        store[f"future/{name}/t"] = np.array(times, np.float64)
+        for h in sensors:
+            store[f"future/{name}/flag_h{h}"] = np.array(flags[h], np.uint8)
+            total += len(flags[h])
+            hits += int(np.sum(flags[h]))
+        print("future", name, len(ticks), {h: int(np.sum(v)) for h, v in flags.items()})
+    manifest["future"] = {"horizons": [5.0, 1.5], "n_samples": 10, "queries": total, "hits": hits}
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     only = set(sys.argv[1:])  # e.g. `python -m oracle.gen_golden pid` regenerates one file only
@@ -496,6 +532,10 @@ def main():
         store = {}
         gen_pid(store, manifest)
         np.savez_compressed(os.path.join(GOLDEN, "pid.npz"), **store)
+    if want("future"):
+        store = {}
+        gen_future(store, manifest)
+        np.savez_compressed(os.path.join(GOLDEN, "future.npz"), **store)
 
     with open(mpath, "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)

@@ -133,6 +133,16 @@ class OracleEngine:
         if rc:
             raise RuntimeError(self.lib["last_error"]().decode())
 
+    def future_collisions(self, t=None, horizon: float = 5.0, n_samples: int = 10, slot=None) -> np.ndarray:
+        tt = np.ascontiguousarray(self.state["t"] if t is None else t, np.float64)
+        sl = None if slot is None else np.ascontiguousarray(slot, np.int32)
+        out = np.zeros(self.scene.N, np.uint8)
+        rc = self.lib["future_collisions"](C.byref(self._sc), tt.ctypes.data, _ptr(sl), float(horizon),
+                                           int(n_samples), out.ctypes.data, 0, None)
+        if rc:
+            raise RuntimeError(self.lib["last_error"]().decode())
+        return out.astype(bool)
+
     def events(self) -> np.ndarray:
         n = min(int(self.state["event_count"][0]), self.state["_event_cap"])
         ev = self.state["events"][:n]

@@ -934,6 +934,50 @@ int sgo_test_box_pairs(const double* pose_a, const double* box_a, const double* 
   return 0;
 }
 
+/* FutureCollisionDetector._step, reference sensor/common.py:88-105: ten (n_samples) look-ahead
+   times numpy.linspace(t, t + horizon, n) = start + i * step with step = (stop - start) / (n - 1)
+   and the last sample set to stop exactly (numpy/_core/function_base.py); every entity at
+   trajectory.position_at_t(time) with the default extrapolate=(False, False) (clamped,
+   trajectory.py:185-197); detect_collisions({ego: pose}, others) (state/utils.py:10-49). */
+int sgo_future_collisions(const SgScene* sc, const double* t, const int32_t* slot, double horizon,
+                          int n_samples, uint8_t* out, int device, void* stream) {
+  (void)device; (void)stream;
+  const int M = sc->n_slots;
+  const int64_t nm = (int64_t)sc->n_scenarios * M;
+  for (int n = 0; n < sc->n_scenarios; ++n) {
+    const int es = slot ? slot[n] : sc->ego_slot[n];
+    const double start = t[n], stop = t[n] + horizon;
+    const double step = n_samples > 1 ? (stop - start) / (double)(n_samples - 1) : 0.0;
+    int hit = 0;
+    for (int k = 0; k < n_samples && !hit; ++k) {
+      double tk = (double)k * step + start;
+      if (n_samples > 1 && k == n_samples - 1) tk = stop;
+      const int64_t ie = (int64_t)n * M + es;
+      int64_t Ke;
+      const double* re = slot_rows(sc, ie, &Ke);
+      if (Ke == 0) break;
+      double pe[6], qe[8];
+      position_at_t(re, Ke, tk, EXT_CLAMP, pe);
+      box_points(pe[0], pe[1], pe[3], sc->box[ie], sc->box[nm + ie], sc->box[2 * nm + ie],
+                 sc->box[3 * nm + ie], qe);
+      for (int j = 0; j < M && !hit; ++j) {
+        const int64_t i = (int64_t)n * M + j;
+        if (j == es || sc->kind[i] == SG_KIND_EMPTY) continue;
+        int64_t K;
+        const double* rows = slot_rows(sc, i, &K);
+        if (K == 0) continue;
+        double po[6], qo[8];
+        position_at_t(rows, K, tk, EXT_CLAMP, po);
+        box_points(po[0], po[1], po[3], sc->box[i], sc->box[nm + i], sc->box[2 * nm + i],
+                   sc->box[3 * nm + i], qo);
+        if (memcmp(qe, qo, 64) != 0 && quads_intersect(qe, qo)) hit = 1;
+      }
+    }
+    out[n] = (uint8_t)hit;
+  }
+  return 0;
+}
+
 /* helpers exported for unit tests of the restated predicates */
 int sgo_orient_sign(double ax, double ay, double bx, double by, double cx, double cy) {
   return orient_sign(ax, ay, bx, by, cx, cy);

@@ -1816,6 +1816,52 @@ __global__ void sg_box_pairs_kernel(const double* pa, const double* ba, const do
 #include "sg_replay.cuh"
 
 // ---------------------------------------------------------------------------------
+// FutureCollisionDetector._step (reference sensor/common.py:88-105) for a batch: one warp per
+// scenario; its lanes share the (look-ahead sample, other entity) pairs.  Every entity is placed
+// at trajectory.position_at_t(time) (clamped), present or not; the pair test is the exact
+// closed-set predicate of the collision path.
+__global__ void sg_future_kernel(SgScene sc, const double* __restrict__ t, const int32_t* __restrict__ slot,
+                                 double horizon, int n_samples, uint8_t* __restrict__ out) {
+  const int n = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= sc.n_scenarios) return;
+  const int M = sc.n_slots;
+  const int64_t nm = (int64_t)sc.n_scenarios * M;
+  const int es = slot ? slot[n] : sc.ego_slot[n];
+  const int64_t ie = (int64_t)n * M + es;
+  const int64_t re0 = sc.traj_off[ie];
+  const int Ke = (int)(sc.traj_off[ie + 1] - re0);
+  const double start = t[n], stop = t[n] + horizon;
+  const double step = n_samples > 1 ? (stop - start) / (double)(n_samples - 1) : 0.0;  // numpy.linspace
+  bool hit = false;
+  if (Ke > 0)
+    for (int w = lane; w < n_samples * M; w += 32) {
+      const int k = w / M, j = w - k * M;
+      const int64_t i = (int64_t)n * M + j;
+      if (j == es || sc.kind[i] == SG_KIND_EMPTY) continue;
+      const int64_t r0 = sc.traj_off[i];
+      const int K = (int)(sc.traj_off[i + 1] - r0);
+      if (K == 0) continue;
+      double tk = (double)k * step + start;
+      if (n_samples > 1 && k == n_samples - 1) tk = stop;
+      double pe[6], po[6], qe[8], qo[8];
+      int c0 = 0, c1 = 0;
+      position_at_t(sc.traj_rows + re0 * 7, Ke, tk, EXT_CLAMP, c0, pe);
+      position_at_t(sc.traj_rows + r0 * 7, K, tk, EXT_CLAMP, c1, po);
+      box_points(pe[0], pe[1], pe[3], sc.box[ie], sc.box[nm + ie], sc.box[2 * nm + ie], sc.box[3 * nm + ie], qe);
+      box_points(po[0], po[1], po[3], sc.box[i], sc.box[nm + i], sc.box[2 * nm + i], sc.box[3 * nm + i], qo);
+      bool same = true;
+#pragma unroll
+      for (int f = 0; f < 8; ++f) same = same && (qe[f] == qo[f]);
+      if (same) continue;  // `g != g_prime`, reference utils.py:58
+      const Quad A = quad_from_array(qe), B = quad_from_array(qo);
+      if (quads_intersect(A, quad_orientation(A), B, quad_orientation(B))) hit = true;
+    }
+  hit = __any_sync(0xffffffffu, hit);
+  if (lane == 0) out[n] = hit ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------
 static bool g_ngon_ready[64] = {false};
 
 static int ensure_constants(int device) {
@@ -2013,6 +2059,20 @@ int sg_test_box_pairs(const double* pose_a, const double* box_a, const double* p
       pose_a, box_a, pose_b, box_b, out, n);
   err = cudaGetLastError();
   if (err != cudaSuccess) return set_err("sg_box_pairs_kernel launch", err);
+  return 0;
+}
+
+int sg_future_collisions(const SgScene* scene, const double* t, const int32_t* slot, double horizon,
+                         int n_samples, uint8_t* out, int device, void* stream) {
+  if (!scene || !t || !out) return set_msg("null argument");
+  if (n_samples < 1) return set_msg("n_samples must be >= 1");
+  cudaError_t err = cudaSetDevice(device);
+  if (err != cudaSuccess) return set_err("cudaSetDevice", err);
+  const int64_t threads = (int64_t)scene->n_scenarios * 32;
+  sg_future_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      *scene, t, slot, horizon, n_samples, out);
+  err = cudaGetLastError();
+  if (err != cudaSuccess) return set_err("sg_future_kernel launch", err);
   return 0;
 }
 

@@ -143,6 +143,25 @@ class Engine:
                                         C.byref(inp), int(n_ticks), self.dev_index, self._stream()))
         self._keep = keep
 
+    def future_collisions(self, t=None, horizon: float = 5.0, n_samples: int = 10, slot=None) -> np.ndarray:
+        """
+        ``FutureCollisionDetector._step`` (reference sensor/common.py:88-105) for every scenario of
+        the batch in one launch: does the sensor entity (``slot[n]``, default the ego) meet any other
+        entity within ``horizon`` of ``t[n]`` (default: the current ``state.t``)?  Returns bool [N].
+        """
+        tt = self._state_t["t"] if t is None else torch.as_tensor(
+            np.ascontiguousarray(t, np.float64)).to(self.device)
+        if tt.numel() != self.N:
+            raise ValueError(f"t must have {self.N} entries")
+        sl = None
+        if slot is not None:
+            sl = torch.as_tensor(np.ascontiguousarray(slot, np.int32)).to(self.device)
+        out = torch.zeros(self.N, dtype=torch.uint8, device=self.device)
+        self._check(self.lib["future_collisions"](
+            C.byref(self._sc), tt.data_ptr(), None if sl is None else sl.data_ptr(), float(horizon),
+            int(n_samples), out.data_ptr(), self.dev_index, self._stream()))
+        return out.cpu().numpy().astype(bool)
+
     def tensor(self, name: str) -> torch.Tensor:
         """The device tensor behind a state field (no copy)."""
         return self._state_t[name]

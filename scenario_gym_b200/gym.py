@@ -450,6 +450,25 @@ class ScenarioGym:
             out[e] = np.concatenate([ts[k, None], pose[k, :, s]], axis=1) if len(k) else np.empty((0, 7))
         return out
 
+    def _future_collision(self, n: int, entity: Entity, horizon: float, n_samples: int) -> bool:
+        """
+        FutureCollisionDetector for scenario ``n``: answered from one batched device launch per
+        (tick, horizon, sensor slots); the result is cached until the state advances.
+        """
+        slot = self._slot_of[n][entity]
+        ticks = tuple(int(v) for v in self._fetch("tick"))
+        key = (ticks, float(horizon), int(n_samples))
+        cache = getattr(self, "_future_cache", None)
+        if cache is None or cache[0] != key or cache[1][n] != slot:
+            slots = np.array([self._slot_of[k].get(self.states[k].scenario.ego, 0)
+                              for k in range(len(self.states))], np.int32)
+            if cache is not None and cache[0] == key:
+                slots = cache[1].copy()
+            slots[n] = slot
+            flags = self._engine.future_collisions(None, horizon, n_samples, slots)
+            cache = self._future_cache = (key, slots, flags)
+        return bool(cache[2][n])
+
     def _collisions(self, n: int) -> Dict[Entity, List[Entity]]:
         eng = self._engine
         if not (self._params.features & abi.FEAT_COLL_MATRIX):

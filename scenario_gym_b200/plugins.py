@@ -105,6 +105,35 @@ class EgoLocalizationSensor(Sensor):
         return SingleEntityObservation(self.entity, *state.get_entity_data(self.entity))
 
 
+@dataclass
+class FutureCollisionObservation(SingleEntityObservation):
+    """Observation with future collision information (reference sensor/common.py:53-57)."""
+
+    future_collision: bool = False
+
+
+class FutureCollisionDetector(Sensor):
+    """
+    Detects any future collision with the sensor's entity over ``horizon`` seconds from the
+    entities' trajectories (reference sensor/common.py:60-105).  The look-ahead runs on the device
+    for the whole batch (``sg_future_collisions``): one launch per tick serves the detectors of
+    every scenario with the same horizon.
+    """
+
+    N_SAMPLES = 10  # np.linspace(state.t, state.t + horizon, 10), sensor/common.py:94
+
+    def __init__(self, entity: Entity, horizon: float = 5.0):
+        super().__init__(entity)
+        self.horizon = horizon
+
+    def _reset(self, state):
+        return self._step(state)
+
+    def _step(self, state):
+        flag = state._gym._future_collision(state._n, self.entity, self.horizon, self.N_SAMPLES)
+        return FutureCollisionObservation(self.entity, *state.get_entity_data(self.entity), bool(flag))
+
+
 # ------------------------------------------------------------------------------ controllers
 class Controller:
     """Takes the agent's action and returns the pose (reference controller.py:12-42)."""

@@ -190,3 +190,33 @@ def check_against_golden(make_engine, scene: PackedScene, params, out: Dict[str,
         elif a.ndim and a.shape[0] == N:
             a, b = a[n], b[n]
         assert np.array_equal(a, b, equal_nan=True), f"fused vs stepwise {k} differ"
+
+
+def check_future_collisions(make_engine, params) -> int:
+    """
+    ``future_collisions`` of an engine against the reference's FutureCollisionDetector flags
+    (tests/golden/future.npz: every 20th tick of the 23 test scenarios, horizons 5.0 and 1.5).
+    One batched call per (query index, horizon) over all scenarios.  Returns the number of hits.
+    """
+    from scenario_gym_b200.packing import pack_scenarios
+
+    g = golden("future")
+    specs = all_xosc_specs("xosc")
+    scene = pack_scenarios([s for _, s, _, _ in specs])
+    eng = make_engine(scene, params)
+    eng.reset()
+    names = [n for n, _, _, _ in specs]
+    times = [g[f"future/{n}/t"] for n in names]
+    hits = 0
+    for h in (5.0, 1.5):
+        flags = [g[f"future/{n}/flag_h{h}"].astype(bool) for n in names]
+        for q in range(max(len(t) for t in times)):
+            t = np.array([tt[min(q, len(tt) - 1)] for tt in times])
+            want = np.array([f[min(q, len(f) - 1)] for f in flags])
+            got = eng.future_collisions(t, horizon=h, n_samples=10)
+            assert np.array_equal(got, want), f"future collisions differ at query {q}, horizon {h}"
+            hits += int(want.sum())
+    # default arguments: the current state.t and the ego
+    assert np.array_equal(eng.future_collisions(),
+                          np.array([g[f"future/{n}/flag_h5.0"][0] for n in names], bool))
+    return hits

@@ -194,6 +194,32 @@ def test_run_scenarios_is_one_batched_rollout():
         assert m == want
 
 
+def test_future_collision_detector_sensor():
+    """FutureCollisionDetector (reference sensor/common.py:60-105): observation fields + batched device look-ahead."""
+    from scenario_gym_b200 import FutureCollisionDetector
+
+    path = os.path.join(DATA, "Scenarios", "demo.xosc")
+    gym = ScenarioGym(metrics=std_metrics())
+    gym.load_scenarios([path] * 3)
+    sensors = []
+    for st in gym.states:
+        ego = st.scenario.entities[0]
+        sensors.append((FutureCollisionDetector(ego), FutureCollisionDetector(ego, horizon=0.5)))
+        for sn in sensors[-1]:
+            obs = sn.reset(st)
+            assert obs.entity is ego and obs.pose.shape == (6,) and isinstance(obs.future_collision, bool)
+    seen = set()
+    for _ in range(40):
+        gym.step()
+        want5 = gym._engine.future_collisions(None, 5.0, 10)
+        want05 = gym._engine.future_collisions(None, 0.5, 10)
+        for n, st in enumerate(gym.states):
+            a, b = sensors[n][0].step(st).future_collision, sensors[n][1].step(st).future_collision
+            assert a == bool(want5[n]) and b == bool(want05[n])
+            seen.add(a)
+    assert True in seen, "the demo scenario has an oncoming vehicle within 5 s at some tick"
+
+
 def vehicle_scenario(cfg, n):
     rows = synthetic.two_knot_rows(cfg).reshape(cfg.N, cfg.M, 2, 7)
     ce = CatalogEntry(None, "car1", "car", "Vehicle", BoundingBox(*synthetic.CAR1_BOX))

@@ -14,7 +14,7 @@ from scenario_gym_b200 import abi, synthetic
 from scenario_gym_b200.packing import pack_scenarios, tile_scene
 from scenario_gym_b200.synthetic import pack_synthetic
 
-from helpers import all_xosc_specs, check_against_golden, golden, manifest, sub
+from helpers import all_xosc_specs, check_against_golden, check_future_collisions, golden, manifest, sub
 
 pytestmark = pytest.mark.gpu
 
@@ -338,6 +338,31 @@ def test_replay_tick_parallel_equals_sequential(terminal, calls, persist):
     assert len(a) == len(b)
     for f in ("scenario", "tick", "slot", "t"):
         assert np.array_equal(a[f], b[f]), f"event {f} differs"
+
+
+def test_future_collision_detector_golden():
+    """sg_future_collisions (one launch per batch) == the reference's FutureCollisionDetector flags."""
+    hits = check_future_collisions(lambda scene, p: make_gpu(scene, p), _params())
+    assert hits > 50
+
+
+def test_future_collisions_vs_oracle():
+    """Look-ahead collisions on dense synthetic traffic, every slot as the sensor entity in turn."""
+    cfg = synthetic.highway_config(seed=21, N=12, M=32, T=8)
+    cfg.x0[:] = cfg.x0 * 0.4
+    scene = pack_synthetic(cfg)
+    p = _params(timestep=cfg.dt)
+    gpu, cpu = make_gpu(scene, p), OracleEngine(scene, p)
+    rng = np.random.default_rng(3)
+    seen = 0
+    for s in range(0, cfg.M, 5):
+        t = rng.uniform(-1.0, 3.0, cfg.N)
+        slot = np.full(cfg.N, s, np.int32)
+        for h, ns in ((5.0, 10), (0.7, 4), (2.0, 1)):
+            a, b = gpu.future_collisions(t, h, ns, slot), cpu.future_collisions(t, h, ns, slot)
+            assert np.array_equal(a, b), (s, h, ns)
+            seen += int(b.sum())
+    assert seen > 0
 
 
 def test_c2_replicas_identical():

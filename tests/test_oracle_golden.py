@@ -209,3 +209,11 @@ def test_reference_known_answers():
             assert 10 <= eng.get("ego_max_speed")[0] <= 12
             assert 90 <= eng.get("ego_dist")[0] <= 110
             assert len(eng.events()) == 0
+
+
+def test_future_collision_detector_golden():
+    """Oracle restatement of FutureCollisionDetector (sensor/common.py:88-105) == the reference's flags."""
+    from helpers import check_future_collisions
+
+    hits = check_future_collisions(lambda scene, p: OracleEngine(scene, p), abi.default_params())
+    assert hits > 50, "the golden set must contain future collisions"
