@@ -1094,6 +1094,7 @@ __device__ __noinline__ void broad_phase_direct(PairSink k, const float4* aabb, 
 }
 
 // phases B2 + C, shared by both kernel flavours.  Returns state.is_done.
+template <bool FAST>
 SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int n, int s, int W,
                         int G, int ego_slot, int first_slot, int parity, int tick, double t,
                         double dt, double length, bool live, bool present, uint8_t& collided,
@@ -1126,7 +1127,10 @@ SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int 
   if ((p.terminal & SG_TERM_MAX_LENGTH) && (t + dt > length)) dn = true;
   if ((p.terminal & SG_TERM_COLLISION) && npairs > 0) dn = true;
   if ((p.terminal & SG_TERM_EGO_COLLISION) && acc[ACC_FIRST_HIT]) dn = true;
-  if (s == 0) {
+  // the single-lane book-keeping runs in another warp than the ego's metrics when there is one,
+  // so that neither warp of the scenario carries all the serial work of the tick
+  const int bs = s - ((G > 32 && ego_slot < 32) ? 32 : 0);
+  if (bs == 0) {
     int* cold = c.cold_i;
     if (npairs > 0) {
       *(long long*)(cold + COLD_PAIR_TICKS) += npairs;
@@ -1140,29 +1144,31 @@ SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int 
     nx[ACC_NPAIRS] = 0; nx[ACC_FIRST_PAIR] = 0x7fffffff; nx[ACC_FIRST_HIT] = 0; nx[ACC_RSS] = 0;
     nx[ACC_QCOUNT] = 0;
   }
-  if (s < W) {  // CollisionMetric._step, metrics/collision.py:70-75
-    const uint32_t now = c.ego_now[s];
+  if (bs >= 0 && bs < W) {  // CollisionMetric._step, metrics/collision.py:70-75
+    const uint32_t now = c.ego_now[bs];
     if (p.features & SG_FEAT_COLLISIONS) {
-      uint32_t fresh = now & ~c.ego_last[s];
+      uint32_t fresh = now & ~c.ego_last[bs];
       while (fresh) {
         const int b = __ffs(fresh) - 1;
         fresh &= fresh - 1;
         const int slot = atomicAdd(st.event_count, 1);
         if (slot < st.event_cap) {
           SgEvent ev;
-          ev.scenario = n; ev.tick = tick; ev.slot = s * 32 + b; ev._pad = 0; ev.t = t;
+          ev.scenario = n; ev.tick = tick; ev.slot = bs * 32 + b; ev._pad = 0; ev.t = t;
           st.events[slot] = ev;
         }
       }
-      c.ego_last[s] = now;
+      c.ego_last[bs] = now;
     }
-    c.ego_now[s] = 0;
-    c.bits[(parity ^ 1) * W + s] = 0;
+    c.ego_now[bs] = 0;
+    c.bits[(parity ^ 1) * W + bs] = 0;
   }
   if (s == ego_slot && (p.features & SG_FEAT_EGO_METRICS)) {  // metrics/trajectory.py:20-24,39-42,58-60
     double* m = c.cold_d;
-    const double sp = norm3(vx, vy, vz);
-    const double w = m[COLD_AVG_T] / t;
+    // (FAST: the vehicle tick's tolerance-level square root / quotient; the general kernel keeps
+    // the IEEE operations so that replayed scenes give the same bits on every path)
+    const double sp = FAST ? fast_sqrt(vx * vx + vy * vy + vz * vz) : norm3(vx, vy, vz);
+    const double w = (FAST && t > 0.0) ? div_r(m[COLD_AVG_T], t, fast_rcp(t)) : m[COLD_AVG_T] / t;
     m[COLD_AVG] += (1.0 - w) * (sp - m[COLD_AVG]);
     m[COLD_AVG_T] = t;
     m[COLD_MAX] = fmax(sp, m[COLD_MAX]);
@@ -1196,13 +1202,15 @@ SG_DEV void store_cold(const SgState& st, const Grp& c, int n, int s, int W, int
     st.ego_avg_speed[n] = c.cold_d[COLD_AVG]; st.ego_avg_t[n] = c.cold_d[COLD_AVG_T];
     st.ego_max_speed[n] = c.cold_d[COLD_MAX]; st.ego_dist[n] = c.cold_d[COLD_EGOD];
   }
-  if (s == 0) {
+  // written back by the threads that keep them in finish_tick (no barrier after the last tick)
+  const int bs = s - ((c.G > 32 && ego_slot < 32) ? 32 : 0);
+  if (bs == 0) {
     st.first_coll_tick[n] = c.cold_i[COLD_FIRST_TICK];
     st.first_coll_pair[2 * n] = c.cold_i[COLD_FP0]; st.first_coll_pair[2 * n + 1] = c.cold_i[COLD_FP1];
     st.n_pair_ticks[n] = *(long long*)(c.cold_i + COLD_PAIR_TICKS);
     st.rss_flags[n] = (uint8_t)c.cold_i[COLD_RSS];
   }
-  if (s < W) st.ego_hits[(int64_t)n * W + s] = c.ego_last[s];
+  if (bs >= 0 && bs < W) st.ego_hits[(int64_t)n * W + bs] = c.ego_last[bs];
 }
 
 SG_DEV RssConst make_rss_const(const SgParams& p) {
@@ -1366,7 +1374,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       if (need_coll) broad_phase(c, parity);
     }
     group_sync(c);
-    done = finish_tick(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick,
+    done = finish_tick<true>(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick,
                        c.cold_d[COLD_T0 + (parity ^ 1)], c.cold_d[COLD_T0 + (parity ^ 1)] - c.cold_d[COLD_PT0 + (parity ^ 1)],
                        c.cold_d[COLD_LEN], live, live && present, collided, vx, vy, 0.0, dist);
     parity ^= 1;
@@ -1667,7 +1675,7 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       if (need_coll && live && e.present) broad_phase_grid(c, parity, gpos);
     }
     group_sync(c);
-    done = finish_tick(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick, t, dt, length, live,
+    done = finish_tick<false>(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick, t, dt, length, live,
                        live && e.present, collided, e.vel[0], e.vel[1], e.vel[2], e.dist);
     parity ^= 1;
   }
