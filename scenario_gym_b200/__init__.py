@@ -8,7 +8,8 @@ gym / engine does (there is no CPU fallback).
 """
 from .entity import BoundingBox, CatalogEntry, Entity, MiscObject, Pedestrian, Vehicle
 from .gym import ScenarioGym
-from .plugins import (RSS, Action, ActionTableAgent, Agent, CollisionMetric, Controller,
+from .plugins import (RSS, Action, ActionTableAgent, Agent, CollisionMetric, CollisionObservation,
+                      CombinedSensor, Controller, GlobalCollisionDetector, combine_observations,
                       EgoAvgSpeed, EgoDistanceTravelled, EgoLocalizationSensor, EgoMaxSpeed,
                       FutureCollisionDetector, FutureCollisionObservation, Metric,
                       Observation, PedestrianAction, PedestrianAgent, PIDAgent, PIDController, ReplayTrajectoryAgent,

@@ -471,18 +471,48 @@ class ScenarioGym:
 
     def _collisions(self, n: int) -> Dict[Entity, List[Entity]]:
         eng = self._engine
-        if not (self._params.features & abi.FEAT_COLL_MATRIX):
-            raise RuntimeError("state.collisions() needs the pair matrix; it is enabled whenever a "
-                               "host-side plugin is present")
-        mask = eng.tensor("coll_mask")[n].cpu().numpy().view(np.uint32)
         ents = self._entity_of[n]
         present = eng.tensor("present")[n * eng.M:(n + 1) * eng.M].cpu().numpy()
+        if not (self._params.features & abi.FEAT_COLL_MATRIX):
+            # no per-tick pair matrix on this run (it is kept whenever a host-side plugin is
+            # present): test the present entities' current boxes pairwise on the device
+            return self._collisions_on_demand(n, ents, present)
+        mask = eng.tensor("coll_mask")[n].cpu().numpy().view(np.uint32)
         out = {}
         for a, e in enumerate(ents):
             if not present[a]:
                 continue
             out[e] = [ents[b] for b in range(len(ents))
                       if (int(mask[a, b >> 5]) >> (b & 31)) & 1]
+        return out
+
+    def _collisions_on_demand(self, n: int, ents, present) -> Dict[Entity, List[Entity]]:
+        import ctypes as C
+
+        import torch
+
+        eng = self._engine
+        M = eng.M
+        idx = [a for a in range(len(ents)) if present[a]]
+        out = {ents[a]: [] for a in idx}
+        pairs = [(a, b) for i, a in enumerate(idx) for b in idx[i + 1:]]
+        if not pairs:
+            return out
+        pose = eng.tensor("pose").view(6, -1)[:, n * M:(n + 1) * M].cpu().numpy()
+        box = eng._scene_t["box"].view(4, -1)[:, n * M:(n + 1) * M].cpu().numpy()
+        ia, ib = np.array([a for a, _ in pairs]), np.array([b for _, b in pairs])
+        dev = eng.device
+        pa = torch.from_numpy(np.ascontiguousarray(pose[[0, 1, 3]][:, ia].T)).to(dev)
+        pb = torch.from_numpy(np.ascontiguousarray(pose[[0, 1, 3]][:, ib].T)).to(dev)
+        ba = torch.from_numpy(np.ascontiguousarray(box[:, ia].T)).to(dev)
+        bb = torch.from_numpy(np.ascontiguousarray(box[:, ib].T)).to(dev)
+        hit = torch.zeros(len(pairs), dtype=torch.uint8, device=dev)
+        eng._check(eng.lib["test_box_pairs"](pa.data_ptr(), ba.data_ptr(), pb.data_ptr(), bb.data_ptr(),
+                                             hit.data_ptr(), len(pairs), eng.dev_index, eng._stream()))
+        for (a, b), h in zip(pairs, hit.cpu().numpy()):
+            if h:
+                out[ents[a]].append(ents[b])
+                out[ents[b]].append(ents[a])
         return out
 
     def _collision_events(self, n: int) -> list:

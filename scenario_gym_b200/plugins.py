@@ -105,6 +105,72 @@ class EgoLocalizationSensor(Sensor):
         return SingleEntityObservation(self.entity, *state.get_entity_data(self.entity))
 
 
+def combine_observations(*obs_classes, prefixes=None):
+    """
+    A dataclass holding the fields of several observation classes (reference observation.py:31-83):
+    the first class that defines a field name provides it; with ``prefixes`` a repeated name is
+    kept as ``f"{prefix}_{name}"`` instead of being skipped.  The class gets ``from_obs(*obs)``.
+    """
+    import dataclasses
+
+    if prefixes is not None and len(prefixes) != len(obs_classes):
+        raise ValueError
+    spec, source = [], []
+    for idx, oc in enumerate(obs_classes):
+        if not dataclasses.is_dataclass(oc):
+            raise TypeError(f"Observation {oc} is not a dataclass.")
+        for f in dataclasses.fields(oc):
+            name = f.name
+            if any(name == n for n, _ in spec):
+                if prefixes is None:
+                    continue
+                name = f"{prefixes[idx]}_{f.name}"
+                if any(name == n for n, _ in spec):
+                    raise ValueError(f"Prefix {prefixes[idx]} still leads to duplicate name for {name}.")
+            spec.append((name, f.type))
+            source.append((idx, f.name))
+
+    def from_obs(cls, *obs):
+        return cls(*(getattr(obs[i], name) for i, name in source))
+
+    return dataclasses.make_dataclass("CombinedObservation", spec, bases=(Observation,),
+                                      namespace={"from_obs": classmethod(from_obs)})
+
+
+class CombinedSensor(Sensor):
+    """Combines the observations of several sensors of one entity (reference sensor/common.py:18-36)."""
+
+    def __init__(self, entity: Entity, *sensors: Sensor):
+        super().__init__(entity)
+        self.sensors = sensors
+        self.obs_class = None
+
+    def _reset(self, state):
+        init_obs = [s.reset(state) for s in self.sensors]
+        self.obs_class = combine_observations(*(o.__class__ for o in init_obs))
+        return self.obs_class.from_obs(*init_obs)
+
+    def _step(self, state):
+        return self.obs_class.from_obs(*(s.step(state) for s in self.sensors))
+
+
+@dataclass
+class CollisionObservation(SingleEntityObservation):
+    """Observation with detected collisions (reference sensor/common.py:108-112)."""
+
+    collisions: Any = None
+
+
+class GlobalCollisionDetector(Sensor):
+    """Returns the collisions observed in the scene (reference sensor/common.py:115-128)."""
+
+    def _reset(self, state):
+        return self._step(state)
+
+    def _step(self, state):
+        return CollisionObservation(self.entity, *state.get_entity_data(self.entity), state.collisions())
+
+
 @dataclass
 class FutureCollisionObservation(SingleEntityObservation):
     """Observation with future collision information (reference sensor/common.py:53-57)."""

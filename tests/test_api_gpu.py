@@ -220,6 +220,26 @@ def test_future_collision_detector_sensor():
     assert True in seen, "the demo scenario has an oncoming vehicle within 5 s at some tick"
 
 
+def test_combined_sensor():
+    """Reference tests/test_sensor.py:12-37: combined observation exposes every sensor's fields."""
+    from scenario_gym_b200 import (CombinedSensor, EgoLocalizationSensor, FutureCollisionDetector,
+                                   GlobalCollisionDetector)
+
+    gym = ScenarioGym()
+    gym.load_scenario(os.path.join(DATA, "Scenarios", "demo.xosc"))
+    ego = gym.state.scenario.entities[0]
+    sensor = CombinedSensor(ego, EgoLocalizationSensor(ego), FutureCollisionDetector(ego),
+                            GlobalCollisionDetector(ego))
+    assert sensor.obs_class is None
+    sensor.reset(gym.state)
+    assert sensor.obs_class is not None
+    gym.step()
+    obs = sensor.step(gym.state)
+    assert obs.pose.shape == (6,) and isinstance(obs.future_collision, bool)
+    assert set(obs.collisions) == set(gym.state.poses)  # present entities only (reference state/utils.py)
+    assert obs.collisions == gym.state.collisions()
+
+
 def vehicle_scenario(cfg, n):
     rows = synthetic.two_knot_rows(cfg).reshape(cfg.N, cfg.M, 2, 7)
     ce = CatalogEntry(None, "car1", "car", "Vehicle", BoundingBox(*synthetic.CAR1_BOX))
