@@ -486,88 +486,108 @@ SG_DEV void broad_phase_grid(const Grp& c, int parity, const GridPos& g) {
   }
 }
 
-// PedestrianAgent._step + SocialForce._step + PedestrianController._step
+// Contribution of neighbour slot o to the pedestrian standing at (px, py), as the two vector terms
+// SocialForce adds for it in application order (reference social_force.py:51-80, 140-188,
+// 213-222): with sight weights w_r F_rep then w_a F_att, without them F_att then F_rep.
+struct NbForce {
+  int valid;
+  double a0, a1, b0, b1;
+};
+SG_DEV NbForce neighbour_force(const SgParams& p, const Grp& c, double px, double py, int o, double step_dt,
+                               double sh, double ch, double sight_cos) {
+  NbForce f;
+  f.valid = 0; f.a0 = 0.0; f.a1 = 0.0; f.b0 = 0.0; f.b1 = 0.0;
+  const double* bx = c.pedbuf;
+  const double* by = c.pedbuf + c.G;
+  const double* bvx = c.pedbuf + 2 * c.G;
+  const double* bvy = c.pedbuf + 3 * c.G;
+  const double ox = bx[o], oy = by[o];
+  if (!in_buffer(px, py, p.ped_distance_threshold, ox, oy)) return f;
+  f.valid = 1;
+  const double ovx = bvx[o], ovy = bvy[o];
+  // (tolerance path: square roots and quotients through the rsqrt / rcp seeded helpers, < 1 ulp)
+  const double vdx = ovx * ch + ovy * -sh, vdy = ovx * sh + ovy * ch;
+  const double vn = fnorm2(vdx, vdy) + 0.0000000001, rvn = fast_rcp(vn);
+  const double view0 = div_r(vdx, vn, rvn), view1 = div_r(vdy, vn, rvn);
+  // _force_pedestrian_repulsion :140-176
+  const double rx = px - ox, ry = py - oy, rn = fnorm2(rx, ry), rrn = fast_rcp(rn);
+  const double vmag = fnorm2(ovx, ovy) + 0.0000000001, rvm = fast_rcp(vmag);
+  const double uox = div_r(ovx, vmag, rvm), uoy = div_r(ovy, vmag, rvm);
+  const double other_step = vmag * step_dt;
+  const double r2x = rx - other_step * uox, r2y = ry - other_step * uoy;
+  const double r2n = fnorm2(r2x, r2y) + 0.0000000001, rr2 = fast_rcp(r2n);
+  const double b = (1.0 / 2) * fast_sqrt((rn + r2n) * (rn + r2n) - other_step * other_step);
+  const double c0 = (1.0 / 4) * fast_rcp(b) * (rn + r2n);
+  const double dbx = c0 * (div_r(rx, rn, rrn) + div_r(r2x, r2n, rr2)),
+               dby = c0 * (div_r(ry, rn, rrn) + div_r(r2y, r2n, rr2));
+  const double g = p.sf_ped_repulse_V / p.sf_ped_repulse_sigma * exp(-b / p.sf_ped_repulse_sigma);
+  const double Fr0 = g * dbx, Fr1 = g * dby;
+  const double Fa0 = 2 * p.sf_ped_attract_C * rx, Fa1 = 2 * p.sf_ped_attract_C * ry;
+  if (p.sf_sight_weight_use) {  // _sight_weight :213-222
+    const double nr = fnorm2(Fr0, Fr1) + 0.0000000001, na = fnorm2(Fa0, Fa1) + 0.0000000001;
+    double dd = div_r(dot2(view0, view1, Fr0, Fr1), nr, fast_rcp(nr));
+    double w = dd >= sight_cos ? 1.0 : p.sf_sight_weight;
+    f.a0 = w * Fr0; f.a1 = w * Fr1;
+    dd = div_r(dot2(view0, view1, Fa0, Fa1), na, fast_rcp(na));
+    w = dd >= sight_cos ? 1.0 : p.sf_sight_weight;
+    f.b0 = w * Fa0; f.b1 = w * Fa1;
+  } else {
+    f.a0 = Fa0; f.a1 = Fa1;
+    f.b0 = Fr0; f.b1 = Fr1;
+  }
+  return f;
+}
+
+// PedestrianAgent._step + SocialForce._step + PedestrianController._step.  Called by every lane
+// (is_ped = this lane steps a pedestrian this tick).  With `coop` (whole warps per scenario) the
+// (pedestrian, neighbour) terms of a warp are pooled and spread evenly over its 32 lanes - a lane
+// no longer waits for the pedestrian with the most neighbours - and handed back to their owners
+// with shuffles in list order, so every force is the same sum in the same order.
 template <bool PED>
-SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c,
+SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c, bool is_ped, bool coop,
                             const double pose[6], const double vel[6], double t, double prev_t,
                             double next_t, double sight_cos, int& goal, double force[2],
                             double& speed_io, double out[6], bool use_grid, double ox, double oy,
                             double inv_cs) {
   if (!PED) return;
-  const int64_t r0 = sc.route_off[c.i];
-  const int R = (int)(sc.route_off[c.i + 1] - r0);
-  const double* route = sc.route_xy + 2 * r0;
-  double speed, heading;
-  if (goal <= R - 1) {  // pedestrian/agent.py:60-62
-    const double sarc = route_project(route, R, pose[0], pose[1]);
-    double arc = 0.0;
-    int last = 0;
-    for (int k = 0; k < R; ++k) {
-      if (k > 0)
-        arc += norm2(__ldg(route + 2 * k) - __ldg(route + 2 * k - 2),
-                     __ldg(route + 2 * k + 1) - __ldg(route + 2 * k - 1));
-      if (arc <= sarc) last = k;
+  const double* route = nullptr;
+  int R = 0, ncand = 0;
+  bool walking = false;
+  double F0 = 0.0, F1 = 0.0, speed_desired = 0.0;
+  double sh, ch;
+  sincos(p.ped_head_rot_angle, &sh, &ch);  // viewer/utils.py:6-17
+  const float4 mb = c.pednb[c.s];
+  uint16_t* nbl = c.nblist + c.s;
+  if (is_ped) {
+    const int64_t r0 = sc.route_off[c.i];
+    R = (int)(sc.route_off[c.i + 1] - r0);
+    route = sc.route_xy + 2 * r0;
+    if (goal <= R - 1) {  // pedestrian/agent.py:60-62
+      const double sarc = route_project(route, R, pose[0], pose[1]);
+      double arc = 0.0;
+      int last = 0;
+      for (int k = 0; k < R; ++k) {
+        if (k > 0)
+          arc += norm2(__ldg(route + 2 * k) - __ldg(route + 2 * k - 2),
+                       __ldg(route + 2 * k + 1) - __ldg(route + 2 * k - 1));
+        if (arc <= sarc) last = k;
+      }
+      goal = last + 1;
     }
-    goal = last + 1;
+    walking = goal <= R - 1;
   }
-  if (goal <= R - 1) {
-    const double speed_desired = sc.ped_speed_desired[c.i];
+  if (walking) {
+    speed_desired = sc.ped_speed_desired[c.i];
     // SocialForce._force_to_goal, pedestrian/social_force.py:119-138
     const double dvx = __ldg(route + 2 * goal) - pose[0], dvy = __ldg(route + 2 * goal + 1) - pose[1];
     double dn = norm2(dvx, dvy);
     if (dn == 0) dn += 0.000000001;
     const double ux = dvx / dn, uy = dvy / dn;
     const double k = 1 / p.sf_relaxation_time;
-    double F0 = k * (speed_desired * ux - vel[0]), F1 = k * (speed_desired * uy - vel[1]);
-    const double thr = p.ped_distance_threshold;
-    double sh, ch;
-    sincos(p.ped_head_rot_angle, &sh, &ch);  // viewer/utils.py:6-17
-    const double* bx = c.pedbuf;
-    const double* by = c.pedbuf + c.G;
-    const double* bvx = c.pedbuf + 2 * c.G;
-    const double* bvy = c.pedbuf + 3 * c.G;
-    // neighbour force of slot o (reference social_force.py:51-80, 140-188, 213-222)
-    auto add_neighbour = [&](int o) {
-      const double ox = bx[o], oy = by[o];
-      if (!in_buffer(pose[0], pose[1], thr, ox, oy)) return;
-      const double ovx = bvx[o], ovy = bvy[o];
-      // (tolerance path: square roots and quotients through the rsqrt / rcp seeded helpers, < 1 ulp)
-      const double vdx = ovx * ch + ovy * -sh, vdy = ovx * sh + ovy * ch;
-      const double vn = fnorm2(vdx, vdy) + 0.0000000001, rvn = fast_rcp(vn);
-      const double view0 = div_r(vdx, vn, rvn), view1 = div_r(vdy, vn, rvn);
-      // _force_pedestrian_repulsion :140-176
-      const double rx = pose[0] - ox, ry = pose[1] - oy, rn = fnorm2(rx, ry), rrn = fast_rcp(rn);
-      const double vmag = fnorm2(ovx, ovy) + 0.0000000001, rvm = fast_rcp(vmag);
-      const double uox = div_r(ovx, vmag, rvm), uoy = div_r(ovy, vmag, rvm);
-      const double other_step = vmag * (next_t - t);
-      const double r2x = rx - other_step * uox, r2y = ry - other_step * uoy;
-      const double r2n = fnorm2(r2x, r2y) + 0.0000000001, rr2 = fast_rcp(r2n);
-      const double b = (1.0 / 2) * fast_sqrt((rn + r2n) * (rn + r2n) - other_step * other_step);
-      const double c0 = (1.0 / 4) * fast_rcp(b) * (rn + r2n);
-      const double dbx = c0 * (div_r(rx, rn, rrn) + div_r(r2x, r2n, rr2)),
-                   dby = c0 * (div_r(ry, rn, rrn) + div_r(r2y, r2n, rr2));
-      const double g = p.sf_ped_repulse_V / p.sf_ped_repulse_sigma * exp(-b / p.sf_ped_repulse_sigma);
-      const double Fr0 = g * dbx, Fr1 = g * dby;
-      const double Fa0 = 2 * p.sf_ped_attract_C * rx, Fa1 = 2 * p.sf_ped_attract_C * ry;
-      if (p.sf_sight_weight_use) {  // _sight_weight :213-222
-        const double nr = fnorm2(Fr0, Fr1) + 0.0000000001, na = fnorm2(Fa0, Fa1) + 0.0000000001;
-        double dd = div_r(dot2(view0, view1, Fr0, Fr1), nr, fast_rcp(nr));
-        double w = dd >= sight_cos ? 1.0 : p.sf_sight_weight;
-        F0 += w * Fr0; F1 += w * Fr1;
-        dd = div_r(dot2(view0, view1, Fa0, Fa1), na, fast_rcp(na));
-        w = dd >= sight_cos ? 1.0 : p.sf_sight_weight;
-        F0 += w * Fa0; F1 += w * Fa1;
-      } else {
-        F0 += Fa0; F1 += Fa1;
-        F0 += Fr0; F1 += Fr1;
-      }
-    };
-    // sensor: fp32 box prefilter over the slots in state.poses (= slot) order; candidates are first
-    // collected per thread, then the k-th candidates of all lanes are evaluated together
-    const float4 mb = c.pednb[c.s];
-    uint16_t* nbl = c.nblist + c.s;
-    int ncand = 0;
-    if (use_grid) {  // candidates from the 3 x 3 cells around the pedestrian, then put in slot order
+    F0 = k * (speed_desired * ux - vel[0]);
+    F1 = k * (speed_desired * uy - vel[1]);
+    // sensor: fp32 box prefilter; candidates are collected per pedestrian in slot (= state.poses) order
+    if (use_grid) {  // from the 3 x 3 cells around the pedestrian, then put in slot order
       const int ix = __double2int_rd((pose[0] - ox) * inv_cs), iy = __double2int_rd((pose[1] - oy) * inv_cs);
       for (int dy = -1; dy <= 1; ++dy) {
         int beg[2], end[2];
@@ -587,15 +607,6 @@ SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c,
         while (b >= 0 && nbl[b * c.G] > v) { nbl[(b + 1) * c.G] = nbl[b * c.G]; --b; }
         nbl[(b + 1) * c.G] = v;
       }
-      if (ncand <= SG_NBCAP) {
-        for (int k = 0; k < ncand; ++k) add_neighbour(nbl[k * c.G]);
-      } else {  // very dense crowd: exhaustive sweep in slot order
-        for (int o = 0; o < c.M; ++o) {
-          const float4 ob = c.pednb[o];
-          if (o == c.s || !(mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w)) continue;
-          add_neighbour(o);
-        }
-      }
     } else {
       for (int o0 = 0; o0 < c.M; o0 += 32) {
         uint32_t cand = 0;
@@ -612,16 +623,71 @@ SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c,
           ++ncand;
         }
       }
-      for (int k = 0; k < min(ncand, SG_NBCAP); ++k) add_neighbour(nbl[k * c.G]);
-      if (ncand > SG_NBCAP) {  // very dense crowd: re-sweep for the candidates beyond the list
-        int seen = 0;
-        for (int o = 0; o < c.M; ++o) {
-          const float4 ob = c.pednb[o];
-          if (o == c.s || !(mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w)) continue;
-          if (seen++ >= SG_NBCAP) add_neighbour(o);
-        }
+    }
+  }
+  // neighbour terms of the listed candidates (grid mode: a list that overflowed is not used)
+  const int nlist = !walking ? 0 : (use_grid ? (ncand <= SG_NBCAP ? ncand : 0) : min(ncand, SG_NBCAP));
+  const double step_dt = next_t - t;
+  if (coop) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wslot0 = c.s - lane;
+    int incl = nlist;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += v;
+    }
+    const int off = incl - nlist, total = __shfl_sync(FULL, incl, 31);
+    __syncwarp();  // the candidate lists of the warp's lanes are complete
+    for (int base = 0; base < total; base += 32) {
+      const int it = base + lane;
+      int q = 0;  // owner lane of item `it`: the first lane whose inclusive count exceeds it
+#pragma unroll
+      for (int stp = 16; stp > 0; stp >>= 1) {
+        const int tq = __shfl_sync(FULL, incl, (q + stp - 1) & 31);
+        if (tq <= it) q += stp;
+      }
+      q &= 31;
+      const int offq = __shfl_sync(FULL, off, q);
+      NbForce nf;
+      nf.valid = 0; nf.a0 = 0.0; nf.a1 = 0.0; nf.b0 = 0.0; nf.b1 = 0.0;
+      if (it < total) {
+        const int slot = wslot0 + q;
+        const int o = c.nblist[(it - offq) * c.G + slot];
+        nf = neighbour_force(p, c, c.pedbuf[slot], c.pedbuf[c.G + slot], o, step_dt, sh, ch, sight_cos);
+      }
+      // hand the terms back: this lane owns items [lo, hi) of the round, in list order
+      const int lo = max(off, base), hi = min(off + nlist, base + 32);
+      const int cnt = max(hi - lo, 0);
+      const int maxc = __reduce_max_sync(FULL, cnt);
+      for (int jj = 0; jj < maxc; ++jj) {
+        const int src = (lo - base + jj) & 31;
+        const int v = __shfl_sync(FULL, nf.valid, src);
+        const double a0 = __shfl_sync(FULL, nf.a0, src), a1 = __shfl_sync(FULL, nf.a1, src);
+        const double b0 = __shfl_sync(FULL, nf.b0, src), b1 = __shfl_sync(FULL, nf.b1, src);
+        if (jj < cnt && v) { F0 += a0; F1 += a1; F0 += b0; F1 += b1; }
       }
     }
+  } else {
+    for (int k = 0; k < nlist; ++k) {
+      const NbForce nf = neighbour_force(p, c, pose[0], pose[1], nbl[k * c.G], step_dt, sh, ch, sight_cos);
+      if (nf.valid) { F0 += nf.a0; F1 += nf.a1; F0 += nf.b0; F1 += nf.b1; }
+    }
+  }
+  if (walking && ncand > SG_NBCAP) {  // very dense crowd: the candidates beyond / instead of the list
+    int seen = 0;
+    for (int o = 0; o < c.M; ++o) {
+      const float4 ob = c.pednb[o];
+      if (o == c.s || !(mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w)) continue;
+      if (use_grid || seen++ >= SG_NBCAP) {
+        const NbForce nf = neighbour_force(p, c, pose[0], pose[1], o, step_dt, sh, ch, sight_cos);
+        if (nf.valid) { F0 += nf.a0; F1 += nf.a1; F0 += nf.b0; F1 += nf.b1; }
+      }
+    }
+  }
+  if (!is_ped) return;
+  double speed, heading;
+  if (walking) {
     speed = py_min(norm2(F0, F1) + p.sf_bias_lon, speed_desired * p.sf_max_speed_factor);
     heading = atan2(F1, F0) + p.sf_bias_lat;
     force[0] = F0;
@@ -1512,6 +1578,11 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     double np_[6];
     bool newpres = false;
     double newspeed = e.speed;
+    double ped_np[6], ped_speed = e.speed;
+    if (PED)  // every lane calls: whole warps of a scenario share the neighbour terms
+      pedestrian_step<PED>(sc, p, c, kind == SG_KIND_PEDESTRIAN && e.present, G >= 32, e.pose, e.vel, t,
+                           prev_t, next_t, sight_cos, goal, force, ped_speed, ped_np, use_grid, ox, oy,
+                           grid_inv_cs);
     if (kind >= SG_KIND_AGENT_REPLAY) {  // scenario_gym.py:233-244
       if (e.present) {
         if (kind == SG_KIND_AGENT_REPLAY) {  // agent.py:125-128, extrapolate=(False, False)
@@ -1564,8 +1635,9 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
           newspeed = ns;
           newpres = true;
         } else if (kind == SG_KIND_PEDESTRIAN) {
-          pedestrian_step<PED>(sc, p, c, e.pose, e.vel, t, prev_t, next_t, sight_cos, goal, force,
-                               newspeed, np_, use_grid, ox, oy, grid_inv_cs);
+#pragma unroll
+          for (int f = 0; f < 6; ++f) np_[f] = ped_np[f];
+          newspeed = ped_speed;
           newpres = true;
         } else {  // SG_KIND_HOST
           if (in.host_present && in.host_present[i]) {
