@@ -26,6 +26,9 @@
 
 #define SG_THREADS 256
 #define SG_NBCAP 12  // per-pedestrian neighbour candidate list kept in shared memory
+#ifndef SG_WARP_PAIRS
+#define SG_WARP_PAIRS 6  // queued pairs per warp up to which the narrow phase runs warp-cooperatively
+#endif
 // uniform cell grid of a crowd scenario (one CTA per scenario): 64 x 64 cells, toroidal
 #define SG_GRID_BITS 6
 #define SG_GRID_DIM (1 << SG_GRID_BITS)
@@ -1169,8 +1172,9 @@ SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int 
   const int nq = acc[ACC_QCOUNT];
   if (nq > 0) {  // phase B2: exact narrow phase on the queued pairs
     const PairSink sink = make_sink(p.features, st.coll_mask, c, ego_slot, first_slot, parity);
-    if (G >= 32 && nq <= 2 * (G >> 5)) {
-      // few pairs (the usual case): one warp per pair, all lanes share the orientation tests
+    if (G >= 32 && nq <= SG_WARP_PAIRS * (G >> 5)) {
+      // up to a few pairs per warp (the usual case): a warp per pair, all lanes share the orientation
+      // tests (~300 cycles per pair against ~2500 for one lane walking the edges)
       for (int q = s >> 5; q < nq; q += G >> 5) {
         const uint32_t pr = c.queue[q];
         const int a = (int)(pr >> 16), b = (int)(pr & 0xffff);
