@@ -63,6 +63,8 @@ struct GroupLayout {
   int QCAP;     // candidate-pair queue capacity
   int off_act, off_rbox, off_tcold, off_hcs, off_ped, off_pednb, off_nbl, off_box, off_ego, off_cold, off_aabb, off_queue, off_hits, off_bits,
       off_acc, off_flags, off_orient;
+  int sorted;   // vehicle scenes with M >= 128: boxes kept sorted by their lower x bound, windowed sweep
+  int off_sid, off_posof, off_sflag;
   int grid;     // crowd scenario with a shared-memory cell grid (sensor + broad phase)
   int off_gstart, off_gsorted, off_glarge, off_gmisc;
   int bytes;
@@ -103,6 +105,11 @@ static GroupLayout make_layout(int M, bool ped, bool rss, bool veh, bool grid = 
   L.off_flags = o;  o += G + 16;                                  // old present|etype<<1
   L.off_orient = o; o += G;                                       // ring orientation of each box
   o = (o + 15) / 16 * 16;
+  L.sorted = (veh && M >= 128) ? 1 : 0;
+  L.off_sid = o;    o += L.sorted ? (M + 64) * (int)sizeof(uint16_t) : 0;   // slot id at each sorted position
+  L.off_posof = o;  o += L.sorted ? G * (int)sizeof(uint16_t) : 0;          // sorted position of each slot
+  o = (o + 15) / 16 * 16;
+  L.off_sflag = o;  o += L.sorted ? 4 * (int)sizeof(int) : 0;
   L.grid = (grid && ped && G > SG_THREADS) ? 1 : 0;
   L.off_gstart = o;  o += L.grid ? (SG_GRID_CELLS / 2 + 4) * (int)sizeof(uint32_t) : 0;  // packed 16-bit cell starts (+ end)
   L.off_gsorted = o; o += L.grid ? G * (int)sizeof(uint16_t) : 0;                         // slot ids sorted by cell
@@ -137,6 +144,10 @@ struct Grp {
   int* acc;
   uint8_t* flags;
   int8_t* orient;
+  uint16_t* sid;
+  uint16_t* posof;
+  int* sflag;
+  int sorted;
   uint32_t* gstart;
   uint16_t* gsorted;
   uint16_t* glarge;
@@ -185,6 +196,10 @@ SG_DEV void setup_group(Grp& g, const SgScene& sc, const GroupLayout& L, unsigne
   g.acc = (int*)(base + L.off_acc);
   g.flags = (uint8_t*)(base + L.off_flags);
   g.orient = (int8_t*)(base + L.off_orient);
+  g.sid = (uint16_t*)(base + L.off_sid);
+  g.posof = (uint16_t*)(base + L.off_posof);
+  g.sflag = (int*)(base + L.off_sflag);
+  g.sorted = L.sorted;
   g.gstart = (uint32_t*)(base + L.off_gstart);
   g.gsorted = (uint16_t*)(base + L.off_gsorted);
   g.glarge = (uint16_t*)(base + L.off_glarge);
@@ -746,8 +761,80 @@ SG_DEV void publish_box(const Grp& c, bool present, double x, double y, double c
     c.orient[c.s] = (int8_t)(orient_hint ? orient_hint : quad_orientation(quad_from_array(my)));
     bb = make_aabb_box(x, y, cs, sn, bw, bl, bcx, bcy, ox, oy);
   }
+  if (c.sorted) {  // the slot keeps its position of the last tick; sort_positions repairs the order
+    const int pos = c.posof[c.s];
+    c.aabb[pos] = bb;
+    c.sid[pos] = (uint16_t)c.s;
+    return;
+  }
   c.aabb[c.s] = bb;
   if (c.s < c.H + 1) c.aabb[c.M + c.s] = bb;
+}
+
+// ---------------------------------------------------------------------------------
+// Sorted sweep (vehicle scenes, M >= 128).  The conservative AABBs are kept sorted by their lower
+// x bound across ticks: entities move a few metres per tick, so an odd-even transposition pass or
+// two restores the order (three rotating flags tell every thread whether a round swapped
+// anything).  Boxes that overlap box r in x then sit directly behind it, so the thread of position
+// r tests a fixed, branch-free window of 32 successors (and walks on only while a successor still
+// starts inside its x-range): O(M * 32) tests instead of O(M^2 / 2), each unordered pair once.
+// ---------------------------------------------------------------------------------
+SG_DEV void sorted_setup(const Grp& c) {  // all G threads, once per launch (followed by a group_sync)
+  if (!c.sorted) return;
+  if (c.s < c.M) { c.posof[c.s] = (uint16_t)c.s; c.sid[c.s] = (uint16_t)c.s; }
+  for (int q = c.M + c.s; q < c.M + c.H + 1; q += c.G)
+    c.aabb[q] = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+  if (c.s < 4) c.sflag[c.s] = 0;
+}
+SG_DEV void sort_positions(const Grp& c, int& round) {  // all G threads
+  const int r = c.s;
+  for (;;) {
+    int* flag = c.sflag + round % 3;
+    if (r == 0) c.sflag[(round + 1) % 3] = 0;  // last read two rounds ago, next written in the next round
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+      if ((r & 1) == ph && r + 1 < c.M) {
+        const float4 a = c.aabb[r], b = c.aabb[r + 1];
+        if (a.x > b.x) {
+          c.aabb[r] = b; c.aabb[r + 1] = a;
+          const uint16_t t = c.sid[r];
+          c.sid[r] = c.sid[r + 1]; c.sid[r + 1] = t;
+          *flag = 1;
+        }
+      }
+      group_sync(c);
+    }
+    const int swapped = *flag;
+    ++round;
+    if (!swapped) break;
+  }
+  if (r < c.M) c.posof[c.sid[r]] = (uint16_t)r;
+}
+SG_DEV void broad_phase_sorted(const Grp& c, int parity) {  // thread = sorted position
+  const int r = c.s;
+  const float4 mb = c.aabb[r];
+  if (!(mb.x <= mb.z)) return;  // empty box (entity absent)
+  const float4* nb = c.aabb + r + 1;
+  int* acc = c.acc + parity * ACC_N;
+  auto push = [&](int d) {
+    const int q = atomicAdd(&acc[ACC_QCOUNT], 1);
+    if (q < c.QCAP) c.queue[q] = ((uint32_t)c.sid[r] << 16) | (uint32_t)c.sid[r + d];
+  };
+  uint32_t hits = 0;
+#pragma unroll
+  for (int dd = 0; dd < 32; ++dd) {  // positions beyond M hold empty boxes
+    const float4 ob = nb[dd];
+    SG_AABB_TEST(hits, mb, ob, 1u << dd);
+  }
+  while (hits) {
+    const int dd = __ffs(hits) - 1;
+    hits &= hits - 1;
+    push(dd + 1);
+  }
+  for (int d = 33; r + d < c.M && c.aabb[r + d].x <= mb.z; ++d) {  // a run longer than the window
+    const float4 ob = c.aabb[r + d];
+    if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) push(d);
+  }
 }
 
 // the ego's box dimensions and the reciprocals safe_ratios divides by (once per launch)
@@ -1162,6 +1249,18 @@ __device__ __noinline__ void broad_phase_direct(PairSink k, const float4* aabb, 
   }
 }
 
+__device__ __noinline__ void broad_phase_direct_sorted(PairSink k, const float4* aabb, const uint16_t* sid,
+                                                       unsigned corners_sh, const int8_t* orient, int G, int M,
+                                                       int r) {
+  const float4 mb = aabb[r];
+  if (!(mb.x <= mb.z)) return;
+  for (int d = 1; r + d < M && aabb[r + d].x <= mb.z; ++d) {
+    const float4 ob = aabb[r + d];
+    if (!(mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w)) continue;
+    record_pair(k, corners_sh, orient, G, sid[r], sid[r + d]);
+  }
+}
+
 // phases B2 + C, shared by both kernel flavours.  Returns state.is_done.
 template <bool FAST>
 SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int n, int s, int W,
@@ -1185,6 +1284,8 @@ SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int 
         const uint32_t pr = c.queue[q];
         record_pair(sink, c.corners_sh, c.orient, G, (int)(pr >> 16), (int)(pr & 0xffff));
       }
+    } else if (c.sorted) {
+      if (s < c.M) broad_phase_direct_sorted(sink, c.aabb, c.sid, c.corners_sh, c.orient, G, c.M, s);
     } else if (present) {
       broad_phase_direct(sink, c.aabb, c.corners_sh, c.orient, G, c.M, c.H, s);
     }
@@ -1359,6 +1460,8 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   bool done = st.done[n] != 0;
   load_cold(st, c, n, s, W, ego_slot);
   if (RSS && s == ego_slot) publish_ego_box(c);
+  sorted_setup(c);
+  int sort_round = 0;
   group_sync(c);
 
   int limit = n_ticks < 0 ? p.max_ticks : n_ticks;
@@ -1427,6 +1530,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       c.cold_d[COLD_PT0 + (parity ^ 1)] = t;
     }
     group_sync(c);
+    if (c.sorted && need_coll) sort_positions(c, sort_round);
     // ---- phase B1: callbacks (RSS) + broad phase
     if (live && present) {
       if (RSS && feat_rss) {  // RSSDistances.__call__, callback.py:57-122
@@ -1441,8 +1545,9 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
           if (found) atomicOr(&c.acc[parity * ACC_N + ACC_RSS], found == 2 ? 1 : 2);
         }
       }
-      if (need_coll) broad_phase(c, parity);
+      if (need_coll && !c.sorted) broad_phase(c, parity);
     }
+    if (c.sorted && need_coll && s < M) broad_phase_sorted(c, parity);
     group_sync(c);
     done = finish_tick<true>(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick,
                        c.cold_d[COLD_T0 + (parity ^ 1)], c.cold_d[COLD_T0 + (parity ^ 1)] - c.cold_d[COLD_PT0 + (parity ^ 1)],
@@ -1792,6 +1897,7 @@ sg_reset_kernel(SgScene sc, SgParams p, SgState st, GroupLayout L) {
   if (gl >= gpb || n >= sc.n_scenarios) return;
   Grp c;
   setup_group(c, sc, L, smem, gl, s, n);
+  c.sorted = 0;  // no broad phase at reset
   const bool live = s < M;
   const int64_t i = c.i, nm = c.nm;
   const int kind = live ? sc.kind[i] : SG_KIND_EMPTY;
