@@ -26,6 +26,12 @@
 
 #define SG_THREADS 256
 #define SG_NBCAP 12  // per-pedestrian neighbour candidate list kept in shared memory
+#ifndef SG_SORT_MIN_M
+#define SG_SORT_MIN_M 128  // vehicle scenes with at least this many slots use the sorted sweep
+#endif
+#ifndef SG_SWEEP_WIN
+#define SG_SWEEP_WIN 8  // successors tested branch-free by the sorted sweep (a longer run is walked)
+#endif
 #ifndef SG_WARP_PAIRS
 #define SG_WARP_PAIRS 6  // queued pairs per warp up to which the narrow phase runs warp-cooperatively
 #endif
@@ -105,7 +111,7 @@ static GroupLayout make_layout(int M, bool ped, bool rss, bool veh, bool grid = 
   L.off_flags = o;  o += G + 16;                                  // old present|etype<<1
   L.off_orient = o; o += G;                                       // ring orientation of each box
   o = (o + 15) / 16 * 16;
-  L.sorted = (veh && M >= 128) ? 1 : 0;
+  L.sorted = (veh && M >= SG_SORT_MIN_M) ? 1 : 0;
   L.off_sid = o;    o += L.sorted ? (M + 64) * (int)sizeof(uint16_t) : 0;   // slot id at each sorted position
   L.off_posof = o;  o += L.sorted ? G * (int)sizeof(uint16_t) : 0;          // sorted position of each slot
   o = (o + 15) / 16 * 16;
@@ -776,8 +782,8 @@ SG_DEV void publish_box(const Grp& c, bool present, double x, double y, double c
 // x bound across ticks: entities move a few metres per tick, so an odd-even transposition pass or
 // two restores the order (three rotating flags tell every thread whether a round swapped
 // anything).  Boxes that overlap box r in x then sit directly behind it, so the thread of position
-// r tests a fixed, branch-free window of 32 successors (and walks on only while a successor still
-// starts inside its x-range): O(M * 32) tests instead of O(M^2 / 2), each unordered pair once.
+// r tests a fixed, branch-free window of SG_SWEEP_WIN successors (and walks on only while a successor still
+// starts inside its x-range): O(M * window) tests instead of O(M^2 / 2), each unordered pair once.
 // ---------------------------------------------------------------------------------
 SG_DEV void sorted_setup(const Grp& c) {  // all G threads, once per launch (followed by a group_sync)
   if (!c.sorted) return;
@@ -822,7 +828,7 @@ SG_DEV void broad_phase_sorted(const Grp& c, int parity) {  // thread = sorted p
   };
   uint32_t hits = 0;
 #pragma unroll
-  for (int dd = 0; dd < 32; ++dd) {  // positions beyond M hold empty boxes
+  for (int dd = 0; dd < SG_SWEEP_WIN; ++dd) {  // positions beyond M hold empty boxes
     const float4 ob = nb[dd];
     SG_AABB_TEST(hits, mb, ob, 1u << dd);
   }
@@ -831,7 +837,7 @@ SG_DEV void broad_phase_sorted(const Grp& c, int parity) {  // thread = sorted p
     hits &= hits - 1;
     push(dd + 1);
   }
-  for (int d = 33; r + d < c.M && c.aabb[r + d].x <= mb.z; ++d) {  // a run longer than the window
+  for (int d = SG_SWEEP_WIN + 1; r + d < c.M && c.aabb[r + d].x <= mb.z; ++d) {  // a run longer than the window
     const float4 ob = c.aabb[r + d];
     if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) push(d);
   }
