@@ -27,7 +27,7 @@
 #define SG_THREADS 256
 #define SG_NBCAP 12  // per-pedestrian neighbour candidate list kept in shared memory
 #ifndef SG_SORT_MIN_M
-#define SG_SORT_MIN_M 128  // vehicle scenes with at least this many slots use the sorted sweep
+#define SG_SORT_MIN_M 129  // vehicle scenes with at least this many slots use the sorted sweep
 #endif
 #ifndef SG_SWEEP_WIN
 #define SG_SWEEP_WIN 8  // successors tested branch-free by the sorted sweep (a longer run is walked)
@@ -111,7 +111,7 @@ static GroupLayout make_layout(int M, bool ped, bool rss, bool veh, bool grid = 
   L.off_flags = o;  o += G + 16;                                  // old present|etype<<1
   L.off_orient = o; o += G;                                       // ring orientation of each box
   o = (o + 15) / 16 * 16;
-  L.sorted = (veh && M >= SG_SORT_MIN_M) ? 1 : 0;
+  L.sorted = (veh && M >= SG_SORT_MIN_M && G > SG_VEH_THREADS) ? 1 : 0;
   L.off_sid = o;    o += L.sorted ? (M + 64) * (int)sizeof(uint16_t) : 0;   // slot id at each sorted position
   L.off_posof = o;  o += L.sorted ? G * (int)sizeof(uint16_t) : 0;          // sorted position of each slot
   o = (o + 15) / 16 * 16;
@@ -747,7 +747,7 @@ SG_DEV int box_orientation_hint(double bw, double bl) {
 }
 
 // Entity.get_bounding_box_points (reference entity/base.py:100-138) from cos/sin of the heading
-template <bool RSS>
+template <bool RSS, bool SORTED = false>
 SG_DEV void publish_box(const Grp& c, bool present, double x, double y, double cs, double sn,
                         int orient_hint, double ox, double oy) {
   float4 bb = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
@@ -767,7 +767,7 @@ SG_DEV void publish_box(const Grp& c, bool present, double x, double y, double c
     c.orient[c.s] = (int8_t)(orient_hint ? orient_hint : quad_orientation(quad_from_array(my)));
     bb = make_aabb_box(x, y, cs, sn, bw, bl, bcx, bcy, ox, oy);
   }
-  if (c.sorted) {  // the slot keeps its position of the last tick; sort_positions repairs the order
+  if (SORTED) {  // the slot keeps its position of the last tick; sort_positions repairs the order
     const int pos = c.posof[c.s];
     c.aabb[pos] = bb;
     c.sid[pos] = (uint16_t)c.s;
@@ -1404,7 +1404,7 @@ SG_DEV RssConst make_rss_const(const SgParams& p) {
 // z, p, r never change under VehicleController._step (controller.py:122-131), so their
 // velocities are 0 after the first tick and they stay in global memory.
 // ---------------------------------------------------------------------------------
-template <bool RSS, int MAXT, int MINB>
+template <bool RSS, int MAXT, int MINB, bool SORTED>
 __global__ void __launch_bounds__(MAXT, MINB)
 sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, GroupLayout L) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -1466,7 +1466,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   bool done = st.done[n] != 0;
   load_cold(st, c, n, s, W, ego_slot);
   if (RSS && s == ego_slot) publish_ego_box(c);
-  sorted_setup(c);
+  if (SORTED) sorted_setup(c);
   int sort_round = 0;
   group_sync(c);
 
@@ -1524,7 +1524,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     }
     if (s < M) {
       if (need_coll || feat_rss)
-        publish_box<RSS>(c, present, x, y, cs, sn, orient_hint, U[COLD_OX], U[COLD_OY]);
+        publish_box<RSS, SORTED>(c, present, x, y, cs, sn, orient_hint, U[COLD_OX], U[COLD_OY]);
       if (matrix) {
         uint32_t* row = st.coll_mask + ((int64_t)n * M + s) * W;
         for (int w = 0; w < W; ++w) row[w] = 0;
@@ -1536,7 +1536,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       c.cold_d[COLD_PT0 + (parity ^ 1)] = t;
     }
     group_sync(c);
-    if (c.sorted && need_coll) sort_positions(c, sort_round);
+    if (SORTED && need_coll) sort_positions(c, sort_round);
     // ---- phase B1: callbacks (RSS) + broad phase
     if (live && present) {
       if (RSS && feat_rss) {  // RSSDistances.__call__, callback.py:57-122
@@ -1551,9 +1551,9 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
           if (found) atomicOr(&c.acc[parity * ACC_N + ACC_RSS], found == 2 ? 1 : 2);
         }
       }
-      if (need_coll && !c.sorted) broad_phase(c, parity);
+      if (need_coll && !SORTED) broad_phase(c, parity);
     }
-    if (c.sorted && need_coll && s < M) broad_phase_sorted(c, parity);
+    if (SORTED && need_coll && s < M) broad_phase_sorted(c, parity);
     group_sync(c);
     done = finish_tick<true>(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick,
                        c.cold_d[COLD_T0 + (parity ^ 1)], c.cold_d[COLD_T0 + (parity ^ 1)] - c.cold_d[COLD_PT0 + (parity ^ 1)],
@@ -2108,9 +2108,15 @@ static cudaError_t launch_vehicle(int n_scen, cudaStream_t s, const SgScene& sc,
                                   const GroupLayout& L) {
   void (*kern)(SgScene, SgParams, SgState, SgInputs, int, GroupLayout);
   int threads;
-  if (L.G <= SG_VEH_THREADS) { kern = sg_vehicle_kernel<RSS, SG_VEH_THREADS, SG_VEH_MINB>; threads = SG_VEH_THREADS; }
-  else if (L.G <= SG_THREADS) { kern = sg_vehicle_kernel<RSS, SG_THREADS, 2>; threads = SG_THREADS; }
-  else { kern = sg_vehicle_kernel<RSS, 1024, 1>; threads = L.G; }
+  // (the sorted sweep is a compile-time variant: scenes of up to 128 slots carry none of its code)
+  if (L.G <= SG_VEH_THREADS) { kern = sg_vehicle_kernel<RSS, SG_VEH_THREADS, SG_VEH_MINB, false>; threads = SG_VEH_THREADS; }
+  else if (L.G <= SG_THREADS) {
+    kern = L.sorted ? sg_vehicle_kernel<RSS, SG_THREADS, 2, true> : sg_vehicle_kernel<RSS, SG_THREADS, 2, false>;
+    threads = SG_THREADS;
+  } else {
+    kern = L.sorted ? sg_vehicle_kernel<RSS, 1024, 1, true> : sg_vehicle_kernel<RSS, 1024, 1, false>;
+    threads = L.G;
+  }
   const int gpb = threads / L.G;
   const int blocks = (n_scen + gpb - 1) / gpb;
   const size_t smem = (size_t)gpb * L.bytes;
