@@ -1404,7 +1404,7 @@ SG_DEV RssConst make_rss_const(const SgParams& p) {
 // z, p, r never change under VehicleController._step (controller.py:122-131), so their
 // velocities are 0 after the first tick and they stay in global memory.
 // ---------------------------------------------------------------------------------
-template <bool RSS, int MAXT, int MINB, bool SORTED>
+template <bool RSS, int MAXT, int MINB, bool SORTED, bool LEAN = false>
 __global__ void __launch_bounds__(MAXT, MINB)
 sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, GroupLayout L) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -1514,7 +1514,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     }
     cp_async_commit();
     tick += 1;
-    if (st.trace_cap > 0 && tick < st.trace_cap && s < M) {
+    if (!LEAN && st.trace_cap > 0 && tick < st.trace_cap && s < M) {
       const int64_t i = c.i, nm = c.nm;
       st.trace_present[(int64_t)tick * nm + i] = present;
       double* tp = st.trace_pose + (int64_t)tick * 6 * nm + i;
@@ -1525,7 +1525,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     if (s < M) {
       if (need_coll || feat_rss)
         publish_box<RSS, SORTED>(c, present, x, y, cs, sn, orient_hint, U[COLD_OX], U[COLD_OY]);
-      if (matrix) {
+      if (!LEAN && matrix) {
         uint32_t* row = st.coll_mask + ((int64_t)n * M + s) * W;
         for (int w = 0; w < W; ++w) row[w] = 0;
       }
@@ -2109,8 +2109,12 @@ static cudaError_t launch_vehicle(int n_scen, cudaStream_t s, const SgScene& sc,
   void (*kern)(SgScene, SgParams, SgState, SgInputs, int, GroupLayout);
   int threads;
   // (the sorted sweep is a compile-time variant: scenes of up to 128 slots carry none of its code)
-  if (L.G <= SG_VEH_THREADS) { kern = sg_vehicle_kernel<RSS, SG_VEH_THREADS, SG_VEH_MINB, false>; threads = SG_VEH_THREADS; }
-  else if (L.G <= SG_THREADS) {
+  const bool lean = st.trace_cap <= 0 && !(p.features & SG_FEAT_COLL_MATRIX);  // no trace, no pair matrix
+  if (L.G <= SG_VEH_THREADS) {
+    kern = lean ? sg_vehicle_kernel<RSS, SG_VEH_THREADS, SG_VEH_MINB, false, true>
+                : sg_vehicle_kernel<RSS, SG_VEH_THREADS, SG_VEH_MINB, false, false>;
+    threads = SG_VEH_THREADS;
+  } else if (L.G <= SG_THREADS) {
     kern = L.sorted ? sg_vehicle_kernel<RSS, SG_THREADS, 2, true> : sg_vehicle_kernel<RSS, SG_THREADS, 2, false>;
     threads = SG_THREADS;
   } else {
