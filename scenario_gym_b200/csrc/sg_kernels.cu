@@ -1267,6 +1267,21 @@ __device__ __noinline__ void broad_phase_direct_sorted(PairSink k, const float4*
   }
 }
 
+// CollisionMetric rising edges of one ego-row word (rare: out of line)
+__device__ __noinline__ void emit_events(SgEvent* events, int32_t* event_count, int event_cap, uint32_t fresh,
+                                         int n, int tick, int slot0, double t) {
+  while (fresh) {
+    const int b = __ffs(fresh) - 1;
+    fresh &= fresh - 1;
+    const int slot = atomicAdd(event_count, 1);
+    if (slot < event_cap) {
+      SgEvent ev;
+      ev.scenario = n; ev.tick = tick; ev.slot = slot0 + b; ev._pad = 0; ev.t = t;
+      events[slot] = ev;
+    }
+  }
+}
+
 // phases B2 + C, shared by both kernel flavours.  Returns state.is_done.
 template <bool FAST>
 SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int n, int s, int W,
@@ -1324,17 +1339,8 @@ SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int 
   if (bs >= 0 && bs < W) {  // CollisionMetric._step, metrics/collision.py:70-75
     const uint32_t now = c.ego_now[bs];
     if (p.features & SG_FEAT_COLLISIONS) {
-      uint32_t fresh = now & ~c.ego_last[bs];
-      while (fresh) {
-        const int b = __ffs(fresh) - 1;
-        fresh &= fresh - 1;
-        const int slot = atomicAdd(st.event_count, 1);
-        if (slot < st.event_cap) {
-          SgEvent ev;
-          ev.scenario = n; ev.tick = tick; ev.slot = bs * 32 + b; ev._pad = 0; ev.t = t;
-          st.events[slot] = ev;
-        }
-      }
+      const uint32_t fresh = now & ~c.ego_last[bs];
+      if (fresh) emit_events(st.events, st.event_count, st.event_cap, fresh, n, tick, bs * 32, t);
       c.ego_last[bs] = now;
     }
     c.ego_now[bs] = 0;
@@ -1418,10 +1424,11 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   setup_group(c, sc, L, smem, gl, s, n);
   const bool live = s < M && sc.kind[c.i] == SG_KIND_VEHICLE;
   const int ego_slot = sc.ego_slot[n], first_slot = sc.first_slot[n];
-  const bool need_coll = (p.features & SG_FEAT_COLLISIONS) ||
+  // (LEAN is only launched with collisions on, no trace and no pair matrix; RSS only with the feature on)
+  const bool need_coll = LEAN || (p.features & SG_FEAT_COLLISIONS) ||
                          (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
-  const bool feat_rss = RSS && (p.features & SG_FEAT_RSS);
-  const bool matrix = (p.features & SG_FEAT_COLL_MATRIX) != 0;
+  const bool feat_rss = RSS;
+  const bool matrix = !LEAN && (p.features & SG_FEAT_COLL_MATRIX) != 0;
 
   // hot per-entity state in registers; everything that is only read back at the end (safe
   // distances, ratios, heading rate) or is uniform per scenario (tick times, length, origin)
@@ -2108,19 +2115,16 @@ static cudaError_t launch_vehicle(int n_scen, cudaStream_t s, const SgScene& sc,
                                   const GroupLayout& L) {
   void (*kern)(SgScene, SgParams, SgState, SgInputs, int, GroupLayout);
   int threads;
-  // (the sorted sweep is a compile-time variant: scenes of up to 128 slots carry none of its code)
-  const bool lean = st.trace_cap <= 0 && !(p.features & SG_FEAT_COLL_MATRIX);  // no trace, no pair matrix
-  if (L.G <= SG_VEH_THREADS) {
-    kern = lean ? sg_vehicle_kernel<RSS, SG_VEH_THREADS, SG_VEH_MINB, false, true>
-                : sg_vehicle_kernel<RSS, SG_VEH_THREADS, SG_VEH_MINB, false, false>;
-    threads = SG_VEH_THREADS;
-  } else if (L.G <= SG_THREADS) {
-    kern = L.sorted ? sg_vehicle_kernel<RSS, SG_THREADS, 2, true> : sg_vehicle_kernel<RSS, SG_THREADS, 2, false>;
-    threads = SG_THREADS;
-  } else {
-    kern = L.sorted ? sg_vehicle_kernel<RSS, 1024, 1, true> : sg_vehicle_kernel<RSS, 1024, 1, false>;
-    threads = L.G;
-  }
+  const bool need_coll = (p.features & SG_FEAT_COLLISIONS) ||
+                         (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
+  // lean: collisions on, no trace, no pair matrix - those code paths are compiled out
+  const bool lean = need_coll && st.trace_cap <= 0 && !(p.features & SG_FEAT_COLL_MATRIX);
+#define SG_VEH_PICK(T, B, S) (lean ? sg_vehicle_kernel<RSS, T, B, S, true> : sg_vehicle_kernel<RSS, T, B, S, false>)
+  // (the sorted sweep is a compile-time variant too: scenes of up to 128 slots carry none of its code)
+  if (L.G <= SG_VEH_THREADS) { kern = SG_VEH_PICK(SG_VEH_THREADS, SG_VEH_MINB, false); threads = SG_VEH_THREADS; }
+  else if (L.G <= SG_THREADS) { kern = L.sorted ? SG_VEH_PICK(SG_THREADS, 2, true) : SG_VEH_PICK(SG_THREADS, 2, false); threads = SG_THREADS; }
+  else { kern = L.sorted ? SG_VEH_PICK(1024, 1, true) : SG_VEH_PICK(1024, 1, false); threads = L.G; }
+#undef SG_VEH_PICK
   const int gpb = threads / L.G;
   const int blocks = (n_scen + gpb - 1) / gpb;
   const size_t smem = (size_t)gpb * L.bytes;
