@@ -2178,11 +2178,12 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
       !inp.actions && !inp.host_present && p->timestep > 0.0 && (n_ticks < 0 || n_ticks >= 8) &&
       !(p->features & SG_FEAT_SEQUENTIAL)) {
     const size_t rsm = replay_smem_bytes(sc->n_slots);
+    auto rk = (p->features & SG_FEAT_COLL_MATRIX) ? sg_replay_kernel<true> : sg_replay_kernel<false>;
     if (rsm > 48 * 1024) {
-      err = cudaFuncSetAttribute(sg_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+      err = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
       if (err != cudaSuccess) return set_err("cudaFuncSetAttribute", err);
     }
-    sg_replay_kernel<<<sc->n_scenarios, SG_RP_BLOCK, rsm, s>>>(*sc, *p, *st, n_ticks);
+    rk<<<sc->n_scenarios, SG_RP_BLOCK, rsm, s>>>(*sc, *p, *st, n_ticks);
     err = cudaGetLastError();
     if (err != cudaSuccess) return set_err("sg_replay_kernel launch", err);
     return 0;

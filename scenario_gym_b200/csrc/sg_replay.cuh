@@ -220,6 +220,7 @@ SG_DEV void rp_ego_metrics(RpCarry* car, const double* spv, const double* cwv, i
   car->avg = avg; car->mx = mx; car->last_sp = last; car->avg_t = t_last;
 }
 
+template <bool MATRIX>  // MATRIX: also write the pair matrix of the final tick (SG_FEAT_COLL_MATRIX)
 __global__ void __launch_bounds__(SG_RP_BLOCK)
 sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgParams p,
                  const __grid_constant__ SgState st, int n_ticks) {
@@ -494,7 +495,7 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
         st.present[i] = pres;
         st.cur_own[i] = 1;
       }
-      if (valid && j == nv && (p.features & SG_FEAT_COLL_MATRIX)) {  // pair matrix of the final tick
+      if (MATRIX && valid && j == nv) {  // pair matrix of the final tick
         uint32_t* rows = st.coll_mask + i0;  // W = 1
         for (int s = 0; s < M; ++s) rows[s] = 0;
         uint32_t pm = 0;
