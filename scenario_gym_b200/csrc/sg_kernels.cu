@@ -768,6 +768,7 @@ SG_DEV void publish_box(const Grp& c, bool present, double x, double y, double c
     bb = make_aabb_box(x, y, cs, sn, bw, bl, bcx, bcy, ox, oy);
   }
   if (SORTED) {  // the slot keeps its position of the last tick; sort_positions repairs the order
+    if (!(bb.x <= bb.z)) bb = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);  // NaN pose: sorts last
     const int pos = c.posof[c.s];
     c.aabb[pos] = bb;
     c.sid[pos] = (uint16_t)c.s;

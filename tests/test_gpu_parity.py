@@ -365,6 +365,29 @@ def test_future_collisions_vs_oracle():
     assert seen > 0
 
 
+@pytest.mark.parametrize("M,half_extent", [(160, 45.0), (256, 25.0), (256, 9.0)])
+def test_sorted_sweep_random_order_vs_oracle(M, half_extent):
+    """
+    Vehicle scenes with more than 128 slots keep their boxes sorted by x and sweep a fixed window.
+    Random placement: the slots start in random x order (the first tick repairs the whole order),
+    dense enough that runs of x-overlapping boxes exceed the window and, at 25 m, that the
+    candidate queue overflows.
+    """
+    cfg = synthetic.vehicles_config(seed=31, N=3, M=M, T=20, half_extent=half_extent)
+    scene = pack_synthetic(cfg)
+    p = _params(timestep=cfg.dt)
+    gpu, cpu = _run_both(scene, p, actions=cfg.actions)
+    assert cpu.get("n_pair_ticks").sum() > 1000
+    compare_engines(gpu, cpu, scene, f"sorted sweep M={M}")
+    p2 = _params(timestep=cfg.dt)
+    p2.features &= ~abi.FEAT_COLL_MATRIX  # the lean kernel variant
+    gpu2, _ = make_gpu(scene, p2), None
+    gpu2.reset()
+    gpu2.rollout(-1, actions=cfg.actions)
+    for k in ("collided", "first_coll_tick", "first_coll_pair", "n_pair_ticks", "ego_hits", "tick"):
+        assert np.array_equal(gpu2.get(k), cpu.get(k)), f"lean variant: {k} differs"
+
+
 def test_c2_replicas_identical():
     """C2: replicas of the test scenarios are bit-identical copies => identical results per file."""
     specs = [s for _, s, _, _ in XOSC]
