@@ -456,8 +456,7 @@ class ScenarioGym:
         (tick, horizon, sensor slots); the result is cached until the state advances.
         """
         slot = self._slot_of[n][entity]
-        ticks = tuple(int(v) for v in self._fetch("tick"))
-        key = (ticks, float(horizon), int(n_samples))
+        key = (id(self._engine), self._fetch("t").tobytes(), float(horizon), int(n_samples))
         cache = getattr(self, "_future_cache", None)
         if cache is None or cache[0] != key or cache[1][n] != slot:
             slots = np.array([self._slot_of[k].get(self.states[k].scenario.ego, 0)
