@@ -165,3 +165,26 @@ def test_batched_ingest_matches_single_imports():
                 assert a.bounding_box == b.bounding_box
     with pytest.raises(FileNotFoundError):
         import_scenarios([f, f + ".missing"])
+
+
+def test_combine_observations_fields_and_prefixes():
+    """Reference observation.py:31-83: first definition of a field wins; prefixes keep repeats."""
+    import dataclasses
+
+    from scenario_gym_b200.plugins import (CollisionObservation, FutureCollisionObservation,
+                                           SingleEntityObservation, combine_observations)
+
+    C = combine_observations(SingleEntityObservation, FutureCollisionObservation, CollisionObservation)
+    names = [f.name for f in dataclasses.fields(C)]
+    assert names[:8] == [f.name for f in dataclasses.fields(SingleEntityObservation)]
+    assert names[8:] == ["future_collision", "collisions"]
+    a = SingleEntityObservation("e", 1.0, 2.0, "pose", "vel", 3.0, "rec", None)
+    b = FutureCollisionObservation("e", 1.0, 2.0, "pose", "vel", 3.0, "rec", None, True)
+    c = CollisionObservation("e", 1.0, 2.0, "pose", "vel", 3.0, "rec", None, {"x": []})
+    obs = C.from_obs(a, b, c)
+    assert obs.entity == "e" and obs.future_collision is True and obs.collisions == {"x": []}
+    P = combine_observations(SingleEntityObservation, FutureCollisionObservation, prefixes=("a", "b"))
+    pn = [f.name for f in dataclasses.fields(P)]
+    assert "b_pose" in pn and "future_collision" in pn and pn.count("pose") == 1
+    with pytest.raises(ValueError):
+        combine_observations(SingleEntityObservation, prefixes=("a", "b"))
