@@ -957,6 +957,28 @@ struct RssConst {  // uniform per launch
 // answered by exact comparisons where those decide and by exact orientation signs otherwise,
 // so every record equals the reference's; scalar quotients with a launch-uniform or shared
 // denominator use div_r.
+// safe_ratios (callback.py:124-166) of one hazard from the ego published in shared memory; pure
+// outputs (no decision reads them), so a fused rollout only needs them after its last tick
+SG_DEV void rss_ratios(const Grp& c, double x, double y, double* out, int ost) {
+  const double* E = c.egop;
+  const double eh0 = E[EGO_C], eh1 = E[EGO_S], ei0 = E[EGO_INV0], ei1 = E[EGO_INV1];
+  const double dirc = c.hcs[c.s], dirs = c.hcs[c.G + c.s];
+  const double bw = c.boxp[c.s], bl = c.boxp[c.G + c.s];
+  const double d0 = x - E[EGO_X], d1 = y - E[EGO_Y];
+  const double pos0 = dot2(d0, d1, ei0, ei1), pos1 = dot2(d0, d1, eh0, eh1);
+  const double hd0 = dot2(dirc, dirs, ei0, ei1), hd1 = dot2(dirc, dirs, eh0, eh1);
+  const double eW = E[EGO_W], eL = E[EGO_L];
+  const double hn = fnorm2(hd1, hd0), rhn = fast_rcp(hn);  // inverse_direction(haz heading)
+  const double inv0 = div_r(hd1, hn, rhn), inv1 = div_r(-hd0, hn, rhn);
+  const double wl_inv = fabs(dot2(bw, bl, inv0, inv1));
+  const double wl_dir = fabs(dot2(bw, bl, hd0, hd1));
+  const double actual_lat = py_max(1e-6, fabs(pos0) - 0.5 * eW - 0.5 * wl_inv);
+  const double actual_long = py_max(1e-6, fabs(pos1) - 0.5 * eL - 0.5 * wl_dir);
+  out[2 * ost] = fabs(div_r(actual_lat, 0.5 * eW, E[EGO_RHW]));
+  out[3 * ost] = fabs(div_r(actual_long, 0.5 * eL, E[EGO_RHL]));
+}
+
+template <bool RATIOS = true>
 SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, double vx, double vy,
                       uint8_t& state, double* out, int ost) {  // out: lat, long, ratio lat, ratio long
   const double* E = c.egop;
@@ -1015,7 +1037,7 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
   out[0] = slat;
   out[ost] = slong;
   // safe_ratios (callback.py:124-166)
-  {
+  if (RATIOS) {
     const double hn = fnorm2(hd1, hd0), rhn = fast_rcp(hn);  // inverse_direction(haz heading)
     const double inv0 = div_r(hd1, hn, rhn), inv1 = div_r(-hd0, hn, rhn);
     const double wl_inv = fabs(dot2(bw, bl, inv0, inv1));
@@ -1438,6 +1460,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
   int orient_hint = 0;
   bool present = false;
   uint8_t collided = 0, rss_state = 0, rss_last = SG_RSS_NONE;
+  bool rss_evald = false;  // RSSDistances ran for this hazard in the last executed tick
   double* tc = c.tcold + s;  // [0..3] safe dist / ratios, [4] heading rate, [5] 1 / wheelbase
   {
     const int64_t i = c.i, nm = c.nm;
@@ -1549,12 +1572,15 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     if (live && present) {
       if (RSS && feat_rss) {  // RSSDistances.__call__, callback.py:57-122
         rss_last = SG_RSS_NONE;
+        rss_evald = false;
         if (next_t != 0.0 && s != ego_slot && c.egop[EGO_PRESENT] != 0.0) {
           RssConst KR;
           KR.CLR = p.rss_min_safe_clearance; KR.RT = p.rss_response_time;
           KR.MAXA = p.rss_max_long_accel; KR.MINA = p.rss_min_long_accel;
           KR.r2mina = c.cold_d[COLD_R2MINA];
-          rss_last = (uint8_t)rss_hazard(KR, c, x, y, vx, vy, rss_state, tc, G);
+          // (lean rollouts: the safe ratios are pure outputs - computed once after the last tick)
+          rss_last = (uint8_t)rss_hazard<!LEAN>(KR, c, x, y, vx, vy, rss_state, tc, G);
+          rss_evald = true;
           const int found = (rss_state >> 2) & 3;  // RSS metric latch, rss.py:71-103
           if (found) atomicOr(&c.acc[parity * ACC_N + ACC_RSS], found == 2 ? 1 : 2);
         }
@@ -1569,6 +1595,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     parity ^= 1;
   }
 
+  if (RSS && LEAN && live && present && rss_evald) rss_ratios(c, x, y, tc, G);
   if (live) {
     const int64_t i = c.i, nm = c.nm;
     st.pose[i] = x; st.pose[nm + i] = y; st.pose[3 * nm + i] = h;

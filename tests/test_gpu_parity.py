@@ -235,6 +235,23 @@ def test_highway_rss_vs_oracle():
     compare_engines(gpu, cpu, scene, "highway", check_rss=True)
 
 
+@pytest.mark.parametrize("M,calls,ticks", [(64, 1, -1), (64, 3, 14), (256, 1, -1), (256, 2, 20)])
+def test_lean_rss_rollout_vs_oracle(M, calls, ticks):
+    """
+    Without a trace and a pair matrix the vehicle kernel runs its lean variant (the safe ratios,
+    pure outputs, are evaluated once after the last tick of a call; M = 256 also takes the
+    sorted sweep): whole and partial rollouts against the oracle.
+    """
+    cfg = synthetic.highway_config(seed=7, N=6, M=M, T=40, lanes=4)
+    cfg.x0[:] = cfg.x0 * 0.5
+    scene = pack_synthetic(cfg)
+    p = _params(timestep=cfg.dt)
+    p.features = abi.FEAT_COLLISIONS | abi.FEAT_EGO_METRICS | abi.FEAT_RSS
+    gpu, cpu = _run_both(scene, p, actions=cfg.actions, n_calls=calls, ticks=ticks)
+    assert cpu.get("rss_flags").any()
+    compare_engines(gpu, cpu, scene, f"lean rss M={M}", check_rss=True)
+
+
 def test_crowd_vs_oracle():
     """C4 shape at reduced size: social force with many neighbours per pedestrian."""
     cfg = synthetic.crowd_config(seed=5, N=6, M=96, T=30, side=9.0)
