@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 7
+#define SG_ABI_VERSION 8
 
 /* entity slot kinds (who produces the slot's next pose each tick) */
 enum SgKind {
@@ -209,6 +209,24 @@ typedef struct SgState {
   double* pid_err;         /* [3][N*M] */
 } SgState;
 
+/* Device-side VehicleAction source for agents that draw uniform random actions (the "random
+   accel/steer" configurations): the value consumed by slot i (= n*M + s) at the k-th tick after
+   reset is
+       low[c] + scale[c] * u_j ,   j = offset[c] + k * tick_stride + i ,   c = 0 accel, 1 steer,
+   where u_j is the j-th double (0-based) of numpy.random.Generator(PCG64).random() started from the
+   given bit-generator state -- PCG64 XSL-RR 128/64, u = (next_uint64 >> 11) * 2^-53, the stream
+   numpy.random.default_rng(seed) produces -- so a host policy drawing
+   rng.uniform(low, high, (T, N*M)) and the device consume bit-identical actions without the table
+   ever crossing PCIe.  The kernels jump ahead per slot (O(log j) at launch, one 128-bit
+   multiply-add per draw afterwards). */
+typedef struct SgActionRng {
+  uint64_t state_hi, state_lo; /* bit_generator.state["state"]["state"] (128 bit) */
+  uint64_t inc_hi, inc_lo;     /* bit_generator.state["state"]["inc"]                */
+  int64_t offset[2];
+  int64_t tick_stride;
+  double low[2], scale[2];
+} SgActionRng;
+
 /* per-call inputs */
 typedef struct SgInputs {
   /* VehicleAction(accel, steer) tables, action.py:66-83: actions[k][c][N*M] is consumed
@@ -221,11 +239,19 @@ typedef struct SgInputs {
   /* SG_KIND_HOST slots: pose returned by the host agent for the next tick */
   const double* host_pose;      /* [6][N*M] or NULL */
   const uint8_t* host_present;  /* [N*M] 0 = agent returned None */
+  /* fp32 action table (policy networks emit fp32; widening is exact): same layout as `actions`,
+     used when `actions` is NULL */
+  const float* actions_f32;
+  /* use_rng != 0 (and no table): actions come from `rng`; the k-th tick executed in this call
+     consumes row rng_tick0 + k, and n_action_ticks bounds the rows as for a table */
+  int32_t use_rng;
+  int32_t rng_tick0;
+  SgActionRng rng;
 } SgInputs;
 
 int sg_abi_version(void);
 /* sizeof() of the ABI structs so bindings can verify their mirror: which = 0 SgParams,
-   1 SgScene, 2 SgState, 3 SgInputs, 4 SgEvent */
+   1 SgScene, 2 SgState, 3 SgInputs, 4 SgEvent, 5 SgActionRng, 6 SgHostResults */
 int64_t sg_sizeof(int which);
 const char* sg_last_error(void);
 void sg_default_params(SgParams* p);
@@ -248,6 +274,12 @@ int sg_rollout(const SgScene* scene, const SgParams* params, SgState* state,
    t [N], slot [N] or NULL, out [N] (0 / 1): device memory. */
 int sg_future_collisions(const SgScene* scene, const double* t, const int32_t* slot, double horizon,
                          int n_samples, uint8_t* out, int device, void* stream);
+
+/* Materialise rows [tick0, tick0 + n_ticks) of the action table an SgActionRng describes:
+   out [n_ticks][2][nm], device memory.  (Used for scenes the fused vehicle kernel does not take,
+   and by the tests that pin the device stream against numpy.) */
+int sg_fill_random_actions(const SgActionRng* rng, int tick0, int n_ticks, int64_t nm, double* out,
+                           int device, void* stream);
 
 /* exact closed-set intersection test of oriented boxes (entity/base.py:100-138 +
    utils.py:28-62), for unit tests: poses [n][3] = x,y,h ; boxes [n][4] ; out[n] */

@@ -116,13 +116,24 @@ class OracleEngine:
 
     def rollout(self, n_ticks: int = -1, actions: Optional[np.ndarray] = None,
                 host_pose: Optional[np.ndarray] = None, host_present: Optional[np.ndarray] = None,
-                step_done: bool = False):
+                step_done: bool = False, tick0: int = 0):
         inp = abi.SgInputs()
         inp.step_done = int(step_done)
-        if actions is not None:
-            actions = np.ascontiguousarray(actions, np.float64)
+        from scenario_gym_b200.action_rng import ActionRng
+
+        if isinstance(actions, ActionRng):  # the oracle's own restatement of numpy's PCG64 stream
+            assert actions.nm == self.scene.N * self.scene.M
+            inp.use_rng, inp.rng_tick0 = 1, int(tick0)
+            inp.rng = actions.struct()
+            inp.n_action_ticks = max(actions.n_ticks - tick0, 0)
+        elif actions is not None:
+            if getattr(actions, "dtype", None) == np.float32:
+                actions = np.ascontiguousarray(actions[tick0:])
+                inp.actions_f32 = actions.ctypes.data
+            else:
+                actions = np.ascontiguousarray(actions[tick0:], np.float64)
+                inp.actions = actions.ctypes.data
             assert actions.shape[1:] == (2, self.scene.N * self.scene.M), actions.shape
-            inp.actions = actions.ctypes.data
             inp.n_action_ticks = actions.shape[0]
         if host_pose is not None:
             inp.host_pose = host_pose.ctypes.data
@@ -132,6 +143,16 @@ class OracleEngine:
         )
         if rc:
             raise RuntimeError(self.lib["last_error"]().decode())
+
+    def fill_actions(self, rng, tick0: int = 0, n_ticks: Optional[int] = None) -> np.ndarray:
+        n_ticks = rng.n_ticks - tick0 if n_ticks is None else n_ticks
+        out = np.empty((n_ticks, 2, rng.nm))
+        r = rng.struct()
+        rc = self.lib["fill_random_actions"](C.byref(r), int(tick0), int(n_ticks), int(rng.nm),
+                                             out.ctypes.data, 0, None)
+        if rc:
+            raise RuntimeError(self.lib["last_error"]().decode())
+        return out
 
     def future_collisions(self, t=None, horizon: float = 5.0, n_samples: int = 10, slot=None) -> np.ndarray:
         tt = np.ascontiguousarray(self.state["t"] if t is None else t, np.float64)

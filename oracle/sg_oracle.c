@@ -42,6 +42,8 @@ int64_t sgo_sizeof(int which) {
     case 2: return sizeof(SgState);
     case 3: return sizeof(SgInputs);
     case 4: return sizeof(SgEvent);
+    case 5: return sizeof(SgActionRng);
+    case 6: return sizeof(SgHostResults);
   }
   return -1;
 }
@@ -800,8 +802,13 @@ static void tick_scenario(const SgScene* sc, const SgParams* p, SgState* st, con
             st->pid_err[i] = e_lon;
             st->pid_err[nm + i] = e_lon_I;
           } else {
-            accel = in->actions[((int64_t)k_action * 2 + 0) * nm + i];
-            steer = in->actions[((int64_t)k_action * 2 + 1) * nm + i];
+            if (in->actions) {
+              accel = in->actions[((int64_t)k_action * 2 + 0) * nm + i];
+              steer = in->actions[((int64_t)k_action * 2 + 1) * nm + i];
+            } else { /* fp32 policy outputs: widening is exact */
+              accel = (double)in->actions_f32[((int64_t)k_action * 2 + 0) * nm + i];
+              steer = (double)in->actions_f32[((int64_t)k_action * 2 + 1) * nm + i];
+            }
           }
           /* VehicleController._step controller.py:105-140 */
           accel = np_clip(accel, -p->veh_max_accel, p->veh_max_accel);
@@ -898,6 +905,56 @@ static void tick_scenario(const SgScene* sc, const SgParams* p, SgState* st, con
   }
 }
 
+/* ---- SgActionRng: numpy's PCG64 stream restated (third-party: numpy 2.3.5,
+   numpy/random/src/pcg64/pcg64.h: pcg_setseq_128_step_r, pcg_output_xsl_rr_128_64, pcg64_advance;
+   numpy/random/_common.pxd / distributions.c: next_double = (next_uint64 >> 11) * (1.0 / 2^53),
+   random_uniform = off + rng * next_double).  Pinned by tests/test_action_rng.py against
+   numpy.random.default_rng itself. ------------------------------------------------------------ */
+typedef unsigned __int128 u128;
+#define PCG_MULT ((((u128)0x2360ED051FC65DA4ULL) << 64) | (u128)0x4385DF649FCCF645ULL)
+
+static u128 pcg_advance(u128 state, u128 inc, u128 delta) {
+  u128 acc_mult = 1, acc_plus = 0, cur_mult = PCG_MULT, cur_plus = inc;
+  while (delta > 0) {
+    if (delta & 1) {
+      acc_mult *= cur_mult;
+      acc_plus = acc_plus * cur_mult + cur_plus;
+    }
+    cur_plus = (cur_mult + 1) * cur_plus;
+    cur_mult *= cur_mult;
+    delta >>= 1;
+  }
+  return acc_mult * state + acc_plus;
+}
+static uint64_t pcg_output(u128 state) {
+  uint64_t hi = (uint64_t)(state >> 64), lo = (uint64_t)state, x = hi ^ lo;
+  unsigned rot = (unsigned)(hi >> 58);
+  return (x >> rot) | (x << ((-rot) & 63));
+}
+
+int sgo_fill_random_actions(const SgActionRng* r, int tick0, int n_ticks, int64_t nm, double* out,
+                            int device, void* stream) {
+  (void)device; (void)stream;
+  const u128 s0 = (((u128)r->state_hi) << 64) | r->state_lo, inc = (((u128)r->inc_hi) << 64) | r->inc_lo;
+  for (int k = 0; k < n_ticks; ++k)
+    for (int c = 0; c < 2; ++c) {
+      u128 st = pcg_advance(s0, inc, (u128)(r->offset[c] + (int64_t)(tick0 + k) * r->tick_stride));
+      double* row = out + ((int64_t)k * 2 + c) * nm;
+      for (int64_t i = 0; i < nm; ++i) {
+        st = st * PCG_MULT + inc;
+        const double u = (double)(pcg_output(st) >> 11) * (1.0 / 9007199254740992.0);
+        row[i] = r->low[c] + r->scale[c] * u;
+      }
+    }
+  return 0;
+}
+
+static int scenario_has_vehicle(const SgScene* sc, int n) {
+  for (int s = 0; s < sc->n_slots; ++s)
+    if (sc->kind[(int64_t)n * sc->n_slots + s] == SG_KIND_VEHICLE) return 1;
+  return 0;
+}
+
 int sgo_rollout(const SgScene* sc, const SgParams* p, SgState* st, const SgInputs* in, int n_ticks,
                 int device, void* stream) {
   (void)device; (void)stream;
@@ -906,14 +963,29 @@ int sgo_rollout(const SgScene* sc, const SgParams* p, SgState* st, const SgInput
   double* newpose = (double*)malloc(sizeof(double) * 6 * M);
   double* newspeed = (double*)malloc(sizeof(double) * M);
   uint8_t* newpres = (uint8_t*)malloc(M);
-  int limit = n_ticks < 0 ? p->max_ticks : n_ticks;
-  if (in && in->actions && limit > in->n_action_ticks) limit = in->n_action_ticks;
+  const int limit = n_ticks < 0 ? p->max_ticks : n_ticks;
+  SgInputs inp;
+  memset(&inp, 0, sizeof(inp));
+  if (in) inp = *in;
+  double* table = NULL;
+  const int have_rows = inp.actions || inp.actions_f32 || inp.use_rng;
+  if (!inp.actions && !inp.actions_f32 && inp.use_rng) { /* materialise the rows this call can consume */
+    int rows = inp.n_action_ticks < limit ? inp.n_action_ticks : limit;
+    if (rows < 0) rows = 0;
+    table = (double*)malloc(sizeof(double) * 2 * NM * (rows > 0 ? rows : 1));
+    sgo_fill_random_actions(&inp.rng, inp.rng_tick0, rows, NM, table, 0, NULL);
+    inp.actions = table;
+  }
   for (int n = 0; n < sc->n_scenarios; ++n) {
-    for (int k = 0; k < limit; ++k) {
-      if (st->done[n] && !(in && in->step_done)) break;
-      tick_scenario(sc, p, st, in, n, k, newpose, newpres, newspeed);
+    /* only scenarios with VehicleController slots are bounded by the action rows */
+    int lim = limit;
+    if (have_rows && lim > inp.n_action_ticks && scenario_has_vehicle(sc, n)) lim = inp.n_action_ticks;
+    for (int k = 0; k < lim; ++k) {
+      if (st->done[n] && !inp.step_done) break;
+      tick_scenario(sc, p, st, &inp, n, k, newpose, newpres, newspeed);
     }
   }
+  free(table);
   free(newpose);
   free(newspeed);
   free(newpres);

@@ -11,7 +11,7 @@ import math
 import os
 from typing import Dict, Optional
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # SgKind
 KIND_EMPTY, KIND_REPLAY, KIND_AGENT_REPLAY, KIND_VEHICLE, KIND_PEDESTRIAN, KIND_HOST, KIND_PID = range(7)
@@ -152,6 +152,19 @@ class SgState(C.Structure):
     ]
 
 
+class SgActionRng(C.Structure):
+    _fields_ = [
+        ("state_hi", C.c_uint64),
+        ("state_lo", C.c_uint64),
+        ("inc_hi", C.c_uint64),
+        ("inc_lo", C.c_uint64),
+        ("offset", C.c_int64 * 2),
+        ("tick_stride", C.c_int64),
+        ("low", C.c_double * 2),
+        ("scale", C.c_double * 2),
+    ]
+
+
 class SgInputs(C.Structure):
     _fields_ = [
         ("actions", _p),
@@ -159,6 +172,10 @@ class SgInputs(C.Structure):
         ("step_done", C.c_int32),
         ("host_pose", _p),
         ("host_present", _p),
+        ("actions_f32", _p),
+        ("use_rng", C.c_int32),
+        ("rng_tick0", C.c_int32),
+        ("rng", SgActionRng),
     ]
 
 
@@ -257,7 +274,8 @@ def default_params() -> SgParams:
 
 EXPORTS = [
     "abi_version", "sizeof", "last_error", "default_params", "reset", "rollout",
-    "test_box_pairs", "rollout_host", "host_h2d_bytes", "host_d2h_bytes",
+    "test_box_pairs", "future_collisions", "fill_random_actions", "rollout_host", "host_h2d_bytes",
+    "host_d2h_bytes",
 ]
 
 
@@ -288,6 +306,8 @@ def bind(lib: C.CDLL, prefix: str) -> Dict[str, object]:
     get("test_box_pairs", C.c_int, [_p, _p, _p, _p, _p, C.c_int64, C.c_int, _p])
     get("future_collisions", C.c_int,
         [C.POINTER(SgScene), _p, _p, C.c_double, C.c_int, _p, C.c_int, _p])
+    get("fill_random_actions", C.c_int,
+        [C.POINTER(SgActionRng), C.c_int, C.c_int, C.c_int64, _p, C.c_int, _p])
     get("rollout_host", C.c_int,
         [C.POINTER(SgScene), C.POINTER(SgScene), C.POINTER(SgParams), C.POINTER(SgState),
          C.POINTER(SgInputs), C.POINTER(SgInputs), C.POINTER(SgHostResults), C.c_int, C.c_int, _p],
@@ -297,7 +317,7 @@ def bind(lib: C.CDLL, prefix: str) -> Dict[str, object]:
 
     if f["abi_version"]() != ABI_VERSION:
         raise RuntimeError(f"ABI version mismatch: lib {f['abi_version']()} != {ABI_VERSION}")
-    for which, st in enumerate((SgParams, SgScene, SgState, SgInputs, SgEvent)):
+    for which, st in enumerate((SgParams, SgScene, SgState, SgInputs, SgEvent, SgActionRng, SgHostResults)):
         if f["sizeof"](which) != C.sizeof(st):
             raise RuntimeError(
                 f"ABI struct {st.__name__}: lib {f['sizeof'](which)} B != ctypes {C.sizeof(st)} B"

@@ -1,0 +1,354 @@
+// sg_api.cu -- the C ABI of include/sg_b200.h: argument checks, kernel selection, host-buffer path.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "sg_internal.h"
+
+static thread_local char g_err[512];
+static int set_err(const char* what, cudaError_t e) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return -2;
+}
+static int set_msg(const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s", what);
+  return -1;
+}
+
+// launch-uniform form of an SgActionRng for rows starting at `tick0` (sg_pcg.cuh)
+static SgRngDev make_rng_dev(const SgActionRng& r, int tick0) {
+  SgRngDev d;
+  memset(&d, 0, sizeof(d));
+  const sg_u128 s0 = sg_u128_make(r.state_hi, r.state_lo), inc = sg_u128_make(r.inc_hi, r.inc_lo);
+  for (int c = 0; c < 2; ++c) {
+    const sg_u128 sc = sg_pcg_advance(s0, inc, (sg_u128)(r.offset[c] + (int64_t)tick0 * r.tick_stride));
+    d.s_hi[c] = (uint64_t)(sc >> 64);
+    d.s_lo[c] = (uint64_t)sc;
+    d.low[c] = r.low[c];
+    d.scale[c] = r.scale[c];
+  }
+  sg_u128 A, C;
+  sg_pcg_jump_coeffs(inc, (sg_u128)r.tick_stride, A, C);
+  d.inc_hi = r.inc_hi; d.inc_lo = r.inc_lo;
+  d.a_hi = (uint64_t)(A >> 64); d.a_lo = (uint64_t)A;
+  d.c_hi = (uint64_t)(C >> 64); d.c_lo = (uint64_t)C;
+  return d;
+}
+
+static int check_rng(const SgActionRng& r) {
+  if (r.offset[0] < 0 || r.offset[1] < 0 || r.tick_stride < 0) return set_msg("SgActionRng: negative offset / stride");
+  if (!(r.inc_lo & 1)) return set_msg("SgActionRng: inc must be odd (not a PCG64 state)");
+  return 0;
+}
+
+static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInputs* in, int n_ticks,
+                  int device, void* stream, int reset) {
+  if (!sc || !p || !st) return set_msg("null argument");
+  if (sc->n_slots < 1 || sc->n_slots > 1024) return set_msg("n_slots must be in 1..1024");
+  if (sc->n_scenarios < 1) return set_msg("n_scenarios must be >= 1");
+  cudaError_t err = cudaSetDevice(device);
+  if (err != cudaSuccess) return set_err("cudaSetDevice", err);
+  const bool ped = sc->route_off != nullptr && sc->n_route_pts > 0;
+  const bool rss = (p->features & SG_FEAT_RSS) != 0;
+  const uint32_t veh_bits = (1u << SG_KIND_VEHICLE), ok_bits = veh_bits | (1u << SG_KIND_EMPTY);
+  const bool veh_only = (sc->kind_mask & veh_bits) && !(sc->kind_mask & ~ok_bits);
+  const bool grid_ok = ped && p->ped_distance_threshold > 0.0 && p->ped_distance_threshold < 1.0e6 &&
+                       !(p->features & SG_FEAT_NO_GRID);
+  GroupLayout L = make_layout(sc->n_slots, ped, rss, veh_only, grid_ok);
+  if (L.grid && (size_t)L.bytes > 227 * 1024) L = make_layout(sc->n_slots, ped, rss, veh_only, false);
+  const int threads = L.G <= SG_THREADS ? SG_THREADS : L.G;
+  const bool big = threads > SG_THREADS;
+  const int gpb = threads / L.G;
+  const int blocks = (sc->n_scenarios + gpb - 1) / gpb;
+  const size_t smem = (size_t)gpb * L.bytes;
+  if (smem > 227 * 1024) return set_msg("scenario does not fit in shared memory");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (reset) {
+    err = sgi_launch_reset(rss, big, blocks, threads, smem, s, *sc, *p, *st, L);
+    if (err != cudaSuccess) return set_err("sg_reset_kernel launch", err);
+    return 0;
+  }
+  SgInputs none;
+  memset(&none, 0, sizeof(none));
+  const SgInputs inp = in ? *in : none;
+  // replay-only scenes (every slot a BatchReplayEntity or ReplayTrajectoryAgent) rolled out for
+  // several ticks: the tick-parallel kernel (sg_replay.cuh)
+  const uint32_t replay_bits = (1u << SG_KIND_EMPTY) | (1u << SG_KIND_REPLAY) | (1u << SG_KIND_AGENT_REPLAY);
+  const bool replay_only = sc->kind_mask != 0 && !(sc->kind_mask & ~replay_bits) &&
+                           (sc->kind_mask & ~(1u << SG_KIND_EMPTY));
+  if (replay_only && !rss && !ped && sc->n_slots <= 32 && st->trace_cap == 0 && !inp.step_done &&
+      !inp.host_present && p->timestep > 0.0 && (n_ticks < 0 || n_ticks >= 8) &&
+      !(p->features & SG_FEAT_SEQUENTIAL)) {
+    err = sgi_launch_replay(s, *sc, *p, *st, n_ticks);
+    if (err != cudaSuccess) return set_err("sg_replay_kernel launch", err);
+    return 0;
+  }
+  const int act = inp.actions ? ACT_F64 : (inp.actions_f32 ? ACT_F32 : (inp.use_rng ? ACT_RNG : -1));
+  SgRngDev rng;
+  memset(&rng, 0, sizeof(rng));
+  if (act == ACT_RNG) {
+    const int rc = check_rng(inp.rng);
+    if (rc) return rc;
+    if (inp.rng_tick0 < 0) return set_msg("rng_tick0 must be >= 0");
+    rng = make_rng_dev(inp.rng, inp.rng_tick0);
+  }
+  if (veh_only) {
+    if (act < 0) return set_msg("vehicle scene needs an action source (table or rng)");
+    if (act != ACT_F64 && !sgi_vehicle_lean(*p, *st))
+      return set_msg("trace / pair-matrix rollouts of vehicle scenes take an fp64 action table "
+                     "(materialise the rows with sg_fill_random_actions / widen the fp32 table)");
+    err = rss ? sgi_launch_vehicle_rss1(sc->n_scenarios, s, *sc, *p, *st, inp, rng, act, n_ticks, L)
+              : sgi_launch_vehicle_rss0(sc->n_scenarios, s, *sc, *p, *st, inp, rng, act, n_ticks, L);
+  } else {
+    err = sgi_launch_rollout(ped, rss, big, blocks, threads, smem, s, *sc, *p, *st, inp, rng, n_ticks, L);
+  }
+  if (err != cudaSuccess) return set_err("sg_rollout_kernel launch", err);
+  return 0;
+}
+
+extern "C" {
+
+int sg_abi_version(void) { return SG_ABI_VERSION; }
+
+int64_t sg_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(SgParams);
+    case 1: return sizeof(SgScene);
+    case 2: return sizeof(SgState);
+    case 3: return sizeof(SgInputs);
+    case 4: return sizeof(SgEvent);
+    case 5: return sizeof(SgActionRng);
+    case 6: return sizeof(SgHostResults);
+  }
+  return -1;
+}
+
+const char* sg_last_error(void) { return g_err; }
+
+void sg_default_params(SgParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->timestep = 1.0 / 30.0;
+  p->terminal = SG_TERM_MAX_LENGTH;
+  p->features = SG_FEAT_COLLISIONS | SG_FEAT_EGO_METRICS;
+  p->max_ticks = 1 << 20;
+  p->veh_max_steer = 0.7;
+  p->veh_max_accel = 5.0;
+  p->veh_max_speed = NAN;
+  p->ped_max_speed = 5.0;
+  p->ped_distance_threshold = 1.0;
+  p->sf_max_speed_factor = 1.3;
+  p->sf_sight_weight = 0.5;
+  p->sf_sight_weight_use = 1;
+  p->sf_sight_angle = 200.0;
+  p->sf_relaxation_time = 1.5;
+  p->sf_ped_repulse_V = 1.0;
+  p->sf_ped_repulse_sigma = 1.0;
+  p->rss_response_time = 0.6;
+  p->rss_min_long_accel = 1.2 * 9.81;
+  p->rss_max_long_accel = 1.2 * 9.81;
+  p->rss_min_safe_clearance = 0.1;
+  p->pid_steer_Kp = 0.03054;
+  p->pid_steer_Kd = 1.5709;
+  p->pid_accel_Kp = 0.3753;
+  p->pid_accel_Kd = 1.8970;
+  p->pid_accel_Ki = 0.0204;
+}
+
+int sg_reset(const SgScene* scene, const SgParams* params, SgState* state, int device, void* stream) {
+  if (state && state->event_count) {
+    cudaError_t err = cudaSetDevice(device);
+    if (err != cudaSuccess) return set_err("cudaSetDevice", err);
+    err = cudaMemsetAsync(state->event_count, 0, sizeof(int32_t), (cudaStream_t)stream);
+    if (err != cudaSuccess) return set_err("cudaMemsetAsync", err);
+  }
+  return launch(scene, params, state, nullptr, 0, device, stream, 1);
+}
+
+int sg_rollout(const SgScene* scene, const SgParams* params, SgState* state, const SgInputs* inputs,
+               int n_ticks, int device, void* stream) {
+  return launch(scene, params, state, inputs, n_ticks, device, stream, 0);
+}
+
+int sg_fill_random_actions(const SgActionRng* rng, int tick0, int n_ticks, int64_t nm, double* out,
+                           int device, void* stream) {
+  if (!rng || (!out && n_ticks > 0 && nm > 0)) return set_msg("null argument");
+  if (tick0 < 0 || n_ticks < 0 || nm < 0) return set_msg("negative size");
+  const int rc = check_rng(*rng);
+  if (rc) return rc;
+  cudaError_t err = cudaSetDevice(device);
+  if (err != cudaSuccess) return set_err("cudaSetDevice", err);
+  err = sgi_launch_fill_actions((cudaStream_t)stream, make_rng_dev(*rng, tick0), n_ticks, nm, out);
+  if (err != cudaSuccess) return set_err("sg_fill_actions_kernel launch", err);
+  return 0;
+}
+
+int sg_test_box_pairs(const double* pose_a, const double* box_a, const double* pose_b,
+                      const double* box_b, uint8_t* out, int64_t n, int device, void* stream) {
+  cudaError_t err = cudaSetDevice(device);
+  if (err != cudaSuccess) return set_err("cudaSetDevice", err);
+  if (n <= 0) return 0;
+  err = sgi_launch_box_pairs((cudaStream_t)stream, pose_a, box_a, pose_b, box_b, out, n);
+  if (err != cudaSuccess) return set_err("sg_box_pairs_kernel launch", err);
+  return 0;
+}
+
+int sg_future_collisions(const SgScene* scene, const double* t, const int32_t* slot, double horizon,
+                         int n_samples, uint8_t* out, int device, void* stream) {
+  if (!scene || !t || !out) return set_msg("null argument");
+  if (n_samples < 1) return set_msg("n_samples must be >= 1");
+  cudaError_t err = cudaSetDevice(device);
+  if (err != cudaSuccess) return set_err("cudaSetDevice", err);
+  err = sgi_launch_future((cudaStream_t)stream, *scene, t, slot, horizon, n_samples, out);
+  if (err != cudaSuccess) return set_err("sg_future_kernel launch", err);
+  return 0;
+}
+
+// ---- host-buffer path ------------------------------------------------------------------
+struct CopyItem { const void* src; void* dst; size_t bytes; };
+
+static int scene_copy_list(const SgScene* h, const SgScene* d, CopyItem* items) {
+  const int64_t N = h->n_scenarios, M = h->n_slots, NM = N * M;
+  int k = 0;
+#define ITEM(field, bytes_) items[k++] = CopyItem{h->field, (void*)d->field, (size_t)(bytes_)}
+  ITEM(kind, NM);
+  ITEM(etype, NM);
+  ITEM(box, 4 * NM * 8);
+  ITEM(traj_off, (NM + 1) * 8);
+  ITEM(traj_rows, h->n_traj_rows * 7 * 8);
+  ITEM(union_off, (N + 1) * 8);
+  ITEM(union_t, h->n_union_rows * 8);
+  ITEM(union_x, h->n_union_rows * 6 * M * 8);
+  ITEM(t0, N * 8);
+  ITEM(length, N * 8);
+  ITEM(ego_slot, N * 4);
+  ITEM(first_slot, N * 4);
+  ITEM(ped_speed_desired, NM * 8);
+  ITEM(route_off, (NM + 1) * 8);
+  ITEM(route_xy, h->n_route_pts * 2 * 8);
+#undef ITEM
+  return k;
+}
+
+int64_t sg_host_h2d_bytes(const SgScene* h, const SgInputs* in, int copy_static) {
+  CopyItem items[16];
+  SgScene dummy = *h;
+  int k = scene_copy_list(h, &dummy, items);
+  int64_t total = 0;
+  if (copy_static)
+    for (int q = 0; q < k; ++q)
+      if (items[q].src) total += (int64_t)items[q].bytes;
+  const int64_t nm = (int64_t)h->n_scenarios * h->n_slots;
+  if (in && in->actions) total += (int64_t)in->n_action_ticks * 2 * nm * 8;
+  else if (in && in->actions_f32) total += (int64_t)in->n_action_ticks * 2 * nm * 4;
+  return total;
+}
+
+int64_t sg_host_d2h_bytes(const SgScene* h) {
+  const int64_t N = h->n_scenarios;
+  return N * (8 * 3 + 4 + 8 + 8 + 1 + 4 + 8) + 4;
+}
+
+// copy stream + events of the host-buffer path, one set per device (created on first use)
+struct HostPathCtx {
+  cudaStream_t copy_stream;
+  cudaEvent_t ev_copy[2], ev_done;
+  bool ready;
+};
+static HostPathCtx g_host_ctx[64];
+
+static int host_ctx(int device, HostPathCtx** out) {
+  if (device < 0 || device >= 64) return set_msg("device index out of range");
+  HostPathCtx& c = g_host_ctx[device];
+  if (!c.ready) {  // (the caller has made `device` current)
+    cudaError_t err = cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) return set_err("cudaStreamCreateWithFlags", err);
+    cudaEvent_t* evs[3] = {&c.ev_copy[0], &c.ev_copy[1], &c.ev_done};
+    for (int q = 0; q < 3; ++q) {
+      err = cudaEventCreateWithFlags(evs[q], cudaEventDisableTiming);
+      if (err != cudaSuccess) return set_err("cudaEventCreateWithFlags", err);
+    }
+    c.ready = true;
+  }
+  *out = &c;
+  return 0;
+}
+
+int sg_rollout_host(const SgScene* hs, const SgScene* ds, const SgParams* params, SgState* dst,
+                    const SgInputs* hin, const SgInputs* din, SgHostResults* res, int copy_static,
+                    int device, void* stream) {
+  if (!hs || !ds || !params || !dst || !res) return set_msg("null argument");
+  cudaError_t err = cudaSetDevice(device);
+  if (err != cudaSuccess) return set_err("cudaSetDevice", err);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (copy_static) {
+    CopyItem items[16];
+    const int k = scene_copy_list(hs, ds, items);
+    for (int q = 0; q < k; ++q) {
+      if (!items[q].src || !items[q].bytes) continue;
+      if (!items[q].dst) return set_msg("device scene mirror is missing an array");
+      err = cudaMemcpyAsync(items[q].dst, items[q].src, items[q].bytes, cudaMemcpyHostToDevice, s);
+      if (err != cudaSuccess) return set_err("cudaMemcpyAsync H2D scene", err);
+    }
+  }
+  int rc = sg_reset(ds, params, dst, device, stream);
+  if (rc) return rc;
+  const int64_t NM = (int64_t)hs->n_scenarios * hs->n_slots;
+  const bool table64 = hin && hin->actions, table32 = hin && !hin->actions && hin->actions_f32;
+  if (table64 || table32) {
+    if (!din || (table64 ? !din->actions : !din->actions_f32)) return set_msg("device action buffer missing");
+    // stream the action table in chunks of ticks: the copy of chunk c+1 overlaps the kernel
+    // of chunk c (copies on a second stream, ordered with events)
+    const int T = hin->n_action_ticks;
+    const int chunk = T < 16 ? T : 16;
+    const size_t esz = table64 ? 8 : 4;
+    HostPathCtx* ctx = nullptr;
+    rc = host_ctx(device, &ctx);
+    if (rc) return rc;
+#define SG_CK(call, what) do { err = (call); if (err != cudaSuccess) return set_err(what, err); } while (0)
+    SG_CK(cudaEventRecord(ctx->ev_done, s), "cudaEventRecord");
+    SG_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0), "cudaStreamWaitEvent");
+    int c = 0;
+    for (int k0 = 0; k0 < T; k0 += chunk, ++c) {
+      const int kt = (T - k0) < chunk ? (T - k0) : chunk;
+      const size_t off = (size_t)k0 * 2 * NM;
+      const char* src = table64 ? (const char*)hin->actions : (const char*)hin->actions_f32;
+      char* dstp = table64 ? (char*)din->actions : (char*)din->actions_f32;
+      SG_CK(cudaMemcpyAsync(dstp + off * esz, src + off * esz, (size_t)kt * 2 * NM * esz,
+                            cudaMemcpyHostToDevice, ctx->copy_stream), "cudaMemcpyAsync H2D actions");
+      SG_CK(cudaEventRecord(ctx->ev_copy[c & 1], ctx->copy_stream), "cudaEventRecord");
+      SG_CK(cudaStreamWaitEvent(s, ctx->ev_copy[c & 1], 0), "cudaStreamWaitEvent");
+      SgInputs part = *din;
+      if (table64) { part.actions = din->actions + off; part.actions_f32 = nullptr; }
+      else { part.actions = nullptr; part.actions_f32 = din->actions_f32 + off; }
+      part.n_action_ticks = kt;
+      rc = sg_rollout(ds, params, dst, &part, kt, device, stream);
+      if (rc) return rc;
+    }
+#undef SG_CK
+  } else {  // no table to move (replay / pedestrians / device-side action source): one fused rollout
+    rc = sg_rollout(ds, params, dst, hin && hin->use_rng ? hin : din, -1, device, stream);
+    if (rc) return rc;
+  }
+  const int64_t N = hs->n_scenarios;
+#define BACK(field, bytes_)                                                                   \
+  if (res->field) {                                                                           \
+    err = cudaMemcpyAsync(res->field, dst->field, (size_t)(bytes_), cudaMemcpyDeviceToHost, s); \
+    if (err != cudaSuccess) return set_err("cudaMemcpyAsync D2H " #field, err);               \
+  }
+  BACK(ego_avg_speed, N * 8);
+  BACK(ego_max_speed, N * 8);
+  BACK(ego_dist, N * 8);
+  BACK(first_coll_tick, N * 4);
+  BACK(first_coll_pair, N * 8);
+  BACK(n_pair_ticks, N * 8);
+  BACK(rss_flags, N);
+  BACK(tick, N * 4);
+  BACK(t, N * 8);
+  BACK(event_count, 4);
+#undef BACK
+  return 0;
+}
+
+}  // extern "C"
+

@@ -1,4 +1,6 @@
-// sg_kernels.cu -- the fused per-tick rollout kernel and the C ABI (include/sg_b200.h).
+// sg_common.cuh -- device code shared by the tick-loop kernels (sg_vehicle.cu, sg_general.cu, sg_crowd.cu):
+// group descriptor, staging of boxes, broad / narrow phase, RSS, social force, tick epilogue.
+//
 //
 // Mapping: one thread per entity slot; the G threads of a scenario ("group") are a
 // sub-warp (M <= 32: G = next pow2, several scenarios per warp) or G/32 whole warps
@@ -17,113 +19,19 @@
 //      fp64 corners; hits set bits in the scenario's collision words;
 //   C  terminal conditions, CollisionMetric rising edges (ego row bit words), ego metrics.
 // Groups synchronise with __syncwarp(mask) (sub-warp) or a named barrier per scenario.
+#pragma once
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
 
 #include "sg_device.cuh"
+#include "sg_layout.h"
 
-#define SG_THREADS 256
-#define SG_NBCAP 12  // per-pedestrian neighbour candidate list kept in shared memory
-#ifndef SG_SORT_MIN_M
-#define SG_SORT_MIN_M 129  // vehicle scenes with at least this many slots use the sorted sweep
-#endif
-#ifndef SG_SWEEP_WIN
-#define SG_SWEEP_WIN 8  // successors tested branch-free by the sorted sweep (a longer run is walked)
-#endif
-#ifndef SG_WARP_PAIRS
-#define SG_WARP_PAIRS 6  // queued pairs per warp up to which the narrow phase runs warp-cooperatively
-#endif
-// uniform cell grid of a crowd scenario (one CTA per scenario): 64 x 64 cells, toroidal
-#define SG_GRID_BITS 6
-#define SG_GRID_DIM (1 << SG_GRID_BITS)
-#define SG_GRID_CELLS (SG_GRID_DIM * SG_GRID_DIM)
-#define SG_GRID_LCAP 64        // entities too large for the grid are kept in a list
-#define SG_GRID_LARGE 0x8000u  // flag on a sorted slot id
-#ifndef SG_VEH_THREADS
-#define SG_VEH_THREADS 128  // CTA size of the vehicle kernel for scenarios of up to that many slots
-#endif
-#ifndef SG_VEH_MINB
-#define SG_VEH_MINB 4  // resident CTAs per SM the vehicle kernel is compiled for
-#endif
-
-__constant__ double c_ngon[64][2];  // (cos, sin)(-k * 2pi/64): GEOS Point.buffer vertices
-
-static thread_local char g_err[512];
-static int set_err(const char* what, cudaError_t e) {
-  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
-  return -2;
-}
-static int set_msg(const char* what) {
-  snprintf(g_err, sizeof(g_err), "%s", what);
-  return -1;
-}
-
-// ---------------------------------------------------------------------------------
-// per-scenario shared-memory block
-struct GroupLayout {
-  int G;        // threads (slots incl. padding) per scenario
-  int W;        // 32-bit words per collision row
-  int H;        // half-sweep length M/2
-  int QCAP;     // candidate-pair queue capacity
-  int off_act, off_rbox, off_tcold, off_hcs, off_ped, off_pednb, off_nbl, off_box, off_ego, off_cold, off_aabb, off_queue, off_hits, off_bits,
-      off_acc, off_flags, off_orient;
-  int sorted;   // vehicle scenes with M >= 128: boxes kept sorted by their lower x bound, windowed sweep
-  int off_sid, off_posof, off_sflag;
-  int grid;     // crowd scenario with a shared-memory cell grid (sensor + broad phase)
-  int off_gstart, off_gsorted, off_glarge, off_gmisc;
-  int bytes;
+// (cos, sin)(-k * 2pi/64): GEOS Point.buffer vertices
+static __constant__ double c_ngon[64][2] = {
+#include "sg_ngon.inc"
 };
-
-enum { EGO_X = 0, EGO_Y, EGO_C, EGO_S, EGO_INV0, EGO_INV1, EGO_HD0, EGO_HD1, EGO_HINV0, EGO_HINV1,
-       EGO_V0, EGO_V1, EGO_VNORM, EGO_VLONG, EGO_W, EGO_L, EGO_RHW, EGO_RHL, EGO_PRESENT, EGO_N = 20 };
-enum { COLD_AVG = 0, COLD_AVG_T, COLD_MAX, COLD_EGOD, COLD_T0, COLD_T1, COLD_PT0, COLD_PT1, COLD_LEN,
-       COLD_OX, COLD_OY, COLD_R2MINA, COLD_ND = 12 };  // doubles (T/PT: tick time, 2 parities)
-enum { COLD_FIRST_TICK = 0, COLD_FP0, COLD_FP1, COLD_RSS, COLD_PAIR_TICKS = 4, COLD_NI = 8 };  // ints
-enum { ACC_NPAIRS = 0, ACC_FIRST_PAIR, ACC_FIRST_HIT, ACC_RSS, ACC_QCOUNT, ACC_N = 8 };
-
-static GroupLayout make_layout(int M, bool ped, bool rss, bool veh, bool grid = false) {
-  GroupLayout L;
-  int G;
-  if (M <= 32) { G = 1; while (G < M) G <<= 1; } else { G = (M + 31) / 32 * 32; }
-  L.G = G;
-  L.W = (M + 31) / 32;
-  L.H = M / 2;
-  L.QCAP = 4 * G;
-  int o = 8 * G * (int)sizeof(double);                            // corners[8][G]
-  L.off_act = o;    o += veh ? 4 * G * (int)sizeof(double) : 0;             // VehicleAction rows, 2 stages x (accel, steer)
-  L.off_rbox = o;   o += rss ? 8 * G * (int)sizeof(double) : 0;   // hazard corners in the ego frame
-  L.off_tcold = o;  o += veh ? 6 * G * (int)sizeof(double) : 0;   // per-thread cold values: sd[2], ratio[2], vh, 1/length
-  L.off_hcs = o;    o += rss ? 2 * G * (int)sizeof(double) : 0;   // cos/sin of each heading
-  L.off_ped = o;    o += ped ? 4 * G * (int)sizeof(double) : 0;   // old x,y,vx,vy (pedestrian sensors)
-  L.off_pednb = o;  o += ped ? (G + 32) * (int)sizeof(float4) : 0; // fp32 sensor boxes of the pedestrians (old state)
-  L.off_nbl = o;    o += ped ? SG_NBCAP * G * (int)sizeof(uint16_t) : 0;
-  o = (o + 15) / 16 * 16;
-  L.off_box = o;    o += 4 * G * (int)sizeof(double);             // width, length, center_x, center_y
-  L.off_ego = o;    o += EGO_N * (int)sizeof(double);
-  L.off_cold = o;   o += COLD_ND * (int)sizeof(double) + COLD_NI * (int)sizeof(int);
-  L.off_aabb = o;   o += (M + L.H + 1) * (int)sizeof(float4);     // duplicated head: no wrap in the sweep
-  L.off_queue = o;  o += L.QCAP * (int)sizeof(uint32_t);
-  L.off_hits = o;   o += 2 * L.W * (int)sizeof(uint32_t);         // ego_now[W], ego_last[W]
-  L.off_bits = o;   o += 2 * L.W * (int)sizeof(uint32_t);         // collided bits, 2 parities
-  L.off_acc = o;    o += 2 * ACC_N * (int)sizeof(int);            // 2 parities
-  L.off_flags = o;  o += G + 16;                                  // old present|etype<<1
-  L.off_orient = o; o += G;                                       // ring orientation of each box
-  o = (o + 15) / 16 * 16;
-  L.sorted = (veh && M >= SG_SORT_MIN_M && G > SG_VEH_THREADS) ? 1 : 0;
-  L.off_sid = o;    o += L.sorted ? (M + 64) * (int)sizeof(uint16_t) : 0;   // slot id at each sorted position
-  L.off_posof = o;  o += L.sorted ? G * (int)sizeof(uint16_t) : 0;          // sorted position of each slot
-  o = (o + 15) / 16 * 16;
-  L.off_sflag = o;  o += L.sorted ? 4 * (int)sizeof(int) : 0;
-  L.grid = (grid && ped && G > SG_THREADS) ? 1 : 0;
-  L.off_gstart = o;  o += L.grid ? (SG_GRID_CELLS / 2 + 4) * (int)sizeof(uint32_t) : 0;  // packed 16-bit cell starts (+ end)
-  L.off_gsorted = o; o += L.grid ? G * (int)sizeof(uint16_t) : 0;                         // slot ids sorted by cell
-  L.off_glarge = o;  o += L.grid ? SG_GRID_LCAP * (int)sizeof(uint16_t) : 0;
-  L.off_gmisc = o;   o += L.grid ? 40 * (int)sizeof(int) : 0;                             // counters + 32 warp totals
-  L.bytes = (o + 15) / 16 * 16;
-  return L;
-}
 
 struct Grp {
   int n, s, M, G, W, H, QCAP, bar_id;
@@ -272,7 +180,7 @@ SG_DEV double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > 
 
 // sin / cos kernels on |x| <= pi/4 (fdlibm k_sin.c / k_cos.c minimax polynomials, < 1 ulp),
 // coefficients read from the constant bank instead of 64-bit immediates
-__constant__ double c_trig[12] = {
+static __constant__ double c_trig[12] = {
     -1.66666666666666324348e-01, 8.33333333332248946124e-03,  -1.98412698298579493134e-04,
     2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10,
     4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
@@ -296,12 +204,12 @@ SG_DEV void sincos_kernel(double x, double& sn, double& cs) {
   cs = w + (((1.0 - w) - hz) + z * (z * q));
 }
 // library fall-backs kept out of line so the tick loop does not carry their code
-__device__ __noinline__ double2 sincos_lib(double x) {  // by value: no address-taken locals in the callers
+static __device__ __noinline__ double2 sincos_lib(double x) {  // by value: no address-taken locals in the callers
   double2 r;
   sincos(x, &r.x, &r.y);
   return r;
 }
-__device__ __noinline__ double tan_lib(double x) { return tan(x); }
+static __device__ __noinline__ double tan_lib(double x) { return tan(x); }
 
 // tan on |x| <= pi/4 (steering angles are clipped to +-max_steer)
 SG_DEV double tan_small(double x) {
@@ -898,7 +806,7 @@ SG_DEV int quad_orientation_sh(unsigned qa, unsigned qs) {
 }
 
 // Does the infinite line through (ax, ay), (bx, by) meet the closed convex quad?  (Exact.)
-__device__ __noinline__ bool line_hits_quad(unsigned qa, unsigned qs, double ax, double ay, double bx,
+static __device__ __noinline__ bool line_hits_quad(unsigned qa, unsigned qs, double ax, double ay, double bx,
                                             double by) {
   int pos = 0, neg = 0;
 #pragma unroll 1
@@ -913,7 +821,7 @@ __device__ __noinline__ bool line_hits_quad(unsigned qa, unsigned qs, double ax,
 // Closed intersection of a convex quad with the rectangle [-a, a] x [-b, b] whose bounding
 // ranges already overlap: separating axes are the quad's edges; per edge only the rectangle
 // corner that is extreme towards the quad's inside has to be tested.  (Exact.)
-__device__ __noinline__ bool quad_hits_centered_rect(unsigned qa, unsigned qs, double a, double b) {
+static __device__ __noinline__ bool quad_hits_centered_rect(unsigned qa, unsigned qs, double a, double b) {
   const int o = quad_orientation_sh(qa, qs);
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) {
@@ -932,7 +840,7 @@ __device__ __noinline__ bool quad_hits_centered_rect(unsigned qa, unsigned qs, d
 // quad's y-range already contains c: the quad's corners are then not strictly on one side of
 // the segment's line, so the segment misses the quad iff some quad edge has both segment
 // endpoints strictly outside.  (Exact.)
-__device__ __noinline__ bool quad_hits_hsegment(unsigned qa, unsigned qs, double w, double c) {
+static __device__ __noinline__ bool quad_hits_hsegment(unsigned qa, unsigned qs, double w, double c) {
   const int o = quad_orientation_sh(qa, qs);
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) {
@@ -943,7 +851,7 @@ __device__ __noinline__ bool quad_hits_hsegment(unsigned qa, unsigned qs, double
   return true;
 }
 
-__device__ __noinline__ bool rss_box_hits_segment(unsigned qa, unsigned qs, double x0, double y0,
+static __device__ __noinline__ bool rss_box_hits_segment(unsigned qa, unsigned qs, double x0, double y0,
                                                   double x1, double y1) {
   const Quad q = load_quad_shared(qa, qs);
   return quad_intersects_segment(q, quad_orientation(q), x0, y0, x1, y1);
@@ -1136,7 +1044,7 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
 // exact narrow phase for one AABB-surviving pair; both quads are read on the fly from the staged
 // corners with ld.shared inside rolled loops (`csh`: shared address of corners[0][0]), so the
 // routine needs few registers and its callers save little around the call
-__device__ __noinline__ bool pair_collides(unsigned csh, const int8_t* orient, int G, int a, int b) {
+static __device__ __noinline__ bool pair_collides(unsigned csh, const int8_t* orient, int G, int a, int b) {
   const unsigned qs = (unsigned)G * 8u;
   unsigned pa = csh + (unsigned)a * 8u, pb = csh + (unsigned)b * 8u;
   bool same = true;
@@ -1185,7 +1093,7 @@ SG_DEV PairSink make_sink(int features, uint32_t* coll_mask, const Grp& c, int e
 }
 
 // book-keeping for one colliding pair (scenario-level shared atomics)
-__device__ __noinline__ void commit_pair(PairSink k, int a, int b) {
+static __device__ __noinline__ void commit_pair(PairSink k, int a, int b) {
   const int lo = min(a, b), hi = max(a, b);
   atomicAdd(&k.acc[ACC_NPAIRS], 1);
   atomicMin(&k.acc[ACC_FIRST_PAIR], (lo << 16) | hi);
@@ -1265,7 +1173,7 @@ SG_DEV void broad_phase(const Grp& c, int parity) {
 }
 
 // queue overflow (very dense scenes): redo the sweep and test every survivor in place
-__device__ __noinline__ void broad_phase_direct(PairSink k, const float4* aabb, unsigned corners_sh,
+static __device__ __noinline__ void broad_phase_direct(PairSink k, const float4* aabb, unsigned corners_sh,
                                                 const int8_t* orient, int G, int M, int H, int s) {
   const float4 mb = aabb[s];
   for (int d = 1; d <= H; ++d) {
@@ -1278,7 +1186,7 @@ __device__ __noinline__ void broad_phase_direct(PairSink k, const float4* aabb, 
   }
 }
 
-__device__ __noinline__ void broad_phase_direct_sorted(PairSink k, const float4* aabb, const uint16_t* sid,
+static __device__ __noinline__ void broad_phase_direct_sorted(PairSink k, const float4* aabb, const uint16_t* sid,
                                                        unsigned corners_sh, const int8_t* orient, int G, int M,
                                                        int r) {
   const float4 mb = aabb[r];
@@ -1291,7 +1199,7 @@ __device__ __noinline__ void broad_phase_direct_sorted(PairSink k, const float4*
 }
 
 // CollisionMetric rising edges of one ego-row word (rare: out of line)
-__device__ __noinline__ void emit_events(SgEvent* events, int32_t* event_count, int event_cap, uint32_t fresh,
+static __device__ __noinline__ void emit_events(SgEvent* events, int32_t* event_count, int event_cap, uint32_t fresh,
                                          int n, int tick, int slot0, double t) {
   while (fresh) {
     const int b = __ffs(fresh) - 1;
@@ -1394,6 +1302,7 @@ SG_DEV void load_cold(const SgState& st, const Grp& c, int n, int s, int W, int 
     c.cold_i[COLD_FP0] = st.first_coll_pair[2 * n]; c.cold_i[COLD_FP1] = st.first_coll_pair[2 * n + 1];
     *(long long*)(c.cold_i + COLD_PAIR_TICKS) = st.n_pair_ticks[n];
     c.cold_i[COLD_RSS] = st.rss_flags[n];
+    c.cold_i[COLD_HAS_VEH] = 0;
     for (int q = 0; q < 2 * ACC_N; ++q) c.acc[q] = 0;
     c.acc[ACC_FIRST_PAIR] = 0x7fffffff; c.acc[ACC_N + ACC_FIRST_PAIR] = 0x7fffffff;
   }
@@ -1426,1011 +1335,3 @@ SG_DEV RssConst make_rss_const(const SgParams& p) {
   K.r2mina = 1.0 / (2 * p.rss_min_long_accel);
   return K;
 }
-
-// ---------------------------------------------------------------------------------
-// Vehicle-only scenes (every live slot has a VehicleController; C3 / C5): a lean tick that
-// keeps x, y, h, their velocities, cos/sin of the heading, distance and speed in registers.
-// z, p, r never change under VehicleController._step (controller.py:122-131), so their
-// velocities are 0 after the first tick and they stay in global memory.
-// ---------------------------------------------------------------------------------
-template <bool RSS, int MAXT, int MINB, bool SORTED, bool LEAN = false>
-__global__ void __launch_bounds__(MAXT, MINB)
-sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, GroupLayout L) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int G = L.G, M = sc.n_slots, W = L.W;
-  const int gpb = blockDim.x / G;
-  const int gl = threadIdx.x / G;
-  const int s = threadIdx.x - gl * G;
-  const int n = blockIdx.x * gpb + gl;
-  if (gl >= gpb || n >= sc.n_scenarios) return;
-  Grp c;
-  setup_group(c, sc, L, smem, gl, s, n);
-  const bool live = s < M && sc.kind[c.i] == SG_KIND_VEHICLE;
-  const int ego_slot = sc.ego_slot[n], first_slot = sc.first_slot[n];
-  // (LEAN is only launched with collisions on, no trace and no pair matrix; RSS only with the feature on)
-  const bool need_coll = LEAN || (p.features & SG_FEAT_COLLISIONS) ||
-                         (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
-  const bool feat_rss = RSS;
-  const bool matrix = !LEAN && (p.features & SG_FEAT_COLL_MATRIX) != 0;
-
-  // hot per-entity state in registers; everything that is only read back at the end (safe
-  // distances, ratios, heading rate) or is uniform per scenario (tick times, length, origin)
-  // lives in shared memory to keep the register footprint of the tick loop small
-  double x = 0, y = 0, h = 0, vx = 0, vy = 0, dist = 0, speed = 0, cs = 1, sn = 0;
-  int orient_hint = 0;
-  bool present = false;
-  uint8_t collided = 0, rss_state = 0, rss_last = SG_RSS_NONE;
-  bool rss_evald = false;  // RSSDistances ran for this hazard in the last executed tick
-  double* tc = c.tcold + s;  // [0..3] safe dist / ratios, [4] heading rate, [5] 1 / wheelbase
-  {
-    const int64_t i = c.i, nm = c.nm;
-    if (live) {
-      x = st.pose[i]; y = st.pose[nm + i]; h = st.pose[3 * nm + i];
-      vx = st.vel[i]; vy = st.vel[nm + i];
-      dist = st.dist[i]; speed = st.speed[i];
-      present = st.present[i] != 0;
-      collided = st.collided[i];
-      sincos_fast(h, sn, cs);
-      const double bw = sc.box[i], bl = sc.box[nm + i];
-      c.boxp[s] = bw; c.boxp[G + s] = bl;
-      c.boxp[2 * G + s] = sc.box[2 * nm + i]; c.boxp[3 * G + s] = sc.box[3 * nm + i];
-      tc[4 * G] = st.vel[3 * nm + i];
-      tc[5 * G] = 1.0 / bl;
-      orient_hint = box_orientation_hint(bw, bl);
-      if (RSS) {
-        rss_state = st.rss_state[i]; rss_last = st.rss_last[i];
-        tc[0] = st.safe_dist[i]; tc[G] = st.safe_dist[nm + i];
-        tc[2 * G] = st.safe_ratio[i]; tc[3 * G] = st.safe_ratio[nm + i];
-      }
-    }
-    if (s == 0) {
-      double* U = c.cold_d;
-      U[COLD_T0] = st.t[n]; U[COLD_PT0] = st.prev_t[n];
-      U[COLD_LEN] = sc.length[n];
-      const int64_t er = sc.traj_off[(int64_t)n * M + ego_slot];  // origin of the fp32 bounds
-      U[COLD_OX] = __ldg(sc.traj_rows + er * 7 + 1);
-      U[COLD_OY] = __ldg(sc.traj_rows + er * 7 + 2);
-      U[COLD_R2MINA] = 1.0 / (2 * p.rss_min_long_accel);
-    }
-  }
-  int tick = st.tick[n];
-  bool done = st.done[n] != 0;
-  load_cold(st, c, n, s, W, ego_slot);
-  if (RSS && s == ego_slot) publish_ego_box(c);
-  if (SORTED) sorted_setup(c);
-  int sort_round = 0;
-  group_sync(c);
-
-  int limit = n_ticks < 0 ? p.max_ticks : n_ticks;
-  if (limit > in.n_action_ticks) limit = in.n_action_ticks;
-  int parity = 0;
-  const int tick0 = tick;
-  // VehicleAction rows are staged one tick ahead with cp.async (no registers held)
-  const double* act = in.actions + c.i;
-  double* ab = c.actbuf + s;
-  const unsigned ab_sh = (unsigned)__cvta_generic_to_shared(ab);  // converted once, not per tick
-  if (live && limit > 0 && (!done || in.step_done)) { cp_async8(ab_sh, act); cp_async8(ab_sh + G * 8, act + c.nm); }
-  cp_async_commit();
-
-  for (int k = 0; k < limit && (!done || in.step_done); ++k) {
-    const double* U = c.cold_d;
-    const double t = U[COLD_T0 + parity];
-    const double next_t = t + p.timestep;  // scenario_gym.py:229
-    const double dt = next_t - t;          // controller.py:123 and State.dt after the step
-    cp_async_wait_all();
-    if (live && present) {  // VehicleController._step, controller.py:105-140
-      const double accel = clipd(ab[parity * 2 * G], -p.veh_max_accel, p.veh_max_accel);
-      const double steer = clipd(ab[parity * 2 * G + G], -p.veh_max_steer, p.veh_max_steer);
-      const double dx = speed * cs, dy = speed * sn;
-      const double tn = fabs(steer) <= 0.78 ? tan_small(steer) : tan_lib(steer);
-      const double dh = div_r(speed * tn, c.boxp[G + s], tc[5 * G]);
-      const double nx = x + dx * dt, ny = y + dy * dt, nh = h + dh * dt;
-      double ns = speed + accel * dt;
-      if (!p.veh_allow_reverse) ns = ns < 0.0 ? 0.0 : ns;
-      if (p.veh_max_speed == p.veh_max_speed) ns = ns > p.veh_max_speed ? p.veh_max_speed : ns;
-      speed = ns;
-      // State.update_statistics (state.py:230-239)
-      const double rdt = fast_rcp(dt);
-      const double ex = nx - x, ey = ny - y;
-      vx = div_r(ex, dt, rdt); vy = div_r(ey, dt, rdt);
-      tc[4 * G] = div_r(nh - h, dt, rdt);
-      dist += fnorm2(ex, ey);
-      x = nx; y = ny; h = nh;
-      sincos_fast(h, sn, cs);
-    }
-    if (live && k + 1 < limit) {
-      act += 2 * c.nm;
-      cp_async8(ab_sh + (parity ^ 1) * 2 * G * 8, act);
-      cp_async8(ab_sh + ((parity ^ 1) * 2 * G + G) * 8, act + c.nm);
-    }
-    cp_async_commit();
-    tick += 1;
-    if (!LEAN && st.trace_cap > 0 && tick < st.trace_cap && s < M) {
-      const int64_t i = c.i, nm = c.nm;
-      st.trace_present[(int64_t)tick * nm + i] = present;
-      double* tp = st.trace_pose + (int64_t)tick * 6 * nm + i;
-      tp[0] = x; tp[nm] = y; tp[2 * nm] = st.pose[2 * nm + i]; tp[3 * nm] = h;
-      tp[4 * nm] = st.pose[4 * nm + i]; tp[5 * nm] = st.pose[5 * nm + i];
-      if (s == 0) st.trace_t[(int64_t)tick * sc.n_scenarios + n] = next_t;
-    }
-    if (s < M) {
-      if (need_coll || feat_rss)
-        publish_box<RSS, SORTED>(c, present, x, y, cs, sn, orient_hint, U[COLD_OX], U[COLD_OY]);
-      if (!LEAN && matrix) {
-        uint32_t* row = st.coll_mask + ((int64_t)n * M + s) * W;
-        for (int w = 0; w < W; ++w) row[w] = 0;
-      }
-    }
-    if (RSS && feat_rss && s == ego_slot) publish_ego(c, present, x, y, cs, sn, vx, vy);
-    if (s == 0) {  // the next tick reads its times from the other parity
-      c.cold_d[COLD_T0 + (parity ^ 1)] = next_t;
-      c.cold_d[COLD_PT0 + (parity ^ 1)] = t;
-    }
-    group_sync(c);
-    if (SORTED && need_coll) sort_positions(c, sort_round);
-    // ---- phase B1: callbacks (RSS) + broad phase
-    if (live && present) {
-      if (RSS && feat_rss) {  // RSSDistances.__call__, callback.py:57-122
-        rss_last = SG_RSS_NONE;
-        rss_evald = false;
-        if (next_t != 0.0 && s != ego_slot && c.egop[EGO_PRESENT] != 0.0) {
-          RssConst KR;
-          KR.CLR = p.rss_min_safe_clearance; KR.RT = p.rss_response_time;
-          KR.MAXA = p.rss_max_long_accel; KR.MINA = p.rss_min_long_accel;
-          KR.r2mina = c.cold_d[COLD_R2MINA];
-          // (lean rollouts: the safe ratios are pure outputs - computed once after the last tick)
-          rss_last = (uint8_t)rss_hazard<!LEAN>(KR, c, x, y, vx, vy, rss_state, tc, G);
-          rss_evald = true;
-          const int found = (rss_state >> 2) & 3;  // RSS metric latch, rss.py:71-103
-          if (found) atomicOr(&c.acc[parity * ACC_N + ACC_RSS], found == 2 ? 1 : 2);
-        }
-      }
-      if (need_coll && !SORTED) broad_phase(c, parity);
-    }
-    if (SORTED && need_coll && s < M) broad_phase_sorted(c, parity);
-    group_sync(c);
-    done = finish_tick<true>(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick,
-                       c.cold_d[COLD_T0 + (parity ^ 1)], c.cold_d[COLD_T0 + (parity ^ 1)] - c.cold_d[COLD_PT0 + (parity ^ 1)],
-                       c.cold_d[COLD_LEN], live, live && present, collided, vx, vy, 0.0, dist);
-    parity ^= 1;
-  }
-
-  if (RSS && LEAN && live && present && rss_evald) rss_ratios(c, x, y, tc, G);
-  if (live) {
-    const int64_t i = c.i, nm = c.nm;
-    st.pose[i] = x; st.pose[nm + i] = y; st.pose[3 * nm + i] = h;
-    st.vel[i] = vx; st.vel[nm + i] = vy; st.vel[3 * nm + i] = tc[4 * G];
-    if (tick > tick0 && present) { st.vel[2 * nm + i] = 0.0; st.vel[4 * nm + i] = 0.0; st.vel[5 * nm + i] = 0.0; }
-    st.dist[i] = dist;
-    st.speed[i] = speed;
-    st.collided[i] = collided;
-    if (RSS) {
-      st.rss_state[i] = rss_state; st.rss_last[i] = rss_last;
-      st.safe_dist[i] = tc[0]; st.safe_dist[nm + i] = tc[G];
-      st.safe_ratio[i] = tc[2 * G]; st.safe_ratio[nm + i] = tc[3 * G];
-    }
-  }
-  if (s == 0) {
-    st.t[n] = c.cold_d[COLD_T0 + parity]; st.prev_t[n] = c.cold_d[COLD_PT0 + parity];
-    st.tick[n] = tick; st.done[n] = done;
-  }
-  store_cold(st, c, n, s, W, ego_slot);
-}
-
-// ---------------------------------------------------------------------------------
-// General scenes: replay / batch replay / vehicles / pedestrians / host-driven slots.
-// ---------------------------------------------------------------------------------
-struct Ent {
-  double pose[6], vel[6], dist, speed;
-  bool present;
-};
-
-template <bool PED, bool RSS, int MAXT>
-__global__ void __launch_bounds__(MAXT, MAXT >= 1024 ? 1 : 2)
-sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, GroupLayout L) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int G = L.G, M = sc.n_slots, W = L.W;
-  const int gpb = blockDim.x / G;  // scenario groups per CTA
-  const int gl = threadIdx.x / G;
-  const int s = threadIdx.x - gl * G;
-  const int n = blockIdx.x * gpb + gl;
-  if (gl >= gpb || n >= sc.n_scenarios) return;
-  Grp c;
-  setup_group(c, sc, L, smem, gl, s, n);
-
-  const bool live = s < M;  // padding threads only take part in barriers
-  const int64_t i = c.i, nm = c.nm;
-  const int kind = live ? sc.kind[i] : SG_KIND_EMPTY;
-  const int etype = live ? sc.etype[i] : 0;
-  const int ego_slot = sc.ego_slot[n], first_slot = sc.first_slot[n];
-  const bool need_coll = (p.features & SG_FEAT_COLLISIONS) ||
-                         (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
-  const bool feat_rss = RSS && (p.features & SG_FEAT_RSS);
-  const bool matrix = (p.features & SG_FEAT_COLL_MATRIX) != 0;
-  const bool exact_div = kind <= SG_KIND_AGENT_REPLAY || kind == SG_KIND_PID;  // IEEE quotients
-  const RssConst KR = make_rss_const(p);
-
-  double bl = 1;
-  int orient_hint = 0;
-  const double* rows = nullptr;
-  int K = 0;
-  if (kind != SG_KIND_EMPTY) {
-    const double bw = sc.box[i];
-    bl = sc.box[nm + i];
-    c.boxp[s] = bw; c.boxp[G + s] = bl;
-    c.boxp[2 * G + s] = sc.box[2 * nm + i]; c.boxp[3 * G + s] = sc.box[3 * nm + i];
-    orient_hint = box_orientation_hint(bw, bl);
-    const int64_t r0 = sc.traj_off[i];
-    K = (int)(sc.traj_off[i + 1] - r0);
-    rows = sc.traj_rows + r0 * 7;
-  }
-  const double traj_min_t = K ? __ldg(rows) : 0.0;
-  const double traj_max_t = K ? __ldg(rows + (int64_t)(K - 1) * 7) : 0.0;
-  const double rcp_bl = 1.0 / bl;
-  double ox, oy;  // scenario origin for the fp32 bounds: the ego's first control point
-  {
-    const int64_t er = sc.traj_off[(int64_t)n * M + ego_slot];
-    ox = __ldg(sc.traj_rows + er * 7 + 1);
-    oy = __ldg(sc.traj_rows + er * 7 + 2);
-  }
-  const double sight_cos = PED ? cos(p.sf_sight_angle / 2 * M_PI / 180) : 0.0;
-  const double length = sc.length[n];
-
-  // ---- load the State rows ------------------------------------------------------------
-  Ent e;
-  double t = st.t[n], prev_t = st.prev_t[n];
-  int tick = st.tick[n], cur_union = st.cur_union[n];
-  bool done = st.done[n] != 0;
-  int cur_own = 1, goal = 0;
-  double force[2] = {0, 0}, sd[2] = {0, 0}, ratio[2] = {0, 0};
-  uint8_t rss_state = 0, rss_last = SG_RSS_NONE, collided = 0;
-  if (live) {
-#pragma unroll
-    for (int f = 0; f < 6; ++f) { e.pose[f] = st.pose[f * nm + i]; e.vel[f] = st.vel[f * nm + i]; }
-    e.dist = st.dist[i];
-    e.speed = st.speed[i];
-    e.present = st.present[i] != 0;
-    cur_own = st.cur_own[i];
-    collided = st.collided[i];
-    if (PED) { goal = st.goal_idx[i]; force[0] = st.force[i]; force[1] = st.force[nm + i]; }
-    if (RSS) {
-      rss_state = st.rss_state[i]; rss_last = st.rss_last[i];
-      sd[0] = st.safe_dist[i]; sd[1] = st.safe_dist[nm + i];
-      ratio[0] = st.safe_ratio[i]; ratio[1] = st.safe_ratio[nm + i];
-    }
-  } else {
-#pragma unroll
-    for (int f = 0; f < 6; ++f) { e.pose[f] = 0; e.vel[f] = 0; }
-    e.dist = 0; e.speed = 0; e.present = false;
-  }
-  load_cold(st, c, n, s, W, ego_slot);
-  if (RSS && s == ego_slot) publish_ego_box(c);
-  // crowd scenarios (one CTA per scenario) bin their entities into a cell grid of the sensor radius
-  const bool use_grid = PED && L.grid != 0;
-  const double grid_cs = p.ped_distance_threshold * (1.0 + 1e-6), grid_inv_cs = 1.0 / grid_cs;
-  GridPos gpos;
-  gpos.ix = 0; gpos.iy = 0; gpos.large = false;
-  if (PED) {  // the "old" state the pedestrians' sensors read in the first tick
-    if (live) stage_ped_state(c, e.present, etype, e.pose[0], e.pose[1], e.vel[0], e.vel[1],
-                              p.ped_distance_threshold, ox, oy);
-    for (int q = s; q < 32; q += G) c.pednb[M + q] = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
-    if (use_grid) gpos = grid_build(c, live && e.present, false, e.pose[0], e.pose[1], ox, oy, grid_cs, grid_inv_cs);
-  }
-  group_sync(c);
-
-  int limit = n_ticks < 0 ? p.max_ticks : n_ticks;
-  if (in.actions && limit > in.n_action_ticks) limit = in.n_action_ticks;
-  int parity = 0;
-
-  for (int k = 0; k < limit && (!done || in.step_done); ++k) {
-    // ---------------- phase A: agents / batch replay produce the new poses ----------------
-    const double next_t = t + p.timestep;  // scenario_gym.py:229
-    double np_[6];
-    bool newpres = false;
-    double newspeed = e.speed;
-    double ped_np[6], ped_speed = e.speed;
-    if (PED)  // every lane calls: whole warps of a scenario share the neighbour terms
-      pedestrian_step<PED>(sc, p, c, kind == SG_KIND_PEDESTRIAN && e.present, G >= 32, e.pose, e.vel, t,
-                           prev_t, next_t, sight_cos, goal, force, ped_speed, ped_np, use_grid, ox, oy,
-                           grid_inv_cs);
-    if (kind >= SG_KIND_AGENT_REPLAY) {  // scenario_gym.py:233-244
-      if (e.present) {
-        if (kind == SG_KIND_AGENT_REPLAY) {  // agent.py:125-128, extrapolate=(False, False)
-          position_at_t(rows, K, next_t, EXT_CLAMP, cur_own, np_);
-          newpres = true;
-        } else if (kind == SG_KIND_VEHICLE || kind == SG_KIND_PID) {
-          double accel, steer;
-          double sh, ch;
-          sincos(e.pose[3], &sh, &ch);
-          if (kind == SG_KIND_PID) {
-            // PIDAgent._step (agent.py:144-148) + PIDController._step (controller.py:205-258);
-            // the three error terms stay in global memory (rare kind)
-            double tgt[6];
-            position_at_t(rows, K, next_t, EXT_CLAMP, cur_own, tgt);
-            const double e0 = tgt[0] - e.pose[0], e1 = tgt[1] - e.pose[1];
-            const double e_lon = ch * e0 + sh * e1, e_lat = -sh * e0 + ch * e1;
-            double gain_adj;
-            if (e.speed > 5.0 && e.speed <= 15) gain_adj = 1.0 - 0.9 * ((e.speed - 5.0)) / 10.0;
-            else if (e.speed > 15) gain_adj = 0.1;
-            else gain_adj = 1.0;
-            const double sdt = t - prev_t;  // state.dt
-            const double e_lat_D = (e_lat - st.pid_err[2 * nm + i]) / sdt;
-            steer = (p.pid_steer_Kp * gain_adj) * e_lat + (p.pid_steer_Kd * gain_adj) * e_lat_D;
-            const double e_lon_D = (e_lon - st.pid_err[i]) / sdt;
-            const double e_lon_I = st.pid_err[nm + i] + e_lon * sdt;
-            accel = fabs(e_lon) > 0.1
-                        ? p.pid_accel_Kp * e_lon + p.pid_accel_Kd * e_lon_D + p.pid_accel_Ki * e_lon_I
-                        : 0.0;
-            st.pid_err[2 * nm + i] = e_lat;
-            st.pid_err[i] = e_lon;
-            st.pid_err[nm + i] = e_lon_I;
-          } else {
-            accel = __ldcs(in.actions + ((int64_t)k * 2 + 0) * nm + i);
-            steer = __ldcs(in.actions + ((int64_t)k * 2 + 1) * nm + i);
-          }
-          // VehicleController._step, controller.py:105-140
-          accel = np_clip(accel, -p.veh_max_accel, p.veh_max_accel);
-          steer = np_clip(steer, -p.veh_max_steer, p.veh_max_steer);
-          const double dt = next_t - t;
-          const double dx = e.speed * ch, dy = e.speed * sh;
-          const double dh = div_r(e.speed * tan(steer), bl, rcp_bl);
-#pragma unroll
-          for (int f = 0; f < 6; ++f) np_[f] = e.pose[f];
-          np_[0] += dx * dt;
-          np_[1] += dy * dt;
-          np_[3] += dh * dt;
-          double ns = e.speed + accel * dt;
-          if (!p.veh_allow_reverse) ns = fmax(0.0, ns);
-          if (!isnan(p.veh_max_speed)) ns = fmin(p.veh_max_speed, ns);
-          newspeed = ns;
-          newpres = true;
-        } else if (kind == SG_KIND_PEDESTRIAN) {
-#pragma unroll
-          for (int f = 0; f < 6; ++f) np_[f] = ped_np[f];
-          newspeed = ped_speed;
-          newpres = true;
-        } else {  // SG_KIND_HOST
-          if (in.host_present && in.host_present[i]) {
-#pragma unroll
-            for (int f = 0; f < 6; ++f) np_[f] = in.host_pose[f * nm + i];
-            newpres = true;
-          } else if (p.persist) {  // scenario_gym.py:238-239
-#pragma unroll
-            for (int f = 0; f < 6; ++f) np_[f] = e.pose[f];
-            newpres = true;
-          }
-        }
-      } else if (traj_min_t >= t) {  // :240-244 agent initialised at its start position
-        position_at_t(rows, K, next_t, EXT_CLAMP, cur_own, np_);
-        newpres = true;
-      }
-    } else if (kind == SG_KIND_REPLAY) {  // BatchReplayEntity.step, entity/batch.py:34-53
-      const int64_t u0 = sc.union_off[n];
-      const int UK = (int)(sc.union_off[n + 1] - u0);
-      const double* ts = sc.union_t + u0;
-      if (p.persist || K == 1 || (next_t >= traj_min_t && next_t <= traj_max_t)) {
-        const double* X = sc.union_x + u0 * 6 * M;
-        if (next_t < __ldg(ts)) {  // fill_value = (X[0], X[-1]), entity/batch.py:120-127
-#pragma unroll
-          for (int f = 0; f < 6; ++f) np_[f] = __ldg(X + f * M + s);
-        } else if (next_t > __ldg(ts + UK - 1)) {
-#pragma unroll
-          for (int f = 0; f < 6; ++f) np_[f] = __ldg(X + ((int64_t)(UK - 1) * 6 + f) * M + s);
-        } else {  // every thread advances the scenario's shared cursor identically
-          cur_union = search_left_cursor(ts, 1, UK, next_t, cur_union);
-          const double x_lo = __ldg(ts + cur_union - 1), x_hi = __ldg(ts + cur_union);
-          const double w1 = (next_t - x_lo) / (x_hi - x_lo), w0 = (x_hi - next_t) / (x_hi - x_lo);
-          const double* lo = X + (int64_t)(cur_union - 1) * 6 * M + s;
-#pragma unroll
-          for (int f = 0; f < 6; ++f) np_[f] = w1 * __ldg(lo + (6 + f) * M) + w0 * __ldg(lo + f * M);
-        }
-        newpres = true;
-      }
-    }
-    // ---------------- State.step: update_poses / update_statistics (state.py:203-239) -------
-    prev_t = t;
-    t = next_t;
-    tick += 1;
-    const double dt = t - prev_t;
-    if (newpres) {
-      double prev[6];
-      if (e.present) {
-#pragma unroll
-        for (int f = 0; f < 6; ++f) prev[f] = e.pose[f];
-      } else {  // :219-222 newcomer: previous pose extrapolated from its trajectory
-        int cur = 0;
-        position_at_t(rows, K, prev_t, EXT_TRUE, cur, prev);
-      }
-      double d[6];
-      if (exact_div) {
-#pragma unroll
-        for (int f = 0; f < 6; ++f) { d[f] = np_[f] - prev[f]; e.vel[f] = d[f] / dt; }
-      } else {
-        const double rdt = 1.0 / dt;
-#pragma unroll
-        for (int f = 0; f < 6; ++f) { d[f] = np_[f] - prev[f]; e.vel[f] = div_r(d[f], dt, rdt); }
-      }
-#pragma unroll
-      for (int f = 0; f < 6; ++f) e.pose[f] = np_[f];
-      e.dist += norm3(d[0], d[1], d[2]);
-      e.speed = newspeed;
-    }
-    e.present = newpres;
-    if (st.trace_cap > 0 && tick < st.trace_cap && live) {
-      st.trace_present[(int64_t)tick * nm + i] = e.present;
-#pragma unroll
-      for (int f = 0; f < 6; ++f) st.trace_pose[((int64_t)tick * 6 + f) * nm + i] = e.pose[f];
-      if (s == 0) st.trace_t[(int64_t)tick * sc.n_scenarios + n] = t;
-    }
-    double hs = 0, hc = 1;
-    if (live) {
-      if (need_coll || feat_rss) {
-        if (e.present) sincos(e.pose[3], &hs, &hc);
-        publish_box<RSS>(c, e.present, e.pose[0], e.pose[1], hc, hs, orient_hint, ox, oy);
-      }
-      if (matrix) {
-        uint32_t* row = st.coll_mask + ((int64_t)n * M + s) * W;
-        for (int w = 0; w < W; ++w) row[w] = 0;
-      }
-    }
-    if (RSS && feat_rss && s == ego_slot)
-      publish_ego(c, e.present, e.pose[0], e.pose[1], hc, hs, e.vel[0], e.vel[1]);
-    group_sync(c);
-    // ---------------- phase B1: callbacks (RSS) + broad phase -------------------------------
-    if (live) {
-      if (PED) stage_ped_state(c, e.present, etype, e.pose[0], e.pose[1], e.vel[0], e.vel[1],
-                               p.ped_distance_threshold, ox, oy);
-      if (RSS && feat_rss) {  // RSSDistances.__call__, callback.py:57-122
-        rss_last = SG_RSS_NONE;
-        if (t != 0.0 && s != ego_slot && e.present && c.egop[EGO_PRESENT] != 0.0) {
-          double ro[4];
-          rss_last = (uint8_t)rss_hazard(KR, c, e.pose[0], e.pose[1], e.vel[0], e.vel[1], rss_state, ro, 1);
-          sd[0] = ro[0]; sd[1] = ro[1]; ratio[0] = ro[2]; ratio[1] = ro[3];
-          const int found = (rss_state >> 2) & 3;  // RSS metric latch, rss.py:71-103
-          if (found) atomicOr(&c.acc[parity * ACC_N + ACC_RSS], found == 2 ? 1 : 2);
-        }
-      }
-      if (need_coll && e.present && !use_grid) broad_phase(c, parity);
-    }
-    if (PED && use_grid) {  // bin the new positions: this tick's broad phase and the next tick's sensors
-      gpos = grid_build(c, live && e.present, need_coll, e.pose[0], e.pose[1], ox, oy, grid_cs, grid_inv_cs);
-      if (need_coll && live && e.present) broad_phase_grid(c, parity, gpos);
-    }
-    group_sync(c);
-    done = finish_tick<false>(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick, t, dt, length, live,
-                       live && e.present, collided, e.vel[0], e.vel[1], e.vel[2], e.dist);
-    parity ^= 1;
-  }
-
-  // ---------------- write the State rows back ----------------------------------------------
-  if (live) {
-#pragma unroll
-    for (int f = 0; f < 6; ++f) { st.pose[f * nm + i] = e.pose[f]; st.vel[f * nm + i] = e.vel[f]; }
-    st.dist[i] = e.dist;
-    st.speed[i] = e.speed;
-    st.present[i] = e.present;
-    st.cur_own[i] = cur_own;
-    st.collided[i] = collided;
-    if (PED) { st.goal_idx[i] = goal; st.force[i] = force[0]; st.force[nm + i] = force[1]; }
-    if (RSS) {
-      st.rss_state[i] = rss_state; st.rss_last[i] = rss_last;
-      st.safe_dist[i] = sd[0]; st.safe_dist[nm + i] = sd[1];
-      st.safe_ratio[i] = ratio[0]; st.safe_ratio[nm + i] = ratio[1];
-    }
-  }
-  if (s == 0) {
-    st.t[n] = t; st.prev_t[n] = prev_t; st.tick[n] = tick; st.done[n] = done; st.cur_union[n] = cur_union;
-  }
-  store_cold(st, c, n, s, W, ego_slot);
-}
-
-// State.reset(t0) + Agent/Metric/StateCallback resets (reference state/state.py:106-143,
-// controller.py:100-103, metrics/trajectory.py:13-18, metrics/rss/callback.py:44-55)
-template <bool RSS, int MAXT>
-__global__ void __launch_bounds__(MAXT, MAXT >= 1024 ? 1 : 2)
-sg_reset_kernel(SgScene sc, SgParams p, SgState st, GroupLayout L) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int G = L.G, M = sc.n_slots, W = L.W;
-  const int gpb = blockDim.x / G;
-  const int gl = threadIdx.x / G;
-  const int s = threadIdx.x - gl * G;
-  const int n = blockIdx.x * gpb + gl;
-  if (gl >= gpb || n >= sc.n_scenarios) return;
-  Grp c;
-  setup_group(c, sc, L, smem, gl, s, n);
-  c.sorted = 0;  // no broad phase at reset
-  const bool live = s < M;
-  const int64_t i = c.i, nm = c.nm;
-  const int kind = live ? sc.kind[i] : SG_KIND_EMPTY;
-  const int ego_slot = sc.ego_slot[n];
-  const double t = sc.t0[n];
-  double pose[6] = {0, 0, 0, 0, 0, 0}, vel[6] = {0, 0, 0, 0, 0, 0};
-  double speed = 0;
-  int orient_hint = 0;
-  bool present = false;
-  if (kind != SG_KIND_EMPTY) {
-    const double bw = sc.box[i], bl = sc.box[nm + i];
-    c.boxp[s] = bw; c.boxp[G + s] = bl;
-    c.boxp[2 * G + s] = sc.box[2 * nm + i]; c.boxp[3 * G + s] = sc.box[3 * nm + i];
-    orient_hint = box_orientation_hint(bw, bl);
-    const int64_t r0 = sc.traj_off[i];
-    const int K = (int)(sc.traj_off[i + 1] - r0);
-    const double* rows = sc.traj_rows + r0 * 7;
-    const int mode = (K == 1) ? EXT_TRUE : (p.persist ? EXT_CLAMP : EXT_NONE);  // :123-129
-    int cur = 0;
-    present = position_at_t(rows, K, t, mode, cur, pose);
-    if (present) velocity_at_t(rows, K, t, vel);  // :132
-    else {
-#pragma unroll
-      for (int f = 0; f < 6; ++f) pose[f] = 0.0;
-    }
-    if (kind == SG_KIND_VEHICLE || kind == SG_KIND_PID) speed = norm2(vel[0], vel[1]);  // controller.py:100-103
-  }
-  uint8_t rss_state = 0, rss_last = SG_RSS_NONE;
-  double sd[2] = {0.0, 0.0}, ratio[2] = {INFINITY, INFINITY};  // callback.py:51-55
-  int rss_flags = 0;
-  const bool feat_rss = RSS && (p.features & SG_FEAT_RSS);
-  if (RSS && feat_rss) {  // update_callbacks() at reset, state.py:137-139
-    const RssConst KR = make_rss_const(p);
-    double ox, oy;
-    {
-      const int64_t er = sc.traj_off[(int64_t)n * M + ego_slot];
-      ox = __ldg(sc.traj_rows + er * 7 + 1);
-      oy = __ldg(sc.traj_rows + er * 7 + 2);
-    }
-    if (s == 0) c.acc[ACC_RSS] = 0;
-    if (s == ego_slot) publish_ego_box(c);
-    double hs = 0, hc = 1;
-    if (live && present) sincos(pose[3], &hs, &hc);
-    if (live) publish_box<RSS>(c, present, pose[0], pose[1], hc, hs, orient_hint, ox, oy);
-    if (s == ego_slot) publish_ego(c, present, pose[0], pose[1], hc, hs, vel[0], vel[1]);
-    group_sync(c);
-    if (live && t != 0.0 && s != ego_slot && present && c.egop[EGO_PRESENT] != 0.0) {
-      double ro[4];
-      rss_last = (uint8_t)rss_hazard(KR, c, pose[0], pose[1], vel[0], vel[1], rss_state, ro, 1);
-      sd[0] = ro[0]; sd[1] = ro[1]; ratio[0] = ro[2]; ratio[1] = ro[3];
-      const int found = (rss_state >> 2) & 3;
-      if (found) atomicOr(&c.acc[ACC_RSS], found == 2 ? 1 : 2);
-    }
-    group_sync(c);
-    rss_flags = c.acc[ACC_RSS];
-  }
-  if (live) {
-#pragma unroll
-    for (int f = 0; f < 6; ++f) { st.pose[f * nm + i] = pose[f]; st.vel[f * nm + i] = vel[f]; }
-    st.dist[i] = 0.0;
-    st.speed[i] = speed;
-    st.present[i] = present;
-    st.cur_own[i] = 1;
-    st.collided[i] = 0;
-    st.goal_idx[i] = 0;
-    st.force[i] = 0.0; st.force[nm + i] = 0.0;
-    st.pid_err[i] = 0.0; st.pid_err[nm + i] = 0.0; st.pid_err[2 * nm + i] = 0.0;  // controller.py:198-203
-    st.rss_state[i] = rss_state; st.rss_last[i] = rss_last;
-    st.safe_dist[i] = sd[0]; st.safe_dist[nm + i] = sd[1];
-    st.safe_ratio[i] = ratio[0]; st.safe_ratio[nm + i] = ratio[1];
-    if (st.trace_cap > 0) {
-      st.trace_present[i] = present;
-#pragma unroll
-      for (int f = 0; f < 6; ++f) st.trace_pose[f * nm + i] = pose[f];
-    }
-  }
-  if (s == ego_slot) {  // Metric.reset, metrics/trajectory.py:13-18, 33-37
-    const double sp = norm3(vel[0], vel[1], vel[2]);
-    st.ego_avg_speed[n] = sp; st.ego_avg_t[n] = 0.0; st.ego_max_speed[n] = sp; st.ego_dist[n] = 0.0;
-  }
-  if (s == 0) {
-    st.t[n] = t; st.prev_t[n] = t - 0.1;  // state.py:135
-    st.tick[n] = 0; st.done[n] = 0; st.cur_union[n] = 1;
-    st.first_coll_tick[n] = -1; st.first_coll_pair[2 * n] = -1; st.first_coll_pair[2 * n + 1] = -1;
-    st.n_pair_ticks[n] = 0;
-    st.rss_flags[n] = (uint8_t)rss_flags;
-    if (st.trace_cap > 0) st.trace_t[n] = t;
-  }
-  if (s < W) st.ego_hits[(int64_t)n * W + s] = 0;
-}
-
-// ---------------------------------------------------------------------------------
-__global__ void sg_box_pairs_kernel(const double* pa, const double* ba, const double* pb,
-                                    const double* bb, uint8_t* out, int64_t n) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double qa[8], qb[8];
-  box_points(pa[3 * i], pa[3 * i + 1], pa[3 * i + 2], ba[4 * i], ba[4 * i + 1], ba[4 * i + 2], ba[4 * i + 3], qa);
-  box_points(pb[3 * i], pb[3 * i + 1], pb[3 * i + 2], bb[4 * i], bb[4 * i + 1], bb[4 * i + 2], bb[4 * i + 3], qb);
-  bool same = true;
-  for (int f = 0; f < 8; ++f) same = same && (qa[f] == qb[f]);
-  const Quad A = quad_from_array(qa), B = quad_from_array(qb);
-  out[i] = !same && quads_intersect(A, quad_orientation(A), B, quad_orientation(B));
-}
-
-#include "sg_replay.cuh"
-
-// ---------------------------------------------------------------------------------
-// FutureCollisionDetector._step (reference sensor/common.py:88-105) for a batch: one warp per
-// scenario; its lanes share the (look-ahead sample, other entity) pairs.  Every entity is placed
-// at trajectory.position_at_t(time) (clamped), present or not; the pair test is the exact
-// closed-set predicate of the collision path.
-__global__ void sg_future_kernel(SgScene sc, const double* __restrict__ t, const int32_t* __restrict__ slot,
-                                 double horizon, int n_samples, uint8_t* __restrict__ out) {
-  const int n = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (n >= sc.n_scenarios) return;
-  const int M = sc.n_slots;
-  const int64_t nm = (int64_t)sc.n_scenarios * M;
-  const int es = slot ? slot[n] : sc.ego_slot[n];
-  const int64_t ie = (int64_t)n * M + es;
-  const int64_t re0 = sc.traj_off[ie];
-  const int Ke = (int)(sc.traj_off[ie + 1] - re0);
-  const double start = t[n], stop = t[n] + horizon;
-  const double step = n_samples > 1 ? (stop - start) / (double)(n_samples - 1) : 0.0;  // numpy.linspace
-  bool hit = false;
-  if (Ke > 0)
-    for (int w = lane; w < n_samples * M; w += 32) {
-      const int k = w / M, j = w - k * M;
-      const int64_t i = (int64_t)n * M + j;
-      if (j == es || sc.kind[i] == SG_KIND_EMPTY) continue;
-      const int64_t r0 = sc.traj_off[i];
-      const int K = (int)(sc.traj_off[i + 1] - r0);
-      if (K == 0) continue;
-      double tk = (double)k * step + start;
-      if (n_samples > 1 && k == n_samples - 1) tk = stop;
-      double pe[6], po[6], qe[8], qo[8];
-      int c0 = 0, c1 = 0;
-      position_at_t(sc.traj_rows + re0 * 7, Ke, tk, EXT_CLAMP, c0, pe);
-      position_at_t(sc.traj_rows + r0 * 7, K, tk, EXT_CLAMP, c1, po);
-      box_points(pe[0], pe[1], pe[3], sc.box[ie], sc.box[nm + ie], sc.box[2 * nm + ie], sc.box[3 * nm + ie], qe);
-      box_points(po[0], po[1], po[3], sc.box[i], sc.box[nm + i], sc.box[2 * nm + i], sc.box[3 * nm + i], qo);
-      bool same = true;
-#pragma unroll
-      for (int f = 0; f < 8; ++f) same = same && (qe[f] == qo[f]);
-      if (same) continue;  // `g != g_prime`, reference utils.py:58
-      const Quad A = quad_from_array(qe), B = quad_from_array(qo);
-      if (quads_intersect(A, quad_orientation(A), B, quad_orientation(B))) hit = true;
-    }
-  hit = __any_sync(0xffffffffu, hit);
-  if (lane == 0) out[n] = hit ? 1 : 0;
-}
-
-// ---------------------------------------------------------------------------------
-static bool g_ngon_ready[64] = {false};
-
-static int ensure_constants(int device) {
-  if (device < 0 || device >= 64) return set_msg("device index out of range");
-  if (g_ngon_ready[device]) return 0;
-  double cs[64][2];
-  const double inc = (2.0 * M_PI) / 64;
-  for (int k = 0; k < 64; ++k) {  // GEOS addDirectedFillet: clockwise from angle 0 (libm on the host)
-    const double ang = 0.0 + -1.0 * k * inc;
-    cs[k][0] = cos(ang);
-    cs[k][1] = sin(ang);
-  }
-  cudaError_t err = cudaMemcpyToSymbol(c_ngon, cs, sizeof(cs));
-  if (err != cudaSuccess) return set_err("cudaMemcpyToSymbol", err);
-  g_ngon_ready[device] = true;
-  return 0;
-}
-
-template <bool RSS>
-static cudaError_t launch_reset(bool big, int blocks, int threads, size_t smem, cudaStream_t s,
-                                const SgScene& sc, const SgParams& p, const SgState& st,
-                                const GroupLayout& L) {
-  auto kern = big ? sg_reset_kernel<RSS, 1024> : sg_reset_kernel<RSS, SG_THREADS>;
-  if (smem > 48 * 1024) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-  }
-  kern<<<blocks, threads, smem, s>>>(sc, p, st, L);
-  return cudaGetLastError();
-}
-
-template <bool PED, bool RSS>
-static cudaError_t launch_rollout(bool big, int blocks, int threads, size_t smem, cudaStream_t s,
-                                  const SgScene& sc, const SgParams& p, const SgState& st,
-                                  const SgInputs& in, int n_ticks, const GroupLayout& L) {
-  auto kern = big ? sg_rollout_kernel<PED, RSS, 1024> : sg_rollout_kernel<PED, RSS, SG_THREADS>;
-  if (smem > 48 * 1024) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-  }
-  kern<<<blocks, threads, smem, s>>>(sc, p, st, in, n_ticks, L);
-  return cudaGetLastError();
-}
-
-template <bool RSS>
-static cudaError_t launch_vehicle(int n_scen, cudaStream_t s, const SgScene& sc, const SgParams& p,
-                                  const SgState& st, const SgInputs& in, int n_ticks,
-                                  const GroupLayout& L) {
-  void (*kern)(SgScene, SgParams, SgState, SgInputs, int, GroupLayout);
-  int threads;
-  const bool need_coll = (p.features & SG_FEAT_COLLISIONS) ||
-                         (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
-  // lean: collisions on, no trace, no pair matrix - those code paths are compiled out
-  const bool lean = need_coll && st.trace_cap <= 0 && !(p.features & SG_FEAT_COLL_MATRIX);
-#define SG_VEH_PICK(T, B, S) (lean ? sg_vehicle_kernel<RSS, T, B, S, true> : sg_vehicle_kernel<RSS, T, B, S, false>)
-  // (the sorted sweep is a compile-time variant too: scenes of up to 128 slots carry none of its code)
-  if (L.G <= SG_VEH_THREADS) { kern = SG_VEH_PICK(SG_VEH_THREADS, SG_VEH_MINB, false); threads = SG_VEH_THREADS; }
-  else if (L.G <= SG_THREADS) { kern = L.sorted ? SG_VEH_PICK(SG_THREADS, 2, true) : SG_VEH_PICK(SG_THREADS, 2, false); threads = SG_THREADS; }
-  else { kern = L.sorted ? SG_VEH_PICK(1024, 1, true) : SG_VEH_PICK(1024, 1, false); threads = L.G; }
-#undef SG_VEH_PICK
-  const int gpb = threads / L.G;
-  const int blocks = (n_scen + gpb - 1) / gpb;
-  const size_t smem = (size_t)gpb * L.bytes;
-  if (smem > 48 * 1024) {
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-  }
-  kern<<<blocks, threads, smem, s>>>(sc, p, st, in, n_ticks, L);
-  return cudaGetLastError();
-}
-
-static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInputs* in, int n_ticks,
-                  int device, void* stream, int reset) {
-  if (!sc || !p || !st) return set_msg("null argument");
-  if (sc->n_slots < 1 || sc->n_slots > 1024) return set_msg("n_slots must be in 1..1024");
-  if (sc->n_scenarios < 1) return set_msg("n_scenarios must be >= 1");
-  cudaError_t err = cudaSetDevice(device);
-  if (err != cudaSuccess) return set_err("cudaSetDevice", err);
-  int rc = ensure_constants(device);
-  if (rc) return rc;
-  const bool ped = sc->route_off != nullptr && sc->n_route_pts > 0;
-  const bool rss = (p->features & SG_FEAT_RSS) != 0;
-  const uint32_t veh_bits = (1u << SG_KIND_VEHICLE), ok_bits = veh_bits | (1u << SG_KIND_EMPTY);
-  const bool veh_only = (sc->kind_mask & veh_bits) && !(sc->kind_mask & ~ok_bits);
-  const bool grid_ok = ped && p->ped_distance_threshold > 0.0 && p->ped_distance_threshold < 1.0e6 &&
-                       !(p->features & SG_FEAT_NO_GRID);
-  GroupLayout L = make_layout(sc->n_slots, ped, rss, veh_only, grid_ok);
-  if (L.grid && (size_t)L.bytes > 227 * 1024) L = make_layout(sc->n_slots, ped, rss, veh_only, false);
-  const int threads = L.G <= SG_THREADS ? SG_THREADS : L.G;
-  const bool big = threads > SG_THREADS;
-  const int gpb = threads / L.G;
-  const int blocks = (sc->n_scenarios + gpb - 1) / gpb;
-  const size_t smem = (size_t)gpb * L.bytes;
-  if (smem > 227 * 1024) return set_msg("scenario does not fit in shared memory");
-  cudaStream_t s = (cudaStream_t)stream;
-  if (reset) {
-    err = rss ? launch_reset<true>(big, blocks, threads, smem, s, *sc, *p, *st, L)
-              : launch_reset<false>(big, blocks, threads, smem, s, *sc, *p, *st, L);
-    if (err != cudaSuccess) return set_err("sg_reset_kernel launch", err);
-    return 0;
-  }
-  SgInputs none;
-  memset(&none, 0, sizeof(none));
-  const SgInputs inp = in ? *in : none;
-  // replay-only scenes (every slot a BatchReplayEntity or ReplayTrajectoryAgent) rolled out for
-  // several ticks: the tick-parallel kernel (sg_replay.cuh)
-  const uint32_t replay_bits = (1u << SG_KIND_EMPTY) | (1u << SG_KIND_REPLAY) | (1u << SG_KIND_AGENT_REPLAY);
-  const bool replay_only = sc->kind_mask != 0 && !(sc->kind_mask & ~replay_bits) &&
-                           (sc->kind_mask & ~(1u << SG_KIND_EMPTY));
-  if (replay_only && !rss && !ped && sc->n_slots <= 32 && st->trace_cap == 0 && !inp.step_done &&
-      !inp.actions && !inp.host_present && p->timestep > 0.0 && (n_ticks < 0 || n_ticks >= 8) &&
-      !(p->features & SG_FEAT_SEQUENTIAL)) {
-    const size_t rsm = replay_smem_bytes(sc->n_slots);
-    auto rk = (p->features & SG_FEAT_COLL_MATRIX) ? sg_replay_kernel<true> : sg_replay_kernel<false>;
-    if (rsm > 48 * 1024) {
-      err = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
-      if (err != cudaSuccess) return set_err("cudaFuncSetAttribute", err);
-    }
-    rk<<<sc->n_scenarios, SG_RP_BLOCK, rsm, s>>>(*sc, *p, *st, n_ticks);
-    err = cudaGetLastError();
-    if (err != cudaSuccess) return set_err("sg_replay_kernel launch", err);
-    return 0;
-  }
-  if (veh_only) {
-    if (!inp.actions) return set_msg("vehicle scene needs an action table");
-    err = rss ? launch_vehicle<true>(sc->n_scenarios, s, *sc, *p, *st, inp, n_ticks, L)
-              : launch_vehicle<false>(sc->n_scenarios, s, *sc, *p, *st, inp, n_ticks, L);
-  } else if (ped && rss) err = launch_rollout<true, true>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
-  else if (ped) err = launch_rollout<true, false>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
-  else if (rss) err = launch_rollout<false, true>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
-  else err = launch_rollout<false, false>(big, blocks, threads, smem, s, *sc, *p, *st, inp, n_ticks, L);
-  if (err != cudaSuccess) return set_err("sg_rollout_kernel launch", err);
-  return 0;
-}
-
-extern "C" {
-
-int sg_abi_version(void) { return SG_ABI_VERSION; }
-
-int64_t sg_sizeof(int which) {
-  switch (which) {
-    case 0: return sizeof(SgParams);
-    case 1: return sizeof(SgScene);
-    case 2: return sizeof(SgState);
-    case 3: return sizeof(SgInputs);
-    case 4: return sizeof(SgEvent);
-  }
-  return -1;
-}
-
-const char* sg_last_error(void) { return g_err; }
-
-void sg_default_params(SgParams* p) {
-  memset(p, 0, sizeof(*p));
-  p->timestep = 1.0 / 30.0;
-  p->terminal = SG_TERM_MAX_LENGTH;
-  p->features = SG_FEAT_COLLISIONS | SG_FEAT_EGO_METRICS;
-  p->max_ticks = 1 << 20;
-  p->veh_max_steer = 0.7;
-  p->veh_max_accel = 5.0;
-  p->veh_max_speed = NAN;
-  p->ped_max_speed = 5.0;
-  p->ped_distance_threshold = 1.0;
-  p->sf_max_speed_factor = 1.3;
-  p->sf_sight_weight = 0.5;
-  p->sf_sight_weight_use = 1;
-  p->sf_sight_angle = 200.0;
-  p->sf_relaxation_time = 1.5;
-  p->sf_ped_repulse_V = 1.0;
-  p->sf_ped_repulse_sigma = 1.0;
-  p->rss_response_time = 0.6;
-  p->rss_min_long_accel = 1.2 * 9.81;
-  p->rss_max_long_accel = 1.2 * 9.81;
-  p->rss_min_safe_clearance = 0.1;
-  p->pid_steer_Kp = 0.03054;
-  p->pid_steer_Kd = 1.5709;
-  p->pid_accel_Kp = 0.3753;
-  p->pid_accel_Kd = 1.8970;
-  p->pid_accel_Ki = 0.0204;
-}
-
-int sg_reset(const SgScene* scene, const SgParams* params, SgState* state, int device, void* stream) {
-  if (state && state->event_count) {
-    cudaError_t err = cudaSetDevice(device);
-    if (err != cudaSuccess) return set_err("cudaSetDevice", err);
-    err = cudaMemsetAsync(state->event_count, 0, sizeof(int32_t), (cudaStream_t)stream);
-    if (err != cudaSuccess) return set_err("cudaMemsetAsync", err);
-  }
-  return launch(scene, params, state, nullptr, 0, device, stream, 1);
-}
-
-int sg_rollout(const SgScene* scene, const SgParams* params, SgState* state, const SgInputs* inputs,
-               int n_ticks, int device, void* stream) {
-  return launch(scene, params, state, inputs, n_ticks, device, stream, 0);
-}
-
-int sg_test_box_pairs(const double* pose_a, const double* box_a, const double* pose_b,
-                      const double* box_b, uint8_t* out, int64_t n, int device, void* stream) {
-  cudaError_t err = cudaSetDevice(device);
-  if (err != cudaSuccess) return set_err("cudaSetDevice", err);
-  if (n <= 0) return 0;
-  sg_box_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      pose_a, box_a, pose_b, box_b, out, n);
-  err = cudaGetLastError();
-  if (err != cudaSuccess) return set_err("sg_box_pairs_kernel launch", err);
-  return 0;
-}
-
-int sg_future_collisions(const SgScene* scene, const double* t, const int32_t* slot, double horizon,
-                         int n_samples, uint8_t* out, int device, void* stream) {
-  if (!scene || !t || !out) return set_msg("null argument");
-  if (n_samples < 1) return set_msg("n_samples must be >= 1");
-  cudaError_t err = cudaSetDevice(device);
-  if (err != cudaSuccess) return set_err("cudaSetDevice", err);
-  const int64_t threads = (int64_t)scene->n_scenarios * 32;
-  sg_future_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      *scene, t, slot, horizon, n_samples, out);
-  err = cudaGetLastError();
-  if (err != cudaSuccess) return set_err("sg_future_kernel launch", err);
-  return 0;
-}
-
-// ---- host-buffer path ------------------------------------------------------------------
-struct CopyItem { const void* src; void* dst; size_t bytes; };
-
-static int scene_copy_list(const SgScene* h, const SgScene* d, CopyItem* items) {
-  const int64_t N = h->n_scenarios, M = h->n_slots, NM = N * M;
-  int k = 0;
-#define ITEM(field, bytes_) items[k++] = CopyItem{h->field, (void*)d->field, (size_t)(bytes_)}
-  ITEM(kind, NM);
-  ITEM(etype, NM);
-  ITEM(box, 4 * NM * 8);
-  ITEM(traj_off, (NM + 1) * 8);
-  ITEM(traj_rows, h->n_traj_rows * 7 * 8);
-  ITEM(union_off, (N + 1) * 8);
-  ITEM(union_t, h->n_union_rows * 8);
-  ITEM(union_x, h->n_union_rows * 6 * M * 8);
-  ITEM(t0, N * 8);
-  ITEM(length, N * 8);
-  ITEM(ego_slot, N * 4);
-  ITEM(first_slot, N * 4);
-  ITEM(ped_speed_desired, NM * 8);
-  ITEM(route_off, (NM + 1) * 8);
-  ITEM(route_xy, h->n_route_pts * 2 * 8);
-#undef ITEM
-  return k;
-}
-
-int64_t sg_host_h2d_bytes(const SgScene* h, const SgInputs* in, int copy_static) {
-  CopyItem items[16];
-  SgScene dummy = *h;
-  int k = scene_copy_list(h, &dummy, items);
-  int64_t total = 0;
-  if (copy_static)
-    for (int q = 0; q < k; ++q)
-      if (items[q].src) total += (int64_t)items[q].bytes;
-  if (in && in->actions) total += (int64_t)in->n_action_ticks * 2 * h->n_scenarios * h->n_slots * 8;
-  return total;
-}
-
-int64_t sg_host_d2h_bytes(const SgScene* h) {
-  const int64_t N = h->n_scenarios;
-  return N * (8 * 3 + 4 + 8 + 8 + 1 + 4 + 8) + 4;
-}
-
-int sg_rollout_host(const SgScene* hs, const SgScene* ds, const SgParams* params, SgState* dst,
-                    const SgInputs* hin, const SgInputs* din, SgHostResults* res, int copy_static,
-                    int device, void* stream) {
-  if (!hs || !ds || !params || !dst || !res) return set_msg("null argument");
-  cudaError_t err = cudaSetDevice(device);
-  if (err != cudaSuccess) return set_err("cudaSetDevice", err);
-  cudaStream_t s = (cudaStream_t)stream;
-  if (copy_static) {
-    CopyItem items[16];
-    const int k = scene_copy_list(hs, ds, items);
-    for (int q = 0; q < k; ++q) {
-      if (!items[q].src || !items[q].bytes) continue;
-      if (!items[q].dst) return set_msg("device scene mirror is missing an array");
-      err = cudaMemcpyAsync(items[q].dst, items[q].src, items[q].bytes, cudaMemcpyHostToDevice, s);
-      if (err != cudaSuccess) return set_err("cudaMemcpyAsync H2D scene", err);
-    }
-  }
-  int rc = sg_reset(ds, params, dst, device, stream);
-  if (rc) return rc;
-  const int64_t NM = (int64_t)hs->n_scenarios * hs->n_slots;
-  if (hin && hin->actions) {
-    if (!din || !din->actions) return set_msg("device action buffer missing");
-    // stream the action table in chunks of ticks: the copy of chunk c+1 overlaps the kernel
-    // of chunk c (copies on a second stream, ordered with events)
-    const int T = hin->n_action_ticks;
-    const int chunk = T < 16 ? T : 16;
-    static thread_local cudaStream_t copy_stream = nullptr;
-    static thread_local cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done = nullptr;
-    if (!copy_stream) {
-      cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
-      cudaEventCreateWithFlags(&ev_copy[0], cudaEventDisableTiming);
-      cudaEventCreateWithFlags(&ev_copy[1], cudaEventDisableTiming);
-      cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming);
-    }
-    cudaEventRecord(ev_done, s);
-    cudaStreamWaitEvent(copy_stream, ev_done, 0);
-    int c = 0;
-    for (int k0 = 0; k0 < T; k0 += chunk, ++c) {
-      const int kt = (T - k0) < chunk ? (T - k0) : chunk;
-      const size_t off = (size_t)k0 * 2 * NM;
-      err = cudaMemcpyAsync((double*)din->actions + off, hin->actions + off,
-                            (size_t)kt * 2 * NM * 8, cudaMemcpyHostToDevice, copy_stream);
-      if (err != cudaSuccess) return set_err("cudaMemcpyAsync H2D actions", err);
-      cudaEventRecord(ev_copy[c & 1], copy_stream);
-      cudaStreamWaitEvent(s, ev_copy[c & 1], 0);
-      SgInputs part = *din;
-      part.actions = din->actions + off;
-      part.n_action_ticks = kt;
-      rc = sg_rollout(ds, params, dst, &part, kt, device, stream);
-      if (rc) return rc;
-    }
-  } else {
-    rc = sg_rollout(ds, params, dst, din, -1, device, stream);
-    if (rc) return rc;
-  }
-  const int64_t N = hs->n_scenarios;
-#define BACK(field, bytes_)                                                                   \
-  if (res->field) {                                                                           \
-    err = cudaMemcpyAsync(res->field, dst->field, (size_t)(bytes_), cudaMemcpyDeviceToHost, s); \
-    if (err != cudaSuccess) return set_err("cudaMemcpyAsync D2H " #field, err);               \
-  }
-  BACK(ego_avg_speed, N * 8);
-  BACK(ego_max_speed, N * 8);
-  BACK(ego_dist, N * 8);
-  BACK(first_coll_tick, N * 4);
-  BACK(first_coll_pair, N * 8);
-  BACK(n_pair_ticks, N * 8);
-  BACK(rss_flags, N);
-  BACK(tick, N * 4);
-  BACK(t, N * 8);
-  BACK(event_count, 4);
-#undef BACK
-  return 0;
-}
-
-}  // extern "C"

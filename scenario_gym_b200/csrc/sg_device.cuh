@@ -106,7 +106,7 @@ SG_DEV void two_prod(double a, double b, double& p, double& e) {
   e = __fma_rn(a, b, -p);
 }
 
-__device__ __noinline__ int orient_exact(double ax, double ay, double bx, double by, double cx,
+static __device__ __noinline__ int orient_exact(double ax, double ay, double bx, double by, double cx,
                                          double cy) {
   double d[4][2];
   two_sum(ax, -cx, d[0][0], d[0][1]);
@@ -199,7 +199,7 @@ SG_DEV bool edge01_separates(const Quad& a, int o, const Quad& b) {
 
 // closed-set intersection of two convex quads (touching counts, as GEOS `intersects`):
 // disjoint iff some edge of either has all four corners of the other strictly outside
-__device__ __noinline__ bool quads_intersect(Quad a, int oa, Quad b, int ob) {
+static __device__ __noinline__ bool quads_intersect(Quad a, int oa, Quad b, int ob) {
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll 1
@@ -214,7 +214,7 @@ __device__ __noinline__ bool quads_intersect(Quad a, int oa, Quad b, int ob) {
 }
 
 // closed-set intersection of a convex quad and the segment (x0, y0)-(x1, y1)
-__device__ __noinline__ bool quad_intersects_segment(Quad q, int o, double x0, double y0, double x1,
+static __device__ __noinline__ bool quad_intersects_segment(Quad q, int o, double x0, double y0, double x1,
                                                      double y1) {
   int pos = 0, neg = 0;
 #pragma unroll 1

@@ -1,0 +1,114 @@
+// sg_misc.cu -- the tick-parallel replay kernel (sg_replay.cuh), the FutureCollisionDetector look-ahead
+// and the box-pair unit-test kernel.
+#include "sg_common.cuh"
+#include "sg_internal.h"
+
+// ---------------------------------------------------------------------------------
+__global__ void sg_box_pairs_kernel(const double* pa, const double* ba, const double* pb,
+                                    const double* bb, uint8_t* out, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double qa[8], qb[8];
+  box_points(pa[3 * i], pa[3 * i + 1], pa[3 * i + 2], ba[4 * i], ba[4 * i + 1], ba[4 * i + 2], ba[4 * i + 3], qa);
+  box_points(pb[3 * i], pb[3 * i + 1], pb[3 * i + 2], bb[4 * i], bb[4 * i + 1], bb[4 * i + 2], bb[4 * i + 3], qb);
+  bool same = true;
+  for (int f = 0; f < 8; ++f) same = same && (qa[f] == qb[f]);
+  const Quad A = quad_from_array(qa), B = quad_from_array(qb);
+  out[i] = !same && quads_intersect(A, quad_orientation(A), B, quad_orientation(B));
+}
+
+#include "sg_replay.cuh"
+
+// ---------------------------------------------------------------------------------
+// FutureCollisionDetector._step (reference sensor/common.py:88-105) for a batch: one warp per
+// scenario; its lanes share the (look-ahead sample, other entity) pairs.  Every entity is placed
+// at trajectory.position_at_t(time) (clamped), present or not; the pair test is the exact
+// closed-set predicate of the collision path.
+__global__ void sg_future_kernel(SgScene sc, const double* __restrict__ t, const int32_t* __restrict__ slot,
+                                 double horizon, int n_samples, uint8_t* __restrict__ out) {
+  const int n = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= sc.n_scenarios) return;
+  const int M = sc.n_slots;
+  const int64_t nm = (int64_t)sc.n_scenarios * M;
+  const int es = slot ? slot[n] : sc.ego_slot[n];
+  const int64_t ie = (int64_t)n * M + es;
+  const int64_t re0 = sc.traj_off[ie];
+  const int Ke = (int)(sc.traj_off[ie + 1] - re0);
+  const double start = t[n], stop = t[n] + horizon;
+  const double step = n_samples > 1 ? (stop - start) / (double)(n_samples - 1) : 0.0;  // numpy.linspace
+  bool hit = false;
+  if (Ke > 0)
+    for (int w = lane; w < n_samples * M; w += 32) {
+      const int k = w / M, j = w - k * M;
+      const int64_t i = (int64_t)n * M + j;
+      if (j == es || sc.kind[i] == SG_KIND_EMPTY) continue;
+      const int64_t r0 = sc.traj_off[i];
+      const int K = (int)(sc.traj_off[i + 1] - r0);
+      if (K == 0) continue;
+      double tk = (double)k * step + start;
+      if (n_samples > 1 && k == n_samples - 1) tk = stop;
+      double pe[6], po[6], qe[8], qo[8];
+      int c0 = 0, c1 = 0;
+      position_at_t(sc.traj_rows + re0 * 7, Ke, tk, EXT_CLAMP, c0, pe);
+      position_at_t(sc.traj_rows + r0 * 7, K, tk, EXT_CLAMP, c1, po);
+      box_points(pe[0], pe[1], pe[3], sc.box[ie], sc.box[nm + ie], sc.box[2 * nm + ie], sc.box[3 * nm + ie], qe);
+      box_points(po[0], po[1], po[3], sc.box[i], sc.box[nm + i], sc.box[2 * nm + i], sc.box[3 * nm + i], qo);
+      bool same = true;
+#pragma unroll
+      for (int f = 0; f < 8; ++f) same = same && (qe[f] == qo[f]);
+      if (same) continue;  // `g != g_prime`, reference utils.py:58
+      const Quad A = quad_from_array(qe), B = quad_from_array(qo);
+      if (quads_intersect(A, quad_orientation(A), B, quad_orientation(B))) hit = true;
+    }
+  hit = __any_sync(0xffffffffu, hit);
+  if (lane == 0) out[n] = hit ? 1 : 0;
+}
+
+// Rows of the action table an SgActionRng describes (sg_fill_random_actions): one thread per slot
+// index walks the ticks with one 128-bit multiply-add per draw; stores are coalesced over the slots.
+__global__ void sg_fill_actions_kernel(SgRngDev rng, int n_ticks, int64_t nm, double* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nm) return;
+  const sg_u128 A = sg_u128_make(rng.a_hi, rng.a_lo), C = sg_u128_make(rng.c_hi, rng.c_lo);
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    sg_u128 q = sg_rng_slot_state(rng, c, i);
+    for (int k = 0; k < n_ticks; ++k) {
+      const double u = sg_pcg_double((uint64_t)(q >> 64), (uint64_t)q);
+      out[((int64_t)k * 2 + c) * nm + i] = rng.low[c] + rng.scale[c] * u;
+      q = A * q + C;
+    }
+  }
+}
+
+cudaError_t sgi_launch_fill_actions(cudaStream_t s, const SgRngDev& rng, int n_ticks, int64_t nm, double* out) {
+  if (nm <= 0 || n_ticks <= 0) return cudaSuccess;
+  sg_fill_actions_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, s>>>(rng, n_ticks, nm, out);
+  return cudaGetLastError();
+}
+
+cudaError_t sgi_launch_replay(cudaStream_t s, const SgScene& sc, const SgParams& p, const SgState& st,
+                              int n_ticks) {
+  const size_t rsm = replay_smem_bytes(sc.n_slots);
+  auto rk = (p.features & SG_FEAT_COLL_MATRIX) ? sg_replay_kernel<true> : sg_replay_kernel<false>;
+  if (rsm > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm);
+    if (err != cudaSuccess) return err;
+  }
+  rk<<<sc.n_scenarios, SG_RP_BLOCK, rsm, s>>>(sc, p, st, n_ticks);
+  return cudaGetLastError();
+}
+
+cudaError_t sgi_launch_box_pairs(cudaStream_t s, const double* pa, const double* ba, const double* pb,
+                                 const double* bb, uint8_t* out, int64_t n) {
+  sg_box_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pa, ba, pb, bb, out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t sgi_launch_future(cudaStream_t s, const SgScene& sc, const double* t, const int32_t* slot,
+                              double horizon, int n_samples, uint8_t* out) {
+  const int64_t threads = (int64_t)sc.n_scenarios * 32;
+  sg_future_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(sc, t, slot, horizon, n_samples, out);
+  return cudaGetLastError();
+}

@@ -130,7 +130,7 @@ SG_DEV void rp_pose_and_prev(const SgScene& sc, const SgParams& p, const SgState
 }
 
 // State rows of slot s as they stand after the tick (tkm -> tk); rare (once per slot per launch)
-__device__ __noinline__ void rp_write_rows(const SgScene* sc, const SgParams* p, const SgState* st,
+static __device__ __noinline__ void rp_write_rows(const SgScene* sc, const SgParams* p, const SgState* st,
                                            RpCtx c, int s, bool agent_pres, double tk, double tkm,
                                            bool first) {
   const int64_t i = (int64_t)c.n * c.M + s, nm = (int64_t)sc->n_scenarios * c.M;
@@ -147,7 +147,7 @@ __device__ __noinline__ void rp_write_rows(const SgScene* sc, const SgParams* p,
 
 // fp64 corners of slot s at time tk (Entity.get_bounding_box_points, entity/base.py:100-138;
 // the same expression and libm call as publish_box) and the ring orientation
-__device__ __noinline__ Quad rp_corners(const SgScene* sc, RpCtx c, int s, double tk, int* orient) {
+static __device__ __noinline__ Quad rp_corners(const SgScene* sc, RpCtx c, int s, double tk, int* orient) {
   const int64_t i = (int64_t)c.n * c.M + s, nm = (int64_t)sc->n_scenarios * c.M;
   const RpSlot e = rp_slot(*sc, i);
   const RpUnion uk = rp_union_weights(c.ts, c.UK, tk);
@@ -170,7 +170,7 @@ __device__ __noinline__ Quad rp_corners(const SgScene* sc, RpCtx c, int s, doubl
 }
 
 // exact narrow phase of one AABB-surviving pair at time tk (state/utils.py:10-49, utils.py:28-62)
-__device__ __noinline__ bool rp_pair_exact(const SgScene* sc, RpCtx c, int a, int b, double tk) {
+static __device__ __noinline__ bool rp_pair_exact(const SgScene* sc, RpCtx c, int a, int b, double tk) {
   int oa, ob;
   const Quad A = rp_corners(sc, c, a, tk, &oa), B = rp_corners(sc, c, b, tk, &ob);
   const bool same = A.x0 == B.x0 && A.y0 == B.y0 && A.x1 == B.x1 && A.y1 == B.y1 && A.x2 == B.x2 &&
@@ -180,13 +180,13 @@ __device__ __noinline__ bool rp_pair_exact(const SgScene* sc, RpCtx c, int a, in
 }
 
 // out-of-line so that the tick loop carries one copy of the control-point search
-__device__ __noinline__ double4 rp_agent_pose4(const double* rows, int K, double t, int mode) {
+static __device__ __noinline__ double4 rp_agent_pose4(const double* rows, int K, double t, int mode) {
   int cur = 0;
   double full[6];
   position_at_t(rows, K, t, mode, cur, full);
   return make_double4(full[0], full[1], full[2], full[3]);
 }
-__device__ __noinline__ RpUnion rp_union_weights_ool(const double* ts, int UK, double t) {
+static __device__ __noinline__ RpUnion rp_union_weights_ool(const double* ts, int UK, double t) {
   return rp_union_weights(ts, UK, t);
 }
 

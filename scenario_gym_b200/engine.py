@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import abi
+from .action_rng import ActionRng
 from .packing import PackedScene
 
 EVENT_DTYPE = np.dtype(
@@ -35,7 +36,7 @@ class Engine:
     """N scenarios x M slots resident on one GPU."""
 
     def __init__(self, scene: PackedScene, params: Optional[abi.SgParams] = None,
-                 device: Union[int, str, torch.device] = 0, event_cap: int = 1 << 16,
+                 device: Union[int, str, torch.device] = 0, event_cap: int = 1 << 20,
                  trace_cap: int = 0, coll_matrix: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("scenario_gym_b200 needs a CUDA device (no CPU fallback)")
@@ -105,35 +106,76 @@ class Engine:
                                       self.dev_index, self._stream()))
 
     def set_actions(self, actions) -> torch.Tensor:
-        """Upload a (T, 2, N*M) VehicleAction table (accel, steer) and keep it resident."""
+        """Upload a (T, 2, N*M) VehicleAction table (accel, steer; fp64 or fp32) and keep it resident."""
         if isinstance(actions, np.ndarray):
-            actions = torch.from_numpy(np.ascontiguousarray(actions, np.float64))
-        actions = actions.to(self.device, dtype=torch.float64).contiguous()
+            if actions.dtype != np.float32:
+                actions = np.ascontiguousarray(actions, np.float64)
+            actions = torch.from_numpy(np.ascontiguousarray(actions))
+        if actions.dtype != torch.float32:
+            actions = actions.to(dtype=torch.float64)
+        actions = actions.to(self.device).contiguous()
         if actions.dim() != 3 or tuple(actions.shape[1:]) != (2, self.N * self.M):
             raise ValueError(f"actions must be (T, 2, {self.N * self.M}), got {tuple(actions.shape)}")
         self._actions_t = actions
         return actions
 
+    def fill_actions(self, rng: ActionRng, tick0: int = 0, n_ticks: Optional[int] = None) -> torch.Tensor:
+        """Rows [tick0, tick0 + n_ticks) of the table `rng` describes, drawn on the device (fp64)."""
+        n_ticks = rng.n_ticks - tick0 if n_ticks is None else n_ticks
+        if rng.nm != self.N * self.M:
+            raise ValueError(f"ActionRng describes {rng.nm} slots, the engine has {self.N * self.M}")
+        out = torch.empty((max(n_ticks, 0), 2, rng.nm), dtype=torch.float64, device=self.device)
+        r = rng.struct()
+        self._check(self.lib["fill_random_actions"](C.byref(r), int(tick0), int(n_ticks), int(rng.nm),
+                                                    out.data_ptr(), self.dev_index, self._stream()))
+        return out
+
+    def _wants_f64_table(self) -> bool:
+        """Vehicle-only scenes rolled out with a trace / pair matrix take an fp64 table (sg_api.cu)."""
+        mask = self._sc.kind_mask
+        veh_only = bool(mask & (1 << abi.KIND_VEHICLE)) and not (
+            mask & ~((1 << abi.KIND_VEHICLE) | (1 << abi.KIND_EMPTY)))
+        f, term = self.params.features, self.params.terminal
+        need_coll = bool(f & abi.FEAT_COLLISIONS) or bool(term & (abi.TERM_COLLISION | abi.TERM_EGO_COLLISION))
+        lean = need_coll and self.trace_cap <= 0 and not (f & abi.FEAT_COLL_MATRIX)
+        return veh_only and not lean
+
     def rollout(self, n_ticks: int = -1, actions=None, tick0: int = 0, host_pose=None,
                 host_present=None, step_done: bool = False) -> None:
         """
         ``n_ticks`` x ScenarioGym.step() fused on the device; ``n_ticks < 0`` runs every
-        scenario to ``is_done`` (ScenarioGym.rollout).  ``actions`` (T, 2, N*M) is consumed
-        from row ``tick0``.
+        scenario to ``is_done`` (ScenarioGym.rollout).  ``actions``: a (T, 2, N*M) table (fp64 or
+        fp32), consumed from row ``tick0``, or an ``ActionRng`` (the rows are then drawn inside the
+        kernel from numpy's PCG64 stream; nothing is uploaded).
         """
         inp = abi.SgInputs()
         inp.step_done = int(step_done)
         keep = []
-        if actions is not None:
+        if isinstance(actions, ActionRng) and self._wants_f64_table():
+            rows = actions.n_ticks - tick0 if n_ticks < 0 else min(n_ticks, actions.n_ticks - tick0)
+            actions, tick0 = self.fill_actions(actions, tick0, rows), 0
+            self._actions_t = actions
+        if isinstance(actions, ActionRng):
+            if actions.nm != self.N * self.M:
+                raise ValueError(f"ActionRng describes {actions.nm} slots, the engine has {self.N * self.M}")
+            inp.use_rng, inp.rng_tick0 = 1, int(tick0)
+            inp.rng = actions.struct()
+            inp.n_action_ticks = max(actions.n_ticks - tick0, 0)
+        elif actions is not None:
             a = self.set_actions(actions) if not (
                 isinstance(actions, torch.Tensor) and actions is self._actions_t) else actions
+            if a.dtype == torch.float32 and self._wants_f64_table():
+                a = a.to(torch.float64)
             if tick0:
                 a = a[tick0:]
-            inp.actions = a.data_ptr()
+            if a.dtype == torch.float32:
+                inp.actions_f32 = a.data_ptr()
+            else:
+                inp.actions = a.data_ptr()
             inp.n_action_ticks = a.shape[0]
             keep.append(a)
         elif (self.scene.kind == abi.KIND_VEHICLE).any():
-            raise ValueError("scene has VehicleController slots: an action table is required")
+            raise ValueError("scene has VehicleController slots: an action table or ActionRng is required")
         if host_pose is not None:
             hp = torch.from_numpy(np.ascontiguousarray(host_pose, np.float64)).to(self.device)
             hm = torch.from_numpy(np.ascontiguousarray(host_present, np.uint8)).to(self.device)

@@ -14,6 +14,7 @@ from typing import Optional
 import numpy as np
 
 from . import abi
+from .action_rng import ActionRng
 from .packing import PackedScene
 
 # tests/input_files/Catalogs/Scenario_Gym/VehicleCatalogs/ScenarioGymVehicleCatalog.xosc:8-9 (car1)
@@ -41,6 +42,9 @@ class SyntheticConfig:
     actions: Optional[np.ndarray] = None  # (T, 2, N*M) accel, steer
     speed_desired: Optional[np.ndarray] = None  # (N, M)
     goal: Optional[np.ndarray] = None  # (N, M, 2) pedestrians' route end point
+    # the action table as a description of its place in the numpy stream (device-side action source);
+    # always set for the random-action configs, `actions` only when the table was materialised
+    action_rng: Optional[ActionRng] = None
 
     @property
     def t_end(self) -> float:
@@ -121,35 +125,43 @@ def _uniform_into(rng, out: np.ndarray, low: float, high: float) -> None:
 
 def vehicles_config(seed: int, N: int, M: int = 64, T: int = 256, dt: float = 0.1,
                     half_extent: float = 200.0, name: str = "C3",
-                    actions_out: Optional[np.ndarray] = None) -> SyntheticConfig:
+                    actions_out: Optional[np.ndarray] = None, materialise: bool = True) -> SyntheticConfig:
     """
     C3: M VehicleController agents per scenario with random accel/steer actions.
     x,y ~ U(-half_extent, half_extent), h ~ U(-pi, pi), v0 ~ U(0, 15),
     accel ~ U(-6, 6) (exercises the +-5 clip), steer ~ U(-1, 1) (+-0.7 clip).
+    The (T, 2, N*M) action table follows the initial conditions in the generator's stream, plane by
+    plane (all accel rows, then all steer rows); ``materialise=False`` only describes it
+    (``action_rng``) for the device-side action source.
     """
     rng = np.random.default_rng(seed)
     x0 = rng.uniform(-half_extent, half_extent, (N, M))
     y0 = rng.uniform(-half_extent, half_extent, (N, M))
     h0 = rng.uniform(-np.pi, np.pi, (N, M))
     v0 = rng.uniform(0.0, 15.0, (N, M))
-    actions = np.empty((T, 2, N * M)) if actions_out is None else actions_out
-    assert actions.shape == (T, 2, N * M) and actions.dtype == np.float64
-    # drawn plane by plane (all accel rows, then all steer rows), in place: the table can be
-    # a view of pinned host memory
-    tmp = np.empty(N * M)
-    for c, (lo, hi) in enumerate(((-6.0, 6.0), (-1.0, 1.0))):
-        for k in range(T):
-            _uniform_into(rng, tmp, lo, hi)
-            actions[k, c] = tmp
+    planes = ((-6.0, 6.0), (-1.0, 1.0))
+    arng = ActionRng.from_generator(rng, offset=(0, T * N * M), tick_stride=N * M,
+                                    low=[lo for lo, _ in planes], high=[hi for _, hi in planes],
+                                    n_ticks=T, nm=N * M)
+    actions = None
+    if materialise or actions_out is not None:
+        actions = np.empty((T, 2, N * M)) if actions_out is None else actions_out
+        assert actions.shape == (T, 2, N * M) and actions.dtype == np.float64
+        # drawn in place: the table can be a view of pinned host memory
+        tmp = np.empty(N * M)
+        for c, (lo, hi) in enumerate(planes):
+            for k in range(T):
+                _uniform_into(rng, tmp, lo, hi)
+                actions[k, c] = tmp
     return SyntheticConfig(
         name=name, N=N, M=M, T=T, dt=dt, x0=x0, y0=y0, h0=h0, v0=v0,
         box=np.array(CAR1_BOX), kind=np.full((N, M), abi.KIND_VEHICLE, np.uint8),
-        etype=np.full((N, M), abi.ETYPE_VEHICLE, np.uint8), actions=actions,
+        etype=np.full((N, M), abi.ETYPE_VEHICLE, np.uint8), actions=actions, action_rng=arng,
     )
 
 
 def highway_config(seed: int, N: int, M: int = 256, T: int = 256, dt: float = 0.1,
-                   lanes: int = 4, name: str = "C5") -> SyntheticConfig:
+                   lanes: int = 4, name: str = "C5", materialise: bool = True) -> SyntheticConfig:
     """
     C5: `lanes` lanes x (M / lanes) vehicles, lane width 3.7 m, headway U(8, 40) m,
     heading ~ 0 +- 0.02, v0 ~ U(20, 35); small random actions.  Ego = slot 0.
@@ -166,13 +178,17 @@ def highway_config(seed: int, N: int, M: int = 256, T: int = 256, dt: float = 0.
     mid = per // 2
     for a in (x0, y0, h0, v0):
         a[:, [0, mid]] = a[:, [mid, 0]]
-    actions = np.empty((T, 2, N * M))
-    actions[:, 0] = rng.uniform(-2.0, 2.0, (T, N * M))
-    actions[:, 1] = rng.uniform(-0.02, 0.02, (T, N * M))
+    arng = ActionRng.from_generator(rng, offset=(0, T * N * M), tick_stride=N * M, low=(-2.0, -0.02),
+                                    high=(2.0, 0.02), n_ticks=T, nm=N * M)
+    actions = None
+    if materialise:
+        actions = np.empty((T, 2, N * M))
+        actions[:, 0] = rng.uniform(-2.0, 2.0, (T, N * M))
+        actions[:, 1] = rng.uniform(-0.02, 0.02, (T, N * M))
     return SyntheticConfig(
         name=name, N=N, M=M, T=T, dt=dt, x0=x0, y0=y0, h0=h0, v0=v0,
         box=np.array(CAR1_BOX), kind=np.full((N, M), abi.KIND_VEHICLE, np.uint8),
-        etype=np.full((N, M), abi.ETYPE_VEHICLE, np.uint8), actions=actions,
+        etype=np.full((N, M), abi.ETYPE_VEHICLE, np.uint8), actions=actions, action_rng=arng,
     )
 
 
