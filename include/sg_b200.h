@@ -281,6 +281,11 @@ int sg_future_collisions(const SgScene* scene, const double* t, const int32_t* s
 int sg_fill_random_actions(const SgActionRng* rng, int tick0, int n_ticks, int64_t nm, double* out,
                            int device, void* stream);
 
+/* Measurement aid for the secondary roofline (bench.py): DFMA thread-instructions per second this
+   GPU sustains at its current clocks (8 independent chains per thread, all SMs, best of 3 timed
+   launches with CUDA events on `stream`).  Blocking. */
+int sg_measure_fp64_peak(double* inst_per_s, int device, void* stream);
+
 /* exact closed-set intersection test of oriented boxes (entity/base.py:100-138 +
    utils.py:28-62), for unit tests: poses [n][3] = x,y,h ; boxes [n][4] ; out[n] */
 int sg_test_box_pairs(const double* pose_a, const double* box_a, const double* pose_b,

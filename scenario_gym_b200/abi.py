@@ -308,6 +308,7 @@ def bind(lib: C.CDLL, prefix: str) -> Dict[str, object]:
         [C.POINTER(SgScene), _p, _p, C.c_double, C.c_int, _p, C.c_int, _p])
     get("fill_random_actions", C.c_int,
         [C.POINTER(SgActionRng), C.c_int, C.c_int, C.c_int64, _p, C.c_int, _p])
+    get("measure_fp64_peak", C.c_int, [C.POINTER(C.c_double), C.c_int, _p], required=False)
     get("rollout_host", C.c_int,
         [C.POINTER(SgScene), C.POINTER(SgScene), C.POINTER(SgParams), C.POINTER(SgState),
          C.POINTER(SgInputs), C.POINTER(SgInputs), C.POINTER(SgHostResults), C.c_int, C.c_int, _p],

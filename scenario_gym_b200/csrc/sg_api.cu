@@ -183,6 +183,15 @@ int sg_fill_random_actions(const SgActionRng* rng, int tick0, int n_ticks, int64
   return 0;
 }
 
+int sg_measure_fp64_peak(double* inst_per_s, int device, void* stream) {
+  if (!inst_per_s) return set_msg("null argument");
+  cudaError_t err = cudaSetDevice(device);
+  if (err != cudaSuccess) return set_err("cudaSetDevice", err);
+  err = sgi_measure_fp64((cudaStream_t)stream, inst_per_s);
+  if (err != cudaSuccess) return set_err("sg_dfma_kernel", err);
+  return 0;
+}
+
 int sg_test_box_pairs(const double* pose_a, const double* box_a, const double* pose_b,
                       const double* box_b, uint8_t* out, int64_t n, int device, void* stream) {
   cudaError_t err = cudaSetDevice(device);

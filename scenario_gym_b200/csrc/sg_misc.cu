@@ -88,6 +88,52 @@ cudaError_t sgi_launch_fill_actions(cudaStream_t s, const SgRngDev& rng, int n_t
   return cudaGetLastError();
 }
 
+// FP64 pipe micro-benchmark (sg_measure_fp64_peak): 8 independent DFMA chains per thread
+__global__ void sg_dfma_kernel(double* __restrict__ out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+  for (int k = 0; k < iters; ++k) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+      x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+    }
+  }
+  const double sum = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (sum == 12345.678) out[0] = sum;  // keeps the chains alive
+}
+
+cudaError_t sgi_measure_fp64(cudaStream_t s, double* inst_per_s) {
+  int dev = 0, sms = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return err;
+  err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (err != cudaSuccess) return err;
+  double* scratch = nullptr;
+  err = cudaMalloc(&scratch, sizeof(double));
+  if (err != cudaSuccess) return err;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  double best = 0.0;
+  for (int rep = 0; rep < 4 && err == cudaSuccess; ++rep) {
+    cudaEventRecord(e0, s);
+    sg_dfma_kernel<<<blocks, threads, 0, s>>>(scratch, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1, s);
+    err = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
+    const double inst = (double)blocks * threads * iters * 32.0;
+    if (err == cudaSuccess && rep > 0 && ms > 0.f) best = fmax(best, inst / (ms * 1e-3));
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(scratch);
+  *inst_per_s = best;
+  return err;
+}
+
 cudaError_t sgi_launch_replay(cudaStream_t s, const SgScene& sc, const SgParams& p, const SgState& st,
                               int n_ticks) {
   const size_t rsm = replay_smem_bytes(sc.n_slots);

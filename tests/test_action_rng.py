@@ -118,7 +118,7 @@ def test_gpu_pcg64_matches_numpy():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", ["c3", "c3_norss", "c5", "subwarp", "m1024"])
+@pytest.mark.parametrize("shape", ["c3", "c3_norss", "c5", "subwarp", "m512"])
 def test_gpu_rollout_rng_equals_table(shape):
     rss = shape != "c3_norss"
     if shape.startswith("c3"):
@@ -126,8 +126,8 @@ def test_gpu_rollout_rng_equals_table(shape):
     elif shape == "c5":
         cfg = synthetic.highway_config(seed=4, N=9, M=256, T=40)
         cfg.x0[:] *= 0.5
-    elif shape == "m1024":
-        cfg = synthetic.vehicles_config(seed=4, N=3, M=1024, T=12, half_extent=150.0)
+    elif shape == "m512":
+        cfg = synthetic.vehicles_config(seed=4, N=3, M=512, T=12, half_extent=100.0)
     else:
         cfg = synthetic.vehicles_config(seed=4, N=33, M=8, T=48, half_extent=15.0)
     scene = pack_synthetic(cfg)
