@@ -84,6 +84,14 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
     if (err != cudaSuccess) return set_err("sg_replay_kernel launch", err);
     return 0;
   }
+  // crowd scenes (more than 256 slots of pedestrians / replayed agents): the two-scenarios-per-SM kernel
+  const uint32_t crowd_bits = (1u << SG_KIND_EMPTY) | (1u << SG_KIND_PEDESTRIAN) | (1u << SG_KIND_AGENT_REPLAY);
+  if (grid_ok && !rss && sc->n_slots > SG_THREADS && (sc->kind_mask & (1u << SG_KIND_PEDESTRIAN)) &&
+      !(sc->kind_mask & ~crowd_bits) && st->trace_cap == 0 && !inp.host_present) {
+    err = sgi_launch_crowd(s, *sc, *p, *st, inp, n_ticks);
+    if (err != cudaSuccess) return set_err("sg_crowd_kernel launch", err);
+    return 0;
+  }
   const int act = inp.actions ? ACT_F64 : (inp.actions_f32 ? ACT_F32 : (inp.use_rng ? ACT_RNG : -1));
   SgRngDev rng;
   memset(&rng, 0, sizeof(rng));

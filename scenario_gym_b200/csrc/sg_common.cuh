@@ -61,6 +61,8 @@ struct Grp {
   uint16_t* sid;
   uint16_t* posof;
   int* sflag;
+  float* skey;
+  float4* tmpbox;
   int sorted;
   uint32_t* gstart;
   uint16_t* gsorted;
@@ -113,6 +115,8 @@ SG_DEV void setup_group(Grp& g, const SgScene& sc, const GroupLayout& L, unsigne
   g.sid = (uint16_t*)(base + L.off_sid);
   g.posof = (uint16_t*)(base + L.off_posof);
   g.sflag = (int*)(base + L.off_sflag);
+  g.skey = (float*)(base + L.off_skey) + SG_SORT_WIN + 1;  // index -WIN-1 .. M+WIN are valid
+  g.tmpbox = (float4*)(base + L.off_tmpbox);
   g.sorted = L.sorted;
   g.gstart = (uint32_t*)(base + L.off_gstart);
   g.gsorted = (uint16_t*)(base + L.off_gsorted);
@@ -675,11 +679,10 @@ SG_DEV void publish_box(const Grp& c, bool present, double x, double y, double c
     c.orient[c.s] = (int8_t)(orient_hint ? orient_hint : quad_orientation(quad_from_array(my)));
     bb = make_aabb_box(x, y, cs, sn, bw, bl, bcx, bcy, ox, oy);
   }
-  if (SORTED) {  // the slot keeps its position of the last tick; sort_positions repairs the order
+  if (SORTED) {  // publish the new key at the position of the last tick; sorted_scatter re-ranks the box
     if (!(bb.x <= bb.z)) bb = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);  // NaN pose: sorts last
-    const int pos = c.posof[c.s];
-    c.aabb[pos] = bb;
-    c.sid[pos] = (uint16_t)c.s;
+    c.skey[c.posof[c.s]] = bb.x;
+    c.tmpbox[c.s] = bb;
     return;
   }
   c.aabb[c.s] = bb;
@@ -699,8 +702,12 @@ SG_DEV void sorted_setup(const Grp& c) {  // all G threads, once per launch (fol
   if (c.s < c.M) { c.posof[c.s] = (uint16_t)c.s; c.sid[c.s] = (uint16_t)c.s; }
   for (int q = c.M + c.s; q < c.M + c.H + 1; q += c.G)
     c.aabb[q] = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
-  if (c.s < 4) c.sflag[c.s] = 0;
+  if (c.s <= SG_SORT_WIN) { c.skey[-1 - c.s] = -INFINITY; c.skey[c.M + c.s] = INFINITY; }
+  if (c.s < 3) c.sflag[c.s] = 0;
+  if (c.s == 3) c.sflag[3] = 1;  // the launch starts from slot order: the first tick sorts from scratch
 }
+// full repair: odd-even transposition rounds until a round swaps nothing (any disorder; used for the
+// first tick of a launch and whenever the one-pass re-ranking below does not verify)
 SG_DEV void sort_positions(const Grp& c, int& round) {  // all G threads
   const int r = c.s;
   for (;;) {
@@ -725,9 +732,33 @@ SG_DEV void sort_positions(const Grp& c, int& round) {  // all G threads
   }
   if (r < c.M) c.posof[c.sid[r]] = (uint16_t)r;
 }
+// One-pass re-ranking (owner threads, after the barrier that follows publish_box): the boxes were
+// sorted before the tick and move a few metres per tick, so a box's new rank differs from its old
+// position p only by the boxes within SG_SORT_WIN positions that it overtook or that overtook it:
+//   rank = p - #(earlier boxes in the window with a larger key) + #(later ones with a smaller key)
+// (ties keep their order).  The result is verified by broad_phase_sorted; when the window was too
+// small the tick falls back to sort_positions.
+SG_DEV void sorted_scatter(const Grp& c) {
+  const int p = c.posof[c.s];
+  const float k = c.skey[p];
+  int np = p;
+#pragma unroll
+  for (int d = 1; d <= SG_SORT_WIN; ++d) {
+    np -= c.skey[p - d] > k ? 1 : 0;
+    np += c.skey[p + d] < k ? 1 : 0;
+  }
+  c.aabb[np] = c.tmpbox[c.s];
+  c.sid[np] = (uint16_t)c.s;
+  c.posof[c.s] = (uint16_t)np;
+}
+template <bool VERIFY = false>
 SG_DEV void broad_phase_sorted(const Grp& c, int parity) {  // thread = sorted position
   const int r = c.s;
   const float4 mb = c.aabb[r];
+  if (VERIFY) {  // every position written by exactly one slot, keys in order
+    const float nx = c.aabb[r + 1].x;  // (position M holds an empty box: key +inf)
+    if (c.posof[c.sid[r]] != r || mb.x > nx) c.sflag[3] = 1;
+  }
   if (!(mb.x <= mb.z)) return;  // empty box (entity absent)
   const float4* nb = c.aabb + r + 1;
   int* acc = c.acc + parity * ACC_N;

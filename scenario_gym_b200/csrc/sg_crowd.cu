@@ -1,0 +1,819 @@
+// sg_crowd.cu -- the fused tick loop of crowd scenes (C4: ~1000 social-force pedestrians per
+// scenario; reference pedestrian/*.py, state/state.py:340-372, state/utils.py:10-49).
+//
+// Scenes it takes: more than 256 slots, every slot a PedestrianAgent with SocialForce, a
+// ReplayTrajectoryAgent (the ego driving past the crowd) or padding; no RSS, no trace.  Everything
+// else goes to the general kernel, whose results this kernel reproduces bit for bit (it calls the
+// same device functions for the arithmetic; tests/test_gpu_parity.py::test_crowd_cell_grid).
+//
+// Mapping.  One scenario = one CTA of 512 threads; a thread owns EPT = 1 or 2 entity slots
+// (s, s + 512).  Two such CTAs share an SM (64 registers per thread, <= 113 KB of shared memory
+// each), so the barrier phases of one scenario are covered by the other scenario's work -- a
+// 1024-thread CTA per SM spends its time waiting at its own barriers.  The State rows that other
+// threads read (x, y, vx, vy: the pedestrians' sensors) live in shared memory, single-buffered:
+//   A  sensors + behaviour: neighbours from the cell grid of the OLD positions, social force
+//      (neighbour terms pooled per warp, summed in state.poses order) -> force per slot
+//   -- barrier --
+//   B  controller + State.step on the thread's own rows (in place), cos/sin of the heading,
+//      conservative fp32 AABB; then the cell grid of the NEW positions (count, scan, scatter)
+//   C  broad phase through the grid; AABB survivors are decided at once by inscribed /
+//      circumscribed circles where those decide (conservatively), the rest are queued
+//   D  exact closed-set predicate on the queued pairs, one pair per thread, corners recomputed
+//      from the rows with the reference's expression (entity/base.py:100-138)
+//   E  terminal conditions, CollisionMetric rising edges, ego metrics.
+#include "sg_common.cuh"
+#include "sg_internal.h"
+
+#define CR_THREADS 512
+#define CR_NBCAP 8       // per-pedestrian neighbour candidate list
+#define CR_WARPS (CR_THREADS / 32)
+
+struct CrowdLayout {
+  int G, W, QCAP;
+  int off_state, off_fcs, off_aabb, off_rad, off_nbl, off_gstart, off_gsorted, off_glarge, off_queue, off_flags,
+      off_wflag, off_orient, off_hits, off_bits, off_acc, off_cold, off_gmisc;
+  int bytes;
+};
+
+static CrowdLayout crowd_layout(int ept) {
+  CrowdLayout L;
+  const int G = CR_THREADS * ept;
+  L.G = G;
+  L.W = G / 32;
+  L.QCAP = 2 * G;
+  int o = 0;
+  L.off_state = o;   o += 4 * G * (int)sizeof(double);          // x, y, vx, vy
+  L.off_fcs = o;     o += 2 * G * (int)sizeof(double);          // force (A -> B), then cos / sin of the heading
+  L.off_aabb = o;    o += G * (int)sizeof(float4);
+  L.off_rad = o;     o += G * (int)sizeof(float2);              // inscribed / circumscribed radius of each box
+  L.off_nbl = o;     o += CR_NBCAP * G * (int)sizeof(uint16_t);
+  o = (o + 15) / 16 * 16;
+  L.off_gstart = o;  o += (SG_GRID_CELLS / 2 + 4) * (int)sizeof(uint32_t);
+  L.off_gsorted = o; o += G * (int)sizeof(uint16_t);
+  L.off_glarge = o;  o += SG_GRID_LCAP * (int)sizeof(uint16_t);
+  o = (o + 15) / 16 * 16;
+  L.off_queue = o;   o += L.QCAP * (int)sizeof(uint32_t);
+  L.off_flags = o;   o += G;                                    // present | etype << 1 | large << 3
+  L.off_wflag = o;   o += G;                                    // walking this tick
+  L.off_orient = o;  o += G;
+  o = (o + 15) / 16 * 16;
+  L.off_hits = o;    o += 2 * L.W * (int)sizeof(uint32_t);      // ego_now, ego_last
+  L.off_bits = o;    o += 2 * L.W * (int)sizeof(uint32_t);      // collided bits, 2 parities
+  L.off_acc = o;     o += 2 * ACC_N * (int)sizeof(int);
+  L.off_cold = o;    o += COLD_ND * (int)sizeof(double) + COLD_NI * (int)sizeof(int);
+  L.off_gmisc = o;   o += 48 * (int)sizeof(int);
+  L.bytes = (o + 15) / 16 * 16;
+  return L;
+}
+
+struct Crowd {  // shared-memory views of one scenario
+  int G, W, QCAP, M;
+  double* state;   // [4][G]
+  double* fcs;     // [2][G]
+  float4* aabb;
+  float2* rad;
+  uint16_t* nbl;
+  uint32_t* gstart;
+  uint16_t* gsorted;
+  uint16_t* glarge;
+  uint32_t* queue;
+  uint8_t* flags;
+  uint8_t* wflag;
+  int8_t* orient;
+  uint32_t* ego_now;
+  uint32_t* ego_last;
+  uint32_t* bits;
+  int* acc;
+  double* cold_d;
+  int* cold_i;
+  int* gmisc;
+};
+
+SG_DEV void crowd_views(Crowd& c, const CrowdLayout& L, unsigned char* base, int M) {
+  c.G = L.G; c.W = L.W; c.QCAP = L.QCAP; c.M = M;
+  c.state = (double*)(base + L.off_state);
+  c.fcs = (double*)(base + L.off_fcs);
+  c.aabb = (float4*)(base + L.off_aabb);
+  c.rad = (float2*)(base + L.off_rad);
+  c.nbl = (uint16_t*)(base + L.off_nbl);
+  c.gstart = (uint32_t*)(base + L.off_gstart);
+  c.gsorted = (uint16_t*)(base + L.off_gsorted);
+  c.glarge = (uint16_t*)(base + L.off_glarge);
+  c.queue = (uint32_t*)(base + L.off_queue);
+  c.flags = base + L.off_flags;
+  c.wflag = base + L.off_wflag;
+  c.orient = (int8_t*)(base + L.off_orient);
+  c.ego_now = (uint32_t*)(base + L.off_hits);
+  c.ego_last = c.ego_now + L.W;
+  c.bits = (uint32_t*)(base + L.off_bits);
+  c.acc = (int*)(base + L.off_acc);
+  c.cold_d = (double*)(base + L.off_cold);
+  c.cold_i = (int*)(base + L.off_cold + COLD_ND * sizeof(double));
+  c.gmisc = (int*)(base + L.off_gmisc);
+}
+
+SG_DEV void cta_sync() { __syncthreads(); }
+
+// ---------------------------------------------------------------------------------
+// cell grid over the scenario's present entities (same cells, cell size and "large" rule as the
+// general kernel's grid_build): packed 16-bit counters -> exclusive scan -> slot ids sorted by cell.
+// `have_box`: AABBs are staged (collision broad phase); entities reaching further than half a cell
+// from their position go to the `large` list.  All threads call it; it ends with a barrier.
+template <int EPT>
+SG_DEV void crowd_grid_build(const Crowd& c, bool have_box, double ox, double oy, double cs, double inv_cs) {
+  const int tid = threadIdx.x;
+  uint32_t* gs = c.gstart;
+  const int nwords = SG_GRID_CELLS / 2;
+  for (int q = tid; q <= nwords; q += CR_THREADS) gs[q] = 0;
+  if (tid == 0) c.gmisc[0] = 0;
+  cta_sync();
+  int cell[EPT];
+  uint32_t rank[EPT];
+  bool large[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const int s = tid + e * CR_THREADS;
+    cell[e] = -1; rank[e] = 0; large[e] = false;
+    if (c.flags[s] & 1) {
+      const double px = c.state[s] - ox, py = c.state[c.G + s] - oy;
+      const int ix = __double2int_rd(px * inv_cs), iy = __double2int_rd(py * inv_cs);
+      cell[e] = ((iy & (SG_GRID_DIM - 1)) << SG_GRID_BITS) | (ix & (SG_GRID_DIM - 1));
+      if (have_box) {
+        const float4 bb = c.aabb[s];
+        const double reach = fmax(fmax(px - (double)bb.x, (double)bb.z - px),
+                                  fmax(py - (double)bb.y, (double)bb.w - py));
+        large[e] = !(reach <= 0.5 * cs * (1.0 - 1e-6));
+        c.flags[s] = (uint8_t)((c.flags[s] & ~8) | (large[e] ? 8 : 0));
+        if (large[e]) {
+          const int k = atomicAdd(&c.gmisc[0], 1);
+          if (k < SG_GRID_LCAP) c.glarge[k] = (uint16_t)s;
+        }
+      }
+      const uint32_t old = atomicAdd(&gs[cell[e] >> 1], (cell[e] & 1) ? 0x10000u : 1u);
+      rank[e] = (cell[e] & 1) ? (old >> 16) : (old & 0xffffu);
+    }
+  }
+  cta_sync();
+  // exclusive scan of the packed counts: thread t owns 4 consecutive words
+  constexpr int WPT = (SG_GRID_CELLS / 2) / CR_THREADS;
+  const int w0 = tid * WPT;
+  uint32_t local = 0;
+#pragma unroll
+  for (int q = 0; q < WPT; ++q) { const uint32_t v = gs[w0 + q]; local += (v & 0xffffu) + (v >> 16); }
+  const int lane = tid & 31, wid = tid >> 5;
+  uint32_t incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) c.gmisc[8 + wid] = (int)incl;
+  cta_sync();
+  uint32_t wt = lane < CR_WARPS ? (uint32_t)c.gmisc[8 + lane] : 0u, wi = wt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+    if (lane >= d) wi += o;
+  }
+  const uint32_t wbase = __shfl_sync(0xffffffffu, wi - wt, wid);
+  const uint32_t total = __shfl_sync(0xffffffffu, wi, 31);
+  uint32_t run = wbase + incl - local;
+#pragma unroll
+  for (int q = 0; q < WPT; ++q) {
+    const uint32_t v = gs[w0 + q], lo = v & 0xffffu, hi = v >> 16;
+    gs[w0 + q] = run | ((run + lo) << 16);
+    run += lo + hi;
+  }
+  if (tid == 0) gs[nwords] = total;
+  cta_sync();
+#pragma unroll
+  for (int e = 0; e < EPT; ++e)
+    if (cell[e] >= 0)
+      c.gsorted[grid_start(gs, cell[e]) + rank[e]] =
+          (uint16_t)((uint32_t)(tid + e * CR_THREADS) | (large[e] ? SG_GRID_LARGE : 0u));
+  cta_sync();
+}
+
+// ---------------------------------------------------------------------------------
+// exact narrow phase of one pair from the State rows (corners as entity/base.py:100-138 computes
+// them; `g != g_prime` exclusion of reference utils.py:58)
+static __device__ __noinline__ bool crowd_pair_collides(const double* __restrict__ state, const double* __restrict__ hcs,
+                                                        const double* __restrict__ box, int64_t nm, int64_t i0,
+                                                        const int8_t* __restrict__ orient, int G, int a, int b) {
+  double qa[8], qb[8];
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+    const int s = w ? b : a;
+    double* q = w ? qb : qa;
+    const double x = state[s], y = state[G + s], cs = hcs[s], sn = hcs[G + s];
+    const double bw = __ldg(box + i0 + s), bl = __ldg(box + nm + i0 + s);
+    const double bcx = __ldg(box + 2 * nm + i0 + s), bcy = __ldg(box + 3 * nm + i0 + s);
+    const double hx0 = bcx - 0.5 * bl, hx1 = bcx + 0.5 * bl;
+    const double hy0 = bcy + 0.5 * bw, hy1 = bcy - 0.5 * bw;
+    q[0] = x + (hx0 * cs + hy0 * -sn); q[1] = y + (hx0 * sn + hy0 * cs);
+    q[2] = x + (hx1 * cs + hy0 * -sn); q[3] = y + (hx1 * sn + hy0 * cs);
+    q[4] = x + (hx1 * cs + hy1 * -sn); q[5] = y + (hx1 * sn + hy1 * cs);
+    q[6] = x + (hx0 * cs + hy1 * -sn); q[7] = y + (hx0 * sn + hy1 * cs);
+  }
+  bool same = true;
+#pragma unroll
+  for (int f = 0; f < 8; ++f) same = same && (qa[f] == qb[f]);
+  if (same) return false;
+  const Quad A = quad_from_array(qa), B = quad_from_array(qb);
+  const int oa = orient[a] ? orient[a] : quad_orientation(A), ob = orient[b] ? orient[b] : quad_orientation(B);
+  return quads_intersect(A, oa, B, ob);
+}
+
+struct CrowdSink {  // where colliding pairs are booked (shared atomics)
+  int* acc;
+  uint32_t* bits;
+  uint32_t* ego_now;
+  uint32_t* rows;
+  int W, ego_slot, first_slot;
+};
+
+static __device__ __noinline__ void crowd_commit(CrowdSink k, int a, int b) {
+  const int lo = min(a, b), hi = max(a, b);
+  atomicAdd(&k.acc[ACC_NPAIRS], 1);
+  atomicMin(&k.acc[ACC_FIRST_PAIR], (lo << 16) | hi);
+  if (lo == k.first_slot || hi == k.first_slot) k.acc[ACC_FIRST_HIT] = 1;
+  atomicOr(&k.bits[lo >> 5], 1u << (lo & 31));
+  atomicOr(&k.bits[hi >> 5], 1u << (hi & 31));
+  if (lo == k.ego_slot) atomicOr(&k.ego_now[hi >> 5], 1u << (hi & 31));
+  if (hi == k.ego_slot) atomicOr(&k.ego_now[lo >> 5], 1u << (lo & 31));
+  if (k.rows) {
+    atomicOr(&k.rows[(int64_t)lo * k.W + (hi >> 5)], 1u << (hi & 31));
+    atomicOr(&k.rows[(int64_t)hi * k.W + (lo >> 5)], 1u << (lo & 31));
+  }
+}
+
+// One AABB-surviving pair (a < b by construction of the callers): decided by circles where they
+// decide -- centres closer than the sum of the inscribed radii: the boxes intersect; further apart
+// than the sum of the circumscribed radii: they cannot -- with a 1e-6 relative margin, nine orders
+// of magnitude above the rounding of the corner coordinates; everything else is queued for the
+// exact predicate.  (Pedestrian boxes are near-square: more than half of the survivors are decided here.)
+SG_DEV void crowd_candidate(const Crowd& c, const CrowdSink& sink, int* acc, int a, int b) {
+  const float2 ra = c.rad[a], rb = c.rad[b];
+  const double dx = c.state[a] - c.state[b], dy = c.state[c.G + a] - c.state[c.G + b];
+  const double d2 = dx * dx + dy * dy;
+  const double rin = (double)ra.x + (double)rb.x, rout = (double)ra.y + (double)rb.y;
+  if (d2 > rout * rout) return;
+  if (d2 < rin * rin && d2 > 0.0) { crowd_commit(sink, a, b); return; }
+  const int q = atomicAdd(&acc[ACC_QCOUNT], 1);
+  if (q < c.QCAP) c.queue[q] = ((uint32_t)a << 16) | (uint32_t)b;
+}
+
+// broad phase of slot s through the grid: every unordered pair whose conservative AABBs overlap is
+// seen exactly once (small-small by the lower slot, small-large by the small one, large-large by
+// the lower slot)
+template <typename F>
+SG_DEV void crowd_for_each_candidate(const Crowd& c, int s, double ox, double oy, double inv_cs, F&& fn) {
+  const float4 mb = c.aabb[s];
+  const int nl = c.gmisc[0];
+  const bool large = (c.flags[s] & 8) != 0;
+  if (!large) {
+    const int ix = __double2int_rd((c.state[s] - ox) * inv_cs), iy = __double2int_rd((c.state[c.G + s] - oy) * inv_cs);
+    for (int dy = -1; dy <= 1; ++dy) {
+      int beg[2], end[2];
+      const int nr = grid_row_ranges(c.gstart, ix, iy, dy, beg, end);
+      for (int r = 0; r < nr; ++r)
+        for (int idx = beg[r]; idx < end[r]; ++idx) {
+          const uint32_t o = c.gsorted[idx];
+          if (o > (uint32_t)s && o < SG_GRID_LARGE) {
+            const float4 ob = c.aabb[o];
+            if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) fn(s, (int)o);
+          }
+        }
+    }
+  }
+  for (int k = 0; k < nl; ++k) {
+    const int o = c.glarge[k];
+    if (o == s || (large && o < s)) continue;
+    const float4 ob = c.aabb[o];
+    if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) fn(min(s, o), max(s, o));
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// ReplayTrajectoryAgent slot (the ego): rare kind, rows kept in global memory
+struct CrowdReplayOut { double x, y, h, vx, vy, speed3; bool present; };
+static __device__ __noinline__ CrowdReplayOut crowd_replay_step(const SgScene sc, const SgState st, int64_t i, int64_t nm,
+                                                               bool present, double t, double next_t) {
+  CrowdReplayOut o;
+  const int64_t r0 = sc.traj_off[i];
+  const int K = (int)(sc.traj_off[i + 1] - r0);
+  const double* rows = sc.traj_rows + r0 * 7;
+  double np_[6], prev[6];
+  int cur = st.cur_own[i];
+  o.present = false;
+  o.x = st.pose[i]; o.y = st.pose[nm + i]; o.h = st.pose[3 * nm + i];
+  o.vx = st.vel[i]; o.vy = st.vel[nm + i]; o.speed3 = 0.0;
+  if (!present && !(K > 0 && __ldg(rows) >= t)) return o;  // scenario_gym.py:240-244
+  position_at_t(rows, K, next_t, EXT_CLAMP, cur, np_);      // agent.py:125-128
+  if (present) {
+#pragma unroll
+    for (int f = 0; f < 6; ++f) prev[f] = st.pose[f * nm + i];
+  } else {  // state.py:219-222
+    int c2 = 0;
+    position_at_t(rows, K, t, EXT_TRUE, c2, prev);
+  }
+  const double dt = next_t - t;
+  double d[6], v[6];
+#pragma unroll
+  for (int f = 0; f < 6; ++f) { d[f] = np_[f] - prev[f]; v[f] = d[f] / dt; }
+#pragma unroll
+  for (int f = 0; f < 6; ++f) { st.pose[f * nm + i] = np_[f]; st.vel[f * nm + i] = v[f]; }
+  st.dist[i] += norm3(d[0], d[1], d[2]);
+  st.cur_own[i] = cur;
+  o.present = true;
+  o.x = np_[0]; o.y = np_[1]; o.h = np_[3]; o.vx = v[0]; o.vy = v[1];
+  o.speed3 = norm3(v[0], v[1], v[2]);
+  return o;
+}
+
+// a pedestrian that is not in the scene yet is inserted at its first control point when its
+// trajectory starts at or after t (scenario_gym.py:240-244); returns false otherwise
+static __device__ __noinline__ bool crowd_ped_appears(const SgScene sc, int64_t i, double t, double next_t,
+                                                      double np_[6], double prev[6]) {
+  const int64_t r0 = sc.traj_off[i];
+  const int K = (int)(sc.traj_off[i + 1] - r0);
+  const double* rows = sc.traj_rows + r0 * 7;
+  if (!(K > 0 && __ldg(rows) >= t)) return false;
+  int cur = 1, c2 = 0;
+  position_at_t(rows, K, next_t, EXT_CLAMP, cur, np_);
+  position_at_t(rows, K, t, EXT_TRUE, c2, prev);  // state.py:219-222
+  return true;
+}
+
+// ---------------------------------------------------------------------------------
+// per-slot values only the owner thread needs between ticks (registers; the loops over a thread's
+// slots copy one PerSlot in and out with constant indices, so the array never goes to local memory)
+struct PerSlot {
+  int kind, goal;
+  double h, dist;
+  uint32_t bits;  // bit 0: was in a collision so far, bit 1: moved during this launch
+};
+enum { CR_EGO_SPEED = COLD_T0, CR_EGO_DIST = COLD_T1 };  // the ego's |v| and distance, for the metrics
+
+template <int EPT>
+__global__ void __launch_bounds__(CR_THREADS, 2)
+sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, CrowdLayout L) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int M = sc.n_slots, G = L.G, W = L.W, WM = (M + 31) / 32;
+  Crowd c;
+  crowd_views(c, L, smem, M);
+  Grp g;  // the view neighbour_force reads: old x, y, vx, vy of every slot
+  g.pedbuf = c.state; g.G = G;
+  const int64_t nm = (int64_t)sc.n_scenarios * M, i0 = (int64_t)n * M;
+  const int ego_slot = sc.ego_slot[n], first_slot = sc.first_slot[n];
+  const bool need_coll = (p.features & SG_FEAT_COLLISIONS) || (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
+  const bool matrix = (p.features & SG_FEAT_COLL_MATRIX) != 0;
+  const double grid_cs = p.ped_distance_threshold * (1.0 + 1e-6), grid_inv_cs = 1.0 / grid_cs;
+  const double sight_cos = cos(p.sf_sight_angle / 2 * M_PI / 180);
+  double sh_rot, ch_rot;
+  sincos(p.ped_head_rot_angle, &sh_rot, &ch_rot);  // viewer/utils.py:6-17
+  double ox, oy;  // origin of the fp32 bounds / the grid: the ego's first control point
+  {
+    const int64_t er = sc.traj_off[i0 + ego_slot];
+    ox = __ldg(sc.traj_rows + er * 7 + 1);
+    oy = __ldg(sc.traj_rows + er * 7 + 2);
+  }
+  const double length = sc.length[n];
+
+  // ---- load the rows ----------------------------------------------------------------------
+  PerSlot ent[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const int s = tid + e * CR_THREADS;
+    PerSlot me;
+    me.kind = SG_KIND_EMPTY; me.goal = 0; me.h = 0; me.dist = 0; me.bits = 0;
+    uint8_t fl = 0;
+    double x = 0, y = 0, vx = 0, vy = 0;
+    float2 rd = make_float2(0.f, 0.f);
+    int8_t oh = 0;
+    if (s < M) {
+      const int64_t i = i0 + s;
+      me.kind = sc.kind[i];
+      if (me.kind != SG_KIND_EMPTY) {
+        x = st.pose[i]; y = st.pose[nm + i]; me.h = st.pose[3 * nm + i];
+        vx = st.vel[i]; vy = st.vel[nm + i];
+        me.dist = st.dist[i];
+        me.goal = st.goal_idx[i];
+        me.bits = st.collided[i] ? 1u : 0u;
+        fl = (uint8_t)((st.present[i] ? 1 : 0) | (sc.etype[i] << 1));
+        const double bw = sc.box[i], bl = sc.box[nm + i], bcx = sc.box[2 * nm + i], bcy = sc.box[3 * nm + i];
+        oh = (int8_t)box_orientation_hint(bw, bl);
+        // circles about the pose position: inscribed only when the box is centred on it
+        const double aw = fabs(bw), al = fabs(bl), off = sqrt(bcx * bcx + bcy * bcy);
+        const double rin = (bcx == 0.0 && bcy == 0.0) ? 0.5 * fmin(aw, al) * (1.0 - 1e-6) : 0.0;
+        const double rout = (0.5 * sqrt(aw * aw + al * al) + off) * (1.0 + 1e-6);
+        rd = make_float2(__double2float_rd(rin), __double2float_ru(rout));
+        if (s == ego_slot) {
+          c.cold_d[CR_EGO_SPEED] = norm3(vx, vy, st.vel[2 * nm + i]);
+          c.cold_d[CR_EGO_DIST] = me.dist;
+        }
+      }
+    }
+    c.state[s] = x; c.state[G + s] = y; c.state[2 * G + s] = vx; c.state[3 * G + s] = vy;
+    c.flags[s] = fl;
+    c.wflag[s] = 0;
+    c.rad[s] = rd;
+    c.orient[s] = oh;
+    c.aabb[s] = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+    ent[e] = me;
+  }
+  double t = st.t[n], prev_t = st.prev_t[n];
+  int tick = st.tick[n];
+  bool done = st.done[n] != 0;
+  if (tid == 0) {
+    c.cold_i[COLD_FIRST_TICK] = st.first_coll_tick[n];
+    c.cold_i[COLD_FP0] = st.first_coll_pair[2 * n]; c.cold_i[COLD_FP1] = st.first_coll_pair[2 * n + 1];
+    *(long long*)(c.cold_i + COLD_PAIR_TICKS) = st.n_pair_ticks[n];
+    for (int q = 0; q < 2 * ACC_N; ++q) c.acc[q] = 0;
+    c.acc[ACC_FIRST_PAIR] = 0x7fffffff; c.acc[ACC_N + ACC_FIRST_PAIR] = 0x7fffffff;
+    c.cold_d[COLD_AVG] = st.ego_avg_speed[n]; c.cold_d[COLD_AVG_T] = st.ego_avg_t[n];
+    c.cold_d[COLD_MAX] = st.ego_max_speed[n]; c.cold_d[COLD_EGOD] = st.ego_dist[n];
+  }
+  if (tid < W) {
+    c.ego_last[tid] = tid < WM ? st.ego_hits[(int64_t)n * WM + tid] : 0u;
+    c.ego_now[tid] = 0;
+    c.bits[tid] = 0; c.bits[W + tid] = 0;
+  }
+  cta_sync();
+  crowd_grid_build<EPT>(c, false, ox, oy, grid_cs, grid_inv_cs);  // the sensors of the first tick
+
+  const int limit = n_ticks < 0 ? p.max_ticks : n_ticks;
+  int parity = 0;
+
+  for (int k = 0; k < limit && (!done || in.step_done); ++k) {
+    const double next_t = t + p.timestep;  // scenario_gym.py:229
+    const double step_dt = next_t - t;
+    // ================= phase A: sensors + behaviour (reads the OLD rows of other slots) ==========
+#pragma unroll 1
+    for (int e = 0; e < EPT; ++e) {
+      const int s = tid + e * CR_THREADS;
+      PerSlot me = ent[0];
+      if (EPT > 1 && e == 1) me = ent[EPT - 1];
+      const bool is_ped = me.kind == SG_KIND_PEDESTRIAN && (c.flags[s] & 1);
+      const double px = c.state[s], py = c.state[G + s];
+      bool walking = false;
+      double F0 = 0.0, F1 = 0.0;
+      int ncand = 0;
+      uint16_t* nbl = c.nbl + s;
+      if (is_ped) {
+        const int64_t i = i0 + s;
+        const int64_t r0 = sc.route_off[i];
+        const int R = (int)(sc.route_off[i + 1] - r0);
+        const double* route = sc.route_xy + 2 * r0;
+        if (me.goal <= R - 1) {  // pedestrian/agent.py:60-62
+          const double sarc = route_project(route, R, px, py);
+          double arc = 0.0;
+          int last = 0;
+          for (int q = 0; q < R; ++q) {
+            if (q > 0)
+              arc += norm2(__ldg(route + 2 * q) - __ldg(route + 2 * q - 2),
+                           __ldg(route + 2 * q + 1) - __ldg(route + 2 * q - 1));
+            if (arc <= sarc) last = q;
+          }
+          me.goal = last + 1;
+        }
+        walking = me.goal <= R - 1;
+        if (walking) {
+          // SocialForce._force_to_goal, pedestrian/social_force.py:119-138
+          const double speed_desired = sc.ped_speed_desired[i];
+          const double dvx = __ldg(route + 2 * me.goal) - px, dvy = __ldg(route + 2 * me.goal + 1) - py;
+          double dn = norm2(dvx, dvy);
+          if (dn == 0) dn += 0.000000001;
+          const double ux = dvx / dn, uy = dvy / dn;
+          const double kk = 1 / p.sf_relaxation_time;
+          F0 = kk * (speed_desired * ux - c.state[2 * G + s]);
+          F1 = kk * (speed_desired * uy - c.state[3 * G + s]);
+          // sensor candidates from the 3 x 3 cells around the pedestrian (a neighbour strictly inside
+          // the 64-gon of circumradius r lies there), then put in slot (= state.poses) order
+          const double rr = p.ped_distance_threshold * (1.0 + 1e-9), r2 = rr * rr;
+          const int ix = __double2int_rd((px - ox) * grid_inv_cs), iy = __double2int_rd((py - oy) * grid_inv_cs);
+          for (int dy = -1; dy <= 1; ++dy) {
+            int beg[2], end[2];
+            const int nr = grid_row_ranges(c.gstart, ix, iy, dy, beg, end);
+            for (int r = 0; r < nr; ++r)
+              for (int idx = beg[r]; idx < end[r]; ++idx) {
+                const int o = (int)(c.gsorted[idx] & (SG_GRID_LARGE - 1u));
+                if (o == s || ((c.flags[o] >> 1) & 3) != SG_ETYPE_PEDESTRIAN) continue;
+                const double ddx = c.state[o] - px, ddy = c.state[G + o] - py;
+                if (ddx * ddx + ddy * ddy > r2) continue;
+                if (ncand < CR_NBCAP) nbl[ncand * G] = (uint16_t)o;
+                ++ncand;
+              }
+          }
+          for (int a = 1; a < min(ncand, CR_NBCAP); ++a) {  // insertion sort (a handful of entries)
+            const uint16_t v = nbl[a * G];
+            int b = a - 1;
+            while (b >= 0 && nbl[b * G] > v) { nbl[(b + 1) * G] = nbl[b * G]; --b; }
+            nbl[(b + 1) * G] = v;
+          }
+        }
+      }
+      // neighbour terms, pooled over the warp's 32 pedestrians of this pass and handed back to their
+      // owners in list order (same sums, same order as one lane walking its own list)
+      const int nlist = (walking && ncand <= CR_NBCAP) ? ncand : 0;
+      {
+        const unsigned FULL = 0xffffffffu;
+        const int wslot0 = s - lane;
+        int incl = nlist;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(FULL, incl, d);
+          if (lane >= d) incl += v;
+        }
+        const int off = incl - nlist, total = __shfl_sync(FULL, incl, 31);
+        __syncwarp();
+        for (int base = 0; base < total; base += 32) {
+          const int it = base + lane;
+          int q = 0;
+#pragma unroll
+          for (int stp = 16; stp > 0; stp >>= 1) {
+            const int tq = __shfl_sync(FULL, incl, (q + stp - 1) & 31);
+            if (tq <= it) q += stp;
+          }
+          q &= 31;
+          const int offq = __shfl_sync(FULL, off, q);
+          NbForce nf;
+          nf.valid = 0; nf.a0 = 0.0; nf.a1 = 0.0; nf.b0 = 0.0; nf.b1 = 0.0;
+          if (it < total) {
+            const int slot = wslot0 + q;
+            const int o = c.nbl[(it - offq) * G + slot];
+            nf = neighbour_force(p, g, c.state[slot], c.state[G + slot], o, step_dt, sh_rot, ch_rot, sight_cos);
+          }
+          const int lo = max(off, base), hi = min(off + nlist, base + 32);
+          const int cnt = max(hi - lo, 0);
+          const int maxc = __reduce_max_sync(FULL, cnt);
+          for (int jj = 0; jj < maxc; ++jj) {
+            const int src = (lo - base + jj) & 31;
+            const int v = __shfl_sync(FULL, nf.valid, src);
+            const double a0 = __shfl_sync(FULL, nf.a0, src), a1 = __shfl_sync(FULL, nf.a1, src);
+            const double b0 = __shfl_sync(FULL, nf.b0, src), b1 = __shfl_sync(FULL, nf.b1, src);
+            if (jj < cnt && v) { F0 += a0; F1 += a1; F0 += b0; F1 += b1; }
+          }
+        }
+      }
+      if (walking && ncand > CR_NBCAP) {  // very dense crowd: every present pedestrian in slot order
+        for (int o = 0; o < M; ++o) {
+          if (o == s || (c.flags[o] & 7) != (1 | (SG_ETYPE_PEDESTRIAN << 1))) continue;
+          const NbForce nf = neighbour_force(p, g, px, py, o, step_dt, sh_rot, ch_rot, sight_cos);
+          if (nf.valid) { F0 += nf.a0; F1 += nf.a1; F0 += nf.b0; F1 += nf.b1; }
+        }
+      }
+      c.fcs[s] = F0; c.fcs[G + s] = F1;
+      c.wflag[s] = walking ? 1 : 0;
+      if (e == 0) ent[0].goal = me.goal; else ent[EPT - 1].goal = me.goal;
+    }
+    cta_sync();
+    // ================= phase B: controllers + State.step on the own rows ===========================
+    const double dt_state = t - prev_t;  // state.dt: PedestrianController uses the previous interval
+    const double t_old = t;
+    prev_t = t;
+    t = next_t;
+    tick += 1;
+    const double dt = t - prev_t;
+    const double rdt = 1.0 / dt;
+#pragma unroll 1
+    for (int e = 0; e < EPT; ++e) {
+      const int s = tid + e * CR_THREADS;
+      PerSlot me = ent[0];
+      if (EPT > 1 && e == 1) me = ent[EPT - 1];
+      const int64_t i = i0 + s;
+      const bool present = (c.flags[s] & 1) != 0;
+      bool newpres = false;
+      double cs = 1.0, sn = 0.0, nx = c.state[s], ny = c.state[G + s];
+      if (me.kind == SG_KIND_PEDESTRIAN) {
+        double prevx = nx, prevy = ny, prevh = me.h, nh = me.h;
+        bool moved = false;
+        if (present) {
+          double speed, heading, F0 = 0.0, F1 = 0.0;
+          if (c.wflag[s]) {
+            F0 = c.fcs[s]; F1 = c.fcs[G + s];
+            speed = py_min(norm2(F0, F1) + p.sf_bias_lon, sc.ped_speed_desired[i] * p.sf_max_speed_factor);
+            heading = atan2(F1, F0) + p.sf_bias_lat;
+          } else {  // agent.py:65-68
+            speed = 0; heading = 0;
+          }
+          // PedestrianController._step, pedestrian/controller.py:38-46 (uses state.dt)
+          const double sp = np_clip(speed, -p.ped_max_speed, p.ped_max_speed);
+          st.speed[i] = sp;                            // pure outputs: written through, not kept
+          st.force[i] = F0; st.force[nm + i] = F1;
+          sincos(heading, &sn, &cs);
+          nx = prevx + sp * dt_state * cs;
+          ny = prevy + sp * dt_state * sn;
+          nh = heading;
+          moved = true;
+          me.dist += norm3(nx - prevx, ny - prevy, 0.0);
+        } else {
+          double np_[6], pv[6];
+          if (crowd_ped_appears(sc, i, t_old, t, np_, pv)) {
+            // (rare) first appearance: all six components go through global memory
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+              st.pose[f * nm + i] = np_[f];
+              st.vel[f * nm + i] = div_r(np_[f] - pv[f], dt, rdt);
+            }
+            me.dist += norm3(np_[0] - pv[0], np_[1] - pv[1], np_[2] - pv[2]);
+            prevx = pv[0]; prevy = pv[1]; prevh = pv[3];
+            nx = np_[0]; ny = np_[1]; nh = np_[3];
+            sincos(nh, &sn, &cs);
+            moved = true;
+            if (s == ego_slot)
+              c.cold_d[CR_EGO_SPEED] = norm3(div_r(nx - prevx, dt, rdt), div_r(ny - prevy, dt, rdt),
+                                             div_r(np_[2] - pv[2], dt, rdt));
+          }
+        }
+        if (moved) {
+          const double ex = nx - prevx, ey = ny - prevy;
+          const double nvx = div_r(ex, dt, rdt), nvy = div_r(ey, dt, rdt);
+          c.state[s] = nx; c.state[G + s] = ny;
+          c.state[2 * G + s] = nvx; c.state[3 * G + s] = nvy;
+          st.vel[3 * nm + i] = div_r(nh - prevh, dt, rdt);
+          me.h = nh;
+          if (present) {
+            me.bits |= 2u;  // z, p, r did not change: their velocities are 0 from now on
+            if (s == ego_slot) c.cold_d[CR_EGO_SPEED] = norm3(nvx, nvy, 0.0);
+          }
+          if (s == ego_slot) c.cold_d[CR_EGO_DIST] = me.dist;
+          newpres = true;
+        }
+      } else if (me.kind == SG_KIND_AGENT_REPLAY) {
+        const CrowdReplayOut r = crowd_replay_step(sc, st, i, nm, present, t_old, t);
+        newpres = r.present;
+        if (newpres) {
+          nx = r.x; ny = r.y;
+          c.state[s] = r.x; c.state[G + s] = r.y; c.state[2 * G + s] = r.vx; c.state[3 * G + s] = r.vy;
+          me.h = r.h;
+          sincos(r.h, &sn, &cs);
+          if (s == ego_slot) { c.cold_d[CR_EGO_SPEED] = r.speed3; c.cold_d[CR_EGO_DIST] = st.dist[i]; }
+        }
+      }
+      if (me.kind != SG_KIND_EMPTY) {
+        c.flags[s] = (uint8_t)((c.flags[s] & ~1) | (newpres ? 1 : 0));
+        float4 bb = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+        if (newpres && need_coll) {
+          c.fcs[s] = cs; c.fcs[G + s] = sn;
+          bb = make_aabb_box(nx, ny, cs, sn, __ldg(sc.box + i), __ldg(sc.box + nm + i), __ldg(sc.box + 2 * nm + i),
+                             __ldg(sc.box + 3 * nm + i), ox, oy);
+        }
+        c.aabb[s] = bb;
+        if (matrix) {
+          uint32_t* row = st.coll_mask + ((int64_t)n * M + s) * WM;
+          for (int w = 0; w < WM; ++w) row[w] = 0;
+        }
+      }
+      if (e == 0) ent[0] = me; else ent[EPT - 1] = me;
+    }
+    cta_sync();
+    // the grid of the new positions: this tick's broad phase and the next tick's sensors
+    crowd_grid_build<EPT>(c, need_coll, ox, oy, grid_cs, grid_inv_cs);
+    int* acc = c.acc + parity * ACC_N;
+    if (need_coll) {
+      CrowdSink sink;
+      sink.acc = acc; sink.bits = c.bits + parity * W; sink.ego_now = c.ego_now;
+      sink.rows = matrix ? st.coll_mask + (int64_t)n * M * WM : nullptr;
+      sink.W = WM; sink.ego_slot = ego_slot; sink.first_slot = first_slot;
+      // ================= phase C: broad phase ======================================================
+      const bool exhaustive = c.gmisc[0] > SG_GRID_LCAP;  // too many large entities for the list
+#pragma unroll 1
+      for (int e = 0; e < EPT; ++e) {
+        const int s = tid + e * CR_THREADS;
+        if (!(c.flags[s] & 1)) continue;
+        if (!exhaustive) {
+          crowd_for_each_candidate(c, s, ox, oy, grid_inv_cs, [&](int a, int b) { crowd_candidate(c, sink, acc, a, b); });
+        } else {
+          const float4 mb = c.aabb[s];
+          for (int o = s + 1; o < M; ++o) {
+            const float4 ob = c.aabb[o];
+            if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) crowd_candidate(c, sink, acc, s, o);
+          }
+        }
+      }
+      cta_sync();
+      // ================= phase D: exact narrow phase ================================================
+      const int nq = acc[ACC_QCOUNT];
+      if (nq <= c.QCAP) {
+        for (int q = tid; q < nq; q += CR_THREADS) {
+          const uint32_t pr = c.queue[q];
+          const int a = (int)(pr >> 16), b = (int)(pr & 0xffff);
+          if (crowd_pair_collides(c.state, c.fcs, sc.box, nm, i0, c.orient, G, a, b)) crowd_commit(sink, a, b);
+        }
+      } else {  // queue overflow (very dense scenes): walk the candidates again and decide in place
+#pragma unroll 1
+        for (int e = 0; e < EPT; ++e) {
+          const int s = tid + e * CR_THREADS;
+          if (!(c.flags[s] & 1)) continue;
+          auto direct = [&](int a, int b) {
+            const float2 ra = c.rad[a], rb = c.rad[b];
+            const double dx = c.state[a] - c.state[b], dy = c.state[G + a] - c.state[G + b];
+            const double d2 = dx * dx + dy * dy;
+            const double rin = (double)ra.x + (double)rb.x, rout = (double)ra.y + (double)rb.y;
+            if (d2 > rout * rout) return;
+            if (d2 < rin * rin && d2 > 0.0) return;  // booked in phase C already
+            if (crowd_pair_collides(c.state, c.fcs, sc.box, nm, i0, c.orient, G, a, b)) crowd_commit(sink, a, b);
+          };
+          if (!exhaustive) {
+            crowd_for_each_candidate(c, s, ox, oy, grid_inv_cs, direct);
+          } else {
+            const float4 mb = c.aabb[s];
+            for (int o = s + 1; o < M; ++o) {
+              const float4 ob = c.aabb[o];
+              if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) direct(s, o);
+            }
+          }
+        }
+      }
+      cta_sync();
+    }
+    // ================= phase E: terminal check + metrics ===========================================
+    const int npairs = acc[ACC_NPAIRS];
+    bool dn = false;  // state.py:268-270, 397-408
+    if ((p.terminal & SG_TERM_MAX_LENGTH) && (t + dt > length)) dn = true;
+    if ((p.terminal & SG_TERM_COLLISION) && npairs > 0) dn = true;
+    if ((p.terminal & SG_TERM_EGO_COLLISION) && acc[ACC_FIRST_HIT]) dn = true;
+    done = dn;
+    if (npairs > 0) {  // slots in a collision this tick
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int s = tid + e * CR_THREADS;
+        ent[e].bits |= (c.bits[parity * W + (s >> 5)] >> (s & 31)) & 1u;
+      }
+    }
+    if (tid == 32) {
+      int* cold = c.cold_i;
+      if (npairs > 0) {
+        *(long long*)(cold + COLD_PAIR_TICKS) += npairs;
+        if (cold[COLD_FIRST_TICK] < 0) {
+          const int fp = acc[ACC_FIRST_PAIR];
+          cold[COLD_FIRST_TICK] = tick; cold[COLD_FP0] = fp >> 16; cold[COLD_FP1] = fp & 0xffff;
+        }
+      }
+      int* nx = c.acc + (parity ^ 1) * ACC_N;  // the other parity is reset for the next tick
+      nx[ACC_NPAIRS] = 0; nx[ACC_FIRST_PAIR] = 0x7fffffff; nx[ACC_FIRST_HIT] = 0; nx[ACC_RSS] = 0; nx[ACC_QCOUNT] = 0;
+    }
+    if (tid >= 64 && tid < 64 + W) {  // CollisionMetric._step, metrics/collision.py:70-75
+      const int w = tid - 64;
+      const uint32_t now = c.ego_now[w];
+      if (p.features & SG_FEAT_COLLISIONS) {
+        const uint32_t fresh = now & ~c.ego_last[w];
+        if (fresh) emit_events(st.events, st.event_count, st.event_cap, fresh, n, tick, w * 32, t);
+        c.ego_last[w] = now;
+      }
+      c.ego_now[w] = 0;
+      c.bits[(parity ^ 1) * W + w] = 0;
+    }
+    if (tid == 0 && (p.features & SG_FEAT_EGO_METRICS)) {  // metrics/trajectory.py:20-24,39-42,58-60
+      double* m = c.cold_d;
+      const double sp = m[CR_EGO_SPEED];
+      const double w = m[COLD_AVG_T] / t;
+      m[COLD_AVG] += (1.0 - w) * (sp - m[COLD_AVG]);
+      m[COLD_AVG_T] = t;
+      m[COLD_MAX] = fmax(sp, m[COLD_MAX]);
+      m[COLD_EGOD] = m[CR_EGO_DIST];
+    }
+    parity ^= 1;
+  }
+  cta_sync();
+
+  // ---------------- write the rows back --------------------------------------------------------------
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const int s = tid + e * CR_THREADS;
+    const PerSlot me = ent[e];
+    if (s >= M || me.kind == SG_KIND_EMPTY) continue;
+    const int64_t i = i0 + s;
+    st.present[i] = (c.flags[s] & 1) != 0;
+    st.collided[i] = (uint8_t)(me.bits & 1u);
+    if (me.kind == SG_KIND_PEDESTRIAN) {
+      st.pose[i] = c.state[s]; st.pose[nm + i] = c.state[G + s]; st.pose[3 * nm + i] = me.h;
+      st.vel[i] = c.state[2 * G + s]; st.vel[nm + i] = c.state[3 * G + s];
+      if (me.bits & 2u) { st.vel[2 * nm + i] = 0.0; st.vel[4 * nm + i] = 0.0; st.vel[5 * nm + i] = 0.0; }
+      st.dist[i] = me.dist;
+      st.goal_idx[i] = me.goal;
+    }
+  }
+  if (tid == 0) {
+    st.t[n] = t; st.prev_t[n] = prev_t; st.tick[n] = tick; st.done[n] = done;
+    st.ego_avg_speed[n] = c.cold_d[COLD_AVG]; st.ego_avg_t[n] = c.cold_d[COLD_AVG_T];
+    st.ego_max_speed[n] = c.cold_d[COLD_MAX]; st.ego_dist[n] = c.cold_d[COLD_EGOD];
+    st.first_coll_tick[n] = c.cold_i[COLD_FIRST_TICK];
+    st.first_coll_pair[2 * n] = c.cold_i[COLD_FP0]; st.first_coll_pair[2 * n + 1] = c.cold_i[COLD_FP1];
+    st.n_pair_ticks[n] = *(long long*)(c.cold_i + COLD_PAIR_TICKS);
+  }
+  if (tid < WM) st.ego_hits[(int64_t)n * WM + tid] = c.ego_last[tid];
+}
+
+cudaError_t sgi_launch_crowd(cudaStream_t s, const SgScene& sc, const SgParams& p, const SgState& st,
+                             const SgInputs& in, int n_ticks) {
+  const int ept = sc.n_slots > CR_THREADS ? 2 : 1;
+  const CrowdLayout L = crowd_layout(ept);
+  auto kern = ept == 2 ? sg_crowd_kernel<2> : sg_crowd_kernel<1>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes);
+  if (err != cudaSuccess) return err;
+  kern<<<sc.n_scenarios, CR_THREADS, L.bytes, s>>>(sc, p, st, in, n_ticks, L);
+  return cudaGetLastError();
+}

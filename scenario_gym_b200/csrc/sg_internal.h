@@ -37,3 +37,5 @@ cudaError_t sgi_launch_box_pairs(cudaStream_t s, const double* pa, const double*
 cudaError_t sgi_launch_future(cudaStream_t s, const SgScene& sc, const double* t, const int32_t* slot,
                               double horizon, int n_samples, uint8_t* out);
 cudaError_t sgi_measure_fp64(cudaStream_t s, double* inst_per_s);
+cudaError_t sgi_launch_crowd(cudaStream_t s, const SgScene& sc, const SgParams& p, const SgState& st,
+                             const SgInputs& in, int n_ticks);

@@ -11,6 +11,9 @@
 #ifndef SG_SWEEP_WIN
 #define SG_SWEEP_WIN 8  // successors tested branch-free by the sorted sweep (a longer run is walked)
 #endif
+#ifndef SG_SORT_WIN
+#define SG_SORT_WIN 4  // positions either side within which the sorted sweep re-ranks a box in one pass
+#endif
 #ifndef SG_WARP_PAIRS
 #define SG_WARP_PAIRS 6  // queued pairs per warp up to which the narrow phase runs warp-cooperatively
 #endif
@@ -37,7 +40,7 @@ struct GroupLayout {
   int off_act, off_rbox, off_tcold, off_hcs, off_ped, off_pednb, off_nbl, off_box, off_ego, off_cold, off_aabb, off_queue, off_hits, off_bits,
       off_acc, off_flags, off_orient;
   int sorted;   // vehicle scenes with M >= 128: boxes kept sorted by their lower x bound, windowed sweep
-  int off_sid, off_posof, off_sflag;
+  int off_sid, off_posof, off_sflag, off_skey, off_tmpbox;
   int grid;     // crowd scenario with a shared-memory cell grid (sensor + broad phase)
   int off_gstart, off_gsorted, off_glarge, off_gmisc;
   int bytes;
@@ -83,6 +86,9 @@ static inline GroupLayout make_layout(int M, bool ped, bool rss, bool veh, bool 
   L.off_posof = o;  o += L.sorted ? G * (int)sizeof(uint16_t) : 0;          // sorted position of each slot
   o = (o + 15) / 16 * 16;
   L.off_sflag = o;  o += L.sorted ? 4 * (int)sizeof(int) : 0;
+  L.off_skey = o;   o += L.sorted ? (M + 2 * SG_SORT_WIN + 2) * (int)sizeof(float) : 0;  // keys by old position (+ sentinels)
+  o = (o + 15) / 16 * 16;
+  L.off_tmpbox = o; o += L.sorted ? G * (int)sizeof(float4) : 0;   // the owner's new box between publish and scatter
   L.grid = (grid && ped && G > SG_THREADS) ? 1 : 0;
   L.off_gstart = o;  o += L.grid ? (SG_GRID_CELLS / 2 + 4) * (int)sizeof(uint32_t) : 0;  // packed 16-bit cell starts (+ end)
   L.off_gsorted = o; o += L.grid ? G * (int)sizeof(uint16_t) : 0;                         // slot ids sorted by cell

@@ -193,7 +193,14 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       c.cold_d[COLD_PT0 + (parity ^ 1)] = t;
     }
     group_sync(c);
-    if (SORTED && need_coll) sort_positions(c, sort_round);
+    bool resort = false;
+    if (SORTED && need_coll) {
+      resort = c.sflag[3] != 0;  // (uniform: set before the barrier above or at launch)
+      if (!resort) {
+        if (s < M) sorted_scatter(c);
+        group_sync(c);
+      }
+    }
     // ---- phase B1: callbacks (RSS) + broad phase
     if (live && present) {
       if (RSS && feat_rss) {  // RSSDistances.__call__, callback.py:57-122
@@ -213,8 +220,20 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       }
       if (need_coll && !SORTED) broad_phase(c, parity);
     }
-    if (SORTED && need_coll && s < M) broad_phase_sorted(c, parity);
+    if (SORTED && need_coll && !resort && s < M) broad_phase_sorted<true>(c, parity);
     group_sync(c);
+    if (SORTED && need_coll && (resort || c.sflag[3] != 0)) {
+      // the one-pass re-ranking did not verify (or the launch starts unsorted): rebuild the order from
+      // the boxes in slot order with full transposition rounds and redo the sweep
+      group_sync(c);  // everyone has read the flag
+      if (s == 0) { c.sflag[3] = 0; c.acc[parity * ACC_N + ACC_QCOUNT] = 0; }
+      if (s < M) { c.aabb[s] = c.tmpbox[s]; c.sid[s] = (uint16_t)s; }
+      group_sync(c);
+      sort_positions(c, sort_round);
+      group_sync(c);
+      if (s < M) broad_phase_sorted<false>(c, parity);
+      group_sync(c);
+    }
     done = finish_tick<true>(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick,
                        c.cold_d[COLD_T0 + (parity ^ 1)], c.cold_d[COLD_T0 + (parity ^ 1)] - c.cold_d[COLD_PT0 + (parity ^ 1)],
                        c.cold_d[COLD_LEN], live, live && present, collided, vx, vy, 0.0, dist);

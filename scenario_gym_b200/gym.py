@@ -130,6 +130,8 @@ class ScenarioGym:
         self._sync_params()
         self._engine.reset()
         self._ticks_since_reset = 0
+        self._epoch += 1
+        self._cache = {}
         self._host_done = [False] * len(self.states)
         self._last_tick = np.zeros(len(self.states), np.int32)
         for n, st in enumerate(self.states):
@@ -183,18 +185,28 @@ class ScenarioGym:
                             host_pose[:, i] = pose
                             host_present[i] = 1
         force = len(self.states) == 1  # the reference's step() has no is_done guard
+        if self._ticks_since_reset < 0:
+            raise RuntimeError("step() after a fused rollout(): call reset_scenario() first")
         if self._action_table is not None:
+            k, T = self._ticks_since_reset, self._action_table_host.shape[0]
+            if k >= T and self._table_scenarios_live():
+                raise IndexError(f"ActionTableAgent: the action table has {T} rows, step {k + 1} needs another")
             if actions is not None:  # merge the host policies' row into the resident table's row
-                row = self._action_table_host[self._ticks_since_reset].copy()
+                row = self._action_table_host[k].copy() if k < T else np.zeros((2, N * M))
                 mask = self._host_policy_mask
                 row[:, mask] = actions[0][:, mask]
                 eng.rollout(1, actions=row[None], host_pose=host_pose, host_present=host_present, step_done=force)
-            else:
-                eng.rollout(1, actions=self._action_table, tick0=self._ticks_since_reset,
+            elif k < T:
+                eng.rollout(1, actions=self._action_table, tick0=k,
                             host_pose=host_pose, host_present=host_present, step_done=force)
+            else:  # only finished table scenarios are left: a zero row keeps the others stepping
+                eng.rollout(1, actions=np.zeros((1, 2, N * M)), host_pose=host_pose,
+                            host_present=host_present, step_done=force)
         else:
             eng.rollout(1, actions=actions, host_pose=host_pose, host_present=host_present, step_done=force)
         self._ticks_since_reset += 1
+        self._epoch += 1
+        self._cache = {}
         for st in self.states:
             st._invalidate()
         if self._host_mode:
@@ -212,8 +224,16 @@ class ScenarioGym:
             self._sync_params()
             self._engine.rollout(-1, actions=self._action_table, tick0=self._ticks_since_reset)
             self._ticks_since_reset = -1  # unknown per scenario; forces the next reset
+            self._epoch += 1
+            self._cache = {}
             for st in self.states:
                 st._invalidate()
+            if self._action_table is not None and not self._fetch("done").all():
+                # the device stops a scenario whose ActionTableAgents ran out of rows; the
+                # reference's agent would have raised on its next table lookup
+                n = int(np.nonzero(self._fetch("done") == 0)[0][0])
+                raise IndexError(f"ActionTableAgent: scenario {n} is not done after the "
+                                 f"{self._action_table_host.shape[0]} rows of its action table")
         for st in self.states:
             for agent in st.agents.values():
                 agent.finish(st)
@@ -291,6 +311,13 @@ class ScenarioGym:
                     else:
                         self._agent_kind[agent] = "host_policy"
                 else:
+                    if isinstance(agent, PedestrianAgent):
+                        raise NotImplementedError(
+                            "PedestrianAgent is integrated on the device with a SocialForce behaviour only "
+                            f"(got {type(agent.behaviour).__name__})")
+                    if agent.controller is None or agent.sensor is None:
+                        raise NotImplementedError(f"{type(agent).__name__} needs a controller and a sensor to "
+                                                  "run as a host-side agent")
                     kind, self._agent_kind[agent] = abi.KIND_HOST, "host"
                 slots.append(SlotSpec(kind=kind, **kw))
             specs.append(ScenarioSpec(slots=slots, ego_slot=ents.index(sc.ego),
@@ -380,13 +407,18 @@ class ScenarioGym:
                     if self._agent_kind[a] == "host_policy":
                         mask[n * M + self._slot_of[n][e]] = True
             self._host_policy_mask = mask
-            if self._any_host_policy and tables:
-                need = 1 << 16
-                if tab.shape[0] < need:  # host policies may run longer than the tables
-                    pass
+        self._table_slots = np.array(sorted(n * M + s_ for (n, s_) in tables), np.int64)
         self._ticks_since_reset = 1
+        self._epoch = 0
         self._host_done = [False] * N
         self._cache: Dict[str, np.ndarray] = {}
+
+    def _table_scenarios_live(self) -> bool:
+        """Is any scenario with an ActionTableAgent still running (it would need another table row)?"""
+        if not len(self._table_slots):
+            return False
+        done = self._fetch("done")
+        return bool((done[np.unique(self._table_slots // self._engine.M)] == 0).any())
 
     def _sync_params(self) -> None:
         self._params.timestep = self.timestep
@@ -456,7 +488,7 @@ class ScenarioGym:
         (tick, horizon, sensor slots); the result is cached until the state advances.
         """
         slot = self._slot_of[n][entity]
-        key = (id(self._engine), self._fetch("t").tobytes(), float(horizon), int(n_samples))
+        key = (id(self._engine), self._epoch, float(horizon), int(n_samples))
         cache = getattr(self, "_future_cache", None)
         if cache is None or cache[0] != key or cache[1][n] != slot:
             slots = np.array([self._slot_of[k].get(self.states[k].scenario.ego, 0)

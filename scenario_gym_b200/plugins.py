@@ -283,6 +283,29 @@ class PIDController(VehicleController):
         self.steer_Kp, self.steer_Kd = steer_Kp, steer_Kd
         self.accel_Kp, self.accel_Ki, self.accel_Kd = accel_Kp, accel_Ki, accel_Kd
 
+    # host implementation: used when the agent is not lowered to the device PID kind (a PIDAgent
+    # subclass, or one that follows a trajectory other than its entity's)
+    def _reset(self, state) -> None:
+        self.e_lon_prev = self.e_lon_int = self.e_lat_prev = 0.0
+        VehicleController._reset(self, state)
+
+    def _step(self, state, action):
+        tx, ty = action.pose[0], action.pose[1]
+        x, y, h = (state.poses[self.entity][k] for k in (0, 1, 3))
+        ch, sh = np.cos(h), np.sin(h)
+        ex, ey = tx - x, ty - y
+        e_lon, e_lat = ch * ex + sh * ey, -sh * ex + ch * ey  # error in the vehicle frame
+        v = self.speed
+        gain = 1.0 - 0.9 * (v - 5.0) / 10.0 if 5.0 < v <= 15 else (0.1 if v > 15 else 1.0)
+        dt = state.dt
+        steer = self.steer_Kp * gain * e_lat + self.steer_Kd * gain * ((e_lat - self.e_lat_prev) / dt)
+        integ = self.e_lon_int + e_lon * dt
+        accel = 0.0
+        if abs(e_lon) > 0.1:
+            accel = self.accel_Kp * e_lon + self.accel_Kd * ((e_lon - self.e_lon_prev) / dt) + self.accel_Ki * integ
+        self.e_lat_prev, self.e_lon_prev, self.e_lon_int = e_lat, e_lon, integ
+        return VehicleController._step(self, state, VehicleAction(accel, steer))
+
 
 # ------------------------------------------------------------------------------ agents
 class Agent:

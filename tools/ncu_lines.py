@@ -31,8 +31,11 @@ def main():
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp,
                           stdout=subprocess.DEVNULL)
-    cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+    # one cubin per translation unit: disassemble all of them (the kernel is matched by name below)
+    dis = ""
+    for f in sorted(os.listdir(tmp)):
+        if f.endswith(".cubin"):
+            dis += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
     demangled = subprocess.run(["cu++filt"], input=dis, capture_output=True, text=True).stdout
     want = kname.replace("(bool)0", "false").replace("(bool)1", "true")
     want = re.sub(r"\(int\)", "", want).replace("void ", "").split("(")[0]
