@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 8
+#define SG_ABI_VERSION 9
 
 /* entity slot kinds (who produces the slot's next pose each tick) */
 enum SgKind {
@@ -54,7 +54,8 @@ enum SgEntityType { SG_ETYPE_VEHICLE = 0, SG_ETYPE_PEDESTRIAN = 1, SG_ETYPE_MISC
 enum SgTerminal {
   SG_TERM_MAX_LENGTH = 1,
   SG_TERM_COLLISION = 2,
-  SG_TERM_EGO_COLLISION = 4
+  SG_TERM_EGO_COLLISION = 4,
+  SG_TERM_EGO_OFF_ROAD = 8  /* entities[0] absent or not strictly inside the driveable surface */
 };
 
 /* feature switches (bit flags in SgParams.features) */
@@ -116,6 +117,9 @@ typedef struct SgParams {
   double rss_min_safe_clearance; /* 0.1                                                   */
   /* PIDController gains, controller.py:154-161 (vehicle limits above apply to it too) */
   double pid_steer_Kp, pid_steer_Kd, pid_accel_Kp, pid_accel_Kd, pid_accel_Ki;
+  /* SocialForce boundary forces, pedestrian/social_force.py:24-29, 86-104, 190-211 */
+  double sf_boundary_repulse_U, sf_boundary_repulse_R;         /* walkable surface: 10.0, 0.2 */
+  double sf_imp_boundary_repulse_U, sf_imp_boundary_repulse_R; /* impenetrable surface: 2.0, 0.1 */
 } SgParams;
 
 /* immutable description of N scenarios x M slots */
@@ -150,6 +154,24 @@ typedef struct SgScene {
   const double* ped_speed_desired; /* [N*M] */
   const int64_t* route_off;        /* [N*M+1] */
   const double* route_xy;          /* [n_route_pts][2] */
+  /* Road-network surfaces (road_network/road_network.py:306-328: the unions of the driveable /
+     walkable / impenetrable geometries' boundaries), kept as polygon soups and shared between
+     scenarios.  Scenario n uses network rn_of[n] (-1 or rn_of == NULL: an empty network).
+     Surface k (0 driveable, 1 walkable, 2 impenetrable) of network r = polygons
+     rn_poly_off[3r+k] .. rn_poly_off[3r+k+1]; polygon q = edges rn_edge_off[q] .. rn_edge_off[q+1]
+     (every ring of the polygon, holes included: membership is the crossing parity over them);
+     edge e = rn_edges[4e .. 4e+3] = x0, y0, x1, y1.  rn_has_area[3r+k]: surface.area > 0.
+     Used by the ego_off_road terminal condition (state/state.py:401-407) and the social-force
+     boundary forces. */
+  int32_t n_networks;
+  int32_t _pad1;
+  int64_t n_rn_polys;
+  int64_t n_rn_edges;
+  const int32_t* rn_of;       /* [N] */
+  const int64_t* rn_poly_off; /* [3*n_networks+1] */
+  const int64_t* rn_edge_off; /* [n_rn_polys+1] */
+  const double* rn_edges;     /* [n_rn_edges][4] */
+  const uint8_t* rn_has_area; /* [3*n_networks] */
 } SgScene;
 
 /* one recorded ego-collision rising edge (metrics/collision.py:70-75) */

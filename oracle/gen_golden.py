@@ -362,6 +362,125 @@ def gen_ped(store, manifest):
     manifest["ped"] = {"N": cfg.N, "M": cfg.M, "T": cfg.T, "dt": cfg.dt}
 
 
+# --------------------------------------------------------------------------- road networks
+def ref_road_network(geometry):
+    """The reference's own RoadNetwork over the geometry of oracle/golden_cases.py (shim polygons)."""
+    from scenario_gym.road_network import Building, Pavement, Road, RoadNetwork
+    from shapely.geometry import LineString, Polygon
+
+    def poly(b):
+        if isinstance(b, dict):
+            return Polygon(b["exterior"], holes=b["interiors"])
+        return Polygon(b)
+
+    center = LineString([(0.0, 0.0), (1.0, 0.0)])
+    return RoadNetwork(
+        roads=[Road(f"road_{k}", poly(b), center, []) for k, b in enumerate(geometry["roads"])],
+        intersections=[],
+        pavements=[Pavement(f"pavement_{k}", poly(b), center) for k, b in enumerate(geometry["pavements"])],
+        buildings=[Building(f"building_{k}", poly(b)) for k, b in enumerate(geometry["buildings"])],
+    )
+
+
+def gen_road(store, manifest):
+    """Social-force boundary forces (buildings in the crowd) and the ego_off_road terminal condition."""
+    # (a) pedestrians among buildings
+    cfg = golden_cases.ped_cfg()
+    rn = ref_road_network(golden_cases.ROAD_PED_GEOMETRY)
+    params = SocialForceParameters(std_lon=0.0, std_lat=0.0)
+    for n in range(cfg.N):
+        sc = ref_scenario(cfg, n, road_network=rn)
+        peds = {}
+
+        def create_agent(scenario, entity, n=n, peds=peds):
+            m = scenario.entities.index(entity)
+            if cfg.kind[n, m] == abi.KIND_PEDESTRIAN:
+                route = [np.array([cfg.x0[n, m], cfg.y0[n, m]]), np.array(cfg.goal[n, m])]
+                a = PedestrianAgent(entity, route, float(cfg.speed_desired[n, m]), SocialForce(params))
+                peds[entity] = a
+                return a
+            return ref.agent._create_agent(scenario, entity)
+
+        rec = Recorder(ped_agents=peds)
+        gym = ScenarioGym(timestep=cfg.dt, metrics=[EgoAvgSpeed(), rec])
+        gym.set_scenario(sc, create_agent=create_agent)
+        out, m = run_gym(gym, rec, dec=4)
+        out["t_end"] = np.float64(gym.state.t)
+        flat(f"road_ped/{n}/out", out, store)
+        print("road_ped", n, rec.tick, repr(float(gym.state.t)), "pairs", len(rec.pairs))
+    # (b) vehicles leaving the driveable surface
+    cfg = golden_cases.veh_cfg()
+    rn = ref_road_network(golden_cases.ROAD_VEH_GEOMETRY)
+    ticks = []
+    for n in range(cfg.N):
+        sc = ref_scenario(cfg, n, road_network=rn)
+        acts = cfg.actions.reshape(cfg.T, 2, cfg.N, cfg.M)
+        rec = Recorder()
+        gym = ScenarioGym(timestep=cfg.dt, metrics=[EgoAvgSpeed(), EgoMaxSpeed(), EgoDistanceTravelled(), rec],
+                          terminal_conditions=["max_length", "ego_off_road"])
+
+        def create_agent(scenario, entity, n=n, acts=acts):
+            m = scenario.entities.index(entity)
+            return TableVehicleAgent(entity, acts[:, :, n, m])
+
+        gym.set_scenario(sc, create_agent=create_agent)
+        out, m = run_gym(gym, rec, dec=8)
+        out["t_end"] = np.float64(gym.state.t)
+        flat(f"road_veh/{n}/out", out, store)
+        ticks.append(rec.tick)
+        print("road_veh", n, rec.tick, repr(float(gym.state.t)))
+    # (c) the reference's own test scenarios with their JSON road networks and ego_off_road
+    import xml.etree.ElementTree as ET
+
+    from scenario_gym.road_network import RoadNetwork as RefRoadNetwork
+
+    xticks = {}
+    for path in sorted(glob.glob(os.path.join(SCEN_DIR, "*.xosc"))):
+        name = os.path.splitext(os.path.basename(path))[0]
+        xroot = ET.parse(path).getroot()
+        node = xroot.find("RoadNetwork/SceneGraphFile")
+        if node is None:
+            node = xroot.find("RoadNetwork/LogicFile")
+        if node is None:
+            continue
+        rn_file = os.path.join(os.path.dirname(path), node.attrib["filepath"])
+        if os.path.splitext(rn_file)[1] == "":
+            rn_file += ".json"
+        if not os.path.exists(rn_file):
+            continue
+        sc = import_scenario(path)
+        sc.road_network = RefRoadNetwork.create_from_json(rn_file)
+        stem = os.path.splitext(os.path.basename(rn_file))[0].replace(" ", "_")
+        store[f"road_xosc/{name}/network"] = np.array(stem)
+        if f"road_net/{stem}/n" not in store:  # the network's surfaces as the reference builds them
+            rn_ = sc.road_network
+            counts = []
+            for tag_, surf in (("d", rn_.driveable_surface), ("w", rn_.walkable_surface), ("i", rn_.impenetrable_surface)):
+                counts.append(len(surf.geoms))
+                for k_, g_ in enumerate(surf.geoms):
+                    rings_ = g_.rings()
+                    store[f"road_net/{stem}/{tag_}{k_}/ext"] = np.asarray(rings_[0], np.float64)
+                    for j_, h_ in enumerate(rings_[1:]):
+                        store[f"road_net/{stem}/{tag_}{k_}/hole{j_}"] = np.asarray(h_, np.float64)
+            store[f"road_net/{stem}/n"] = np.array(counts, np.int64)
+        gym = ScenarioGym(metrics=[EgoAvgSpeed(), EgoDistanceTravelled()],
+                          terminal_conditions=["max_length", "ego_off_road"])
+        gym.set_scenario(sc)
+        ticks_n = 0
+        gym.reset_scenario()
+        while not gym.state.is_done:
+            gym.step()
+            ticks_n += 1
+        m = gym.get_metrics()
+        store[f"road_xosc/{name}/n_ticks"] = np.int64(ticks_n)
+        store[f"road_xosc/{name}/t_end"] = np.float64(gym.state.t)
+        store[f"road_xosc/{name}/ego_avg_speed"] = np.float64(m["ego_avg_speed"])
+        store[f"road_xosc/{name}/ego_distance_travelled"] = np.float64(m["ego_distance_travelled"])
+        xticks[name] = ticks_n
+        print("road_xosc", name[:8], ticks_n, repr(float(gym.state.t)))
+    manifest["road"] = {"ped": {"N": golden_cases.ped_cfg().N}, "veh_ticks": ticks, "xosc_ticks": xticks}
+
+
 # --------------------------------------------------------------------------- PID
 def gen_pid(store, manifest):
     """PIDAgent / PIDController (agent.py:131-148, controller.py:143-258) on two test scenarios."""
@@ -532,6 +651,10 @@ def main():
         store = {}
         gen_pid(store, manifest)
         np.savez_compressed(os.path.join(GOLDEN, "pid.npz"), **store)
+    if want("road"):
+        store = {}
+        gen_road(store, manifest)
+        np.savez_compressed(os.path.join(GOLDEN, "road.npz"), **store)
     if want("future"):
         store = {}
         gen_future(store, manifest)

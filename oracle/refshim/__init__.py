@@ -98,8 +98,10 @@ def _make_shapely(fullname: str) -> types.ModuleType:
             Point=ms.Point,
             Polygon=ms.Polygon,
             LineString=ms.LineString,
+            LinearRing=ms.LinearRing,
             MultiPolygon=ms.MultiPolygon,
         ),
+        "shapely.validation": dict(make_valid=ms.make_valid),
         "shapely.geometry.base": dict(BaseGeometry=ms.BaseGeometry),
         "shapely.strtree": dict(STRtree=ms.STRtree),
         "shapely.vectorized": dict(contains=ms.contains),

@@ -182,15 +182,73 @@ class LineString(BaseGeometry):
         return best_s
 
 
-class Polygon(BaseGeometry):
-    """Simple polygon without holes (only convex shells are needed)."""
+def _open_ring(coords) -> np.ndarray:
+    if isinstance(coords, LinearRing):
+        return coords._pts
+    pts = np.array([tuple(map(float, c))[:2] for c in coords], dtype=np.float64).reshape(-1, 2)
+    if len(pts) > 1 and (pts[0] == pts[-1]).all():
+        pts = pts[:-1]
+    return pts
 
-    def __init__(self, shell: Iterable):
-        pts = np.array([tuple(map(float, c))[:2] for c in shell], dtype=np.float64)
-        if len(pts) > 1 and (pts[0] == pts[-1]).all():
-            pts = pts[:-1]
-        self._pts = pts
+
+class LinearRing(BaseGeometry):
+    def __init__(self, coords: Iterable):
+        self._pts = _open_ring(coords)
+
+    @property
+    def coords(self):
+        return _Coords(np.concatenate([self._pts, self._pts[:1]], axis=0))
+
+
+def _ring_side(pts: np.ndarray, px: float, py: float) -> int:
+    """+1 strictly inside the ring, 0 on it, -1 outside: crossing parity with exact orientation signs."""
+    inside = False
+    n = len(pts)
+    for k in range(n):
+        ax, ay = pts[k]
+        bx, by = pts[(k + 1) % n]
+        straddles = (ay > py) != (by > py)
+        in_box = min(ax, bx) <= px <= max(ax, bx) and min(ay, by) <= py <= max(ay, by)
+        if not straddles and not in_box:
+            continue
+        o = orient_sign(ax, ay, bx, by, px, py)
+        if o == 0 and in_box:
+            return 0
+        if straddles and ((o > 0) == (by > ay)):
+            inside = not inside
+    return 1 if inside else -1
+
+
+class Polygon(BaseGeometry):
+    """Polygon with optional holes.  Box-to-box predicates assume convex shells; point membership
+    (`contains`, road-network surfaces) is general."""
+
+    is_valid = True
+
+    def __init__(self, shell: Iterable, holes: Iterable = None):
+        self._pts = _open_ring(shell)
+        self._holes = [_open_ring(h) for h in (holes or [])]
         self._orient = None
+
+    @property
+    def interiors(self):
+        return [LinearRing(h) for h in self._holes]
+
+    def point_side(self, px: float, py: float) -> int:
+        """+1 interior, 0 boundary, -1 exterior."""
+        s = _ring_side(self._pts, px, py)
+        if s <= 0:
+            return s
+        for h in self._holes:
+            hs = _ring_side(h, px, py)
+            if hs == 0:
+                return 0
+            if hs > 0:
+                return -1
+        return 1
+
+    def rings(self):
+        return [self._pts] + self._holes
 
     @property
     def exterior(self):
@@ -203,8 +261,11 @@ class Polygon(BaseGeometry):
 
     @property
     def area(self) -> float:
-        x, y = self._pts[:, 0], self._pts[:, 1]
-        return 0.5 * abs(float(np.dot(x, np.roll(y, -1)) - np.dot(np.roll(x, -1), y)))
+        def shoelace(p):
+            x, y = p[:, 0], p[:, 1]
+            return 0.5 * abs(float(np.dot(x, np.roll(y, -1)) - np.dot(np.roll(x, -1), y)))
+
+        return shoelace(self._pts) - sum(shoelace(h) for h in getattr(self, "_holes", []))
 
     @property
     def centroid(self) -> Point:
@@ -278,9 +339,9 @@ class Polygon(BaseGeometry):
         raise NotImplementedError(type(other))
 
     def contains(self, other) -> bool:
-        """Strict interior membership for points (convex polygon)."""
+        """Strict interior membership for points."""
         if isinstance(other, Point):
-            return bool(contains(self, np.array([other.x]), np.array([other.y]))[0])
+            return self.point_side(float(other.x), float(other.y)) > 0
         raise NotImplementedError(type(other))
 
     def intersection(self, other):
@@ -362,8 +423,46 @@ class STRtree:
         return np.array(hits, dtype=np.int64)
 
 
-def nearest_points(a, b):  # pragma: no cover - needs a non-empty road network
-    raise NotImplementedError("nearest_points is not restated (empty road networks only)")
+def nearest_points(a, b):
+    """
+    ``shapely.ops.nearest_points(area, Point)`` (reference pedestrian/social_force.py:204): the point
+    itself when it lies in the closed area, else the closest point on the rings of its polygons
+    (GEOS LineSegment::closestPoint: the projection for a projection factor in (0, 1), else the closer
+    end point; the first strictly closer segment wins).
+    """
+    if not isinstance(b, Point):
+        raise NotImplementedError(type(b))
+    px, py = float(b.x), float(b.y)
+    polys = a.geoms if isinstance(a, MultiPolygon) else [a]
+    if any(g.point_side(px, py) >= 0 for g in polys):
+        return Point(px, py), b
+    best, best_d2 = (px, py), float("inf")
+    for g in polys:
+        for ring in g.rings():
+            n = len(ring)
+            for k in range(n):
+                ax, ay = map(float, ring[k])
+                bx, by = map(float, ring[(k + 1) % n])
+                dx, dy = bx - ax, by - ay
+                len2 = dx * dx + dy * dy
+                cx, cy = ax, ay
+                if len2 > 0.0:
+                    f = ((px - ax) * dx + (py - ay) * dy) / len2
+                    if 0.0 < f < 1.0:
+                        cx, cy = ax + f * dx, ay + f * dy
+                    else:
+                        da = (px - ax) * (px - ax) + (py - ay) * (py - ay)
+                        db = (px - bx) * (px - bx) + (py - by) * (py - by)
+                        if db < da:
+                            cx, cy = bx, by
+                d2 = (px - cx) * (px - cx) + (py - cy) * (py - cy)
+                if d2 < best_d2:
+                    best_d2, best = d2, (cx, cy)
+    return Point(*best), b
+
+
+def make_valid(geom):
+    return geom
 
 
 def unary_union(geoms):

@@ -81,6 +81,9 @@ def scene_struct(scene: PackedScene) -> abi.SgScene:
     s.n_traj_rows = scene.traj_rows.shape[0]
     s.n_union_rows = scene.union_t.shape[0]
     s.n_route_pts = scene.route_xy.shape[0]
+    s.n_networks = scene.n_networks
+    s.n_rn_polys = len(scene.rn_edge_off) - 1
+    s.n_rn_edges = scene.rn_edges.shape[0]
     s.kind_mask = scene.kind_mask()
     for k, a in scene.arrays().items():
         assert a.flags["C_CONTIGUOUS"], k

@@ -81,6 +81,10 @@ void sgo_default_params(SgParams* p) {
   p->pid_accel_Kp = 0.3753;
   p->pid_accel_Kd = 1.8970;
   p->pid_accel_Ki = 0.0204;
+  p->sf_boundary_repulse_U = 10.0; /* pedestrian/social_force.py:26-29 */
+  p->sf_boundary_repulse_R = 0.2;
+  p->sf_imp_boundary_repulse_U = 2.0;
+  p->sf_imp_boundary_repulse_R = 0.1;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -667,6 +671,79 @@ static double sight_weight(const SgParams* p, const double F[2], const double vi
   return p->sf_sight_weight;
 }
 
+/* ---- road-network surfaces (SgScene.rn_*): restated Shapely semantics.  The reference builds
+   driveable / walkable / impenetrable_surface with shapely.ops.unary_union
+   (road_network/road_network.py:306-328) and asks `surface.contains(Point)` (state/state.py:401-407,
+   pedestrian/social_force.py:87,96) and `nearest_points(surface, Point)` (social_force.py:204).
+   Restated on the polygon soup: contained = strictly inside one member polygon (crossing parity over
+   all of its rings with exact orientation signs; on a ring = boundary); nearest point = the point
+   itself when it lies in the closed surface, else the closest point on the rings
+   (GEOS LineSegment::closestPoint).  GEOS itself is absent: parity unpinned for points exactly on an
+   edge shared by two member polygons (the dissolved union has no edge there). */
+static int polygon_side(const double* edges, int64_t e0, int64_t e1, double px, double py) {
+  int inside = 0;
+  for (int64_t e = e0; e < e1; ++e) {
+    double ax = edges[4 * e], ay = edges[4 * e + 1], bx = edges[4 * e + 2], by = edges[4 * e + 3];
+    int straddles = (ay > py) != (by > py);
+    int in_box = px >= fmin(ax, bx) && px <= fmax(ax, bx) && py >= fmin(ay, by) && py <= fmax(ay, by);
+    if (!straddles && !in_box) continue;
+    int o = orient_sign(ax, ay, bx, by, px, py);
+    if (o == 0 && in_box) return 0;
+    if (straddles && ((o > 0) == (by > ay))) inside = !inside;
+  }
+  return inside ? 1 : -1;
+}
+static int surface_network(const SgScene* sc, int n) {
+  if (!sc->rn_of || sc->n_networks <= 0) return -1;
+  return sc->rn_of[n];
+}
+static int surface_has_area(const SgScene* sc, int n, int k) {
+  int r = surface_network(sc, n);
+  return r >= 0 && sc->rn_has_area[3 * r + k] != 0;
+}
+static int surface_contains(const SgScene* sc, int n, int k, double px, double py) {
+  int r = surface_network(sc, n);
+  if (r < 0) return 0;
+  for (int64_t q = sc->rn_poly_off[3 * r + k]; q < sc->rn_poly_off[3 * r + k + 1]; ++q)
+    if (polygon_side(sc->rn_edges, sc->rn_edge_off[q], sc->rn_edge_off[q + 1], px, py) > 0) return 1;
+  return 0;
+}
+static void surface_nearest(const SgScene* sc, int n, int k, double px, double py, double out[2]) {
+  int r = surface_network(sc, n);
+  out[0] = px; out[1] = py;
+  int64_t q0 = sc->rn_poly_off[3 * r + k], q1 = sc->rn_poly_off[3 * r + k + 1];
+  for (int64_t q = q0; q < q1; ++q)
+    if (polygon_side(sc->rn_edges, sc->rn_edge_off[q], sc->rn_edge_off[q + 1], px, py) >= 0) return;
+  double best = INFINITY;
+  for (int64_t e = sc->rn_edge_off[q0]; e < sc->rn_edge_off[q1]; ++e) {
+    const double* E = sc->rn_edges + 4 * e;
+    double ax = E[0], ay = E[1], bx = E[2], by = E[3];
+    double dx = bx - ax, dy = by - ay, len2 = dx * dx + dy * dy, cx = ax, cy = ay;
+    if (len2 > 0.0) {
+      double f = ((px - ax) * dx + (py - ay) * dy) / len2;
+      if (f > 0.0 && f < 1.0) { cx = ax + f * dx; cy = ay + f * dy; }
+      else {
+        double da = (px - ax) * (px - ax) + (py - ay) * (py - ay);
+        double db = (px - bx) * (px - bx) + (py - by) * (py - by);
+        if (db < da) { cx = bx; cy = by; }
+      }
+    }
+    double d2 = (px - cx) * (px - cx) + (py - cy) * (py - cy);
+    if (d2 < best) { best = d2; out[0] = cx; out[1] = cy; }
+  }
+}
+/* SocialForce._force_boundary, pedestrian/social_force.py:190-211 */
+static void boundary_force(const SgScene* sc, int n, int k, double px, double py, double U, double R, double out[2]) {
+  double c[2];
+  surface_nearest(sc, n, k, px, py, c);
+  double r0 = px - c[0], r1 = py - c[1];
+  double rn = sqrt(r0 * r0 + r1 * r1);
+  double u0 = r0 / (rn + 0.0000000001), u1 = r1 / (rn + 0.0000000001);
+  double ex = exp(-rn / R);
+  out[0] = U / R * u0 * ex;
+  out[1] = U / R * u1 * ex;
+}
+
 static void pedestrian_step(const SgScene* sc, const SgParams* p, SgState* st, int n, int s,
                             double next_t, double out[6]) {
   int64_t nm = NM, i = IDX(n, s);
@@ -731,7 +808,19 @@ static void pedestrian_step(const SgScene* sc, const SgParams* p, SgState* st, i
         F[0] += Frep[0]; F[1] += Frep[1];
       }
     }
-    /* empty road network: boundary forces skipped (:86-104). noise std = 0 (:106-108) */
+    /* boundary forces, social_force.py:83-104 (skipped for surfaces without area, e.g. an empty network) */
+    if (surface_has_area(sc, n, 1) && surface_contains(sc, n, 1, pose[0], pose[1])) {
+      double fb[2];
+      boundary_force(sc, n, 1, pose[0], pose[1], p->sf_boundary_repulse_U, p->sf_boundary_repulse_R, fb);
+      F[0] += fb[0]; F[1] += fb[1];
+    }
+    if (surface_has_area(sc, n, 2)) {
+      double sign = 1 - 2 * surface_contains(sc, n, 2, pose[0], pose[1]);
+      double fb[2];
+      boundary_force(sc, n, 2, pose[0], pose[1], p->sf_imp_boundary_repulse_U, p->sf_imp_boundary_repulse_R, fb);
+      F[0] += sign * fb[0]; F[1] += sign * fb[1];
+    }
+    /* noise std = 0 (:106-108) */
     speed = py_min(norm2(F[0], F[1]) + p->sf_bias_lon, speed_desired * p->sf_max_speed_factor);
     heading = atan2(F[1], F[0]) + p->sf_bias_lat;
     st->force[i] = F[0];
@@ -892,6 +981,10 @@ static void tick_scenario(const SgScene* sc, const SgParams* p, SgState* st, con
   if ((p->terminal & SG_TERM_MAX_LENGTH) && (st->t[n] + dt > sc->length[n])) done = 1;
   if ((p->terminal & SG_TERM_COLLISION) && any_coll) done = 1;
   if ((p->terminal & SG_TERM_EGO_COLLISION) && first_hit) done = 1; /* collisions()[entities[0]] */
+  if (p->terminal & SG_TERM_EGO_OFF_ROAD) { /* state.py:401-407 */
+    int64_t fi = IDX(n, sc->first_slot[n]);
+    if (!(st->present[fi] && surface_contains(sc, n, 0, st->pose[fi], st->pose[nm + fi]))) done = 1;
+  }
   st->done[n] = (uint8_t)done;
   /* metrics, scenario_gym.py:251-252 ; metrics/trajectory.py:20-24, 39-42, 58-60 */
   if (p->features & SG_FEAT_EGO_METRICS) {
@@ -1063,6 +1156,9 @@ int sgo_position_at_t(const double* rows, int64_t K, double t, int mode, double*
   return position_at_t(rows, K, t, mode, out);
 }
 void sgo_velocity_at_t(const double* rows, int64_t K, double t, double* out) { velocity_at_t(rows, K, t, out); }
+int sgo_polygon_side(const double* edges, int64_t n_edges, double px, double py) {
+  return polygon_side(edges, 0, n_edges, px, py);
+}
 int sgo_in_buffer(double x, double y, double r, double qx, double qy) {
   ngon_init();
   return in_buffer(x, y, r, qx, qy);

@@ -16,6 +16,7 @@ from .plugins import (RSS, Action, ActionTableAgent, Agent, CollisionMetric, Col
                       ReplayTrajectoryController, RSSDistances, RSSParameters, Sensor,
                       SingleEntityObservation, SocialForce, SocialForceParameters, StateCallback,
                       TeleportAction, VehicleAction, VehicleController)
+from .road_network import RoadNetwork
 from .scenario import Scenario
 from .state import State
 from .trajectory import Trajectory

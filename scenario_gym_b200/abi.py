@@ -11,14 +11,14 @@ import math
 import os
 from typing import Dict, Optional
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # SgKind
 KIND_EMPTY, KIND_REPLAY, KIND_AGENT_REPLAY, KIND_VEHICLE, KIND_PEDESTRIAN, KIND_HOST, KIND_PID = range(7)
 # SgEntityType
 ETYPE_VEHICLE, ETYPE_PEDESTRIAN, ETYPE_MISC = range(3)
 # SgTerminal
-TERM_MAX_LENGTH, TERM_COLLISION, TERM_EGO_COLLISION = 1, 2, 4
+TERM_MAX_LENGTH, TERM_COLLISION, TERM_EGO_COLLISION, TERM_EGO_OFF_ROAD = 1, 2, 4, 8
 # SgFeature
 FEAT_COLLISIONS, FEAT_EGO_METRICS, FEAT_RSS, FEAT_COLL_MATRIX, FEAT_NO_GRID, FEAT_SEQUENTIAL = 1, 2, 4, 8, 16, 32
 # SgRssRecord
@@ -71,6 +71,10 @@ class SgParams(C.Structure):
         ("pid_accel_Kp", C.c_double),
         ("pid_accel_Kd", C.c_double),
         ("pid_accel_Ki", C.c_double),
+        ("sf_boundary_repulse_U", C.c_double),
+        ("sf_boundary_repulse_R", C.c_double),
+        ("sf_imp_boundary_repulse_U", C.c_double),
+        ("sf_imp_boundary_repulse_R", C.c_double),
     ]
 
 
@@ -98,6 +102,15 @@ class SgScene(C.Structure):
         ("ped_speed_desired", _p),
         ("route_off", _p),
         ("route_xy", _p),
+        ("n_networks", C.c_int32),
+        ("_pad1", C.c_int32),
+        ("n_rn_polys", C.c_int64),
+        ("n_rn_edges", C.c_int64),
+        ("rn_of", _p),
+        ("rn_poly_off", _p),
+        ("rn_edge_off", _p),
+        ("rn_edges", _p),
+        ("rn_has_area", _p),
     ]
 
 
@@ -235,6 +248,7 @@ STATE_FIELDS = [
 SCENE_FIELDS = [
     "kind", "etype", "box", "traj_off", "traj_rows", "union_off", "union_t", "union_x",
     "t0", "length", "ego_slot", "first_slot", "ped_speed_desired", "route_off", "route_xy",
+    "rn_of", "rn_poly_off", "rn_edge_off", "rn_edges", "rn_has_area",
 ]
 
 
@@ -269,6 +283,8 @@ def default_params() -> SgParams:
     p.rss_min_safe_clearance = 0.1
     p.pid_steer_Kp, p.pid_steer_Kd = 0.03054, 1.5709
     p.pid_accel_Kp, p.pid_accel_Kd, p.pid_accel_Ki = 0.3753, 1.8970, 0.0204
+    p.sf_boundary_repulse_U, p.sf_boundary_repulse_R = 10.0, 0.2
+    p.sf_imp_boundary_repulse_U, p.sf_imp_boundary_repulse_R = 2.0, 0.1
     return p
 
 

@@ -52,7 +52,9 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
   const bool ped = sc->route_off != nullptr && sc->n_route_pts > 0;
   const bool rss = (p->features & SG_FEAT_RSS) != 0;
   const uint32_t veh_bits = (1u << SG_KIND_VEHICLE), ok_bits = veh_bits | (1u << SG_KIND_EMPTY);
-  const bool veh_only = (sc->kind_mask & veh_bits) && !(sc->kind_mask & ~ok_bits);
+  // the ego_off_road terminal condition and the boundary forces live in the general kernel only
+  const bool roads = (p->terminal & SG_TERM_EGO_OFF_ROAD) != 0;
+  const bool veh_only = (sc->kind_mask & veh_bits) && !(sc->kind_mask & ~ok_bits) && !roads;
   const bool grid_ok = ped && p->ped_distance_threshold > 0.0 && p->ped_distance_threshold < 1.0e6 &&
                        !(p->features & SG_FEAT_NO_GRID);
   GroupLayout L = make_layout(sc->n_slots, ped, rss, veh_only, grid_ok);
@@ -77,7 +79,7 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
   const uint32_t replay_bits = (1u << SG_KIND_EMPTY) | (1u << SG_KIND_REPLAY) | (1u << SG_KIND_AGENT_REPLAY);
   const bool replay_only = sc->kind_mask != 0 && !(sc->kind_mask & ~replay_bits) &&
                            (sc->kind_mask & ~(1u << SG_KIND_EMPTY));
-  if (replay_only && !rss && !ped && sc->n_slots <= 32 && st->trace_cap == 0 && !inp.step_done &&
+  if (replay_only && !roads && !rss && !ped && sc->n_slots <= 32 && st->trace_cap == 0 && !inp.step_done &&
       !inp.host_present && p->timestep > 0.0 && (n_ticks < 0 || n_ticks >= 8) &&
       !(p->features & SG_FEAT_SEQUENTIAL)) {
     err = sgi_launch_replay(s, *sc, *p, *st, n_ticks);
@@ -86,7 +88,7 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
   }
   // crowd scenes (more than 256 slots of pedestrians / replayed agents): the two-scenarios-per-SM kernel
   const uint32_t crowd_bits = (1u << SG_KIND_EMPTY) | (1u << SG_KIND_PEDESTRIAN) | (1u << SG_KIND_AGENT_REPLAY);
-  if (grid_ok && !rss && sc->n_slots > SG_THREADS && (sc->kind_mask & (1u << SG_KIND_PEDESTRIAN)) &&
+  if (grid_ok && !rss && !roads && sc->n_networks <= 0 && sc->n_slots > SG_THREADS && (sc->kind_mask & (1u << SG_KIND_PEDESTRIAN)) &&
       !(sc->kind_mask & ~crowd_bits) && st->trace_cap == 0 && !inp.host_present) {
     err = sgi_launch_crowd(s, *sc, *p, *st, inp, n_ticks);
     if (err != cudaSuccess) return set_err("sg_crowd_kernel launch", err);
@@ -161,6 +163,10 @@ void sg_default_params(SgParams* p) {
   p->pid_accel_Kp = 0.3753;
   p->pid_accel_Kd = 1.8970;
   p->pid_accel_Ki = 0.0204;
+  p->sf_boundary_repulse_U = 10.0; /* pedestrian/social_force.py:26-29 */
+  p->sf_boundary_repulse_R = 0.2;
+  p->sf_imp_boundary_repulse_U = 2.0;
+  p->sf_imp_boundary_repulse_R = 0.1;
 }
 
 int sg_reset(const SgScene* scene, const SgParams* params, SgState* state, int device, void* stream) {
@@ -243,12 +249,19 @@ static int scene_copy_list(const SgScene* h, const SgScene* d, CopyItem* items) 
   ITEM(ped_speed_desired, NM * 8);
   ITEM(route_off, (NM + 1) * 8);
   ITEM(route_xy, h->n_route_pts * 2 * 8);
+  if (h->n_networks > 0) {
+    ITEM(rn_of, N * 4);
+    ITEM(rn_poly_off, (3 * (int64_t)h->n_networks + 1) * 8);
+    ITEM(rn_edge_off, (h->n_rn_polys + 1) * 8);
+    ITEM(rn_edges, h->n_rn_edges * 4 * 8);
+    ITEM(rn_has_area, 3 * (int64_t)h->n_networks);
+  }
 #undef ITEM
   return k;
 }
 
 int64_t sg_host_h2d_bytes(const SgScene* h, const SgInputs* in, int copy_static) {
-  CopyItem items[16];
+  CopyItem items[24];
   SgScene dummy = *h;
   int k = scene_copy_list(h, &dummy, items);
   int64_t total = 0;
@@ -299,7 +312,7 @@ int sg_rollout_host(const SgScene* hs, const SgScene* ds, const SgParams* params
   if (err != cudaSuccess) return set_err("cudaSetDevice", err);
   cudaStream_t s = (cudaStream_t)stream;
   if (copy_static) {
-    CopyItem items[16];
+    CopyItem items[24];
     const int k = scene_copy_list(hs, ds, items);
     for (int q = 0; q < k; ++q) {
       if (!items[q].src || !items[q].bytes) continue;

@@ -236,20 +236,33 @@ SG_DEV void sincos_fast(double x, double& sn, double& cs) {
   cs = ((k + 1) & 2) ? -c0 : c0;
 }
 
-// strict interior of Point(x, y).buffer(r): GEOS 64-gon (reference state/state.py:352-372)
+// strict interior of Point(x, y).buffer(r): GEOS 64-gon (reference state/state.py:352-372).
+// Between the inscribed and the circumscribed circle the polygon decides: the query point lies in
+// the angular sector of one edge, and only that edge (and, against rounding of the sector index, its
+// two neighbours) can have the point on its outer side -- every other edge's line is further than
+// 0.009 r away from any point of the band in this sector.  The three edges are tested with the exact
+// orientation sign, so the answer equals the all-edges test.
+static __device__ __noinline__ bool in_buffer_band(double x, double y, double r, double qx, double qy) {
+  const double a = atan2(-(qy - y), qx - x);  // clockwise angle: vertex k sits at k * 2 pi / 64
+  double kk = a * (64.0 / (2.0 * M_PI));
+  if (kk < 0.0) kk += 64.0;
+  const int k0 = (int)kk;
+#pragma unroll 1
+  for (int j = -1; j <= 1; ++j) {
+    const int k = (k0 + j) & 63, k1 = (k + 1) & 63;
+    const double ax = x + r * c_ngon[k][0], ay = y + r * c_ngon[k][1];
+    const double bx = x + r * c_ngon[k1][0], by = y + r * c_ngon[k1][1];
+    if (orient_sign(ax, ay, bx, by, qx, qy) >= 0) return false;
+  }
+  return true;
+}
 SG_DEV bool in_buffer(double x, double y, double r, double qx, double qy) {
   const double dx = qx - x, dy = qy - y, d2 = dx * dx + dy * dy;
   const double rin = r * 0.99879545620517241 * (1.0 - 1e-9);  // cos(pi/64): inscribed circle
   if (d2 < rin * rin) return true;
   const double rout = r * (1.0 + 1e-9);
   if (d2 > rout * rout) return false;
-  for (int k = 0; k < 64; ++k) {
-    const int k1 = (k + 1) & 63;
-    const double ax = x + r * c_ngon[k][0], ay = y + r * c_ngon[k][1];
-    const double bx = x + r * c_ngon[k1][0], by = y + r * c_ngon[k1][1];
-    if (orient_sign(ax, ay, bx, by, qx, qy) >= 0) return false;
-  }
-  return true;
+  return in_buffer_band(x, y, r, qx, qy);
 }
 
 // closed-interval overlap of two conservative AABBs as one predicate chain; sets bit `bit`
@@ -622,6 +635,19 @@ SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c, 
     }
   }
   if (!is_ped) return;
+  if (walking && sc.n_networks > 0) {  // pedestrian/social_force.py:83-104
+    if (surface_has_area(sc, c.n, 1) && surface_contains(sc, c.n, 1, pose[0], pose[1])) {
+      double fb[2];
+      boundary_force(sc, c.n, 1, pose[0], pose[1], p.sf_boundary_repulse_U, p.sf_boundary_repulse_R, fb);
+      F0 += fb[0]; F1 += fb[1];
+    }
+    if (surface_has_area(sc, c.n, 2)) {
+      const double sign = 1 - 2 * (surface_contains(sc, c.n, 2, pose[0], pose[1]) ? 1 : 0);
+      double fb[2];
+      boundary_force(sc, c.n, 2, pose[0], pose[1], p.sf_imp_boundary_repulse_U, p.sf_imp_boundary_repulse_R, fb);
+      F0 += sign * fb[0]; F1 += sign * fb[1];
+    }
+  }
   double speed, heading;
   if (walking) {
     speed = py_min(norm2(F0, F1) + p.sf_bias_lon, speed_desired * p.sf_max_speed_factor);
@@ -1139,34 +1165,53 @@ static __device__ __noinline__ void commit_pair(PairSink k, int a, int b) {
   }
 }
 
+// Conservative separating-axis classification of two boxes from their fp64 corners (ring order of
+// entity/base.py:117-136: corner1 - corner0 runs along the box's length, corner0 - corner3 along its
+// width): +1 they intersect, -1 they are disjoint, 0 too close to call -- the exact predicate decides.
+// Rectangles are disjoint iff one of their four edge directions separates them.  Every gap
+//   |D.a| - (|E1A.a| + |E2A.a| + |E1B.a| + |E2B.a|)      (D = 2 x centre difference, E = full edges)
+// is compared with a tolerance of 1e-9 relative to the coordinates involved, seven orders of
+// magnitude above its rounding error, so a +-1 answer is the exact closed-set answer for these
+// corners.  Branch-free, ~130 flops: the exact edge tests cost ~8x that and diverge.
+SG_DEV int sat_classify(const double* A, const double* B) {
+  const double e1ax = A[2] - A[0], e1ay = A[3] - A[1], e2ax = A[0] - A[6], e2ay = A[1] - A[7];
+  const double e1bx = B[2] - B[0], e1by = B[3] - B[1], e2bx = B[0] - B[6], e2by = B[1] - B[7];
+  const double dx = (B[0] + B[4]) - (A[0] + A[4]), dy = (B[1] + B[5]) - (A[1] + A[5]);
+  const double scale = fabs(A[0]) + fabs(A[1]) + fabs(B[0]) + fabs(B[1]) + fabs(e1ax) + fabs(e1ay) + fabs(e2ax) +
+                       fabs(e2ay) + fabs(e1bx) + fabs(e1by) + fabs(e2bx) + fabs(e2by);
+  const double rel = 1e-9 * scale;
+  bool apart = false, inside = true;
+#define SG_SAT_AXIS(ax, ay)                                                                             \
+  {                                                                                                     \
+    const double gap = fabs(dx * (ax) + dy * (ay)) -                                                    \
+                       (fabs(e1ax * (ax) + e1ay * (ay)) + fabs(e2ax * (ax) + e2ay * (ay)) +             \
+                        fabs(e1bx * (ax) + e1by * (ay)) + fabs(e2bx * (ax) + e2by * (ay)));             \
+    const double tol = rel * (fabs(ax) + fabs(ay));                                                     \
+    apart = apart || gap > tol;                                                                         \
+    inside = inside && gap < -tol;                                                                      \
+  }
+  SG_SAT_AXIS(e1ax, e1ay)
+  SG_SAT_AXIS(e2ax, e2ay)
+  SG_SAT_AXIS(e1bx, e1by)
+  SG_SAT_AXIS(e2bx, e2by)
+#undef SG_SAT_AXIS
+  if (!(fabs(dx) + fabs(dy) > rel)) return 0;  // (nearly) coincident boxes: `g != g_prime` is the exact path's call
+  return apart ? -1 : (inside ? 1 : 0);
+}
+
 SG_DEV void record_pair(const PairSink& k, unsigned corners_sh, const int8_t* orient, int G, int a, int b) {
   if (pair_collides(corners_sh, orient, G, a, b)) commit_pair(k, a, b);
 }
 
-// Warp-cooperative exact narrow phase for one pair: the 32 lanes evaluate the 8 edges x 4 corners
-// orientation signs of the separating-edge test at once (lane = 4*edge + corner; edges 0-3 belong
-// to quad a and are tested against b's corners, edges 4-7 the other way round), a ballot combines
-// them.  ~16x lower latency than one lane walking the edges, which matters because the rest of
-// the scenario waits for the narrow phase.  All 32 lanes must call it.
-SG_DEV bool pair_collides_warp(unsigned csh, const int8_t* orient, int G, int a, int b) {
-  const unsigned lane = threadIdx.x & 31u, qs = (unsigned)G * 8u;
-  const unsigned e = lane >> 2, m = lane & 3u;
-  const bool second = e >= 4;
-  const unsigned pe = csh + (unsigned)(second ? b : a) * 8u;  // quad owning the edge
-  const unsigned pp = csh + (unsigned)(second ? a : b) * 8u;  // quad owning the corner
-  const int o = orient[second ? b : a];
-  const int k = (int)(e & 3u);
-  const int sg = orient_sign(qx(pe, qs, k), qy(pe, qs, k), qx(pe, qs, k + 1), qy(pe, qs, k + 1),
-                             qx(pp, qs, (int)m), qy(pp, qs, (int)m));
-  const unsigned outside = __ballot_sync(0xffffffffu, sg * o < 0);
-  // `g != g_prime` (reference utils.py:58): lanes 0-7 compare one coordinate each
-  const bool diff = lane < 8 ? (lds_f64(csh + (unsigned)a * 8u + lane * qs) != lds_f64(csh + (unsigned)b * 8u + lane * qs))
-                             : false;
-  const unsigned differs = __ballot_sync(0xffffffffu, diff);
-  unsigned full = outside & (outside >> 1);
-  full &= full >> 2;  // bit 4j set iff lanes 4j..4j+3 all reported strictly outside
-  const bool separated = (full & 0x11111111u) != 0;
-  return differs != 0 && !separated;
+// one queued pair: separating-axis filter on the staged corners, exact predicate when it cannot tell
+static __device__ __noinline__ void decide_pair(PairSink k, const double* corners, unsigned corners_sh,
+                                                const int8_t* orient, int G, int a, int b) {
+  double qa[8], qb[8];
+#pragma unroll
+  for (int f = 0; f < 8; ++f) { qa[f] = corners[f * G + a]; qb[f] = corners[f * G + b]; }
+  const int v = sat_classify(qa, qb);
+  if (v > 0) commit_pair(k, a, b);
+  else if (v == 0) record_pair(k, corners_sh, orient, G, a, b);
 }
 
 // circular half sweep over the staged AABBs (STRtree's envelope filter is closed too);
@@ -1254,18 +1299,12 @@ SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int 
   const int nq = acc[ACC_QCOUNT];
   if (nq > 0) {  // phase B2: exact narrow phase on the queued pairs
     const PairSink sink = make_sink(p.features, st.coll_mask, c, ego_slot, first_slot, parity);
-    if (G >= 32 && nq <= SG_WARP_PAIRS * (G >> 5)) {
-      // up to a few pairs per warp (the usual case): a warp per pair, all lanes share the orientation
-      // tests (~300 cycles per pair against ~2500 for one lane walking the edges)
-      for (int q = s >> 5; q < nq; q += G >> 5) {
-        const uint32_t pr = c.queue[q];
-        const int a = (int)(pr >> 16), b = (int)(pr & 0xffff);
-        if (pair_collides_warp(c.corners_sh, c.orient, G, a, b) && (s & 31) == 0) commit_pair(sink, a, b);
-      }
-    } else if (nq <= c.QCAP) {
+    if (nq <= c.QCAP) {
+      // a pair per lane: the branch-free separating-axis filter decides all but knife-edge contacts,
+      // which go to the exact predicate
       for (int q = s; q < nq; q += G) {
         const uint32_t pr = c.queue[q];
-        record_pair(sink, c.corners_sh, c.orient, G, (int)(pr >> 16), (int)(pr & 0xffff));
+        decide_pair(sink, c.corners, c.corners_sh, c.orient, G, (int)(pr >> 16), (int)(pr & 0xffff));
       }
     } else if (c.sorted) {
       if (s < c.M) broad_phase_direct_sorted(sink, c.aabb, c.sid, c.corners_sh, c.orient, G, c.M, s);
@@ -1280,6 +1319,7 @@ SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int 
   bool dn = false;  // state.py:268-270, 397-408
   if ((p.terminal & SG_TERM_MAX_LENGTH) && (t + dt > length)) dn = true;
   if ((p.terminal & SG_TERM_COLLISION) && npairs > 0) dn = true;
+  if ((p.terminal & SG_TERM_EGO_OFF_ROAD) && acc[ACC_OFFROAD]) dn = true;
   if ((p.terminal & SG_TERM_EGO_COLLISION) && acc[ACC_FIRST_HIT]) dn = true;
   // the single-lane book-keeping runs in another warp than the ego's metrics when there is one,
   // so that neither warp of the scenario carries all the serial work of the tick
@@ -1296,7 +1336,7 @@ SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int 
     cold[COLD_RSS] |= acc[ACC_RSS];
     int* nx = c.acc + (parity ^ 1) * ACC_N;  // reset the other parity for the next tick
     nx[ACC_NPAIRS] = 0; nx[ACC_FIRST_PAIR] = 0x7fffffff; nx[ACC_FIRST_HIT] = 0; nx[ACC_RSS] = 0;
-    nx[ACC_QCOUNT] = 0;
+    nx[ACC_QCOUNT] = 0; nx[ACC_OFFROAD] = 0;
   }
   if (bs >= 0 && bs < W) {  // CollisionMetric._step, metrics/collision.py:70-75
     const uint32_t now = c.ego_now[bs];

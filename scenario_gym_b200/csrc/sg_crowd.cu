@@ -31,7 +31,7 @@
 struct CrowdLayout {
   int G, W, QCAP;
   int off_state, off_fcs, off_aabb, off_rad, off_nbl, off_gstart, off_gsorted, off_glarge, off_queue, off_flags,
-      off_wflag, off_orient, off_hits, off_bits, off_acc, off_cold, off_gmisc;
+      off_wflag, off_ncnt, off_orient, off_hits, off_bits, off_acc, off_cold, off_gmisc, off_unif;
   int bytes;
 };
 
@@ -48,13 +48,14 @@ static CrowdLayout crowd_layout(int ept) {
   L.off_rad = o;     o += G * (int)sizeof(float2);              // inscribed / circumscribed radius of each box
   L.off_nbl = o;     o += CR_NBCAP * G * (int)sizeof(uint16_t);
   o = (o + 15) / 16 * 16;
-  L.off_gstart = o;  o += (SG_GRID_CELLS / 2 + 4) * (int)sizeof(uint32_t);
-  L.off_gsorted = o; o += G * (int)sizeof(uint16_t);
+  L.off_gstart = o;  o += SG_GRID_CELLS * (int)sizeof(uint16_t);    // head slot of every cell's list (0xffff: empty)
+  L.off_gsorted = o; o += G * (int)sizeof(uint16_t);                // next slot in the cell's list
   L.off_glarge = o;  o += SG_GRID_LCAP * (int)sizeof(uint16_t);
   o = (o + 15) / 16 * 16;
   L.off_queue = o;   o += L.QCAP * (int)sizeof(uint32_t);
   L.off_flags = o;   o += G;                                    // present | etype << 1 | large << 3
   L.off_wflag = o;   o += G;                                    // walking this tick
+  L.off_ncnt = o;    o += G;                                    // sensor candidates of each slot (next tick)
   L.off_orient = o;  o += G;
   o = (o + 15) / 16 * 16;
   L.off_hits = o;    o += 2 * L.W * (int)sizeof(uint32_t);      // ego_now, ego_last
@@ -62,6 +63,7 @@ static CrowdLayout crowd_layout(int ept) {
   L.off_acc = o;     o += 2 * ACC_N * (int)sizeof(int);
   L.off_cold = o;    o += COLD_ND * (int)sizeof(double) + COLD_NI * (int)sizeof(int);
   L.off_gmisc = o;   o += 48 * (int)sizeof(int);
+  L.off_unif = o;    o += 8 * (int)sizeof(double);            // launch-uniform doubles (kept out of the registers)
   L.bytes = (o + 15) / 16 * 16;
   return L;
 }
@@ -73,12 +75,13 @@ struct Crowd {  // shared-memory views of one scenario
   float4* aabb;
   float2* rad;
   uint16_t* nbl;
-  uint32_t* gstart;
-  uint16_t* gsorted;
+  uint16_t* ghead;
+  uint16_t* gnext;
   uint16_t* glarge;
   uint32_t* queue;
   uint8_t* flags;
   uint8_t* wflag;
+  uint8_t* ncnt;
   int8_t* orient;
   uint32_t* ego_now;
   uint32_t* ego_last;
@@ -87,6 +90,7 @@ struct Crowd {  // shared-memory views of one scenario
   double* cold_d;
   int* cold_i;
   int* gmisc;
+  double* unif;
 };
 
 SG_DEV void crowd_views(Crowd& c, const CrowdLayout& L, unsigned char* base, int M) {
@@ -96,12 +100,13 @@ SG_DEV void crowd_views(Crowd& c, const CrowdLayout& L, unsigned char* base, int
   c.aabb = (float4*)(base + L.off_aabb);
   c.rad = (float2*)(base + L.off_rad);
   c.nbl = (uint16_t*)(base + L.off_nbl);
-  c.gstart = (uint32_t*)(base + L.off_gstart);
-  c.gsorted = (uint16_t*)(base + L.off_gsorted);
+  c.ghead = (uint16_t*)(base + L.off_gstart);
+  c.gnext = (uint16_t*)(base + L.off_gsorted);
   c.glarge = (uint16_t*)(base + L.off_glarge);
   c.queue = (uint32_t*)(base + L.off_queue);
   c.flags = base + L.off_flags;
   c.wflag = base + L.off_wflag;
+  c.ncnt = base + L.off_ncnt;
   c.orient = (int8_t*)(base + L.off_orient);
   c.ego_now = (uint32_t*)(base + L.off_hits);
   c.ego_last = c.ego_now + L.W;
@@ -110,111 +115,80 @@ SG_DEV void crowd_views(Crowd& c, const CrowdLayout& L, unsigned char* base, int
   c.cold_d = (double*)(base + L.off_cold);
   c.cold_i = (int*)(base + L.off_cold + COLD_ND * sizeof(double));
   c.gmisc = (int*)(base + L.off_gmisc);
+  c.unif = (double*)(base + L.off_unif);
 }
 
 SG_DEV void cta_sync() { __syncthreads(); }
 
 // ---------------------------------------------------------------------------------
-// cell grid over the scenario's present entities (same cells, cell size and "large" rule as the
-// general kernel's grid_build): packed 16-bit counters -> exclusive scan -> slot ids sorted by cell.
-// `have_box`: AABBs are staged (collision broad phase); entities reaching further than half a cell
-// from their position go to the `large` list.  All threads call it; it ends with a barrier.
-template <int EPT>
-SG_DEV void crowd_grid_build(const Crowd& c, bool have_box, double ox, double oy, double cs, double inv_cs) {
-  const int tid = threadIdx.x;
-  uint32_t* gs = c.gstart;
-  const int nwords = SG_GRID_CELLS / 2;
-  for (int q = tid; q <= nwords; q += CR_THREADS) gs[q] = 0;
-  if (tid == 0) c.gmisc[0] = 0;
-  cta_sync();
-  int cell[EPT];
-  uint32_t rank[EPT];
-  bool large[EPT];
-#pragma unroll
-  for (int e = 0; e < EPT; ++e) {
-    const int s = tid + e * CR_THREADS;
-    cell[e] = -1; rank[e] = 0; large[e] = false;
-    if (c.flags[s] & 1) {
-      const double px = c.state[s] - ox, py = c.state[c.G + s] - oy;
-      const int ix = __double2int_rd(px * inv_cs), iy = __double2int_rd(py * inv_cs);
-      cell[e] = ((iy & (SG_GRID_DIM - 1)) << SG_GRID_BITS) | (ix & (SG_GRID_DIM - 1));
-      if (have_box) {
-        const float4 bb = c.aabb[s];
-        const double reach = fmax(fmax(px - (double)bb.x, (double)bb.z - px),
-                                  fmax(py - (double)bb.y, (double)bb.w - py));
-        large[e] = !(reach <= 0.5 * cs * (1.0 - 1e-6));
-        c.flags[s] = (uint8_t)((c.flags[s] & ~8) | (large[e] ? 8 : 0));
-        if (large[e]) {
-          const int k = atomicAdd(&c.gmisc[0], 1);
-          if (k < SG_GRID_LCAP) c.glarge[k] = (uint16_t)s;
-        }
-      }
-      const uint32_t old = atomicAdd(&gs[cell[e] >> 1], (cell[e] & 1) ? 0x10000u : 1u);
-      rank[e] = (cell[e] & 1) ? (old >> 16) : (old & 0xffffu);
-    }
-  }
-  cta_sync();
-  // exclusive scan of the packed counts: thread t owns 4 consecutive words
-  constexpr int WPT = (SG_GRID_CELLS / 2) / CR_THREADS;
-  const int w0 = tid * WPT;
-  uint32_t local = 0;
-#pragma unroll
-  for (int q = 0; q < WPT; ++q) { const uint32_t v = gs[w0 + q]; local += (v & 0xffffu) + (v >> 16); }
-  const int lane = tid & 31, wid = tid >> 5;
-  uint32_t incl = local;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += o;
-  }
-  if (lane == 31) c.gmisc[8 + wid] = (int)incl;
-  cta_sync();
-  uint32_t wt = lane < CR_WARPS ? (uint32_t)c.gmisc[8 + lane] : 0u, wi = wt;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
-    if (lane >= d) wi += o;
-  }
-  const uint32_t wbase = __shfl_sync(0xffffffffu, wi - wt, wid);
-  const uint32_t total = __shfl_sync(0xffffffffu, wi, 31);
-  uint32_t run = wbase + incl - local;
-#pragma unroll
-  for (int q = 0; q < WPT; ++q) {
-    const uint32_t v = gs[w0 + q], lo = v & 0xffffu, hi = v >> 16;
-    gs[w0 + q] = run | ((run + lo) << 16);
-    run += lo + hi;
-  }
-  if (tid == 0) gs[nwords] = total;
-  cta_sync();
-#pragma unroll
-  for (int e = 0; e < EPT; ++e)
-    if (cell[e] >= 0)
-      c.gsorted[grid_start(gs, cell[e]) + rank[e]] =
-          (uint16_t)((uint32_t)(tid + e * CR_THREADS) | (large[e] ? SG_GRID_LARGE : 0u));
-  cta_sync();
+// Cell grid over the scenario's present entities (same cells, cell size and "large" rule as the
+// general kernel's grid): every cell heads a linked list of the slots whose position falls into it
+// (`ghead[cell]`, `gnext[slot]`; 0xffff ends a list).  Inserting is one atomic exchange on the head,
+// so the grid needs no scan / scatter passes and no barriers of its own: the heads are cleared at
+// the start of a tick (nobody reads the grid in phase A), every owner inserts its slots at the end of
+// phase B, and the barrier that ends phase B publishes the lists.
+#define CR_NIL 0xffffu
+
+SG_DEV void crowd_grid_clear(const Crowd& c) {
+  uint32_t* w = (uint32_t*)c.ghead;
+  for (int q = threadIdx.x; q < SG_GRID_CELLS / 2; q += CR_THREADS) w[q] = 0xffffffffu;
+  if (threadIdx.x == 0) c.gmisc[0] = 0;
 }
 
-// ---------------------------------------------------------------------------------
-// exact narrow phase of one pair from the State rows (corners as entity/base.py:100-138 computes
-// them; `g != g_prime` exclusion of reference utils.py:58)
-static __device__ __noinline__ bool crowd_pair_collides(const double* __restrict__ state, const double* __restrict__ hcs,
-                                                        const double* __restrict__ box, int64_t nm, int64_t i0,
-                                                        const int8_t* __restrict__ orient, int G, int a, int b) {
-  double qa[8], qb[8];
-#pragma unroll
-  for (int w = 0; w < 2; ++w) {
-    const int s = w ? b : a;
-    double* q = w ? qb : qa;
-    const double x = state[s], y = state[G + s], cs = hcs[s], sn = hcs[G + s];
-    const double bw = __ldg(box + i0 + s), bl = __ldg(box + nm + i0 + s);
-    const double bcx = __ldg(box + 2 * nm + i0 + s), bcy = __ldg(box + 3 * nm + i0 + s);
-    const double hx0 = bcx - 0.5 * bl, hx1 = bcx + 0.5 * bl;
-    const double hy0 = bcy + 0.5 * bw, hy1 = bcy - 0.5 * bw;
-    q[0] = x + (hx0 * cs + hy0 * -sn); q[1] = y + (hx0 * sn + hy0 * cs);
-    q[2] = x + (hx1 * cs + hy0 * -sn); q[3] = y + (hx1 * sn + hy0 * cs);
-    q[4] = x + (hx1 * cs + hy1 * -sn); q[5] = y + (hx1 * sn + hy1 * cs);
-    q[6] = x + (hx0 * cs + hy1 * -sn); q[7] = y + (hx0 * sn + hy1 * cs);
+// 16-bit exchange on a shared array through the containing 32-bit word
+SG_DEV uint32_t crowd_exch16(uint16_t* arr, int idx, uint32_t v) {
+  uint32_t* w = (uint32_t*)arr + (idx >> 1);
+  const int sh = (idx & 1) * 16;
+  uint32_t old = *w, assumed;
+  do {
+    assumed = old;
+    old = atomicCAS(w, assumed, (assumed & ~(0xffffu << sh)) | (v << sh));
+  } while (old != assumed);
+  return (old >> sh) & 0xffffu;
+}
+
+// insert slot s (present) at its position; `have_box`: its AABB is staged -- entities reaching further
+// than half a cell from their position are "large": listed for everyone to test against
+SG_DEV void crowd_grid_insert(const Crowd& c, int s, bool have_box, double gox, double goy, double cs, double inv_cs) {
+  const double px = c.state[s] - gox, py = c.state[c.G + s] - goy;
+  const int ix = __double2int_rd(px * inv_cs), iy = __double2int_rd(py * inv_cs);
+  const int cell = ((iy & (SG_GRID_DIM - 1)) << SG_GRID_BITS) | (ix & (SG_GRID_DIM - 1));
+  bool large = false;
+  if (have_box) {
+    const float4 bb = c.aabb[s];
+    const double reach = fmax(fmax(px - (double)bb.x, (double)bb.z - px), fmax(py - (double)bb.y, (double)bb.w - py));
+    large = !(reach <= 0.5 * cs * (1.0 - 1e-6));
+    if (large) {
+      const int k = atomicAdd(&c.gmisc[0], 1);
+      if (k < SG_GRID_LCAP) c.glarge[k] = (uint16_t)s;
+    }
   }
+  c.flags[s] = (uint8_t)((c.flags[s] & ~8) | (large ? 8 : 0));
+  c.gnext[s] = (uint16_t)crowd_exch16(c.ghead, cell, (uint32_t)s);
+}
+
+// corners of slot s as entity/base.py:100-138 computes them, from the State rows
+SG_DEV void crowd_corners(const double* __restrict__ state, const double* __restrict__ hcs, const double* __restrict__ box,
+                          int64_t nm, int64_t i0, int G, int s, double q[8]) {
+  const double x = state[s], y = state[G + s], cs = hcs[s], sn = hcs[G + s];
+  const double bw = __ldg(box + i0 + s), bl = __ldg(box + nm + i0 + s);
+  const double bcx = __ldg(box + 2 * nm + i0 + s), bcy = __ldg(box + 3 * nm + i0 + s);
+  const double hx0 = bcx - 0.5 * bl, hx1 = bcx + 0.5 * bl;
+  const double hy0 = bcy + 0.5 * bw, hy1 = bcy - 0.5 * bw;
+  q[0] = x + (hx0 * cs + hy0 * -sn); q[1] = y + (hx0 * sn + hy0 * cs);
+  q[2] = x + (hx1 * cs + hy0 * -sn); q[3] = y + (hx1 * sn + hy0 * cs);
+  q[4] = x + (hx1 * cs + hy1 * -sn); q[5] = y + (hx1 * sn + hy1 * cs);
+  q[6] = x + (hx0 * cs + hy1 * -sn); q[7] = y + (hx0 * sn + hy1 * cs);
+}
+
+// exact narrow phase of one pair (`g != g_prime` exclusion of reference utils.py:58, then the closed-set
+// predicate on the corners); only reached for knife-edge contacts
+static __device__ __noinline__ bool crowd_pair_exact(const double* __restrict__ state, const double* __restrict__ hcs,
+                                                     const double* __restrict__ box, int64_t nm, int64_t i0,
+                                                     const int8_t* __restrict__ orient, int G, int a, int b) {
+  double qa[8], qb[8];
+  crowd_corners(state, hcs, box, nm, i0, G, a, qa);
+  crowd_corners(state, hcs, box, nm, i0, G, b, qb);
   bool same = true;
 #pragma unroll
   for (int f = 0; f < 8; ++f) same = same && (qa[f] == qb[f]);
@@ -222,6 +196,18 @@ static __device__ __noinline__ bool crowd_pair_collides(const double* __restrict
   const Quad A = quad_from_array(qa), B = quad_from_array(qb);
   const int oa = orient[a] ? orient[a] : quad_orientation(A), ob = orient[b] ? orient[b] : quad_orientation(B);
   return quads_intersect(A, oa, B, ob);
+}
+
+// one queued pair: the branch-free separating-axis filter decides all but knife-edge contacts
+static __device__ __noinline__ bool crowd_pair_collides(const double* __restrict__ state, const double* __restrict__ hcs,
+                                                        const double* __restrict__ box, int64_t nm, int64_t i0,
+                                                        const int8_t* __restrict__ orient, int G, int a, int b) {
+  double qa[8], qb[8];
+  crowd_corners(state, hcs, box, nm, i0, G, a, qa);
+  crowd_corners(state, hcs, box, nm, i0, G, b, qb);
+  const int v = sat_classify(qa, qb);
+  if (v != 0) return v > 0;
+  return crowd_pair_exact(state, hcs, box, nm, i0, orient, G, a, b);
 }
 
 struct CrowdSink {  // where colliding pairs are booked (shared atomics)
@@ -265,32 +251,93 @@ SG_DEV void crowd_candidate(const Crowd& c, const CrowdSink& sink, int* acc, int
 
 // broad phase of slot s through the grid: every unordered pair whose conservative AABBs overlap is
 // seen exactly once (small-small by the lower slot, small-large by the small one, large-large by
-// the lower slot)
+// the lower slot).  (Used when the pair queue overflowed: the candidates are decided in place.)
 template <typename F>
-SG_DEV void crowd_for_each_candidate(const Crowd& c, int s, double ox, double oy, double inv_cs, F&& fn) {
+SG_DEV void crowd_for_each_candidate(const Crowd& c, int s, double gox, double goy, double inv_cs, F&& fn) {
   const float4 mb = c.aabb[s];
   const int nl = c.gmisc[0];
   const bool large = (c.flags[s] & 8) != 0;
   if (!large) {
-    const int ix = __double2int_rd((c.state[s] - ox) * inv_cs), iy = __double2int_rd((c.state[c.G + s] - oy) * inv_cs);
-    for (int dy = -1; dy <= 1; ++dy) {
-      int beg[2], end[2];
-      const int nr = grid_row_ranges(c.gstart, ix, iy, dy, beg, end);
-      for (int r = 0; r < nr; ++r)
-        for (int idx = beg[r]; idx < end[r]; ++idx) {
-          const uint32_t o = c.gsorted[idx];
-          if (o > (uint32_t)s && o < SG_GRID_LARGE) {
+    const int ix = __double2int_rd((c.state[s] - gox) * inv_cs), iy = __double2int_rd((c.state[c.G + s] - goy) * inv_cs);
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int cell = (((iy + dy) & (SG_GRID_DIM - 1)) << SG_GRID_BITS) | ((ix + dx) & (SG_GRID_DIM - 1));
+        for (uint32_t o = c.ghead[cell]; o != CR_NIL; o = c.gnext[o]) {
+          if (o > (uint32_t)s && !(c.flags[o] & 8)) {
             const float4 ob = c.aabb[o];
             if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) fn(s, (int)o);
           }
         }
-    }
+      }
   }
   for (int k = 0; k < nl; ++k) {
     const int o = c.glarge[k];
     if (o == s || (large && o < s)) continue;
     const float4 ob = c.aabb[o];
     if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) fn(min(s, o), max(s, o));
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// One walk over the 3 x 3 cells around slot s on the grid of the positions just computed serves
+//   * the pedestrian's sensor of the NEXT tick (neighbours strictly inside the 64-gon of
+//     circumradius r lie in these cells): pedestrians within r (1 + 1e-9) go to the slot's
+//     candidate list, which is then put in slot (= state.poses) order, and
+//   * this tick's collision broad phase: pairs (s, o), o > s, whose centres are within the sum of
+//     the circumscribed radii and whose conservative AABBs overlap (crowd_candidate).
+// `r2` = (r (1 + 1e-9))^2; sensor = the slot is a present pedestrian; coll = it takes part in the
+// cell broad phase (present, not large).
+SG_DEV void crowd_walk(const Crowd& c, const CrowdSink& sink, int* acc, int s, bool sensor, bool coll, double r2,
+                       double gox, double goy, double inv_cs) {
+  const int G = c.G;
+  const double px = c.state[s], py = c.state[G + s];
+  const int ix = __double2int_rd((px - gox) * inv_cs), iy = __double2int_rd((py - goy) * inv_cs);
+  const float2 rs = c.rad[s];
+  int ncand = 0;
+  const int cx0 = (ix - 1) & (SG_GRID_DIM - 1), cx1 = ix & (SG_GRID_DIM - 1), cx2 = (ix + 1) & (SG_GRID_DIM - 1);
+  uint32_t o = c.ghead[(((iy - 1) & (SG_GRID_DIM - 1)) << SG_GRID_BITS) | cx0];
+#pragma unroll 1
+  for (int q = 0; q < 9; ++q) {
+    // the head of the next cell is fetched while this cell's list is walked
+    uint32_t nxt = CR_NIL;
+    if (q < 8) {
+      const int q1 = q + 1, row = (iy + q1 / 3 - 1) & (SG_GRID_DIM - 1), col = q1 % 3;
+      nxt = c.ghead[(row << SG_GRID_BITS) | (col == 0 ? cx0 : (col == 1 ? cx1 : cx2))];
+    }
+    for (; o != CR_NIL; o = c.gnext[o]) {
+      if (o == (uint32_t)s) continue;
+      const double ddx = c.state[o] - px, ddy = c.state[G + o] - py, d2 = ddx * ddx + ddy * ddy;
+      const uint8_t fo = c.flags[o];
+      if (sensor && ((fo >> 1) & 3) == SG_ETYPE_PEDESTRIAN && !(d2 > r2)) {
+        if (ncand < CR_NBCAP) c.nbl[ncand * G + s] = (uint16_t)o;
+        ++ncand;
+      }
+      if (coll && o > (uint32_t)s && !(fo & 8)) {
+        const double rout = (double)rs.y + (double)c.rad[o].y;
+        if (!(d2 > rout * rout)) {  // (crowd_candidate repeats the circle tests; most candidates stop here)
+          const float4 mb = c.aabb[s], ob = c.aabb[o];
+          if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) crowd_candidate(c, sink, acc, s, (int)o);
+        }
+      }
+    }
+    o = nxt;
+  }
+  if (sensor) {
+    c.ncnt[s] = (uint8_t)min(ncand, 255);
+    // slot (= state.poses) order: every listed slot goes to the rank of its id (ids are distinct)
+    const int n = min(ncand, CR_NBCAP);
+    uint32_t v[CR_NBCAP];
+#pragma unroll
+    for (int a = 0; a < CR_NBCAP; ++a) v[a] = a < n ? (uint32_t)c.nbl[a * G + s] : 0xffffffffu;
+    if (n > 1) {
+#pragma unroll
+      for (int a = 0; a < CR_NBCAP; ++a) {
+        int rank = 0;
+#pragma unroll
+        for (int b = 0; b < CR_NBCAP; ++b) rank += v[b] < v[a] ? 1 : 0;
+        if (a < n) c.nbl[rank * G + s] = (uint16_t)v[a];
+      }
+    }
   }
 }
 
@@ -353,7 +400,8 @@ struct PerSlot {
   double h, dist;
   uint32_t bits;  // bit 0: was in a collision so far, bit 1: moved during this launch
 };
-enum { CR_EGO_SPEED = COLD_T0, CR_EGO_DIST = COLD_T1 };  // the ego's |v| and distance, for the metrics
+enum { CR_EGO_SPEED = COLD_T0, CR_EGO_DIST = COLD_T1 };
+enum { U_INV_CS = 0, U_SIGHT, U_SH, U_CH, U_OX, U_OY, U_LEN };  // the ego's |v| and distance, for the metrics
 
 template <int EPT>
 __global__ void __launch_bounds__(CR_THREADS, 2)
@@ -369,17 +417,26 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
   const int ego_slot = sc.ego_slot[n], first_slot = sc.first_slot[n];
   const bool need_coll = (p.features & SG_FEAT_COLLISIONS) || (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
   const bool matrix = (p.features & SG_FEAT_COLL_MATRIX) != 0;
-  const double grid_cs = p.ped_distance_threshold * (1.0 + 1e-6), grid_inv_cs = 1.0 / grid_cs;
-  const double sight_cos = cos(p.sf_sight_angle / 2 * M_PI / 180);
-  double sh_rot, ch_rot;
-  sincos(p.ped_head_rot_angle, &sh_rot, &ch_rot);  // viewer/utils.py:6-17
-  double ox, oy;  // origin of the fp32 bounds / the grid: the ego's first control point
-  {
-    const int64_t er = sc.traj_off[i0 + ego_slot];
-    ox = __ldg(sc.traj_rows + er * 7 + 1);
-    oy = __ldg(sc.traj_rows + er * 7 + 2);
+  const double grid_cs = p.ped_distance_threshold * (1.0 + 1e-6);
+  if (tid == 0) {  // launch-uniform doubles live in shared memory: 64 registers per thread are all there is
+    double sh, ch;
+    sincos(p.ped_head_rot_angle, &sh, &ch);  // viewer/utils.py:6-17
+    const int64_t er = sc.traj_off[i0 + ego_slot];  // origin of the fp32 bounds / the grid: the ego's first control point
+    c.unif[U_INV_CS] = 1.0 / grid_cs;
+    c.unif[U_SIGHT] = cos(p.sf_sight_angle / 2 * M_PI / 180);
+    c.unif[U_SH] = sh; c.unif[U_CH] = ch;
+    c.unif[U_OX] = __ldg(sc.traj_rows + er * 7 + 1);
+    c.unif[U_OY] = __ldg(sc.traj_rows + er * 7 + 2);
+    c.unif[U_LEN] = sc.length[n];
   }
-  const double length = sc.length[n];
+  __syncthreads();
+#define grid_inv_cs (c.unif[U_INV_CS])
+#define sight_cos (c.unif[U_SIGHT])
+#define sh_rot (c.unif[U_SH])
+#define ch_rot (c.unif[U_CH])
+#define ox (c.unif[U_OX])
+#define oy (c.unif[U_OY])
+#define length (c.unif[U_LEN])
 
   // ---- load the rows ----------------------------------------------------------------------
   PerSlot ent[EPT];
@@ -440,8 +497,27 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
     c.ego_now[tid] = 0;
     c.bits[tid] = 0; c.bits[W + tid] = 0;
   }
+  crowd_grid_clear(c);
   cta_sync();
-  crowd_grid_build<EPT>(c, false, ox, oy, grid_cs, grid_inv_cs);  // the sensors of the first tick
+#pragma unroll 1
+  for (int e = 0; e < EPT; ++e) {  // the grid of the loaded positions: the sensors of the first tick
+    const int s = tid + e * CR_THREADS;
+    if (c.flags[s] & 1) crowd_grid_insert(c, s, false, ox, oy, grid_cs, grid_inv_cs);
+  }
+  cta_sync();
+  {
+    const double rr = p.ped_distance_threshold * (1.0 + 1e-9), r2s = rr * rr;
+    CrowdSink nosink;
+    nosink.acc = c.acc; nosink.bits = c.bits; nosink.ego_now = c.ego_now; nosink.rows = nullptr;
+    nosink.W = WM; nosink.ego_slot = ego_slot; nosink.first_slot = first_slot;
+#pragma unroll 1
+    for (int e = 0; e < EPT; ++e) {
+      const int s = tid + e * CR_THREADS;
+      const uint8_t fl = c.flags[s];
+      if ((fl & 1) && ((fl >> 1) & 3) == SG_ETYPE_PEDESTRIAN) crowd_walk(c, nosink, c.acc, s, true, false, r2s, ox, oy, grid_inv_cs);
+    }
+  }
+  cta_sync();
 
   const int limit = n_ticks < 0 ? p.max_ticks : n_ticks;
   int parity = 0;
@@ -449,6 +525,7 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
   for (int k = 0; k < limit && (!done || in.step_done); ++k) {
     const double next_t = t + p.timestep;  // scenario_gym.py:229
     const double step_dt = next_t - t;
+    crowd_grid_clear(c);  // (nobody reads the grid in phase A; the owners insert again at the end of phase B)
     // ================= phase A: sensors + behaviour (reads the OLD rows of other slots) ==========
 #pragma unroll 1
     for (int e = 0; e < EPT; ++e) {
@@ -489,31 +566,10 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
           const double kk = 1 / p.sf_relaxation_time;
           F0 = kk * (speed_desired * ux - c.state[2 * G + s]);
           F1 = kk * (speed_desired * uy - c.state[3 * G + s]);
-          // sensor candidates from the 3 x 3 cells around the pedestrian (a neighbour strictly inside
-          // the 64-gon of circumradius r lies there), then put in slot (= state.poses) order
-          const double rr = p.ped_distance_threshold * (1.0 + 1e-9), r2 = rr * rr;
-          const int ix = __double2int_rd((px - ox) * grid_inv_cs), iy = __double2int_rd((py - oy) * grid_inv_cs);
-          for (int dy = -1; dy <= 1; ++dy) {
-            int beg[2], end[2];
-            const int nr = grid_row_ranges(c.gstart, ix, iy, dy, beg, end);
-            for (int r = 0; r < nr; ++r)
-              for (int idx = beg[r]; idx < end[r]; ++idx) {
-                const int o = (int)(c.gsorted[idx] & (SG_GRID_LARGE - 1u));
-                if (o == s || ((c.flags[o] >> 1) & 3) != SG_ETYPE_PEDESTRIAN) continue;
-                const double ddx = c.state[o] - px, ddy = c.state[G + o] - py;
-                if (ddx * ddx + ddy * ddy > r2) continue;
-                if (ncand < CR_NBCAP) nbl[ncand * G] = (uint16_t)o;
-                ++ncand;
-              }
-          }
-          for (int a = 1; a < min(ncand, CR_NBCAP); ++a) {  // insertion sort (a handful of entries)
-            const uint16_t v = nbl[a * G];
-            int b = a - 1;
-            while (b >= 0 && nbl[b * G] > v) { nbl[(b + 1) * G] = nbl[b * G]; --b; }
-            nbl[(b + 1) * G] = v;
-          }
         }
       }
+      // the sensor's candidates were listed by the walk over the grid of these (now old) positions
+      if (walking) ncand = c.ncnt[s];
       // neighbour terms, pooled over the warp's 32 pedestrians of this pass and handed back to their
       // owners in list order (same sums, same order as one lane walking its own list)
       const int nlist = (walking && ncand <= CR_NBCAP) ? ncand : 0;
@@ -661,6 +717,7 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
                              __ldg(sc.box + 3 * nm + i), ox, oy);
         }
         c.aabb[s] = bb;
+        if (newpres) crowd_grid_insert(c, s, need_coll, ox, oy, grid_cs, grid_inv_cs);
         if (matrix) {
           uint32_t* row = st.coll_mask + ((int64_t)n * M + s) * WM;
           for (int w = 0; w < WM; ++w) row[w] = 0;
@@ -668,28 +725,45 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
       }
       if (e == 0) ent[0] = me; else ent[EPT - 1] = me;
     }
-    cta_sync();
-    // the grid of the new positions: this tick's broad phase and the next tick's sensors
-    crowd_grid_build<EPT>(c, need_coll, ox, oy, grid_cs, grid_inv_cs);
+    cta_sync();  // the rows, boxes and the grid of the new positions are complete
     int* acc = c.acc + parity * ACC_N;
-    if (need_coll) {
-      CrowdSink sink;
-      sink.acc = acc; sink.bits = c.bits + parity * W; sink.ego_now = c.ego_now;
-      sink.rows = matrix ? st.coll_mask + (int64_t)n * M * WM : nullptr;
-      sink.W = WM; sink.ego_slot = ego_slot; sink.first_slot = first_slot;
-      // ================= phase C: broad phase ======================================================
-      const bool exhaustive = c.gmisc[0] > SG_GRID_LCAP;  // too many large entities for the list
+    CrowdSink sink;
+    sink.acc = acc; sink.bits = c.bits + parity * W; sink.ego_now = c.ego_now;
+    sink.rows = matrix ? st.coll_mask + (int64_t)n * M * WM : nullptr;
+    sink.W = WM; sink.ego_slot = ego_slot; sink.first_slot = first_slot;
+    const bool exhaustive = need_coll && c.gmisc[0] > SG_GRID_LCAP;  // too many large entities for the list
+    {
+      // ================= phase C: next tick's sensor candidates + broad phase ========================
+      const double rr = p.ped_distance_threshold * (1.0 + 1e-9), r2s = rr * rr;
 #pragma unroll 1
       for (int e = 0; e < EPT; ++e) {
         const int s = tid + e * CR_THREADS;
-        if (!(c.flags[s] & 1)) continue;
+        const uint8_t fl = c.flags[s];
+        const bool pres = (fl & 1) != 0, large = (fl & 8) != 0;
+        const bool sensor = pres && ((fl >> 1) & 3) == SG_ETYPE_PEDESTRIAN;
         if (!exhaustive) {
-          crowd_for_each_candidate(c, s, ox, oy, grid_inv_cs, [&](int a, int b) { crowd_candidate(c, sink, acc, a, b); });
-        } else {
-          const float4 mb = c.aabb[s];
-          for (int o = s + 1; o < M; ++o) {
-            const float4 ob = c.aabb[o];
-            if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) crowd_candidate(c, sink, acc, s, o);
+          if (!pres) continue;
+          crowd_walk(c, sink, acc, s, sensor, need_coll && !large, r2s, ox, oy, grid_inv_cs);
+          if (need_coll) {  // the large entities are kept in a list everyone tests against
+            const float4 mb = c.aabb[s];
+            const int nl = c.gmisc[0];
+            for (int k = 0; k < nl; ++k) {
+              const int o = c.glarge[k];
+              if (o == s || (large && o < s)) continue;
+              const float4 ob = c.aabb[o];
+              if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) crowd_candidate(c, sink, acc, min(s, o), max(s, o));
+            }
+          }
+        } else if (!pres) {
+          continue;
+        } else {  // too many large entities for the list: exhaustive sweeps (sensor candidates included)
+          crowd_walk(c, sink, acc, s, sensor, false, r2s, ox, oy, grid_inv_cs);
+          {
+            const float4 mb = c.aabb[s];
+            for (int o = s + 1; o < M; ++o) {
+              const float4 ob = c.aabb[o];
+              if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) crowd_candidate(c, sink, acc, s, o);
+            }
           }
         }
       }
@@ -805,6 +879,13 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
     st.n_pair_ticks[n] = *(long long*)(c.cold_i + COLD_PAIR_TICKS);
   }
   if (tid < WM) st.ego_hits[(int64_t)n * WM + tid] = c.ego_last[tid];
+#undef grid_inv_cs
+#undef sight_cos
+#undef sh_rot
+#undef ch_rot
+#undef ox
+#undef oy
+#undef length
 }
 
 cudaError_t sgi_launch_crowd(cudaStream_t s, const SgScene& sc, const SgParams& p, const SgState& st,

@@ -285,3 +285,86 @@ SG_DEV double route_project(const double* __restrict__ xy, int R, double px, dou
   }
   return best_s;
 }
+
+// ----------------------------------------------------------------------------------
+// Road-network surfaces as polygon soups (SgScene.rn_*; reference road_network/road_network.py:
+// 306-328 builds them with shapely's unary_union).  Restated semantics: a point is contained in a
+// surface iff it is strictly inside one of its polygons (crossing parity over all rings of the
+// polygon, decided with exact orientation signs; a point on a ring is on the boundary), and the
+// nearest point of a surface to a point outside it is the nearest point on the polygons' rings.
+// Knife-edge cases that GEOS' dissolved union would decide differently (points exactly on an edge
+// shared by two polygons) are unpinned -- see DESIGN.md.
+// ----------------------------------------------------------------------------------
+// +1 strictly inside, 0 on the boundary, -1 outside
+static __device__ __noinline__ int polygon_side(const double* __restrict__ edges, int64_t e0, int64_t e1, double px,
+                                                double py) {
+  bool inside = false;
+  for (int64_t e = e0; e < e1; ++e) {
+    const double ax = __ldg(edges + 4 * e), ay = __ldg(edges + 4 * e + 1);
+    const double bx = __ldg(edges + 4 * e + 2), by = __ldg(edges + 4 * e + 3);
+    const bool straddles = (ay > py) != (by > py);
+    const bool in_box = px >= fmin(ax, bx) && px <= fmax(ax, bx) && py >= fmin(ay, by) && py <= fmax(ay, by);
+    if (!straddles && !in_box) continue;
+    const int o = orient_sign(ax, ay, bx, by, px, py);
+    if (o == 0 && in_box) return 0;
+    if (straddles && ((o > 0) == (by > ay))) inside = !inside;
+  }
+  return inside ? 1 : -1;
+}
+
+SG_DEV bool surface_has_area(const SgScene& sc, int n, int k) {
+  if (!sc.rn_of || sc.n_networks <= 0) return false;
+  const int r = sc.rn_of[n];
+  return r >= 0 && sc.rn_has_area[3 * r + k] != 0;
+}
+
+// shapely: surface.contains(Point(px, py))
+static __device__ __noinline__ bool surface_contains(const SgScene sc, int n, int k, double px, double py) {
+  if (!sc.rn_of || sc.n_networks <= 0) return false;
+  const int r = sc.rn_of[n];
+  if (r < 0) return false;
+  for (int64_t q = sc.rn_poly_off[3 * r + k]; q < sc.rn_poly_off[3 * r + k + 1]; ++q)
+    if (polygon_side(sc.rn_edges, sc.rn_edge_off[q], sc.rn_edge_off[q + 1], px, py) > 0) return true;
+  return false;
+}
+
+// shapely.ops.nearest_points(surface, Point(px, py))[0]: the point itself when it lies in the
+// (closed) surface, else the closest point on a ring (GEOS LineSegment::closestPoint: projection
+// factor r = ((p - a).(b - a)) / |b - a|^2, the projection for 0 < r < 1, else the closer end point)
+static __device__ __noinline__ double2 surface_nearest(const SgScene sc, int n, int k, double px, double py) {
+  double2 best = make_double2(px, py);
+  const int r = sc.rn_of[n];
+  const int64_t q0 = sc.rn_poly_off[3 * r + k], q1 = sc.rn_poly_off[3 * r + k + 1];
+  for (int64_t q = q0; q < q1; ++q)
+    if (polygon_side(sc.rn_edges, sc.rn_edge_off[q], sc.rn_edge_off[q + 1], px, py) >= 0) return best;
+  double best_d2 = INFINITY;
+  for (int64_t e = sc.rn_edge_off[q0]; e < sc.rn_edge_off[q1]; ++e) {
+    const double ax = __ldg(sc.rn_edges + 4 * e), ay = __ldg(sc.rn_edges + 4 * e + 1);
+    const double bx = __ldg(sc.rn_edges + 4 * e + 2), by = __ldg(sc.rn_edges + 4 * e + 3);
+    const double dx = bx - ax, dy = by - ay, len2 = dx * dx + dy * dy;
+    double cx = ax, cy = ay;
+    if (len2 > 0.0) {
+      const double f = ((px - ax) * dx + (py - ay) * dy) / len2;
+      if (f > 0.0 && f < 1.0) { cx = ax + f * dx; cy = ay + f * dy; }
+      else {
+        const double da = (px - ax) * (px - ax) + (py - ay) * (py - ay);
+        const double db = (px - bx) * (px - bx) + (py - by) * (py - by);
+        if (db < da) { cx = bx; cy = by; }
+      }
+    }
+    const double d2 = (px - cx) * (px - cx) + (py - cy) * (py - cy);
+    if (d2 < best_d2) { best_d2 = d2; best = make_double2(cx, cy); }
+  }
+  return best;
+}
+
+// SocialForce._force_boundary (pedestrian/social_force.py:190-211) for surface k
+SG_DEV void boundary_force(const SgScene& sc, int n, int k, double px, double py, double U, double R, double out[2]) {
+  const double2 c = surface_nearest(sc, n, k, px, py);
+  const double r0 = px - c.x, r1 = py - c.y;
+  const double rn = sqrt(r0 * r0 + r1 * r1);
+  const double u0 = r0 / (rn + 0.0000000001), u1 = r1 / (rn + 0.0000000001);
+  const double ex = exp(-rn / R);
+  out[0] = U / R * u0 * ex;
+  out[1] = U / R * u1 * ex;
+}

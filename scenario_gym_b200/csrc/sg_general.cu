@@ -309,6 +309,10 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
         }
       }
       if (need_coll && e.present && !use_grid) broad_phase(c, parity);
+      // ego_off_road (state/state.py:401-407): entities[0] absent, or not strictly inside the driveable surface
+      if ((p.terminal & SG_TERM_EGO_OFF_ROAD) && s == first_slot &&
+          !(e.present && surface_contains(sc, n, 0, e.pose[0], e.pose[1])))
+        c.acc[parity * ACC_N + ACC_OFFROAD] = 1;
     }
     if (PED && use_grid) {  // bin the new positions: this tick's broad phase and the next tick's sensors
       gpos = grid_build(c, live && e.present, need_coll, e.pose[0], e.pose[1], ox, oy, grid_cs, grid_inv_cs);

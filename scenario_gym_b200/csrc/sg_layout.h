@@ -51,7 +51,7 @@ enum { EGO_X = 0, EGO_Y, EGO_C, EGO_S, EGO_INV0, EGO_INV1, EGO_HD0, EGO_HD1, EGO
 enum { COLD_AVG = 0, COLD_AVG_T, COLD_MAX, COLD_EGOD, COLD_T0, COLD_T1, COLD_PT0, COLD_PT1, COLD_LEN,
        COLD_OX, COLD_OY, COLD_R2MINA, COLD_ND = 12 };  // doubles (T/PT: tick time, 2 parities)
 enum { COLD_FIRST_TICK = 0, COLD_FP0, COLD_FP1, COLD_RSS, COLD_PAIR_TICKS = 4, COLD_HAS_VEH = 6, COLD_NI = 8 };  // ints
-enum { ACC_NPAIRS = 0, ACC_FIRST_PAIR, ACC_FIRST_HIT, ACC_RSS, ACC_QCOUNT, ACC_N = 8 };
+enum { ACC_NPAIRS = 0, ACC_FIRST_PAIR, ACC_FIRST_HIT, ACC_RSS, ACC_QCOUNT, ACC_OFFROAD, ACC_N = 8 };
 
 static inline GroupLayout make_layout(int M, bool ped, bool rss, bool veh, bool grid = false) {
   GroupLayout L;

@@ -59,6 +59,9 @@ class Engine:
         self._sc.n_traj_rows = scene.traj_rows.shape[0]
         self._sc.n_union_rows = scene.union_t.shape[0]
         self._sc.n_route_pts = scene.route_xy.shape[0]
+        self._sc.n_networks = scene.n_networks
+        self._sc.n_rn_polys = len(scene.rn_edge_off) - 1
+        self._sc.n_rn_edges = scene.rn_edges.shape[0]
         self._sc.kind_mask = scene.kind_mask()
         for k, a in scene.arrays().items():
             t = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)

@@ -35,7 +35,7 @@ from .state import State
 from .xosc import import_scenario, import_scenarios
 
 _TERMINAL_BITS = {"max_length": abi.TERM_MAX_LENGTH, "collision": abi.TERM_COLLISION,
-                  "ego_collision": abi.TERM_EGO_COLLISION}
+                  "ego_collision": abi.TERM_EGO_COLLISION, "ego_off_road": abi.TERM_EGO_OFF_ROAD}
 
 
 class ScenarioGym:
@@ -294,7 +294,9 @@ class ScenarioGym:
                     ped_params.add((agent.max_speed, agent.head_rot_angle, agent.distance_threshold,
                                     pr.max_speed_factor, pr.bias_lon, pr.bias_lat, pr.sight_weight,
                                     bool(pr.sight_weight_use), pr.sight_angle, pr.relaxation_time,
-                                    pr.ped_repulse_V, pr.ped_repulse_sigma, pr.ped_attract_C))
+                                    pr.ped_repulse_V, pr.ped_repulse_sigma, pr.ped_attract_C,
+                                    pr.boundary_repulse_U, pr.boundary_repulse_R,
+                                    pr.imp_boundary_repulse_U, pr.imp_boundary_repulse_R))
                 elif type(agent) is PIDAgent and type(agent.controller) is PIDController \
                         and agent._trajectory is None:
                     kind, self._agent_kind[agent] = abi.KIND_PID, "device"
@@ -322,7 +324,8 @@ class ScenarioGym:
                 slots.append(SlotSpec(kind=kind, **kw))
             specs.append(ScenarioSpec(slots=slots, ego_slot=ents.index(sc.ego),
                                       first_slot=ents.index(sc.entities[0]),
-                                      t0=self.get_start_time(sc), length=sc.length, name=sc.name or ""))
+                                      t0=self.get_start_time(sc), length=sc.length, name=sc.name or "",
+                                      road_network=sc.road_network))
             self._slot_of.append({e: s for s, e in enumerate(ents)})
             self._entity_of.append(ents)
         if len(veh_params) > 1 or len(ped_params) > 1 or len(pid_params) > 1:
@@ -380,7 +383,9 @@ class ScenarioGym:
         if self._ped_params:
             (p.ped_max_speed, p.ped_head_rot_angle, p.ped_distance_threshold, p.sf_max_speed_factor,
              p.sf_bias_lon, p.sf_bias_lat, p.sf_sight_weight, suse, p.sf_sight_angle,
-             p.sf_relaxation_time, p.sf_ped_repulse_V, p.sf_ped_repulse_sigma, p.sf_ped_attract_C) = self._ped_params
+             p.sf_relaxation_time, p.sf_ped_repulse_V, p.sf_ped_repulse_sigma, p.sf_ped_attract_C,
+             p.sf_boundary_repulse_U, p.sf_boundary_repulse_R, p.sf_imp_boundary_repulse_U,
+             p.sf_imp_boundary_repulse_R) = self._ped_params
             p.sf_sight_weight_use = int(suse)
         self._params = p
         trace_cap = 0

@@ -85,6 +85,7 @@ class ScenarioSpec:
     t0: Optional[float] = None
     length: Optional[float] = None
     name: str = ""
+    road_network: Optional[object] = None  # scenario_gym_b200.road_network.RoadNetwork (or None: empty)
 
     def finalize(self):
         if self.length is None:  # Scenario.length, scenario/scenario.py:88-91
@@ -115,6 +116,24 @@ class PackedScene:
     route_off: np.ndarray
     route_xy: np.ndarray
     n_entities: np.ndarray = field(default=None)
+    # road-network surfaces (SgScene.rn_*): networks are shared between scenarios
+    rn_of: np.ndarray = field(default=None)
+    rn_poly_off: np.ndarray = field(default=None)
+    rn_edge_off: np.ndarray = field(default=None)
+    rn_edges: np.ndarray = field(default=None)
+    rn_has_area: np.ndarray = field(default=None)
+
+    def __post_init__(self):
+        if self.rn_of is None:  # no road networks
+            self.rn_of = np.full(self.N, -1, np.int32)
+            self.rn_poly_off = np.zeros(1, np.int64)
+            self.rn_edge_off = np.zeros(1, np.int64)
+            self.rn_edges = np.zeros((0, 4), np.float64)
+            self.rn_has_area = np.zeros(0, np.uint8)
+
+    @property
+    def n_networks(self) -> int:
+        return (len(self.rn_poly_off) - 1) // 3
 
     @property
     def W(self) -> int:
@@ -142,6 +161,35 @@ class PackedScene:
 
     def nbytes(self) -> int:
         return int(sum(a.nbytes for a in self.arrays().values()))
+
+
+def pack_road_networks(networks: Sequence[Optional[object]]):
+    """
+    Lower the road networks of a batch (one entry per scenario, ``None`` = empty network) to the
+    polygon soups of ``SgScene.rn_*``: (rn_of, rn_poly_off, rn_edge_off, rn_edges, rn_has_area).
+    Networks are stored once per distinct object; networks without any geometry count as empty.
+    """
+    index, uniq = {}, []
+    rn_of = np.full(len(networks), -1, np.int32)
+    for n, rn in enumerate(networks):
+        if rn is None or not any(len(sf) for sf in rn.surfaces()):
+            continue
+        if id(rn) not in index:
+            index[id(rn)] = len(uniq)
+            uniq.append(rn)
+        rn_of[n] = index[id(rn)]
+    poly_off, edge_off, edges, has_area = [0], [0], [], []
+    for rn in uniq:
+        for surface in rn.surfaces():
+            for poly in surface.polygons:
+                e = poly.edges()
+                edges.append(e)
+                edge_off.append(edge_off[-1] + len(e))
+            poly_off.append(len(edge_off) - 1)
+            has_area.append(1 if surface.area > 0 else 0)
+    return (rn_of, np.array(poly_off, np.int64), np.array(edge_off, np.int64),
+            np.ascontiguousarray(np.concatenate(edges, axis=0) if edges else np.zeros((0, 4)), np.float64),
+            np.array(has_area, np.uint8))
 
 
 def pack_scenarios(specs: Sequence[ScenarioSpec], n_slots: Optional[int] = None) -> PackedScene:
@@ -217,6 +265,8 @@ def pack_scenarios(specs: Sequence[ScenarioSpec], n_slots: Optional[int] = None)
         route_off=route_off,
         route_xy=np.concatenate(routes, axis=0) if routes else np.zeros((0, 2)),
         n_entities=np.array([len(s.slots) for s in specs], np.int32),
+        **dict(zip(("rn_of", "rn_poly_off", "rn_edge_off", "rn_edges", "rn_has_area"),
+                   pack_road_networks([s.road_network for s in specs]))),
     )
 
 
@@ -262,6 +312,8 @@ def tile_scene(scene: PackedScene, reps: int) -> PackedScene:
         route_off=route_off,
         route_xy=route_xy,
         n_entities=scene.n_entities[order].copy(),
+        rn_of=scene.rn_of[order].copy(), rn_poly_off=scene.rn_poly_off, rn_edge_off=scene.rn_edge_off,
+        rn_edges=scene.rn_edges, rn_has_area=scene.rn_has_area,
     )
 
 
@@ -290,4 +342,6 @@ def slice_scene(scene: PackedScene, lo: int, hi: int) -> PackedScene:
         ego_slot=scene.ego_slot[lo:hi].copy(), first_slot=scene.first_slot[lo:hi].copy(),
         ped_speed_desired=plane(scene.ped_speed_desired), route_off=route_off, route_xy=route_xy,
         n_entities=scene.n_entities[lo:hi].copy(),
+        rn_of=scene.rn_of[lo:hi].copy(), rn_poly_off=scene.rn_poly_off, rn_edge_off=scene.rn_edge_off,
+        rn_edges=scene.rn_edges, rn_has_area=scene.rn_has_area,
     )

@@ -66,7 +66,10 @@ def two_knot_rows(cfg: SyntheticConfig) -> np.ndarray:
     return rows
 
 
-def pack_synthetic(cfg: SyntheticConfig) -> PackedScene:
+def pack_synthetic(cfg: SyntheticConfig, road_network=None) -> PackedScene:
+    """Pack a synthetic configuration; `road_network` (optional) is shared by all its scenarios."""
+    from .packing import pack_road_networks
+
     N, M = cfg.N, cfg.M
     NM = N * M
     rows = two_knot_rows(cfg).reshape(NM * 2, 7)
@@ -113,6 +116,8 @@ def pack_synthetic(cfg: SyntheticConfig) -> PackedScene:
         route_off=route_off,
         route_xy=np.ascontiguousarray(route),
         n_entities=np.full(N, M, np.int32),
+        **(dict(zip(("rn_of", "rn_poly_off", "rn_edge_off", "rn_edges", "rn_has_area"),
+                    pack_road_networks([road_network] * N))) if road_network is not None else {}),
     )
 
 

@@ -1,8 +1,9 @@
 """
 OpenSCENARIO ingest -- ``import_scenario`` with the reference's signature and conventions
 (reference scenario_gym/xosc_interface/read.py:20-282, catalogs.py:30-84) on top of
-``xml.etree.ElementTree``.  Road networks are not loaded (out of scope for the rollout path);
-``scenario.road_network`` is ``None``.
+``xml.etree.ElementTree``.  A JSON road network next to the file is loaded into
+``scenario.road_network`` (surfaces only, see road_network.py); a missing file gives ``None`` as in
+the reference (read.py:75-85).
 """
 from __future__ import annotations
 
@@ -15,6 +16,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 from .entity import ENTITY_CLASS_BY_TAG, BoundingBox, CatalogEntry, Entity, Pedestrian, Vehicle
+from .road_network import RoadNetwork
 from .scenario import Scenario
 from .trajectory import Trajectory
 
@@ -105,6 +107,27 @@ def relabel_scenario(scenario: Scenario) -> Scenario:
     return scenario
 
 
+@lru_cache(maxsize=15)
+def _road_network_from_json(filepath: str, mtime: float) -> RoadNetwork:
+    return RoadNetwork.create_from_json(filepath)
+
+
+def _load_road_network(root, cwd: str) -> Optional[RoadNetwork]:
+    """RoadNetwork/SceneGraphFile or LogicFile of the scenario (reference read.py:65-85); JSON only."""
+    node = root.find("RoadNetwork/SceneGraphFile")
+    if node is None:
+        node = root.find("RoadNetwork/LogicFile")
+    if node is None:
+        return None
+    rn_path = node.attrib["filepath"]
+    filepath = rn_path if os.path.isabs(rn_path) else os.path.join(cwd, rn_path)
+    if os.path.splitext(filepath)[1] == "":
+        filepath = f"{filepath}.json"
+    if not filepath.endswith(".json") or not os.path.exists(filepath):
+        return None
+    return _road_network_from_json(filepath, os.path.getmtime(filepath))
+
+
 def import_scenario(osc_file: str, relabel: bool = True, entity_types=None) -> Scenario:
     """Import a scenario from an OpenSCENARIO file (reference read.py:20-189)."""
     if not os.path.exists(osc_file):
@@ -121,6 +144,7 @@ def import_scenario(osc_file: str, relabel: bool = True, entity_types=None) -> S
             if fn.endswith(".xosc"):
                 name, entries = read_catalog_cached(os.path.join(path, fn))
                 catalogs[name] = entries
+    road_network = _load_road_network(root, cwd)
     entities: Dict[str, Entity] = {}
     for obj in root.iterfind("Entities/ScenarioObject"):
         ref = obj.attrib["name"]
@@ -171,8 +195,8 @@ def import_scenario(osc_file: str, relabel: bool = True, entity_types=None) -> S
         props, files = _properties(header)
         if files and "files" not in props:
             props["files"] = files
-    scenario = Scenario(list(entities.values()),
-                        name=os.path.splitext(os.path.basename(osc_file))[0], properties=props)
+    scenario = Scenario(list(entities.values()), name=os.path.splitext(os.path.basename(osc_file))[0],
+                        road_network=road_network, properties=props)
     return relabel_scenario(scenario) if relabel else scenario
 
 

@@ -440,3 +440,70 @@ def test_recorded_poses_and_to_scenario():
     # replaying the recorded scenario reproduces the ego's path at the recorded times
     t_mid = ego[len(ego) // 2, 0]
     assert np.allclose(new.ego.trajectory.position_at_t(t_mid), ego[len(ego) // 2, 1:])
+
+
+def _network_from_golden(g, stem):
+    """The reference's surfaces of a road network (tests/golden/road.npz) as a RoadNetwork of custom layers."""
+    from scenario_gym_b200.road_network import PolygonArea, RoadGeometry, RoadNetwork
+
+    class OnlyDriveable(RoadGeometry):
+        driveable, walkable, impenetrable = True, False, False
+
+    class OnlyWalkable(RoadGeometry):
+        driveable, walkable, impenetrable = False, True, False
+
+    class OnlyImpenetrable(RoadGeometry):
+        driveable, walkable, impenetrable = False, False, True
+
+    layers = {}
+    for tag, cls, count in zip("dwi", (OnlyDriveable, OnlyWalkable, OnlyImpenetrable), g[f"road_net/{stem}/n"]):
+        objs = []
+        for k in range(int(count)):
+            holes, j = [], 0
+            while f"road_net/{stem}/{tag}{k}/hole{j}" in g:
+                holes.append(g[f"road_net/{stem}/{tag}{k}/hole{j}"])
+                j += 1
+            objs.append(cls(f"{tag}{k}", PolygonArea(g[f"road_net/{stem}/{tag}{k}/ext"], holes)))
+        layers[f"layer_{tag}"] = objs
+    return RoadNetwork(roads=[], intersections=[], **layers)
+
+
+def test_ego_off_road_on_the_reference_scenarios():
+    """
+    terminal_conditions=["max_length", "ego_off_road"] on the reference's own test scenarios with
+    their road networks (surfaces as the reference builds them): same tick counts, end times and
+    ego metrics as the reference (tests/golden/road.npz, road_xosc/*).
+    """
+    g, gx = golden("road"), golden("xosc")
+    names = sorted({k.split("/")[1] for k in g if k.startswith("road_xosc/")})
+    nets = {}
+    scenarios = []
+    for name in names:
+        stem = str(g[f"road_xosc/{name}/network"])
+        if stem not in nets:
+            nets[stem] = _network_from_golden(g, stem)
+        inp = sub(gx, f"xosc/{name}/in")
+        sc = scenario_from_golden(inp, manifest()["xosc"][name]["refs"])
+        sc.road_network = nets[stem]
+        scenarios.append(sc)
+    gym = ScenarioGym(metrics=[EgoAvgSpeed(), EgoDistanceTravelled()],
+                      terminal_conditions=["max_length", "ego_off_road"])
+    gym.set_scenarios(scenarios)
+    gym.rollout()
+    ms = gym.get_metrics()
+    ticks = gym._engine.get("tick")
+    for n, name in enumerate(names):
+        assert int(ticks[n]) == int(g[f"road_xosc/{name}/n_ticks"]), name
+        assert gym.states[n].t == float(g[f"road_xosc/{name}/t_end"]), name
+        assert close(ms[n]["ego_avg_speed"], g[f"road_xosc/{name}/ego_avg_speed"]), name
+        assert close(ms[n]["ego_distance_travelled"], g[f"road_xosc/{name}/ego_distance_travelled"]), name
+    # moving a scenario's ego trajectory off the network ends it at the first tick
+    inp = sub(gx, f"xosc/{names[0]}/in")
+    sc = scenario_from_golden(inp, manifest()["xosc"][names[0]]["refs"])
+    sc.road_network = nets[str(g[f"road_xosc/{names[0]}/network"])]
+    data = np.array(sc.ego.trajectory.data)
+    data[:, 1] += 5000.0
+    sc.ego.trajectory = Trajectory(data)
+    gym.set_scenario(sc)
+    gym.rollout()
+    assert int(gym._engine.get("tick")[0]) == 1

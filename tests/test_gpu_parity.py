@@ -151,6 +151,38 @@ def test_social_force_golden():
         check_against_golden(make_gpu, scene, p, sub(g, f"ped/{n}/out"), n, list(range(M)))
 
 
+def test_road_network_golden():
+    """Boundary forces among buildings + the ego_off_road terminal condition (general kernel)."""
+    g = golden("road")
+    cfg = golden_cases.ped_cfg()
+    scene = pack_synthetic(cfg, road_network=golden_cases.road_network(golden_cases.ROAD_PED_GEOMETRY))
+    p = _params(timestep=cfg.dt)
+    M = cfg.M
+    eng = make_gpu(scene, p)
+    eng.reset()
+    for k in range(1, cfg.T + 1):
+        eng.rollout(1)
+        goal = eng.get("goal_idx").reshape(cfg.N, M)
+        force = eng.get("force").reshape(2, cfg.N, M)
+        for n in range(cfg.N):
+            out = sub(g, f"road_ped/{n}/out")
+            assert np.array_equal(goal[n], out["goal"][k]), f"goal_idx scenario {n} tick {k}"
+            close(force[:, n].T, out["force"][k], "social force with boundary forces")
+    for n in range(cfg.N):
+        check_against_golden(make_gpu, scene, p, sub(g, f"road_ped/{n}/out"), n, list(range(M)))
+    cfg = golden_cases.veh_cfg()
+    scene = pack_synthetic(cfg, road_network=golden_cases.road_network(golden_cases.ROAD_VEH_GEOMETRY))
+    p = _params(timestep=cfg.dt, terminal=abi.TERM_MAX_LENGTH | abi.TERM_EGO_OFF_ROAD)
+    for n in range(cfg.N):
+        check_against_golden(make_gpu, scene, p, sub(g, f"road_veh/{n}/out"), n, list(range(cfg.M)),
+                             actions=cfg.actions)
+    # and on a large batch against the oracle: a crowd scene with a road network takes the general kernel
+    big = synthetic.crowd_config(seed=21, N=2, M=300, T=6, side=6.0)
+    scene = pack_synthetic(big, road_network=golden_cases.road_network(golden_cases.ROAD_PED_GEOMETRY))
+    gpu, cpu = _run_both(scene, _params(timestep=big.dt))
+    compare_engines(gpu, cpu, scene, "crowd with buildings", check_ped=True)
+
+
 def test_pid_golden():
     from test_oracle_golden import pid_cases
 

@@ -108,6 +108,44 @@ def test_social_force():
             np.testing.assert_allclose(eng.get("force")[:, sl].T, out["force"][k], rtol=1e-9, atol=1e-9)
 
 
+def test_road_network_surfaces():
+    """
+    Road-network coupling: social-force boundary forces among buildings and the
+    ego_off_road terminal condition, against rollouts of the reference with the same geometry.
+    """
+    g = golden("road")
+    # (a) pedestrians among buildings: per-tick forces, goals, poses
+    cfg = golden_cases.ped_cfg()
+    scene = pack_synthetic(cfg, road_network=golden_cases.road_network(golden_cases.ROAD_PED_GEOMETRY))
+    assert scene.n_networks == 1 and scene.rn_has_area.tolist() == [1, 1, 1]
+    p = _params(timestep=cfg.dt)
+    M = cfg.M
+    plain = golden("ped")
+    differs = False
+    for n in range(cfg.N):
+        out = sub(g, f"road_ped/{n}/out")
+        check_against_golden(make_oracle, scene, p, out, n, list(range(M)))
+        eng = make_oracle(scene, p)
+        eng.reset()
+        sl = slice(n * M, (n + 1) * M)
+        for k in range(1, int(out["n_ticks"]) + 1):
+            eng.rollout(1)
+            assert np.array_equal(eng.get("goal_idx")[sl], out["goal"][k]), f"goal_idx at tick {k}"
+            np.testing.assert_allclose(eng.get("force")[:, sl].T, out["force"][k], rtol=1e-9, atol=1e-9)
+        differs |= not np.allclose(out["force"][5], sub(plain, f"ped/{n}/out")["force"][5])
+    assert differs, "the buildings must change the forces (the case must exercise the boundary force)"
+    # (b) vehicles leaving the driveable surface
+    cfg = golden_cases.veh_cfg()
+    scene = pack_synthetic(cfg, road_network=golden_cases.road_network(golden_cases.ROAD_VEH_GEOMETRY))
+    p = _params(timestep=cfg.dt, terminal=abi.TERM_MAX_LENGTH | abi.TERM_EGO_OFF_ROAD)
+    ticks = []
+    for n in range(cfg.N):
+        out = sub(g, f"road_veh/{n}/out")
+        check_against_golden(make_oracle, scene, p, out, n, list(range(cfg.M)), actions=cfg.actions)
+        ticks.append(int(out["n_ticks"]))
+    assert min(ticks) < cfg.T and max(ticks) == cfg.T, "some egos leave the road, some stay"
+
+
 def pid_cases():
     from helpers import xosc_spec
 
