@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 9
+#define SG_ABI_VERSION 10
 
 /* entity slot kinds (who produces the slot's next pose each tick) */
 enum SgKind {
@@ -120,6 +120,13 @@ typedef struct SgParams {
   /* SocialForce boundary forces, pedestrian/social_force.py:24-29, 86-104, 190-211 */
   double sf_boundary_repulse_U, sf_boundary_repulse_R;         /* walkable surface: 10.0, 0.2 */
   double sf_imp_boundary_repulse_U, sf_imp_boundary_repulse_R; /* impenetrable surface: 2.0, 0.1 */
+  /* SocialForce random fluctuations (RandomWalkParameters.std_lon / std_lat, random_walk.py:13-19,
+     drawn at social_force.py:106-108).  The reference draws them from the global numpy generator, so
+     no engine can reproduce its values: with a non-zero std the engine adds N(0, std) noise from its
+     own counter-based stream (a function of sf_noise_seed, scenario, slot and tick; the CPU oracle
+     evaluates the same function).  std = 0 (the parity configurations) adds the bias exactly. */
+  double sf_std_lon, sf_std_lat;
+  uint64_t sf_noise_seed;
 } SgParams;
 
 /* immutable description of N scenarios x M slots */
@@ -172,6 +179,10 @@ typedef struct SgScene {
   const int64_t* rn_edge_off; /* [n_rn_polys+1] */
   const double* rn_edges;     /* [n_rn_edges][4] */
   const uint8_t* rn_has_area; /* [3*n_networks] */
+  /* Per-agent VehicleController limits (controller.py:64-98 are constructor arguments of each
+     instance): [4][N*M] max_steer, max_accel, max_speed (NaN = None), allow_reverse (0 / 1); NULL: every
+     vehicle / PID slot uses the SgParams values. */
+  const double* veh_limits;
 } SgScene;
 
 /* one recorded ego-collision rising edge (metrics/collision.py:70-75) */
@@ -302,6 +313,13 @@ int sg_future_collisions(const SgScene* scene, const double* t, const int32_t* s
    and by the tests that pin the device stream against numpy.) */
 int sg_fill_random_actions(const SgActionRng* rng, int tick0, int n_ticks, int64_t nm, double* out,
                            int device, void* stream);
+
+/* State.get_entities_in_radius (state/state.py:352-372) for a whole batch: out[n*M + s] = 1 iff slot s
+   of scenario n is present and its position lies strictly inside Point(x[n], y[n]).buffer(r[n]) --
+   GEOS' 64-gon, the predicate of the pedestrians' sensor.  Scenarios with r[n] <= 0 are skipped
+   (their rows are zeroed).  x, y, r [N], out [N*M]: device memory. */
+int sg_entities_in_radius(const SgState* state, int n_scenarios, int n_slots, const double* x, const double* y,
+                          const double* r, uint8_t* out, int device, void* stream);
 
 /* Measurement aid for the secondary roofline (bench.py): DFMA thread-instructions per second this
    GPU sustains at its current clocks (8 independent chains per thread, all SMs, best of 3 timed

@@ -167,6 +167,16 @@ class OracleEngine:
             raise RuntimeError(self.lib["last_error"]().decode())
         return out.astype(bool)
 
+    def entities_in_radius(self, x, y, r) -> np.ndarray:
+        N, M = self.scene.N, self.scene.M
+        a = [np.ascontiguousarray(np.broadcast_to(np.asarray(v, np.float64), (N,))) for v in (x, y, r)]
+        out = np.zeros(N * M, np.uint8)
+        rc = self.lib["entities_in_radius"](C.byref(self._st), N, M, a[0].ctypes.data, a[1].ctypes.data,
+                                            a[2].ctypes.data, out.ctypes.data, 0, None)
+        if rc:
+            raise RuntimeError(self.lib["last_error"]().decode())
+        return out.astype(bool).reshape(N, M)
+
     def events(self) -> np.ndarray:
         n = min(int(self.state["event_count"][0]), self.state["_event_cap"])
         ev = self.state["events"][:n]

@@ -744,6 +744,24 @@ static void boundary_force(const SgScene* sc, int n, int k, double px, double py
   out[1] = U / R * u1 * ex;
 }
 
+/* SocialForce noise with std != 0: the ENGINE's counter-based stream (include/sg_b200.h, SgParams.sf_std_*);
+   the reference draws from numpy's global generator (social_force.py:106-108), which nothing can reproduce. */
+static uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+static void noise2(uint64_t seed, int64_t i, int tick, double z[2]) {
+  uint64_t a = splitmix64(seed ^ splitmix64((uint64_t)i * 0x9E3779B97F4A7C15ULL + (uint64_t)(unsigned)tick));
+  uint64_t b = splitmix64(a);
+  double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+  double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
+  double r = sqrt(-2.0 * log(u1));
+  z[0] = r * cos(2.0 * M_PI * u2);
+  z[1] = r * sin(2.0 * M_PI * u2);
+}
+
 static void pedestrian_step(const SgScene* sc, const SgParams* p, SgState* st, int n, int s,
                             double next_t, double out[6]) {
   int64_t nm = NM, i = IDX(n, s);
@@ -820,9 +838,16 @@ static void pedestrian_step(const SgScene* sc, const SgParams* p, SgState* st, i
       boundary_force(sc, n, 2, pose[0], pose[1], p->sf_imp_boundary_repulse_U, p->sf_imp_boundary_repulse_R, fb);
       F[0] += sign * fb[0]; F[1] += sign * fb[1];
     }
-    /* noise std = 0 (:106-108) */
-    speed = py_min(norm2(F[0], F[1]) + p->sf_bias_lon, speed_desired * p->sf_max_speed_factor);
-    heading = atan2(F[1], F[0]) + p->sf_bias_lat;
+    /* random fluctuations :106-108; np.random.normal(bias, 0) == bias */
+    double speed_rand = p->sf_bias_lon, heading_rand = p->sf_bias_lat;
+    if (p->sf_std_lon != 0.0 || p->sf_std_lat != 0.0) {
+      double z[2];
+      noise2(p->sf_noise_seed, i, st->tick[n], z);
+      speed_rand = p->sf_bias_lon + p->sf_std_lon * z[0];
+      heading_rand = p->sf_bias_lat + p->sf_std_lat * z[1];
+    }
+    speed = py_min(norm2(F[0], F[1]) + speed_rand, speed_desired * p->sf_max_speed_factor);
+    heading = atan2(F[1], F[0]) + heading_rand;
     st->force[i] = F[0];
     st->force[nm + i] = F[1];
   } else { /* agent.py:65-68 reached goal */
@@ -899,17 +924,23 @@ static void tick_scenario(const SgScene* sc, const SgParams* p, SgState* st, con
               steer = (double)in->actions_f32[((int64_t)k_action * 2 + 1) * nm + i];
             }
           }
-          /* VehicleController._step controller.py:105-140 */
-          accel = np_clip(accel, -p->veh_max_accel, p->veh_max_accel);
-          steer = np_clip(steer, -p->veh_max_steer, p->veh_max_steer);
+          /* VehicleController._step controller.py:105-140; the limits are per controller instance (:64-98) */
+          double max_steer = p->veh_max_steer, max_accel = p->veh_max_accel, max_speed = p->veh_max_speed;
+          int allow_reverse = p->veh_allow_reverse;
+          if (sc->veh_limits) {
+            max_steer = sc->veh_limits[i]; max_accel = sc->veh_limits[nm + i];
+            max_speed = sc->veh_limits[2 * nm + i]; allow_reverse = sc->veh_limits[3 * nm + i] != 0.0;
+          }
+          accel = np_clip(accel, -max_accel, max_accel);
+          steer = np_clip(steer, -max_steer, max_steer);
           double dt = next_t - t;
           double dx = spd * cos(h), dy = spd * sin(h), dh = spd * tan(steer) / l;
           pose[0] += dx * dt;
           pose[1] += dy * dt;
           pose[3] += dh * dt;
           double ns = spd + accel * dt;
-          if (!p->veh_allow_reverse) ns = fmax(0.0, ns);
-          if (!isnan(p->veh_max_speed)) ns = fmin(p->veh_max_speed, ns);
+          if (!allow_reverse) ns = fmax(0.0, ns);
+          if (!isnan(max_speed)) ns = fmin(max_speed, ns);
           newspeed[s] = ns;
           memcpy(np_, pose, 48);
           newpres[s] = 1;
@@ -1156,6 +1187,18 @@ int sgo_position_at_t(const double* rows, int64_t K, double t, int mode, double*
   return position_at_t(rows, K, t, mode, out);
 }
 void sgo_velocity_at_t(const double* rows, int64_t K, double t, double* out) { velocity_at_t(rows, K, t, out); }
+/* State.get_entities_in_radius, state/state.py:352-372 */
+int sgo_entities_in_radius(const SgState* st, int n_scenarios, int n_slots, const double* x, const double* y,
+                           const double* r, uint8_t* out, int device, void* stream) {
+  (void)device; (void)stream;
+  ngon_init();
+  int64_t nm = (int64_t)n_scenarios * n_slots;
+  for (int64_t i = 0; i < nm; ++i) {
+    int n = (int)(i / n_slots);
+    out[i] = (uint8_t)(r[n] > 0.0 && st->present[i] && in_buffer(x[n], y[n], r[n], st->pose[i], st->pose[nm + i]));
+  }
+  return 0;
+}
 int sgo_polygon_side(const double* edges, int64_t n_edges, double px, double py) {
   return polygon_side(edges, 0, n_edges, px, py);
 }

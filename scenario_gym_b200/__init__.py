@@ -6,6 +6,7 @@ rollout path; the arithmetic runs in hand-written sm_100a kernels (``csrc/``) re
 the C ABI of ``include/sg_b200.h``.  Importing the package does not need a GPU; constructing a
 gym / engine does (there is no CPU fallback).
 """
+from .actions import FixedTAction, ScenarioAction, UpdateStateVariableAction, UserDefinedAction
 from .entity import BoundingBox, CatalogEntry, Entity, MiscObject, Pedestrian, Vehicle
 from .gym import ScenarioGym
 from .plugins import (RSS, Action, ActionTableAgent, Agent, CollisionMetric, CollisionObservation,
@@ -15,7 +16,8 @@ from .plugins import (RSS, Action, ActionTableAgent, Agent, CollisionMetric, Col
                       Observation, PedestrianAction, PedestrianAgent, PIDAgent, PIDController, ReplayTrajectoryAgent,
                       ReplayTrajectoryController, RSSDistances, RSSParameters, Sensor,
                       SingleEntityObservation, SocialForce, SocialForceParameters, StateCallback,
-                      TeleportAction, VehicleAction, VehicleController)
+                      TeleportAction, VehicleAction, VehicleController, cache_mean, cache_metric,
+                      CollisionPointMetric, PedestrianController, PedestrianObservation, PedestrianSensor)
 from .road_network import RoadNetwork
 from .scenario import Scenario
 from .state import State

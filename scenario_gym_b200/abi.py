@@ -11,7 +11,7 @@ import math
 import os
 from typing import Dict, Optional
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # SgKind
 KIND_EMPTY, KIND_REPLAY, KIND_AGENT_REPLAY, KIND_VEHICLE, KIND_PEDESTRIAN, KIND_HOST, KIND_PID = range(7)
@@ -75,6 +75,9 @@ class SgParams(C.Structure):
         ("sf_boundary_repulse_R", C.c_double),
         ("sf_imp_boundary_repulse_U", C.c_double),
         ("sf_imp_boundary_repulse_R", C.c_double),
+        ("sf_std_lon", C.c_double),
+        ("sf_std_lat", C.c_double),
+        ("sf_noise_seed", C.c_uint64),
     ]
 
 
@@ -111,6 +114,7 @@ class SgScene(C.Structure):
         ("rn_edge_off", _p),
         ("rn_edges", _p),
         ("rn_has_area", _p),
+        ("veh_limits", _p),
     ]
 
 
@@ -248,7 +252,7 @@ STATE_FIELDS = [
 SCENE_FIELDS = [
     "kind", "etype", "box", "traj_off", "traj_rows", "union_off", "union_t", "union_x",
     "t0", "length", "ego_slot", "first_slot", "ped_speed_desired", "route_off", "route_xy",
-    "rn_of", "rn_poly_off", "rn_edge_off", "rn_edges", "rn_has_area",
+    "rn_of", "rn_poly_off", "rn_edge_off", "rn_edges", "rn_has_area", "veh_limits",
 ]
 
 
@@ -324,6 +328,8 @@ def bind(lib: C.CDLL, prefix: str) -> Dict[str, object]:
         [C.POINTER(SgScene), _p, _p, C.c_double, C.c_int, _p, C.c_int, _p])
     get("fill_random_actions", C.c_int,
         [C.POINTER(SgActionRng), C.c_int, C.c_int, C.c_int64, _p, C.c_int, _p])
+    get("entities_in_radius", C.c_int,
+        [C.POINTER(SgState), C.c_int, C.c_int, _p, _p, _p, _p, C.c_int, _p])
     get("measure_fp64_peak", C.c_int, [C.POINTER(C.c_double), C.c_int, _p], required=False)
     get("rollout_host", C.c_int,
         [C.POINTER(SgScene), C.POINTER(SgScene), C.POINTER(SgParams), C.POINTER(SgState),

@@ -54,7 +54,7 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
   const uint32_t veh_bits = (1u << SG_KIND_VEHICLE), ok_bits = veh_bits | (1u << SG_KIND_EMPTY);
   // the ego_off_road terminal condition and the boundary forces live in the general kernel only
   const bool roads = (p->terminal & SG_TERM_EGO_OFF_ROAD) != 0;
-  const bool veh_only = (sc->kind_mask & veh_bits) && !(sc->kind_mask & ~ok_bits) && !roads;
+  const bool veh_only = (sc->kind_mask & veh_bits) && !(sc->kind_mask & ~ok_bits) && !roads && !sc->veh_limits;
   const bool grid_ok = ped && p->ped_distance_threshold > 0.0 && p->ped_distance_threshold < 1.0e6 &&
                        !(p->features & SG_FEAT_NO_GRID);
   GroupLayout L = make_layout(sc->n_slots, ped, rss, veh_only, grid_ok);
@@ -197,6 +197,17 @@ int sg_fill_random_actions(const SgActionRng* rng, int tick0, int n_ticks, int64
   return 0;
 }
 
+int sg_entities_in_radius(const SgState* state, int n_scenarios, int n_slots, const double* x, const double* y,
+                          const double* r, uint8_t* out, int device, void* stream) {
+  if (!state || !x || !y || !r || !out) return set_msg("null argument");
+  if (n_scenarios < 1 || n_slots < 1) return set_msg("empty batch");
+  cudaError_t err = cudaSetDevice(device);
+  if (err != cudaSuccess) return set_err("cudaSetDevice", err);
+  err = sgi_launch_radius((cudaStream_t)stream, *state, n_scenarios, n_slots, x, y, r, out);
+  if (err != cudaSuccess) return set_err("sg_radius_kernel launch", err);
+  return 0;
+}
+
 int sg_measure_fp64_peak(double* inst_per_s, int device, void* stream) {
   if (!inst_per_s) return set_msg("null argument");
   cudaError_t err = cudaSetDevice(device);
@@ -249,6 +260,7 @@ static int scene_copy_list(const SgScene* h, const SgScene* d, CopyItem* items) 
   ITEM(ped_speed_desired, NM * 8);
   ITEM(route_off, (NM + 1) * 8);
   ITEM(route_xy, h->n_route_pts * 2 * 8);
+  ITEM(veh_limits, 4 * NM * 8);
   if (h->n_networks > 0) {
     ITEM(rn_of, N * 4);
     ITEM(rn_poly_off, (3 * (int64_t)h->n_networks + 1) * 8);

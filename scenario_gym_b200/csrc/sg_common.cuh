@@ -497,7 +497,7 @@ SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c, 
                             const double pose[6], const double vel[6], double t, double prev_t,
                             double next_t, double sight_cos, int& goal, double force[2],
                             double& speed_io, double out[6], bool use_grid, double ox, double oy,
-                            double inv_cs) {
+                            double inv_cs, int tick) {
   if (!PED) return;
   const double* route = nullptr;
   int R = 0, ncand = 0;
@@ -650,8 +650,14 @@ SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c, 
   }
   double speed, heading;
   if (walking) {
-    speed = py_min(norm2(F0, F1) + p.sf_bias_lon, speed_desired * p.sf_max_speed_factor);
-    heading = atan2(F1, F0) + p.sf_bias_lat;
+    double speed_rand = p.sf_bias_lon, heading_rand = p.sf_bias_lat;  // np.random.normal(bias, 0) == bias
+    if (p.sf_std_lon != 0.0 || p.sf_std_lat != 0.0) {
+      const double2 z = sg_noise2(p.sf_noise_seed, c.i, tick);
+      speed_rand = p.sf_bias_lon + p.sf_std_lon * z.x;
+      heading_rand = p.sf_bias_lat + p.sf_std_lat * z.y;
+    }
+    speed = py_min(norm2(F0, F1) + speed_rand, speed_desired * p.sf_max_speed_factor);
+    heading = atan2(F1, F0) + heading_rand;
     force[0] = F0;
     force[1] = F1;
   } else {  // agent.py:65-68

@@ -649,8 +649,14 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
           double speed, heading, F0 = 0.0, F1 = 0.0;
           if (c.wflag[s]) {
             F0 = c.fcs[s]; F1 = c.fcs[G + s];
-            speed = py_min(norm2(F0, F1) + p.sf_bias_lon, sc.ped_speed_desired[i] * p.sf_max_speed_factor);
-            heading = atan2(F1, F0) + p.sf_bias_lat;
+            double speed_rand = p.sf_bias_lon, heading_rand = p.sf_bias_lat;
+            if (p.sf_std_lon != 0.0 || p.sf_std_lat != 0.0) {  // engine-defined noise stream (sg_device.cuh)
+              const double2 z = sg_noise2(p.sf_noise_seed, i, tick - 1);
+              speed_rand = p.sf_bias_lon + p.sf_std_lon * z.x;
+              heading_rand = p.sf_bias_lat + p.sf_std_lat * z.y;
+            }
+            speed = py_min(norm2(F0, F1) + speed_rand, sc.ped_speed_desired[i] * p.sf_max_speed_factor);
+            heading = atan2(F1, F0) + heading_rand;
           } else {  // agent.py:65-68
             speed = 0; heading = 0;
           }

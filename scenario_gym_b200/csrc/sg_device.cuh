@@ -368,3 +368,25 @@ SG_DEV void boundary_force(const SgScene& sc, int n, int k, double px, double py
   out[0] = U / R * u0 * ex;
   out[1] = U / R * u1 * ex;
 }
+
+// ----------------------------------------------------------------------------------
+// SocialForce noise (SgParams.sf_std_*): two independent N(0, 1) values as a pure function of
+// (seed, slot index, tick) -- splitmix64 of the counter, Box-Muller on the two 53-bit uniforms.
+// Engine-defined (the reference draws from numpy's global generator: not reproducible by design).
+// ----------------------------------------------------------------------------------
+SG_DEV uint64_t sg_splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+static __device__ __noinline__ double2 sg_noise2(uint64_t seed, int64_t i, int tick) {
+  const uint64_t a = sg_splitmix64(seed ^ sg_splitmix64((uint64_t)i * 0x9E3779B97F4A7C15ULL + (uint64_t)(unsigned)tick));
+  const uint64_t b = sg_splitmix64(a);
+  const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740992.0);  // (0, 1]
+  const double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);          // [0, 1)
+  const double r = sqrt(-2.0 * log(u1));
+  double sn, cs;
+  sincos(2.0 * M_PI * u2, &sn, &cs);
+  return make_double2(r * cs, r * sn);
+}

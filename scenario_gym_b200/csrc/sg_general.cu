@@ -142,7 +142,7 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     if (PED)  // every lane calls: whole warps of a scenario share the neighbour terms
       pedestrian_step<PED>(sc, p, c, kind == SG_KIND_PEDESTRIAN && e.present, G >= 32, e.pose, e.vel, t,
                            prev_t, next_t, sight_cos, goal, force, ped_speed, ped_np, use_grid, ox, oy,
-                           grid_inv_cs);
+                           grid_inv_cs, tick);
     if (kind >= SG_KIND_AGENT_REPLAY) {  // scenario_gym.py:233-244
       if (e.present) {
         if (kind == SG_KIND_AGENT_REPLAY) {  // agent.py:125-128, extrapolate=(False, False)
@@ -186,9 +186,15 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
               accel = a.x; steer = a.y;
             }
           }
-          // VehicleController._step, controller.py:105-140
-          accel = np_clip(accel, -p.veh_max_accel, p.veh_max_accel);
-          steer = np_clip(steer, -p.veh_max_steer, p.veh_max_steer);
+          // VehicleController._step, controller.py:105-140 (limits per agent when the scene carries them)
+          double max_steer = p.veh_max_steer, max_accel = p.veh_max_accel, max_speed = p.veh_max_speed;
+          bool allow_reverse = p.veh_allow_reverse != 0;
+          if (sc.veh_limits) {
+            max_steer = sc.veh_limits[i]; max_accel = sc.veh_limits[nm + i];
+            max_speed = sc.veh_limits[2 * nm + i]; allow_reverse = sc.veh_limits[3 * nm + i] != 0.0;
+          }
+          accel = np_clip(accel, -max_accel, max_accel);
+          steer = np_clip(steer, -max_steer, max_steer);
           const double dt = next_t - t;
           const double dx = e.speed * ch, dy = e.speed * sh;
           const double dh = div_r(e.speed * tan(steer), bl, rcp_bl);
@@ -198,8 +204,8 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
           np_[1] += dy * dt;
           np_[3] += dh * dt;
           double ns = e.speed + accel * dt;
-          if (!p.veh_allow_reverse) ns = fmax(0.0, ns);
-          if (!isnan(p.veh_max_speed)) ns = fmin(p.veh_max_speed, ns);
+          if (!allow_reverse) ns = fmax(0.0, ns);
+          if (!isnan(max_speed)) ns = fmin(max_speed, ns);
           newspeed = ns;
           newpres = true;
         } else if (kind == SG_KIND_PEDESTRIAN) {

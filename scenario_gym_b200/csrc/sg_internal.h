@@ -39,3 +39,5 @@ cudaError_t sgi_launch_future(cudaStream_t s, const SgScene& sc, const double* t
 cudaError_t sgi_measure_fp64(cudaStream_t s, double* inst_per_s);
 cudaError_t sgi_launch_crowd(cudaStream_t s, const SgScene& sc, const SgParams& p, const SgState& st,
                              const SgInputs& in, int n_ticks);
+cudaError_t sgi_launch_radius(cudaStream_t s, const SgState& st, int n_scen, int M, const double* x, const double* y,
+                              const double* r, uint8_t* out);

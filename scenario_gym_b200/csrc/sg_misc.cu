@@ -88,6 +88,24 @@ cudaError_t sgi_launch_fill_actions(cudaStream_t s, const SgRngDev& rng, int n_t
   return cudaGetLastError();
 }
 
+// State.get_entities_in_radius for a batch (sg_entities_in_radius): one thread per slot
+__global__ void sg_radius_kernel(SgState st, int n_scen, int M, const double* __restrict__ x, const double* __restrict__ y,
+                                 const double* __restrict__ r, uint8_t* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nm = (int64_t)n_scen * M;
+  if (i >= nm) return;
+  const int n = (int)(i / M);
+  uint8_t hit = 0;
+  if (r[n] > 0.0 && st.present[i]) hit = in_buffer(x[n], y[n], r[n], st.pose[i], st.pose[nm + i]) ? 1 : 0;
+  out[i] = hit;
+}
+
+cudaError_t sgi_launch_radius(cudaStream_t s, const SgState& st, int n_scen, int M, const double* x, const double* y,
+                              const double* r, uint8_t* out) {
+  const int64_t nm = (int64_t)n_scen * M;
+  sg_radius_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, s>>>(st, n_scen, M, x, y, r, out);
+  return cudaGetLastError();
+}
+
 // FP64 pipe micro-benchmark (sg_measure_fp64_peak): 8 independent DFMA chains per thread
 __global__ void sg_dfma_kernel(double* __restrict__ out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;

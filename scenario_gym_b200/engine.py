@@ -207,6 +207,19 @@ class Engine:
             int(n_samples), out.data_ptr(), self.dev_index, self._stream()))
         return out.cpu().numpy().astype(bool)
 
+    def entities_in_radius(self, x, y, r) -> np.ndarray:
+        """
+        ``State.get_entities_in_radius`` for every scenario in one launch: bool [N, M], slot s of
+        scenario n present and strictly inside ``Point(x[n], y[n]).buffer(r[n])`` (r[n] <= 0: skipped).
+        """
+        args = [torch.as_tensor(np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.float64), (self.N,)))).to(self.device)
+                for a in (x, y, r)]
+        out = torch.zeros(self.N * self.M, dtype=torch.uint8, device=self.device)
+        self._check(self.lib["entities_in_radius"](C.byref(self._st), self.N, self.M, args[0].data_ptr(),
+                                                   args[1].data_ptr(), args[2].data_ptr(), out.data_ptr(),
+                                                   self.dev_index, self._stream()))
+        return out.cpu().numpy().astype(bool).reshape(self.N, self.M)
+
     def tensor(self, name: str) -> torch.Tensor:
         """The device tensor behind a state field (no copy)."""
         return self._state_t[name]

@@ -45,6 +45,19 @@ class CatalogEntry:
     properties: Dict[str, Any] = field(default_factory=dict)
     files: List[str] = field(default_factory=list)
 
+    def to_dict(self) -> Dict[str, Any]:
+        cat = self.catalog
+        if cat is not None and not isinstance(cat, dict):
+            cat = {"name": getattr(cat, "name", str(cat)), "group_name": getattr(cat, "group_name", None)}
+        return {"catalog": cat, "catalog_entry": self.catalog_entry, "catalog_category": self.catalog_category,
+                "catalog_type": self.catalog_type, "bounding_box": self.bounding_box.to_dict(),
+                "properties": self.properties, "files": self.files}
+
+    @classmethod
+    def from_dict(cls, d: Dict[str, Any]) -> "CatalogEntry":
+        return cls(d.get("catalog"), d["catalog_entry"], d["catalog_category"], d["catalog_type"],
+                   BoundingBox.from_dict(d["bounding_box"]), d.get("properties", {}), d.get("files", []))
+
 
 class Entity:
     """An entity: a catalog entry plus a trajectory (reference entity/base.py:15-183)."""
@@ -83,6 +96,16 @@ class Entity:
 
     def copy(self) -> "Entity":
         return copy(self)
+
+    def to_dict(self) -> Dict[str, Any]:
+        """reference entity/base.py:158-165"""
+        return {"ref": self.ref, "trajectory": self.trajectory.to_json(),
+                "catalog_entry": self.catalog_entry.to_dict(), "entity_class": self.__class__.__name__}
+
+    @classmethod
+    def from_dict(cls, data: Dict[str, Any]) -> "Entity":
+        return cls(CatalogEntry.from_dict(data["catalog_entry"]),
+                   trajectory=Trajectory(np.array(data["trajectory"])), ref=data.get("ref"))
 
     def get_bounding_box_points(self, pose) -> np.ndarray:
         """Corners RL, FL, FR, RR in the global frame (reference entity/base.py:100-138)."""

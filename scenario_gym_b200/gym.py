@@ -88,7 +88,10 @@ class ScenarioGym:
 
     def load_scenario(self, scenario_path: str, create_agent=_create_agent, relabel: bool = False,
                       **kwargs) -> None:
-        scenario = import_scenario(scenario_path, relabel=relabel, **kwargs)
+        if str(scenario_path).endswith(".json"):  # reference scenario_gym.py:145-146
+            scenario = Scenario.from_json(scenario_path, **kwargs)
+        else:
+            scenario = import_scenario(scenario_path, relabel=relabel, **kwargs)
         self.set_scenario(scenario, scenario_path=scenario_path, create_agent=create_agent)
 
     def load_scenarios(self, scenario_paths: List[str], create_agent=_create_agent,
@@ -138,6 +141,8 @@ class ScenarioGym:
             st._invalidate()
             st._recorded = {e: [] for e in st.scenario.entities}
             st.next_t = None
+            st._reset_actions()
+            st.update_actions()  # reference State.reset, state.py:136
         if self._host_mode:
             for n, st in enumerate(self.states):
                 st._record()
@@ -209,6 +214,7 @@ class ScenarioGym:
         self._cache = {}
         for st in self.states:
             st._invalidate()
+            st.update_actions()
         if self._host_mode:
             self._after_tick_host()
 
@@ -228,6 +234,13 @@ class ScenarioGym:
             self._cache = {}
             for st in self.states:
                 st._invalidate()
+            self._replay_scenario_actions()
+            for m in self.metrics:  # cache_metric / cache_mean on device metrics: one step on the final state
+                if isinstance(m, _DeviceMetric) and getattr(m, "_sg_cached", False):
+                    for n, st in enumerate(self.states):
+                        m._n = n
+                        m._step(st)
+                    m._n = 0
             if self._action_table is not None and not self._fetch("done").all():
                 # the device stops a scenario whose ActionTableAgents ran out of rows; the
                 # reference's agent would have raised on its next table lookup
@@ -246,7 +259,7 @@ class ScenarioGym:
             values = {}
             for metric in self._metrics_for(n):
                 if isinstance(metric, _DeviceMetric):
-                    metric._pull(self, n)
+                    metric._n = n
                 value = metric.get_state()
                 if isinstance(value, dict):
                     for k, v in value.items():
@@ -255,6 +268,9 @@ class ScenarioGym:
                 elif value is not None:
                     values[metric.name] = value
             out.append(values)
+        for metric in self.metrics:
+            if isinstance(metric, _DeviceMetric):
+                metric._n = 0
         return out[0] if len(out) == 1 else out
 
     def close(self) -> None:
@@ -296,17 +312,20 @@ class ScenarioGym:
                                     bool(pr.sight_weight_use), pr.sight_angle, pr.relaxation_time,
                                     pr.ped_repulse_V, pr.ped_repulse_sigma, pr.ped_attract_C,
                                     pr.boundary_repulse_U, pr.boundary_repulse_R,
-                                    pr.imp_boundary_repulse_U, pr.imp_boundary_repulse_R))
+                                    pr.imp_boundary_repulse_U, pr.imp_boundary_repulse_R,
+                                    pr.std_lon, pr.std_lat, agent.behaviour.noise_seed))
                 elif type(agent) is PIDAgent and type(agent.controller) is PIDController \
                         and agent._trajectory is None:
                     kind, self._agent_kind[agent] = abi.KIND_PID, "device"
                     c = agent.controller
                     veh_params.add((c.max_steer, c.max_accel, c.max_speed, bool(c.allow_reverse)))
+                    kw.update(veh_limits=(c.max_steer, c.max_accel, c.max_speed, bool(c.allow_reverse)))
                     pid_params.add((c.steer_Kp, c.steer_Kd, c.accel_Kp, c.accel_Kd, c.accel_Ki))
                 elif type(agent.controller) is VehicleController:
                     kind = abi.KIND_VEHICLE
                     c = agent.controller
                     veh_params.add((c.max_steer, c.max_accel, c.max_speed, bool(c.allow_reverse)))
+                    kw.update(veh_limits=(c.max_steer, c.max_accel, c.max_speed, bool(c.allow_reverse)))
                     if type(agent) is ActionTableAgent:
                         self._agent_kind[agent] = "device"
                         tables[(n, s)] = agent.table
@@ -328,12 +347,23 @@ class ScenarioGym:
                                       road_network=sc.road_network))
             self._slot_of.append({e: s for s, e in enumerate(ents)})
             self._entity_of.append(ents)
-        if len(veh_params) > 1 or len(ped_params) > 1 or len(pid_params) > 1:
-            raise NotImplementedError("controller / behaviour parameters must be equal across agents")
-        self._veh_params = next(iter(veh_params)) if veh_params else None
+        if len(ped_params) > 1 or len(pid_params) > 1:
+            raise NotImplementedError("pedestrian behaviour / PID gain parameters must be equal across agents")
+        if len(veh_params) <= 1:  # one set of VehicleController limits: it travels in SgParams (fast kernels)
+            for sp in specs:
+                for sl in sp.slots:
+                    sl.veh_limits = None
+        self._veh_params = next(iter(veh_params)) if len(veh_params) == 1 else None
         self._ped_params = next(iter(ped_params)) if ped_params else None
         scene = pack_scenarios(specs)
         N, M = scene.N, scene.M
+        for n, st in enumerate(self.states):  # device rows behind agent.force / agent.goal_idx
+            for e, a in st.agents.items():
+                if isinstance(a, PedestrianAgent) and self._agent_kind.get(a) == "device":
+                    a._bound = (self, n * M + self._slot_of[n][e])
+        for m in self.metrics:
+            if isinstance(m, _DeviceMetric):
+                m._gym, m._n = self, 0
 
         # host-side plugins
         self._host_metric_protos = [m for m in self.metrics if not isinstance(m, _DeviceMetric)]
@@ -385,7 +415,7 @@ class ScenarioGym:
              p.sf_bias_lon, p.sf_bias_lat, p.sf_sight_weight, suse, p.sf_sight_angle,
              p.sf_relaxation_time, p.sf_ped_repulse_V, p.sf_ped_repulse_sigma, p.sf_ped_attract_C,
              p.sf_boundary_repulse_U, p.sf_boundary_repulse_R, p.sf_imp_boundary_repulse_U,
-             p.sf_imp_boundary_repulse_R) = self._ped_params
+             p.sf_imp_boundary_repulse_R, p.sf_std_lon, p.sf_std_lat, p.sf_noise_seed) = self._ped_params
             p.sf_sight_weight_use = int(suse)
         self._params = p
         trace_cap = 0
@@ -417,6 +447,30 @@ class ScenarioGym:
         self._epoch = 0
         self._host_done = [False] * N
         self._cache: Dict[str, np.ndarray] = {}
+
+    def _replay_scenario_actions(self) -> None:
+        """
+        Scenario actions after a fused rollout: the tick times of a scenario are t0 plus the timestep
+        added tick by tick (the sum the device accumulates, scenario_gym.py:229); every pending
+        action is applied at the first of them that satisfies its trigger condition.
+        """
+        pending = [n for n, st in enumerate(self.states) if st.unapplied_actions]
+        if not pending:
+            return
+        ticks, t0 = self._fetch("tick"), self._engine.scene.t0
+        for n in pending:
+            times, t = [], float(t0[n])
+            for _ in range(int(ticks[n])):
+                t = t + self.timestep
+                times.append(t)
+            self.states[n]._replay_actions(times)
+
+    def _entities_in_radius(self, n: int, x: float, y: float, r: float) -> np.ndarray:
+        """Present slots of scenario n strictly inside Point(x, y).buffer(r) (device query)."""
+        N = len(self.states)
+        xs, ys, rs = np.zeros(N), np.zeros(N), np.full(N, -1.0)
+        xs[n], ys[n], rs[n] = x, y, r
+        return self._engine.entities_in_radius(xs, ys, rs)[n]
 
     def _table_scenarios_live(self) -> bool:
         """Is any scenario with an ActionTableAgent still running (it would need another table row)?"""

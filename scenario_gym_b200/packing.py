@@ -66,6 +66,8 @@ class SlotSpec:
     traj: np.ndarray  # (K, 7) [t, x, y, z, h, p, r] as held by Trajectory.data
     box: Sequence[float] = (2.0, 4.0, 0.0, 0.0)  # width, length, center_x, center_y
     etype: int = abi.ETYPE_VEHICLE
+    # VehicleController(max_steer, max_accel, max_speed, allow_reverse) of this slot, or None: SgParams
+    veh_limits: Optional[Sequence[float]] = None
     speed_desired: float = 0.0
     route: Optional[np.ndarray] = None  # (R, 2)
     ref: str = ""
@@ -122,6 +124,7 @@ class PackedScene:
     rn_edge_off: np.ndarray = field(default=None)
     rn_edges: np.ndarray = field(default=None)
     rn_has_area: np.ndarray = field(default=None)
+    veh_limits: np.ndarray = field(default=None)  # (4, N*M) per-agent VehicleController limits, or None
 
     def __post_init__(self):
         if self.rn_of is None:  # no road networks
@@ -140,7 +143,8 @@ class PackedScene:
         return (self.M + 31) // 32
 
     def arrays(self):
-        return {k: getattr(self, k) for k in abi.SCENE_FIELDS}
+        """Every SgScene array that is present (optional ones -- veh_limits -- are left out when None)."""
+        return {k: getattr(self, k) for k in abi.SCENE_FIELDS if getattr(self, k) is not None}
 
     def kind_mask(self) -> int:
         """SgScene.kind_mask: OR of (1 << kind), or 0 when the vehicle fast path's promise
@@ -214,6 +218,10 @@ def pack_scenarios(specs: Sequence[ScenarioSpec], n_slots: Optional[int] = None)
     union_off = np.zeros(N + 1, np.int64)
     union_t, union_x = [], []
     nrow = nroute = 0
+    limits = None
+    if any(sl.veh_limits is not None for sp in specs for sl in sp.slots):
+        limits = np.zeros((4, NM), np.float64)
+        limits[0], limits[1], limits[2] = 0.7, 5.0, np.nan  # VehicleController defaults
     for n, sp in enumerate(specs):
         replay_idx = []
         for s in range(M):
@@ -227,6 +235,9 @@ def pack_scenarios(specs: Sequence[ScenarioSpec], n_slots: Optional[int] = None)
                 etype[i] = sl.etype
                 box[:, i] = sl.box
                 speed_desired[i] = sl.speed_desired
+                if limits is not None and sl.veh_limits is not None:
+                    ms, ma, mv, rev = sl.veh_limits
+                    limits[:, i] = (ms, ma, np.nan if mv is None else mv, 1.0 if rev else 0.0)
                 rows.append(tr)
                 nrow += tr.shape[0]
                 if sl.route is not None:
@@ -265,6 +276,7 @@ def pack_scenarios(specs: Sequence[ScenarioSpec], n_slots: Optional[int] = None)
         route_off=route_off,
         route_xy=np.concatenate(routes, axis=0) if routes else np.zeros((0, 2)),
         n_entities=np.array([len(s.slots) for s in specs], np.int32),
+        veh_limits=limits,
         **dict(zip(("rn_of", "rn_poly_off", "rn_edge_off", "rn_edges", "rn_has_area"),
                    pack_road_networks([s.road_network for s in specs]))),
     )
@@ -314,6 +326,7 @@ def tile_scene(scene: PackedScene, reps: int) -> PackedScene:
         n_entities=scene.n_entities[order].copy(),
         rn_of=scene.rn_of[order].copy(), rn_poly_off=scene.rn_poly_off, rn_edge_off=scene.rn_edge_off,
         rn_edges=scene.rn_edges, rn_has_area=scene.rn_has_area,
+        veh_limits=None if scene.veh_limits is None else plane(scene.veh_limits),
     )
 
 
@@ -344,4 +357,5 @@ def slice_scene(scene: PackedScene, lo: int, hi: int) -> PackedScene:
         n_entities=scene.n_entities[lo:hi].copy(),
         rn_of=scene.rn_of[lo:hi].copy(), rn_poly_off=scene.rn_poly_off, rn_edge_off=scene.rn_edge_off,
         rn_edges=scene.rn_edges, rn_has_area=scene.rn_has_area,
+        veh_limits=None if scene.veh_limits is None else plane(scene.veh_limits),
     )

@@ -13,7 +13,7 @@ from typing import Any, Dict, List, Optional, Tuple, Type
 
 import numpy as np
 
-from .entity import Entity
+from .entity import Entity, Pedestrian
 from .trajectory import Trajectory
 
 
@@ -472,6 +472,9 @@ class _DeviceMetric(Metric):
     """Built-in metric whose value is accumulated on the device; ``_pull`` reads it back."""
 
     _device = True
+    _gym = None   # bound by ScenarioGym when the scenarios are built
+    _n = 0        # scenario of the batch get_state() reports (get_metrics() walks over all of them)
+    _value = None
 
     def _reset(self, state) -> None:
         self._value = None
@@ -483,6 +486,8 @@ class _DeviceMetric(Metric):
         raise NotImplementedError
 
     def get_state(self):
+        if self._gym is not None and self._gym._engine is not None:
+            self._pull(self._gym, self._n)
         return self._value
 
 
@@ -527,6 +532,7 @@ class CollisionMetric(_DeviceMetric):
         self._value = gym._collision_events(n)
 
     def get_state(self):
+        super().get_state()
         return list(self._value or [])
 
 
@@ -568,6 +574,125 @@ class RSS(_DeviceMetric):
         self._value = {"safe_longitudinal": not (flags & 1), "safe_lateral": not (flags & 2)}
 
 
+def cache_metric(Met: Type[Metric]) -> Type[Metric]:
+    """Keep the metric's value of the last finished scenario in ``previous_value`` (metrics/base.py:76-89)."""
+    prev_step = Met._step
+    Met.previous_value = None
+    Met._sg_cached = True  # device metrics: ScenarioGym calls _step once a fused rollout has finished
+
+    def new_step(self, state):
+        prev_step(self, state)
+        if state.is_done:
+            self.previous_value = self.get_state()
+
+    Met._step = new_step
+    return Met
+
+
+def cache_mean(Met: Type[Metric]) -> Type[Metric]:
+    """
+    Running mean of the metric's value over finished scenarios; reading ``previous_value`` returns it
+    and starts a new mean (metrics/base.py:92-113).
+    """
+
+    def previous_value(self):
+        val = self._previous_value
+        self._previous_value = 0.0
+        self._prev_count = 0
+        return val
+
+    prev_step = Met._step
+    Met._previous_value = 0.0
+    Met._prev_count = 0
+    Met.previous_value = property(previous_value)
+    Met._sg_cached = True
+
+    def new_step(self, state):
+        prev_step(self, state)
+        if state.is_done:
+            self._prev_count += 1
+            self._previous_value += (self.get_state() - self._previous_value) / self._prev_count
+
+    Met._step = new_step
+    return Met
+
+
+def _clip_convex(subject: np.ndarray, clip: np.ndarray) -> np.ndarray:
+    """Sutherland-Hodgman: the part of convex polygon `subject` inside convex polygon `clip` (vertex rows)."""
+    def area2(p):
+        return float(np.dot(p[:, 0], np.roll(p[:, 1], -1)) - np.dot(np.roll(p[:, 0], -1), p[:, 1]))
+
+    if area2(clip) < 0:
+        clip = clip[::-1]
+    out = subject
+    for k in range(len(clip)):
+        a, b = clip[k], clip[(k + 1) % len(clip)]
+        if len(out) == 0:
+            break
+        side = (b[0] - a[0]) * (out[:, 1] - a[1]) - (b[1] - a[1]) * (out[:, 0] - a[0])
+        nxt = []
+        for i in range(len(out)):
+            j = (i + 1) % len(out)
+            if side[i] >= 0:
+                nxt.append(out[i])
+            if (side[i] >= 0) != (side[j] >= 0):
+                t = side[i] / (side[i] - side[j])
+                nxt.append(out[i] + t * (out[j] - out[i]))
+        out = np.array(nxt).reshape(-1, 2)
+    return out
+
+
+def _centroid(p: np.ndarray) -> np.ndarray:
+    if len(p) == 0:
+        return np.array([np.nan, np.nan])
+    x, y = p[:, 0], p[:, 1]
+    xn, yn = np.roll(x, -1), np.roll(y, -1)
+    cr = x * yn - xn * y
+    a = cr.sum() / 2.0
+    if a == 0.0:
+        return p.mean(axis=0)
+    return np.array([((x + xn) * cr).sum() / (6 * a), ((y + yn) * cr).sum() / (6 * a)])
+
+
+class CollisionPointMetric(Metric):
+    """
+    ``(ref, point, angle)`` of every entity that starts colliding with the ego: the centroid of the
+    overlap of the two boxes and the relative heading in [0, 2 pi) (reference metrics/collision.py:
+    206-262).  Host-side metric (it runs per tick on the materialised state).  The reference reads the
+    headings from ``entity.pose``, an attribute entities do not have at v0.3.1 (AttributeError on the
+    first collision); the headings of ``state.poses`` -- the evident intent -- are used here.
+    """
+
+    name = "collision_points"
+
+    def __init__(self, name: Optional[str] = None):
+        self.ego: Optional[Entity] = None
+        self.collisions: List[Tuple[str, np.ndarray, float]] = []
+        super().__init__(name=name)
+
+    def _reset(self, state) -> None:
+        self.ego = state.scenario.ego
+        self.collisions = []
+        self.last_timestep: List[Entity] = []
+
+    def _step(self, state) -> None:
+        now = state.collisions().get(self.ego, [])
+        for other in now:
+            if other not in self.last_timestep:
+                self.collisions.append(self.record_collision_position(state, other))
+        self.last_timestep = list(now)
+
+    def get_state(self):
+        return self.collisions
+
+    def record_collision_position(self, state, hazard: Entity):
+        ego_box = self.ego.get_bounding_box_points(state.poses[self.ego])
+        hazard_box = hazard.get_bounding_box_points(state.poses[hazard])
+        point = _centroid(_clip_convex(ego_box, hazard_box))
+        angle = (state.poses[hazard][3] - state.poses[self.ego][3]) % (np.pi * 2)
+        return hazard.ref, point, float(angle)
+
+
 # ------------------------------------------------------------------------------ pedestrians
 class BehaviourParameters:
     max_speed_factor = 1.3
@@ -602,33 +727,124 @@ class SocialForceParameters(RandomWalkParameters):
 
 
 class SocialForce:
-    """Social force behaviour (reference pedestrian/social_force.py:33-222), run on the device."""
+    """
+    Social force behaviour (reference pedestrian/social_force.py:33-222), run on the device.
 
-    def __init__(self, params: SocialForceParameters):
+    With ``std_lon = std_lat = 0`` the rollout reproduces the reference.  With non-zero standard
+    deviations (the reference's defaults are 2e-6 / 1e-7) the reference draws its fluctuations from
+    numpy's global generator; the engine then adds N(0, std) noise from its own counter-based stream
+    (``noise_seed``): statistically the same model, not the same numbers.
+    """
+
+    def __init__(self, params: SocialForceParameters, noise_seed: int = 0):
         self.params = params
         self.max_speed_factor = params.max_speed_factor
-        if params.std_lon != 0 or params.std_lat != 0:
-            raise ValueError(
-                "SocialForce noise draws from the global np.random in the reference; the device "
-                "engine supports std_lon = std_lat = 0 only")
+        self.noise_seed = int(noise_seed)
+
+
+@dataclass
+class PedestrianObservation(SingleEntityObservation):
+    """Observation of a pedestrian (reference pedestrian/observation.py)."""
+
+    head_rot_angle: float = 0.0
+    near_peds: Any = None
+    walkable_surface: Any = None
+    impenetrable_surface: Any = None
+
+
+class PedestrianSensor(Sensor):
+    """
+    Pedestrians within ``distance_threshold`` plus the road-network surfaces (reference
+    pedestrian/sensor.py:9-64).  On the device the query is part of the fused tick; this host class
+    serves custom agents that want the same observation.
+    """
+
+    def __init__(self, entity: Entity, head_rot_angle: float = 0.0, distance_threshold: float = 1.0):
+        super().__init__(entity)
+        self.head_rot_angle = head_rot_angle
+        self.distance_threshold = distance_threshold
+
+    def _reset(self, state):
+        return self._step(state)
+
+    def _step(self, state):
+        rn = state.scenario.road_network
+        return PedestrianObservation(
+            self.entity, *state.get_entity_data(self.entity), self.head_rot_angle,
+            self.get_nearby_pedestrians(state),
+            None if rn is None else rn.walkable_surface, None if rn is None else rn.impenetrable_surface)
+
+    def get_nearby_pedestrians(self, state):
+        x, y = state.poses[self.entity][:2]
+        return [(e, state.poses[e], state.velocities[e])
+                for e in state.get_entities_in_radius(x, y, self.distance_threshold)
+                if (isinstance(e, Pedestrian) or e.type == "Pedestrian") and e != self.entity]
+
+
+class PedestrianController(Controller):
+    """Moves the pedestrian by speed and heading (reference pedestrian/controller.py:9-46)."""
+
+    def __init__(self, entity: Entity, max_speed: float = 5.0):
+        super().__init__(entity)
+        self.max_speed = max_speed
+
+    def _reset(self, state) -> None:
+        self.speed = np.linalg.norm(state.velocities[self.entity][:2])
+
+    def _step(self, state, action: PedestrianAction):
+        speed = np.clip(action.speed, -self.max_speed, self.max_speed)
+        pose = state.poses[self.entity].copy()
+        pose[0] += speed * state.dt * np.cos(action.heading)  # state.dt: the previous interval
+        pose[1] += speed * state.dt * np.sin(action.heading)
+        pose[3] = action.heading
+        self.speed = speed
+        return pose
 
 
 class PedestrianAgent(Agent):
-    """Pedestrian following a route with a behaviour model (reference pedestrian/agent.py:15-69)."""
+    """
+    Pedestrian following a route with a behaviour model (reference pedestrian/agent.py:15-69).
+    ``force`` and ``goal_idx`` read the device rows of the agent's slot once it is part of a gym.
+    """
 
     def __init__(self, entity: Entity, route: List[np.ndarray], speed_desired: float,
                  behaviour: SocialForce, max_speed: float = 5.0, head_rot_angle: float = 0.0,
                  distance_threshold: float = 1.0):
-        super().__init__(entity, None, None)
+        super().__init__(entity, PedestrianController(entity, max_speed=max_speed),
+                         PedestrianSensor(entity, head_rot_angle=head_rot_angle,
+                                          distance_threshold=distance_threshold))
         self.route = [np.asarray(r, dtype=np.float64) for r in route]
         self.speed_desired = speed_desired
         self.behaviour = behaviour
         self.max_speed = max_speed
         self.head_rot_angle = head_rot_angle
         self.distance_threshold = distance_threshold
-        self.goal_idx = 0
-        self.force = np.array([0.0, 0.0])
+        self._bound = None  # (gym, flat slot index) once lowered to the device
+        self._goal_idx = 0
+        self._force = np.array([0.0, 0.0])
+
+    @property
+    def force(self) -> np.ndarray:
+        if self._bound is not None and self._bound[0]._engine is not None:
+            gym, i = self._bound
+            return np.array(gym._fetch("force")[:, i])
+        return self._force
+
+    @force.setter
+    def force(self, value) -> None:
+        self._force = np.asarray(value, dtype=np.float64)
+
+    @property
+    def goal_idx(self) -> int:
+        if self._bound is not None and self._bound[0]._engine is not None:
+            gym, i = self._bound
+            return int(gym._fetch("goal_idx")[i])
+        return self._goal_idx
+
+    @goal_idx.setter
+    def goal_idx(self, value: int) -> None:
+        self._goal_idx = int(value)
 
     def reset(self, state) -> None:
-        self.goal_idx = 0
-        self.force = np.array([0.0, 0.0])
+        self._goal_idx = 0
+        self._force = np.array([0.0, 0.0])

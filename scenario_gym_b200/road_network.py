@@ -29,6 +29,37 @@ def _ring(points) -> np.ndarray:
     return pts
 
 
+def _orient(ax, ay, bx, by, cx, cy) -> int:
+    """Exact sign of the orientation determinant (floating-point filter, rational arithmetic behind it)."""
+    l, r = (ax - cx) * (by - cy), (ay - cy) * (bx - cx)
+    det = l - r
+    if abs(det) > 3.3306690738754716e-16 * (abs(l) + abs(r)):
+        return 1 if det > 0 else -1
+    from fractions import Fraction as F
+
+    d = (F(ax) - F(cx)) * (F(by) - F(cy)) - (F(ay) - F(cy)) * (F(bx) - F(cx))
+    return (d > 0) - (d < 0)
+
+
+def _ring_side(pts: np.ndarray, px: float, py: float) -> int:
+    """+1 strictly inside the ring, 0 on it, -1 outside (crossing parity, exact)."""
+    inside = False
+    n = len(pts)
+    for k in range(n):
+        ax, ay = float(pts[k, 0]), float(pts[k, 1])
+        bx, by = float(pts[(k + 1) % n, 0]), float(pts[(k + 1) % n, 1])
+        straddles = (ay > py) != (by > py)
+        in_box = min(ax, bx) <= px <= max(ax, bx) and min(ay, by) <= py <= max(ay, by)
+        if not straddles and not in_box:
+            continue
+        o = _orient(ax, ay, bx, by, px, py)
+        if o == 0 and in_box:
+            return 0
+        if straddles and ((o > 0) == (by > ay)):
+            inside = not inside
+    return 1 if inside else -1
+
+
 class PolygonArea:
     """A polygon with optional holes, as rings of (x, y) vertices (open rings: no repeated end point)."""
 
@@ -54,6 +85,23 @@ class PolygonArea:
                 out.append(np.concatenate([r, np.roll(r, -1, axis=0)], axis=1))
         return np.concatenate(out, axis=0) if out else np.zeros((0, 4))
 
+    def point_side(self, x: float, y: float) -> int:
+        """+1 interior, 0 boundary, -1 exterior (the same crossing-parity rule the device applies)."""
+        x, y = float(x), float(y)
+        side = _ring_side(self.exterior, x, y)
+        if side <= 0:
+            return side
+        for h in self.interiors:
+            hs = _ring_side(h, x, y)
+            if hs == 0:
+                return 0
+            if hs > 0:
+                return -1
+        return 1
+
+    def contains(self, x: float, y: float) -> bool:
+        return self.point_side(x, y) > 0
+
     @property
     def area(self) -> float:
         def shoelace(r):
@@ -71,6 +119,10 @@ class Surface:
     @property
     def area(self) -> float:
         return float(sum(p.area for p in self.polygons))
+
+    def contains(self, x: float, y: float) -> bool:
+        """Strictly inside one member polygon."""
+        return any(p.contains(x, y) for p in self.polygons)
 
     def __len__(self) -> int:
         return len(self.polygons)
@@ -214,6 +266,15 @@ class RoadNetwork:
     @property
     def impenetrable_surface(self) -> Surface:
         return self._surface("impenetrable")
+
+    def get_geometries_at_point(self, x: float, y: float) -> Tuple[List[str], List[RoadGeometry]]:
+        """Class names and objects of the geometries strictly containing (x, y) (road_network.py:375-401)."""
+        names, geoms = [], []
+        for g in self.road_network_geometries:
+            if g.boundary.contains(x, y):
+                names.append(g.__class__.__name__)
+                geoms.append(g)
+        return names, geoms
 
     def surfaces(self) -> Tuple[Surface, Surface, Surface]:
         """(driveable, walkable, impenetrable) in the order the device indexes them."""

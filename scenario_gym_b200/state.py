@@ -24,11 +24,58 @@ class State:
         self.agents: Dict[Entity, Any] = {}
         self.state_callbacks = gym.state_callbacks
         self.entity_state: Dict[Entity, Any] = dict.fromkeys(scenario.entities)
+        self.unapplied_actions: list = []
+        self.action_apply_times: dict = {}
         self.next_t: Optional[float] = None
         self.last_keystroke = None
         self._recorded: Dict[Entity, List[Tuple[float, np.ndarray]]] = {e: [] for e in scenario.entities}
         self._snap: Optional[dict] = None
         self._collisions = None
+        self._reset_actions()
+
+    # ------------------------------------------------------------------ scenario actions
+    def _reset_actions(self) -> None:
+        """reference state.py:145-163 (_reset_data): nothing applied, entity states cleared."""
+        actions = list(getattr(self._scenario, "actions", None) or [])
+        self.unapplied_actions = actions.copy()
+        self.action_apply_times = {a: float("nan") for a in actions}
+        self.entity_state = dict.fromkeys(self._scenario.entities)
+
+    def update_actions(self) -> None:
+        """Apply the actions whose trigger condition holds now (reference state.py:241-250)."""
+        if not self.unapplied_actions:
+            return
+        still = []
+        for act in self.unapplied_actions:
+            if act.trigger_condition(self):
+                self.apply_action(act)
+                self.action_apply_times[act] = self.t
+            else:
+                still.append(act)
+        self.unapplied_actions = still
+
+    def apply_action(self, action) -> None:
+        import warnings
+
+        entity = self._scenario.entity_by_name(action.entity_ref)
+        if entity is None:
+            warnings.warn(f"No entity with name {action.entity_ref} was found for action "
+                          f"{action.__class__.__name__}.")
+        else:
+            action.apply(self, entity)
+
+    def _replay_actions(self, times) -> None:
+        """After a fused rollout: visit the tick times one by one so every action fires at its tick."""
+        if not self.unapplied_actions:
+            return
+        saved = self._snap
+        for t in times:
+            if not self.unapplied_actions:
+                break
+            self._snap = {"t": float(t), "prev_t": float(t), "done": False, "poses": {}, "velocities": {},
+                          "distances": {}}
+            self.update_actions()
+        self._snap = saved
 
     # ------------------------------------------------------------------ device sync
     def _invalidate(self) -> None:
@@ -132,3 +179,31 @@ class State:
 
     def get_entity_box_points(self, e: Entity) -> np.ndarray:
         return e.get_bounding_box_points(self.poses[e])
+
+    def get_road_info_at_entity(self, e: Entity):
+        """Names and geometries of the road network at the entity's position (reference state.py:330-338)."""
+        rn = self.scenario.road_network
+        if not rn:
+            return [], []
+        return rn.get_geometries_at_point(*self.poses[e][:2])
+
+    def get_entities_in_radius(self, x: float, y: float, r: float) -> List[Entity]:
+        """
+        Entities whose position lies strictly inside ``Point(x, y).buffer(r)`` -- the 64-gon GEOS
+        builds, not the circle (reference state.py:352-372).  Decided on the device for the whole
+        batch (``sg_entities_in_radius``) with the sensor's own predicate.
+        """
+        mask = self._gym._entities_in_radius(self._n, float(x), float(y), float(r))
+        ents = self._gym._entity_of[self._n]
+        return [e for s, e in enumerate(ents) if mask[s]]
+
+    def get_entities_in_area(self, area) -> List[Entity]:
+        """
+        Entities whose position lies strictly inside ``area`` (reference state.py:340-350): a
+        ``road_network.PolygonArea`` / ``Surface``, or a sequence of (x, y) vertices.
+        """
+        from .road_network import PolygonArea, Surface
+
+        if not isinstance(area, (PolygonArea, Surface)):
+            area = PolygonArea(area)
+        return [e for e, pose in self.poses.items() if area.contains(pose[0], pose[1])]

@@ -188,3 +188,59 @@ def test_combine_observations_fields_and_prefixes():
     assert "b_pose" in pn and "future_collision" in pn and pn.count("pose") == 1
     with pytest.raises(ValueError):
         combine_observations(SingleEntityObservation, prefixes=("a", "b"))
+
+
+def test_scenario_json_round_trip_and_actions(tmp_path):
+    """Scenario.to_json / from_json (reference scenario.py:186-319) incl. actions; action trigger rules."""
+    import numpy as np
+
+    from scenario_gym_b200 import (BoundingBox, CatalogEntry, Pedestrian, Scenario, Trajectory,
+                                   UpdateStateVariableAction, Vehicle)
+
+    ce = CatalogEntry(None, "car1", "car", "Vehicle", BoundingBox(2.0, 4.2, 1.37, 0.0), {"mass": 1.0}, ["m.osgb"])
+    pe = CatalogEntry(None, "ped", "pedestrian", "Pedestrian", BoundingBox(0.69, 0.7, 0.0, 0.0))
+    ego = Vehicle(ce, trajectory=Trajectory(np.array([[0.0, 0, 0, 0, 0, 0, 0], [4.0, 20, 1, 0, 0.1, 0, 0]])), ref="ego")
+    ped = Pedestrian(pe, trajectory=Trajectory(np.array([[1.0, 5, 5, 0, 0, 0, 0]])), ref="ped_0")
+    sc = Scenario([ego, ped], name="rt", properties={"k": 1})
+    sc.add_action(UpdateStateVariableAction(3.0, "TestAction", "ego", {"var": 1.0}), inplace=True)
+    path = str(tmp_path / "rt.json")
+    sc.to_json(path)
+    back = Scenario.from_json(path)
+    assert [type(e).__name__ for e in back.entities] == ["Vehicle", "Pedestrian"]
+    for a, b in zip(sc.entities, back.entities):
+        assert a.ref == b.ref and np.array_equal(a.trajectory.data, b.trajectory.data)
+        assert a.catalog_entry == b.catalog_entry
+    assert back.properties == {"k": 1} and back.name == "rt" and back.road_network is None
+    act = back.actions[0]
+    assert isinstance(act, UpdateStateVariableAction) and act.t == 3.0 and act.action_variables == {"var": 1.0}
+    shifted = back.reset_start(back.entities[1])  # pedestrian starts at t = 1
+    assert shifted.entities[0].trajectory.min_t == -1.0 and shifted.actions[0].t == 2.0 and back.actions[0].t == 3.0
+
+    class FakeState:
+        def __init__(self, t):
+            self.t = t
+            self.entity_state = {ego: None}
+
+    assert not act.trigger_condition(FakeState(3.0)) and act.trigger_condition(FakeState(3.0000001))
+    st = FakeState(3.5)
+    act.apply(st, ego)
+    assert st.entity_state[ego] == {"var": 1.0}
+
+
+def test_road_network_surfaces_host():
+    """RoadNetwork surfaces: class flags, point membership incl. holes, packing for the device."""
+    from oracle import golden_cases
+    from scenario_gym_b200.packing import pack_road_networks
+
+    rn = golden_cases.road_network(golden_cases.ROAD_PED_GEOMETRY)
+    d, w, i = rn.surfaces()
+    assert (len(d), len(w), len(i)) == (1, 3, 2)  # buildings are walkable too (reference class flags)
+    assert i.contains(2.0, 2.0) and not i.contains(1.8, 2.0) and not i.contains(4.5, 1.3)  # boundary / L notch
+    pav = w.polygons[0]
+    assert pav.contains(3.0, 3.0) and not pav.contains(0.5, 4.2) and pav.point_side(0.2, 4.0) == 0  # hole
+    assert abs(pav.area - (81.0 - 0.49)) < 1e-12
+    names, geoms = rn.get_geometries_at_point(2.0, 2.0)
+    assert sorted(names) == ["Building", "Pavement"]
+    rn_of, poly_off, edge_off, edges, has_area = pack_road_networks([rn, None, rn])
+    assert rn_of.tolist() == [0, -1, 0] and poly_off.tolist() == [0, 1, 4, 6] and has_area.tolist() == [1, 1, 1]
+    assert edges.shape == (edge_off[-1], 4) and edge_off[1] == 4 and edge_off[2] - edge_off[1] == 8

@@ -16,6 +16,8 @@ from scenario_gym_b200 import (RSS, ActionTableAgent, Agent, BoundingBox, Catalo
                                ReplayTrajectoryAgent, RSSDistances, Scenario, ScenarioGym, SocialForce,
                                SocialForceParameters, TeleportAction, Trajectory, Vehicle, VehicleAction,
                                VehicleController, import_scenario)
+from scenario_gym_b200 import (CollisionPointMetric, PedestrianSensor, UpdateStateVariableAction, cache_mean,
+                               cache_metric)
 from scenario_gym_b200 import abi, synthetic
 
 from helpers import golden, manifest, sub
@@ -507,3 +509,150 @@ def test_ego_off_road_on_the_reference_scenarios():
     gym.set_scenario(sc)
     gym.rollout()
     assert int(gym._engine.get("tick")[0]) == 1
+
+
+def _golden_scenario(name):
+    g = golden("xosc")
+    return scenario_from_golden(sub(g, f"xosc/{name}/in"), manifest()["xosc"][name]["refs"])
+
+
+def test_state_info_radius_queries():
+    """reference tests/test_state.py:74-100: entities within a radius of the first entity."""
+    sc = _golden_scenario("3e39a079-5653-440c-bcbe-24dc9f6bf0e6")
+    gym = ScenarioGym(timestep=0.1)
+    gym.set_scenario(sc)
+    for _ in range(50):
+        gym.step()
+    assert len(gym.state.poses) >= 2
+    e = gym.state.scenario.entities[0]
+    pose = gym.state.poses[e]
+    distances = [np.linalg.norm(p_[:3] - pose[:3]) for e_, p_ in gym.state.poses.items() if e_ != e]
+    assert len(gym.state.get_entities_in_radius(*pose[:2], np.min(distances) - 0.1)) == 1
+    assert len(gym.state.get_entities_in_radius(*pose[:2], np.max(distances) + 1)) == 1 + len(distances)
+    square = [(pose[0] - 1, pose[1] - 1), (pose[0] + 1, pose[1] - 1), (pose[0] + 1, pose[1] + 1), (pose[0] - 1, pose[1] + 1)]
+    assert e in gym.state.get_entities_in_area(square)
+    # the batched device query against the CPU oracle's restatement of the same predicate
+    from oracle.runner import OracleEngine
+
+    eng = gym._engine
+    cpu = OracleEngine(eng.scene, eng.params)
+    for k in ("pose", "present"):
+        cpu.state[k][...] = eng.get(k)
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        x, y, r = pose[0] + rng.uniform(-30, 30), pose[1] + rng.uniform(-30, 30), rng.uniform(1, 40)
+        assert np.array_equal(eng.entities_in_radius(x, y, r), cpu.entities_in_radius(x, y, r))
+    # a point on a vertex / an edge of the 64-gon is not strictly inside
+    assert not eng.entities_in_radius(pose[0] - 5.0, pose[1], 5.0)[0, gym._slot_of[0][e]]
+
+
+def test_state_actions():
+    """reference tests/test_state.py:197-207: an UpdateStateVariableAction fires during the rollout."""
+    sc = _golden_scenario("3e39a079-5653-440c-bcbe-24dc9f6bf0e6")
+    sc.add_action(UpdateStateVariableAction(3.0, "TestAction", "ego", {"var": 1.0}), inplace=True)
+    gym = ScenarioGym(timestep=0.1)
+    gym.set_scenario(sc)
+    assert not gym.state.entity_state[sc.entities[0]], "No actions should be applied."
+    gym.rollout()  # fused: the action is applied at the first tick time past 3.0
+    assert gym.state.entity_state[sc.entities[0]]["var"] == 1.0, "Action not applied."
+    act = sc.actions[0]
+    t_apply = gym.state.action_apply_times[act]
+    assert 3.0 < t_apply <= 3.0 + 0.1 + 1e-9
+    # tick by tick gives the same apply time
+    gym.reset_scenario()
+    assert not gym.state.entity_state[sc.entities[0]]
+    while not gym.state.is_done:
+        gym.step()
+    assert gym.state.action_apply_times[act] == t_apply
+
+
+def test_cache_mean_and_cache_metric():
+    """reference tests/test_metrics.py:37-77 on device metrics."""
+    names = ["3fee6507-fd24-432f-b781-ca5676c834ef", "41dac6fa-6f83-461e-a145-08692da5f3c7"]
+    gym = ScenarioGym(metrics=[EgoAvgSpeed()])
+    vals = []
+    for n in names:
+        gym.set_scenario(_golden_scenario(n))
+        gym.rollout()
+        vals.append(gym.metrics[0].get_state())
+    avg = 0.5 * (vals[0] + vals[1])
+    gym = ScenarioGym(metrics=[cache_mean(type("CachedAvg", (EgoAvgSpeed,), {}))(),
+                               cache_metric(type("CachedDist", (EgoDistanceTravelled,), {}))()])
+    assert gym.metrics[0].previous_value == 0.0
+    assert gym.metrics[0]._prev_count == 0.0
+    for n in names:
+        gym.set_scenario(_golden_scenario(n))
+        gym.rollout()
+    assert gym.metrics[0].previous_value == avg
+    assert gym.metrics[0].previous_value == 0.0
+    assert gym.metrics[1].previous_value == gym.metrics[1].get_state() > 0.0
+
+
+def test_collision_point_metric_head_on():
+    """Two boxes driving into each other: the overlap centroid lies between them on the x axis."""
+    def car(ref, x0, x1):
+        ce = CatalogEntry(None, "car", "car", "Vehicle", BoundingBox(2.0, 5.0, 0.0, 0.0))
+        tr = Trajectory(np.array([[0.0, x0, 0.0, 0, 0 if x1 > x0 else np.pi, 0, 0], [10.0, x1, 0.0, 0, 0 if x1 > x0 else np.pi, 0, 0]]))
+        return Vehicle(ce, trajectory=tr, ref=ref)
+
+    sc = Scenario([car("ego", -20.0, 0.0), car("other", 20.0, 0.0)])
+    gym = ScenarioGym(timestep=0.1, metrics=[CollisionPointMetric()])
+    gym.set_scenario(sc)
+    gym.rollout()
+    hits = gym.get_metrics()["collision_points"]
+    assert len(hits) == 1
+    ref, point, angle = hits[0]
+    assert ref == "other" and abs(point[0]) < 0.2 and abs(point[1]) < 1e-9 and abs(angle - np.pi) < 1e-9
+
+
+def test_per_agent_vehicle_limits_and_noise():
+    """VehicleControllers with different limits in one scene; SocialForce with the reference's default noise."""
+    cfg = golden_cases.veh_cfg()
+    acts = cfg.actions.reshape(cfg.T, 2, cfg.N, cfg.M)
+    rows = synthetic.two_knot_rows(cfg).reshape(cfg.N, cfg.M, 2, 7)
+    ents = []
+    for m in range(cfg.M):
+        ce = CatalogEntry(None, "car", "car", "Vehicle", BoundingBox(*synthetic.CAR1_BOX))
+        ents.append(Vehicle(ce, trajectory=Trajectory(rows[0, m]), ref="ego" if m == 0 else f"entity_{m}"))
+    sc = Scenario(ents)
+
+    def create_agent(scenario, entity):
+        m = scenario.entities.index(entity)
+        return ActionTableAgent(entity, acts[:, :, 0, m].T, max_accel=5.0 if m % 2 else 1.0,
+                                max_steer=0.7 if m % 3 else 0.2, max_speed=None if m % 4 else 6.0)
+
+    gym = ScenarioGym(timestep=cfg.dt, metrics=[EgoAvgSpeed()])
+    gym.set_scenario(sc, create_agent=create_agent)
+    gym.rollout()
+    eng = gym._engine
+    assert eng.scene.veh_limits is not None
+    from oracle.runner import OracleEngine
+
+    cpu = OracleEngine(eng.scene, eng.params)
+    cpu.reset()
+    cpu.rollout(-1, actions=gym._action_table_host)
+    assert np.array_equal(eng.get("tick"), cpu.get("tick"))
+    assert np.allclose(eng.get("pose"), cpu.get("pose"), rtol=1e-9, atol=1e-9)
+    assert float(eng.get("speed")[::4].max()) <= 6.0 + 1e-12
+    # the reference's own example: SocialForce(SocialForceParameters()) -- default noise
+    pcfg = golden_cases.ped_cfg()
+    scene = synthetic.pack_synthetic(pcfg)
+    p = abi.default_params()
+    p.timestep = pcfg.dt
+    p.sf_std_lon, p.sf_std_lat, p.sf_noise_seed = 2e-6, 1e-7, 1234
+    from scenario_gym_b200.engine import Engine
+
+    noisy = Engine(scene, p, device=0)
+    noisy.reset()
+    noisy.rollout(-1)
+    ocpu = OracleEngine(scene, p)
+    ocpu.reset()
+    ocpu.rollout(-1)
+    assert np.allclose(noisy.get("pose"), ocpu.get("pose"), rtol=1e-9, atol=1e-9)
+    q = abi.default_params()
+    q.timestep = pcfg.dt
+    clean = Engine(scene, q, device=0)
+    clean.reset()
+    clean.rollout(-1)
+    d = np.abs(noisy.get("pose") - clean.get("pose")).max()
+    assert 0.0 < d < 1e-2, "the noise perturbs the rollout, slightly"
