@@ -686,6 +686,79 @@ class Bench:
         return out
 
 
+def api_records(bench, n_fused: int = 4096, n_host: int = 64) -> dict:
+    """
+    The C2 workload through the reference-facing Python API: ScenarioGym.set_scenarios -> rollout ->
+    get_metrics on `n_fused` replicas of the reference's test scenarios (one fused launch), and on
+    `n_host` replicas with a custom host-side Metric (per-tick host mode: every tick the batch's planes
+    are copied back once and the metric runs on the materialised states).
+    """
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from helpers import golden, manifest, sub
+
+    from scenario_gym_b200 import (BoundingBox, CatalogEntry, CollisionMetric, EgoAvgSpeed, Entity, Metric,
+                                   Pedestrian, Scenario, ScenarioGym, Trajectory, Vehicle)
+
+    g, man = golden("xosc"), manifest()["xosc"]
+    names = sorted(man)
+    cls = {abi.ETYPE_VEHICLE: (Vehicle, "Vehicle"), abi.ETYPE_PEDESTRIAN: (Pedestrian, "Pedestrian")}
+
+    def build(name):
+        inp = sub(g, f"xosc/{name}/in")
+        ents = []
+        for i in range(int(inp["n_entities"])):
+            C_, ctype = cls.get(int(inp["etype"][i]), (Entity, "MiscObject"))
+            ce = CatalogEntry(None, "entry", None, ctype, BoundingBox(*[float(v) for v in inp["box"][i]]))
+            ents.append(C_(ce, trajectory=Trajectory(inp[f"traj{i}"]), ref=man[name]["refs"][i]))
+        return Scenario(ents, name=name)
+
+    per = {n: int(sub(g, f"xosc/{n}/out")["present"][1:].sum()) for n in names}
+    want = {n: float(sub(g, f"xosc/{n}/out")["ego_avg_speed"]) for n in names}
+
+    class MaxEntities(Metric):  # a user metric the engine knows nothing about
+        name = "max_entities"
+
+        def _reset(self, state):
+            self.value = len(state.poses)
+
+        def _step(self, state):
+            self.value = max(self.value, len(state.poses))
+
+        def get_state(self):
+            return self.value
+
+    out = {}
+    for tag, n_scen, metrics in (("fused", n_fused, lambda: [CollisionMetric(), EgoAvgSpeed()]),
+                                 ("host_metric", n_host, lambda: [EgoAvgSpeed(), MaxEntities()])):
+        order = [names[k % len(names)] for k in range(n_scen)]
+        t0 = time.perf_counter()
+        scenarios = [build(n) for n in order]
+        gym = ScenarioGym(metrics=metrics(), device=bench.local)
+        gym.set_scenarios(scenarios)
+        t_set = time.perf_counter() - t0
+        gym.rollout()  # warm-up
+        gym.get_metrics()
+        bench.torch.cuda.synchronize(bench.dev)
+        reps = 3 if tag == "fused" else 1
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            gym.rollout()
+            bench.torch.cuda.synchronize(bench.dev)
+        t_roll = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        ms = gym.get_metrics()
+        t_get = time.perf_counter() - t0
+        ms = ms if isinstance(ms, list) else [ms]
+        ok = all(abs(m["ego_avg_speed"] - want[n]) <= 1e-9 * max(1.0, abs(want[n])) for m, n in zip(ms, order))
+        steps = sum(per[n] for n in order)
+        out[tag] = {"scenarios": n_scen, "entity_steps": steps, "value": steps / (t_roll + t_get), "unit": UNIT,
+                    "ms_set_scenarios": 1e3 * t_set, "ms_rollout": 1e3 * t_roll, "ms_get_metrics": 1e3 * t_get,
+                    "metrics_match_reference_goldens": bool(ok),
+                    "path": "ScenarioGym.set_scenarios -> rollout -> get_metrics" +
+                            ("" if tag == "fused" else " with a custom host Metric (per-tick host mode)")}
+    return out
+
+
 def measure_fp64_peak(dev_index: int, stream) -> float:
     """DFMA thread-instructions/s of this GPU at its current clocks (library micro-benchmark)."""
     import ctypes as C
@@ -737,6 +810,11 @@ def run_b200(args):
                 out[k] = main[k]
         if subs:
             out["workloads"] = subs
+        if world == 1 and not args.no_subs and args.workload == "c3" and not n_over:
+            try:
+                out["python_api"] = api_records(b)
+            except Exception as e:  # noqa: BLE001
+                out["python_api"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(out))
     b.sampler.stop()
     if world > 1:

@@ -331,6 +331,13 @@ int sg_measure_fp64_peak(double* inst_per_s, int device, void* stream);
 int sg_test_box_pairs(const double* pose_a, const double* box_a, const double* pose_b,
                       const double* box_b, uint8_t* out, int64_t n, int device, void* stream);
 
+/* Trajectory.position_at_t / velocity_at_t on the device, for unit tests (trajectory.py:142-205,
+   243-273): rows [K][7] = t, x, y, z, h, p, r; t [n]; mode 0 extrapolate=False (None outside the time
+   range), 1 extrapolate=(False, False) (clamped), 2 extrapolate=True; pos [n][6], ok [n] (0: None),
+   vel [n][6] or NULL.  All device memory. */
+int sg_test_trajectory(const double* rows, int64_t K, const double* t, int64_t n, int mode, double* pos,
+                       uint8_t* ok, double* vel, int device, void* stream);
+
 /* Host-buffer convenience used for the end-to-end number: copy the scene/initial
    inputs H2D (pinned host memory recommended), reset, rollout to completion and copy
    the per-scenario results back.  `dev_*` are device mirrors with the same shapes. */

@@ -223,18 +223,47 @@ static int quad_orientation(const double q[8]) {
   return s;
 }
 
-/* is every point of pts strictly outside edge k of convex polygon q (n verts)? */
+/* is every point of pts strictly outside edge k of convex polygon q (n verts)?  A quad without
+   area (o == 0: a segment or a point) has no inside: its edge separates when the points lie strictly
+   on one side of it, whichever side. */
 static int edge_separates(const double* q, int n, int o, int k, const double* pts, int npts) {
   double ax = q[2 * k], ay = q[2 * k + 1];
   double bx = q[2 * ((k + 1) % n)], by = q[2 * ((k + 1) % n) + 1];
+  if (o == 0) {
+    int pos = 0, neg = 0;
+    for (int m = 0; m < npts; ++m) {
+      int sg = orient_sign(ax, ay, bx, by, pts[2 * m], pts[2 * m + 1]);
+      pos += sg > 0; neg += sg < 0;
+    }
+    return pos == npts || neg == npts;
+  }
   for (int m = 0; m < npts; ++m)
     if (orient_sign(ax, ay, bx, by, pts[2 * m], pts[2 * m + 1]) * o >= 0) return 0;
   return 1;
 }
 
+/* closed segments (a, b) and (c, d) share a point (exact) */
+static int on_segment(double ax, double ay, double bx, double by, double px, double py) {
+  return orient_sign(ax, ay, bx, by, px, py) == 0 && fmin(ax, bx) <= px && px <= fmax(ax, bx) &&
+         fmin(ay, by) <= py && py <= fmax(ay, by);
+}
+static int segments_meet(const double* a, const double* b, const double* c, const double* d) {
+  int o1 = orient_sign(a[0], a[1], b[0], b[1], c[0], c[1]), o2 = orient_sign(a[0], a[1], b[0], b[1], d[0], d[1]);
+  int o3 = orient_sign(c[0], c[1], d[0], d[1], a[0], a[1]), o4 = orient_sign(c[0], c[1], d[0], d[1], b[0], b[1]);
+  if (o1 * o2 < 0 && o3 * o4 < 0) return 1;
+  return on_segment(a[0], a[1], b[0], b[1], c[0], c[1]) || on_segment(a[0], a[1], b[0], b[1], d[0], d[1]) ||
+         on_segment(c[0], c[1], d[0], d[1], a[0], a[1]) || on_segment(c[0], c[1], d[0], d[1], b[0], b[1]);
+}
+
 /* closed-set intersection of two convex quads */
 static int quads_intersect(const double a[8], const double b[8]) {
   int oa = quad_orientation(a), ob = quad_orientation(b);
+  if (oa == 0 && ob == 0) { /* two quads without area (segments / points): they meet iff their rings do */
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j)
+        if (segments_meet(a + 2 * i, a + 2 * ((i + 1) % 4), b + 2 * j, b + 2 * ((j + 1) % 4))) return 1;
+    return 0;
+  }
   for (int k = 0; k < 4; ++k) if (edge_separates(a, 4, oa, k, b, 4)) return 0;
   for (int k = 0; k < 4; ++k) if (edge_separates(b, 4, ob, k, a, 4)) return 0;
   return 1;
@@ -1196,6 +1225,17 @@ int sgo_entities_in_radius(const SgState* st, int n_scenarios, int n_slots, cons
   for (int64_t i = 0; i < nm; ++i) {
     int n = (int)(i / n_slots);
     out[i] = (uint8_t)(r[n] > 0.0 && st->present[i] && in_buffer(x[n], y[n], r[n], st->pose[i], st->pose[nm + i]));
+  }
+  return 0;
+}
+int sgo_test_trajectory(const double* rows, int64_t K, const double* t, int64_t n, int mode, double* pos,
+                        uint8_t* ok, double* vel, int device, void* stream) {
+  (void)device; (void)stream;
+  for (int64_t i = 0; i < n; ++i) {
+    double out[6] = {0, 0, 0, 0, 0, 0};
+    ok[i] = (uint8_t)position_at_t(rows, K, t[i], mode, out);
+    memcpy(pos + 6 * i, out, 48);
+    if (vel) velocity_at_t(rows, K, t[i], vel + 6 * i);
   }
   return 0;
 }

@@ -330,6 +330,8 @@ def bind(lib: C.CDLL, prefix: str) -> Dict[str, object]:
         [C.POINTER(SgActionRng), C.c_int, C.c_int, C.c_int64, _p, C.c_int, _p])
     get("entities_in_radius", C.c_int,
         [C.POINTER(SgState), C.c_int, C.c_int, _p, _p, _p, _p, C.c_int, _p])
+    get("test_trajectory", C.c_int,
+        [_p, C.c_int64, _p, C.c_int64, C.c_int, _p, _p, _p, C.c_int, _p])
     get("measure_fp64_peak", C.c_int, [C.POINTER(C.c_double), C.c_int, _p], required=False)
     get("rollout_host", C.c_int,
         [C.POINTER(SgScene), C.POINTER(SgScene), C.POINTER(SgParams), C.POINTER(SgState),

@@ -208,6 +208,17 @@ int sg_entities_in_radius(const SgState* state, int n_scenarios, int n_slots, co
   return 0;
 }
 
+int sg_test_trajectory(const double* rows, int64_t K, const double* t, int64_t n, int mode, double* pos,
+                       uint8_t* ok, double* vel, int device, void* stream) {
+  if (!rows || !t || !pos || !ok) return set_msg("null argument");
+  if (K < 1 || K > 0x7fffffff || mode < 0 || mode > 2) return set_msg("bad trajectory length / mode");
+  cudaError_t err = cudaSetDevice(device);
+  if (err != cudaSuccess) return set_err("cudaSetDevice", err);
+  err = sgi_launch_traj((cudaStream_t)stream, rows, (int)K, t, n, mode, pos, ok, vel);
+  if (err != cudaSuccess) return set_err("sg_traj_kernel launch", err);
+  return 0;
+}
+
 int sg_measure_fp64_peak(double* inst_per_s, int device, void* stream) {
   if (!inst_per_s) return set_msg("null argument");
   cudaError_t err = cudaSetDevice(device);

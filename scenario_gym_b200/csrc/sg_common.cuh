@@ -1115,6 +1115,10 @@ static __device__ __noinline__ bool pair_collides(unsigned csh, const int8_t* or
   for (unsigned f = 0; f < 8; ++f) same = same && (lds_f64(pa + f * qs) == lds_f64(pb + f * qs));
   if (same) return false;  // `g != g_prime`, reference utils.py:58
   int oa = orient[a], ob = orient[b];
+  if (oa == 0 || ob == 0) {  // a box without area (rare): the register version knows the degenerate rules
+    const Quad A = load_quad_shared(pa, qs), B = load_quad_shared(pb, qs);
+    return quads_intersect(A, oa, B, ob);
+  }
   // closed-set intersection of two convex quads (touching counts, as GEOS `intersects`):
   // disjoint iff some edge of either has all four corners of the other strictly outside
 #pragma unroll 1

@@ -190,16 +190,47 @@ SG_DEV int quad_orientation(const Quad& q) {
 }
 
 // are all four corners of b strictly outside edge (corner 0 -> corner 1) of a (orientation o)?
+// A quad without area (o == 0: a segment or a point) has no inside: its edge separates when b lies
+// strictly on one side of it, whichever side.
 SG_DEV bool edge01_separates(const Quad& a, int o, const Quad& b) {
-  return orient_sign(a.x0, a.y0, a.x1, a.y1, b.x0, b.y0) * o < 0 &&
-         orient_sign(a.x0, a.y0, a.x1, a.y1, b.x1, b.y1) * o < 0 &&
-         orient_sign(a.x0, a.y0, a.x1, a.y1, b.x2, b.y2) * o < 0 &&
-         orient_sign(a.x0, a.y0, a.x1, a.y1, b.x3, b.y3) * o < 0;
+  const int s0 = orient_sign(a.x0, a.y0, a.x1, a.y1, b.x0, b.y0);
+  if (o != 0 ? s0 * o >= 0 : s0 == 0) return false;
+  const int want = o != 0 ? -o : s0;
+  return orient_sign(a.x0, a.y0, a.x1, a.y1, b.x1, b.y1) == want &&
+         orient_sign(a.x0, a.y0, a.x1, a.y1, b.x2, b.y2) == want &&
+         orient_sign(a.x0, a.y0, a.x1, a.y1, b.x3, b.y3) == want;
+}
+
+// closed segments (a, b) and (c, d) share a point (exact)
+SG_DEV bool on_segment(double ax, double ay, double bx, double by, double px, double py) {
+  return orient_sign(ax, ay, bx, by, px, py) == 0 && fmin(ax, bx) <= px && px <= fmax(ax, bx) &&
+         fmin(ay, by) <= py && py <= fmax(ay, by);
+}
+SG_DEV bool segments_meet(double ax, double ay, double bx, double by, double cx, double cy, double dx, double dy) {
+  const int o1 = orient_sign(ax, ay, bx, by, cx, cy), o2 = orient_sign(ax, ay, bx, by, dx, dy);
+  const int o3 = orient_sign(cx, cy, dx, dy, ax, ay), o4 = orient_sign(cx, cy, dx, dy, bx, by);
+  if (o1 * o2 < 0 && o3 * o4 < 0) return true;
+  return on_segment(ax, ay, bx, by, cx, cy) || on_segment(ax, ay, bx, by, dx, dy) ||
+         on_segment(cx, cy, dx, dy, ax, ay) || on_segment(cx, cy, dx, dy, bx, by);
+}
+// two quads without area (segments / points): they meet iff their rings do
+static __device__ __noinline__ bool flat_quads_meet(Quad a, Quad b) {
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      if (segments_meet(a.x0, a.y0, a.x1, a.y1, b.x0, b.y0, b.x1, b.y1)) return true;
+      rotate(b);
+    }
+    rotate(a);
+  }
+  return false;
 }
 
 // closed-set intersection of two convex quads (touching counts, as GEOS `intersects`):
 // disjoint iff some edge of either has all four corners of the other strictly outside
 static __device__ __noinline__ bool quads_intersect(Quad a, int oa, Quad b, int ob) {
+  if (oa == 0 && ob == 0) return flat_quads_meet(a, b);
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll 1

@@ -106,6 +106,29 @@ cudaError_t sgi_launch_radius(cudaStream_t s, const SgState& st, int n_scen, int
   return cudaGetLastError();
 }
 
+// Trajectory.position_at_t / velocity_at_t truth tables (sg_test_trajectory): one thread per query time
+__global__ void sg_traj_kernel(const double* __restrict__ rows, int K, const double* __restrict__ t, int64_t n,
+                               int mode, double* __restrict__ pos, uint8_t* __restrict__ ok, double* __restrict__ vel) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double out[6] = {0, 0, 0, 0, 0, 0};
+  int cur = 0;
+  const bool present = position_at_t(rows, K, t[i], mode, cur, out);
+  ok[i] = present ? 1 : 0;
+  for (int f = 0; f < 6; ++f) pos[6 * i + f] = out[f];
+  if (vel) {
+    velocity_at_t(rows, K, t[i], out);
+    for (int f = 0; f < 6; ++f) vel[6 * i + f] = out[f];
+  }
+}
+
+cudaError_t sgi_launch_traj(cudaStream_t s, const double* rows, int K, const double* t, int64_t n, int mode,
+                            double* pos, uint8_t* ok, double* vel) {
+  if (n <= 0) return cudaSuccess;
+  sg_traj_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(rows, K, t, n, mode, pos, ok, vel);
+  return cudaGetLastError();
+}
+
 // FP64 pipe micro-benchmark (sg_measure_fp64_peak): 8 independent DFMA chains per thread
 __global__ void sg_dfma_kernel(double* __restrict__ out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;

@@ -490,32 +490,31 @@ class ScenarioGym:
         return self._cache[name]
 
     def _materialise(self, n: int) -> dict:
-        eng = self._engine
-        M = eng.M
+        """
+        Host view of scenario n.  The planes come from ONE device->host copy per field for the whole
+        batch (``_fetch`` caches them until the state advances), sliced here.
+        """
+        M = self._engine.M
         sl = slice(n * M, (n + 1) * M)
-        pose = eng.tensor("pose")[:, sl].cpu().numpy()
-        vel = eng.tensor("vel")[:, sl].cpu().numpy()
-        dist = eng.tensor("dist")[sl].cpu().numpy()
-        present = eng.tensor("present")[sl].cpu().numpy()
+        pose, vel = self._fetch("pose")[:, sl], self._fetch("vel")[:, sl]
+        dist, present = self._fetch("dist")[sl], self._fetch("present")[sl]
         ents = self._entity_of[n]
         poses, vels = {}, {}
-        for s, e in enumerate(ents):
-            if present[s]:
-                poses[e] = pose[:, s].copy()
-                vels[e] = vel[:, s].copy()
+        for s in np.nonzero(present[: len(ents)])[0]:
+            e = ents[s]
+            poses[e] = pose[:, s].copy()
+            vels[e] = vel[:, s].copy()
         if self._rss_cb is not None:
             self._sync_rss(n, ents, sl)
         return {
-            "t": float(eng.tensor("t")[n].item()), "prev_t": float(eng.tensor("prev_t")[n].item()),
-            "done": bool(eng.tensor("done")[n].item()), "poses": poses, "velocities": vels,
-            "distances": {e: float(dist[s]) for s, e in enumerate(ents)},
+            "t": float(self._fetch("t")[n]), "prev_t": float(self._fetch("prev_t")[n]),
+            "done": bool(self._fetch("done")[n]), "poses": poses, "velocities": vels,
+            "distances": dict(zip(ents, dist[: len(ents)].tolist())),
         }
 
     def _sync_rss(self, n: int, ents, sl) -> None:
-        eng, cb = self._engine, self._rss_cb
-        sd = eng.tensor("safe_dist")[:, sl].cpu().numpy()
-        ratio = eng.tensor("safe_ratio")[:, sl].cpu().numpy()
-        rec = eng.tensor("rss_last")[sl].cpu().numpy()
+        cb = self._rss_cb
+        sd, ratio, rec = self._fetch("safe_dist")[:, sl], self._fetch("safe_ratio")[:, sl], self._fetch("rss_last")[sl]
         cb.safe_distances = {e: [float(sd[0, s]), float(sd[1, s])] for s, e in enumerate(ents)
                              if rec[s] != abi.RSS_NONE}
         cb.entity_safe_ratios = {e: [float(ratio[0, s]), float(ratio[1, s])] for s, e in enumerate(ents)}
@@ -562,18 +561,16 @@ class ScenarioGym:
     def _collisions(self, n: int) -> Dict[Entity, List[Entity]]:
         eng = self._engine
         ents = self._entity_of[n]
-        present = eng.tensor("present")[n * eng.M:(n + 1) * eng.M].cpu().numpy()
+        present = self._fetch("present")[n * eng.M:(n + 1) * eng.M]
         if not (self._params.features & abi.FEAT_COLL_MATRIX):
             # no per-tick pair matrix on this run (it is kept whenever a host-side plugin is
             # present): test the present entities' current boxes pairwise on the device
             return self._collisions_on_demand(n, ents, present)
-        mask = eng.tensor("coll_mask")[n].cpu().numpy().view(np.uint32)
+        rows = self._fetch("coll_mask")[n]  # [M, W] uint32 (one copy per tick for the whole batch)
+        bits = np.unpackbits(rows.view(np.uint8), axis=1, bitorder="little")[:, : len(ents)]
         out = {}
-        for a, e in enumerate(ents):
-            if not present[a]:
-                continue
-            out[e] = [ents[b] for b in range(len(ents))
-                      if (int(mask[a, b >> 5]) >> (b & 31)) & 1]
+        for a in np.nonzero(present[: len(ents)])[0]:
+            out[ents[a]] = [ents[b] for b in np.nonzero(bits[a])[0]]
         return out
 
     def _collisions_on_demand(self, n: int, ents, present) -> Dict[Entity, List[Entity]]:
