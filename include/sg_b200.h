@@ -71,6 +71,12 @@ enum SgFeature {
                                distances; kept for cross-checks) */
 };
 
+/* facts about a scene the packer knows (SgScene.scene_flags) */
+enum SgSceneFlag {
+  SG_SCENE_FLAT_BOXES = 1 /* some live slot has a box without area (width * length == 0): such scenes
+                             take the general kernel, whose narrow phase knows the degenerate rules */
+};
+
 /* record codes appended to RSSDistances.intersect[e] (rss/callback.py:168-228,304-338) */
 enum SgRssRecord {
   SG_RSS_SAFE = 0,
@@ -140,7 +146,7 @@ typedef struct SgScene {
      lets the library pick a specialised kernel; {VEHICLE[,EMPTY]} additionally promises that
      every vehicle slot is present at reset (its trajectory covers t0). */
   uint32_t kind_mask;
-  uint32_t _pad0;
+  uint32_t scene_flags; /* SgSceneFlag bits */
   const uint8_t* kind;   /* [N*M] SgKind */
   const uint8_t* etype;  /* [N*M] SgEntityType */
   const double* box;     /* [4][N*M]: width, length, center_x, center_y (catalog_entry.py:83-90) */

@@ -85,6 +85,7 @@ def scene_struct(scene: PackedScene) -> abi.SgScene:
     s.n_rn_polys = len(scene.rn_edge_off) - 1
     s.n_rn_edges = scene.rn_edges.shape[0]
     s.kind_mask = scene.kind_mask()
+    s.scene_flags = scene.scene_flags()
     for k, a in scene.arrays().items():
         assert a.flags["C_CONTIGUOUS"], k
         setattr(s, k, a.ctypes.data)

@@ -32,6 +32,7 @@ RSS_RECORD_NAMES = {
     6: "found",
 }
 RSS_NONE = 255
+SCENE_FLAT_BOXES = 1
 
 _p = C.c_void_p
 
@@ -89,7 +90,7 @@ class SgScene(C.Structure):
         ("n_union_rows", C.c_int64),
         ("n_route_pts", C.c_int64),
         ("kind_mask", C.c_uint32),
-        ("_pad0", C.c_uint32),
+        ("scene_flags", C.c_uint32),
         ("kind", _p),
         ("etype", _p),
         ("box", _p),

@@ -54,7 +54,8 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
   const uint32_t veh_bits = (1u << SG_KIND_VEHICLE), ok_bits = veh_bits | (1u << SG_KIND_EMPTY);
   // the ego_off_road terminal condition and the boundary forces live in the general kernel only
   const bool roads = (p->terminal & SG_TERM_EGO_OFF_ROAD) != 0;
-  const bool veh_only = (sc->kind_mask & veh_bits) && !(sc->kind_mask & ~ok_bits) && !roads && !sc->veh_limits;
+  const bool veh_only = (sc->kind_mask & veh_bits) && !(sc->kind_mask & ~ok_bits) && !roads && !sc->veh_limits &&
+                        !(sc->scene_flags & SG_SCENE_FLAT_BOXES);
   const bool grid_ok = ped && p->ped_distance_threshold > 0.0 && p->ped_distance_threshold < 1.0e6 &&
                        !(p->features & SG_FEAT_NO_GRID);
   GroupLayout L = make_layout(sc->n_slots, ped, rss, veh_only, grid_ok);

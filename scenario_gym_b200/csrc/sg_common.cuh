@@ -1104,9 +1104,28 @@ SG_DEV int rss_hazard(const RssConst& K, const Grp& c, double x, double y, doubl
 // ---------------------------------------------------------------------------------
 // collisions (reference state/utils.py:10-49, utils.py:28-62)
 // ---------------------------------------------------------------------------------
+#ifdef SG_FLAT_BOXES
+// two staged quads without area (segments / points): they meet iff their rings do
+static __device__ __noinline__ bool flat_pair_meets(unsigned pa, unsigned pb, unsigned qs) {
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    const double ax = qx(pa, qs, i), ay = qy(pa, qs, i), bx = qx(pa, qs, i + 1), by = qy(pa, qs, i + 1);
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j)
+      if (segments_meet(ax, ay, bx, by, qx(pb, qs, j), qy(pb, qs, j), qx(pb, qs, j + 1), qy(pb, qs, j + 1))) return true;
+  }
+  return false;
+}
+#endif
+
 // exact narrow phase for one AABB-surviving pair; both quads are read on the fly from the staged
 // corners with ld.shared inside rolled loops (`csh`: shared address of corners[0][0]), so the
-// routine needs few registers and its callers save little around the call
+// routine needs few registers and its callers save little around the call.
+// Boxes without area (orientation 0: segments / points) follow their own rules -- such a quad has no
+// inside: its edge separates when the other quad lies strictly on one side of it, whichever side, and
+// two of them meet iff their rings do.  Those rules are compiled in with SG_FLAT_BOXES only (the
+// general, replay and crowd kernels): they cost registers at every call site, so the vehicle kernels
+// leave them out and sg_api.cu routes scenes with such boxes (SG_SCENE_FLAT_BOXES) to the general kernel.
 static __device__ __noinline__ bool pair_collides(unsigned csh, const int8_t* orient, int G, int a, int b) {
   const unsigned qs = (unsigned)G * 8u;
   unsigned pa = csh + (unsigned)a * 8u, pb = csh + (unsigned)b * 8u;
@@ -1115,10 +1134,9 @@ static __device__ __noinline__ bool pair_collides(unsigned csh, const int8_t* or
   for (unsigned f = 0; f < 8; ++f) same = same && (lds_f64(pa + f * qs) == lds_f64(pb + f * qs));
   if (same) return false;  // `g != g_prime`, reference utils.py:58
   int oa = orient[a], ob = orient[b];
-  if (oa == 0 || ob == 0) {  // a box without area (rare): the register version knows the degenerate rules
-    const Quad A = load_quad_shared(pa, qs), B = load_quad_shared(pb, qs);
-    return quads_intersect(A, oa, B, ob);
-  }
+#ifdef SG_FLAT_BOXES
+  if (oa == 0 && ob == 0) return flat_pair_meets(pa, pb, qs);
+#endif
   // closed-set intersection of two convex quads (touching counts, as GEOS `intersects`):
   // disjoint iff some edge of either has all four corners of the other strictly outside
 #pragma unroll 1
@@ -1127,9 +1145,19 @@ static __device__ __noinline__ bool pair_collides(unsigned csh, const int8_t* or
     for (int k = 0; k < 4; ++k) {
       const double ax = qx(pa, qs, k), ay = qy(pa, qs, k), bx = qx(pa, qs, k + 1), by = qy(pa, qs, k + 1);
       bool sep = true;
+#ifdef SG_FLAT_BOXES
+      int want = -oa;
+#pragma unroll 1
+      for (int m = 0; m < 4 && sep; ++m) {
+        const int sg = orient_sign(ax, ay, bx, by, qx(pb, qs, m), qy(pb, qs, m));
+        if (want == 0) want = sg;  // flat quad: the side of the first corner decides which side is "outside"
+        sep = sg != 0 && sg == want;
+      }
+#else
 #pragma unroll 1
       for (int m = 0; m < 4 && sep; ++m)
         sep = orient_sign(ax, ay, bx, by, qx(pb, qs, m), qy(pb, qs, m)) * oa < 0;
+#endif
       if (sep) return false;
     }
     const unsigned tp = pa; pa = pb; pb = tp;

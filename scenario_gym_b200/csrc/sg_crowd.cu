@@ -21,6 +21,7 @@
 //   D  exact closed-set predicate on the queued pairs, one pair per thread, corners recomputed
 //      from the rows with the reference's expression (entity/base.py:100-138)
 //   E  terminal conditions, CollisionMetric rising edges, ego metrics.
+#define SG_FLAT_BOXES 1  // boxes without area follow their own narrow-phase rules (sg_common.cuh)
 #include "sg_common.cuh"
 #include "sg_internal.h"
 

@@ -1,5 +1,6 @@
 // sg_general.cu -- the general tick-loop kernel (replay / batch replay / vehicles / pedestrians /
 // PID / host-driven slots) and the reset kernel.
+#define SG_FLAT_BOXES 1  // boxes without area follow their own narrow-phase rules (sg_common.cuh)
 #include "sg_common.cuh"
 #include "sg_internal.h"
 #include "sg_pcg.cuh"

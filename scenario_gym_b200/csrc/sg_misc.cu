@@ -1,5 +1,6 @@
 // sg_misc.cu -- the tick-parallel replay kernel (sg_replay.cuh), the FutureCollisionDetector look-ahead
 // and the box-pair unit-test kernel.
+#define SG_FLAT_BOXES 1  // boxes without area follow their own narrow-phase rules (sg_common.cuh)
 #include "sg_common.cuh"
 #include "sg_internal.h"
 

@@ -63,6 +63,7 @@ class Engine:
         self._sc.n_rn_polys = len(scene.rn_edge_off) - 1
         self._sc.n_rn_edges = scene.rn_edges.shape[0]
         self._sc.kind_mask = scene.kind_mask()
+        self._sc.scene_flags = scene.scene_flags()
         for k, a in scene.arrays().items():
             t = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
             if t.numel() == 0:  # keep a valid pointer for empty tables

@@ -163,6 +163,12 @@ class PackedScene:
                 return 0
         return mask
 
+    def scene_flags(self) -> int:
+        """SgScene.scene_flags: facts the kernels' dispatcher needs (boxes without area)."""
+        live = self.kind != abi.KIND_EMPTY
+        flat = bool(np.any((self.box[0] * self.box[1] == 0.0) & live))
+        return abi.SCENE_FLAT_BOXES if flat else 0
+
     def nbytes(self) -> int:
         return int(sum(a.nbytes for a in self.arrays().values()))
 
