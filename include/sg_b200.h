@@ -20,6 +20,17 @@
  *   - stream-ordered and non-blocking unless stated; `stream` is a cudaStream_t
  *     passed as void* (NULL = legacy default stream).
  *   - no global mutable state except the last-error string (thread-local).
+ *   - which kernel runs is the library's choice (vehicle-only scenes, replay-only scenes, crowds and
+ *     everything else have their own kernels).  Discrete results -- presence, tick counts and times,
+ *     collision flags / pairs / events, RSS records and flags, goal indices -- are decided by exact
+ *     predicates and do not depend on that choice.  Continuous results agree with the reference
+ *     within 1e-9, but not bit for bit ACROSS kernel families: the vehicle-only kernels use
+ *     Newton-refined reciprocals / square roots and their own sincos (< 1 ulp), the general kernel
+ *     libm and IEEE division, so adding one replayed entity to a vehicle scene changes the vehicles'
+ *     poses in the last place.  RSS branches that compare such values with zero (`vr == 0.0`,
+ *     sign(pos) == sign(v), callback.py:243-268) are only reached with exact zeros produced by
+ *     clamping, which every kernel produces identically.  Within one family (table / in-kernel
+ *     action source, fused / chunked / host-buffer rollouts, trace on / off) results are bit-equal.
  *
  * The CPU oracle (oracle/sg_oracle.c, test infrastructure) exports the same
  * signatures with the prefix sgo_ and host pointers, so tests drive both through

@@ -17,7 +17,7 @@ from .plugins import (RSS, Action, ActionTableAgent, Agent, CollisionMetric, Col
                       ReplayTrajectoryController, RSSDistances, RSSParameters, Sensor,
                       SingleEntityObservation, SocialForce, SocialForceParameters, StateCallback,
                       TeleportAction, VehicleAction, VehicleController, cache_mean, cache_metric,
-                      CollisionPointMetric, PedestrianController, PedestrianObservation, PedestrianSensor)
+                      CollisionPointMetric, PedestrianController, RandomActionAgent, RandomActionSource, PedestrianObservation, PedestrianSensor)
 from .road_network import RoadNetwork
 from .scenario import Scenario
 from .state import State

@@ -219,19 +219,25 @@ struct CrowdSink {  // where colliding pairs are booked (shared atomics)
   int W, ego_slot, first_slot;
 };
 
-static __device__ __noinline__ void crowd_commit(CrowdSink k, int a, int b) {
-  const int lo = min(a, b), hi = max(a, b);
-  atomicAdd(&k.acc[ACC_NPAIRS], 1);
-  atomicMin(&k.acc[ACC_FIRST_PAIR], (lo << 16) | hi);
+// rare parts of booking a pair: the ego's row, the optional pair matrix
+static __device__ __noinline__ void crowd_commit_rare(CrowdSink k, int lo, int hi) {
   if (lo == k.first_slot || hi == k.first_slot) k.acc[ACC_FIRST_HIT] = 1;
-  atomicOr(&k.bits[lo >> 5], 1u << (lo & 31));
-  atomicOr(&k.bits[hi >> 5], 1u << (hi & 31));
   if (lo == k.ego_slot) atomicOr(&k.ego_now[hi >> 5], 1u << (hi & 31));
   if (hi == k.ego_slot) atomicOr(&k.ego_now[lo >> 5], 1u << (lo & 31));
   if (k.rows) {
     atomicOr(&k.rows[(int64_t)lo * k.W + (hi >> 5)], 1u << (hi & 31));
     atomicOr(&k.rows[(int64_t)hi * k.W + (lo >> 5)], 1u << (lo & 31));
   }
+}
+// a colliding pair (crowds have hundreds per tick): two bit sets, a count and the smallest pair
+SG_DEV void crowd_commit(const CrowdSink& k, int a, int b) {
+  const int lo = min(a, b), hi = max(a, b);
+  atomicAdd(&k.acc[ACC_NPAIRS], 1);
+  atomicMin(&k.acc[ACC_FIRST_PAIR], (lo << 16) | hi);
+  atomicOr(&k.bits[lo >> 5], 1u << (lo & 31));
+  atomicOr(&k.bits[hi >> 5], 1u << (hi & 31));
+  if (k.rows || lo == k.ego_slot || hi == k.ego_slot || lo == k.first_slot || hi == k.first_slot)
+    crowd_commit_rare(k, lo, hi);
 }
 
 // One AABB-surviving pair (a < b by construction of the callers): decided by circles where they

@@ -213,7 +213,7 @@ class Engine:
         ``State.get_entities_in_radius`` for every scenario in one launch: bool [N, M], slot s of
         scenario n present and strictly inside ``Point(x[n], y[n]).buffer(r[n])`` (r[n] <= 0: skipped).
         """
-        args = [torch.as_tensor(np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.float64), (self.N,)))).to(self.device)
+        args = [torch.from_numpy(np.array(np.broadcast_to(np.asarray(a, np.float64), (self.N,)))).to(self.device)
                 for a in (x, y, r)]
         out = torch.zeros(self.N * self.M, dtype=torch.uint8, device=self.device)
         self._check(self.lib["entities_in_radius"](C.byref(self._st), self.N, self.M, args[0].data_ptr(),

@@ -27,7 +27,7 @@ from . import abi
 from .entity import Entity
 from .packing import ScenarioSpec, SlotSpec, pack_scenarios
 from .plugins import (ActionTableAgent, Agent, CollisionMetric, EgoLocalizationSensor, Metric,
-                      PedestrianAgent, PIDAgent, PIDController, ReplayTrajectoryAgent, ReplayTrajectoryController, RSSDistances,
+                      PedestrianAgent, PIDAgent, PIDController, RandomActionAgent, ReplayTrajectoryAgent, ReplayTrajectoryController, RSSDistances,
                       SocialForce, StateCallback, VehicleAction, VehicleController, _create_agent,
                       _DeviceMetric)
 from .scenario import Scenario
@@ -207,6 +207,9 @@ class ScenarioGym:
             else:  # only finished table scenarios are left: a zero row keeps the others stepping
                 eng.rollout(1, actions=np.zeros((1, 2, N * M)), host_pose=host_pose,
                             host_present=host_present, step_done=force)
+        elif self._action_rng is not None:
+            eng.rollout(1, actions=self._action_rng, tick0=self._ticks_since_reset, host_pose=host_pose,
+                        host_present=host_present, step_done=force)
         else:
             eng.rollout(1, actions=actions, host_pose=host_pose, host_present=host_present, step_done=force)
         self._ticks_since_reset += 1
@@ -228,7 +231,8 @@ class ScenarioGym:
                 self.step()
         else:
             self._sync_params()
-            self._engine.rollout(-1, actions=self._action_table, tick0=self._ticks_since_reset)
+            self._engine.rollout(-1, actions=self._action_rng if self._action_rng is not None else self._action_table,
+                                 tick0=self._ticks_since_reset)
             self._ticks_since_reset = -1  # unknown per scenario; forces the next reset
             self._epoch += 1
             self._cache = {}
@@ -241,7 +245,9 @@ class ScenarioGym:
                         m._n = n
                         m._step(st)
                     m._n = 0
-            if self._action_table is not None and not self._fetch("done").all():
+            if (self._action_table is not None or self._action_rng is not None) and not self._fetch("done").all():
+                if self._action_rng is not None:
+                    raise IndexError(f"RandomActionSource: a scenario is not done after its {self._action_rng.n_ticks} rows")
                 # the device stops a scenario whose ActionTableAgents ran out of rows; the
                 # reference's agent would have raised on its next table lookup
                 n = int(np.nonzero(self._fetch("done") == 0)[0][0])
@@ -288,7 +294,7 @@ class ScenarioGym:
         specs, self._slot_of, self._entity_of = [], [], []
         self._agent_kind: Dict[Agent, str] = {}
         veh_params, ped_params, pid_params = set(), set(), set()
-        tables = {}
+        tables, random_agents = {}, {}
         for n, st in enumerate(self.states):
             sc = st.scenario
             ents = [e for e in sc.entities if e in st.agents] + [e for e in sc.entities if e not in st.agents]
@@ -329,6 +335,9 @@ class ScenarioGym:
                     if type(agent) is ActionTableAgent:
                         self._agent_kind[agent] = "device"
                         tables[(n, s)] = agent.table
+                    elif type(agent) is RandomActionAgent:
+                        self._agent_kind[agent] = "device"
+                        random_agents[(n, s)] = agent
                     else:
                         self._agent_kind[agent] = "host_policy"
                 else:
@@ -424,6 +433,17 @@ class ScenarioGym:
             trace_cap = int(max((sp.length - sp.t0) / ts for sp in specs)) + 8
         self._engine = Engine(scene, p, device=self.device, trace_cap=trace_cap)
 
+        # RandomActionAgents: the actions are drawn inside the kernel when one source feeds every vehicle
+        # agent of the batch; otherwise their columns join the resident table below
+        self._action_rng = None
+        for (n, s_), a in random_agents.items():
+            a._column = (N * M, n * M + s_)
+        sources = {id(a.source): a.source for a in random_agents.values()}
+        if random_agents and len(sources) == 1 and not tables and not self._any_host_policy:
+            self._action_rng = next(iter(sources.values())).action_rng(N * M)
+        else:
+            for (n, s_), a in random_agents.items():
+                tables[(n, s_)] = a.source.table(N * M)[:, :, n * M + s_]
         # resident action table of ActionTableAgents
         self._action_table = self._action_table_host = None
         if tables or self._any_host_policy:

@@ -399,6 +399,57 @@ class ActionTableAgent(Agent):
         return VehicleAction(a[0], a[1])
 
 
+class RandomActionSource:
+    """
+    The random policy of the "random accel / steer" configurations: a ``(n_ticks, 2, N*M)`` table of
+    uniform actions drawn from ``numpy.random.default_rng(seed)``, accelerations first
+    (``rng.uniform(low[0], high[0], (n_ticks, N*M))``), then steering.  Agents sharing one source read
+    their own column; when every vehicle agent of a batch is a ``RandomActionAgent`` of one source the
+    table is never built -- the kernels evaluate numpy's PCG64 stream in place (``ActionRng``).
+    """
+
+    def __init__(self, seed: int, n_ticks: int, low=(-6.0, -1.0), high=(6.0, 1.0)):
+        self.seed, self.n_ticks = int(seed), int(n_ticks)
+        self.low, self.high = (float(low[0]), float(low[1])), (float(high[0]), float(high[1]))
+        self._table = None
+
+    def action_rng(self, nm: int):
+        from .action_rng import ActionRng
+
+        return ActionRng.from_generator(self.seed, offset=(0, self.n_ticks * nm), tick_stride=nm,
+                                        low=self.low, high=self.high, n_ticks=self.n_ticks, nm=nm)
+
+    def table(self, nm: int) -> np.ndarray:
+        if self._table is None or self._table.shape[2] != nm:
+            rng = np.random.default_rng(self.seed)
+            tab = np.empty((self.n_ticks, 2, nm))
+            for c in range(2):
+                tab[:, c] = rng.uniform(self.low[c], self.high[c], (self.n_ticks, nm))
+            self._table = tab
+        return self._table
+
+
+class RandomActionAgent(Agent):
+    """Vehicle agent whose VehicleActions are the columns of a ``RandomActionSource`` (see there)."""
+
+    def __init__(self, entity: Entity, source: RandomActionSource, **controller_kwargs):
+        super().__init__(entity, VehicleController(entity, **controller_kwargs), EgoLocalizationSensor(entity))
+        self.source = source
+        self.k = 0
+        self._column = None  # (nm, flat slot index), set when the agent is lowered
+
+    def _reset(self) -> None:
+        self.k = 0
+
+    def _step(self, observation) -> VehicleAction:
+        if self._column is None:
+            raise RuntimeError("RandomActionAgent is not part of a gym yet")
+        nm, i = self._column
+        a = self.source.table(nm)[self.k, :, i]
+        self.k += 1
+        return VehicleAction(float(a[0]), float(a[1]))
+
+
 def _create_agent(scenario, entity) -> Optional[Agent]:
     """Default: a replay agent for the entity named "ego" (reference agent.py:151-169)."""
     if entity.ref == "ego":

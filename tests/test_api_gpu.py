@@ -656,3 +656,44 @@ def test_per_agent_vehicle_limits_and_noise():
     clean.rollout(-1)
     d = np.abs(noisy.get("pose") - clean.get("pose")).max()
     assert 0.0 < d < 1e-2, "the noise perturbs the rollout, slightly"
+
+
+def test_random_action_agents_draw_in_kernel():
+    """RandomActionAgent: in-kernel PCG64 stream == ActionTableAgents fed the numpy table of the same source."""
+    from scenario_gym_b200 import RandomActionAgent, RandomActionSource
+
+    cfg = golden_cases.veh_cfg()
+    rows = synthetic.two_knot_rows(cfg).reshape(cfg.N, cfg.M, 2, 7)
+
+    def scenarios():
+        out = []
+        for n in range(3):
+            ents = []
+            for m in range(cfg.M):
+                ce = CatalogEntry(None, "car", "car", "Vehicle", BoundingBox(*synthetic.CAR1_BOX))
+                ents.append(Vehicle(ce, trajectory=Trajectory(rows[n, m]), ref="ego" if m == 0 else f"entity_{m}"))
+            out.append(Scenario(ents))
+        return out
+
+    source = RandomActionSource(seed=99, n_ticks=cfg.T)
+    gym = ScenarioGym(timestep=cfg.dt, metrics=[CollisionMetric(), EgoAvgSpeed(), EgoDistanceTravelled()])
+    gym.set_scenarios(scenarios(), create_agent=lambda sc, e: RandomActionAgent(e, source))
+    assert gym._action_rng is not None and gym._action_table is None
+    gym.rollout()
+    a = gym.get_metrics()
+    pose_a = gym._engine.get("pose").copy()
+    nm = 3 * cfg.M
+    tab = source.table(nm)
+    scs = scenarios()
+    index = {id(e): n * cfg.M + m for n, sc in enumerate(scs) for m, e in enumerate(sc.entities)}
+    gym2 = ScenarioGym(timestep=cfg.dt, metrics=[CollisionMetric(), EgoAvgSpeed(), EgoDistanceTravelled()])
+    gym2.set_scenarios(scs, create_agent=lambda sc, e: ActionTableAgent(e, tab[:, :, index[id(e)]]))
+    gym2.rollout()
+    b = gym2.get_metrics()
+    assert a == b
+    assert np.array_equal(pose_a, gym2._engine.get("pose"))
+    # tick by tick as well
+    gym.reset_scenario()
+    while not all(st.is_done for st in gym.states):
+        gym.step()
+    assert np.array_equal(pose_a, gym._engine.get("pose"))

@@ -79,7 +79,18 @@ def summarise(rep, out_md, title):
         x = float(v.replace(",", ""))
         return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
 
-    return num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+    fp64 = 0.0
+    for op in ("dadd", "dmul", "dfma"):
+        k = f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum"
+        if k in m:
+            fp64 += float(m[k][1].replace(",", ""))
+    with open(out_md, "a") as f:
+        f.write(f"\n## FP64\n\nfp64 thread-instructions (dadd + dmul + dfma, predicated on) per launch: {fp64:.6g}\n")
+    grid = m.get("Grid Size", ("", ""))[1]
+    return {"dram_bytes": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"), "fp64_inst": fp64,
+            "kernel": m.get("Kernel Name", ("", ""))[1].split("(")[0], "grid": grid,
+            "kernel_ms_under_ncu": float(m["gpu__time_duration.sum"][1].replace(",", "")) *
+            {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}.get(m["gpu__time_duration.sum"][0], 1.0)}
 
 
 tpath = os.path.join(out_dir, "traffic.json")
@@ -89,13 +100,16 @@ for w in ("c3", "c5", "c2", "c4"):
     if not os.path.exists(rep):
         continue
     traffic = summarise(rep, os.path.join(out_dir, f"{tag}_top_kernel_{w}.md"), f"dominant kernel of workload {w} ({tag})")
-    # the bench looks the measurement up under "<workload>[_norss]_<N>x<M>x<T>" of its own config
-    bj = os.path.join(go, f"bench_{tag}.json" if w == "c3" else f"bench_{tag}_{w}.json")
-    if os.path.exists(bj) and os.path.getsize(bj) > 2 and w != "c4":  # (the c4 capture runs a reduced scenario count)
-        cfg = json.loads(open(bj).read().strip().splitlines()[-1])["config"]
-        key = f"{w}_{cfg['scenarios_per_gpu']}x{cfg['entities']}x{cfg['ticks']}"
-        tj[key] = traffic
-        print("traffic bytes/launch", traffic, "->", key)
+    # the bench looks the measurement up under "<workload>[_norss]_<N>x<M>x<T>" of its own config; the
+    # captures of tools/profile_round2.sh run every workload at its benchmarked size
+    bj = os.path.join(go, f"bench_{tag}.json")
+    if os.path.exists(bj) and os.path.getsize(bj) > 2:
+        line = json.loads(open(bj).read().strip().splitlines()[-1])
+        cfg = line["config"] if w == "c3" else line.get("workloads", {}).get(w, {}).get("config")
+        if cfg:
+            key = f"{w}_{cfg['scenarios_per_gpu']}x{cfg['entities']}x{cfg['ticks']}"
+            tj[key] = traffic
+            print("per launch", traffic, "->", key)
     print(open(os.path.join(out_dir, f"{tag}_top_kernel_{w}.md")).read()[:1800])
 json.dump(tj, open(tpath, "w"), indent=1, sort_keys=True)
 
