@@ -80,10 +80,11 @@ def summarise(rep, out_md, title):
         return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
 
     fp64 = 0.0
-    for op in ("dadd", "dmul", "dfma"):
-        k = f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum"
+    cyc = float(m["smsp__cycles_elapsed.avg"][1].replace(",", "")) if "smsp__cycles_elapsed.avg" in m else 0.0
+    for op in ("dadd", "dmul", "dfma"):  # (--set full reports them per elapsed cycle, summed over the sub-partitions)
+        k = f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed"
         if k in m:
-            fp64 += float(m[k][1].replace(",", ""))
+            fp64 += float(m[k][1].replace(",", "")) * cyc
     with open(out_md, "a") as f:
         f.write(f"\n## FP64\n\nfp64 thread-instructions (dadd + dmul + dfma, predicated on) per launch: {fp64:.6g}\n")
     grid = m.get("Grid Size", ("", ""))[1]
