@@ -11,15 +11,17 @@
 // each), so the barrier phases of one scenario are covered by the other scenario's work -- a
 // 1024-thread CTA per SM spends its time waiting at its own barriers.  The State rows that other
 // threads read (x, y, vx, vy: the pedestrians' sensors) live in shared memory, single-buffered:
-//   A  sensors + behaviour: neighbours from the cell grid of the OLD positions, social force
-//      (neighbour terms pooled per warp, summed in state.poses order) -> force per slot
+//   A  sensors + behaviour: neighbours listed by last tick's phase C, social force (neighbour terms
+//      pooled per warp, summed in state.poses order) -> force per slot
 //   -- barrier --
-//   B  controller + State.step on the thread's own rows (in place), cos/sin of the heading,
-//      conservative fp32 AABB; then the cell grid of the NEW positions (count, scan, scatter)
-//   C  broad phase through the grid; AABB survivors are decided at once by inscribed /
-//      circumscribed circles where those decide (conservatively), the rest are queued
-//   D  exact closed-set predicate on the queued pairs, one pair per thread, corners recomputed
-//      from the rows with the reference's expression (entity/base.py:100-138)
+//   B  controller + State.step on the thread's own rows (in place), cos/sin of the heading; the
+//      owner inserts its slots into the cell grid of the NEW positions (linked lists)
+//   C  every slot gathers the ids listed in the 3 x 3 cells around it into a private strip of shared
+//      memory (a light, ragged walk), then runs the candidate tests over the strip: next tick's sensor
+//      list (pedestrians within r) and this tick's collision broad phase by inscribed / circumscribed
+//      circles -- colliding for sure, apart for sure, or queued
+//   D  separating-axis filter / exact closed-set predicate on the queued pairs, one pair per thread,
+//      corners recomputed from the rows with the reference's expression (entity/base.py:100-138)
 //   E  terminal conditions, CollisionMetric rising edges, ego metrics.
 #define SG_FLAT_BOXES 1  // boxes without area follow their own narrow-phase rules (sg_common.cuh)
 #include "sg_common.cuh"
@@ -28,16 +30,18 @@
 #define CR_THREADS 512
 #define CR_NBCAP 8       // per-pedestrian neighbour candidate list
 #define CR_WARPS (CR_THREADS / 32)
+#define CR_CAP 16        // ids a slot gathers from its 3 x 3 cells before the tests (more: tested while walking)
 
 struct CrowdLayout {
   int G, W, QCAP;
-  int off_state, off_fcs, off_aabb, off_rad, off_nbl, off_gstart, off_gsorted, off_glarge, off_queue, off_flags,
+  int off_state, off_fcs, off_pool, off_rad, off_nbl, off_gstart, off_gsorted, off_glarge, off_queue, off_flags,
       off_wflag, off_ncnt, off_orient, off_hits, off_bits, off_acc, off_cold, off_gmisc, off_unif;
   int bytes;
 };
 
-static CrowdLayout crowd_layout(int ept) {
-  CrowdLayout L;
+// (constexpr: the kernel's shared-memory views are compile-time offsets, no registers or address arithmetic)
+__host__ __device__ constexpr CrowdLayout crowd_layout(int ept) {
+  CrowdLayout L{};
   const int G = CR_THREADS * ept;
   L.G = G;
   L.W = G / 32;
@@ -45,7 +49,7 @@ static CrowdLayout crowd_layout(int ept) {
   int o = 0;
   L.off_state = o;   o += 4 * G * (int)sizeof(double);          // x, y, vx, vy
   L.off_fcs = o;     o += 2 * G * (int)sizeof(double);          // force (A -> B), then cos / sin of the heading
-  L.off_aabb = o;    o += G * (int)sizeof(float4);
+  L.off_pool = o;    o += CR_WARPS * CR_CAP * 32 * (int)sizeof(uint16_t);  // [warp][k][lane]: gathered ids
   L.off_rad = o;     o += G * (int)sizeof(float2);              // inscribed / circumscribed radius of each box
   L.off_nbl = o;     o += CR_NBCAP * G * (int)sizeof(uint16_t);
   o = (o + 15) / 16 * 16;
@@ -60,7 +64,7 @@ static CrowdLayout crowd_layout(int ept) {
   L.off_orient = o;  o += G;
   o = (o + 15) / 16 * 16;
   L.off_hits = o;    o += 2 * L.W * (int)sizeof(uint32_t);      // ego_now, ego_last
-  L.off_bits = o;    o += 2 * L.W * (int)sizeof(uint32_t);      // collided bits, 2 parities
+  L.off_bits = o;    o += L.W * (int)sizeof(uint32_t);          // slots that collided during this launch
   L.off_acc = o;     o += 2 * ACC_N * (int)sizeof(int);
   L.off_cold = o;    o += COLD_ND * (int)sizeof(double) + COLD_NI * (int)sizeof(int);
   L.off_gmisc = o;   o += 48 * (int)sizeof(int);
@@ -73,7 +77,7 @@ struct Crowd {  // shared-memory views of one scenario
   int G, W, QCAP, M;
   double* state;   // [4][G]
   double* fcs;     // [2][G]
-  float4* aabb;
+  uint16_t* pool;
   float2* rad;
   uint16_t* nbl;
   uint16_t* ghead;
@@ -98,7 +102,7 @@ SG_DEV void crowd_views(Crowd& c, const CrowdLayout& L, unsigned char* base, int
   c.G = L.G; c.W = L.W; c.QCAP = L.QCAP; c.M = M;
   c.state = (double*)(base + L.off_state);
   c.fcs = (double*)(base + L.off_fcs);
-  c.aabb = (float4*)(base + L.off_aabb);
+  c.pool = (uint16_t*)(base + L.off_pool);
   c.rad = (float2*)(base + L.off_rad);
   c.nbl = (uint16_t*)(base + L.off_nbl);
   c.ghead = (uint16_t*)(base + L.off_gstart);
@@ -133,7 +137,6 @@ SG_DEV void cta_sync() { __syncthreads(); }
 SG_DEV void crowd_grid_clear(const Crowd& c) {
   uint32_t* w = (uint32_t*)c.ghead;
   for (int q = threadIdx.x; q < SG_GRID_CELLS / 2; q += CR_THREADS) w[q] = 0xffffffffu;
-  if (threadIdx.x == 0) c.gmisc[0] = 0;
 }
 
 // 16-bit exchange on a shared array through the containing 32-bit word
@@ -148,23 +151,11 @@ SG_DEV uint32_t crowd_exch16(uint16_t* arr, int idx, uint32_t v) {
   return (old >> sh) & 0xffffu;
 }
 
-// insert slot s (present) at its position; `have_box`: its AABB is staged -- entities reaching further
-// than half a cell from their position are "large": listed for everyone to test against
-SG_DEV void crowd_grid_insert(const Crowd& c, int s, bool have_box, double gox, double goy, double cs, double inv_cs) {
+// insert slot s (present) at its position
+SG_DEV void crowd_grid_insert(const Crowd& c, int s, double gox, double goy, double inv_cs) {
   const double px = c.state[s] - gox, py = c.state[c.G + s] - goy;
   const int ix = __double2int_rd(px * inv_cs), iy = __double2int_rd(py * inv_cs);
   const int cell = ((iy & (SG_GRID_DIM - 1)) << SG_GRID_BITS) | (ix & (SG_GRID_DIM - 1));
-  bool large = false;
-  if (have_box) {
-    const float4 bb = c.aabb[s];
-    const double reach = fmax(fmax(px - (double)bb.x, (double)bb.z - px), fmax(py - (double)bb.y, (double)bb.w - py));
-    large = !(reach <= 0.5 * cs * (1.0 - 1e-6));
-    if (large) {
-      const int k = atomicAdd(&c.gmisc[0], 1);
-      if (k < SG_GRID_LCAP) c.glarge[k] = (uint16_t)s;
-    }
-  }
-  c.flags[s] = (uint8_t)((c.flags[s] & ~8) | (large ? 8 : 0));
   c.gnext[s] = (uint16_t)crowd_exch16(c.ghead, cell, (uint32_t)s);
 }
 
@@ -217,6 +208,7 @@ struct CrowdSink {  // where colliding pairs are booked (shared atomics)
   uint32_t* ego_now;
   uint32_t* rows;
   int W, ego_slot, first_slot;
+  bool need_first;  // no tick of this scenario had a collision yet: the smallest pair of the tick is wanted
 };
 
 // rare parts of booking a pair: the ego's row, the optional pair matrix
@@ -229,78 +221,51 @@ static __device__ __noinline__ void crowd_commit_rare(CrowdSink k, int lo, int h
     atomicOr(&k.rows[(int64_t)hi * k.W + (lo >> 5)], 1u << (lo & 31));
   }
 }
-// a colliding pair (crowds have hundreds per tick): two bit sets, a count and the smallest pair
-SG_DEV void crowd_commit(const CrowdSink& k, int a, int b) {
+// a colliding pair (crowds have hundreds per tick).  The pair count is kept by the calling thread and
+// added to the scenario's once per tick; the `collided` bits are sticky over the launch (a slot's
+// bit is set by its first collision only); the smallest pair is only wanted until the first tick
+// with a collision is on record.
+SG_DEV void crowd_commit(const CrowdSink& k, int a, int b, int& mypairs) {
   const int lo = min(a, b), hi = max(a, b);
-  atomicAdd(&k.acc[ACC_NPAIRS], 1);
-  atomicMin(&k.acc[ACC_FIRST_PAIR], (lo << 16) | hi);
-  atomicOr(&k.bits[lo >> 5], 1u << (lo & 31));
-  atomicOr(&k.bits[hi >> 5], 1u << (hi & 31));
+  ++mypairs;
+  if (k.need_first) atomicMin(&k.acc[ACC_FIRST_PAIR], (lo << 16) | hi);
+  if (!((k.bits[lo >> 5] >> (lo & 31)) & 1u)) atomicOr(&k.bits[lo >> 5], 1u << (lo & 31));
+  if (!((k.bits[hi >> 5] >> (hi & 31)) & 1u)) atomicOr(&k.bits[hi >> 5], 1u << (hi & 31));
   if (k.rows || lo == k.ego_slot || hi == k.ego_slot || lo == k.first_slot || hi == k.first_slot)
     crowd_commit_rare(k, lo, hi);
 }
 
-// One AABB-surviving pair (a < b by construction of the callers): decided by circles where they
-// decide -- centres closer than the sum of the inscribed radii: the boxes intersect; further apart
-// than the sum of the circumscribed radii: they cannot -- with a 1e-6 relative margin, nine orders
-// of magnitude above the rounding of the corner coordinates; everything else is queued for the
-// exact predicate.  (Pedestrian boxes are near-square: more than half of the survivors are decided here.)
-SG_DEV void crowd_candidate(const Crowd& c, const CrowdSink& sink, int* acc, int a, int b) {
+struct CrowdBoxes {  // what the narrow phase needs to rebuild corners (DIRECT mode only)
+  const double* box;
+  int64_t nm, i0;
+};
+
+// One pair (a < b) whose squared centre distance is d2, decided by circles where they decide --
+// centres closer than the sum of the inscribed radii: the boxes intersect; further apart than the sum
+// of the circumscribed radii: they cannot -- with a 1e-6 relative margin, nine orders of magnitude
+// above the rounding of the corner coordinates; everything else is queued for the separating-axis /
+// exact predicate (DIRECT: decided in place -- the redo after a queue overflow, where the pairs the
+// circles decide are already on record).
+template <bool DIRECT>
+SG_DEV void crowd_pair(const Crowd& c, const CrowdSink& sink, const CrowdBoxes& bx, int a, int b, double d2, int& mypairs) {
   const float2 ra = c.rad[a], rb = c.rad[b];
-  const double dx = c.state[a] - c.state[b], dy = c.state[c.G + a] - c.state[c.G + b];
-  const double d2 = dx * dx + dy * dy;
   const double rin = (double)ra.x + (double)rb.x, rout = (double)ra.y + (double)rb.y;
   if (d2 > rout * rout) return;
-  if (d2 < rin * rin && d2 > 0.0) { crowd_commit(sink, a, b); return; }
-  const int q = atomicAdd(&acc[ACC_QCOUNT], 1);
-  if (q < c.QCAP) c.queue[q] = ((uint32_t)a << 16) | (uint32_t)b;
+  if (d2 < rin * rin && d2 > 0.0) {
+    if (!DIRECT) crowd_commit(sink, a, b, mypairs);
+    return;
+  }
+  if (!DIRECT) {
+    const int q = atomicAdd(&sink.acc[ACC_QCOUNT], 1);
+    if (q < c.QCAP) c.queue[q] = ((uint32_t)a << 16) | (uint32_t)b;
+  } else if (crowd_pair_collides(c.state, c.fcs, bx.box, bx.nm, bx.i0, c.orient, c.G, a, b)) {
+    crowd_commit(sink, a, b, mypairs);
+  }
 }
 
-// broad phase of slot s through the grid: every unordered pair whose conservative AABBs overlap is
-// seen exactly once (small-small by the lower slot, small-large by the small one, large-large by
-// the lower slot).  (Used when the pair queue overflowed: the candidates are decided in place.)
+// fn(o) for every slot listed in the 3 x 3 cells around cell (ix, iy)
 template <typename F>
-SG_DEV void crowd_for_each_candidate(const Crowd& c, int s, double gox, double goy, double inv_cs, F&& fn) {
-  const float4 mb = c.aabb[s];
-  const int nl = c.gmisc[0];
-  const bool large = (c.flags[s] & 8) != 0;
-  if (!large) {
-    const int ix = __double2int_rd((c.state[s] - gox) * inv_cs), iy = __double2int_rd((c.state[c.G + s] - goy) * inv_cs);
-    for (int dy = -1; dy <= 1; ++dy)
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int cell = (((iy + dy) & (SG_GRID_DIM - 1)) << SG_GRID_BITS) | ((ix + dx) & (SG_GRID_DIM - 1));
-        for (uint32_t o = c.ghead[cell]; o != CR_NIL; o = c.gnext[o]) {
-          if (o > (uint32_t)s && !(c.flags[o] & 8)) {
-            const float4 ob = c.aabb[o];
-            if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) fn(s, (int)o);
-          }
-        }
-      }
-  }
-  for (int k = 0; k < nl; ++k) {
-    const int o = c.glarge[k];
-    if (o == s || (large && o < s)) continue;
-    const float4 ob = c.aabb[o];
-    if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) fn(min(s, o), max(s, o));
-  }
-}
-
-// ---------------------------------------------------------------------------------
-// One walk over the 3 x 3 cells around slot s on the grid of the positions just computed serves
-//   * the pedestrian's sensor of the NEXT tick (neighbours strictly inside the 64-gon of
-//     circumradius r lie in these cells): pedestrians within r (1 + 1e-9) go to the slot's
-//     candidate list, which is then put in slot (= state.poses) order, and
-//   * this tick's collision broad phase: pairs (s, o), o > s, whose centres are within the sum of
-//     the circumscribed radii and whose conservative AABBs overlap (crowd_candidate).
-// `r2` = (r (1 + 1e-9))^2; sensor = the slot is a present pedestrian; coll = it takes part in the
-// cell broad phase (present, not large).
-SG_DEV void crowd_walk(const Crowd& c, const CrowdSink& sink, int* acc, int s, bool sensor, bool coll, double r2,
-                       double gox, double goy, double inv_cs) {
-  const int G = c.G;
-  const double px = c.state[s], py = c.state[G + s];
-  const int ix = __double2int_rd((px - gox) * inv_cs), iy = __double2int_rd((py - goy) * inv_cs);
-  const float2 rs = c.rad[s];
-  int ncand = 0;
+SG_DEV void crowd_cells(const Crowd& c, int ix, int iy, F&& fn) {
   const int cx0 = (ix - 1) & (SG_GRID_DIM - 1), cx1 = ix & (SG_GRID_DIM - 1), cx2 = (ix + 1) & (SG_GRID_DIM - 1);
   uint32_t o = c.ghead[(((iy - 1) & (SG_GRID_DIM - 1)) << SG_GRID_BITS) | cx0];
 #pragma unroll 1
@@ -311,39 +276,120 @@ SG_DEV void crowd_walk(const Crowd& c, const CrowdSink& sink, int* acc, int s, b
       const int q1 = q + 1, row = (iy + q1 / 3 - 1) & (SG_GRID_DIM - 1), col = q1 % 3;
       nxt = c.ghead[(row << SG_GRID_BITS) | (col == 0 ? cx0 : (col == 1 ? cx1 : cx2))];
     }
-    for (; o != CR_NIL; o = c.gnext[o]) {
-      if (o == (uint32_t)s) continue;
-      const double ddx = c.state[o] - px, ddy = c.state[G + o] - py, d2 = ddx * ddx + ddy * ddy;
-      const uint8_t fo = c.flags[o];
-      if (sensor && ((fo >> 1) & 3) == SG_ETYPE_PEDESTRIAN && !(d2 > r2)) {
-        if (ncand < CR_NBCAP) c.nbl[ncand * G + s] = (uint16_t)o;
-        ++ncand;
-      }
-      if (coll && o > (uint32_t)s && !(fo & 8)) {
-        const double rout = (double)rs.y + (double)c.rad[o].y;
-        if (!(d2 > rout * rout)) {  // (crowd_candidate repeats the circle tests; most candidates stop here)
-          const float4 mb = c.aabb[s], ob = c.aabb[o];
-          if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) crowd_candidate(c, sink, acc, s, (int)o);
-        }
-      }
-    }
+    for (; o != CR_NIL; o = c.gnext[o]) fn(o);
     o = nxt;
   }
-  if (sensor) {
-    c.ncnt[s] = (uint8_t)min(ncand, 255);
-    // slot (= state.poses) order: every listed slot goes to the rank of its id (ids are distinct)
-    const int n = min(ncand, CR_NBCAP);
-    uint32_t v[CR_NBCAP];
-#pragma unroll
-    for (int a = 0; a < CR_NBCAP; ++a) v[a] = a < n ? (uint32_t)c.nbl[a * G + s] : 0xffffffffu;
-    if (n > 1) {
-#pragma unroll
-      for (int a = 0; a < CR_NBCAP; ++a) {
-        int rank = 0;
-#pragma unroll
-        for (int b = 0; b < CR_NBCAP; ++b) rank += v[b] < v[a] ? 1 : 0;
-        if (a < n) c.nbl[rank * G + s] = (uint16_t)v[a];
+}
+
+// the tests of slot s (at px, py) against listed slot o: next tick's sensor list and this tick's pair
+struct CrowdSlot {
+  double px, py, r2;
+  int s, ncand;
+  bool sensor, coll;
+};
+template <bool DIRECT>
+SG_DEV void crowd_item(const Crowd& c, const CrowdSink& sink, const CrowdBoxes& bx, CrowdSlot& w, uint32_t o, int& mypairs) {
+  const int G = c.G;
+  const double ddx = c.state[o] - w.px, ddy = c.state[G + o] - w.py, d2 = ddx * ddx + ddy * ddy;
+  const uint8_t fo = c.flags[o];
+  if (!DIRECT && w.sensor && ((fo >> 1) & 3) == SG_ETYPE_PEDESTRIAN && !(d2 > w.r2)) {
+    if (w.ncand < CR_NBCAP) c.nbl[w.ncand * G + w.s] = (uint16_t)o;
+    ++w.ncand;
+  }
+  if (w.coll && o > (uint32_t)w.s && !(fo & 8)) crowd_pair<DIRECT>(c, sink, bx, w.s, (int)o, d2, mypairs);
+}
+
+// ---------------------------------------------------------------------------------
+// One pass over the 3 x 3 cells around present slot s on the grid of the positions just computed serves
+//   * the pedestrian's sensor of the NEXT tick (neighbours strictly inside the 64-gon of
+//     circumradius r lie in these cells): pedestrians within r (1 + 1e-9) go to the slot's
+//     candidate list, which is then put in slot (= state.poses) order, and
+//   * this tick's collision broad phase: pairs (s, o), o > s, of entities small enough for the grid
+//     (circumscribed radius <= half a cell: their boxes can only meet from neighbouring cells).
+// The ragged part -- chasing the cells' lists -- only copies ids into the thread's strip of `pool`;
+// the tests then run over the strip in a plain counted loop.
+// `r2` = (r (1 + 1e-9))^2; sensor = the slot is a present pedestrian; coll = it takes part in the
+// cell broad phase (present, not large).
+// Called by all 32 lanes of a warp (`active`: the slot is present and has something to test): the
+// lanes leave the ragged walk at different times and are brought together again before the counted
+// loop and before the sorting network, which would otherwise run once per straggler group.
+template <bool DIRECT>
+SG_DEV void crowd_scan(const Crowd& c, const CrowdSink& sink, const CrowdBoxes& bx, int s, bool active, bool sensor,
+                       bool coll, double r2, double gox, double goy, double inv_cs, uint16_t* mypool, int& mypairs) {
+  const int G = c.G;
+  CrowdSlot w;
+  w.px = c.state[s]; w.py = c.state[G + s]; w.r2 = r2;
+  w.s = s; w.ncand = 0; w.sensor = sensor; w.coll = coll;
+  const int ix = __double2int_rd((w.px - gox) * inv_cs), iy = __double2int_rd((w.py - goy) * inv_cs);
+  int k = 0;
+  if (active)
+    crowd_cells(c, ix, iy, [&](uint32_t o) {
+      if (o != (uint32_t)s) {
+        if (k < CR_CAP) mypool[k * 32] = (uint16_t)o;
+        ++k;
       }
+    });
+  __syncwarp();
+  const int kk = min(k, CR_CAP), kmax = __reduce_max_sync(0xffffffffu, kk);
+  for (int j = 0; j < kmax; ++j)
+    if (j < kk) crowd_item<DIRECT>(c, sink, bx, w, (uint32_t)mypool[j * 32], mypairs);
+  if (k > CR_CAP) {  // (a very dense neighbourhood: the ids beyond the strip are tested while walking)
+    int j = 0;
+    crowd_cells(c, ix, iy, [&](uint32_t o) {
+      if (o != (uint32_t)s && j++ >= CR_CAP) crowd_item<DIRECT>(c, sink, bx, w, o, mypairs);
+    });
+  }
+  __syncwarp();
+  if (!DIRECT && sensor) {
+    c.ncnt[s] = (uint8_t)min(w.ncand, 255);
+    // slot (= state.poses) order: a sorting network over the (at most CR_NBCAP) listed ids
+    const int n = min(w.ncand, CR_NBCAP);
+    if (n > 1) {
+      uint32_t v[CR_NBCAP];
+#pragma unroll
+      for (int a = 0; a < CR_NBCAP; ++a) v[a] = a < n ? (uint32_t)c.nbl[a * G + s] : 0xffffu;
+#define CR_CE(a, b) { const uint32_t lo_ = min(v[a], v[b]), hi_ = max(v[a], v[b]); v[a] = lo_; v[b] = hi_; }
+      CR_CE(0, 2) CR_CE(1, 3) CR_CE(4, 6) CR_CE(5, 7)
+      CR_CE(0, 4) CR_CE(1, 5) CR_CE(2, 6) CR_CE(3, 7)
+      CR_CE(0, 1) CR_CE(2, 3) CR_CE(4, 5) CR_CE(6, 7)
+      CR_CE(2, 4) CR_CE(3, 5)
+      CR_CE(1, 4) CR_CE(3, 6)
+      CR_CE(1, 2) CR_CE(3, 4) CR_CE(5, 6)
+#undef CR_CE
+#pragma unroll
+      for (int a = 0; a < CR_NBCAP; ++a)
+        if (a < n) c.nbl[a * G + s] = (uint16_t)v[a];
+    }
+  }
+}
+
+// the pairs of present slot s this tick: through the grid (crowd_scan) when s is small, against the
+// list of large entities, or -- too many large entities for the list -- against every later slot
+// (called by all lanes of a warp; fl = the slot's flags, bit 0: present)
+template <bool DIRECT>
+SG_DEV void crowd_slot_pairs(const Crowd& c, const CrowdSink& sink, const CrowdBoxes& bx, int s, uint8_t fl,
+                             bool need_coll, bool exhaustive, double r2, double gox, double goy, double inv_cs,
+                             uint16_t* mypool, int& mypairs) {
+  const int G = c.G;
+  const bool pres = (fl & 1) != 0, large = (fl & 8) != 0;
+  const bool sensor = !DIRECT && pres && ((fl >> 1) & 3) == SG_ETYPE_PEDESTRIAN;
+  const bool coll = pres && need_coll && !large && !exhaustive;
+  crowd_scan<DIRECT>(c, sink, bx, s, sensor || coll, sensor, coll, r2, gox, goy, inv_cs, mypool, mypairs);
+  if (!need_coll || !pres) return;
+  const double px = c.state[s], py = c.state[G + s];
+  if (!exhaustive) {  // the large entities are kept in a list everyone tests against
+    const int nl = c.gmisc[0];
+    for (int k = 0; k < nl; ++k) {
+      const int o = c.glarge[k];
+      if (o == s || (large && o < s) || !(c.flags[o] & 1)) continue;
+      const double ddx = c.state[o] - px, ddy = c.state[G + o] - py;
+      crowd_pair<DIRECT>(c, sink, bx, min(s, o), max(s, o), ddx * ddx + ddy * ddy, mypairs);
+    }
+  } else {
+    for (int o = s + 1; o < c.M; ++o) {
+      if (!(c.flags[o] & 1)) continue;
+      const double ddx = c.state[o] - px, ddy = c.state[G + o] - py;
+      crowd_pair<DIRECT>(c, sink, bx, s, o, ddx * ddx + ddy * ddy, mypairs);
     }
   }
 }
@@ -412,8 +458,9 @@ enum { U_INV_CS = 0, U_SIGHT, U_SH, U_CH, U_OX, U_OY, U_LEN };  // the ego's |v|
 
 template <int EPT>
 __global__ void __launch_bounds__(CR_THREADS, 2)
-sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, CrowdLayout L) {
+sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
   extern __shared__ __align__(16) unsigned char smem[];
+  constexpr CrowdLayout L = crowd_layout(EPT);
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int M = sc.n_slots, G = L.G, W = L.W, WM = (M + 31) / 32;
   Crowd c;
@@ -435,6 +482,7 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
     c.unif[U_OX] = __ldg(sc.traj_rows + er * 7 + 1);
     c.unif[U_OY] = __ldg(sc.traj_rows + er * 7 + 2);
     c.unif[U_LEN] = sc.length[n];
+    c.gmisc[0] = 0;  // entities too large for the grid (a property of the box: listed once, below)
   }
   __syncthreads();
 #define grid_inv_cs (c.unif[U_INV_CS])
@@ -473,6 +521,12 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
         const double rin = (bcx == 0.0 && bcy == 0.0) ? 0.5 * fmin(aw, al) * (1.0 - 1e-6) : 0.0;
         const double rout = (0.5 * sqrt(aw * aw + al * al) + off) * (1.0 + 1e-6);
         rd = make_float2(__double2float_rd(rin), __double2float_ru(rout));
+        // the box stays within rout of the pose position: up to half a cell, boxes only meet from neighbouring cells
+        if (!((double)rd.y <= 0.5 * grid_cs * (1.0 - 1e-6))) {
+          fl |= 8;
+          const int k = atomicAdd(&c.gmisc[0], 1);
+          if (k < SG_GRID_LCAP) c.glarge[k] = (uint16_t)s;
+        }
         if (s == ego_slot) {
           c.cold_d[CR_EGO_SPEED] = norm3(vx, vy, st.vel[2 * nm + i]);
           c.cold_d[CR_EGO_DIST] = me.dist;
@@ -484,7 +538,6 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
     c.wflag[s] = 0;
     c.rad[s] = rd;
     c.orient[s] = oh;
-    c.aabb[s] = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
     ent[e] = me;
   }
   double t = st.t[n], prev_t = st.prev_t[n];
@@ -502,26 +555,30 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
   if (tid < W) {
     c.ego_last[tid] = tid < WM ? st.ego_hits[(int64_t)n * WM + tid] : 0u;
     c.ego_now[tid] = 0;
-    c.bits[tid] = 0; c.bits[W + tid] = 0;
+    c.bits[tid] = 0;
   }
   crowd_grid_clear(c);
   cta_sync();
 #pragma unroll 1
   for (int e = 0; e < EPT; ++e) {  // the grid of the loaded positions: the sensors of the first tick
     const int s = tid + e * CR_THREADS;
-    if (c.flags[s] & 1) crowd_grid_insert(c, s, false, ox, oy, grid_cs, grid_inv_cs);
+    if (c.flags[s] & 1) crowd_grid_insert(c, s, ox, oy, grid_inv_cs);
   }
   cta_sync();
+  uint16_t* const mypool = c.pool + (tid >> 5) * (CR_CAP * 32) + lane;  // this thread's strip: mypool[k * 32]
+  CrowdBoxes bx;
+  bx.box = sc.box; bx.nm = nm; bx.i0 = i0;
+  const double rr_sensor = p.ped_distance_threshold * (1.0 + 1e-9);
   {
-    const double rr = p.ped_distance_threshold * (1.0 + 1e-9), r2s = rr * rr;
     CrowdSink nosink;
     nosink.acc = c.acc; nosink.bits = c.bits; nosink.ego_now = c.ego_now; nosink.rows = nullptr;
-    nosink.W = WM; nosink.ego_slot = ego_slot; nosink.first_slot = first_slot;
+    nosink.W = WM; nosink.ego_slot = ego_slot; nosink.first_slot = first_slot; nosink.need_first = false;
+    int nopairs = 0;
 #pragma unroll 1
     for (int e = 0; e < EPT; ++e) {
       const int s = tid + e * CR_THREADS;
       const uint8_t fl = c.flags[s];
-      if ((fl & 1) && ((fl >> 1) & 3) == SG_ETYPE_PEDESTRIAN) crowd_walk(c, nosink, c.acc, s, true, false, r2s, ox, oy, grid_inv_cs);
+      crowd_slot_pairs<false>(c, nosink, bx, s, fl, false, false, rr_sensor * rr_sensor, ox, oy, grid_inv_cs, mypool, nopairs);
     }
   }
   cta_sync();
@@ -723,14 +780,8 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
       }
       if (me.kind != SG_KIND_EMPTY) {
         c.flags[s] = (uint8_t)((c.flags[s] & ~1) | (newpres ? 1 : 0));
-        float4 bb = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
-        if (newpres && need_coll) {
-          c.fcs[s] = cs; c.fcs[G + s] = sn;
-          bb = make_aabb_box(nx, ny, cs, sn, __ldg(sc.box + i), __ldg(sc.box + nm + i), __ldg(sc.box + 2 * nm + i),
-                             __ldg(sc.box + 3 * nm + i), ox, oy);
-        }
-        c.aabb[s] = bb;
-        if (newpres) crowd_grid_insert(c, s, need_coll, ox, oy, grid_cs, grid_inv_cs);
+        if (newpres && need_coll) { c.fcs[s] = cs; c.fcs[G + s] = sn; }
+        if (newpres) crowd_grid_insert(c, s, ox, oy, grid_inv_cs);
         if (matrix) {
           uint32_t* row = st.coll_mask + ((int64_t)n * M + s) * WM;
           for (int w = 0; w < WM; ++w) row[w] = 0;
@@ -741,44 +792,20 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
     cta_sync();  // the rows, boxes and the grid of the new positions are complete
     int* acc = c.acc + parity * ACC_N;
     CrowdSink sink;
-    sink.acc = acc; sink.bits = c.bits + parity * W; sink.ego_now = c.ego_now;
+    sink.acc = acc; sink.bits = c.bits; sink.ego_now = c.ego_now;
     sink.rows = matrix ? st.coll_mask + (int64_t)n * M * WM : nullptr;
     sink.W = WM; sink.ego_slot = ego_slot; sink.first_slot = first_slot;
+    sink.need_first = c.cold_i[COLD_FIRST_TICK] < 0;  // (written in phase E only, behind the barriers)
     const bool exhaustive = need_coll && c.gmisc[0] > SG_GRID_LCAP;  // too many large entities for the list
+    int mypairs = 0;
     {
       // ================= phase C: next tick's sensor candidates + broad phase ========================
-      const double rr = p.ped_distance_threshold * (1.0 + 1e-9), r2s = rr * rr;
+      const double r2s = rr_sensor * rr_sensor;
 #pragma unroll 1
       for (int e = 0; e < EPT; ++e) {
         const int s = tid + e * CR_THREADS;
         const uint8_t fl = c.flags[s];
-        const bool pres = (fl & 1) != 0, large = (fl & 8) != 0;
-        const bool sensor = pres && ((fl >> 1) & 3) == SG_ETYPE_PEDESTRIAN;
-        if (!exhaustive) {
-          if (!pres) continue;
-          crowd_walk(c, sink, acc, s, sensor, need_coll && !large, r2s, ox, oy, grid_inv_cs);
-          if (need_coll) {  // the large entities are kept in a list everyone tests against
-            const float4 mb = c.aabb[s];
-            const int nl = c.gmisc[0];
-            for (int k = 0; k < nl; ++k) {
-              const int o = c.glarge[k];
-              if (o == s || (large && o < s)) continue;
-              const float4 ob = c.aabb[o];
-              if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) crowd_candidate(c, sink, acc, min(s, o), max(s, o));
-            }
-          }
-        } else if (!pres) {
-          continue;
-        } else {  // too many large entities for the list: exhaustive sweeps (sensor candidates included)
-          crowd_walk(c, sink, acc, s, sensor, false, r2s, ox, oy, grid_inv_cs);
-          {
-            const float4 mb = c.aabb[s];
-            for (int o = s + 1; o < M; ++o) {
-              const float4 ob = c.aabb[o];
-              if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) crowd_candidate(c, sink, acc, s, o);
-            }
-          }
-        }
+        crowd_slot_pairs<false>(c, sink, bx, s, fl, need_coll, exhaustive, r2s, ox, oy, grid_inv_cs, mypool, mypairs);
       }
       cta_sync();
       // ================= phase D: exact narrow phase ================================================
@@ -787,32 +814,19 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
         for (int q = tid; q < nq; q += CR_THREADS) {
           const uint32_t pr = c.queue[q];
           const int a = (int)(pr >> 16), b = (int)(pr & 0xffff);
-          if (crowd_pair_collides(c.state, c.fcs, sc.box, nm, i0, c.orient, G, a, b)) crowd_commit(sink, a, b);
+          if (crowd_pair_collides(c.state, c.fcs, sc.box, nm, i0, c.orient, G, a, b)) crowd_commit(sink, a, b, mypairs);
         }
-      } else {  // queue overflow (very dense scenes): walk the candidates again and decide in place
+      } else {  // queue overflow (very dense scenes): go over the candidates again and decide in place
 #pragma unroll 1
         for (int e = 0; e < EPT; ++e) {
           const int s = tid + e * CR_THREADS;
-          if (!(c.flags[s] & 1)) continue;
-          auto direct = [&](int a, int b) {
-            const float2 ra = c.rad[a], rb = c.rad[b];
-            const double dx = c.state[a] - c.state[b], dy = c.state[G + a] - c.state[G + b];
-            const double d2 = dx * dx + dy * dy;
-            const double rin = (double)ra.x + (double)rb.x, rout = (double)ra.y + (double)rb.y;
-            if (d2 > rout * rout) return;
-            if (d2 < rin * rin && d2 > 0.0) return;  // booked in phase C already
-            if (crowd_pair_collides(c.state, c.fcs, sc.box, nm, i0, c.orient, G, a, b)) crowd_commit(sink, a, b);
-          };
-          if (!exhaustive) {
-            crowd_for_each_candidate(c, s, ox, oy, grid_inv_cs, direct);
-          } else {
-            const float4 mb = c.aabb[s];
-            for (int o = s + 1; o < M; ++o) {
-              const float4 ob = c.aabb[o];
-              if (mb.x <= ob.z && ob.x <= mb.z && mb.y <= ob.w && ob.y <= mb.w) direct(s, o);
-            }
-          }
+          const uint8_t fl = c.flags[s];
+          crowd_slot_pairs<true>(c, sink, bx, s, fl, need_coll, exhaustive, r2s, ox, oy, grid_inv_cs, mypool, mypairs);
         }
+      }
+      {  // the colliding pairs this thread booked: one shared atomic per warp
+        const int wsum = __reduce_add_sync(0xffffffffu, mypairs);
+        if (lane == 0 && wsum) atomicAdd(&acc[ACC_NPAIRS], wsum);
       }
       cta_sync();
     }
@@ -823,13 +837,6 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
     if ((p.terminal & SG_TERM_COLLISION) && npairs > 0) dn = true;
     if ((p.terminal & SG_TERM_EGO_COLLISION) && acc[ACC_FIRST_HIT]) dn = true;
     done = dn;
-    if (npairs > 0) {  // slots in a collision this tick
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        const int s = tid + e * CR_THREADS;
-        ent[e].bits |= (c.bits[parity * W + (s >> 5)] >> (s & 31)) & 1u;
-      }
-    }
     if (tid == 32) {
       int* cold = c.cold_i;
       if (npairs > 0) {
@@ -851,7 +858,6 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
         c.ego_last[w] = now;
       }
       c.ego_now[w] = 0;
-      c.bits[(parity ^ 1) * W + w] = 0;
     }
     if (tid == 0 && (p.features & SG_FEAT_EGO_METRICS)) {  // metrics/trajectory.py:20-24,39-42,58-60
       double* m = c.cold_d;
@@ -874,7 +880,7 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, Cr
     if (s >= M || me.kind == SG_KIND_EMPTY) continue;
     const int64_t i = i0 + s;
     st.present[i] = (c.flags[s] & 1) != 0;
-    st.collided[i] = (uint8_t)(me.bits & 1u);
+    st.collided[i] = (uint8_t)((me.bits | (c.bits[s >> 5] >> (s & 31))) & 1u);  // before the launch or during it
     if (me.kind == SG_KIND_PEDESTRIAN) {
       st.pose[i] = c.state[s]; st.pose[nm + i] = c.state[G + s]; st.pose[3 * nm + i] = me.h;
       st.vel[i] = c.state[2 * G + s]; st.vel[nm + i] = c.state[3 * G + s];
@@ -908,6 +914,6 @@ cudaError_t sgi_launch_crowd(cudaStream_t s, const SgScene& sc, const SgParams& 
   auto kern = ept == 2 ? sg_crowd_kernel<2> : sg_crowd_kernel<1>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes);
   if (err != cudaSuccess) return err;
-  kern<<<sc.n_scenarios, CR_THREADS, L.bytes, s>>>(sc, p, st, in, n_ticks, L);
+  kern<<<sc.n_scenarios, CR_THREADS, L.bytes, s>>>(sc, p, st, in, n_ticks);
   return cudaGetLastError();
 }
