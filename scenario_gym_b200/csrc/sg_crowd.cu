@@ -27,39 +27,36 @@
 #include "sg_common.cuh"
 #include "sg_internal.h"
 
-#define CR_THREADS 512
 #define CR_NBCAP 8       // per-pedestrian neighbour candidate list
-#define CR_WARPS (CR_THREADS / 32)
 #define CR_CAP 16        // ids a slot gathers from its 3 x 3 cells before the tests (more: tested while walking)
 
 struct CrowdLayout {
   int G, W, QCAP;
   int off_state, off_fcs, off_pool, off_rad, off_nbl, off_gstart, off_gsorted, off_glarge, off_queue, off_flags,
-      off_wflag, off_ncnt, off_orient, off_hits, off_bits, off_acc, off_cold, off_gmisc, off_unif;
+      off_ncnt, off_orient, off_hits, off_bits, off_acc, off_cold, off_gmisc, off_unif;
   int bytes;
 };
 
 // (constexpr: the kernel's shared-memory views are compile-time offsets, no registers or address arithmetic)
-__host__ __device__ constexpr CrowdLayout crowd_layout(int ept) {
+__host__ __device__ constexpr CrowdLayout crowd_layout(int ept, int threads) {
   CrowdLayout L{};
-  const int G = CR_THREADS * ept;
+  const int G = threads * ept;
   L.G = G;
   L.W = G / 32;
   L.QCAP = 2 * G;
   int o = 0;
-  L.off_state = o;   o += 4 * G * (int)sizeof(double);          // x, y, vx, vy
-  L.off_fcs = o;     o += 2 * G * (int)sizeof(double);          // force (A -> B), then cos / sin of the heading
-  L.off_pool = o;    o += CR_WARPS * CR_CAP * 32 * (int)sizeof(uint16_t);  // [warp][k][lane]: gathered ids
+  L.off_state = o;   o += 2 * 4 * G * (int)sizeof(double);      // x, y, vx, vy: the State of this tick and of the next
+  L.off_fcs = o;     o += 2 * G * (int)sizeof(double);          // cos / sin of the heading
+  L.off_pool = o;    o += (threads / 32) * CR_CAP * 32 * (int)sizeof(uint16_t);  // [warp][k][lane]: gathered ids
   L.off_rad = o;     o += G * (int)sizeof(float2);              // inscribed / circumscribed radius of each box
   L.off_nbl = o;     o += CR_NBCAP * G * (int)sizeof(uint16_t);
   o = (o + 15) / 16 * 16;
-  L.off_gstart = o;  o += SG_GRID_CELLS * (int)sizeof(uint16_t);    // head slot of every cell's list (0xffff: empty)
+  L.off_gstart = o;  o += 2 * SG_GRID_CELLS * (int)sizeof(uint16_t);  // head slot of every cell's list (0xffff: empty), 2 grids
   L.off_gsorted = o; o += G * (int)sizeof(uint16_t);                // next slot in the cell's list
   L.off_glarge = o;  o += SG_GRID_LCAP * (int)sizeof(uint16_t);
   o = (o + 15) / 16 * 16;
   L.off_queue = o;   o += L.QCAP * (int)sizeof(uint32_t);
-  L.off_flags = o;   o += G;                                    // present | etype << 1 | large << 3
-  L.off_wflag = o;   o += G;                                    // walking this tick
+  L.off_flags = o;   o += 2 * G;                                // present | etype << 1 | large << 3, this tick / next
   L.off_ncnt = o;    o += G;                                    // sensor candidates of each slot (next tick)
   L.off_orient = o;  o += G;
   o = (o + 15) / 16 * 16;
@@ -85,7 +82,6 @@ struct Crowd {  // shared-memory views of one scenario
   uint16_t* glarge;
   uint32_t* queue;
   uint8_t* flags;
-  uint8_t* wflag;
   uint8_t* ncnt;
   int8_t* orient;
   uint32_t* ego_now;
@@ -110,7 +106,6 @@ SG_DEV void crowd_views(Crowd& c, const CrowdLayout& L, unsigned char* base, int
   c.glarge = (uint16_t*)(base + L.off_glarge);
   c.queue = (uint32_t*)(base + L.off_queue);
   c.flags = base + L.off_flags;
-  c.wflag = base + L.off_wflag;
   c.ncnt = base + L.off_ncnt;
   c.orient = (int8_t*)(base + L.off_orient);
   c.ego_now = (uint32_t*)(base + L.off_hits);
@@ -134,9 +129,9 @@ SG_DEV void cta_sync() { __syncthreads(); }
 // phase B, and the barrier that ends phase B publishes the lists.
 #define CR_NIL 0xffffu
 
-SG_DEV void crowd_grid_clear(const Crowd& c) {
-  uint32_t* w = (uint32_t*)c.ghead;
-  for (int q = threadIdx.x; q < SG_GRID_CELLS / 2; q += CR_THREADS) w[q] = 0xffffffffu;
+SG_DEV void crowd_grid_clear(uint16_t* ghead) {
+  uint4* w = (uint4*)ghead;
+  for (int q = threadIdx.x; q < SG_GRID_CELLS / 8; q += blockDim.x) w[q] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
 }
 
 // 16-bit exchange on a shared array through the containing 32-bit word
@@ -207,6 +202,9 @@ struct CrowdSink {  // where colliding pairs are booked (shared atomics)
   uint32_t* bits;
   uint32_t* ego_now;
   uint32_t* rows;
+  uint32_t* wqueue;  // this warp's strip of the pair queue and its fill count
+  int* wqcount;
+  int wqcap;
   int W, ego_slot, first_slot;
   bool need_first;  // no tick of this scenario had a collision yet: the smallest pair of the tick is wanted
 };
@@ -256,8 +254,8 @@ SG_DEV void crowd_pair(const Crowd& c, const CrowdSink& sink, const CrowdBoxes& 
     return;
   }
   if (!DIRECT) {
-    const int q = atomicAdd(&sink.acc[ACC_QCOUNT], 1);
-    if (q < c.QCAP) c.queue[q] = ((uint32_t)a << 16) | (uint32_t)b;
+    const int q = atomicAdd(sink.wqcount, 1);
+    if (q < sink.wqcap) sink.wqueue[q] = ((uint32_t)a << 16) | (uint32_t)b;
   } else if (crowd_pair_collides(c.state, c.fcs, bx.box, bx.nm, bx.i0, c.orient, c.G, a, b)) {
     crowd_commit(sink, a, b, mypairs);
   }
@@ -456,11 +454,15 @@ struct PerSlot {
 enum { CR_EGO_SPEED = COLD_T0, CR_EGO_DIST = COLD_T1 };
 enum { U_INV_CS = 0, U_SIGHT, U_SH, U_CH, U_OX, U_OY, U_LEN };  // the ego's |v| and distance, for the metrics
 
-template <int EPT>
-__global__ void __launch_bounds__(CR_THREADS, 2)
+#ifndef CR_MINB
+#define CR_MINB 1  // one scenario per SM at 128 registers: no spills, and shared memory for the double buffers
+#endif
+template <int EPT, int CR_THREADS>
+__global__ void __launch_bounds__(CR_THREADS, CR_MINB)
 sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr CrowdLayout L = crowd_layout(EPT);
+  constexpr CrowdLayout L = crowd_layout(EPT, CR_THREADS);
+  constexpr int CR_WARPS = CR_THREADS / 32;
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int M = sc.n_slots, G = L.G, W = L.W, WM = (M + 31) / 32;
   Crowd c;
@@ -535,7 +537,6 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
     }
     c.state[s] = x; c.state[G + s] = y; c.state[2 * G + s] = vx; c.state[3 * G + s] = vy;
     c.flags[s] = fl;
-    c.wflag[s] = 0;
     c.rad[s] = rd;
     c.orient[s] = oh;
     ent[e] = me;
@@ -557,7 +558,8 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
     c.ego_now[tid] = 0;
     c.bits[tid] = 0;
   }
-  crowd_grid_clear(c);
+  crowd_grid_clear(c.ghead);
+  crowd_grid_clear(c.ghead + SG_GRID_CELLS);
   cta_sync();
 #pragma unroll 1
   for (int e = 0; e < EPT; ++e) {  // the grid of the loaded positions: the sensors of the first tick
@@ -569,41 +571,63 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
   CrowdBoxes bx;
   bx.box = sc.box; bx.nm = nm; bx.i0 = i0;
   const double rr_sensor = p.ped_distance_threshold * (1.0 + 1e-9);
+  constexpr int QW = L.QCAP / CR_WARPS;  // pair queue strip of a warp
+  CrowdSink sink;
+  sink.bits = c.bits; sink.ego_now = c.ego_now;
+  sink.rows = matrix ? st.coll_mask + (int64_t)n * M * WM : nullptr;
+  sink.wqueue = c.queue + (tid >> 5) * QW; sink.wqcount = c.gmisc + 8 + (tid >> 5); sink.wqcap = QW;
+  sink.W = WM; sink.ego_slot = ego_slot; sink.first_slot = first_slot;
+  sink.acc = c.acc; sink.need_first = false;
   {
-    CrowdSink nosink;
-    nosink.acc = c.acc; nosink.bits = c.bits; nosink.ego_now = c.ego_now; nosink.rows = nullptr;
-    nosink.W = WM; nosink.ego_slot = ego_slot; nosink.first_slot = first_slot; nosink.need_first = false;
     int nopairs = 0;
 #pragma unroll 1
     for (int e = 0; e < EPT; ++e) {
       const int s = tid + e * CR_THREADS;
       const uint8_t fl = c.flags[s];
-      crowd_slot_pairs<false>(c, nosink, bx, s, fl, false, false, rr_sensor * rr_sensor, ox, oy, grid_inv_cs, mypool, nopairs);
+      crowd_slot_pairs<false>(c, sink, bx, s, fl, false, false, rr_sensor * rr_sensor, ox, oy, grid_inv_cs, mypool, nopairs);
     }
   }
   cta_sync();
 
   const int limit = n_ticks < 0 ? p.max_ticks : n_ticks;
   int parity = 0;
+  // The State rows / flags other threads read are double-buffered (`cur`: the buffer holding the current
+  // State), and so are the heads of the cell grid (`gp`: the grid the last candidate phase read, cleared
+  // during this tick while the owners insert into the other one): a tick needs two CTA barriers --
+  // new rows + grid complete, pairs booked -- instead of one per phase.
+  int cur = 0, gp = 0;
 
   for (int k = 0; k < limit && (!done || in.step_done); ++k) {
     const double next_t = t + p.timestep;  // scenario_gym.py:229
     const double step_dt = next_t - t;
-    crowd_grid_clear(c);  // (nobody reads the grid in phase A; the owners insert again at the end of phase B)
-    // ================= phase A: sensors + behaviour (reads the OLD rows of other slots) ==========
+    Crowd co = c, cn = c;  // views of the State before / after this tick's step
+    co.state = c.state + cur * 4 * G;       co.flags = c.flags + cur * G;
+    cn.state = c.state + (cur ^ 1) * 4 * G; cn.flags = c.flags + (cur ^ 1) * G;
+    cn.ghead = c.ghead + (gp ^ 1) * SG_GRID_CELLS;
+    g.pedbuf = co.state;
+    crowd_grid_clear(c.ghead + gp * SG_GRID_CELLS);
+    const double dt_state = t - prev_t;  // state.dt: PedestrianController uses the previous interval
+    const double t_old = t;
+    prev_t = t;
+    t = next_t;
+    tick += 1;
+    const double dt = t - prev_t;
+    const double rdt = 1.0 / dt;
 #pragma unroll 1
     for (int e = 0; e < EPT; ++e) {
       const int s = tid + e * CR_THREADS;
       PerSlot me = ent[0];
       if (EPT > 1 && e == 1) me = ent[EPT - 1];
-      const bool is_ped = me.kind == SG_KIND_PEDESTRIAN && (c.flags[s] & 1);
-      const double px = c.state[s], py = c.state[G + s];
+      const int64_t i = i0 + s;
+      const uint8_t fl_old = co.flags[s];
+      const bool present = (fl_old & 1) != 0;
+      const double px = co.state[s], py = co.state[G + s];
+      // ============ sensors + behaviour (reads the rows of other slots as they were before the tick) =====
+      const bool is_ped = me.kind == SG_KIND_PEDESTRIAN && present;
       bool walking = false;
       double F0 = 0.0, F1 = 0.0;
       int ncand = 0;
-      uint16_t* nbl = c.nbl + s;
       if (is_ped) {
-        const int64_t i = i0 + s;
         const int64_t r0 = sc.route_off[i];
         const int R = (int)(sc.route_off[i + 1] - r0);
         const double* route = sc.route_xy + 2 * r0;
@@ -628,11 +652,11 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
           if (dn == 0) dn += 0.000000001;
           const double ux = dvx / dn, uy = dvy / dn;
           const double kk = 1 / p.sf_relaxation_time;
-          F0 = kk * (speed_desired * ux - c.state[2 * G + s]);
-          F1 = kk * (speed_desired * uy - c.state[3 * G + s]);
+          F0 = kk * (speed_desired * ux - co.state[2 * G + s]);
+          F1 = kk * (speed_desired * uy - co.state[3 * G + s]);
         }
       }
-      // the sensor's candidates were listed by the walk over the grid of these (now old) positions
+      // the sensor's candidates were listed by the last candidate phase, on the grid of these positions
       if (walking) ncand = c.ncnt[s];
       // neighbour terms, pooled over the warp's 32 pedestrians of this pass and handed back to their
       // owners in list order (same sums, same order as one lane walking its own list)
@@ -663,7 +687,7 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
           if (it < total) {
             const int slot = wslot0 + q;
             const int o = c.nbl[(it - offq) * G + slot];
-            nf = neighbour_force(p, g, c.state[slot], c.state[G + slot], o, step_dt, sh_rot, ch_rot, sight_cos);
+            nf = neighbour_force(p, g, co.state[slot], co.state[G + slot], o, step_dt, sh_rot, ch_rot, sight_cos);
           }
           const int lo = max(off, base), hi = min(off + nlist, base + 32);
           const int cnt = max(hi - lo, 0);
@@ -679,40 +703,20 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
       }
       if (walking && ncand > CR_NBCAP) {  // very dense crowd: every present pedestrian in slot order
         for (int o = 0; o < M; ++o) {
-          if (o == s || (c.flags[o] & 7) != (1 | (SG_ETYPE_PEDESTRIAN << 1))) continue;
+          if (o == s || (co.flags[o] & 7) != (1 | (SG_ETYPE_PEDESTRIAN << 1))) continue;
           const NbForce nf = neighbour_force(p, g, px, py, o, step_dt, sh_rot, ch_rot, sight_cos);
           if (nf.valid) { F0 += nf.a0; F1 += nf.a1; F0 += nf.b0; F1 += nf.b1; }
         }
       }
-      c.fcs[s] = F0; c.fcs[G + s] = F1;
-      c.wflag[s] = walking ? 1 : 0;
-      if (e == 0) ent[0].goal = me.goal; else ent[EPT - 1].goal = me.goal;
-    }
-    cta_sync();
-    // ================= phase B: controllers + State.step on the own rows ===========================
-    const double dt_state = t - prev_t;  // state.dt: PedestrianController uses the previous interval
-    const double t_old = t;
-    prev_t = t;
-    t = next_t;
-    tick += 1;
-    const double dt = t - prev_t;
-    const double rdt = 1.0 / dt;
-#pragma unroll 1
-    for (int e = 0; e < EPT; ++e) {
-      const int s = tid + e * CR_THREADS;
-      PerSlot me = ent[0];
-      if (EPT > 1 && e == 1) me = ent[EPT - 1];
-      const int64_t i = i0 + s;
-      const bool present = (c.flags[s] & 1) != 0;
+      // ============ controller + State.step on the own row (written to the other buffer) =================
       bool newpres = false;
-      double cs = 1.0, sn = 0.0, nx = c.state[s], ny = c.state[G + s];
+      double cs = 1.0, sn = 0.0, nx = px, ny = py, nvx = co.state[2 * G + s], nvy = co.state[3 * G + s];
       if (me.kind == SG_KIND_PEDESTRIAN) {
         double prevx = nx, prevy = ny, prevh = me.h, nh = me.h;
         bool moved = false;
         if (present) {
-          double speed, heading, F0 = 0.0, F1 = 0.0;
-          if (c.wflag[s]) {
-            F0 = c.fcs[s]; F1 = c.fcs[G + s];
+          double speed, heading;
+          if (walking) {
             double speed_rand = p.sf_bias_lon, heading_rand = p.sf_bias_lat;
             if (p.sf_std_lon != 0.0 || p.sf_std_lat != 0.0) {  // engine-defined noise stream (sg_device.cuh)
               const double2 z = sg_noise2(p.sf_noise_seed, i, tick - 1);
@@ -722,7 +726,7 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
             speed = py_min(norm2(F0, F1) + speed_rand, sc.ped_speed_desired[i] * p.sf_max_speed_factor);
             heading = atan2(F1, F0) + heading_rand;
           } else {  // agent.py:65-68
-            speed = 0; heading = 0;
+            speed = 0; heading = 0; F0 = 0.0; F1 = 0.0;
           }
           // PedestrianController._step, pedestrian/controller.py:38-46 (uses state.dt)
           const double sp = np_clip(speed, -p.ped_max_speed, p.ped_max_speed);
@@ -755,9 +759,7 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
         }
         if (moved) {
           const double ex = nx - prevx, ey = ny - prevy;
-          const double nvx = div_r(ex, dt, rdt), nvy = div_r(ey, dt, rdt);
-          c.state[s] = nx; c.state[G + s] = ny;
-          c.state[2 * G + s] = nvx; c.state[3 * G + s] = nvy;
+          nvx = div_r(ex, dt, rdt); nvy = div_r(ey, dt, rdt);
           st.vel[3 * nm + i] = div_r(nh - prevh, dt, rdt);
           me.h = nh;
           if (present) {
@@ -771,17 +773,17 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
         const CrowdReplayOut r = crowd_replay_step(sc, st, i, nm, present, t_old, t);
         newpres = r.present;
         if (newpres) {
-          nx = r.x; ny = r.y;
-          c.state[s] = r.x; c.state[G + s] = r.y; c.state[2 * G + s] = r.vx; c.state[3 * G + s] = r.vy;
+          nx = r.x; ny = r.y; nvx = r.vx; nvy = r.vy;
           me.h = r.h;
           sincos(r.h, &sn, &cs);
           if (s == ego_slot) { c.cold_d[CR_EGO_SPEED] = r.speed3; c.cold_d[CR_EGO_DIST] = st.dist[i]; }
         }
       }
+      cn.state[s] = nx; cn.state[G + s] = ny; cn.state[2 * G + s] = nvx; cn.state[3 * G + s] = nvy;
+      cn.flags[s] = (uint8_t)((fl_old & ~1) | (newpres ? 1 : 0));
       if (me.kind != SG_KIND_EMPTY) {
-        c.flags[s] = (uint8_t)((c.flags[s] & ~1) | (newpres ? 1 : 0));
         if (newpres && need_coll) { c.fcs[s] = cs; c.fcs[G + s] = sn; }
-        if (newpres) crowd_grid_insert(c, s, ox, oy, grid_inv_cs);
+        if (newpres) crowd_grid_insert(cn, s, ox, oy, grid_inv_cs);
         if (matrix) {
           uint32_t* row = st.coll_mask + ((int64_t)n * M + s) * WM;
           for (int w = 0; w < WM; ++w) row[w] = 0;
@@ -789,48 +791,44 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
       }
       if (e == 0) ent[0] = me; else ent[EPT - 1] = me;
     }
-    cta_sync();  // the rows, boxes and the grid of the new positions are complete
+    if (lane == 0) *sink.wqcount = 0;
+    cta_sync();  // the rows, the flags and the grid of the new positions are complete
     int* acc = c.acc + parity * ACC_N;
-    CrowdSink sink;
-    sink.acc = acc; sink.bits = c.bits; sink.ego_now = c.ego_now;
-    sink.rows = matrix ? st.coll_mask + (int64_t)n * M * WM : nullptr;
-    sink.W = WM; sink.ego_slot = ego_slot; sink.first_slot = first_slot;
-    sink.need_first = c.cold_i[COLD_FIRST_TICK] < 0;  // (written in phase E only, behind the barriers)
+    sink.acc = acc;
+    sink.need_first = c.cold_i[COLD_FIRST_TICK] < 0;  // (written in the tick epilogue only, behind the barriers)
     const bool exhaustive = need_coll && c.gmisc[0] > SG_GRID_LCAP;  // too many large entities for the list
     int mypairs = 0;
     {
-      // ================= phase C: next tick's sensor candidates + broad phase ========================
+      // ============ next tick's sensor candidates + broad phase; the warp then decides the pairs it queued =====
       const double r2s = rr_sensor * rr_sensor;
 #pragma unroll 1
       for (int e = 0; e < EPT; ++e) {
         const int s = tid + e * CR_THREADS;
-        const uint8_t fl = c.flags[s];
-        crowd_slot_pairs<false>(c, sink, bx, s, fl, need_coll, exhaustive, r2s, ox, oy, grid_inv_cs, mypool, mypairs);
+        crowd_slot_pairs<false>(cn, sink, bx, s, cn.flags[s], need_coll, exhaustive, r2s, ox, oy, grid_inv_cs, mypool, mypairs);
       }
-      cta_sync();
-      // ================= phase D: exact narrow phase ================================================
-      const int nq = acc[ACC_QCOUNT];
-      if (nq <= c.QCAP) {
-        for (int q = tid; q < nq; q += CR_THREADS) {
-          const uint32_t pr = c.queue[q];
+      __syncwarp();
+      const int nq = *sink.wqcount;
+      if (nq <= QW) {
+        for (int q = lane; q < nq; q += 32) {
+          const uint32_t pr = sink.wqueue[q];
           const int a = (int)(pr >> 16), b = (int)(pr & 0xffff);
-          if (crowd_pair_collides(c.state, c.fcs, sc.box, nm, i0, c.orient, G, a, b)) crowd_commit(sink, a, b, mypairs);
+          if (crowd_pair_collides(cn.state, c.fcs, sc.box, nm, i0, c.orient, G, a, b)) crowd_commit(sink, a, b, mypairs);
         }
-      } else {  // queue overflow (very dense scenes): go over the candidates again and decide in place
+      } else {  // the warp's strip overflowed (very dense scenes): go over its candidates again and decide in place
 #pragma unroll 1
         for (int e = 0; e < EPT; ++e) {
           const int s = tid + e * CR_THREADS;
-          const uint8_t fl = c.flags[s];
-          crowd_slot_pairs<true>(c, sink, bx, s, fl, need_coll, exhaustive, r2s, ox, oy, grid_inv_cs, mypool, mypairs);
+          crowd_slot_pairs<true>(cn, sink, bx, s, cn.flags[s], need_coll, exhaustive, r2s, ox, oy, grid_inv_cs, mypool, mypairs);
         }
       }
+      __syncwarp();
       {  // the colliding pairs this thread booked: one shared atomic per warp
         const int wsum = __reduce_add_sync(0xffffffffu, mypairs);
         if (lane == 0 && wsum) atomicAdd(&acc[ACC_NPAIRS], wsum);
       }
       cta_sync();
     }
-    // ================= phase E: terminal check + metrics ===========================================
+    // ============ terminal check + metrics ==========================================================
     const int npairs = acc[ACC_NPAIRS];
     bool dn = false;  // state.py:268-270, 397-408
     if ((p.terminal & SG_TERM_MAX_LENGTH) && (t + dt > length)) dn = true;
@@ -859,7 +857,9 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
       }
       c.ego_now[w] = 0;
     }
-    if (tid == 0 && (p.features & SG_FEAT_EGO_METRICS)) {  // metrics/trajectory.py:20-24,39-42,58-60
+    // (by the thread that owns the ego's row: it writes the ego's speed / distance in the next step phase,
+    // which other warps may already have entered)
+    if (tid == (ego_slot & (CR_THREADS - 1)) && (p.features & SG_FEAT_EGO_METRICS)) {  // metrics/trajectory.py:20-24,39-42,58-60
       double* m = c.cold_d;
       const double sp = m[CR_EGO_SPEED];
       const double w = m[COLD_AVG_T] / t;
@@ -869,21 +869,25 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
       m[COLD_EGOD] = m[CR_EGO_DIST];
     }
     parity ^= 1;
+    cur ^= 1;
+    gp ^= 1;
   }
   cta_sync();
 
   // ---------------- write the rows back --------------------------------------------------------------
+  const double* rows = c.state + cur * 4 * G;
+  const uint8_t* flags = c.flags + cur * G;
 #pragma unroll
   for (int e = 0; e < EPT; ++e) {
     const int s = tid + e * CR_THREADS;
     const PerSlot me = ent[e];
     if (s >= M || me.kind == SG_KIND_EMPTY) continue;
     const int64_t i = i0 + s;
-    st.present[i] = (c.flags[s] & 1) != 0;
+    st.present[i] = (flags[s] & 1) != 0;
     st.collided[i] = (uint8_t)((me.bits | (c.bits[s >> 5] >> (s & 31))) & 1u);  // before the launch or during it
     if (me.kind == SG_KIND_PEDESTRIAN) {
-      st.pose[i] = c.state[s]; st.pose[nm + i] = c.state[G + s]; st.pose[3 * nm + i] = me.h;
-      st.vel[i] = c.state[2 * G + s]; st.vel[nm + i] = c.state[3 * G + s];
+      st.pose[i] = rows[s]; st.pose[nm + i] = rows[G + s]; st.pose[3 * nm + i] = me.h;
+      st.vel[i] = rows[2 * G + s]; st.vel[nm + i] = rows[3 * G + s];
       if (me.bits & 2u) { st.vel[2 * nm + i] = 0.0; st.vel[4 * nm + i] = 0.0; st.vel[5 * nm + i] = 0.0; }
       st.dist[i] = me.dist;
       st.goal_idx[i] = me.goal;
@@ -907,13 +911,19 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
 #undef length
 }
 
+#ifndef CR_WIDE
+#define CR_WIDE 1
+#endif
 cudaError_t sgi_launch_crowd(cudaStream_t s, const SgScene& sc, const SgParams& p, const SgState& st,
                              const SgInputs& in, int n_ticks) {
-  const int ept = sc.n_slots > CR_THREADS ? 2 : 1;
-  const CrowdLayout L = crowd_layout(ept);
-  auto kern = ept == 2 ? sg_crowd_kernel<2> : sg_crowd_kernel<1>;
+  // up to 512 slots: 512 threads, a slot each; up to 1024: 1024 threads at 64 registers (CR_WIDE) or 512
+  // threads owning two slots each at 128 registers
+  const bool big = sc.n_slots > 512;
+  const int threads = (big && CR_WIDE) ? 1024 : 512;
+  const CrowdLayout L = crowd_layout(big && !CR_WIDE ? 2 : 1, threads);
+  auto kern = !big ? sg_crowd_kernel<1, 512> : (CR_WIDE ? sg_crowd_kernel<1, 1024> : sg_crowd_kernel<2, 512>);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes);
   if (err != cudaSuccess) return err;
-  kern<<<sc.n_scenarios, CR_THREADS, L.bytes, s>>>(sc, p, st, in, n_ticks);
+  kern<<<sc.n_scenarios, threads, L.bytes, s>>>(sc, p, st, in, n_ticks);
   return cudaGetLastError();
 }
