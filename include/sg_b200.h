@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 10
+#define SG_ABI_VERSION 11
 
 /* entity slot kinds (who produces the slot's next pose each tick) */
 enum SgKind {
@@ -337,6 +337,15 @@ int sg_fill_random_actions(const SgActionRng* rng, int tick0, int n_ticks, int64
    (their rows are zeroed).  x, y, r [N], out [N*M]: device memory. */
 int sg_entities_in_radius(const SgState* state, int n_scenarios, int n_slots, const double* x, const double* y,
                           const double* r, uint8_t* out, int device, void* stream);
+
+/* BatchReplayEntity.add_entities (entity/batch.py:80-112) on the device: fill scene->union_x
+   [n_union_rows][6][M] from the replayed slots' own control points (traj_off / traj_rows) resampled,
+   clamped, at the union knot times union_t -- the rows packing.build_union_table computes on the host,
+   bit for bit (trajectories with finite values; the reference passes the data through
+   numpy.nan_to_num first).  All pointers device memory.  sg_rollout_host calls it when the host scene
+   carries union_t but no union_x: the table is 6 M times the size of its knot times and need not cross
+   PCIe. */
+int sg_build_union_x(const SgScene* scene, int device, void* stream);
 
 /* Measurement aid for the secondary roofline (bench.py): DFMA thread-instructions per second this
    GPU sustains at its current clocks (8 independent chains per thread, all SMs, best of 3 timed

@@ -1228,6 +1228,34 @@ int sgo_entities_in_radius(const SgState* st, int n_scenarios, int n_slots, cons
   }
   return 0;
 }
+/* BatchReplayEntity.add_entities, entity/batch.py:80-112: every replayed slot resampled (clamped)
+   at the scenario's union knot times; a single control point is duplicated 0.1 s later (:94-96) */
+int sgo_build_union_x(const SgScene* sc, int device, void* stream) {
+  (void)device; (void)stream;
+  int M = sc->n_slots;
+  double* X = (double*)sc->union_x;
+  for (int n = 0; n < sc->n_scenarios; ++n)
+    for (int64_t r = sc->union_off[n]; r < sc->union_off[n + 1]; ++r)
+      for (int s = 0; s < M; ++s) {
+        int64_t i = (int64_t)n * M + s;
+        double out[6] = {0, 0, 0, 0, 0, 0};
+        if (sc->kind[i] == SG_KIND_REPLAY) {
+          int64_t r0 = sc->traj_off[i], K = sc->traj_off[i + 1] - r0;
+          const double* rows = sc->traj_rows + r0 * 7;
+          double t = sc->union_t[r];
+          if (K == 1) {
+            double x_lo = rows[0], x_hi = x_lo + 1e-1;
+            int inside = !(t < x_lo) && !(t > x_hi);
+            double w1 = (t - x_lo) / (x_hi - x_lo), w0 = (x_hi - t) / (x_hi - x_lo);
+            for (int f = 0; f < 6; ++f) out[f] = inside ? w1 * rows[1 + f] + w0 * rows[1 + f] : rows[1 + f];
+          } else if (K > 1) {
+            position_at_t(rows, K, t, EXT_CLAMP, out);
+          }
+        }
+        for (int f = 0; f < 6; ++f) X[(r * 6 + f) * M + s] = out[f];
+      }
+  return 0;
+}
 int sgo_test_trajectory(const double* rows, int64_t K, const double* t, int64_t n, int mode, double* pos,
                         uint8_t* ok, double* vel, int device, void* stream) {
   (void)device; (void)stream;

@@ -209,6 +209,18 @@ int sg_entities_in_radius(const SgState* state, int n_scenarios, int n_slots, co
   return 0;
 }
 
+int sg_build_union_x(const SgScene* scene, int device, void* stream) {
+  if (!scene) return set_msg("null argument");
+  if (scene->n_union_rows <= 0) return 0;
+  if (!scene->union_off || !scene->union_t || !scene->union_x || !scene->traj_off || !scene->traj_rows || !scene->kind)
+    return set_msg("sg_build_union_x: the scene lacks union_off / union_t / union_x / trajectories");
+  cudaError_t err = cudaSetDevice(device);
+  if (err != cudaSuccess) return set_err("cudaSetDevice", err);
+  err = sgi_launch_union((cudaStream_t)stream, *scene);
+  if (err != cudaSuccess) return set_err("sg_union_kernel launch", err);
+  return 0;
+}
+
 int sg_test_trajectory(const double* rows, int64_t K, const double* t, int64_t n, int mode, double* pos,
                        uint8_t* ok, double* vel, int device, void* stream) {
   if (!rows || !t || !pos || !ok) return set_msg("null argument");
@@ -345,7 +357,12 @@ int sg_rollout_host(const SgScene* hs, const SgScene* ds, const SgParams* params
       if (err != cudaSuccess) return set_err("cudaMemcpyAsync H2D scene", err);
     }
   }
-  int rc = sg_reset(ds, params, dst, device, stream);
+  int rc = 0;
+  if (copy_static && !hs->union_x && hs->n_union_rows > 0) {  // knot times uploaded, rows built here
+    rc = sg_build_union_x(ds, device, stream);
+    if (rc) return rc;
+  }
+  rc = sg_reset(ds, params, dst, device, stream);
   if (rc) return rc;
   const int64_t NM = (int64_t)hs->n_scenarios * hs->n_slots;
   const bool table64 = hin && hin->actions, table32 = hin && !hin->actions && hin->actions_f32;

@@ -107,6 +107,55 @@ cudaError_t sgi_launch_radius(cudaStream_t s, const SgState& st, int n_scen, int
   return cudaGetLastError();
 }
 
+// BatchReplayEntity union-knot table on the device (sg_build_union_x; reference entity/batch.py:80-112):
+// one thread per (union row, slot).  Every replayed slot's trajectory is resampled, clamped, at the
+// scenario's union knot times with scipy's `_call_linear` arithmetic -- the device's position_at_t in
+// clamped mode; a single control point is duplicated 0.1 s later (batch.py:94-96).  The host uploads the
+// 8-byte knot times only, not the 48 M-byte rows.
+__global__ void sg_union_kernel(SgScene sc) {
+  const int M = sc.n_slots;
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= sc.n_union_rows * M) return;
+  const int64_t r = idx / M;
+  const int s = (int)(idx - r * M);
+  int lo = 0, hi = sc.n_scenarios;  // scenario of row r: union_off[n] <= r < union_off[n + 1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(sc.union_off + mid) <= r) lo = mid; else hi = mid;
+  }
+  const int64_t i = (int64_t)lo * M + s;
+  double out[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (sc.kind[i] == SG_KIND_REPLAY) {
+    const int64_t r0 = sc.traj_off[i];
+    const int K = (int)(sc.traj_off[i + 1] - r0);
+    const double* rows = sc.traj_rows + r0 * 7;
+    const double t = sc.union_t[r];
+    if (K == 1) {
+      const double x_lo = __ldg(rows), x_hi = x_lo + 1e-1;
+      const bool inside = !(t < x_lo) && !(t > x_hi);
+      const double w1 = (t - x_lo) / (x_hi - x_lo), w0 = (x_hi - t) / (x_hi - x_lo);
+#pragma unroll
+      for (int f = 0; f < 6; ++f) {
+        const double y = __ldg(rows + 1 + f);
+        out[f] = inside ? w1 * y + w0 * y : y;
+      }
+    } else if (K > 1) {
+      int cur = 0;
+      position_at_t(rows, K, t, EXT_CLAMP, cur, out);
+    }
+  }
+  double* X = (double*)sc.union_x + r * 6 * M + s;
+#pragma unroll
+  for (int f = 0; f < 6; ++f) X[(int64_t)f * M] = out[f];
+}
+
+cudaError_t sgi_launch_union(cudaStream_t s, const SgScene& sc) {
+  const int64_t n = sc.n_union_rows * sc.n_slots;
+  if (n <= 0) return cudaSuccess;
+  sg_union_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sc);
+  return cudaGetLastError();
+}
+
 // Trajectory.position_at_t / velocity_at_t truth tables (sg_test_trajectory): one thread per query time
 __global__ void sg_traj_kernel(const double* __restrict__ rows, int K, const double* __restrict__ t, int64_t n,
                                int mode, double* __restrict__ pos, uint8_t* __restrict__ ok, double* __restrict__ vel) {

@@ -221,7 +221,10 @@ SG_DEV void rp_ego_metrics(RpCarry* car, const double* spv, const double* cwv, i
 }
 
 template <bool MATRIX>  // MATRIX: also write the pair matrix of the final tick (SG_FEAT_COLL_MATRIX)
-__global__ void __launch_bounds__(SG_RP_BLOCK)
+#ifndef SG_RP_MINB
+#define SG_RP_MINB 4
+#endif
+__global__ void __launch_bounds__(SG_RP_BLOCK, SG_RP_MINB)
 sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgParams p,
                  const __grid_constant__ SgState st, int n_ticks) {
   extern __shared__ __align__(16) unsigned char smem[];

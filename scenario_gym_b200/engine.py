@@ -109,6 +109,14 @@ class Engine:
         self._check(self.lib["reset"](C.byref(self._sc), C.byref(self.params), C.byref(self._st),
                                       self.dev_index, self._stream()))
 
+    def build_union_on_device(self) -> torch.Tensor:
+        """
+        Recompute the resident BatchReplayEntity union table from the uploaded control points and knot
+        times (sg_build_union_x; entity/batch.py:80-112); returns the device tensor (rows, 6, M).
+        """
+        self._check(self.lib["build_union_x"](C.byref(self._sc), self.dev_index, self._stream()))
+        return self._scene_t["union_x"]
+
     def set_actions(self, actions) -> torch.Tensor:
         """Upload a (T, 2, N*M) VehicleAction table (accel, steer; fp64 or fp32) and keep it resident."""
         if isinstance(actions, np.ndarray):

@@ -29,16 +29,24 @@ RESULT_FIELDS = (
 class HostRollout:
     """Pinned host mirrors of an engine's scene + action source, and the result buffers."""
 
-    def __init__(self, engine: Engine, actions: Union[None, ActionRng, np.ndarray, torch.Tensor] = None):
+    def __init__(self, engine: Engine, actions: Union[None, ActionRng, np.ndarray, torch.Tensor] = None,
+                 device_union: bool = True):
         self.engine = eng = engine
         scene = eng.scene
         N = scene.N
-        self._host = {k: torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for k, a in scene.arrays().items()}
+        # The BatchReplayEntity union table is 6 M times the size of its knot times: with finite control
+        # points (the reference's nan_to_num is then the identity) only the knot times are uploaded and
+        # sg_rollout_host builds the rows on the device (sg_build_union_x), bit-identical to the host's.
+        self.device_union = bool(device_union and scene.union_t.size and np.isfinite(scene.traj_rows).all())
+        self._host = {k: torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for k, a in scene.arrays().items()
+                      if not (self.device_union and k == "union_x")}
         self._hs = abi.SgScene()
         for f, _ in abi.SgScene._fields_:
             setattr(self._hs, f, getattr(eng._sc, f))
         for k, t in self._host.items():
             setattr(self._hs, k, t.data_ptr() if t.numel() else None)
+        if self.device_union:
+            self._hs.union_x = None
         self._hin, self._din = abi.SgInputs(), abi.SgInputs()
         self.action_host: Optional[torch.Tensor] = None
         if isinstance(actions, ActionRng):

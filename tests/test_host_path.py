@@ -70,7 +70,48 @@ def test_host_path_without_actions():
     ref = Engine(scene, p, device=0)
     ref.reset()
     ref.rollout(-1)
-    eng = Engine(scene, p, device=0)
-    got = HostRollout(eng).run()
-    for k in FIELDS:
-        assert np.array_equal(got[k], ref.get(k), equal_nan=True), k
+    for device_union in (True, False):  # union table built on the device from the knot times / uploaded
+        eng = Engine(scene, p, device=0)
+        hr = HostRollout(eng, device_union=device_union)
+        assert hr.device_union == device_union
+        got = hr.run()
+        for k in FIELDS:
+            assert np.array_equal(got[k], ref.get(k), equal_nan=True), (device_union, k)
+    assert HostRollout(eng, device_union=True).h2d_bytes < HostRollout(eng, device_union=False).h2d_bytes
+
+
+def _union_scenes():
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import all_xosc_specs
+    from scenario_gym_b200.packing import ScenarioSpec, SlotSpec, pack_scenarios
+
+    scenes = [pack_scenarios([s for _, s, _, _ in all_xosc_specs("xosc")])]
+    # single control points (duplicated 0.1 s later by the reference), knots shared between entities,
+    # times before / after a trajectory's range
+    rng = np.random.default_rng(3)
+    specs = []
+    for n in range(7):
+        slots = []
+        for s in range(5):
+            K = [1, 2, 7, 30, 1][s] if n % 2 == 0 else int(rng.integers(1, 12))
+            t = np.sort(rng.uniform(-1.0, 9.0, K)) if s % 2 else np.arange(K) * 0.5 + 0.25 * s
+            tr = np.concatenate([t[:, None], rng.normal(0, 20, (K, 6))], axis=1)
+            slots.append(SlotSpec(kind=abi.KIND_AGENT_REPLAY if s == 0 else abi.KIND_REPLAY, traj=tr))
+        sp = ScenarioSpec(slots=slots)
+        sp.finalize()
+        specs.append(sp)
+    scenes.append(pack_scenarios(specs))
+    return scenes
+
+
+def test_union_table_built_on_device():
+    """sg_build_union_x == packing.build_union_table (entity/batch.py:80-112), bit for bit."""
+    from scenario_gym_b200.engine import Engine
+
+    for scene in _union_scenes():
+        eng = Engine(scene, abi.default_params(), device=0)
+        eng._scene_t["union_x"].fill_(-7.0)
+        got = eng.build_union_on_device().cpu().numpy()
+        assert got.shape == scene.union_x.shape and scene.union_x.size > 0
+        assert np.array_equal(got, scene.union_x)

@@ -255,3 +255,21 @@ def test_future_collision_detector_golden():
 
     hits = check_future_collisions(lambda scene, p: OracleEngine(scene, p), abi.default_params())
     assert hits > 50, "the golden set must contain future collisions"
+
+
+def test_union_table_oracle():
+    """The oracle's restatement of BatchReplayEntity.add_entities equals the host packer's table (numpy)."""
+    import ctypes as C
+
+    from oracle.runner import load_oracle, scene_struct
+    from scenario_gym_b200.packing import pack_scenarios
+
+    from helpers import all_xosc_specs
+
+    scene = pack_scenarios([s for _, s, _, _ in all_xosc_specs("xosc")])
+    want = scene.union_x.copy()
+    assert want.size > 0
+    scene.union_x[...] = -7.0
+    sc = scene_struct(scene)
+    assert load_oracle()["build_union_x"](C.byref(sc), 0, None) == 0
+    assert np.array_equal(scene.union_x, want)
