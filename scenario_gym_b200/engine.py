@@ -64,12 +64,19 @@ class Engine:
         self._sc.n_rn_edges = scene.rn_edges.shape[0]
         self._sc.kind_mask = scene.kind_mask()
         self._sc.scene_flags = scene.scene_flags()
-        for k, a in scene.arrays().items():
+        # a union table that was not built on the host is built here from the uploaded control points
+        device_union = not scene.union_ready and scene.union_on_device_ok()
+        for k, a in scene.arrays(union_rows=not device_union).items():
             t = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
             if t.numel() == 0:  # keep a valid pointer for empty tables
                 t = torch.zeros(8, dtype=t.dtype, device=self.device)
             self._scene_t[k] = t
             setattr(self._sc, k, t.data_ptr())
+        if device_union:
+            t = torch.empty((scene.union_t.shape[0], 6, scene.M), dtype=torch.float64, device=self.device)
+            self._scene_t["union_x"] = t
+            self._sc.union_x = t.data_ptr()
+            self.build_union_on_device()
 
         # --- state
         N, M, W = self.N, self.M, self.W

@@ -364,7 +364,7 @@ class ScenarioGym:
                     sl.veh_limits = None
         self._veh_params = next(iter(veh_params)) if len(veh_params) == 1 else None
         self._ped_params = next(iter(ped_params)) if ped_params else None
-        scene = pack_scenarios(specs)
+        scene = pack_scenarios(specs, union_rows=False)  # knot times only: the rows are built on the device
         N, M = scene.N, scene.M
         for n, st in enumerate(self.states):  # device rows behind agent.force / agent.goal_idx
             for e, a in st.agents.items():
@@ -623,10 +623,12 @@ class ScenarioGym:
         return out
 
     def _collision_events(self, n: int) -> list:
-        if "events" not in self._cache:
-            self._cache["events"] = self._engine.events()
-        ev = self._cache["events"]
-        ev = ev[ev["scenario"] == n]
+        if "events_by_scenario" not in self._cache:  # one pass over the batch's event list, kept in order
+            ev = self._engine.events()  # sorted by (scenario, tick, slot)
+            starts = np.searchsorted(ev["scenario"], np.arange(len(self.states) + 1))
+            self._cache["events_by_scenario"] = (ev, starts)
+        ev, starts = self._cache["events_by_scenario"]
+        ev = ev[starts[n]:starts[n + 1]]
         ents = self._entity_of[n]
         out = []
         for e in ev:

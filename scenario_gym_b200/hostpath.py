@@ -37,9 +37,9 @@ class HostRollout:
         # The BatchReplayEntity union table is 6 M times the size of its knot times: with finite control
         # points (the reference's nan_to_num is then the identity) only the knot times are uploaded and
         # sg_rollout_host builds the rows on the device (sg_build_union_x), bit-identical to the host's.
-        self.device_union = bool(device_union and scene.union_t.size and np.isfinite(scene.traj_rows).all())
-        self._host = {k: torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for k, a in scene.arrays().items()
-                      if not (self.device_union and k == "union_x")}
+        self.device_union = bool(device_union and scene.union_on_device_ok())
+        self._host = {k: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+                      for k, a in scene.arrays(union_rows=not self.device_union).items()}
         self._hs = abi.SgScene()
         for f, _ in abi.SgScene._fields_:
             setattr(self._hs, f, getattr(eng._sc, f))

@@ -40,19 +40,27 @@ def call_linear_clamped(x: np.ndarray, y: np.ndarray, x_new: np.ndarray) -> np.n
     return out
 
 
+def _batch_data(data: np.ndarray) -> np.ndarray:
+    """A trajectory as BatchReplayEntity.add_entities holds it (entity/batch.py:88-96)."""
+    d = np.nan_to_num(data)
+    if d.shape[0] == 1:
+        d = np.repeat(d, 2, axis=0)
+        d[-1, 0] += 1e-1
+    return d
+
+
+def build_union_times(trajs: Sequence[np.ndarray]) -> np.ndarray:
+    """The sorted union of all control-point times (entity/batch.py:98-99)."""
+    return np.array(sorted(set(t for data in trajs for t in _batch_data(data)[:, 0])))
+
+
 def build_union_table(trajs: Sequence[np.ndarray]):
     """
     Restates ``BatchReplayEntity.add_entities`` (entity/batch.py:80-112): every
     trajectory is resampled (clamped) at the sorted union of all control-point
     times.  Returns ``ts (Nk,)`` and ``X (Nk, n_ents, 6)``.
     """
-    datas = []
-    for data in trajs:
-        d = np.nan_to_num(data)
-        if d.shape[0] == 1:
-            d = np.repeat(d, 2, axis=0)
-            d[-1, 0] += 1e-1
-        datas.append(d)
+    datas = [_batch_data(data) for data in trajs]
     ts = np.array(sorted(set(t for d in datas for t in d[:, 0])))
     X = np.stack([call_linear_clamped(d[:, 0], d[:, 1:], ts) for d in datas], axis=1)
     return ts, X
@@ -109,7 +117,7 @@ class PackedScene:
     traj_rows: np.ndarray
     union_off: np.ndarray
     union_t: np.ndarray
-    union_x: np.ndarray
+    union_x: Optional[np.ndarray]  # (rows, 6, M); None: not built yet (on the device, or on first host access)
     t0: np.ndarray
     length: np.ndarray
     ego_slot: np.ndarray
@@ -142,9 +150,11 @@ class PackedScene:
     def W(self) -> int:
         return (self.M + 31) // 32
 
-    def arrays(self):
-        """Every SgScene array that is present (optional ones -- veh_limits -- are left out when None)."""
-        return {k: getattr(self, k) for k in abi.SCENE_FIELDS if getattr(self, k) is not None}
+    def arrays(self, union_rows: bool = True):
+        """Every SgScene array that is present (optional ones -- veh_limits -- are left out when None);
+        ``union_rows=False`` leaves the union table out (it is built on the device)."""
+        return {k: getattr(self, k) for k in abi.SCENE_FIELDS
+                if (union_rows or k != "union_x") and getattr(self, k) is not None}
 
     def kind_mask(self) -> int:
         """SgScene.kind_mask: OR of (1 << kind), or 0 when the vehicle fast path's promise
@@ -171,6 +181,46 @@ class PackedScene:
 
     def nbytes(self) -> int:
         return int(sum(a.nbytes for a in self.arrays().values()))
+
+    @property
+    def union_ready(self) -> bool:
+        """The union table exists on the host (False: knot times only)."""
+        return self._union_x is not None
+
+    def union_on_device_ok(self) -> bool:
+        """sg_build_union_x reproduces the host table: finite control points (nan_to_num is the identity)."""
+        return bool(self.union_t.size) and bool(np.isfinite(self.traj_rows).all())
+
+
+def _host_union_x(scene: "PackedScene") -> np.ndarray:
+    """The union table of a packed scene from its control points and knot times (host build)."""
+    M = scene.M
+    X = np.zeros((scene.union_t.shape[0], 6, M), np.float64)
+    for n in range(scene.N):
+        a, b = int(scene.union_off[n]), int(scene.union_off[n + 1])
+        if a == b:
+            continue
+        ts = scene.union_t[a:b]
+        for s in np.nonzero(scene.kind[n * M:(n + 1) * M] == abi.KIND_REPLAY)[0]:
+            i = n * M + int(s)
+            d = _batch_data(scene.traj_rows[scene.traj_off[i]:scene.traj_off[i + 1]])
+            X[a:b, :, s] = call_linear_clamped(d[:, 0], d[:, 1:], ts)
+    return X
+
+
+def _get_union_x(self):
+    if self._union_x is None:
+        self._union_x = _host_union_x(self)
+    return self._union_x
+
+
+def _set_union_x(self, value):
+    self._union_x = value
+
+
+# `union_x` may be left unbuilt (pack_scenarios(..., union_rows=False)): the engine then builds it on the
+# device (sg_build_union_x); host code that reads the attribute (the oracle, tests) gets it built here
+PackedScene.union_x = property(_get_union_x, _set_union_x)
 
 
 def pack_road_networks(networks: Sequence[Optional[object]]):
@@ -202,7 +252,8 @@ def pack_road_networks(networks: Sequence[Optional[object]]):
             np.array(has_area, np.uint8))
 
 
-def pack_scenarios(specs: Sequence[ScenarioSpec], n_slots: Optional[int] = None) -> PackedScene:
+def pack_scenarios(specs: Sequence[ScenarioSpec], n_slots: Optional[int] = None,
+                   union_rows: bool = True) -> PackedScene:
     """Pack scenario specs into one PackedScene (slots padded with EMPTY)."""
     N = len(specs)
     for s in specs:
@@ -254,7 +305,11 @@ def pack_scenarios(specs: Sequence[ScenarioSpec], n_slots: Optional[int] = None)
                     replay_idx.append(s)
             traj_off[i + 1] = nrow
             route_off[i + 1] = nroute
-        if replay_idx:
+        if replay_idx and not union_rows:  # knot times only: the rows are built on the device
+            ts = build_union_times([sp.slots[s].traj for s in replay_idx])
+            union_t.append(ts)
+            union_off[n + 1] = union_off[n] + len(ts)
+        elif replay_idx:
             ts, X = build_union_table([sp.slots[s].traj for s in replay_idx])
             full = np.zeros((len(ts), 6, M), np.float64)
             full[:, :, replay_idx] = np.transpose(X, (0, 2, 1))
@@ -273,7 +328,7 @@ def pack_scenarios(specs: Sequence[ScenarioSpec], n_slots: Optional[int] = None)
         traj_rows=np.concatenate(rows, axis=0) if rows else np.zeros((0, 7)),
         union_off=union_off,
         union_t=np.concatenate(union_t) if union_t else np.zeros(0),
-        union_x=np.concatenate(union_x, axis=0) if union_x else np.zeros((0, 6, M)),
+        union_x=None if (not union_rows and union_t) else (np.concatenate(union_x, axis=0) if union_x else np.zeros((0, 6, M))),
         t0=np.array([s.t0 for s in specs], np.float64),
         length=np.array([s.length for s in specs], np.float64),
         ego_slot=np.array([s.ego_slot for s in specs], np.int32),
@@ -310,7 +365,7 @@ def tile_scene(scene: PackedScene, reps: int) -> PackedScene:
     traj_off, traj_rows = csr(scene.traj_off, scene.traj_rows, M)
     route_off, route_xy = csr(scene.route_off, scene.route_xy, M)
     union_off, union_t = csr(scene.union_off, scene.union_t, 1)
-    _, union_x = csr(scene.union_off, scene.union_x, 1)
+    union_x = csr(scene.union_off, scene.union_x, 1)[1] if scene.union_ready else None
     return PackedScene(
         N=len(order),
         M=M,
@@ -353,7 +408,7 @@ def slice_scene(scene: PackedScene, lo: int, hi: int) -> PackedScene:
     traj_off, traj_rows = csr(scene.traj_off, scene.traj_rows, M)
     route_off, route_xy = csr(scene.route_off, scene.route_xy, M)
     union_off, union_t = csr(scene.union_off, scene.union_t, 1)
-    _, union_x = csr(scene.union_off, scene.union_x, 1)
+    union_x = csr(scene.union_off, scene.union_x, 1)[1] if scene.union_ready else None
     return PackedScene(
         N=n, M=M, kind=plane(scene.kind), etype=plane(scene.etype), box=plane(scene.box),
         traj_off=traj_off, traj_rows=traj_rows, union_off=union_off, union_t=union_t,
