@@ -33,7 +33,7 @@
 struct CrowdLayout {
   int G, W, QCAP;
   int off_state, off_fcs, off_pool, off_rad, off_nbl, off_gstart, off_gsorted, off_glarge, off_queue, off_flags,
-      off_ncnt, off_orient, off_hits, off_bits, off_acc, off_cold, off_gmisc, off_unif;
+      off_ncnt, off_orient, off_hits, off_bits, off_acc, off_cold, off_gmisc, off_unif, off_egoc, off_ring;
   int bytes;
 };
 
@@ -66,6 +66,8 @@ __host__ __device__ constexpr CrowdLayout crowd_layout(int ept, int threads) {
   L.off_cold = o;    o += COLD_ND * (int)sizeof(double) + COLD_NI * (int)sizeof(int);
   L.off_gmisc = o;   o += 48 * (int)sizeof(int);
   L.off_unif = o;    o += 8 * (int)sizeof(double);            // launch-uniform doubles (kept out of the registers)
+  L.off_egoc = o;    o += 12 * (int)sizeof(double);           // the ego's cached row (crowd_replay_cached)
+  L.off_ring = o;    o += 32 * 18 * (int)sizeof(double);      // the ego's next 32 steps (crowd_ego_ring)
   L.bytes = (o + 15) / 16 * 16;
   return L;
 }
@@ -92,6 +94,8 @@ struct Crowd {  // shared-memory views of one scenario
   int* cold_i;
   int* gmisc;
   double* unif;
+  double* egoc;
+  double* ring;
 };
 
 SG_DEV void crowd_views(Crowd& c, const CrowdLayout& L, unsigned char* base, int M) {
@@ -116,6 +120,8 @@ SG_DEV void crowd_views(Crowd& c, const CrowdLayout& L, unsigned char* base, int
   c.cold_i = (int*)(base + L.off_cold + COLD_ND * sizeof(double));
   c.gmisc = (int*)(base + L.off_gmisc);
   c.unif = (double*)(base + L.off_unif);
+  c.egoc = (double*)(base + L.off_egoc);
+  c.ring = (double*)(base + L.off_ring);
 }
 
 SG_DEV void cta_sync() { __syncthreads(); }
@@ -429,6 +435,72 @@ static __device__ __noinline__ CrowdReplayOut crowd_replay_step(const SgScene sc
   return o;
 }
 
+// The ego's ReplayTrajectoryAgent step with its State row cached on chip: x, y in the shared State rows,
+// heading / distance / control-point cursor in the owner's registers, z / p / r and the six velocities in
+// shared memory (`eg`); the row goes back to global memory once, after the last tick.  Same arithmetic as
+// crowd_replay_step; one lane of one warp runs it, so every L2 round trip it saves is taken off the tick's
+// critical path (the other warps wait for that warp at the barrier).
+enum { EG_Z = 0, EG_P, EG_R, EG_H, EG_V0, EG_N = EG_V0 + 6 };
+SG_DEV CrowdReplayOut crowd_replay_cached(const double* __restrict__ rows, int K, double* eg, bool present, double px,
+                                          double py, double& h, double& dist, int& cur, double t, double next_t) {
+  CrowdReplayOut o;
+  o.present = false;
+  o.x = px; o.y = py; o.h = h; o.vx = eg[EG_V0]; o.vy = eg[EG_V0 + 1]; o.speed3 = 0.0;
+  if (!present && !(K > 0 && __ldg(rows) >= t)) return o;  // scenario_gym.py:240-244
+  double np_[6], prev[6];
+  position_at_t(rows, K, next_t, EXT_CLAMP, cur, np_);  // agent.py:125-128
+  if (present) {
+    prev[0] = px; prev[1] = py; prev[2] = eg[EG_Z]; prev[3] = h; prev[4] = eg[EG_P]; prev[5] = eg[EG_R];
+  } else {  // state.py:219-222
+    int c2 = 0;
+    position_at_t(rows, K, t, EXT_TRUE, c2, prev);
+  }
+  const double dt = next_t - t;
+  double d[6], v[6];
+#pragma unroll
+  for (int f = 0; f < 6; ++f) { d[f] = np_[f] - prev[f]; v[f] = d[f] / dt; eg[EG_V0 + f] = v[f]; }
+  eg[EG_Z] = np_[2]; eg[EG_P] = np_[4]; eg[EG_R] = np_[5]; eg[EG_H] = np_[3];
+  dist += norm3(d[0], d[1], d[2]);
+  o.present = true;
+  o.x = np_[0]; o.y = np_[1]; o.h = np_[3]; o.vx = v[0]; o.vy = v[1];
+  o.speed3 = norm3(v[0], v[1], v[2]);
+  h = np_[3];
+  return o;
+}
+
+// The ego's next 32 steps at once: lane l of one warp evaluates the tick l + 1 ticks ahead -- the tick times
+// by the same repeated addition as the tick loop, the pose at each, and against the pose one lane below
+// (lane 0: the ego's current row, `pose`) the velocities, the distance increment, |v| and cos / sin of the
+// heading, exactly as crowd_replay_step computes them tick by tick.  The owner of the ego's row then only
+// copies an entry per tick: a replay step run by one lane of one warp kept the scenario's other 31 warps
+// waiting at the barrier for 8 % of the tick.  Valid while the ego stays present (it does, once it is).
+enum { ER_X = 0, ER_Y, ER_Z, ER_H, ER_P, ER_R, ER_V0, ER_SPEED3 = ER_V0 + 6, ER_INC, ER_CS, ER_SN, ER_CUR, ER_N = 18 };
+static __device__ __noinline__ void crowd_ego_ring(const double* __restrict__ rows, int K, const double* xy, int G, int ego,
+                                                   const double* eg, double t, double timestep, double* ring, int lane) {
+  double told = t;
+  for (int q = 0; q < lane; ++q) told = told + timestep;  // scenario_gym.py:229, tick by tick
+  const double tnew = told + timestep;
+  double np_[6], prev[6];
+  int cur = 0;
+  position_at_t(rows, K, tnew, EXT_CLAMP, cur, np_);  // agent.py:125-128
+#pragma unroll
+  for (int f = 0; f < 6; ++f) prev[f] = __shfl_up_sync(0xffffffffu, np_[f], 1);
+  if (lane == 0) {
+    prev[0] = xy[ego]; prev[1] = xy[G + ego]; prev[2] = eg[EG_Z]; prev[3] = eg[EG_H]; prev[4] = eg[EG_P]; prev[5] = eg[EG_R];
+  }
+  const double dt = tnew - told;
+  double* e = ring + lane * ER_N;
+  double d[6], v[6];
+#pragma unroll
+  for (int f = 0; f < 6; ++f) { d[f] = np_[f] - prev[f]; v[f] = d[f] / dt; e[ER_X + f] = np_[f]; e[ER_V0 + f] = v[f]; }
+  e[ER_INC] = norm3(d[0], d[1], d[2]);
+  e[ER_SPEED3] = norm3(v[0], v[1], v[2]);
+  double sn, cs;
+  sincos(np_[3], &sn, &cs);
+  e[ER_CS] = cs; e[ER_SN] = sn;
+  e[ER_CUR] = (double)cur;
+}
+
 // a pedestrian that is not in the scene yet is inserted at its first control point when its
 // trajectory starts at or after t (scenario_gym.py:240-244); returns false otherwise
 static __device__ __noinline__ bool crowd_ped_appears(const SgScene sc, int64_t i, double t, double next_t,
@@ -473,6 +545,7 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
   const int ego_slot = sc.ego_slot[n], first_slot = sc.first_slot[n];
   const bool need_coll = (p.features & SG_FEAT_COLLISIONS) || (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
   const bool matrix = (p.features & SG_FEAT_COLL_MATRIX) != 0;
+  const bool ego_cached = sc.kind[i0 + ego_slot] == SG_KIND_AGENT_REPLAY;  // its row lives on chip
   const double grid_cs = p.ped_distance_threshold * (1.0 + 1e-6);
   if (tid == 0) {  // launch-uniform doubles live in shared memory: 64 registers per thread are all there is
     double sh, ch;
@@ -485,6 +558,7 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
     c.unif[U_OY] = __ldg(sc.traj_rows + er * 7 + 2);
     c.unif[U_LEN] = sc.length[n];
     c.gmisc[0] = 0;  // entities too large for the grid (a property of the box: listed once, below)
+    c.gmisc[6] = -1; // chunk of 32 ticks the ego's ring holds (none)
   }
   __syncthreads();
 #define grid_inv_cs (c.unif[U_INV_CS])
@@ -532,6 +606,13 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
         if (s == ego_slot) {
           c.cold_d[CR_EGO_SPEED] = norm3(vx, vy, st.vel[2 * nm + i]);
           c.cold_d[CR_EGO_DIST] = me.dist;
+          if (me.kind == SG_KIND_AGENT_REPLAY) {  // its row stays on chip (crowd_replay_cached)
+            me.goal = st.cur_own[i];
+            c.egoc[EG_Z] = st.pose[2 * nm + i]; c.egoc[EG_P] = st.pose[4 * nm + i]; c.egoc[EG_R] = st.pose[5 * nm + i];
+            c.egoc[EG_H] = me.h;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) c.egoc[EG_V0 + f] = st.vel[f * nm + i];
+          }
         }
       }
     }
@@ -770,13 +851,34 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
           newpres = true;
         }
       } else if (me.kind == SG_KIND_AGENT_REPLAY) {
-        const CrowdReplayOut r = crowd_replay_step(sc, st, i, nm, present, t_old, t);
+        CrowdReplayOut r;
+        bool have_cs = false;
+        if (s == ego_slot && present && k > 0 && c.gmisc[6] == ((k - 1) >> 5)) {  // precomputed (crowd_ego_ring)
+          const double* e = c.ring + ((k - 1) & 31) * ER_N;
+          r.present = true;
+          r.x = e[ER_X]; r.y = e[ER_Y]; r.h = e[ER_H]; r.vx = e[ER_V0]; r.vy = e[ER_V0 + 1]; r.speed3 = e[ER_SPEED3];
+          me.dist += e[ER_INC];
+          me.goal = (int)e[ER_CUR];
+          me.bits |= 4u;
+          cs = e[ER_CS]; sn = e[ER_SN];
+          have_cs = true;
+          c.egoc[EG_Z] = e[ER_Z]; c.egoc[EG_P] = e[ER_P]; c.egoc[EG_R] = e[ER_R]; c.egoc[EG_H] = e[ER_H];
+#pragma unroll
+          for (int f = 0; f < 6; ++f) c.egoc[EG_V0 + f] = e[ER_V0 + f];
+        } else if (s == ego_slot) {  // cached rows: no round trips to global memory on the tick's critical path
+          const int64_t r0 = sc.traj_off[i];
+          r = crowd_replay_cached(sc.traj_rows + r0 * 7, (int)(sc.traj_off[i + 1] - r0), c.egoc, present, px, py, me.h,
+                                  me.dist, me.goal, t_old, t);
+          if (r.present) me.bits |= 4u;
+        } else {
+          r = crowd_replay_step(sc, st, i, nm, present, t_old, t);
+        }
         newpres = r.present;
         if (newpres) {
           nx = r.x; ny = r.y; nvx = r.vx; nvy = r.vy;
           me.h = r.h;
-          sincos(r.h, &sn, &cs);
-          if (s == ego_slot) { c.cold_d[CR_EGO_SPEED] = r.speed3; c.cold_d[CR_EGO_DIST] = st.dist[i]; }
+          if (!have_cs) sincos(r.h, &sn, &cs);
+          if (s == ego_slot) { c.cold_d[CR_EGO_SPEED] = r.speed3; c.cold_d[CR_EGO_DIST] = me.dist; }
         }
       }
       cn.state[s] = nx; cn.state[G + s] = ny; cn.state[2 * G + s] = nvx; cn.state[3 * G + s] = nvy;
@@ -798,6 +900,13 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
     sink.need_first = c.cold_i[COLD_FIRST_TICK] < 0;  // (written in the tick epilogue only, behind the barriers)
     const bool exhaustive = need_coll && c.gmisc[0] > SG_GRID_LCAP;  // too many large entities for the list
     int mypairs = 0;
+    if (ego_cached && (k & 31) == 0 && (tid >> 5) == ((k >> 5) & (CR_WARPS - 1)) && (cn.flags[ego_slot] & 1)) {
+      // one warp (a different one every time) lays out the ego's next 32 steps
+      const int64_t ie = i0 + ego_slot, r0 = sc.traj_off[ie];
+      crowd_ego_ring(sc.traj_rows + r0 * 7, (int)(sc.traj_off[ie + 1] - r0), cn.state, G, ego_slot, c.egoc, t, p.timestep,
+                     c.ring, lane);
+      if (lane == 0) c.gmisc[6] = k >> 5;
+    }
     {
       // ============ next tick's sensor candidates + broad phase; the warp then decides the pairs it queued =====
       const double r2s = rr_sensor * rr_sensor;
@@ -885,6 +994,14 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
     const int64_t i = i0 + s;
     st.present[i] = (flags[s] & 1) != 0;
     st.collided[i] = (uint8_t)((me.bits | (c.bits[s >> 5] >> (s & 31))) & 1u);  // before the launch or during it
+    if (me.kind == SG_KIND_AGENT_REPLAY && (me.bits & 4u)) {  // the ego's cached row
+      st.pose[i] = rows[s]; st.pose[nm + i] = rows[G + s]; st.pose[2 * nm + i] = c.egoc[EG_Z];
+      st.pose[3 * nm + i] = me.h; st.pose[4 * nm + i] = c.egoc[EG_P]; st.pose[5 * nm + i] = c.egoc[EG_R];
+#pragma unroll
+      for (int f = 0; f < 6; ++f) st.vel[f * nm + i] = c.egoc[EG_V0 + f];
+      st.dist[i] = me.dist;
+      st.cur_own[i] = me.goal;
+    }
     if (me.kind == SG_KIND_PEDESTRIAN) {
       st.pose[i] = rows[s]; st.pose[nm + i] = rows[G + s]; st.pose[3 * nm + i] = me.h;
       st.vel[i] = rows[2 * G + s]; st.vel[nm + i] = rows[3 * G + s];
