@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 11
+#define SG_ABI_VERSION 12
 
 /* entity slot kinds (who produces the slot's next pose each tick) */
 enum SgKind {
@@ -200,6 +200,17 @@ typedef struct SgScene {
      instance): [4][N*M] max_steer, max_accel, max_speed (NaN = None), allow_reverse (0 / 1); NULL: every
      vehicle / PID slot uses the SgParams values. */
   const double* veh_limits;
+  /* A window onto scenarios [scenario_base, scenario_base + n_scenarios) of a larger batch whose arrays
+     were laid out for plane_stride / n_slots scenarios: every pointer above (and in the SgState passed
+     with it) addresses the window's first element, planes of [k][N*M] arrays stay plane_stride elements
+     apart, and slot / scenario numbers that mean something outside the arrays (the action stream's
+     draw index, the noise stream, SgEvent.scenario) are counted from the start of the batch.
+     plane_stride = 0: the whole batch (plane_stride = N*M, scenario_base = 0).  sg_rollout_host uses
+     windows to overlap the upload of one part of a batch with the rollout of another; traces
+     (trace_cap > 0) are not supported on a window. */
+  int64_t plane_stride;
+  int32_t scenario_base;
+  int32_t _pad2;
 } SgScene;
 
 /* one recorded ego-collision rising edge (metrics/collision.py:70-75) */

@@ -11,7 +11,7 @@ import math
 import os
 from typing import Dict, Optional
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 # SgKind
 KIND_EMPTY, KIND_REPLAY, KIND_AGENT_REPLAY, KIND_VEHICLE, KIND_PEDESTRIAN, KIND_HOST, KIND_PID = range(7)
@@ -116,6 +116,9 @@ class SgScene(C.Structure):
         ("rn_edges", _p),
         ("rn_has_area", _p),
         ("veh_limits", _p),
+        ("plane_stride", C.c_int64),   # scenario windows (sg_b200.h): 0 = the whole batch
+        ("scenario_base", C.c_int32),
+        ("_pad2", C.c_int32),
     ]
 
 

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "sg_internal.h"
@@ -47,6 +48,16 @@ static int launch(const SgScene* sc, const SgParams* p, SgState* st, const SgInp
   if (!sc || !p || !st) return set_msg("null argument");
   if (sc->n_slots < 1 || sc->n_slots > 1024) return set_msg("n_slots must be in 1..1024");
   if (sc->n_scenarios < 1) return set_msg("n_scenarios must be >= 1");
+  SgScene view = *sc;  // (what the kernels get: the plane stride is always stated)
+  if (view.plane_stride <= 0) {
+    view.plane_stride = (int64_t)sc->n_scenarios * sc->n_slots;
+    view.scenario_base = 0;
+  } else {
+    if (view.plane_stride < (int64_t)sc->n_scenarios * sc->n_slots || view.scenario_base < 0)
+      return set_msg("scenario window: plane_stride smaller than the window / negative scenario_base");
+    if (st->trace_cap > 0) return set_msg("traces are not supported on a scenario window");
+  }
+  sc = &view;
   cudaError_t err = cudaSetDevice(device);
   if (err != cudaSuccess) return set_err("cudaSetDevice", err);
   const bool ped = sc->route_off != nullptr && sc->n_route_pts > 0;
@@ -216,7 +227,7 @@ int sg_build_union_x(const SgScene* scene, int device, void* stream) {
     return set_msg("sg_build_union_x: the scene lacks union_off / union_t / union_x / trajectories");
   cudaError_t err = cudaSetDevice(device);
   if (err != cudaSuccess) return set_err("cudaSetDevice", err);
-  err = sgi_launch_union((cudaStream_t)stream, *scene);
+  err = sgi_launch_union((cudaStream_t)stream, *scene, scene->n_union_rows);
   if (err != cudaSuccess) return set_err("sg_union_kernel launch", err);
   return 0;
 }
@@ -257,53 +268,108 @@ int sg_future_collisions(const SgScene* scene, const double* t, const int32_t* s
   if (n_samples < 1) return set_msg("n_samples must be >= 1");
   cudaError_t err = cudaSetDevice(device);
   if (err != cudaSuccess) return set_err("cudaSetDevice", err);
-  err = sgi_launch_future((cudaStream_t)stream, *scene, t, slot, horizon, n_samples, out);
+  SgScene view = *scene;
+  if (view.plane_stride <= 0) view.plane_stride = (int64_t)scene->n_scenarios * scene->n_slots;
+  err = sgi_launch_future((cudaStream_t)stream, view, t, slot, horizon, n_samples, out);
   if (err != cudaSuccess) return set_err("sg_future_kernel launch", err);
   return 0;
 }
 
 // ---- host-buffer path ------------------------------------------------------------------
-struct CopyItem { const void* src; void* dst; size_t bytes; };
+// scenarios [n0, n1) of a scene laid out for the whole batch (SgScene.plane_stride / scenario_base)
+static SgScene scene_window(const SgScene& s, int n0, int n1) {
+  SgScene w = s;
+  const int64_t M = s.n_slots, off = (int64_t)n0 * M;
+  w.n_scenarios = n1 - n0;
+  w.plane_stride = s.plane_stride > 0 ? s.plane_stride : (int64_t)s.n_scenarios * M;
+  w.scenario_base = (s.plane_stride > 0 ? s.scenario_base : 0) + n0;
+#define OFF(f, k) if (w.f) w.f += (k)
+  OFF(kind, off); OFF(etype, off); OFF(box, off); OFF(traj_off, off); OFF(union_off, n0);
+  OFF(t0, n0); OFF(length, n0); OFF(ego_slot, n0); OFF(first_slot, n0);
+  OFF(ped_speed_desired, off); OFF(route_off, off); OFF(rn_of, n0); OFF(veh_limits, off);
+#undef OFF
+  return w;
+}
+static SgState state_window(const SgState& s, const SgParams& p, int n0, int M) {
+  SgState w = s;
+  const int64_t off = (int64_t)n0 * M, W = (M + 31) / 32;
+#define OFF(f, k) if (w.f) w.f += (k)
+  OFF(pose, off); OFF(vel, off); OFF(dist, off); OFF(present, off); OFF(speed, off); OFF(goal_idx, off);
+  OFF(force, off); OFF(cur_own, off); OFF(collided, off); OFF(rss_state, off); OFF(rss_last, off);
+  OFF(safe_dist, off); OFF(safe_ratio, off); OFF(pid_err, off);
+  OFF(t, n0); OFF(prev_t, n0); OFF(tick, n0); OFF(done, n0); OFF(cur_union, n0);
+  OFF(ego_avg_speed, n0); OFF(ego_avg_t, n0); OFF(ego_max_speed, n0); OFF(ego_dist, n0);
+  OFF(first_coll_tick, n0); OFF(n_pair_ticks, n0); OFF(rss_flags, n0);
+  OFF(ego_hits, (int64_t)n0 * W); OFF(first_coll_pair, 2 * (int64_t)n0);
+  if (p.features & SG_FEAT_COLL_MATRIX) OFF(coll_mask, (int64_t)n0 * M * W);
+#undef OFF
+  return w;
+}
 
-static int scene_copy_list(const SgScene* h, const SgScene* d, CopyItem* items) {
-  const int64_t N = h->n_scenarios, M = h->n_slots, NM = N * M;
-  int k = 0;
-#define ITEM(field, bytes_) items[k++] = CopyItem{h->field, (void*)d->field, (size_t)(bytes_)}
-  ITEM(kind, NM);
-  ITEM(etype, NM);
-  ITEM(box, 4 * NM * 8);
-  ITEM(traj_off, (NM + 1) * 8);
-  ITEM(traj_rows, h->n_traj_rows * 7 * 8);
-  ITEM(union_off, (N + 1) * 8);
-  ITEM(union_t, h->n_union_rows * 8);
-  ITEM(union_x, h->n_union_rows * 6 * M * 8);
-  ITEM(t0, N * 8);
-  ITEM(length, N * 8);
-  ITEM(ego_slot, N * 4);
-  ITEM(first_slot, N * 4);
-  ITEM(ped_speed_desired, NM * 8);
-  ITEM(route_off, (NM + 1) * 8);
-  ITEM(route_xy, h->n_route_pts * 2 * 8);
-  ITEM(veh_limits, 4 * NM * 8);
-  if (h->n_networks > 0) {
-    ITEM(rn_of, N * 4);
-    ITEM(rn_poly_off, (3 * (int64_t)h->n_networks + 1) * 8);
-    ITEM(rn_edge_off, (h->n_rn_polys + 1) * 8);
-    ITEM(rn_edges, h->n_rn_edges * 4 * 8);
-    ITEM(rn_has_area, 3 * (int64_t)h->n_networks);
+// Host -> device copies of scenarios [n0, n1) of a scene (`shared`: also the arrays all scenarios share,
+// the road networks).  With `do_copy` false only the bytes are counted.  Returns 0 or an error code.
+static int copy_scene_window(const SgScene* h, const SgScene* d, int n0, int n1, bool shared, bool do_copy,
+                             cudaStream_t s, int64_t* bytes) {
+  const int64_t N = h->n_scenarios, M = h->n_slots, NM = N * M, o = (int64_t)n0 * M, cnt = (int64_t)(n1 - n0) * M;
+  const int ns = n1 - n0;
+  int64_t total = 0;
+  cudaError_t err = cudaSuccess;
+  auto flat = [&](const void* src, const void* dst, int64_t first, int64_t n, int64_t esz) -> bool {
+    if (!src || n <= 0) return true;
+    total += n * esz;
+    if (!do_copy) return true;
+    if (!dst) { set_msg("device scene mirror is missing an array"); return false; }
+    err = cudaMemcpyAsync((char*)dst + first * esz, (const char*)src + first * esz, (size_t)(n * esz),
+                          cudaMemcpyHostToDevice, s);
+    if (err != cudaSuccess) { set_err("cudaMemcpyAsync H2D scene", err); return false; }
+    return true;
+  };
+  auto planes = [&](const void* src, const void* dst, int np, int64_t esz) -> bool {  // [np][N*M]
+    if (!src || cnt <= 0) return true;
+    total += (int64_t)np * cnt * esz;
+    if (!do_copy) return true;
+    if (!dst) { set_msg("device scene mirror is missing an array"); return false; }
+    err = cudaMemcpy2DAsync((char*)dst + o * esz, (size_t)(NM * esz), (const char*)src + o * esz, (size_t)(NM * esz),
+                            (size_t)(cnt * esz), (size_t)np, cudaMemcpyHostToDevice, s);
+    if (err != cudaSuccess) { set_err("cudaMemcpy2DAsync H2D scene", err); return false; }
+    return true;
+  };
+  bool ok = planes(h->kind, d->kind, 1, 1) && planes(h->etype, d->etype, 1, 1) && planes(h->box, d->box, 4, 8) &&
+            flat(h->traj_off, d->traj_off, o, cnt + 1, 8) && planes(h->veh_limits, d->veh_limits, 4, 8) &&
+            flat(h->union_off, d->union_off, n0, ns + 1, 8) && flat(h->t0, d->t0, n0, ns, 8) &&
+            flat(h->length, d->length, n0, ns, 8) && flat(h->ego_slot, d->ego_slot, n0, ns, 4) &&
+            flat(h->first_slot, d->first_slot, n0, ns, 4);
+  if (ok && h->traj_off && h->traj_rows) {
+    const int64_t r0 = h->traj_off[o], r1 = h->traj_off[o + cnt];
+    ok = flat(h->traj_rows, d->traj_rows, r0 * 7, (r1 - r0) * 7, 8);
   }
-#undef ITEM
-  return k;
+  if (ok && h->union_off && h->n_union_rows > 0) {
+    const int64_t u0 = h->union_off[n0], u1 = h->union_off[n1];
+    ok = flat(h->union_t, d->union_t, u0, u1 - u0, 8) && flat(h->union_x, d->union_x, u0 * 6 * M, (u1 - u0) * 6 * M, 8);
+  }
+  // (kind_mask: OR of 1 << kind over the slots, 0 = not stated) pedestrian rows are only read for pedestrians
+  if (ok && (h->kind_mask == 0 || (h->kind_mask & (1u << SG_KIND_PEDESTRIAN)))) {
+    ok = planes(h->ped_speed_desired, d->ped_speed_desired, 1, 8) && flat(h->route_off, d->route_off, o, cnt + 1, 8);
+    if (ok && h->route_off && h->route_xy) {
+      const int64_t r0 = h->route_off[o], r1 = h->route_off[o + cnt];
+      ok = flat(h->route_xy, d->route_xy, r0 * 2, (r1 - r0) * 2, 8);
+    }
+  }
+  if (ok && h->n_networks > 0) {
+    ok = flat(h->rn_of, d->rn_of, n0, ns, 4);
+    if (ok && shared)
+      ok = flat(h->rn_poly_off, d->rn_poly_off, 0, 3 * (int64_t)h->n_networks + 1, 8) &&
+           flat(h->rn_edge_off, d->rn_edge_off, 0, h->n_rn_polys + 1, 8) &&
+           flat(h->rn_edges, d->rn_edges, 0, h->n_rn_edges * 4, 8) &&
+           flat(h->rn_has_area, d->rn_has_area, 0, 3 * (int64_t)h->n_networks, 1);
+  }
+  if (bytes) *bytes = total;
+  return ok ? 0 : (err != cudaSuccess ? -2 : -1);
 }
 
 int64_t sg_host_h2d_bytes(const SgScene* h, const SgInputs* in, int copy_static) {
-  CopyItem items[24];
-  SgScene dummy = *h;
-  int k = scene_copy_list(h, &dummy, items);
   int64_t total = 0;
-  if (copy_static)
-    for (int q = 0; q < k; ++q)
-      if (items[q].src) total += (int64_t)items[q].bytes;
+  if (copy_static) copy_scene_window(h, h, 0, h->n_scenarios, true, false, nullptr, &total);
   const int64_t nm = (int64_t)h->n_scenarios * h->n_slots;
   if (in && in->actions) total += (int64_t)in->n_action_ticks * 2 * nm * 8;
   else if (in && in->actions_f32) total += (int64_t)in->n_action_ticks * 2 * nm * 4;
@@ -315,10 +381,11 @@ int64_t sg_host_d2h_bytes(const SgScene* h) {
   return N * (8 * 3 + 4 + 8 + 8 + 1 + 4 + 8) + 4;
 }
 
-// copy stream + events of the host-buffer path, one set per device (created on first use)
+// streams + events of the host-buffer path, one set per device (created on first use)
+#define SG_HOST_MAX_WINDOWS 4
 struct HostPathCtx {
-  cudaStream_t copy_stream;
-  cudaEvent_t ev_copy[2], ev_done;
+  cudaStream_t copy_stream, aux_stream;
+  cudaEvent_t ev_copy[2], ev_done, ev_win[SG_HOST_MAX_WINDOWS], ev_aux;
   bool ready;
 };
 static HostPathCtx g_host_ctx[64];
@@ -329,8 +396,11 @@ static int host_ctx(int device, HostPathCtx** out) {
   if (!c.ready) {  // (the caller has made `device` current)
     cudaError_t err = cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking);
     if (err != cudaSuccess) return set_err("cudaStreamCreateWithFlags", err);
-    cudaEvent_t* evs[3] = {&c.ev_copy[0], &c.ev_copy[1], &c.ev_done};
-    for (int q = 0; q < 3; ++q) {
+    err = cudaStreamCreateWithFlags(&c.aux_stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) return set_err("cudaStreamCreateWithFlags", err);
+    cudaEvent_t* evs[4 + SG_HOST_MAX_WINDOWS] = {&c.ev_copy[0], &c.ev_copy[1], &c.ev_done, &c.ev_aux};
+    for (int q = 0; q < SG_HOST_MAX_WINDOWS; ++q) evs[4 + q] = &c.ev_win[q];
+    for (int q = 0; q < 4 + SG_HOST_MAX_WINDOWS; ++q) {
       err = cudaEventCreateWithFlags(evs[q], cudaEventDisableTiming);
       if (err != cudaSuccess) return set_err("cudaEventCreateWithFlags", err);
     }
@@ -340,6 +410,17 @@ static int host_ctx(int device, HostPathCtx** out) {
   return 0;
 }
 
+// How many windows a batch without an action table is uploaded and rolled out in: the first one small,
+// so the rollout starts early, the upload of every later window hidden behind the rollout of the one
+// before.  SG_HOST_WINDOWS=<n> (1 .. 4) overrides the choice (1: one upload, then one rollout).
+static int host_windows(const SgScene* hs, int64_t scene_bytes) {
+  const char* env = getenv("SG_HOST_WINDOWS");
+  int n = (scene_bytes >= (8 << 20) && hs->n_scenarios >= 64) ? 3 : 1;
+  if (env && env[0] >= '1' && env[0] <= '0' + SG_HOST_MAX_WINDOWS && !env[1]) n = env[0] - '0';
+  if (n > hs->n_scenarios) n = hs->n_scenarios;
+  return n < 1 ? 1 : n;
+}
+
 int sg_rollout_host(const SgScene* hs, const SgScene* ds, const SgParams* params, SgState* dst,
                     const SgInputs* hin, const SgInputs* din, SgHostResults* res, int copy_static,
                     int device, void* stream) {
@@ -347,61 +428,101 @@ int sg_rollout_host(const SgScene* hs, const SgScene* ds, const SgParams* params
   cudaError_t err = cudaSetDevice(device);
   if (err != cudaSuccess) return set_err("cudaSetDevice", err);
   cudaStream_t s = (cudaStream_t)stream;
-  if (copy_static) {
-    CopyItem items[24];
-    const int k = scene_copy_list(hs, ds, items);
-    for (int q = 0; q < k; ++q) {
-      if (!items[q].src || !items[q].bytes) continue;
-      if (!items[q].dst) return set_msg("device scene mirror is missing an array");
-      err = cudaMemcpyAsync(items[q].dst, items[q].src, items[q].bytes, cudaMemcpyHostToDevice, s);
-      if (err != cudaSuccess) return set_err("cudaMemcpyAsync H2D scene", err);
-    }
-  }
-  int rc = 0;
-  if (copy_static && !hs->union_x && hs->n_union_rows > 0) {  // knot times uploaded, rows built here
-    rc = sg_build_union_x(ds, device, stream);
-    if (rc) return rc;
-  }
-  rc = sg_reset(ds, params, dst, device, stream);
-  if (rc) return rc;
-  const int64_t NM = (int64_t)hs->n_scenarios * hs->n_slots;
+  const int64_t N = hs->n_scenarios, NM = N * hs->n_slots;
   const bool table64 = hin && hin->actions, table32 = hin && !hin->actions && hin->actions_f32;
-  if (table64 || table32) {
-    if (!din || (table64 ? !din->actions : !din->actions_f32)) return set_msg("device action buffer missing");
-    // stream the action table in chunks of ticks: the copy of chunk c+1 overlaps the kernel
-    // of chunk c (copies on a second stream, ordered with events)
-    const int T = hin->n_action_ticks;
-    const int chunk = T < 16 ? T : 16;
-    const size_t esz = table64 ? 8 : 4;
+  const bool build_union = copy_static && !hs->union_x && hs->n_union_rows > 0;  // knot times uploaded, rows built here
+  int rc = 0;
+#define SG_CK(call, what) do { err = (call); if (err != cudaSuccess) return set_err(what, err); } while (0)
+  int64_t scene_bytes = 0;
+  copy_scene_window(hs, ds, 0, (int)N, true, false, nullptr, &scene_bytes);
+  const int nwin = (copy_static && !table64 && !table32 && dst->trace_cap <= 0 && hs->plane_stride <= 0)
+                       ? host_windows(hs, scene_bytes) : 1;
+  if (nwin > 1) {
+    // Scenarios are independent: the batch goes up in windows on a copy stream, and every window is
+    // reset and rolled out (alternating between two compute streams, so one window's last CTAs overlap
+    // the next one's first) as soon as it has arrived.
     HostPathCtx* ctx = nullptr;
     rc = host_ctx(device, &ctx);
     if (rc) return rc;
-#define SG_CK(call, what) do { err = (call); if (err != cudaSuccess) return set_err(what, err); } while (0)
+    if (dst->event_count) SG_CK(cudaMemsetAsync(dst->event_count, 0, sizeof(int32_t), s), "cudaMemsetAsync");
     SG_CK(cudaEventRecord(ctx->ev_done, s), "cudaEventRecord");
     SG_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0), "cudaStreamWaitEvent");
-    int c = 0;
-    for (int k0 = 0; k0 < T; k0 += chunk, ++c) {
-      const int kt = (T - k0) < chunk ? (T - k0) : chunk;
-      const size_t off = (size_t)k0 * 2 * NM;
-      const char* src = table64 ? (const char*)hin->actions : (const char*)hin->actions_f32;
-      char* dstp = table64 ? (char*)din->actions : (char*)din->actions_f32;
-      SG_CK(cudaMemcpyAsync(dstp + off * esz, src + off * esz, (size_t)kt * 2 * NM * esz,
-                            cudaMemcpyHostToDevice, ctx->copy_stream), "cudaMemcpyAsync H2D actions");
-      SG_CK(cudaEventRecord(ctx->ev_copy[c & 1], ctx->copy_stream), "cudaEventRecord");
-      SG_CK(cudaStreamWaitEvent(s, ctx->ev_copy[c & 1], 0), "cudaStreamWaitEvent");
-      SgInputs part = *din;
-      if (table64) { part.actions = din->actions + off; part.actions_f32 = nullptr; }
-      else { part.actions = nullptr; part.actions_f32 = din->actions_f32 + off; }
-      part.n_action_ticks = kt;
-      rc = sg_rollout(ds, params, dst, &part, kt, device, stream);
+    SG_CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_done, 0), "cudaStreamWaitEvent");
+    int bounds[SG_HOST_MAX_WINDOWS + 1];
+    bounds[0] = 0;
+    for (int w = 1; w <= nwin; ++w)  // windows end at 1/8, 1/2, 1 of the batch (three windows): each four times the last
+      bounds[w] = w == nwin ? (int)N : (int)(N >> (2 * (nwin - w) - 1));
+    bool used_aux = false;
+    for (int w = 0; w < nwin; ++w) {
+      const int n0 = bounds[w], n1 = bounds[w + 1];
+      if (n1 <= n0) continue;
+      rc = copy_scene_window(hs, ds, n0, n1, w == 0, true, ctx->copy_stream, nullptr);
+      if (rc) return rc;
+      SG_CK(cudaEventRecord(ctx->ev_win[w], ctx->copy_stream), "cudaEventRecord");
+      cudaStream_t cs = (w & 1) ? ctx->aux_stream : s;
+      used_aux = used_aux || (w & 1);
+      SG_CK(cudaStreamWaitEvent(cs, ctx->ev_win[w], 0), "cudaStreamWaitEvent");
+      const SgScene sw = scene_window(*ds, n0, n1);
+      SgState stw = state_window(*dst, *params, n0, hs->n_slots);
+      if (build_union) {
+        err = sgi_launch_union(cs, sw, hs->union_off[n1] - hs->union_off[n0]);
+        if (err != cudaSuccess) return set_err("sg_union_kernel launch", err);
+      }
+      rc = launch(&sw, params, &stw, nullptr, 0, device, (void*)cs, 1);
+      if (rc) return rc;
+      rc = launch(&sw, params, &stw, hin && hin->use_rng ? hin : din, -1, device, (void*)cs, 0);
       if (rc) return rc;
     }
-#undef SG_CK
-  } else {  // no table to move (replay / pedestrians / device-side action source): one fused rollout
-    rc = sg_rollout(ds, params, dst, hin && hin->use_rng ? hin : din, -1, device, stream);
+    if (used_aux) {
+      SG_CK(cudaEventRecord(ctx->ev_aux, ctx->aux_stream), "cudaEventRecord");
+      SG_CK(cudaStreamWaitEvent(s, ctx->ev_aux, 0), "cudaStreamWaitEvent");
+    }
+  } else {
+    if (copy_static) {
+      rc = copy_scene_window(hs, ds, 0, (int)N, true, true, s, nullptr);
+      if (rc) return rc;
+    }
+    if (build_union) {
+      rc = sg_build_union_x(ds, device, stream);
+      if (rc) return rc;
+    }
+    rc = sg_reset(ds, params, dst, device, stream);
     if (rc) return rc;
+    if (table64 || table32) {
+      if (!din || (table64 ? !din->actions : !din->actions_f32)) return set_msg("device action buffer missing");
+      // stream the action table in chunks of ticks: the copy of chunk c+1 overlaps the kernel
+      // of chunk c (copies on a second stream, ordered with events)
+      const int T = hin->n_action_ticks;
+      const int chunk = T < 16 ? T : 16;
+      const size_t esz = table64 ? 8 : 4;
+      HostPathCtx* ctx = nullptr;
+      rc = host_ctx(device, &ctx);
+      if (rc) return rc;
+      SG_CK(cudaEventRecord(ctx->ev_done, s), "cudaEventRecord");
+      SG_CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0), "cudaStreamWaitEvent");
+      int c = 0;
+      for (int k0 = 0; k0 < T; k0 += chunk, ++c) {
+        const int kt = (T - k0) < chunk ? (T - k0) : chunk;
+        const size_t off = (size_t)k0 * 2 * NM;
+        const char* src = table64 ? (const char*)hin->actions : (const char*)hin->actions_f32;
+        char* dstp = table64 ? (char*)din->actions : (char*)din->actions_f32;
+        SG_CK(cudaMemcpyAsync(dstp + off * esz, src + off * esz, (size_t)kt * 2 * NM * esz,
+                              cudaMemcpyHostToDevice, ctx->copy_stream), "cudaMemcpyAsync H2D actions");
+        SG_CK(cudaEventRecord(ctx->ev_copy[c & 1], ctx->copy_stream), "cudaEventRecord");
+        SG_CK(cudaStreamWaitEvent(s, ctx->ev_copy[c & 1], 0), "cudaStreamWaitEvent");
+        SgInputs part = *din;
+        if (table64) { part.actions = din->actions + off; part.actions_f32 = nullptr; }
+        else { part.actions = nullptr; part.actions_f32 = din->actions_f32 + off; }
+        part.n_action_ticks = kt;
+        rc = sg_rollout(ds, params, dst, &part, kt, device, stream);
+        if (rc) return rc;
+      }
+    } else {  // no table to move (replay / pedestrians / device-side action source): one fused rollout
+      rc = sg_rollout(ds, params, dst, hin && hin->use_rng ? hin : din, -1, device, stream);
+      if (rc) return rc;
+    }
   }
-  const int64_t N = hs->n_scenarios;
+#undef SG_CK
 #define BACK(field, bytes_)                                                                   \
   if (res->field) {                                                                           \
     err = cudaMemcpyAsync(res->field, dst->field, (size_t)(bytes_), cudaMemcpyDeviceToHost, s); \

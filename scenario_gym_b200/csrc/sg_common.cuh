@@ -88,7 +88,7 @@ SG_DEV void setup_group(Grp& g, const SgScene& sc, const GroupLayout& L, unsigne
   g.bar_id = 1 + gl;
   g.mask = 0xffffffffu;
   if (L.G < 32) g.mask = ((1u << L.G) - 1u) << ((threadIdx.x & 31) / L.G * L.G);
-  g.nm = (int64_t)sc.n_scenarios * sc.n_slots;
+  g.nm = sc.plane_stride;  // (sg_api.cu fills it in for whole batches)
   g.i = (int64_t)n * sc.n_slots + s;
   g.corners = (double*)base;
   g.actbuf = (double*)(base + L.off_act);
@@ -652,7 +652,7 @@ SG_DEV void pedestrian_step(const SgScene& sc, const SgParams& p, const Grp& c, 
   if (walking) {
     double speed_rand = p.sf_bias_lon, heading_rand = p.sf_bias_lat;  // np.random.normal(bias, 0) == bias
     if (p.sf_std_lon != 0.0 || p.sf_std_lat != 0.0) {
-      const double2 z = sg_noise2(p.sf_noise_seed, c.i, tick);
+      const double2 z = sg_noise2(p.sf_noise_seed, c.i + (int64_t)sc.scenario_base * sc.n_slots, tick);
       speed_rand = p.sf_bias_lon + p.sf_std_lon * z.x;
       heading_rand = p.sf_bias_lat + p.sf_std_lat * z.y;
     }
@@ -1327,7 +1327,8 @@ static __device__ __noinline__ void emit_events(SgEvent* events, int32_t* event_
   }
 }
 
-// phases B2 + C, shared by both kernel flavours.  Returns state.is_done.
+// phases B2 + C, shared by both kernel flavours.  Returns state.is_done.  (`n`: the scenario's number in
+// the whole batch, for the event records; the arrays are addressed through the group descriptor)
 template <bool FAST>
 SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int n, int s, int W,
                         int G, int ego_slot, int first_slot, int parity, int tick, double t,

@@ -541,7 +541,7 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
   crowd_views(c, L, smem, M);
   Grp g;  // the view neighbour_force reads: old x, y, vx, vy of every slot
   g.pedbuf = c.state; g.G = G;
-  const int64_t nm = (int64_t)sc.n_scenarios * M, i0 = (int64_t)n * M;
+  const int64_t nm = sc.plane_stride, i0 = (int64_t)n * M;
   const int ego_slot = sc.ego_slot[n], first_slot = sc.first_slot[n];
   const bool need_coll = (p.features & SG_FEAT_COLLISIONS) || (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
   const bool matrix = (p.features & SG_FEAT_COLL_MATRIX) != 0;
@@ -800,7 +800,7 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
           if (walking) {
             double speed_rand = p.sf_bias_lon, heading_rand = p.sf_bias_lat;
             if (p.sf_std_lon != 0.0 || p.sf_std_lat != 0.0) {  // engine-defined noise stream (sg_device.cuh)
-              const double2 z = sg_noise2(p.sf_noise_seed, i, tick - 1);
+              const double2 z = sg_noise2(p.sf_noise_seed, i + (int64_t)sc.scenario_base * M, tick - 1);
               speed_rand = p.sf_bias_lon + p.sf_std_lon * z.x;
               heading_rand = p.sf_bias_lat + p.sf_std_lat * z.y;
             }
@@ -961,7 +961,7 @@ sg_crowd_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks) {
       const uint32_t now = c.ego_now[w];
       if (p.features & SG_FEAT_COLLISIONS) {
         const uint32_t fresh = now & ~c.ego_last[w];
-        if (fresh) emit_events(st.events, st.event_count, st.event_cap, fresh, n, tick, w * 32, t);
+        if (fresh) emit_events(st.events, st.event_count, st.event_cap, fresh, n + sc.scenario_base, tick, w * 32, t);
         c.ego_last[w] = now;
       }
       c.ego_now[w] = 0;

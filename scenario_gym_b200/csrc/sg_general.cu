@@ -183,7 +183,7 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
               accel = (double)__ldcs(in.actions_f32 + ((int64_t)k * 2 + 0) * nm + i);
               steer = (double)__ldcs(in.actions_f32 + ((int64_t)k * 2 + 1) * nm + i);
             } else {
-              const double2 a = rng_action(rng, k, i);
+              const double2 a = rng_action(rng, k, i + (int64_t)sc.scenario_base * sc.n_slots);
               accel = a.x; steer = a.y;
             }
           }
@@ -326,7 +326,7 @@ sg_rollout_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       if (need_coll && live && e.present) broad_phase_grid(c, parity, gpos);
     }
     group_sync(c);
-    done = finish_tick<false>(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick, t, dt, length, live,
+    done = finish_tick<false>(p, st, c, n + sc.scenario_base, s, W, G, ego_slot, first_slot, parity, tick, t, dt, length, live,
                        live && e.present, collided, e.vel[0], e.vel[1], e.vel[2], e.dist);
     parity ^= 1;
   }

@@ -41,6 +41,7 @@ cudaError_t sgi_launch_crowd(cudaStream_t s, const SgScene& sc, const SgParams& 
                              const SgInputs& in, int n_ticks);
 cudaError_t sgi_launch_radius(cudaStream_t s, const SgState& st, int n_scen, int M, const double* x, const double* y,
                               const double* r, uint8_t* out);
-cudaError_t sgi_launch_union(cudaStream_t s, const SgScene& sc);
+// rows: an upper bound of the union rows of the scene's scenarios (a window holds fewer than n_union_rows)
+cudaError_t sgi_launch_union(cudaStream_t s, const SgScene& sc, int64_t rows);
 cudaError_t sgi_launch_traj(cudaStream_t s, const double* rows, int K, const double* t, int64_t n, int mode,
                             double* pos, uint8_t* ok, double* vel);

@@ -31,7 +31,7 @@ __global__ void sg_future_kernel(SgScene sc, const double* __restrict__ t, const
   const int lane = threadIdx.x & 31;
   if (n >= sc.n_scenarios) return;
   const int M = sc.n_slots;
-  const int64_t nm = (int64_t)sc.n_scenarios * M;
+  const int64_t nm = sc.plane_stride;
   const int es = slot ? slot[n] : sc.ego_slot[n];
   const int64_t ie = (int64_t)n * M + es;
   const int64_t re0 = sc.traj_off[ie];
@@ -115,9 +115,11 @@ cudaError_t sgi_launch_radius(cudaStream_t s, const SgState& st, int n_scen, int
 __global__ void sg_union_kernel(SgScene sc) {
   const int M = sc.n_slots;
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (idx >= sc.n_union_rows * M) return;
-  const int64_t r = idx / M;
-  const int s = (int)(idx - r * M);
+  // (a scenario window's rows are union_off[0] .. union_off[n_scenarios] of the batch's table)
+  const int64_t row0 = __ldg(sc.union_off), row1 = __ldg(sc.union_off + sc.n_scenarios);
+  if (idx >= (row1 - row0) * M) return;
+  const int64_t r = row0 + idx / M;
+  const int s = (int)(idx - (r - row0) * M);
   int lo = 0, hi = sc.n_scenarios;  // scenario of row r: union_off[n] <= r < union_off[n + 1]
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -149,8 +151,8 @@ __global__ void sg_union_kernel(SgScene sc) {
   for (int f = 0; f < 6; ++f) X[(int64_t)f * M] = out[f];
 }
 
-cudaError_t sgi_launch_union(cudaStream_t s, const SgScene& sc) {
-  const int64_t n = sc.n_union_rows * sc.n_slots;
+cudaError_t sgi_launch_union(cudaStream_t s, const SgScene& sc, int64_t rows) {
+  const int64_t n = rows * sc.n_slots;
   if (n <= 0) return cudaSuccess;
   sg_union_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sc);
   return cudaGetLastError();

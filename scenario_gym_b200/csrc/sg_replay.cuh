@@ -106,7 +106,7 @@ struct RpCtx {  // per-scenario constants
 SG_DEV void rp_pose_and_prev(const SgScene& sc, const SgParams& p, const SgState& st, const RpCtx& c,
                              const RpSlot& e, int s, bool agent_pres, double tk, double tkm, bool first,
                              double pk[6], double prev[6]) {
-  const int64_t i = (int64_t)c.n * c.M + s, nm = (int64_t)sc.n_scenarios * c.M;
+  const int64_t i = (int64_t)c.n * c.M + s, nm = sc.plane_stride;
   const RpUnion uk = rp_union_weights(c.ts, c.UK, tk);
   rp_pose<6>(e, uk, c.X, c.UK, c.M, s, tk, pk);
   bool ppres;
@@ -133,7 +133,7 @@ SG_DEV void rp_pose_and_prev(const SgScene& sc, const SgParams& p, const SgState
 static __device__ __noinline__ void rp_write_rows(const SgScene* sc, const SgParams* p, const SgState* st,
                                            RpCtx c, int s, bool agent_pres, double tk, double tkm,
                                            bool first) {
-  const int64_t i = (int64_t)c.n * c.M + s, nm = (int64_t)sc->n_scenarios * c.M;
+  const int64_t i = (int64_t)c.n * c.M + s, nm = sc->plane_stride;
   const RpSlot e = rp_slot(*sc, i);
   double pk[6], prev[6];
   rp_pose_and_prev(*sc, *p, *st, c, e, s, agent_pres, tk, tkm, first, pk, prev);
@@ -148,7 +148,7 @@ static __device__ __noinline__ void rp_write_rows(const SgScene* sc, const SgPar
 // fp64 corners of slot s at time tk (Entity.get_bounding_box_points, entity/base.py:100-138;
 // the same expression and libm call as publish_box) and the ring orientation
 static __device__ __noinline__ Quad rp_corners(const SgScene* sc, RpCtx c, int s, double tk, int* orient) {
-  const int64_t i = (int64_t)c.n * c.M + s, nm = (int64_t)sc->n_scenarios * c.M;
+  const int64_t i = (int64_t)c.n * c.M + s, nm = sc->plane_stride;
   const RpSlot e = rp_slot(*sc, i);
   const RpUnion uk = rp_union_weights(c.ts, c.UK, tk);
   double pk[6];
@@ -234,7 +234,7 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
   RpCtx c;
   c.n = blockIdx.x; c.M = sc.n_slots;
   const int M = c.M, n = c.n;
-  const int64_t nm = (int64_t)sc.n_scenarios * M, i0 = (int64_t)n * M;
+  const int64_t nm = sc.plane_stride, i0 = (int64_t)n * M;
   c.ego_slot = sc.ego_slot[n]; c.first_slot = sc.first_slot[n];
   {
     const int64_t u0 = sc.union_off[n];
@@ -469,7 +469,7 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
           const int slot = atomicAdd(st.event_count, 1);
           if (slot < st.event_cap) {
             SgEvent ev;
-            ev.scenario = n; ev.tick = car->tick + j; ev.slot = b; ev._pad = 0; ev.t = T[j];
+            ev.scenario = n + sc.scenario_base; ev.tick = car->tick + j; ev.slot = b; ev._pad = 0; ev.t = T[j];
             st.events[slot] = ev;
           }
         }

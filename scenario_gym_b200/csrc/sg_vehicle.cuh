@@ -98,7 +98,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     if (live && limit > 0) {
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
-        const sg_u128 q = sg_rng_slot_state(rng, cc, c.i);
+        const sg_u128 q = sg_rng_slot_state(rng, cc, c.i + (int64_t)sc.scenario_base * M);
         rq[(2 * cc) * G] = (unsigned long long)q;
         rq[(2 * cc + 1) * G] = (unsigned long long)(q >> 64);
       }
@@ -234,7 +234,7 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       if (s < M) broad_phase_sorted<false>(c, parity);
       group_sync(c);
     }
-    done = finish_tick<true>(p, st, c, n, s, W, G, ego_slot, first_slot, parity, tick,
+    done = finish_tick<true>(p, st, c, n + sc.scenario_base, s, W, G, ego_slot, first_slot, parity, tick,
                        c.cold_d[COLD_T0 + (parity ^ 1)], c.cold_d[COLD_T0 + (parity ^ 1)] - c.cold_d[COLD_PT0 + (parity ^ 1)],
                        c.cold_d[COLD_LEN], live, live && present, collided, vx, vy, 0.0, dist);
     parity ^= 1;

@@ -115,3 +115,52 @@ def test_union_table_built_on_device():
         got = eng.build_union_on_device().cpu().numpy()
         assert got.shape == scene.union_x.shape and scene.union_x.size > 0
         assert np.array_equal(got, scene.union_x)
+
+
+_STATE_FIELDS = ("tick", "done", "present", "collided", "first_coll_tick", "first_coll_pair", "n_pair_ticks", "ego_hits",
+                 "t", "prev_t", "pose", "vel", "dist", "speed", "ego_avg_speed", "ego_max_speed", "ego_dist", "rss_flags",
+                 "rss_state", "rss_last", "safe_dist", "goal_idx", "force")
+
+
+def _window_cases():
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import all_xosc_specs
+    from scenario_gym_b200.packing import pack_scenarios
+
+    cfg = synthetic.vehicles_config(seed=21, N=37, M=64, T=30, half_extent=60.0)
+    yield "vehicles+rss (in-kernel actions)", pack_synthetic(cfg), _params(cfg.dt, rss=True), cfg.action_rng
+    cfg = synthetic.highway_config(seed=22, N=9, M=256, T=12)
+    cfg.x0[:] = cfg.x0 * 0.5
+    yield "sorted sweep", pack_synthetic(cfg), _params(cfg.dt, rss=True), cfg.action_rng
+    yield "replay", pack_scenarios([s for _, s, _, _ in all_xosc_specs("xosc")]), abi.default_params(), None
+    cfg = synthetic.crowd_config(seed=23, N=5, M=320, T=8, side=14.0)
+    yield "crowd", pack_synthetic(cfg), _params(cfg.dt, rss=False), None
+    cfg = synthetic.crowd_config(seed=24, N=6, M=96, T=10, side=9.0)
+    yield "pedestrians (general kernel)", pack_synthetic(cfg), _params(cfg.dt, rss=False), None
+
+
+@pytest.mark.parametrize("windows", ["2", "3", "4"])
+def test_host_path_scenario_windows(windows, monkeypatch):
+    """
+    sg_rollout_host uploads a batch in windows of scenarios and rolls every window out as it arrives
+    (SgScene.plane_stride / scenario_base): every State row, the action stream's draws and the event
+    records must equal the one-piece rollout bit for bit.
+    """
+    from scenario_gym_b200.engine import Engine
+    from scenario_gym_b200.hostpath import HostRollout
+
+    for tag, scene, p, actions in _window_cases():
+        ref = Engine(scene, p, device=0)
+        monkeypatch.setenv("SG_HOST_WINDOWS", "1")
+        want = HostRollout(ref, actions).run()
+        eng = Engine(scene, p, device=0)
+        monkeypatch.setenv("SG_HOST_WINDOWS", windows)
+        got = HostRollout(eng, actions).run()
+        for k in FIELDS:
+            assert np.array_equal(got[k], want[k], equal_nan=True), (tag, k)
+        assert int(got["event_count"][0]) == int(want["event_count"][0]), tag
+        for k in _STATE_FIELDS:
+            assert np.array_equal(eng.get(k), ref.get(k), equal_nan=True), (tag, k)
+        a, b = eng.events(), ref.events()
+        assert a.tobytes() == b.tobytes(), (tag, "events")
