@@ -82,14 +82,15 @@ SG_DEV void group_sync(const Grp& g) {
 }
 
 SG_DEV void setup_group(Grp& g, const SgScene& sc, const GroupLayout& L, unsigned char* smem,
-                        int gl, int s, int n) {
+                        int gl, int s, int n, int M = -1) {
+  if (M < 0) M = sc.n_slots;  // (kernels specialised for a slot count pass it as a constant)
   unsigned char* base = smem + (size_t)gl * L.bytes;
-  g.n = n; g.s = s; g.M = sc.n_slots; g.G = L.G; g.W = L.W; g.H = L.H; g.QCAP = L.QCAP;
+  g.n = n; g.s = s; g.M = M; g.G = L.G; g.W = L.W; g.H = L.H; g.QCAP = L.QCAP;
   g.bar_id = 1 + gl;
   g.mask = 0xffffffffu;
   if (L.G < 32) g.mask = ((1u << L.G) - 1u) << ((threadIdx.x & 31) / L.G * L.G);
   g.nm = sc.plane_stride;  // (sg_api.cu fills it in for whole batches)
-  g.i = (int64_t)n * sc.n_slots + s;
+  g.i = (int64_t)n * M + s;
   g.corners = (double*)base;
   g.actbuf = (double*)(base + L.off_act);
   g.rbox = (double*)(base + L.off_rbox);

@@ -53,10 +53,11 @@ enum { COLD_AVG = 0, COLD_AVG_T, COLD_MAX, COLD_EGOD, COLD_T0, COLD_T1, COLD_PT0
 enum { COLD_FIRST_TICK = 0, COLD_FP0, COLD_FP1, COLD_RSS, COLD_PAIR_TICKS = 4, COLD_HAS_VEH = 6, COLD_NI = 8 };  // ints
 enum { ACC_NPAIRS = 0, ACC_FIRST_PAIR, ACC_FIRST_HIT, ACC_RSS, ACC_QCOUNT, ACC_OFFROAD, ACC_N = 8 };
 
-static inline GroupLayout make_layout(int M, bool ped, bool rss, bool veh, bool grid = false) {
-  GroupLayout L;
-  int G;
-  if (M <= 32) { G = 1; while (G < M) G <<= 1; } else { G = (M + 31) / 32 * 32; }
+// (constexpr: kernels specialised for a slot count take their shared-memory offsets as immediates)
+__host__ __device__ constexpr GroupLayout make_layout(int M, bool ped, bool rss, bool veh, bool grid = false) {
+  GroupLayout L{};
+  int G = 1;
+  if (M <= 32) { while (G < M) G <<= 1; } else { G = (M + 31) / 32 * 32; }
   L.G = G;
   L.W = (M + 31) / 32;
   L.H = M / 2;

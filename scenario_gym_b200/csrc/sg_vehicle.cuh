@@ -15,18 +15,26 @@ SG_DEV void cp_async4(unsigned smem_addr, const void* gsrc) {
 // z, p, r never change under VehicleController._step (controller.py:122-131), so their
 // velocities are 0 after the first tick and they stay in global memory.
 // ---------------------------------------------------------------------------------
-template <bool RSS, int MAXT, int MINB, bool SORTED, bool LEAN = false, int ACT = ACT_F64>
+// MC > 0: the kernel is specialised for scenes of exactly MC slots -- the shared-memory layout, the
+// group size and every index stride are compile-time constants (immediates instead of address
+// arithmetic on the layout struct in the constant bank: 5 % of the tick's instructions).
+template <bool RSS, int MC>
+struct VehLayout {
+  static constexpr GroupLayout value = make_layout(MC > 0 ? MC : 64, false, RSS, true, false);
+};
+template <bool RSS, int MAXT, int MINB, bool SORTED, bool LEAN = false, int ACT = ACT_F64, int MC = 0>
 __global__ void __launch_bounds__(MAXT, MINB)
-sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, GroupLayout L, SgRngDev rng) {
+sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, GroupLayout Lrt, SgRngDev rng) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int G = L.G, M = sc.n_slots, W = L.W;
+  const GroupLayout L = MC > 0 ? VehLayout<RSS, MC>::value : Lrt;
+  const int G = L.G, M = MC > 0 ? MC : sc.n_slots, W = L.W;
   const int gpb = blockDim.x / G;
   const int gl = threadIdx.x / G;
   const int s = threadIdx.x - gl * G;
   const int n = blockIdx.x * gpb + gl;
   if (gl >= gpb || n >= sc.n_scenarios) return;
   Grp c;
-  setup_group(c, sc, L, smem, gl, s, n);
+  setup_group(c, sc, L, smem, gl, s, n, M);
   const bool live = s < M && sc.kind[c.i] == SG_KIND_VEHICLE;
   const int ego_slot = sc.ego_slot[n], first_slot = sc.first_slot[n];
   // (LEAN is only launched with collisions on, no trace and no pair matrix; RSS only with the feature on)
@@ -277,11 +285,26 @@ static cudaError_t launch_vehicle_t(int n_scen, cudaStream_t s, const SgScene& s
          : act == ACT_RNG ? sg_vehicle_kernel<RSS, T, B, S, true, ACT_RNG>                     \
          : act == ACT_F32 ? sg_vehicle_kernel<RSS, T, B, S, true, ACT_F32>                     \
                           : sg_vehicle_kernel<RSS, T, B, S, true, ACT_F64>)
+  // lean kernels specialised for a slot count (compile-time layout): the device-side action source and the fp64 table
+#define SG_VEH_PICK_M(T, B, S, MC_)                                                            \
+  (act == ACT_RNG ? sg_vehicle_kernel<RSS, T, B, S, true, ACT_RNG, MC_>                        \
+                  : sg_vehicle_kernel<RSS, T, B, S, true, ACT_F64, MC_>)
+  const int M = sc.n_slots;
+  const bool spec = lean && (act == ACT_RNG || act == ACT_F64);
   // (the sorted sweep is a compile-time variant too: scenes of up to 128 slots carry none of its code)
-  if (L.G <= SG_VEH_THREADS) { kern = SG_VEH_PICK(SG_VEH_THREADS, SG_VEH_MINB, false); threads = SG_VEH_THREADS; }
-  else if (L.G <= SG_THREADS) { kern = L.sorted ? SG_VEH_PICK(SG_THREADS, 2, true) : SG_VEH_PICK(SG_THREADS, 2, false); threads = SG_THREADS; }
+  if (L.G <= SG_VEH_THREADS) {
+    kern = (spec && M == 64) ? SG_VEH_PICK_M(SG_VEH_THREADS, SG_VEH_MINB, false, 64)
+         : (spec && M == 128) ? SG_VEH_PICK_M(SG_VEH_THREADS, SG_VEH_MINB, false, 128)
+                              : SG_VEH_PICK(SG_VEH_THREADS, SG_VEH_MINB, false);
+    threads = SG_VEH_THREADS;
+  } else if (L.G <= SG_THREADS) {
+    kern = (spec && M == 256 && L.sorted) ? SG_VEH_PICK_M(SG_THREADS, 2, true, 256)
+         : L.sorted ? SG_VEH_PICK(SG_THREADS, 2, true) : SG_VEH_PICK(SG_THREADS, 2, false);
+    threads = SG_THREADS;
+  }
   else { kern = L.sorted ? SG_VEH_PICK(1024, 1, true) : SG_VEH_PICK(1024, 1, false); threads = L.G; }
 #undef SG_VEH_PICK
+#undef SG_VEH_PICK_M
   const int gpb = threads / L.G;
   const int blocks = (n_scen + gpb - 1) / gpb;
   const size_t smem = (size_t)gpb * L.bytes;
