@@ -516,14 +516,19 @@ class ScenarioGym:
         """
         M = self._engine.M
         sl = slice(n * M, (n + 1) * M)
-        pose, vel = self._fetch("pose")[:, sl], self._fetch("vel")[:, sl]
-        dist, present = self._fetch("dist")[sl], self._fetch("present")[sl]
+        if "poseT" not in self._cache:  # entity-major rows, transposed once per tick for the whole batch
+            self._cache["poseT"] = np.ascontiguousarray(self._fetch("pose").T)
+            self._cache["velT"] = np.ascontiguousarray(self._fetch("vel").T)
         ents = self._entity_of[n]
-        poses, vels = {}, {}
-        for s in np.nonzero(present[: len(ents)])[0]:
-            e = ents[s]
-            poses[e] = pose[:, s].copy()
-            vels[e] = vel[:, s].copy()
+        k = len(ents)
+        dist, present = self._fetch("dist")[sl], self._fetch("present")[n * M:n * M + k]
+        rows_p, rows_v = self._cache["poseT"][n * M:n * M + k], self._cache["velT"][n * M:n * M + k]
+        if present.all():
+            here, rows_p, rows_v = ents, rows_p.copy(), rows_v.copy()
+        else:
+            idx = np.nonzero(present)[0]
+            here, rows_p, rows_v = [ents[i] for i in idx], rows_p[idx], rows_v[idx]
+        poses, vels = dict(zip(here, rows_p)), dict(zip(here, rows_v))  # (rows of this scenario's own copies)
         if self._rss_cb is not None:
             self._sync_rss(n, ents, sl)
         return {

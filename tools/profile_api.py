@@ -27,3 +27,17 @@ for what, fn in (("set_scenarios", lambda: gym.set_scenarios(scenarios)), ("roll
     pr = cProfile.Profile(); t0 = time.perf_counter(); pr.enable(); fn(); pr.disable()
     print(f"==== {what}: {time.perf_counter() - t0:.4f} s")
     pstats.Stats(pr).sort_stats("cumulative").print_stats(12)
+
+# ---- per-tick host mode: a custom Metric the engine knows nothing about
+from scenario_gym_b200 import Metric
+class MaxEntities(Metric):
+    name = "max_entities"
+    def _reset(self, state): self.value = len(state.poses)
+    def _step(self, state): self.value = max(self.value, len(state.poses))
+    def get_state(self): return self.value
+gym2 = ScenarioGym(metrics=[EgoAvgSpeed(), MaxEntities()], device=0)
+gym2.set_scenarios(scenarios[:64])
+gym2.rollout()
+pr = cProfile.Profile(); t0 = time.perf_counter(); pr.enable(); gym2.rollout(); pr.disable()
+print(f"==== host-metric rollout (64 scenarios): {time.perf_counter() - t0:.4f} s")
+pstats.Stats(pr).sort_stats("cumulative").print_stats(30)
