@@ -375,9 +375,19 @@ int sg_test_box_pairs(const double* pose_a, const double* box_a, const double* p
 int sg_test_trajectory(const double* rows, int64_t K, const double* t, int64_t n, int mode, double* pos,
                        uint8_t* ok, double* vel, int device, void* stream);
 
-/* Host-buffer convenience used for the end-to-end number: copy the scene/initial
-   inputs H2D (pinned host memory recommended), reset, rollout to completion and copy
-   the per-scenario results back.  `dev_*` are device mirrors with the same shapes. */
+/* Host-buffer entry point (the end-to-end number): copy the scene / initial inputs H2D (pinned host
+   memory recommended), reset, roll every scenario out to completion and copy the per-scenario results
+   back, all enqueued on `stream`.  `dev_*` are device mirrors with the same shapes.
+   - copy_static = 0: the device scene is already up to date, nothing but the action table is copied.
+   - An action table (host_inputs->actions / actions_f32) is streamed in chunks of 16 ticks, each chunk's
+     copy overlapping the previous chunk's rollout; with host_inputs->use_rng the actions are drawn on the
+     device and nothing but the scene crosses PCIe.
+   - Without a table the batch is uploaded in windows of scenarios (SgScene.plane_stride) on an internal
+     copy stream and every window is reset and rolled out as soon as it has arrived (three windows for
+     scenes of 8 MiB or more; the environment variable SG_HOST_WINDOWS = 1 .. 4 overrides the number):
+     the results equal the one-piece rollout's bit for bit, the upload hides behind the rollout.
+   - host_scene->union_x = NULL with union_t present: the union table is built on the device
+     (sg_build_union_x) instead of being uploaded. */
 typedef struct SgHostResults {
   double* ego_avg_speed;    /* [N] */
   double* ego_max_speed;    /* [N] */
