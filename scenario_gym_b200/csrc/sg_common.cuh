@@ -1402,6 +1402,63 @@ SG_DEV bool finish_tick(const SgParams& p, const SgState& st, const Grp& c, int 
   return dn;
 }
 
+// ---------------------------------------------------------------------------------
+// The lean vehicle kernels' tick tail when no terminal condition reads the tick's collisions: the narrow
+// phase runs on the warps that do NOT hold the ego (whose warp carries the scenario's other serial job,
+// publish_ego), nobody waits for it, and what finish_tick's phase C books -- pair counts, the first
+// collision, CollisionMetric rising edges, the RSS latch -- is booked one barrier later, at the start of
+// the next tick's callback phase (lagged_epilogue; once more after the last tick).  The `collided` bits
+// are sticky over the launch and read once at its end.  Same results, a shorter critical path per tick.
+// ---------------------------------------------------------------------------------
+SG_DEV void narrow_phase_lagged(const SgParams& p, const SgState& st, const Grp& c, int s, int G, int ego_slot,
+                                int first_slot, int parity, bool present) {
+  const int nq = c.acc[parity * ACC_N + ACC_QCOUNT];
+  if (nq <= 0) return;
+  PairSink sink = make_sink(p.features, st.coll_mask, c, ego_slot, first_slot, parity);
+  sink.bits = c.bits;  // (parity 0's words: sticky)
+  if (nq <= c.QCAP) {
+    int qs = s - (((ego_slot >> 5) + 1) << 5);  // the lanes behind the ego's warp take the first entries
+    if (qs < 0) qs += G;
+    for (int q = qs; q < nq; q += G) {
+      const uint32_t pr = c.queue[q];
+      decide_pair(sink, c.corners, c.corners_sh, c.orient, G, (int)(pr >> 16), (int)(pr & 0xffff));
+    }
+  } else if (c.sorted) {
+    if (s < c.M) broad_phase_direct_sorted(sink, c.aabb, c.sid, c.corners_sh, c.orient, G, c.M, s);
+  } else if (present) {
+    broad_phase_direct(sink, c.aabb, c.corners_sh, c.orient, G, c.M, c.H, s);
+  }
+}
+// books the tick whose accumulators are `parity` (tick number `tick`, time after it `t`) and clears them
+SG_DEV void lagged_epilogue(const SgParams& p, const SgState& st, const Grp& c, int n, int s, int W, int G,
+                            int ego_slot, int parity, int tick, double t) {
+  int* acc = c.acc + parity * ACC_N;
+  const int bs = s - ((G > 32 && ego_slot < 32) ? 32 : 0);
+  if (bs == 0) {
+    int* cold = c.cold_i;
+    const int npairs = acc[ACC_NPAIRS];
+    if (npairs > 0) {
+      *(long long*)(cold + COLD_PAIR_TICKS) += npairs;
+      if (cold[COLD_FIRST_TICK] < 0) {
+        const int fp = acc[ACC_FIRST_PAIR];
+        cold[COLD_FIRST_TICK] = tick; cold[COLD_FP0] = fp >> 16; cold[COLD_FP1] = fp & 0xffff;
+      }
+    }
+    cold[COLD_RSS] |= acc[ACC_RSS];
+    acc[ACC_NPAIRS] = 0; acc[ACC_FIRST_PAIR] = 0x7fffffff; acc[ACC_FIRST_HIT] = 0; acc[ACC_RSS] = 0;
+    acc[ACC_QCOUNT] = 0; acc[ACC_OFFROAD] = 0;
+  }
+  if (bs >= 0 && bs < W) {  // CollisionMetric._step, metrics/collision.py:70-75
+    const uint32_t now = c.ego_now[bs];
+    if (p.features & SG_FEAT_COLLISIONS) {
+      const uint32_t fresh = now & ~c.ego_last[bs];
+      if (fresh) emit_events(st.events, st.event_count, st.event_cap, fresh, n, tick, bs * 32, t);
+      c.ego_last[bs] = now;
+    }
+    c.ego_now[bs] = 0;
+  }
+}
+
 // per-scenario accumulators live in shared memory between ticks
 SG_DEV void load_cold(const SgState& st, const Grp& c, int n, int s, int W, int ego_slot) {
   if (s == ego_slot) {

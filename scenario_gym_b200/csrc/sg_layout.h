@@ -62,7 +62,8 @@ __host__ __device__ constexpr GroupLayout make_layout(int M, bool ped, bool rss,
   L.W = (M + 31) / 32;
   L.H = M / 2;
   L.QCAP = 4 * G;
-  int o = 8 * G * (int)sizeof(double);                            // corners[8][G]
+  L.sorted = (veh && M >= SG_SORT_MIN_M && G > SG_VEH_THREADS) ? 1 : 0;
+  int o = (L.sorted ? 2 : 1) * 8 * G * (int)sizeof(double);       // corners[8][G] (sorted vehicle kernels: one per tick parity)
   L.off_act = o;    o += veh ? 4 * G * (int)sizeof(double) : 0;             // VehicleAction rows, 2 stages x (accel, steer)
   L.off_rbox = o;   o += rss ? 8 * G * (int)sizeof(double) : 0;   // hazard corners in the ego frame
   L.off_tcold = o;  o += veh ? 6 * G * (int)sizeof(double) : 0;   // per-thread cold values: sd[2], ratio[2], vh, 1/length
@@ -82,7 +83,6 @@ __host__ __device__ constexpr GroupLayout make_layout(int M, bool ped, bool rss,
   L.off_flags = o;  o += G + 16;                                  // old present|etype<<1
   L.off_orient = o; o += G;                                       // ring orientation of each box
   o = (o + 15) / 16 * 16;
-  L.sorted = (veh && M >= SG_SORT_MIN_M && G > SG_VEH_THREADS) ? 1 : 0;
   L.off_sid = o;    o += L.sorted ? (M + 64) * (int)sizeof(uint16_t) : 0;   // slot id at each sorted position
   L.off_posof = o;  o += L.sorted ? G * (int)sizeof(uint16_t) : 0;          // sorted position of each slot
   o = (o + 15) / 16 * 16;

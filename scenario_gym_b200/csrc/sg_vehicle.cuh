@@ -42,6 +42,10 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
                          (p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
   const bool feat_rss = RSS;
   const bool matrix = !LEAN && (p.features & SG_FEAT_COLL_MATRIX) != 0;
+  // lagged tick tail (sg_common.cuh): whole-warp groups of two or more warps, no terminal condition on collisions
+  // (scenarios of several warps with the sorted sweep: C5 + 7 %; two-warp scenarios lose 8 % with it, the ego's
+  // warp stays their critical path)
+  const bool lag = LEAN && SORTED && !(p.terminal & (SG_TERM_COLLISION | SG_TERM_EGO_COLLISION));
 
   // hot per-entity state in registers; everything that is only read back at the end (safe
   // distances, ratios, heading rate) or is uniform per scenario (tick times, length, origin)
@@ -119,7 +123,13 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
     cp_async_commit();
   }
 
+  double* const corners0 = c.corners;
+  const unsigned corners_sh0 = c.corners_sh;
   for (int k = 0; k < limit && (!done || in.step_done); ++k) {
+    if (LEAN && lag) {  // this tick's corners: the previous tick's narrow phase may still be reading the other set
+      c.corners = corners0 + parity * 8 * G;
+      c.corners_sh = corners_sh0 + (unsigned)(parity * 8 * G * 8);
+    }
     const double* U = c.cold_d;
     const double t = U[COLD_T0 + parity];
     const double next_t = t + p.timestep;  // scenario_gym.py:229
@@ -210,6 +220,8 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       }
     }
     // ---- phase B1: callbacks (RSS) + broad phase
+    if (LEAN && lag && k > 0)  // the previous tick's books (its narrow phase is complete: it ran before this tick's barrier)
+      lagged_epilogue(p, st, c, n + sc.scenario_base, s, W, G, ego_slot, parity ^ 1, tick - 1, t);
     if (live && present) {
       if (RSS && feat_rss) {  // RSSDistances.__call__, callback.py:57-122
         rss_last = SG_RSS_NONE;
@@ -242,10 +254,31 @@ sg_vehicle_kernel(SgScene sc, SgParams p, SgState st, SgInputs in, int n_ticks, 
       if (s < M) broad_phase_sorted<false>(c, parity);
       group_sync(c);
     }
-    done = finish_tick<true>(p, st, c, n + sc.scenario_base, s, W, G, ego_slot, first_slot, parity, tick,
-                       c.cold_d[COLD_T0 + (parity ^ 1)], c.cold_d[COLD_T0 + (parity ^ 1)] - c.cold_d[COLD_PT0 + (parity ^ 1)],
-                       c.cold_d[COLD_LEN], live, live && present, collided, vx, vy, 0.0, dist);
+    if (LEAN && lag) {
+      narrow_phase_lagged(p, st, c, s, G, ego_slot, first_slot, parity, live && present);
+      if (c.acc[parity * ACC_N + ACC_QCOUNT] > c.QCAP) group_sync(c);  // (queue overflow: the redo reads this tick's AABBs)
+      const double ta = c.cold_d[COLD_T0 + (parity ^ 1)], dta = ta - c.cold_d[COLD_PT0 + (parity ^ 1)];
+      done = (p.terminal & SG_TERM_MAX_LENGTH) && (ta + dta > c.cold_d[COLD_LEN]);  // state.py:397-398
+      if (s == ego_slot && (p.features & SG_FEAT_EGO_METRICS)) {  // metrics/trajectory.py:20-24,39-42,58-60
+        double* m = c.cold_d;
+        const double sp = fast_sqrt(vx * vx + vy * vy);
+        const double w = ta > 0.0 ? div_r(m[COLD_AVG_T], ta, fast_rcp(ta)) : m[COLD_AVG_T] / ta;
+        m[COLD_AVG] += (1.0 - w) * (sp - m[COLD_AVG]);
+        m[COLD_AVG_T] = ta;
+        m[COLD_MAX] = fmax(sp, m[COLD_MAX]);
+        m[COLD_EGOD] = dist;
+      }
+    } else {
+      done = finish_tick<true>(p, st, c, n + sc.scenario_base, s, W, G, ego_slot, first_slot, parity, tick,
+                         c.cold_d[COLD_T0 + (parity ^ 1)], c.cold_d[COLD_T0 + (parity ^ 1)] - c.cold_d[COLD_PT0 + (parity ^ 1)],
+                         c.cold_d[COLD_LEN], live, live && present, collided, vx, vy, 0.0, dist);
+    }
     parity ^= 1;
+  }
+  if (LEAN && lag && tick > tick0) {  // the last tick's books, and the slots that collided during the launch
+    group_sync(c);
+    lagged_epilogue(p, st, c, n + sc.scenario_base, s, W, G, ego_slot, parity ^ 1, tick, c.cold_d[COLD_T0 + parity]);
+    if (live && ((c.bits[s >> 5] >> (s & 31)) & 1)) collided = 1;
   }
 
   if (RSS && LEAN && live && present && rss_evald) rss_ratios(c, x, y, tc, G);
