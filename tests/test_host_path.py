@@ -117,7 +117,7 @@ def test_union_table_built_on_device():
         assert np.array_equal(got, scene.union_x)
 
 
-_STATE_FIELDS = ("tick", "done", "present", "collided", "first_coll_tick", "first_coll_pair", "n_pair_ticks", "ego_hits",
+_STATE_FIELDS = ("coll_mask", "tick", "done", "present", "collided", "first_coll_tick", "first_coll_pair", "n_pair_ticks", "ego_hits",
                  "t", "prev_t", "pose", "vel", "dist", "speed", "ego_avg_speed", "ego_max_speed", "ego_dist", "rss_flags",
                  "rss_state", "rss_last", "safe_dist", "goal_idx", "force")
 
@@ -138,6 +138,18 @@ def _window_cases():
     yield "crowd", pack_synthetic(cfg), _params(cfg.dt, rss=False), None
     cfg = synthetic.crowd_config(seed=24, N=6, M=96, T=10, side=9.0)
     yield "pedestrians (general kernel)", pack_synthetic(cfg), _params(cfg.dt, rss=False), None
+    # per-agent VehicleController limits route the scene to the general kernel (device-side action source,
+    # RSS, per-slot limit planes and the pair matrix all addressed through the window)
+    cfg = synthetic.vehicles_config(seed=25, N=11, M=40, T=20, half_extent=35.0)
+    scene = pack_synthetic(cfg)
+    lim = np.zeros((4, scene.N * scene.M))
+    rng = np.random.default_rng(7)
+    lim[0], lim[1], lim[2], lim[3] = rng.uniform(0.3, 0.9, lim.shape[1]), rng.uniform(2.0, 6.0, lim.shape[1]), np.nan, 1.0
+    lim[2, ::3] = 12.0
+    scene.veh_limits = lim
+    p = _params(cfg.dt, rss=True)
+    p.features |= abi.FEAT_COLL_MATRIX
+    yield "vehicles with per-agent limits + pair matrix (general kernel)", scene, p, cfg.action_rng
 
 
 @pytest.mark.parametrize("windows", ["2", "3", "4"])
