@@ -12,8 +12,9 @@
 //      `max_length` is then decided for all ticks of the chunk at once;
 //   2  every thread evaluates its time: presence and poses of all slots (uniform loops over the
 //      slots: no divergence between entity kinds; the previous pose comes from the neighbouring
-//      lane), distance increments, ego speed, staged conservative fp32 AABBs, the pair sweep and
-//      (rarely) the exact narrow phase;
+//      lane), distance increments, ego speed, staged conservative fp32 AABBs, the pair sweep and the
+//      narrow phase of its survivors from the poses staged in shared memory (separating-axis
+//      filter, exact predicate for knife edges);
 //   3  the chunk is committed: ordered reductions over the ticks (distance, EgoAvgSpeed recurrence
 //      with the same operation order as metrics/trajectory.py:20-24, collision rising edges,
 //      first collision, terminal conditions) and the State rows of the entities that left / the
@@ -145,40 +146,6 @@ static __device__ __noinline__ void rp_write_rows(const SgScene* sc, const SgPar
   }
 }
 
-// fp64 corners of slot s at time tk (Entity.get_bounding_box_points, entity/base.py:100-138;
-// the same expression and libm call as publish_box) and the ring orientation
-static __device__ __noinline__ Quad rp_corners(const SgScene* sc, RpCtx c, int s, double tk, int* orient) {
-  const int64_t i = (int64_t)c.n * c.M + s, nm = sc->plane_stride;
-  const RpSlot e = rp_slot(*sc, i);
-  const RpUnion uk = rp_union_weights(c.ts, c.UK, tk);
-  double pk[6];
-  rp_pose<4>(e, uk, c.X, c.UK, c.M, s, tk, pk);
-  double sn, cs;
-  sincos(pk[3], &sn, &cs);
-  const double bw = sc->box[i], bl = sc->box[nm + i], bcx = sc->box[2 * nm + i], bcy = sc->box[3 * nm + i];
-  const double hx0 = bcx - 0.5 * bl, hx1 = bcx + 0.5 * bl;
-  const double hy0 = bcy + 0.5 * bw, hy1 = bcy - 0.5 * bw;
-  const double x = pk[0], y = pk[1];
-  Quad q;
-  q.x0 = x + (hx0 * cs + hy0 * -sn); q.y0 = y + (hx0 * sn + hy0 * cs);
-  q.x1 = x + (hx1 * cs + hy0 * -sn); q.y1 = y + (hx1 * sn + hy0 * cs);
-  q.x2 = x + (hx1 * cs + hy1 * -sn); q.y2 = y + (hx1 * sn + hy1 * cs);
-  q.x3 = x + (hx0 * cs + hy1 * -sn); q.y3 = y + (hx0 * sn + hy1 * cs);
-  const int hint = box_orientation_hint(bw, bl);
-  *orient = hint ? hint : quad_orientation(q);
-  return q;
-}
-
-// exact narrow phase of one AABB-surviving pair at time tk (state/utils.py:10-49, utils.py:28-62)
-static __device__ __noinline__ bool rp_pair_exact(const SgScene* sc, RpCtx c, int a, int b, double tk) {
-  int oa, ob;
-  const Quad A = rp_corners(sc, c, a, tk, &oa), B = rp_corners(sc, c, b, tk, &ob);
-  const bool same = A.x0 == B.x0 && A.y0 == B.y0 && A.x1 == B.x1 && A.y1 == B.y1 && A.x2 == B.x2 &&
-                    A.y2 == B.y2 && A.x3 == B.x3 && A.y3 == B.y3;
-  if (same) return false;  // `g != g_prime`, reference utils.py:58
-  return quads_intersect(A, oa, B, ob);
-}
-
 // out-of-line so that the tick loop carries one copy of the control-point search
 static __device__ __noinline__ double4 rp_agent_pose4(const double* rows, int K, double t, int mode) {
   int cur = 0;
@@ -198,6 +165,39 @@ struct RpDesc {  // per-slot constants staged in shared memory
 SG_DEV bool rp_present_d(const RpDesc& e, int persist, double tau, bool agent_pres) {
   if (e.kind == SG_KIND_AGENT_REPLAY) return agent_pres;
   return persist || e.K == 1 || (tau >= e.tmin && tau <= e.tmax);
+}
+
+// fp64 corners of a slot from its staged pose (Entity.get_bounding_box_points, entity/base.py:100-138; the
+// same expression as publish_box, on the cos / sin the tick's own libm call returned)
+SG_DEV void rp_corners_staged(const RpDesc& e, double2 xy, double2 hc, double q[8]) {
+  const double x = xy.x, y = xy.y, cs = hc.x, sn = hc.y;
+  const double hx0 = e.bcx - 0.5 * e.bl, hx1 = e.bcx + 0.5 * e.bl;
+  const double hy0 = e.bcy + 0.5 * e.bw, hy1 = e.bcy - 0.5 * e.bw;
+  q[0] = x + (hx0 * cs + hy0 * -sn); q[1] = y + (hx0 * sn + hy0 * cs);
+  q[2] = x + (hx1 * cs + hy0 * -sn); q[3] = y + (hx1 * sn + hy0 * cs);
+  q[4] = x + (hx1 * cs + hy1 * -sn); q[5] = y + (hx1 * sn + hy1 * cs);
+  q[6] = x + (hx0 * cs + hy1 * -sn); q[7] = y + (hx0 * sn + hy1 * cs);
+}
+
+// narrow phase of one AABB-surviving pair of a tick (state/utils.py:10-49, utils.py:28-62) from the poses the
+// slot loop staged in shared memory: nothing is re-read from global memory, no control-point search, no
+// second sincos.  The branch-free separating-axis filter decides all but knife-edge contacts; those (and
+// coincident boxes, `g != g_prime` utils.py:58) go to the exact predicate.
+static __device__ __noinline__ bool rp_pair_staged(const RpDesc* desc, const double2* xy, const double2* hc,
+                                                   int a, int b, int col) {
+  const RpDesc ea = desc[a], eb = desc[b];
+  double qa[8], qb[8];
+  rp_corners_staged(ea, xy[a * SG_RP_THREADS + col], hc[a * SG_RP_THREADS + col], qa);
+  rp_corners_staged(eb, xy[b * SG_RP_THREADS + col], hc[b * SG_RP_THREADS + col], qb);
+  const int v = sat_classify(qa, qb);
+  if (v != 0) return v > 0;
+  bool same = true;
+#pragma unroll
+  for (int f = 0; f < 8; ++f) same = same && qa[f] == qb[f];
+  if (same) return false;
+  const Quad A = quad_from_array(qa), B = quad_from_array(qb);
+  const int ha = box_orientation_hint(ea.bw, ea.bl), hb = box_orientation_hint(eb.bw, eb.bl);
+  return quads_intersect(A, ha ? ha : quad_orientation(A), B, hb ? hb : quad_orientation(B));
 }
 
 struct RpCarry {  // cross-chunk state of the scenario (shared memory)
@@ -222,7 +222,7 @@ SG_DEV void rp_ego_metrics(RpCarry* car, const double* spv, const double* cwv, i
 
 template <bool MATRIX>  // MATRIX: also write the pair matrix of the final tick (SG_FEAT_COLL_MATRIX)
 #ifndef SG_RP_MINB
-#define SG_RP_MINB 4
+#define SG_RP_MINB 3  // (the staged poses bring a 9-slot scene to 64 KB of shared memory: three CTAs per SM, 128 registers)
 #endif
 __global__ void __launch_bounds__(SG_RP_BLOCK, SG_RP_MINB)
 sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgParams p,
@@ -260,7 +260,9 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
   double* cdist = part + SG_RP_WARPS * M;            // [M] accumulated distance
   RpDesc* desc = (RpDesc*)(cdist + M + (M & 1));     // [M]
   float4* aabb = (float4*)(desc + M);                // [M][CH]
-  uint32_t* egonow = (uint32_t*)(aabb + (size_t)M * CH);  // [TS]; [0] = ego row before the chunk
+  double2* sxy = (double2*)(aabb + (size_t)M * CH);  // [M][CH] position of a present slot after the thread's tick
+  double2* shc = sxy + (size_t)M * CH;               // [M][CH] cos / sin of its heading
+  uint32_t* egonow = (uint32_t*)(shc + (size_t)M * CH);  // [TS]; [0] = ego row before the chunk
   uint32_t* cbits = egonow + TS;                     // [TS]
   uint32_t* fpair = cbits + TS;                      // [TS]
   int* npairs = (int*)(fpair + TS);                  // [TS]
@@ -300,7 +302,12 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
     Tb[cnt + 1] = t + p.timestep;
     car->cnt = cnt;
   }
+  for (int q = tid; q < SG_RP_WARPS * M; q += SG_RP_BLOCK) part[q] = 0.0;
   __syncthreads();
+  // slots past the last non-empty one take no part in any loop below (scenes padded to the batch's slot count)
+  int ML = 0;
+  for (int s = 0; s < M; ++s)
+    if (desc[s].kind != SG_KIND_EMPTY) ML = s + 1;
 
   for (;;) {
     const int buf = car->buf;
@@ -337,9 +344,11 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
       car->cnt_next = cn;
     }
 
+    uint32_t leave = 0;  // slots present after this thread's tick but not after the next one
     for (int attempt = 0; attempt < 2; ++attempt) {
       // ---- 2: every thread evaluates its time ----------------------------------------------------
       if (warp < SG_RP_WARPS) {
+        leave = 0;
         const bool live_t = j <= nv;             // T[j] is a time of this chunk
         const bool valid = lane >= 1 && live_t;  // this thread owns tick j
         const double tj = live_t ? T[j] : T[0], tkm = valid ? T[j - 1] : T[0];
@@ -348,7 +357,7 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
         const RpUnion uk = rp_union_weights_ool(c.ts, c.UK, tj);
         uint32_t pm = 0;  // present slots after this tick
         double sp = NAN;
-        for (int s = 0; s < M; ++s) {
+        for (int s = 0; s < ML; ++s) {
           const RpDesc e = desc[s];
           if (e.kind == SG_KIND_EMPTY) {
             if (need_coll) aabb[(size_t)s * CH + tid] = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
@@ -357,6 +366,8 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
           }
           const bool ap = apres[s] != 0;
           const bool pres = live_t && rp_present_d(e, p.persist, tj, ap);
+          if (valid && pres && e.kind != SG_KIND_AGENT_REPLAY && !rp_present_d(e, p.persist, T[j + 1], ap))
+            leave |= 1u << s;
           double4 pk = make_double4(0.0, 0.0, 0.0, 0.0);
           if (pres) {
             if (e.kind == SG_KIND_AGENT_REPLAY) pk = rp_agent_pose4(e.rows, e.K, tj, EXT_CLAMP);  // agent.py:125-128
@@ -389,6 +400,8 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
               double sn, cs;
               sincos(pk.w, &sn, &cs);
               bb = make_aabb_box(pk.x, pk.y, cs, sn, e.bw, e.bl, e.bcx, e.bcy, c.ox, c.oy);
+              sxy[(size_t)s * CH + tid] = make_double2(pk.x, pk.y);  // for the narrow phase (rp_pair_staged)
+              shc[(size_t)s * CH + tid] = make_double2(cs, sn);
             }
           }
           if (need_coll) aabb[(size_t)s * CH + tid] = bb;
@@ -397,18 +410,18 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
           for (int off = 16; off > 0; off >>= 1) inc += __shfl_xor_sync(0xffffffffu, inc, off);
           if (lane == 0) part[warp * M + s] = inc;
         }
-        // pair sweep on the conservative AABBs, exact narrow phase on the survivors
+        // pair sweep on the conservative AABBs, narrow phase on the survivors (from the staged poses)
         uint32_t cb = 0, en = 0, fp = 0x7fffffffu, term = 0;
         int np = 0;
         if (need_coll && valid) {
-          for (int a = 0; a < M; ++a) {
+          for (int a = 0; a < ML; ++a) {
             if (!((pm >> a) & 1)) continue;
             const float4 A = aabb[(size_t)a * CH + tid];
-            for (int b = a + 1; b < M; ++b) {
+            for (int b = a + 1; b < ML; ++b) {
               if (!((pm >> b) & 1)) continue;
               const float4 B = aabb[(size_t)b * CH + tid];
               if (!(A.x <= B.z && B.x <= A.z && A.y <= B.w && B.y <= A.w)) continue;
-              if (!rp_pair_exact(&sc, c, a, b, tj)) continue;
+              if (!rp_pair_staged(desc, sxy, shc, a, b, tid)) continue;
               ++np;
               fp = min(fp, ((uint32_t)a << 16) | (uint32_t)b);
               cb |= (1u << a) | (1u << b);
@@ -477,13 +490,10 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
     }
     // State rows of a slot that is present after tick j but not after the next one
     if (valid && !(end_here && j == nv)) {
-      const double tj = T[j], tkm = T[j - 1], tkn = T[j + 1];
-      for (int s = 0; s < M; ++s) {
-        const RpDesc e = desc[s];
-        const bool ap = apres[s] != 0;
-        if (e.kind != SG_KIND_EMPTY && e.kind != SG_KIND_AGENT_REPLAY && rp_present_d(e, p.persist, tj, ap) &&
-            !rp_present_d(e, p.persist, tkn, ap))
-          rp_write_rows(&sc, &p, &st, c, s, ap, tj, tkm, first_chunk && j == 1);
+      const double tj = T[j], tkm = T[j - 1];
+      for (uint32_t lv = leave; lv; lv &= lv - 1) {
+        const int s = __ffs(lv) - 1;
+        rp_write_rows(&sc, &p, &st, c, s, apres[s] != 0, tj, tkm, first_chunk && j == 1);
       }
     }
     if (end_here) {
@@ -514,7 +524,7 @@ sg_replay_kernel(const __grid_constant__ SgScene sc, const __grid_constant__ SgP
               if (!((pm >> b) & 1)) continue;
               const float4 B = aabb[(size_t)b * CH + tid];
               if (!(A.x <= B.z && B.x <= A.z && A.y <= B.w && B.y <= A.w)) continue;
-              if (!rp_pair_exact(&sc, c, a, b, tj)) continue;
+              if (!rp_pair_staged(desc, sxy, shc, a, b, tid)) continue;
               rows[a] |= 1u << b;
               rows[b] |= 1u << a;
             }
@@ -572,7 +582,7 @@ static size_t replay_smem_bytes(int M) {
   const int CH = SG_RP_THREADS, TS = SG_RP_TPC + 2;
   size_t o = (size_t)(6 * TS + SG_RP_WARPS * M + M + (M & 1)) * sizeof(double);
   o += (size_t)M * sizeof(RpDesc);
-  o += (size_t)M * CH * sizeof(float4);
+  o += (size_t)M * CH * (sizeof(float4) + 2 * sizeof(double2));
   o += (size_t)TS * 4 * sizeof(uint32_t);
   o += (size_t)((M + 15) / 16) * 16;
   o += sizeof(RpCarry) + 16;
