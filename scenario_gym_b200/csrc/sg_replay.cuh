@@ -38,13 +38,45 @@ struct RpUnion {  // position of a time in the scenario's union-knot table
   double w1, w0;
 };
 
+// min(max(search_left(x, stride, K, t), 1), K - 1) for K >= 2, started from where t would sit if the knots
+// were evenly spaced (x0 = x[0], xN = x[K - 1]): recorded trajectories mostly are, and then two probes replace
+// the log2(K) dependent loads of the bisection.  A wrong guess costs three more probes and then bisects the
+// side of the guess the answer is on -- the result is the bisection's for any knot sequence.
+SG_DEV int rp_search_guess(const double* __restrict__ x, int stride, int K, double t, double x0, double xN) {
+  const float span = (float)(xN - x0);
+  int g = 1;
+  if (span > 0.f) g = 1 + (int)((float)(t - x0) * (float)(K - 1) / span);
+  g = min(max(g, 1), K - 1);
+  if (__ldg(x + (int64_t)(g - 1) * stride) < t) {  // the answer is >= g
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+      if (g >= K - 1 || !(__ldg(x + (int64_t)g * stride) < t)) return g;
+      ++g;
+    }
+    int lo = g, hi = K;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(x + (int64_t)mid * stride) < t) lo = mid + 1; else hi = mid;
+    }
+    return min(lo, K - 1);
+  }
+  int lo = 0, hi = g - 1;  // x[g - 1] >= t: the first such index is in [0, g - 1]
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(x + (int64_t)mid * stride) < t) lo = mid + 1; else hi = mid;
+  }
+  return max(lo, 1);
+}
+
 SG_DEV RpUnion rp_union_weights(const double* __restrict__ ts, int UK, double t) {
   RpUnion u;
   u.mode = 0; u.cur = 1; u.w1 = 0.0; u.w0 = 0.0;
-  if (UK <= 0 || t < __ldg(ts)) return u;  // fill_value = (X[0], X[-1]), entity/batch.py:120-127
-  if (t > __ldg(ts + UK - 1)) { u.mode = 1; return u; }
+  if (UK <= 0) return u;
+  const double t_first = __ldg(ts), t_last = __ldg(ts + UK - 1);
+  if (t < t_first) return u;  // fill_value = (X[0], X[-1]), entity/batch.py:120-127
+  if (t > t_last) { u.mode = 1; return u; }
   u.mode = 2;
-  u.cur = min(max(search_left(ts, 1, UK, t), 1), UK - 1);
+  u.cur = UK >= 2 ? rp_search_guess(ts, 1, UK, t, t_first, t_last) : min(max(search_left(ts, 1, UK, t), 1), UK - 1);
   const double x_lo = __ldg(ts + u.cur - 1), x_hi = __ldg(ts + u.cur);
   u.w1 = (t - x_lo) / (x_hi - x_lo);
   u.w0 = (x_hi - t) / (x_hi - x_lo);
@@ -148,7 +180,8 @@ static __device__ __noinline__ void rp_write_rows(const SgScene* sc, const SgPar
 
 // out-of-line so that the tick loop carries one copy of the control-point search
 static __device__ __noinline__ double4 rp_agent_pose4(const double* rows, int K, double t, int mode) {
-  int cur = 0;
+  int cur = 0;  // (position_at_t verifies the cursor it is given: two probes when it is the answer)
+  if (K >= 2) cur = rp_search_guess(rows, 7, K, t, __ldg(rows), __ldg(rows + (int64_t)(K - 1) * 7));
   double full[6];
   position_at_t(rows, K, t, mode, cur, full);
   return make_double4(full[0], full[1], full[2], full[3]);
