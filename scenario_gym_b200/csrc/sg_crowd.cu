@@ -6,23 +6,25 @@
 // else goes to the general kernel, whose results this kernel reproduces bit for bit (it calls the
 // same device functions for the arithmetic; tests/test_gpu_parity.py::test_crowd_cell_grid).
 //
-// Mapping.  One scenario = one CTA of 512 threads; a thread owns EPT = 1 or 2 entity slots
-// (s, s + 512).  Two such CTAs share an SM (64 registers per thread, <= 113 KB of shared memory
-// each), so the barrier phases of one scenario are covered by the other scenario's work -- a
-// 1024-thread CTA per SM spends its time waiting at its own barriers.  The State rows that other
-// threads read (x, y, vx, vy: the pedestrians' sensors) live in shared memory, single-buffered:
-//   A  sensors + behaviour: neighbours listed by last tick's phase C, social force (neighbour terms
-//      pooled per warp, summed in state.poses order) -> force per slot
-//   -- barrier --
-//   B  controller + State.step on the thread's own rows (in place), cos/sin of the heading; the
-//      owner inserts its slots into the cell grid of the NEW positions (linked lists)
-//   C  every slot gathers the ids listed in the 3 x 3 cells around it into a private strip of shared
-//      memory (a light, ragged walk), then runs the candidate tests over the strip: next tick's sensor
-//      list (pedestrians within r) and this tick's collision broad phase by inscribed / circumscribed
-//      circles -- colliding for sure, apart for sure, or queued
-//   D  separating-axis filter / exact closed-set predicate on the queued pairs, one pair per thread,
-//      corners recomputed from the rows with the reference's expression (entity/base.py:100-138)
-//   E  terminal conditions, CollisionMetric rising edges, ego metrics.
+// Mapping.  One scenario = one CTA: 1024 threads, a slot each, one CTA per SM at 64 registers (scenes of
+// up to 512 slots: 512 threads at 128 registers).  The State rows other threads read (x, y, vx, vy), the
+// flags and the heads of the cell grid are double-buffered in shared memory, so a tick needs two CTA
+// barriers:
+//   step phase       sensors + behaviour -- neighbours listed by last tick's candidate phase, social force
+//                    (neighbour terms pooled per warp, summed in state.poses order) -- then controller +
+//                    State.step on the thread's own row (written to the other buffer), cos / sin of the
+//                    heading; the owner inserts its slot into the cell grid of the NEW positions (linked
+//                    lists) while the grid the last candidate phase read is cleared
+//   -- barrier: rows, flags and grid of the new positions complete --
+//   candidate phase  every slot gathers the ids listed in the 3 x 3 cells around it into a private strip of
+//                    shared memory (a light, ragged walk), then runs the candidate tests over the strip:
+//                    next tick's sensor list (pedestrians within r) and this tick's collision broad phase by
+//                    inscribed / circumscribed circles -- colliding for sure, apart for sure, or queued on
+//                    the warp's own pair queue, which the same warp then drains (separating-axis filter /
+//                    exact closed-set predicate, corners recomputed from the rows with the reference's
+//                    expression, entity/base.py:100-138)
+//   -- barrier: pairs booked --
+//   epilogue         terminal conditions, CollisionMetric rising edges, ego metrics.
 #define SG_FLAT_BOXES 1  // boxes without area follow their own narrow-phase rules (sg_common.cuh)
 #include "sg_common.cuh"
 #include "sg_internal.h"
