@@ -750,9 +750,14 @@ def api_records(bench, n_fused: int = 4096, n_host: int = 64) -> dict:
         t_get = time.perf_counter() - t0
         ms = ms if isinstance(ms, list) else [ms]
         ok = all(abs(m["ego_avg_speed"] - want[n]) <= 1e-9 * max(1.0, abs(want[n])) for m, n in zip(ms, order))
+        t0 = time.perf_counter()
+        arr = gym.get_metric_arrays()  # the batch-wide form of the device metrics (no per-scenario Python)
+        t_arr = time.perf_counter() - t0
+        ok = ok and all(arr["ego_avg_speed"][k] == m["ego_avg_speed"] for k, m in enumerate(ms))
         steps = sum(per[n] for n in order)
         out[tag] = {"scenarios": n_scen, "entity_steps": steps, "value": steps / (t_roll + t_get), "unit": UNIT,
                     "ms_set_scenarios": 1e3 * t_set, "ms_rollout": 1e3 * t_roll, "ms_get_metrics": 1e3 * t_get,
+                    "ms_get_metric_arrays": 1e3 * t_arr, "value_with_metric_arrays": steps / (t_roll + t_arr),
                     "metrics_match_reference_goldens": bool(ok),
                     "path": "ScenarioGym.set_scenarios -> rollout -> get_metrics" +
                             ("" if tag == "fused" else " with a custom host Metric (per-tick host mode)")}

@@ -279,6 +279,32 @@ class ScenarioGym:
                 metric._n = 0
         return out[0] if len(out) == 1 else out
 
+    def get_metric_arrays(self) -> Dict[str, np.ndarray]:
+        """
+        The device-side metrics of the whole batch as arrays indexed by scenario -- what ``get_metrics()`` reports
+        scenario by scenario (a Python loop: ~4 us per scenario and metric), read back once.  Keys follow
+        ``get_metrics()``: ``ego_avg_speed``, ``ego_max_speed``, ``ego_distance_travelled``,
+        ``RSS_safe_longitudinal`` / ``RSS_safe_lateral``; ``CollisionMetric`` gives ``collisions_count`` and the
+        batch's ``collisions_events`` records (scenario, tick, slot, t; ``slot_entities(n)[slot]`` is the hazard).
+        Host-side (custom) metrics have no array
+        form and are left to ``get_metrics()``.
+        """
+        if self._engine is None:
+            return {}
+        self._cache = {}
+        out: Dict[str, np.ndarray] = {}
+        for metric in self.metrics:
+            if isinstance(metric, _DeviceMetric):
+                try:
+                    out.update(metric._arrays(self))
+                except NotImplementedError:
+                    pass
+        return out
+
+    def slot_entities(self, n: int = 0) -> List[Entity]:
+        """The entities of scenario ``n`` in device slot order (agents first): what a ``slot`` index refers to."""
+        return list(self._entity_of[n])
+
     def close(self) -> None:
         pass
 

@@ -541,6 +541,10 @@ class _DeviceMetric(Metric):
             self._pull(self._gym, self._n)
         return self._value
 
+    def _arrays(self, gym) -> Dict[str, np.ndarray]:
+        """The metric over the whole batch as arrays indexed by scenario (ScenarioGym.get_metric_arrays)."""
+        raise NotImplementedError
+
 
 class EgoAvgSpeed(_DeviceMetric):
     """Time-weighted average ego speed (reference metrics/trajectory.py:8-28)."""
@@ -550,6 +554,9 @@ class EgoAvgSpeed(_DeviceMetric):
     def _pull(self, gym, n):
         self._value = float(gym._fetch("ego_avg_speed")[n])
 
+    def _arrays(self, gym):
+        return {self.name: gym._fetch("ego_avg_speed").copy()}
+
 
 class EgoMaxSpeed(_DeviceMetric):
     name = "ego_max_speed"
@@ -557,12 +564,18 @@ class EgoMaxSpeed(_DeviceMetric):
     def _pull(self, gym, n):
         self._value = float(gym._fetch("ego_max_speed")[n])
 
+    def _arrays(self, gym):
+        return {self.name: gym._fetch("ego_max_speed").copy()}
+
 
 class EgoDistanceTravelled(_DeviceMetric):
     name = "ego_distance_travelled"
 
     def _pull(self, gym, n):
         self._value = float(gym._fetch("ego_dist")[n])
+
+    def _arrays(self, gym):
+        return {self.name: gym._fetch("ego_dist").copy()}
 
 
 class CollisionMetric(_DeviceMetric):
@@ -585,6 +598,13 @@ class CollisionMetric(_DeviceMetric):
     def get_state(self):
         super().get_state()
         return list(self._value or [])
+
+    def _arrays(self, gym):
+        # the batch's rising edges as one record array (scenario, tick, slot, t), sorted by scenario, and how many
+        # each scenario has; `slot` indexes ScenarioGym.slot_entities(n)
+        ev = gym._engine.events()
+        counts = np.bincount(ev["scenario"], minlength=len(gym.states)).astype(np.int64)
+        return {f"{self.name}_events": ev, f"{self.name}_count": counts}
 
 
 class RSSParameters:
@@ -623,6 +643,10 @@ class RSS(_DeviceMetric):
     def _pull(self, gym, n):
         flags = int(gym._fetch("rss_flags")[n])
         self._value = {"safe_longitudinal": not (flags & 1), "safe_lateral": not (flags & 2)}
+
+    def _arrays(self, gym):
+        flags = gym._fetch("rss_flags")
+        return {f"{self.name}_safe_longitudinal": (flags & 1) == 0, f"{self.name}_safe_lateral": (flags & 2) == 0}
 
 
 def cache_metric(Met: Type[Metric]) -> Type[Metric]:

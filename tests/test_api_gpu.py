@@ -102,6 +102,26 @@ def test_batched_equals_single():
         assert single.get_metrics() == m, name
 
 
+def test_metric_arrays_equal_get_metrics():
+    """get_metric_arrays(): the batch's device metrics as arrays == get_metrics() scenario by scenario."""
+    scs = golden_scenarios()
+    gym = ScenarioGym(metrics=std_metrics())
+    gym.set_scenarios([sc for _, sc, _ in scs] * 2)
+    gym.rollout()
+    per = gym.get_metrics()
+    arr = gym.get_metric_arrays()
+    assert set(arr) == {"collisions_events", "collisions_count", "ego_avg_speed", "ego_max_speed",
+                        "ego_distance_travelled"}
+    ev = arr["collisions_events"]
+    assert len(ev) == int(arr["collisions_count"].sum()) and np.all(np.diff(ev["scenario"]) >= 0)
+    for n, m in enumerate(per):
+        for k in ("ego_avg_speed", "ego_max_speed", "ego_distance_travelled"):
+            assert arr[k][n] == m[k], (n, k)
+        mine = ev[ev["scenario"] == n]
+        ents = gym.slot_entities(n)
+        assert [(float(e["t"]), ents[int(e["slot"])].ref) for e in mine] == [(t, ref) for t, ref, _ in m["collisions"]]
+
+
 def test_head_on_collision():
     """reference tests/test_utils.py:12-61: two 5x2 boxes head on; no collision at reset, collision at the end."""
     ce = CatalogEntry("car", "car", "car", "car", BoundingBox(2.0, 5.0, 0.0, 0.0))
