@@ -1238,6 +1238,38 @@ SG_DEV int sat_classify(const double* A, const double* B) {
   return apart ? -1 : (inside ? 1 : 0);
 }
 
+// Separating-axis classification of two boxes from centre + half-edge vectors (the quantities sat_classify
+// derives from the corners, taken from the staged pose instead): +1 intersect, -1 disjoint, 0 too close to
+// call.  Every gap is compared with a tolerance of 1e-9 relative to the coordinates involved -- seven orders
+// of magnitude above the rounding error of these expressions AND of the reference's corner formula -- so a
+// +-1 answer is the exact closed-set answer for the fp64 corners; 0 sends the pair to the exact predicate.
+struct Obb {
+  double cx, cy, ux, uy, vx, vy;  // centre, half-length vector, half-width vector
+};
+SG_DEV int sat_classify_obb(const Obb& A, const Obb& B) {
+  const double dx = B.cx - A.cx, dy = B.cy - A.cy;
+  const double scale = fabs(A.cx) + fabs(A.cy) + fabs(B.cx) + fabs(B.cy) + fabs(A.ux) + fabs(A.uy) + fabs(A.vx) +
+                       fabs(A.vy) + fabs(B.ux) + fabs(B.uy) + fabs(B.vx) + fabs(B.vy);
+  const double rel = 1e-9 * scale;
+  bool apart = false, inside = true;
+#define SG_OBB_AXIS(ax, ay)                                                                              \
+  {                                                                                                     \
+    const double gap = fabs(dx * (ax) + dy * (ay)) -                                                    \
+                       (fabs(A.ux * (ax) + A.uy * (ay)) + fabs(A.vx * (ax) + A.vy * (ay)) +             \
+                        fabs(B.ux * (ax) + B.uy * (ay)) + fabs(B.vx * (ax) + B.vy * (ay)));             \
+    const double tol = rel * (fabs(ax) + fabs(ay));                                                     \
+    apart = apart || gap > tol;                                                                         \
+    inside = inside && gap < -tol;                                                                      \
+  }
+  SG_OBB_AXIS(A.ux, A.uy)
+  SG_OBB_AXIS(A.vx, A.vy)
+  SG_OBB_AXIS(B.ux, B.uy)
+  SG_OBB_AXIS(B.vx, B.vy)
+#undef SG_OBB_AXIS
+  if (!(fabs(dx) + fabs(dy) > rel)) return 0;  // (nearly) coincident boxes: `g != g_prime` is the exact path's call
+  return apart ? -1 : (inside ? 1 : 0);
+}
+
 SG_DEV void record_pair(const PairSink& k, unsigned corners_sh, const int8_t* orient, int G, int a, int b) {
   if (pair_collides(corners_sh, orient, G, a, b)) commit_pair(k, a, b);
 }

@@ -176,6 +176,19 @@ SG_DEV void crowd_corners(const double* __restrict__ state, const double* __rest
   q[6] = x + (hx0 * cs + hy1 * -sn); q[7] = y + (hx0 * sn + hy1 * cs);
 }
 
+// centre and half-edge vectors of slot s's box for the separating-axis filter (sat_classify_obb)
+SG_DEV Obb crowd_obb(const double* __restrict__ state, const double* __restrict__ hcs, const double* __restrict__ box,
+                     int64_t nm, int64_t i0, int G, int s) {
+  const double x = state[s], y = state[G + s], cs = hcs[s], sn = hcs[G + s];
+  const double hw = 0.5 * __ldg(box + i0 + s), hl = 0.5 * __ldg(box + nm + i0 + s);
+  const double bcx = __ldg(box + 2 * nm + i0 + s), bcy = __ldg(box + 3 * nm + i0 + s);
+  Obb o;
+  o.cx = x + (bcx * cs - bcy * sn); o.cy = y + (bcx * sn + bcy * cs);
+  o.ux = hl * cs; o.uy = hl * sn;
+  o.vx = -hw * sn; o.vy = hw * cs;
+  return o;
+}
+
 // exact narrow phase of one pair (`g != g_prime` exclusion of reference utils.py:58, then the closed-set
 // predicate on the corners); only reached for knife-edge contacts
 static __device__ __noinline__ bool crowd_pair_exact(const double* __restrict__ state, const double* __restrict__ hcs,
@@ -197,10 +210,8 @@ static __device__ __noinline__ bool crowd_pair_exact(const double* __restrict__ 
 static __device__ __noinline__ bool crowd_pair_collides(const double* __restrict__ state, const double* __restrict__ hcs,
                                                         const double* __restrict__ box, int64_t nm, int64_t i0,
                                                         const int8_t* __restrict__ orient, int G, int a, int b) {
-  double qa[8], qb[8];
-  crowd_corners(state, hcs, box, nm, i0, G, a, qa);
-  crowd_corners(state, hcs, box, nm, i0, G, b, qb);
-  const int v = sat_classify(qa, qb);
+  const Obb A = crowd_obb(state, hcs, box, nm, i0, G, a), B = crowd_obb(state, hcs, box, nm, i0, G, b);
+  const int v = sat_classify_obb(A, B);
   if (v != 0) return v > 0;
   return crowd_pair_exact(state, hcs, box, nm, i0, orient, G, a, b);
 }

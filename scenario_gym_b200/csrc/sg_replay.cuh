@@ -212,46 +212,14 @@ SG_DEV void rp_corners_staged(const RpDesc& e, double2 xy, double2 hc, double q[
   q[6] = x + (hx0 * cs + hy1 * -sn); q[7] = y + (hx0 * sn + hy1 * cs);
 }
 
-// Separating-axis classification of two boxes from centre + half-edge vectors (the quantities sat_classify
-// derives from the corners, taken from the staged pose instead): +1 intersect, -1 disjoint, 0 too close to
-// call.  Every gap is compared with a tolerance of 1e-9 relative to the coordinates involved -- seven orders
-// of magnitude above the rounding error of these expressions AND of the reference's corner formula -- so a
-// +-1 answer is the exact closed-set answer for the fp64 corners; 0 sends the pair to the exact predicate.
-struct RpObb {
-  double cx, cy, ux, uy, vx, vy;  // centre, half-length vector, half-width vector
-};
-SG_DEV RpObb rp_obb(const RpDesc& e, double2 xy, double2 hc) {
-  RpObb o;
+SG_DEV Obb rp_obb(const RpDesc& e, double2 xy, double2 hc) {
+  Obb o;
   const double cs = hc.x, sn = hc.y, hl = 0.5 * e.bl, hw = 0.5 * e.bw;
   o.cx = xy.x + (e.bcx * cs - e.bcy * sn); o.cy = xy.y + (e.bcx * sn + e.bcy * cs);
   o.ux = hl * cs; o.uy = hl * sn;
   o.vx = -hw * sn; o.vy = hw * cs;
   return o;
 }
-SG_DEV int rp_sat_obb(const RpObb& A, const RpObb& B) {
-  const double dx = B.cx - A.cx, dy = B.cy - A.cy;
-  const double scale = fabs(A.cx) + fabs(A.cy) + fabs(B.cx) + fabs(B.cy) + fabs(A.ux) + fabs(A.uy) + fabs(A.vx) +
-                       fabs(A.vy) + fabs(B.ux) + fabs(B.uy) + fabs(B.vx) + fabs(B.vy);
-  const double rel = 1e-9 * scale;
-  bool apart = false, inside = true;
-#define SG_RP_AXIS(ax, ay)                                                                              \
-  {                                                                                                     \
-    const double gap = fabs(dx * (ax) + dy * (ay)) -                                                    \
-                       (fabs(A.ux * (ax) + A.uy * (ay)) + fabs(A.vx * (ax) + A.vy * (ay)) +             \
-                        fabs(B.ux * (ax) + B.uy * (ay)) + fabs(B.vx * (ax) + B.vy * (ay)));             \
-    const double tol = rel * (fabs(ax) + fabs(ay));                                                     \
-    apart = apart || gap > tol;                                                                         \
-    inside = inside && gap < -tol;                                                                      \
-  }
-  SG_RP_AXIS(A.ux, A.uy)
-  SG_RP_AXIS(A.vx, A.vy)
-  SG_RP_AXIS(B.ux, B.uy)
-  SG_RP_AXIS(B.vx, B.vy)
-#undef SG_RP_AXIS
-  if (!(fabs(dx) + fabs(dy) > rel)) return 0;  // (nearly) coincident boxes: `g != g_prime` is the exact path's call
-  return apart ? -1 : (inside ? 1 : 0);
-}
-
 // narrow phase of one AABB-surviving pair of a tick (state/utils.py:10-49, utils.py:28-62) from the poses the
 // slot loop staged in shared memory: nothing is re-read from global memory, no control-point search, no
 // second sincos.  The branch-free separating-axis filter decides all but knife-edge contacts; those (and
@@ -271,9 +239,9 @@ static __device__ __noinline__ bool rp_pair_exact_staged(const RpDesc* desc, con
   return quads_intersect(A, ha ? ha : quad_orientation(A), B, hb ? hb : quad_orientation(B));
 }
 SG_DEV bool rp_pair_staged(const RpDesc* desc, const double2* xy, const double2* hc, int a, int b, int col) {
-  const RpObb A = rp_obb(desc[a], xy[a * SG_RP_THREADS + col], hc[a * SG_RP_THREADS + col]);
-  const RpObb B = rp_obb(desc[b], xy[b * SG_RP_THREADS + col], hc[b * SG_RP_THREADS + col]);
-  const int v = rp_sat_obb(A, B);
+  const Obb A = rp_obb(desc[a], xy[a * SG_RP_THREADS + col], hc[a * SG_RP_THREADS + col]);
+  const Obb B = rp_obb(desc[b], xy[b * SG_RP_THREADS + col], hc[b * SG_RP_THREADS + col]);
+  const int v = sat_classify_obb(A, B);
   if (v != 0) return v > 0;
   return rp_pair_exact_staged(desc, xy, hc, a, b, col);
 }
