@@ -382,7 +382,7 @@ int64_t sg_host_d2h_bytes(const SgScene* h) {
 }
 
 // streams + events of the host-buffer path, one set per device (created on first use)
-#define SG_HOST_MAX_WINDOWS 4
+#define SG_HOST_MAX_WINDOWS 6
 struct HostPathCtx {
   cudaStream_t copy_stream, aux_stream;
   cudaEvent_t ev_copy[2], ev_done, ev_win[SG_HOST_MAX_WINDOWS], ev_aux;
@@ -413,9 +413,14 @@ static int host_ctx(int device, HostPathCtx** out) {
 // How many windows a batch without an action table is uploaded and rolled out in: the first one small,
 // so the rollout starts early, the upload of every later window hidden behind the rollout of the one
 // before.  SG_HOST_WINDOWS=<n> (1 .. 4) overrides the choice (1: one upload, then one rollout).
+// replay-only scenes: a rollout costs less than its upload (C2: 115 MB of control points against a 1 ms kernel)
+static bool host_upload_bound(const SgScene* hs) {
+  const uint32_t replay_bits = (1u << SG_KIND_EMPTY) | (1u << SG_KIND_REPLAY) | (1u << SG_KIND_AGENT_REPLAY);
+  return hs->kind_mask != 0 && !(hs->kind_mask & ~replay_bits);
+}
 static int host_windows(const SgScene* hs, int64_t scene_bytes) {
   const char* env = getenv("SG_HOST_WINDOWS");
-  int n = (scene_bytes >= (8 << 20) && hs->n_scenarios >= 64) ? 3 : 1;
+  int n = (scene_bytes >= (8 << 20) && hs->n_scenarios >= 64) ? (host_upload_bound(hs) ? 5 : 3) : 1;
   if (env && env[0] >= '1' && env[0] <= '0' + SG_HOST_MAX_WINDOWS && !env[1]) n = env[0] - '0';
   if (n > hs->n_scenarios) n = hs->n_scenarios;
   return n < 1 ? 1 : n;
@@ -450,8 +455,13 @@ int sg_rollout_host(const SgScene* hs, const SgScene* ds, const SgParams* params
     SG_CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_done, 0), "cudaStreamWaitEvent");
     int bounds[SG_HOST_MAX_WINDOWS + 1];
     bounds[0] = 0;
-    for (int w = 1; w <= nwin; ++w)  // windows end at 1/8, 1/2, 1 of the batch (three windows): each four times the last
-      bounds[w] = w == nwin ? (int)N : (int)(N >> (2 * (nwin - w) - 1));
+    // Compute-bound batches: windows end at 1/8, 1/2, 1 of the batch (three windows), each four times the last --
+    // the first rollout starts early and the uploads hide behind the rollouts.  Upload-bound batches (replay-only
+    // scenes): what cannot hide is the LAST window's rollout, so the windows end at 1/8, 3/8, 5/8, 7/8, 1.
+    const bool even = host_upload_bound(hs) && nwin >= 3;
+    for (int w = 1; w <= nwin; ++w)
+      bounds[w] = w == nwin ? (int)N
+                            : even ? (int)(N * (2 * w - 1) / (2 * (nwin - 1))) : (int)(N >> (2 * (nwin - w) - 1));
     bool used_aux = false;
     for (int w = 0; w < nwin; ++w) {
       const int n0 = bounds[w], n1 = bounds[w + 1];
