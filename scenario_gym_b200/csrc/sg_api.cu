@@ -308,10 +308,16 @@ static SgState state_window(const SgState& s, const SgParams& p, int n0, int M) 
 
 // Host -> device copies of scenarios [n0, n1) of a scene (`shared`: also the arrays all scenarios share,
 // the road networks).  With `do_copy` false only the bytes are counted.  Returns 0 or an error code.
+// `part`: 0 = every array of scenarios [n0, n1); 1 = the per-slot / per-scenario arrays of the WHOLE batch and the
+// control points / knot tables of [n0, n1); 2 = the control points / knot tables of [n0, n1) only.  (Upload-bound
+// batches: the small arrays go up once with the first window instead of a dozen small copies per window.)
 static int copy_scene_window(const SgScene* h, const SgScene* d, int n0, int n1, bool shared, bool do_copy,
-                             cudaStream_t s, int64_t* bytes) {
-  const int64_t N = h->n_scenarios, M = h->n_slots, NM = N * M, o = (int64_t)n0 * M, cnt = (int64_t)(n1 - n0) * M;
-  const int ns = n1 - n0;
+                             cudaStream_t s, int64_t* bytes, int part = 0) {
+  const int64_t N = h->n_scenarios, M = h->n_slots, NM = N * M;
+  const int m0 = part == 1 ? 0 : n0, m1 = part == 1 ? (int)N : n1;  // the scenarios whose small arrays go up
+  const int64_t o = (int64_t)m0 * M, cnt = part == 2 ? 0 : (int64_t)(m1 - m0) * M;
+  const int ns = part == 2 ? 0 : m1 - m0;
+  const int64_t bo = (int64_t)n0 * M, bcnt = (int64_t)(n1 - n0) * M;  // the slots whose control points go up
   int64_t total = 0;
   cudaError_t err = cudaSuccess;
   auto flat = [&](const void* src, const void* dst, int64_t first, int64_t n, int64_t esz) -> bool {
@@ -334,13 +340,15 @@ static int copy_scene_window(const SgScene* h, const SgScene* d, int n0, int n1,
     if (err != cudaSuccess) { set_err("cudaMemcpy2DAsync H2D scene", err); return false; }
     return true;
   };
-  bool ok = planes(h->kind, d->kind, 1, 1) && planes(h->etype, d->etype, 1, 1) && planes(h->box, d->box, 4, 8) &&
-            flat(h->traj_off, d->traj_off, o, cnt + 1, 8) && planes(h->veh_limits, d->veh_limits, 4, 8) &&
-            flat(h->union_off, d->union_off, n0, ns + 1, 8) && flat(h->t0, d->t0, n0, ns, 8) &&
-            flat(h->length, d->length, n0, ns, 8) && flat(h->ego_slot, d->ego_slot, n0, ns, 4) &&
-            flat(h->first_slot, d->first_slot, n0, ns, 4);
+  bool ok = true;
+  if (part != 2)
+    ok = planes(h->kind, d->kind, 1, 1) && planes(h->etype, d->etype, 1, 1) && planes(h->box, d->box, 4, 8) &&
+         flat(h->traj_off, d->traj_off, o, cnt + 1, 8) && planes(h->veh_limits, d->veh_limits, 4, 8) &&
+         flat(h->union_off, d->union_off, m0, ns + 1, 8) && flat(h->t0, d->t0, m0, ns, 8) &&
+         flat(h->length, d->length, m0, ns, 8) && flat(h->ego_slot, d->ego_slot, m0, ns, 4) &&
+         flat(h->first_slot, d->first_slot, m0, ns, 4);
   if (ok && h->traj_off && h->traj_rows) {
-    const int64_t r0 = h->traj_off[o], r1 = h->traj_off[o + cnt];
+    const int64_t r0 = h->traj_off[bo], r1 = h->traj_off[bo + bcnt];
     ok = flat(h->traj_rows, d->traj_rows, r0 * 7, (r1 - r0) * 7, 8);
   }
   if (ok && h->union_off && h->n_union_rows > 0) {
@@ -349,14 +357,15 @@ static int copy_scene_window(const SgScene* h, const SgScene* d, int n0, int n1,
   }
   // (kind_mask: OR of 1 << kind over the slots, 0 = not stated) pedestrian rows are only read for pedestrians
   if (ok && (h->kind_mask == 0 || (h->kind_mask & (1u << SG_KIND_PEDESTRIAN)))) {
-    ok = planes(h->ped_speed_desired, d->ped_speed_desired, 1, 8) && flat(h->route_off, d->route_off, o, cnt + 1, 8);
+    if (part != 2)
+      ok = planes(h->ped_speed_desired, d->ped_speed_desired, 1, 8) && flat(h->route_off, d->route_off, o, cnt + 1, 8);
     if (ok && h->route_off && h->route_xy) {
-      const int64_t r0 = h->route_off[o], r1 = h->route_off[o + cnt];
+      const int64_t r0 = h->route_off[bo], r1 = h->route_off[bo + bcnt];
       ok = flat(h->route_xy, d->route_xy, r0 * 2, (r1 - r0) * 2, 8);
     }
   }
-  if (ok && h->n_networks > 0) {
-    ok = flat(h->rn_of, d->rn_of, n0, ns, 4);
+  if (ok && h->n_networks > 0 && part != 2) {
+    ok = flat(h->rn_of, d->rn_of, m0, ns, 4);
     if (ok && shared)
       ok = flat(h->rn_poly_off, d->rn_poly_off, 0, 3 * (int64_t)h->n_networks + 1, 8) &&
            flat(h->rn_edge_off, d->rn_edge_off, 0, h->n_rn_polys + 1, 8) &&
@@ -466,7 +475,7 @@ int sg_rollout_host(const SgScene* hs, const SgScene* ds, const SgParams* params
     for (int w = 0; w < nwin; ++w) {
       const int n0 = bounds[w], n1 = bounds[w + 1];
       if (n1 <= n0) continue;
-      rc = copy_scene_window(hs, ds, n0, n1, w == 0, true, ctx->copy_stream, nullptr);
+      rc = copy_scene_window(hs, ds, n0, n1, w == 0, true, ctx->copy_stream, nullptr, even ? (w == 0 ? 1 : 2) : 0);
       if (rc) return rc;
       SG_CK(cudaEventRecord(ctx->ev_win[w], ctx->copy_stream), "cudaEventRecord");
       cudaStream_t cs = (w & 1) ? ctx->aux_stream : s;
