@@ -384,7 +384,7 @@ int sg_test_trajectory(const double* rows, int64_t K, const double* t, int64_t n
      device and nothing but the scene crosses PCIe.
    - Without a table the batch is uploaded in windows of scenarios (SgScene.plane_stride) on an internal
      copy stream and every window is reset and rolled out as soon as it has arrived (scenes of 8 MiB or
-     more: three windows ending at 1/8, 1/2, 1 of the batch, or -- replay-only scenes, whose rollout costs
+     more: four windows ending at 1/32, 1/8, 1/2, 1 of the batch (under 4096 scenarios three, from 1/8 on), or -- replay-only scenes, whose rollout costs
      less than their upload -- five ending at 1/8, 3/8, 5/8, 7/8, 1, so that only a small last window's
      rollout is left when the upload ends; the environment variable SG_HOST_WINDOWS = 1 .. 6 overrides the
      number): the results equal the one-piece rollout's bit for bit, the upload hides behind the rollout.

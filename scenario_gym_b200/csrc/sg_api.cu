@@ -429,7 +429,7 @@ static bool host_upload_bound(const SgScene* hs) {
 }
 static int host_windows(const SgScene* hs, int64_t scene_bytes) {
   const char* env = getenv("SG_HOST_WINDOWS");
-  int n = (scene_bytes >= (8 << 20) && hs->n_scenarios >= 64) ? (host_upload_bound(hs) ? 5 : 3) : 1;
+  int n = (scene_bytes >= (8 << 20) && hs->n_scenarios >= 64) ? (host_upload_bound(hs) ? 5 : (hs->n_scenarios >= 4096 ? 4 : 3)) : 1;
   if (env && env[0] >= '1' && env[0] <= '0' + SG_HOST_MAX_WINDOWS && !env[1]) n = env[0] - '0';
   if (n > hs->n_scenarios) n = hs->n_scenarios;
   return n < 1 ? 1 : n;
@@ -464,7 +464,8 @@ int sg_rollout_host(const SgScene* hs, const SgScene* ds, const SgParams* params
     SG_CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_done, 0), "cudaStreamWaitEvent");
     int bounds[SG_HOST_MAX_WINDOWS + 1];
     bounds[0] = 0;
-    // Compute-bound batches: windows end at 1/8, 1/2, 1 of the batch (three windows), each four times the last --
+    // Compute-bound batches: windows end at 1/32, 1/8, 1/2, 1 of the batch (four windows; three from 1/8 on when the
+    // batch has fewer than 4096 scenarios: a first window of a few dozen one-scenario CTAs leaves the GPU idle), each four times the last --
     // the first rollout starts early and the uploads hide behind the rollouts.  Upload-bound batches (replay-only
     // scenes): what cannot hide is the LAST window's rollout, so the windows end at 1/8, 3/8, 5/8, 7/8, 1.
     const bool even = host_upload_bound(hs) && nwin >= 3;
