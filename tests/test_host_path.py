@@ -152,12 +152,13 @@ def _window_cases():
     yield "vehicles with per-agent limits + pair matrix (general kernel)", scene, p, cfg.action_rng
 
 
-@pytest.mark.parametrize("windows", ["2", "3", "4"])
+@pytest.mark.parametrize("windows", ["2", "3", "4", "5", "6"])
 def test_host_path_scenario_windows(windows, monkeypatch):
     """
     sg_rollout_host uploads a batch in windows of scenarios and rolls every window out as it arrives
     (SgScene.plane_stride / scenario_base): every State row, the action stream's draws and the event
-    records must equal the one-piece rollout bit for bit.
+    records must equal the one-piece rollout bit for bit.  (Replay-only batches of three or more windows
+    take the upload-bound policy: even windows, per-slot / per-scenario arrays sent once with the first.)
     """
     from scenario_gym_b200.engine import Engine
     from scenario_gym_b200.hostpath import HostRollout
