@@ -51,7 +51,15 @@ def _batch_data(data: np.ndarray) -> np.ndarray:
 
 def build_union_times(trajs: Sequence[np.ndarray]) -> np.ndarray:
     """The sorted union of all control-point times (entity/batch.py:98-99)."""
-    return np.array(sorted(set(t for data in trajs for t in _batch_data(data)[:, 0])))
+    cols = []
+    for data in trajs:
+        t = np.asarray(data, dtype=np.float64)[:, 0]
+        if not np.isfinite(t).all():
+            t = np.nan_to_num(t)
+        if t.shape[0] == 1:  # (a single control point is held twice, 0.1 s apart: _batch_data)
+            t = np.array([t[0], t[0] + 1e-1])
+        cols.append(t)
+    return np.unique(np.concatenate(cols)) if cols else np.zeros(0)
 
 
 def build_union_table(trajs: Sequence[np.ndarray]):
