@@ -823,12 +823,30 @@ SG_DEV void publish_ego_box(const Grp& c) {
   c.egop[EGO_RHW] = 1.0 / (0.5 * eW); c.egop[EGO_RHL] = 1.0 / (0.5 * eL);
 }
 
+// The norm of a direction that is a unit vector up to rounding (s2 = a^2 + b^2 within 1e-8 of 1) and its
+// reciprocal, without the square-root / reciprocal iterations: sqrt(1 + d) = 1 + d/2 - d^2/8 ..., so 1 + d/2 is
+// the correctly rounded root for |d| < 1e-8 (d = s2 - 1 is exact), and one Newton step on 2 - n gives 1/n to
+// the last bit.  publish_ego is one lane's serial work on the tick's critical path (every other warp of the
+// scenario waits for it at the barrier); the general case falls back to fnorm2 / fast_rcp.
+SG_DEV void unit_norm(double a, double b, double& nn, double& rn) {
+  const double s2 = a * a + b * b, d = s2 - 1.0;
+  if (fabs(d) < 1e-8) {
+    nn = 1.0 + 0.5 * d;
+    const double r0 = 2.0 - nn, e = __fma_rn(-nn, r0, 1.0);
+    rn = __fma_rn(r0, e, r0);
+  } else {
+    nn = fast_sqrt(s2);
+    rn = fast_rcp(nn);
+  }
+}
+
 // ego parameters in its own frame (reference metrics/rss/callback.py:73-97, 340-386)
 SG_DEV void publish_ego(const Grp& c, bool present, double x, double y, double ec, double es,
                         double vx, double vy) {
   double einv[2];
   {  // inverse_direction((cos h, sin h)), rss_utils.py:7-21
-    const double nn = fnorm2(es, ec), rn = fast_rcp(nn);
+    double nn, rn;
+    unit_norm(es, ec, nn, rn);
     einv[0] = div_r(es, nn, rn);
     einv[1] = div_r(-ec, nn, rn);
   }
@@ -840,7 +858,8 @@ SG_DEV void publish_ego(const Grp& c, bool present, double x, double y, double e
   E[EGO_HD0] = hd[0]; E[EGO_HD1] = hd[1];
   double hinv[2];  // inverse_direction(ego-frame heading): used by safe_lateral_distance
   {
-    const double nn = fnorm2(hd[1], hd[0]), rn = fast_rcp(nn);
+    double nn, rn;
+    unit_norm(hd[1], hd[0], nn, rn);
     hinv[0] = div_r(hd[1], nn, rn);
     hinv[1] = div_r(-hd[0], nn, rn);
   }
