@@ -389,6 +389,63 @@ def test_replay_tick_parallel_equals_sequential(terminal, calls, persist):
         assert np.array_equal(a[f], b[f]), f"event {f} differs"
 
 
+@pytest.mark.parametrize("M", [17, 32])
+def test_replay_wide_scenes_parallel_vs_sequential_and_oracle(M):
+    """
+    Replay-only scenes of up to 32 slots (the tick-parallel kernel's limit: 200 KB of staged boxes and poses per
+    CTA at 32): crossing traffic with ragged knot counts, late arrivals and leavers, many overlapping boxes.
+    Tick-parallel == sequential kernel bit for bit (distances: summation order), and both agree with the oracle.
+    """
+    from scenario_gym_b200.packing import ScenarioSpec, SlotSpec
+
+    rng = np.random.default_rng(100 + M)
+    specs = []
+    for n in range(5):
+        slots = []
+        for s in range(M - (n % 3)):  # (ragged: the batch pads to M slots)
+            K = int(rng.integers(1, 9))
+            t = np.sort(rng.uniform(0.0 if s < 2 else -1.0, 9.0, K))
+            t[0] = 0.0 if s == 0 else t[0]
+            traj = np.zeros((K, 7))
+            traj[:, 0] = t
+            p0, v = rng.uniform(-12, 12, 2), rng.uniform(-4, 4, 2)
+            traj[:, 1:3] = p0 + np.outer(t, v) + rng.normal(0, 0.3, (K, 2))
+            traj[:, 3] = rng.normal(0, 0.05, K)
+            traj[:, 4] = np.arctan2(v[1], v[0]) + rng.normal(0, 0.2, K)
+            kind = abi.KIND_AGENT_REPLAY if s == 0 else abi.KIND_REPLAY
+            slots.append(SlotSpec(kind=kind, traj=traj, box=(float(rng.uniform(0.6, 2.2)), float(rng.uniform(0.7, 4.5)),
+                                                             float(rng.uniform(0, 1.4)), 0.0)))
+        specs.append(ScenarioSpec(slots=slots))
+    scene = pack_scenarios(specs)
+    assert scene.M == M
+    engines = []
+    for seq in (False, True):
+        p = _params()
+        p.timestep = 1.0 / 20.0
+        if seq:
+            p.features |= abi.FEAT_SEQUENTIAL
+        eng = make_gpu(scene, p)
+        eng.reset()
+        eng.rollout(-1)
+        engines.append(eng)
+    par, seq = engines
+    assert int(par.get("n_pair_ticks").sum()) > 100, "the case must have collisions"
+    for k in _RP_DISC:
+        assert np.array_equal(par.get(k), seq.get(k), equal_nan=True), f"{k} differs"
+    close(par.get("dist"), seq.get("dist"), "dist")
+    a, b = par.events(), seq.events()
+    assert a.tobytes() == b.tobytes()
+    p = _params()
+    p.timestep = 1.0 / 20.0
+    cpu = OracleEngine(scene, p)
+    cpu.reset()
+    cpu.rollout(-1)
+    for k in ("tick", "done", "present", "collided", "first_coll_tick", "first_coll_pair", "n_pair_ticks", "ego_hits"):
+        assert np.array_equal(par.get(k), cpu.get(k)), f"oracle: {k} differs"
+    close(par.get("pose"), cpu.get("pose"), "pose")
+    close(par.get("ego_avg_speed"), cpu.get("ego_avg_speed"), "ego_avg_speed")
+
+
 def test_future_collision_detector_golden():
     """sg_future_collisions (one launch per batch) == the reference's FutureCollisionDetector flags."""
     hits = check_future_collisions(lambda scene, p: make_gpu(scene, p), _params())
