@@ -446,6 +446,34 @@ def test_replay_wide_scenes_parallel_vs_sequential_and_oracle(M):
     close(par.get("ego_avg_speed"), cpu.get("ego_avg_speed"), "ego_avg_speed")
 
 
+def test_replay_padding_invariance():
+    """
+    The same scenarios packed into 9, 16 and 32 slots (more trailing empty slots): the tick-parallel kernel stops
+    its loops at the last non-empty slot, so every per-scenario result and every live slot's rows are unchanged.
+    """
+    specs = [s for _, s, _, _ in XOSC]
+    outs = []
+    for M in (None, 16, 32):
+        scene = pack_scenarios(specs, n_slots=M)
+        eng = make_gpu(scene, _params())
+        eng.reset()
+        eng.rollout(-1)
+        outs.append((scene, eng))
+    scene0, e0 = outs[0]
+    M0 = scene0.M
+    for scene, eng in outs[1:]:
+        for k in ("tick", "done", "first_coll_tick", "first_coll_pair", "n_pair_ticks", "ego_hits", "t", "prev_t",
+                  "ego_avg_speed", "ego_max_speed", "ego_dist"):
+            assert np.array_equal(eng.get(k), e0.get(k), equal_nan=True), (scene.M, k)
+        for k in ("present", "collided", "dist"):
+            a = eng.get(k).reshape(scene.N, scene.M)[:, :M0]
+            assert np.array_equal(a, e0.get(k).reshape(scene0.N, M0), equal_nan=True), (scene.M, k)
+        for k in ("pose", "vel"):
+            a = eng.get(k).reshape(6, scene.N, scene.M)[:, :, :M0]
+            assert np.array_equal(a, e0.get(k).reshape(6, scene0.N, M0), equal_nan=True), (scene.M, k)
+        assert eng.events().tobytes() == e0.events().tobytes()
+
+
 def test_future_collision_detector_golden():
     """sg_future_collisions (one launch per batch) == the reference's FutureCollisionDetector flags."""
     hits = check_future_collisions(lambda scene, p: make_gpu(scene, p), _params())
