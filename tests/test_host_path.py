@@ -177,3 +177,33 @@ def test_host_path_scenario_windows(windows, monkeypatch):
             assert np.array_equal(eng.get(k), ref.get(k), equal_nan=True), (tag, k)
         a, b = eng.events(), ref.events()
         assert a.tobytes() == b.tobytes(), (tag, "events")
+
+
+def test_host_path_default_window_policy_large_replay_batch(monkeypatch):
+    """
+    A replay-only batch above the windowing threshold (8 MiB, 64 scenarios) with NO override takes the
+    upload-bound policy (five even windows, the per-slot / per-scenario arrays of the whole batch sent once
+    with the first): results equal the one-piece upload's bit for bit.
+    """
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import all_xosc_specs
+    from scenario_gym_b200.engine import Engine
+    from scenario_gym_b200.hostpath import HostRollout
+    from scenario_gym_b200.packing import pack_scenarios, tile_scene
+
+    scene = tile_scene(pack_scenarios([s for _, s, _, _ in all_xosc_specs("xosc")]), 40)
+    assert scene.N >= 64 and scene.traj_rows.nbytes >= (8 << 20)
+    p = abi.default_params()
+    ref = Engine(scene, p, device=0)
+    monkeypatch.setenv("SG_HOST_WINDOWS", "1")
+    want = HostRollout(ref).run()
+    want = {k: v.copy() for k, v in want.items()}
+    monkeypatch.delenv("SG_HOST_WINDOWS")
+    eng = Engine(scene, p, device=0)
+    got = HostRollout(eng).run()
+    for k in FIELDS:
+        assert np.array_equal(got[k], want[k], equal_nan=True), k
+    for k in _STATE_FIELDS:
+        assert np.array_equal(eng.get(k), ref.get(k), equal_nan=True), k
+    assert eng.events().tobytes() == ref.events().tobytes()
