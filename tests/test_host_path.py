@@ -207,3 +207,29 @@ def test_host_path_default_window_policy_large_replay_batch(monkeypatch):
     for k in _STATE_FIELDS:
         assert np.array_equal(eng.get(k), ref.get(k), equal_nan=True), k
     assert eng.events().tobytes() == ref.events().tobytes()
+
+
+def test_host_path_default_window_policy_large_vehicle_batch(monkeypatch):
+    """
+    A compute-bound batch of 4096+ scenarios with NO override goes up in four windows (1/32, 1/8, 1/2, 1 of the
+    batch; in-kernel action stream addressed through the windows): equals the one-piece upload bit for bit.
+    """
+    from scenario_gym_b200.engine import Engine
+    from scenario_gym_b200.hostpath import HostRollout
+
+    cfg = synthetic.vehicles_config(seed=31, N=4100, M=64, T=10, half_extent=60.0, materialise=False)
+    scene = pack_synthetic(cfg)
+    assert scene.traj_rows.nbytes >= (8 << 20)
+    p = _params(cfg.dt, rss=True)
+    ref = Engine(scene, p, device=0)
+    monkeypatch.setenv("SG_HOST_WINDOWS", "1")
+    want = {k: v.copy() for k, v in HostRollout(ref, cfg.action_rng).run().items()}
+    monkeypatch.delenv("SG_HOST_WINDOWS")
+    eng = Engine(scene, p, device=0)
+    got = HostRollout(eng, cfg.action_rng).run()
+    for k in FIELDS:
+        assert np.array_equal(got[k], want[k], equal_nan=True), k
+    for k in ("tick", "done", "collided", "pose", "vel", "dist", "rss_state", "rss_last", "safe_dist"):
+        assert np.array_equal(eng.get(k), ref.get(k), equal_nan=True), k
+    assert eng.events().tobytes() == ref.events().tobytes()
+    assert int(got["n_pair_ticks"].sum()) > 0
