@@ -244,3 +244,24 @@ def test_road_network_surfaces_host():
     rn_of, poly_off, edge_off, edges, has_area = pack_road_networks([rn, None, rn])
     assert rn_of.tolist() == [0, -1, 0] and poly_off.tolist() == [0, 1, 4, 6] and has_area.tolist() == [1, 1, 1]
     assert edges.shape == (edge_off[-1], 4) and edge_off[1] == 4 and edge_off[2] - edge_off[1] == 8
+
+
+def test_union_times_equal_the_set_formulation():
+    """packing.build_union_times (numpy) == sorted(set(...)) over the trajectories as BatchReplayEntity holds them
+    (entity/batch.py:88-99): NaN times become 0, a single control point is held twice 0.1 s apart, duplicates merge."""
+    from scenario_gym_b200.packing import _batch_data, build_union_times
+
+    rng = np.random.default_rng(5)
+    for trial in range(100):
+        trajs = []
+        for _ in range(int(rng.integers(1, 7))):
+            K = int(rng.integers(1, 9))
+            d = rng.normal(size=(K, 7))
+            d[:, 0] = np.sort(rng.choice(np.arange(24) * 0.125, K, replace=False))
+            if rng.random() < 0.2:
+                d[int(rng.integers(0, K)), 0] = np.nan
+            trajs.append(d)
+        want = np.array(sorted(set(t for data in trajs for t in _batch_data(data)[:, 0])))
+        got = build_union_times(trajs)
+        assert got.dtype == np.float64 and np.array_equal(got, want), trial
+    assert build_union_times([]).shape == (0,)
