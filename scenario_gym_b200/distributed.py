@@ -60,6 +60,10 @@ def gather_records(local: torch.Tensor, n_total: int) -> torch.Tensor:
     world = dist.get_world_size()
     sizes = [shard_range(n_total, r, world) for r in range(world)]
     width = max(hi - lo for lo, hi in sizes)
+    if all(hi - lo == width for lo, hi in sizes):  # equal shards: the gathered buffer is the answer
+        out = torch.empty((world * width, local.shape[1]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return out
     padded = torch.zeros((width, local.shape[1]), dtype=local.dtype, device=local.device)
     padded[: local.shape[0]] = local
     out = torch.empty((world * width, local.shape[1]), dtype=local.dtype, device=local.device)

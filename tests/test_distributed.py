@@ -4,6 +4,7 @@ import socket
 import sys
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -46,15 +47,17 @@ def _worker(rank, world, port, n_total, q):
     dist.destroy_process_group()
 
 
-def test_shard_and_gather_gloo():
+@pytest.mark.parametrize("n_total", [11, 12])
+def test_shard_and_gather_gloo(n_total):
     sys.path.insert(0, REPO)
     from oracle.runner import OracleEngine, build_oracle
     from scenario_gym_b200 import abi, synthetic
     from scenario_gym_b200.distributed import RECORD_FIELDS, shard_range
 
     build_oracle()
-    n_total, world = 11, 2  # uneven shards: 6 + 5
-    assert [shard_range(n_total, r, world) for r in range(world)] == [(0, 6), (6, 11)]
+    world = 2  # n_total = 11: uneven shards, 6 + 5 (padded collective); 12: equal shards (gathered in place)
+    if n_total == 11:
+        assert [shard_range(n_total, r, world) for r in range(world)] == [(0, 6), (6, 11)]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
